@@ -1,0 +1,295 @@
+/* t4r_b200.h -- C ABI of libt4r_b200.so: the sm_100a hot path behind the
+ * TabularSequenceFeatures / TransformerBlock / NextItemPredictionTask surface
+ * of NVIDIA-Merlin/Transformers4Rec.
+ *
+ * The reference has no FFI of its own (it is pure Python dispatching to ATen);
+ * each entry point below replaces the torch call sequence cited next to it
+ * (paths relative to the upstream repository; "HF:" = Hugging Face transformers,
+ * where the encoder arithmetic lives).  INTEGRATION.md shows the ctypes binding
+ * a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *    parameter comment says "host"; `stream` is a cudaStream_t passed as void*.
+ *  - every call is asynchronous w.r.t. the host (no implicit synchronisation),
+ *    never allocates or frees caller memory, and takes scratch from the caller
+ *    (`*_workspace_bytes` queries).
+ *  - return value 0 = OK; non-zero = error, message via t4r_last_error()
+ *    (thread-local).  There is NO CPU fallback: a missing GPU or an unsupported
+ *    shape is an error, never a silent slow path.
+ *  - "planes" = the split-bf16 operand format consumed by the tcgen05 GEMMs:
+ *    for a logical fp32 matrix X[rows, K] two bf16 matrices hi = bf16(X),
+ *    lo = bf16(X - hi), each [rows, Kp] row-major with Kp = round_up(K, 64) and
+ *    zero padding, stored back to back ([2, rows, Kp]).  Three bf16 tensor-core
+ *    products (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) reproduce the
+ *    fp32 product to ~2^-16 relative error.
+ */
+#ifndef T4R_B200_H_
+#define T4R_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T4R_MAX_FEATURES 32
+#define T4R_OK 0
+#define T4R_ERR_INVALID 1
+#define T4R_ERR_CUDA 2
+#define T4R_ERR_UNSUPPORTED 3
+
+const char* t4r_last_error(void);
+int t4r_version(void);
+/* number of kernels this library has launched since load (all threads). */
+long long t4r_launch_count(void);
+
+static inline int t4r_round_up64(int k) { return (k + 63) / 64 * 64; }
+
+/* ------------------------------------------------------------------------- *
+ * K1  fused multi-table embedding gather + continuous + concat
+ *     replaces: EmbeddingFeatures.forward  transformers4rec/torch/features/embedding.py:226-249
+ *               (nn.Embedding per feature, features/sequence.py:75-81),
+ *               ContinuousFeatures.forward features/continuous.py:60-63,
+ *               ConcatFeatures.forward     tabular/aggregation.py:35-47
+ *     The caller lists features already in sorted-name order with their column
+ *     offsets in the concatenated row.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int n_cat;
+  int n_cont;
+  const float* table[T4R_MAX_FEATURES];     /* [rows, dim] fp32 row-major            */
+  const int64_t* ids[T4R_MAX_FEATURES];     /* [M] int64                              */
+  int64_t table_rows[T4R_MAX_FEATURES];
+  int dim[T4R_MAX_FEATURES];
+  int cat_col[T4R_MAX_FEATURES];            /* first output column of the feature     */
+  const float* cont[T4R_MAX_FEATURES];      /* [M] fp32                               */
+  int cont_col[T4R_MAX_FEATURES];
+} t4r_feature_list;
+
+/* out_f32: [M, C] or NULL; out_planes: bf16 [2, M, Cp] or NULL (Cp = round_up64(C)).
+ * err_flag: optional int32 device word set to 1 if any id is outside [0, rows). */
+int t4r_embed_concat_fwd(const t4r_feature_list* feats /*host*/, int64_t M, int C, float* out_f32,
+                         void* out_planes, int32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K3  mask / label generation (integer, bit-exact)
+ *     replaces: MaskedLanguageModeling._compute_masked_targets masking.py:376-470
+ *               CausalLanguageModeling._compute_masked_targets masking.py:274-300
+ *               MaskSequence.predict_all masking.py:182-213
+ *     Randomness enters only through `u` (uniforms in [0,1), [B, L+2]:
+ *     u[b, 0..L) bernoulli draws, u[b, L] "force one label", u[b, L+1] "un-label
+ *     one"); see DESIGN.md "Random draws".
+ *     row_code (uint8 [B, Lout]) tells the projection epilogue what
+ *     apply_mask_to_inputs (masking.py:473-498 / 302-337) does to that position:
+ *     0 keep, 1 replace by masked_item_embedding, 2 zero.
+ * ------------------------------------------------------------------------- */
+#define T4R_MLM_TRAIN 0
+#define T4R_MLM_EVAL_LAST 1
+#define T4R_MLM_EVAL_ALL 2
+#define T4R_MLM_INFERENCE 3 /* outputs have L+1 columns */
+int t4r_mask_mlm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode, float mlm_probability,
+                 const float* u, uint8_t* mask_schema, int64_t* masked_targets, uint8_t* row_code, void* stream);
+
+#define T4R_CLM_ALL 0       /* training (or eval with eval_on_last_item_seq_only=False) */
+#define T4R_CLM_LAST 1      /* last item only (eval default / train_on_last_item_seq_only) */
+#define T4R_CLM_INFERENCE 2
+int t4r_mask_clm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode, uint8_t* mask_schema,
+                 int64_t* masked_targets, uint8_t* row_code, void* stream);
+
+/* Row compaction of label positions (row-major order), replaces the
+ * masked_select pair at model/prediction_task.py:436-443,472-479.
+ * tgt_rows[i] = flat index (b*L+l) of the i-th non-pad label, tgt_labels[i] its id,
+ * *count_dev = T.  Entries i >= T are set to row 0 / label 0. */
+int t4r_compact_targets(const int64_t* masked_targets, int64_t n, int64_t padding_idx, int32_t* tgt_rows,
+                        int64_t* tgt_labels, int32_t* count_dev, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * operand packing / elementwise helpers
+ * ------------------------------------------------------------------------- */
+/* fp32 [rows, K] (row stride ld) -> planes bf16 [2, rows, Kp].  Optional row_code/
+ * mask_vec apply apply_mask_to_inputs (used when there is no projection GEMM to
+ * fuse it into); out_f32 (optional, [rows, K]) receives the masked fp32 rows. */
+int t4r_split_planes(const float* x, int64_t rows, int K, int ld, const uint8_t* row_code, const float* mask_vec,
+                     float* out_f32, void* out_planes, void* stream);
+/* gather rows then split: out[i] = x[idx[i]] for i < *count_dev (all `cap` rows when
+ * count_dev is NULL); rows >= count are zero.  out_f32 optional. */
+int t4r_gather_rows_split(const float* x, int K, int ld, const int32_t* idx, const int32_t* count_dev, int cap,
+                          float* out_f32, void* out_planes, void* stream);
+/* idx variant for int64 indices (embedding rows for sampled softmax) */
+int t4r_gather_rows_split_i64(const float* x, int K, int ld, const int64_t* idx, int cap, float* out_f32,
+                              void* out_planes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2  dense layer on tcgen05:  Y = epilogue(X * W^T)
+ *     replaces: DenseBlock (Linear + ReLU) block/mlp.py:123-144 built at
+ *               features/sequence.py:213-219, fused with
+ *               apply_mask_to_inputs masking.py:473-498 / 302-337; also the
+ *               head's task_block Linear model/prediction_task.py:390-397.
+ * ------------------------------------------------------------------------- */
+#define T4R_ACT_NONE 0
+#define T4R_ACT_RELU 1
+#define T4R_ACT_GELU 2
+typedef struct {
+  int64_t M;                 /* rows of X (capacity if m_dev != NULL)                    */
+  int N;                     /* output features, multiple of 64                          */
+  int K;                     /* input features (planes are padded to round_up64(K))      */
+  const void* x_planes;      /* bf16 [2, M, Kp]                                          */
+  const void* w_planes;      /* bf16 [2, N, Kp]  (W is [N, K] like nn.Linear.weight)     */
+  const int32_t* m_dev;      /* optional device row count; tiles beyond it are skipped   */
+  const float* bias;         /* [N] or NULL                                              */
+  int act;                   /* T4R_ACT_*                                                */
+  const uint8_t* row_code;   /* [M] or NULL                                              */
+  const float* mask_vec;     /* [N] masked_item_embedding (needed when row_code)         */
+  const float* residual;     /* [M, N] fp32 or NULL (added after act / mask)             */
+  const float* ln_gamma;     /* [N] or NULL: LayerNorm over the N outputs (N <= 256)     */
+  const float* ln_beta;
+  float ln_eps;
+  float* out_pre_ln;         /* optional fp32 [M, N]: value before LayerNorm             */
+  float* out_f32;            /* optional fp32 [M, N]: final value                        */
+  void* out_planes;          /* optional bf16 [2, M, round_up64(N)]: final value, split  */
+  int nprod;                 /* 3 = fp32-grade split product (default), 1 = plain bf16   */
+} t4r_linear_args;
+int t4r_linear_fwd(const t4r_linear_args* a /*host*/, void* stream);
+
+/* debug/reference: plain fp32 SIMT GEMM  C[M,N] = A[M,K] * B[N,K]^T (+bias). Used by
+ * the GPU tests to check the tensor-core path at sizes the CPU oracle cannot reach. */
+int t4r_debug_sgemm_nt(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4-K7  XLNet encoder (relative attention, post-LN), all layers
+ *     replaces: TransformerBlock.forward block/transformer.py:179-199 ->
+ *               HF XLNetModel.forward HF:models/xlnet/modeling_xlnet.py:979-1205
+ *               (XLNetRelativeAttention :245-277, rel_attn_core :95-140,
+ *                rel_shift_bnij :81-93, post_attention :142-152,
+ *                XLNetFeedForward :285-305, relative_positional_encoding :940-976)
+ *               built by XLNetConfig.build config/transformer.py:432-482.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const void* wqkv_planes;   /* bf16 [2, 3d, d]: rows = [q | k | v] output features       */
+  const float* wr;           /* fp32 [d, d] = rel_attn.r reshaped [d_in, H*dh]            */
+  const float* r_w_bias;     /* [H*dh]                                                    */
+  const float* r_r_bias;     /* [H*dh]                                                    */
+  const void* wo_planes;     /* bf16 [2, d, d]   = rel_attn.o reshaped [d_out, H*dh]      */
+  const float* ln1_gamma;    /* rel_attn.layer_norm                                       */
+  const float* ln1_beta;
+  const void* w1_planes;     /* bf16 [2, 4d, d]  = ff.layer_1.weight                      */
+  const float* b1;
+  const void* w2_planes;     /* bf16 [2, d, 4d]  = ff.layer_2.weight                      */
+  const float* b2;
+  const float* ln2_gamma;    /* ff.layer_norm                                             */
+  const float* ln2_beta;
+} t4r_xlnet_layer;
+size_t t4r_xlnet_encoder_workspace_bytes(int B, int L, int d, int n_head);
+/* x_f32 [B*L, d]; x_planes [2, B*L, d] or NULL (then split internally);
+ * out_f32 [B*L, d]; out_planes optional. d multiple of 64, d <= 256, L <= 64. */
+int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers /*host*/, int n_layer, int B, int L, int d, int n_head,
+                          float ln_eps, const float* x_f32, const void* x_planes, float* out_f32, void* out_planes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * GPT-2 encoder (pre-LN, learned positions, causal attention)
+ *     replaces: TransformerBlock.forward + GPT2Prepare block/transformer.py:55-73,179-199 ->
+ *               HF GPT2Model.forward HF:models/gpt2/modeling_gpt2.py:522-636
+ *               (GPT2Block :246-309, GPT2Attention :144-226, GPT2MLP :229-243)
+ *               built by GPT2Config.build config/transformer.py:217-260.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const float* ln1_gamma;
+  const float* ln1_beta;
+  const void* wqkv_planes;   /* bf16 [2, 3d, d] = c_attn.weight^T                         */
+  const float* bqkv;         /* [3d]                                                      */
+  const void* wo_planes;     /* bf16 [2, d, d]  = attn.c_proj.weight^T                    */
+  const float* bo;
+  const float* ln2_gamma;
+  const float* ln2_beta;
+  const void* w1_planes;     /* bf16 [2, 4d, d] = mlp.c_fc.weight^T                       */
+  const float* b1;
+  const void* w2_planes;     /* bf16 [2, d, 4d] = mlp.c_proj.weight^T                     */
+  const float* b2;
+} t4r_gpt2_layer;
+size_t t4r_gpt2_encoder_workspace_bytes(int B, int L, int d, int n_head);
+int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers /*host*/, int n_layer, int B, int L, int d, int n_head,
+                         float ln_eps, const float* wpe /*[n_positions, d]*/, const float* lnf_gamma,
+                         const float* lnf_beta, const float* x_f32, float* out_f32, void* out_planes,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K8  tied-weight item logits + softmax cross-entropy, never materialising [T, V]
+ *     replaces: _NextItemPredictionTask.forward model/prediction_task.py:648-671
+ *               + nn.CrossEntropyLoss (mean) :446/:347, and for evaluation
+ *               RecallAt ranking_metric.py:111-147 (rank of the label instead of
+ *               one-hot + topk, utils/torch_utils.py:226-238).
+ * K9  sampled softmax: _NextItemPredictionTask.sampled :673-696 with the
+ *               LogUniformSampler probabilities :766-796.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int T_cap;                 /* capacity of the target-row buffers                       */
+  const int32_t* t_dev;      /* device count of valid rows (NULL -> T_cap)                */
+  int De;                    /* embedding dim of the output table                         */
+  int64_t V;                 /* number of classes (rows of the table / of the shard)      */
+  const void* xt_planes;     /* bf16 [2, T_cap, Dep] hidden rows at label positions       */
+  const float* xt_f32;       /* fp32 [T_cap, De] same rows (exact target logit)           */
+  const int64_t* labels;     /* [T_cap] class ids                                         */
+  const void* w_planes;      /* bf16 [2, V, Dep] split table                              */
+  const float* w_f32;        /* fp32 [V, De] table (exact target logit); may be NULL when
+                                tgt_logit_in is given                                     */
+  float inv_temperature;     /* 1 / softmax_temperature                                   */
+  /* sampled softmax (all NULL/0 for the full softmax): the V "classes" are then the
+   * S sampled negatives (w_planes = gathered rows) and class 0 is the positive. */
+  const float* col_bias;     /* [V] added to each logit (= -log(q+1e-16))                 */
+  const int64_t* col_ids;    /* [V] item id of each column, for accidental-hit removal    */
+  float hit_value;           /* value accidental hits are set to (-655.04)                */
+  const float* pos_logit;    /* [T_cap] positive logit incl. its logQ term, or NULL       */
+  /* shard support: this call covers table rows [v_offset, v_offset + V) */
+  int64_t v_offset;
+  /* outputs */
+  float* row_lse;            /* [T_cap] log-sum-exp over this call's classes (+pos)       */
+  float* row_tgt;            /* [T_cap] logit of the label (0 if not in this shard)       */
+  float* row_loss;           /* [T_cap] lse - target logit (single-shard use)             */
+  float* loss;               /* [1] mean over valid rows, or NULL                         */
+  int32_t* row_rank;         /* [T_cap] #classes scoring above the label (ties: lower id
+                                first), or NULL                                           */
+  void* workspace;
+  size_t workspace_bytes;
+  int nprod;
+  /* optional cudaEvent_t pair recorded on `stream` immediately around the logits/LSE
+   * GEMM launch (bench.py's per-kernel roofline timing); NULL = off */
+  void* ev_gemm_start;
+  void* ev_gemm_stop;
+} t4r_head_args;
+size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De);
+int t4r_head_softmax_ce_fwd(const t4r_head_args* a /*host*/, void* stream);
+
+/* exact fp32 logit of each row's label plus an optional per-class bias:
+ * out[t] = (xt[t] . W[label] + class_bias[label]) * inv_temperature -- the positive
+ * score of the sampled softmax incl. its logQ term (model/prediction_task.py:681-687). */
+int t4r_label_logit(const float* xt_f32, const float* w_f32, const int64_t* labels, int T_cap, const int32_t* t_dev,
+                    int De, int64_t V, const float* class_bias, float inv_temperature, float* out, void* stream);
+
+/* materialise logits [T_cap, V] = xt * W^T * inv_temperature (the reference's
+ * "predictions" output, model/prediction_task.py:447-451) -- optional, on demand. */
+int t4r_head_logits(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V, int De,
+                    float inv_temperature, float* out /*[T_cap, ldo]*/, int64_t ldo, int nprod, void* stream);
+
+/* K10 Recall@k from label ranks: out[j] = mean_t(rank[t] < ks[j]).
+ * replaces RecallAt._metric + RankingMetric.update ranking_metric.py:52-63,111-147 */
+int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks /*host*/,
+                          int n_ks, float* out, void* stream);
+
+/* top-k (k <= 64) scores and ids of materialised logits, lower id first on ties
+ * (model/prediction_task.py:467-470 torch.topk on the inference path). */
+int t4r_topk(const float* logits, int64_t rows, int64_t V, int64_t ld, int k, float* out_scores, int64_t* out_ids,
+             void* stream);
+
+/* combine per-shard (lse, target-logit) rows gathered from `world` ranks:
+ * parts [world, T_cap, 2] -> loss (mean of lse_total - tgt_total). */
+int t4r_combine_shard_lse(const float* parts, int world, int T_cap, const int32_t* t_dev, float* row_loss,
+                          float* loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T4R_B200_H_ */

@@ -1,0 +1,345 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Bit-exact for integer/index work and pure copies,
+1e-3 absolute (the north-star tolerance) for fp32 results -- in practice the
+split-bf16 tensor-core products land near 1e-5."""
+import math
+
+import pytest
+import torch
+
+import t4r_oracle as O
+from _util import make_pair, mlm_draws, synth_batch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from transformers4rec_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 64, 133), (1000, 192, 256), (257, 128, 64),
+                                   (4096, 256, 256), (513, 1024, 256), (640, 256, 1024)])
+@pytest.mark.parametrize("nprod", [3, 1])
+def test_linear_matches_fp32(ops, M, N, K, nprod):
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.1
+    b = torch.randn(N, device="cuda")
+    xp, wp = ops.split_planes(x), ops.split_planes(w)
+    y, yp, _ = ops.linear(xp, wp, K, bias=b, nprod=nprod)
+    ref = ops.debug_sgemm_nt(x, w, b)
+    ref_cpu = (x.double().cpu() @ w.double().cpu().t() + b.double().cpu()).float()
+    assert (ref.cpu() - ref_cpu).abs().max() < 1e-3  # the SIMT reference itself
+    tol = 2e-4 if nprod == 3 else 0.15
+    err = (y.cpu() - ref_cpu).abs().max().item()
+    assert err < tol, f"max err {err}"
+    # planes output reproduces y: hi + lo
+    rec = yp[0].float() + yp[1].float()
+    assert (rec[:, :N] - y).abs().max().item() < 1e-3 * max(1.0, y.abs().max().item()) * 0.01 + 1e-4
+
+
+def test_linear_epilogues(ops):
+    torch.manual_seed(1)
+    M, N, K = 700, 256, 192
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.1
+    b = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    g, beta = torch.rand(N, device="cuda") + 0.5, torch.randn(N, device="cuda")
+    mv = torch.randn(N, device="cuda")
+    code = torch.randint(0, 3, (M,), device="cuda", dtype=torch.uint8)
+    xp, wp = ops.split_planes(x), ops.split_planes(w)
+    from transformers4rec_b200 import _lib
+    # relu + mask
+    y, _, _ = ops.linear(xp, wp, K, bias=b, act=_lib.ACT_RELU, row_code=code, mask_vec=mv)
+    ref = torch.relu(x @ w.t() + b)
+    ref = torch.where((code == 1).unsqueeze(1), mv.unsqueeze(0), ref)
+    ref = torch.where((code == 2).unsqueeze(1), torch.zeros_like(ref), ref)
+    assert (y - ref).abs().max().item() < 5e-4
+    # gelu
+    y, _, _ = ops.linear(xp, wp, K, bias=b, act=_lib.ACT_GELU)
+    assert (y - torch.nn.functional.gelu(x @ w.t() + b)).abs().max().item() < 5e-4
+    # residual + layernorm (+ pre-LN output)
+    for eps in (0.03, 1e-5):
+        y, yp, pre = ops.linear(xp, wp, K, bias=b, residual=res, ln=(g, beta), ln_eps=eps, want_pre_ln=True)
+        t = x @ w.t() + b + res
+        ref = torch.nn.functional.layer_norm(t, (N,), g, beta, eps)
+        assert (pre - t).abs().max().item() < 5e-4
+        assert (y - ref).abs().max().item() < 5e-4
+        assert ((yp[0].float() + yp[1].float()) - y).abs().max().item() < 1e-4
+
+
+def test_embed_concat_bit_exact(ops):
+    cards = {"item": 1001, "cat": 37, "brand": 500}
+    dims = {"item": 64, "cat": 13, "brand": 32}
+    batch = synth_batch(64, 20, cards, continuous=("price", "age"), seed=3)
+    torch.manual_seed(4)
+    tables = {n: torch.randn(c, dims[n]) for n, c in cards.items()}
+    ref = O.embed_concat(tables, {n: batch[n] for n in cards}, {n: batch[n] for n in ("price", "age")})
+    names = sorted(list(cards) + ["price", "age"])
+    col, cats, conts = 0, [], []
+    for n in names:
+        if n in cards:
+            cats.append((tables[n].cuda(), batch[n].cuda().reshape(-1), col)); col += dims[n]
+        else:
+            conts.append((batch[n].cuda().reshape(-1), col)); col += 1
+    of, planes, err = ops.embed_concat(cats, conts, 64 * 20, col, True, True)
+    assert torch.equal(of.cpu().view(64, 20, col), ref)
+    assert int(err.item()) == 0
+    rec = (planes[0].float() + planes[1].float()).cpu()
+    assert (rec[:, :col] - ref.view(-1, col)).abs().max().item() < 1e-4
+    assert (rec[:, col:] == 0).all()
+
+
+@pytest.mark.parametrize("mode", ["train", "eval_last", "eval_all", "inference"])
+def test_mask_mlm_bit_exact(ops, mode):
+    from transformers4rec_b200 import _lib
+    B, L = 257, 20
+    ids = synth_batch(B, L, {"item": 5000}, seed=5, min_len=1)["item"]
+    ids[3] = 0  # an empty session
+    u, draws = mlm_draws(B, L, seed=6)
+    kw = dict(train=(True, False), eval_last=(False, True), eval_all=(False, True), inference=(False, False))[mode]
+    rm, rl = O.mlm_compute_masked_targets(ids, kw[0], kw[1], eval_on_last_item_seq_only=(mode != "eval_all"), **draws)
+    code = dict(train=_lib.MLM_TRAIN, eval_last=_lib.MLM_EVAL_LAST, eval_all=_lib.MLM_EVAL_ALL,
+                inference=_lib.MLM_INFERENCE)[mode]
+    m, l, rc = ops.mask_mlm(ids.cuda(), code, 0, 0.15, u.cuda())
+    assert torch.equal(l.cpu(), rl) and torch.equal(m.cpu(), rm)
+    assert torch.equal(rc.cpu().bool(), rm)
+
+
+@pytest.mark.parametrize("mode", ["all", "last", "inference"])
+def test_mask_clm_bit_exact(ops, mode):
+    from transformers4rec_b200 import _lib
+    B, L = 130, 20
+    ids = synth_batch(B, L, {"item": 5000}, seed=7, min_len=1)["item"]
+    ids[5] = 0
+    if mode == "all":
+        rm, rl = O.clm_compute_masked_targets(ids, True, False)
+    elif mode == "last":
+        rm, rl = O.clm_compute_masked_targets(ids, False, True)
+    else:
+        rm, rl = O.clm_compute_masked_targets(ids, False, False)
+    code = dict(all=_lib.CLM_ALL, last=_lib.CLM_LAST, inference=_lib.CLM_INFERENCE)[mode]
+    m, l, rc = ops.mask_clm(ids.cuda(), code, 0)
+    assert torch.equal(l.cpu(), rl) and torch.equal(m.cpu(), rm)
+    # row codes reproduce apply_mask_to_inputs
+    x = torch.randn(B, L, 8)
+    emb = torch.randn(8)
+    ref = O.clm_apply_mask_to_inputs(x, rm, emb, training=(mode == "all"), testing=(mode == "last"))
+    rcc = rc.cpu()
+    got = torch.where((rcc == 1).unsqueeze(-1), emb, x)
+    got = torch.where((rcc == 2).unsqueeze(-1), torch.zeros_like(x), got)
+    assert torch.equal(got, ref)
+
+
+def test_compact_targets(ops):
+    torch.manual_seed(8)
+    labels = torch.randint(0, 50, (300, 20))
+    labels[labels < 40] = 0
+    rows, labs, count = ops.compact_targets(labels.cuda(), 0)
+    T = int(count.item())
+    flat = labels.flatten()
+    nz = flat.nonzero().squeeze(1)
+    assert T == nz.numel()
+    assert torch.equal(rows[:T].cpu().long(), nz) and torch.equal(labs[:T].cpu(), flat[nz])
+    assert (rows[T:] == 0).all() and (labs[T:] == 0).all()
+
+
+@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 8, 1, 9, 50), (64, 1, 1, 5, 21)])
+def test_xlnet_encoder_matches_hf(d, H, NL, B, L):
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(10)
+    hf = O.build_hf_xlnet(d, H, NL).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "layer_norm" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+            else:
+                p.normal_(0.0, 0.08)
+    blk = tr.TransformerBlock(hf).cuda()
+    x = torch.randn(B, L, d)
+    with torch.no_grad():
+        ref = O.hf_encoder_forward(hf, x)
+        ref2 = O.xlnet_forward_restated(x, hf.state_dict(), NL, H)
+        got = blk(x.cuda()).cpu()
+    assert (ref - ref2).abs().max().item() < 1e-4
+    err = (got - ref).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 2, 1, 7, 40)])
+def test_gpt2_encoder_matches_hf(d, H, NL, B, L):
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(11)
+    hf = O.build_hf_gpt2(d, H, NL, L).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "ln_" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+            else:
+                p.normal_(0.0, 0.08)
+    blk = tr.TransformerBlock(hf).cuda()
+    x = torch.randn(B, L, d)
+    with torch.no_grad():
+        ref = O.hf_encoder_forward(hf, x)
+        ref2 = O.gpt2_forward_restated(x, hf.state_dict(), NL, H)
+        got = blk(x.cuda()).cpu()
+    assert (ref - ref2).abs().max().item() < 1e-4
+    err = (got - ref).abs().max().item()
+    assert err < TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5)])
+def test_head_full_softmax(ops, T, V, De, tau):
+    torch.manual_seed(12)
+    xt = torch.randn(T, De)
+    W = torch.randn(V, De) * 0.1
+    y = torch.randint(1, V, (T,))
+    ref_loss, ref_logits = O.full_softmax_head(xt, y, W, tau)
+    cap = T + 37
+    xt_pad = torch.zeros(cap, De); xt_pad[:T] = xt
+    y_pad = torch.zeros(cap, dtype=torch.long); y_pad[:T] = y
+    count = torch.tensor([T], dtype=torch.int32, device="cuda")
+    xp = ops.split_planes(xt_pad.cuda())
+    wp = ops.split_planes(W.cuda())
+    res = ops.head_softmax_ce(xp, xt_pad.cuda(), y_pad.cuda(), wp, W.cuda(), t_dev=count, inv_temperature=1.0 / tau,
+                              want_rank=True)
+    assert abs(res["loss"].item() - ref_loss.item()) < 1e-4
+    ref_lse = torch.logsumexp(ref_logits, dim=1)
+    assert (res["row_lse"][:T].cpu() - ref_lse).abs().max().item() < 1e-4
+    # ranks -> Recall@k against the reference's one-hot/topk formulation
+    ks = [1, 5, 10, 20]
+    ref_rec = O.recall_at_mean(ks, ref_logits, y)
+    got_rec = ops.recall_from_ranks(res["row_rank"], ks, count).cpu()
+    assert (got_rec - ref_rec).abs().max().item() < 1e-6
+    # materialised logits
+    logits = ops.head_logits(xp, wp, De, t_dev=count, inv_temperature=1.0 / tau)[:T].cpu()
+    assert (logits - ref_logits).abs().max().item() < 2e-4
+
+
+def test_head_sampled_softmax(ops):
+    torch.manual_seed(13)
+    T, V, De, S = 300, 20001, 64, 500
+    xt = torch.randn(T, De)
+    W = torch.randn(V, De) * 0.1
+    y = torch.randint(1, V, (T,))
+    dist = O.log_uniform_distr(V, 1)
+    udist = O.unique_sampling_distr(dist, 2 * S)
+    raw = torch.multinomial(dist, 2 * S, replacement=True)
+    neg = O.negatives_from_draws(raw, S)
+    neg[:5] = y[:5].sort().values  # force accidental hits
+    neg = neg.unique()
+    ref_loss, ref_logits = O.sampled_softmax_head(xt, y, W, neg, udist, 1.0)
+    nlq = (-torch.log(udist + 1e-16)).cuda()
+    xp = ops.split_planes(xt.cuda())
+    negp, _ = ops.gather_rows_split(W.cuda(), neg.cuda(), None, neg.numel(), want_f32=False)
+    pos = ops.label_logit(xt.cuda(), W.cuda(), y.cuda(), class_bias=nlq)
+    assert (pos.cpu() - ref_logits[:, 0]).abs().max().item() < 1e-4
+    res = ops.head_softmax_ce(xp, xt.cuda(), y.cuda(), negp, None, col_bias=nlq[neg.cuda()].contiguous(),
+                              col_ids=neg.cuda(), hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos)
+    assert abs(res["loss"].item() - ref_loss.item()) < 1e-4
+
+
+def _run_pair(oracle, model, batch, training, testing, draws_u=None, draws=None):
+    dev = {k: v.cuda() for k, v in batch.items()}
+    inputs = model.heads[0].body[0]
+    if draws_u is not None:
+        inputs.masking.set_draws(draws_u.cuda())
+    with torch.no_grad():
+        ref = oracle(batch, training=training, testing=testing, draws=draws)
+        out = model(dev, training=training, testing=testing)
+    return ref, out
+
+
+@pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("xlnet", "clm"), ("gpt2", "clm")])
+def test_model_end_to_end_config1(arch, masking):
+    """BASELINE configs[0]: yoochoose-like schema, 10K items, L=20, d=64, 2 layers."""
+    cards = {"item_id/list": 10001, "category/list": 337}
+    dims = {"item_id/list": 64, "category/list": 64}
+    cont = tuple(f"cont{i}/list" for i in range(5))
+    B, L = 96, 20
+    oracle, model = make_pair(cards, dims, "item_id/list", cont, 64, 4, 2, L, arch=arch, masking=masking,
+                              weight_scale=0.08)
+    batch = synth_batch(B, L, cards, cont, seed=0)
+    u, draws = mlm_draws(B, L)
+    ref, out = _run_pair(oracle, model, batch, True, False, u if masking == "mlm" else None,
+                         draws if masking == "mlm" else None)
+    inputs = model.heads[0].body[0]
+    assert torch.equal(inputs.masking.masked_targets.cpu(), ref["masked_targets"])
+    assert torch.equal(inputs.masking.mask_schema.cpu(), ref["mask_schema"])
+    assert torch.equal(out["labels"].cpu(), ref["labels"])
+    assert abs(out["loss"].item() - ref["loss"].item()) < TOL
+    assert (out["predictions"].cpu() - ref["predictions"]).abs().max().item() < TOL
+    # evaluation: last item only, Recall@k
+    ref_e, out_e = _run_pair(oracle, model, batch, False, True)
+    assert abs(out_e["loss"].item() - ref_e["loss"].item()) < TOL
+    ks = [10, 20]
+    ref_rec = O.recall_at_mean(ks, ref_e["predictions"], ref_e["labels"])
+    got = model.calculate_metrics(out_e)
+    key = [k for k in got if k.endswith("recall_at")][0]
+    assert (got[key].cpu() - ref_rec).abs().max().item() < 1e-6
+
+
+def test_model_hidden_states_xlnet_base():
+    """BASELINE configs[1] shape at a reduced table/batch: d=256, 8 heads, 4 layers."""
+    cards = {"item_id/list": 50001}
+    dims = {"item_id/list": 256}
+    B, L = 48, 20
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 256, 8, 4, L, weight_scale=0.05)
+    batch = synth_batch(B, L, cards, seed=0)
+    u, draws = mlm_draws(B, L)
+    ref, out = _run_pair(oracle, model, batch, True, False, u, draws)
+    body = model.heads[0].body
+    with torch.no_grad():
+        body[0].masking.set_draws(u.cuda())
+        hid = body({k: v.cuda() for k, v in batch.items()}, training=True).cpu()
+    assert (hid - ref["hidden"]).abs().max().item() < TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) < TOL
+
+
+def test_model_sampled_softmax():
+    cards = {"item_id/list": 20001}
+    dims = {"item_id/list": 64}
+    B, L, S = 64, 20, 400
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 1, L, sampled=True, max_n_samples=S,
+                              weight_scale=0.08)
+    batch = synth_batch(B, L, cards, seed=1)
+    u, draws = mlm_draws(B, L)
+    torch.manual_seed(3)
+    raw = torch.multinomial(oracle.dist, 2 * S, replacement=True)
+    neg = O.negatives_from_draws(raw, S)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    task.set_negative_draws(raw.cuda())
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws, neg_samples=neg)
+        out = model({k: v.cuda() for k, v in batch.items()}, training=True)
+    assert abs(out["loss"].item() - ref["loss"].item()) < TOL
+    assert (out["predictions"].cpu() - ref["predictions"]).abs().max().item() < TOL
+
+
+def test_inference_topk():
+    cards = {"item_id/list": 3001}
+    dims = {"item_id/list": 64}
+    B, L = 32, 20
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 1, L, weight_scale=0.08)
+    batch = synth_batch(B, L - 1, cards, seed=2)  # room for the extra [MASK] position
+    batch = {k: torch.nn.functional.pad(v, (0, 1)) for k, v in batch.items()}
+    with torch.no_grad():
+        x, mask, labels = oracle.input_block(batch, False, False)
+        h = O.hf_encoder_forward(oracle.transformer, x)
+        ids = batch["item_id/list"]
+        last = (ids != 0).sum(1)
+        hs = h[torch.arange(B), last]
+        ref_scores = hs @ oracle.item_table().t()
+        scores = model({k: v.cuda() for k, v in batch.items()}, training=False, testing=False).cpu()
+    assert (scores - ref_scores).abs().max().item() < TOL
+    model.top_k = 10
+    with torch.no_grad():
+        s, i = model({k: v.cuda() for k, v in batch.items()}, training=False, testing=False)
+    rs, ri = torch.topk(ref_scores, 10)
+    assert (s.cpu() - rs).abs().max().item() < TOL
+    assert (i.cpu() == ri).float().mean().item() > 0.98

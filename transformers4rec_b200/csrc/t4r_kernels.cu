@@ -1,0 +1,993 @@
+// t4r_kernels.cu -- the HBM-/latency-bound kernels of the path: fused embedding
+// gather + concat (K1), mask/label generation (K3), label compaction, plane
+// packing, short-session attention (K5), LayerNorm prologue, head reductions.
+#include <math.h>
+
+#include "t4r_common.cuh"
+#include "t4r_internal.h"
+
+namespace t4r {
+
+// ============================================================================
+// K1: fused multi-table gather + continuous + concat
+//     one warp per (b, l) row; each lane moves 16-byte chunks when the feature
+//     geometry allows it (dim % 4 == 0, col % 4 == 0), else 4-byte elements.
+// ============================================================================
+struct FeatDev {
+  t4r_feature_list f;
+};
+
+__global__ void __launch_bounds__(256)
+embed_concat_kernel(const __grid_constant__ FeatDev fd, int64_t M, int C, int Cp, float* __restrict__ out_f32,
+                    __nv_bfloat16* __restrict__ planes, int32_t* err_flag) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
+  if (row >= M) return;
+  const int lane = lane_id();
+  const t4r_feature_list& f = fd.f;
+  __nv_bfloat16* hi = planes ? planes + row * Cp : nullptr;
+  __nv_bfloat16* lo = planes ? planes + (M + row) * Cp : nullptr;
+  float* of = out_f32 ? out_f32 + row * C : nullptr;
+  const bool out_vec_ok = (C % 4 == 0);
+
+  for (int t = 0; t < f.n_cat; ++t) {
+    int64_t id = f.ids[t][row];
+    const int dim = f.dim[t];
+    const int col = f.cat_col[t];
+    if (id < 0 || id >= f.table_rows[t]) {
+      if (err_flag && lane == 0) *err_flag = 1;
+      id = 0;
+    }
+    const float* src = f.table[t] + id * dim;
+    if ((dim & 3) == 0 && (col & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int q = lane; q < dim / 4; q += 32) {
+        const float4 v = __ldg(s4 + q);
+        const int c = col + 4 * q;
+        if (of) {
+          if (out_vec_ok) {
+            *reinterpret_cast<float4*>(of + c) = v;
+          } else {
+            of[c] = v.x; of[c + 1] = v.y; of[c + 2] = v.z; of[c + 3] = v.w;
+          }
+        }
+        if (hi) {
+          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+          split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+          *reinterpret_cast<uint2*>(hi + c) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+          *reinterpret_cast<uint2*>(lo + c) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+        }
+      }
+    } else {
+      for (int e = lane; e < dim; e += 32) {
+        const float v = __ldg(src + e);
+        if (of) of[col + e] = v;
+        if (hi) {
+          __nv_bfloat16 h, l;
+          split_bf16(v, h, l);
+          hi[col + e] = h;
+          lo[col + e] = l;
+        }
+      }
+    }
+  }
+  for (int t = lane; t < f.n_cont; t += 32) {
+    const float v = f.cont[t][row];
+    const int c = f.cont_col[t];
+    if (of) of[c] = v;
+    if (hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[c] = h;
+      lo[c] = l;
+    }
+  }
+  if (hi) {
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    for (int c = C + lane; c < Cp; c += 32) {
+      hi[c] = z;
+      lo[c] = z;
+    }
+  }
+}
+
+}  // namespace t4r
+
+extern "C" int t4r_embed_concat_fwd(const t4r_feature_list* feats, int64_t M, int C, float* out_f32,
+                                    void* out_planes, int32_t* err_flag, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(feats != nullptr && M > 0 && C > 0, "embed_concat: bad arguments");
+  T4R_REQUIRE(feats->n_cat >= 0 && feats->n_cat <= T4R_MAX_FEATURES && feats->n_cont >= 0 &&
+                  feats->n_cont <= T4R_MAX_FEATURES,
+              "embed_concat: at most %d categorical and %d continuous features", T4R_MAX_FEATURES, T4R_MAX_FEATURES);
+  T4R_REQUIRE(out_f32 || out_planes, "embed_concat: no output requested");
+  int width = feats->n_cont;
+  for (int t = 0; t < feats->n_cat; ++t) {
+    T4R_REQUIRE(feats->table[t] && feats->ids[t] && feats->dim[t] > 0, "embed_concat: feature %d incomplete", t);
+    T4R_REQUIRE(feats->cat_col[t] >= 0 && feats->cat_col[t] + feats->dim[t] <= C, "embed_concat: feature %d columns out of range", t);
+    width += feats->dim[t];
+  }
+  T4R_REQUIRE(width == C, "embed_concat: feature widths sum to %d but C = %d", width, C);
+  FeatDev fd;
+  fd.f = *feats;
+  const int Cp = t4r_round_up64(C);
+  const int warps = 8;
+  const int64_t blocks = (M + warps - 1) / warps;
+  embed_concat_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      fd, M, C, Cp, out_f32, static_cast<__nv_bfloat16*>(out_planes), err_flag);
+  T4R_LAUNCH_CHECK("embed_concat_kernel");
+  return 0;
+}
+
+namespace t4r {
+
+// ============================================================================
+// K3: masks / labels (integer).  One thread per session.
+// ============================================================================
+__device__ __forceinline__ int kth_pick(double u, int n) {
+  int k = static_cast<int>(floor(u * static_cast<double>(n)));
+  if (k > n - 1) k = n - 1;
+  if (k < 0) k = 0;
+  return k;
+}
+
+__global__ void mask_mlm_kernel(const int64_t* __restrict__ ids, int B, int L, int64_t pad, int mode, float prob,
+                                const float* __restrict__ u, uint8_t* __restrict__ mask, int64_t* __restrict__ labels,
+                                uint8_t* __restrict__ code) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t* row = ids + static_cast<int64_t>(b) * L;
+  int n_nonpad = 0;
+  for (int l = 0; l < L; ++l) n_nonpad += (row[l] != pad);
+
+  if (mode == T4R_MLM_INFERENCE) {
+    // masking.py:403-418: labels [B, L+1]; labels[b, n] = ids[b, n-1]
+    const int Lo = L + 1;
+    int64_t* lab = labels + static_cast<int64_t>(b) * Lo;
+    const int64_t src = row[(n_nonpad - 1 + L) % L];  // python index -1 wraps
+    for (int l = 0; l < Lo; ++l) {
+      const int64_t v = (l == n_nonpad) ? src : pad;
+      lab[l] = v;
+      const bool m = v != pad;
+      mask[static_cast<int64_t>(b) * Lo + l] = m;
+      code[static_cast<int64_t>(b) * Lo + l] = m ? 1 : 0;
+    }
+    return;
+  }
+  int64_t* lab = labels + static_cast<int64_t>(b) * L;
+  if (mode == T4R_MLM_TRAIN) {
+    const float* ur = u + static_cast<int64_t>(b) * (L + 2);
+    // masking.py:427-436 bernoulli & non_pad
+    for (int l = 0; l < L; ++l) lab[l] = (ur[l] < prob && row[l] != pad) ? row[l] : pad;
+    // masking.py:438-445 force one label among the non-padded positions
+    if (n_nonpad > 0) {
+      int k = kth_pick(static_cast<double>(ur[L]), n_nonpad);
+      for (int l = 0; l < L; ++l) {
+        if (row[l] != pad) {
+          if (k == 0) { lab[l] = row[l]; break; }
+          --k;
+        }
+      }
+    } else {
+      lab[0] = row[0];
+    }
+    int n_lab = 0;
+    for (int l = 0; l < L; ++l) n_lab += (lab[l] != pad);
+    // masking.py:447-459 a session made of labels only gets one of them back
+    if (n_lab == n_nonpad) {
+      if (n_lab > 0) {
+        int k = kth_pick(static_cast<double>(ur[L + 1]), n_lab);
+        for (int l = 0; l < L; ++l) {
+          if (lab[l] != pad) {
+            if (k == 0) { lab[l] = pad; break; }
+            --k;
+          }
+        }
+      } else {
+        lab[0] = pad;
+      }
+    }
+  } else if (mode == T4R_MLM_EVAL_LAST) {
+    // masking.py:461-465
+    for (int l = 0; l < L; ++l) lab[l] = pad;
+    const int last = (n_nonpad - 1 + L) % L;
+    lab[last] = row[last];
+  } else {
+    // predict_all masking.py:182-213
+    for (int l = 0; l < L; ++l) lab[l] = (l + 1 < L) ? row[l + 1] : 0;
+  }
+  for (int l = 0; l < L; ++l) {
+    const bool m = lab[l] != pad;
+    mask[static_cast<int64_t>(b) * L + l] = m;
+    code[static_cast<int64_t>(b) * L + l] = m ? 1 : 0;
+  }
+}
+
+__global__ void mask_clm_kernel(const int64_t* __restrict__ ids, int B, int L, int64_t pad, int mode,
+                                uint8_t* __restrict__ mask, int64_t* __restrict__ labels, uint8_t* __restrict__ code) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t* row = ids + static_cast<int64_t>(b) * L;
+  int64_t* lab = labels + static_cast<int64_t>(b) * L;
+  uint8_t* mk = mask + static_cast<int64_t>(b) * L;
+  uint8_t* cd = code + static_cast<int64_t>(b) * L;
+  if (mode == T4R_CLM_INFERENCE) {
+    // masking.py:277-279 and :309-317
+    for (int l = 0; l < L; ++l) {
+      const bool m = row[l] != pad;
+      lab[l] = row[l];
+      mk[l] = m;
+      cd[l] = m ? 0 : 1;
+    }
+    return;
+  }
+  // predict_all masking.py:182-213
+  int n_lab = 0;
+  for (int l = 0; l < L; ++l) {
+    const int64_t v = (l + 1 < L) ? row[l + 1] : 0;
+    lab[l] = v;
+    n_lab += (v != pad);
+  }
+  if (mode == T4R_CLM_LAST) {
+    // masking.py:284-298
+    const int last = (n_lab - 1 + L) % L;
+    const int64_t keep = lab[last];
+    for (int l = 0; l < L; ++l) lab[l] = 0;
+    lab[last] = keep;
+    for (int l = 0; l < L; ++l) mk[l] = row[l] != pad;
+  } else {
+    for (int l = 0; l < L; ++l) mk[l] = lab[l] != pad;
+  }
+  // masking.py:319-337: drop last position (zero row), then where(mask, x, masked_emb)
+  for (int l = 0; l < L; ++l) cd[l] = mk[l] ? ((l == L - 1) ? 2 : 0) : 1;
+}
+
+// label compaction: single block, contiguous chunks per thread, block-wide scan
+__global__ void __launch_bounds__(1024)
+compact_targets_kernel(const int64_t* __restrict__ labels, int64_t n, int64_t pad, int32_t* __restrict__ rows,
+                       int64_t* __restrict__ out_labels, int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int total_s;
+  const int tid = threadIdx.x;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t beg = tid * per;
+  const int64_t end = (beg + per < n) ? beg + per : n;
+  int cnt = 0;
+  for (int64_t i = beg; i < end; ++i) cnt += (labels[i] != pad);
+  // inclusive scan within warp
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane_id() >= o) incl += t;
+  }
+  if (lane_id() == 31) warp_tot[warp_id()] = incl;
+  __syncthreads();
+  if (warp_id() == 0) {
+    int w = warp_tot[lane_id()];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane_id() >= o) wi += t;
+    }
+    warp_tot[lane_id()] = wi - w;  // exclusive
+    if (lane_id() == 31) total_s = wi;
+  }
+  __syncthreads();
+  int pos = warp_tot[warp_id()] + incl - cnt;
+  for (int64_t i = beg; i < end; ++i) {
+    const int64_t v = labels[i];
+    if (v != pad) {
+      rows[pos] = static_cast<int32_t>(i);
+      out_labels[pos] = v;
+      ++pos;
+    }
+  }
+  const int total = total_s;
+  if (tid == 0) *count = total;
+  for (int64_t i = total + tid; i < n; i += blockDim.x) {
+    rows[i] = 0;
+    out_labels[i] = 0;
+  }
+}
+
+}  // namespace t4r
+
+extern "C" int t4r_mask_mlm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode,
+                            float mlm_probability, const float* u, uint8_t* mask_schema, int64_t* masked_targets,
+                            uint8_t* row_code, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(item_ids && mask_schema && masked_targets && row_code && B > 0 && L > 0, "mask_mlm: bad arguments");
+  T4R_REQUIRE(mode >= T4R_MLM_TRAIN && mode <= T4R_MLM_INFERENCE, "mask_mlm: unknown mode %d", mode);
+  T4R_REQUIRE(mode != T4R_MLM_TRAIN || u != nullptr, "mask_mlm: training mode needs the uniform draws u[B, L+2]");
+  mask_mlm_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      item_ids, B, L, padding_idx, mode, mlm_probability, u, mask_schema, masked_targets, row_code);
+  T4R_LAUNCH_CHECK("mask_mlm_kernel");
+  return 0;
+}
+
+extern "C" int t4r_mask_clm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode,
+                            uint8_t* mask_schema, int64_t* masked_targets, uint8_t* row_code, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(item_ids && mask_schema && masked_targets && row_code && B > 0 && L > 0, "mask_clm: bad arguments");
+  T4R_REQUIRE(mode >= T4R_CLM_ALL && mode <= T4R_CLM_INFERENCE, "mask_clm: unknown mode %d", mode);
+  mask_clm_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      item_ids, B, L, padding_idx, mode, mask_schema, masked_targets, row_code);
+  T4R_LAUNCH_CHECK("mask_clm_kernel");
+  return 0;
+}
+
+extern "C" int t4r_compact_targets(const int64_t* masked_targets, int64_t n, int64_t padding_idx, int32_t* tgt_rows,
+                                   int64_t* tgt_labels, int32_t* count_dev, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(masked_targets && tgt_rows && tgt_labels && count_dev && n > 0 && n < (1ll << 31),
+              "compact_targets: bad arguments");
+  compact_targets_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(masked_targets, n, padding_idx, tgt_rows,
+                                                                            tgt_labels, count_dev);
+  T4R_LAUNCH_CHECK("compact_targets_kernel");
+  return 0;
+}
+
+namespace t4r {
+
+// ============================================================================
+// plane packing
+// ============================================================================
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ x, int64_t rows, int K, int64_t ld, int Kp,
+                    const uint8_t* __restrict__ row_code, const float* __restrict__ mask_vec,
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ planes) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
+  if (row >= rows) return;
+  const int lane = lane_id();
+  const int code = row_code ? row_code[row] : 0;
+  const float* src = x + row * ld;
+  __nv_bfloat16* hi = planes ? planes + row * Kp : nullptr;
+  __nv_bfloat16* lo = planes ? planes + (rows + row) * Kp : nullptr;
+  for (int c = lane; c < Kp; c += 32) {
+    float v = 0.f;
+    if (c < K) {
+      v = (code == 1) ? __ldg(mask_vec + c) : ((code == 2) ? 0.f : src[c]);
+      if (out_f32) out_f32[row * K + c] = v;
+    }
+    if (hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[c] = h;
+      lo[c] = l;
+    }
+  }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_rows_split_kernel(const float* __restrict__ x, int K, int64_t ld, int Kp, const IdxT* __restrict__ idx,
+                         const int32_t* __restrict__ count_dev, int cap, float* __restrict__ out_f32,
+                         __nv_bfloat16* __restrict__ planes) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
+  if (row >= cap) return;
+  const int lane = lane_id();
+  const int count = count_dev ? *count_dev : cap;
+  const bool valid = row < count;
+  const float* src = valid ? x + static_cast<int64_t>(idx[row]) * ld : nullptr;
+  __nv_bfloat16* hi = planes ? planes + row * Kp : nullptr;
+  __nv_bfloat16* lo = planes ? planes + (static_cast<int64_t>(cap) + row) * Kp : nullptr;
+  for (int c = lane; c < Kp; c += 32) {
+    float v = 0.f;
+    if (c < K) {
+      if (valid) v = __ldg(src + c);
+      if (out_f32) out_f32[row * K + c] = v;
+    }
+    if (hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[c] = h;
+      lo[c] = l;
+    }
+  }
+}
+
+int launch_split_planes(const float* x, int64_t rows, int K, int64_t ld, const uint8_t* row_code,
+                        const float* mask_vec, float* out_f32, __nv_bfloat16* planes, cudaStream_t s) {
+  T4R_REQUIRE(x && rows > 0 && K > 0 && ld >= K && (out_f32 || planes), "split_planes: bad arguments");
+  T4R_REQUIRE(row_code == nullptr || mask_vec != nullptr, "split_planes: row_code needs mask_vec");
+  const int Kp = t4r_round_up64(K);
+  const int64_t blocks = (rows + 7) / 8;
+  split_planes_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, rows, K, ld, Kp, row_code, mask_vec, out_f32,
+                                                                   planes);
+  T4R_LAUNCH_CHECK("split_planes_kernel");
+  return 0;
+}
+
+}  // namespace t4r
+
+extern "C" int t4r_split_planes(const float* x, int64_t rows, int K, int ld, const uint8_t* row_code,
+                                const float* mask_vec, float* out_f32, void* out_planes, void* stream) {
+  return t4r::launch_split_planes(x, rows, K, ld, row_code, mask_vec, out_f32,
+                                  static_cast<__nv_bfloat16*>(out_planes), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int t4r_gather_rows_split(const float* x, int K, int ld, const int32_t* idx, const int32_t* count_dev,
+                                     int cap, float* out_f32, void* out_planes, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(x && idx && K > 0 && ld >= K && cap > 0 && (out_f32 || out_planes), "gather_rows_split: bad arguments");
+  gather_rows_split_kernel<int32_t><<<(cap + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, K, ld, t4r_round_up64(K), idx, count_dev, cap, out_f32, static_cast<__nv_bfloat16*>(out_planes));
+  T4R_LAUNCH_CHECK("gather_rows_split_kernel");
+  return 0;
+}
+
+extern "C" int t4r_gather_rows_split_i64(const float* x, int K, int ld, const int64_t* idx, int cap, float* out_f32,
+                                         void* out_planes, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(x && idx && K > 0 && ld >= K && cap > 0 && (out_f32 || out_planes), "gather_rows_split_i64: bad arguments");
+  gather_rows_split_kernel<int64_t><<<(cap + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, K, ld, t4r_round_up64(K), idx, nullptr, cap, out_f32, static_cast<__nv_bfloat16*>(out_planes));
+  T4R_LAUNCH_CHECK("gather_rows_split_kernel");
+  return 0;
+}
+
+namespace t4r {
+
+// ============================================================================
+// XLNet relative positional projection  R[m, :] = pos(m) @ Wr,  m in [0, 2L)
+//   pos(m) = [sin(p w) || cos(p w)], p = L - m, w_k = 10000^(-2k/d)
+//   HF:models/xlnet/modeling_xlnet.py:930-976 (bi_data=False, clamp_len=-1)
+// ============================================================================
+__global__ void rel_pos_proj_kernel(const float* __restrict__ wr, int L, int d, float* __restrict__ r_out) {
+  extern __shared__ float pos_s[];  // [d]
+  const int m = blockIdx.x;
+  const float p = static_cast<float>(L - m);
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const int kk = (k < d / 2) ? k : k - d / 2;
+    const float inv_freq = 1.0f / powf(10000.0f, static_cast<float>(2 * kk) / static_cast<float>(d));
+    const float a = p * inv_freq;
+    pos_s[k] = (k < d / 2) ? sinf(a) : cosf(a);
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < d; n += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(pos_s[k], __ldg(wr + static_cast<int64_t>(k) * d + n), acc);
+    r_out[static_cast<int64_t>(m) * d + n] = acc;
+  }
+}
+
+int launch_rel_pos_proj(const float* wr, int L, int d, float* r_out, cudaStream_t s) {
+  const int threads = d < 256 ? d : 256;
+  rel_pos_proj_kernel<<<2 * L, threads, d * sizeof(float), s>>>(wr, L, d, r_out);
+  T4R_LAUNCH_CHECK("rel_pos_proj_kernel");
+  return 0;
+}
+
+// ============================================================================
+// K5: attention over one short session per warp.
+//   REL = true : XLNet  s[i,j] = ((q_i + r_w_bias) . k_j + (q_i + r_r_bias) . R[j + L - i]) / sqrt(dh)
+//                (HF:xlnet:95-140; rel_shift_bnij :81-93 as the index identity), no masks
+//   REL = false: GPT-2  s[i,j] = q_i . k_j / sqrt(dh) for j <= i (HF:gpt2:54-72,144-226)
+//   out = softmax_j(s) @ V, written as split-bf16 planes (A operand of the O-projection).
+// Layout: qkv fp32 [B*L, 3d] (q | k | v, head h at columns h*dh..), r [2L, d].
+// A block owns one head (R staged once in shared memory) and its warps loop over
+// sessions.  Lane j owns key j (and j+32): scores live in registers, softmax is a
+// warp reduction, P@V runs with lane = output column.
+// ============================================================================
+template <int DH, int LT, bool REL>
+__global__ void __launch_bounds__(128)
+attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const float* __restrict__ rw,
+            const float* __restrict__ rr, int B, int L, int d, int sessions_per_block,
+            __nv_bfloat16* __restrict__ out_planes, int64_t plane_stride) {
+  constexpr int DP = DH + 4;    // padded row stride (floats): conflict-free float4 row reads
+  constexpr int LMAX = 32 * LT;
+  extern __shared__ __align__(16) float sm[];
+  const int h = blockIdx.y;
+  const int warp = warp_id(), lane = lane_id();
+  const int nwarps = blockDim.x >> 5;
+  const int Lp = ((L + 3) / 4) * 4 + 4;  // pT row stride
+  float* Rs = sm;                                                  // [2L][DP]   (REL only)
+  float* wbase = sm + (REL ? 2 * L * DP : 0);
+  const int per_warp = 2 * L * DH + L * DP + L * DH + L * Lp + LMAX;
+  float* qw = wbase + warp * per_warp;  // [L][DH]  q + r_w_bias (or q)
+  float* qr = qw + L * DH;              // [L][DH]  q + r_r_bias
+  float* ks = qr + L * DH;              // [L][DP]
+  float* vs = ks + L * DP;              // [L][DH]
+  float* pT = vs + L * DH;              // [L (j)][Lp (i)]
+  float* inv_sum = pT + L * Lp;         // [LMAX]
+
+  if (REL) {
+    for (int idx = threadIdx.x; idx < 2 * L * DH; idx += blockDim.x) {
+      const int m = idx / DH, c = idx % DH;
+      Rs[m * DP + c] = __ldg(r + static_cast<int64_t>(m) * d + h * DH + c);
+    }
+  }
+  __syncthreads();
+  const float scale = rsqrtf(static_cast<float>(DH));
+  const int b_begin = blockIdx.x * sessions_per_block;
+  const int b_end = min(B, b_begin + sessions_per_block);
+
+  for (int b = b_begin + warp; b < b_end; b += nwarps) {
+    const float* base = qkv + static_cast<int64_t>(b) * L * 3 * d + h * DH;
+    // stage q (+biases), k, v for this (b, h)
+    for (int idx = lane; idx < L * DH; idx += 32) {
+      const int i = idx / DH, c = idx % DH;
+      const float* rowp = base + static_cast<int64_t>(i) * 3 * d;
+      const float q = rowp[c];
+      if (REL) {
+        qw[i * DH + c] = q + __ldg(rw + h * DH + c);
+        qr[i * DH + c] = q + __ldg(rr + h * DH + c);
+      } else {
+        qw[i * DH + c] = q;
+      }
+      ks[i * DP + c] = rowp[d + c];
+      vs[i * DH + c] = rowp[2 * d + c];
+    }
+    __syncwarp();
+
+    // ---- scores: lane owns key j = lane + 32 t; raw scores go to pT[j][i]
+#pragma unroll
+    for (int t = 0; t < LT; ++t) {
+      const int j = lane + 32 * t;
+      const bool jok = j < L;
+      float4 kreg[DH / 4];
+#pragma unroll
+      for (int c4 = 0; c4 < DH / 4; ++c4)
+        kreg[c4] = jok ? *reinterpret_cast<const float4*>(ks + j * DP + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int i = 0; i < L; ++i) {
+        float acc = 0.f;
+        const float4* qwi = reinterpret_cast<const float4*>(qw + i * DH);
+#pragma unroll
+        for (int c4 = 0; c4 < DH / 4; ++c4) {
+          const float4 a = qwi[c4];
+          acc = fmaf(a.x, kreg[c4].x, acc); acc = fmaf(a.y, kreg[c4].y, acc);
+          acc = fmaf(a.z, kreg[c4].z, acc); acc = fmaf(a.w, kreg[c4].w, acc);
+        }
+        if (REL) {
+          const float4* qri = reinterpret_cast<const float4*>(qr + i * DH);
+          const int m = jok ? (j + L - i) : 0;
+          const float4* rm = reinterpret_cast<const float4*>(Rs + m * DP);
+#pragma unroll
+          for (int c4 = 0; c4 < DH / 4; ++c4) {
+            const float4 a = qri[c4];
+            const float4 bb = rm[c4];
+            acc = fmaf(a.x, bb.x, acc); acc = fmaf(a.y, bb.y, acc);
+            acc = fmaf(a.z, bb.z, acc); acc = fmaf(a.w, bb.w, acc);
+          }
+        }
+        acc *= scale;
+        if (!REL && j > i) acc = -INFINITY;
+        if (jok) pT[j * Lp + i] = acc;
+      }
+    }
+    __syncwarp();
+    // ---- softmax over keys (across lanes) for each query i; exp() overwrites the score
+#pragma unroll 1
+    for (int i = 0; i < L; ++i) {
+      float v[LT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < LT; ++t) {
+        const int j = lane + 32 * t;
+        v[t] = (j < L) ? pT[j * Lp + i] : -INFINITY;
+        mx = fmaxf(mx, v[t]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < LT; ++t) {
+        const int j = lane + 32 * t;
+        const float e = (v[t] == -INFINITY) ? 0.f : expf(v[t] - mx);
+        sum += e;
+        if (j < L) pT[j * Lp + i] = e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) inv_sum[i] = 1.f / sum;
+    }
+    __syncwarp();
+    // ---- out[i, c] = sum_j p[i, j] v[j, c]; lane owns column(s) c
+#pragma unroll
+    for (int ct = 0; ct < (DH + 31) / 32; ++ct) {
+      const int c = lane + 32 * ct;
+      const bool cok = c < DH;
+      float acc[LMAX];
+#pragma unroll
+      for (int i = 0; i < LMAX; ++i) acc[i] = 0.f;
+      for (int j = 0; j < L; ++j) {
+        const float vj = cok ? vs[j * DH + c] : 0.f;
+        const float4* pj = reinterpret_cast<const float4*>(pT + j * Lp);
+#pragma unroll
+        for (int i4 = 0; i4 < LMAX / 4; ++i4) {
+          if (4 * i4 < L) {
+            const float4 pp = pj[i4];
+            acc[4 * i4 + 0] = fmaf(pp.x, vj, acc[4 * i4 + 0]);
+            acc[4 * i4 + 1] = fmaf(pp.y, vj, acc[4 * i4 + 1]);
+            acc[4 * i4 + 2] = fmaf(pp.z, vj, acc[4 * i4 + 2]);
+            acc[4 * i4 + 3] = fmaf(pp.w, vj, acc[4 * i4 + 3]);
+          }
+        }
+      }
+      if (cok) {
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) {
+          if (i < L) {
+            const float o = acc[i] * inv_sum[i];
+            __nv_bfloat16 hi, lo;
+            split_bf16(o, hi, lo);
+            const int64_t off = (static_cast<int64_t>(b) * L + i) * d + h * DH + c;
+            out_planes[off] = hi;
+            out_planes[off + plane_stride] = lo;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int DH, int LT, bool REL>
+static int launch_attn_inst(const float* qkv, const float* r, const float* rw, const float* rr, int B, int L, int d,
+                            int H, __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s) {
+  constexpr int DP = DH + 4;
+  const int Lp = ((L + 3) / 4) * 4 + 4;
+  const int per_warp = 2 * L * DH + L * DP + L * DH + L * Lp + 32 * LT;
+  const int r_floats = REL ? 2 * L * DP : 0;
+  int warps = 4;
+  while (warps > 1 && (r_floats + warps * per_warp) * 4 > 200 * 1024) warps >>= 1;
+  const size_t smem = static_cast<size_t>(r_floats + warps * per_warp) * 4;
+  T4R_REQUIRE(smem <= 220 * 1024, "attention: L=%d dh=%d needs %zu bytes of shared memory", L, DH, smem);
+  auto kern = attn_kernel<DH, LT, REL>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  // sessions per block: enough blocks to fill the machine, enough sessions to amortise R staging
+  int spb = 8 * warps;
+  while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 4) spb >>= 1;
+  dim3 grid((B + spb - 1) / spb, H);
+  kern<<<grid, warps * 32, smem, s>>>(qkv, r, rw, rr, B, L, d, spb, out_planes, plane_stride);
+  T4R_LAUNCH_CHECK("attn_kernel");
+  return 0;
+}
+
+template <bool REL>
+static int launch_attn_any(const float* qkv, const float* r, const float* rw, const float* rr, int B, int L, int d,
+                           int H, __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s) {
+  T4R_REQUIRE(d % H == 0, "attention: d_model %d not divisible by n_head %d", d, H);
+  const int dh = d / H;
+  T4R_REQUIRE(L >= 1 && L <= 64, "attention: sequence length %d not supported (1..64)", L);
+  const int lt = (L <= 32) ? 1 : 2;
+#define T4R_ATTN_CASE(DHV)                                                                               \
+  if (dh == DHV) {                                                                                       \
+    if (lt == 1) return launch_attn_inst<DHV, 1, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s); \
+    return launch_attn_inst<DHV, 2, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);       \
+  }
+  T4R_ATTN_CASE(16)
+  T4R_ATTN_CASE(32)
+  T4R_ATTN_CASE(64)
+#undef T4R_ATTN_CASE
+  set_error("attention: head dim %d not supported (16, 32, 64)", dh);
+  return T4R_ERR_UNSUPPORTED;
+}
+
+int launch_xlnet_attn(const float* qkv, const float* r, const float* rw, const float* rr, int B, int L, int d, int H,
+                      __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s) {
+  return launch_attn_any<true>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);
+}
+int launch_causal_attn(const float* qkv, int B, int L, int d, int H, __nv_bfloat16* out_planes, int64_t plane_stride,
+                       cudaStream_t s) {
+  return launch_attn_any<false>(qkv, nullptr, nullptr, nullptr, B, L, d, H, out_planes, plane_stride, s);
+}
+
+// ============================================================================
+// GPT-2 prologue: h = x + wpe[l]; planes = LN(h)   (HF:gpt2:579-585 and ln_1 of block 0)
+// one warp per row
+// ============================================================================
+__global__ void __launch_bounds__(256)
+addpos_ln_kernel(const float* __restrict__ x, const float* __restrict__ wpe, int64_t rows, int L, int d,
+                 const float* __restrict__ g, const float* __restrict__ bta, float eps, float* __restrict__ h_out,
+                 __nv_bfloat16* __restrict__ planes, int64_t plane_stride) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
+  if (row >= rows) return;
+  const int lane = lane_id();
+  const int l = static_cast<int>(row % L);
+  const float* xr = x + row * d;
+  const float* pr = wpe ? wpe + static_cast<int64_t>(l) * d : nullptr;
+  float sum = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = xr[c] + (pr ? __ldg(pr + c) : 0.f);
+    if (h_out) h_out[row * d + c] = v;
+    sum += v;
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(d);
+  float sq = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = xr[c] + (pr ? __ldg(pr + c) : 0.f) - mean;
+    sq = fmaf(v, v, sq);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(d) + eps);
+  for (int c = lane; c < d; c += 32) {
+    const float v = xr[c] + (pr ? __ldg(pr + c) : 0.f);
+    const float o = (v - mean) * rstd * __ldg(g + c) + __ldg(bta + c);
+    __nv_bfloat16 hi, lo;
+    split_bf16(o, hi, lo);
+    planes[row * d + c] = hi;
+    planes[row * d + c + plane_stride] = lo;
+  }
+}
+
+int launch_addpos_ln(const float* x, const float* wpe, int B, int L, int d, const float* g, const float* b, float eps,
+                     float* h_out, __nv_bfloat16* planes, int64_t plane_stride, cudaStream_t s) {
+  const int64_t rows = static_cast<int64_t>(B) * L;
+  addpos_ln_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(x, wpe, rows, L, d, g, b, eps, h_out, planes,
+                                                                         plane_stride);
+  T4R_LAUNCH_CHECK("addpos_ln_kernel");
+  return 0;
+}
+
+// ============================================================================
+// head reductions
+// ============================================================================
+// exact fp32 logit of the label: out[t] = (xt[t] . W[label - v_offset] + class_bias[label]) * inv_tau
+__global__ void __launch_bounds__(256)
+target_logit_kernel(const float* __restrict__ xt, const float* __restrict__ w, const int64_t* __restrict__ labels,
+                    int T_cap, const int32_t* __restrict__ t_dev, int De, int64_t v_offset, int64_t V,
+                    const float* __restrict__ class_bias, float inv_tau, float* __restrict__ out) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
+  if (row >= T_cap) return;
+  const int T = t_dev ? *t_dev : T_cap;
+  const int lane = lane_id();
+  float acc = 0.f;
+  bool mine = false;
+  if (row < T) {
+    const int64_t lab = labels[row] - v_offset;
+    mine = (lab >= 0 && lab < V);
+    if (mine) {
+      const float* a = xt + row * De;
+      const float* b = w + lab * De;
+      for (int c = lane; c < De; c += 32) acc = fmaf(a[c], __ldg(b + c), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (mine && class_bias) acc += class_bias[labels[row]];
+    out[row] = mine ? acc * inv_tau : 0.f;
+  }
+}
+
+int launch_target_logit(const float* xt, const float* w, const int64_t* labels, int T_cap, const int32_t* t_dev,
+                        int De, int64_t v_offset, int64_t V, const float* class_bias, float inv_tau, float* out,
+                        cudaStream_t s) {
+  target_logit_kernel<<<(T_cap + 7) / 8, 256, 0, s>>>(xt, w, labels, T_cap, t_dev, De, v_offset, V, class_bias, inv_tau,
+                                                      out);
+  T4R_LAUNCH_CHECK("target_logit_kernel");
+  return 0;
+}
+
+// stage 1: thread = row, block column = chunk of column tiles -> (m, s) per (chunk, row)
+__global__ void __launch_bounds__(128)
+head_reduce1_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s, int n_tiles, int part_ld,
+                    int T_cap, const int32_t* __restrict__ t_dev, int tiles_per_chunk, float* __restrict__ red_m,
+                    float* __restrict__ red_s) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  if (row >= T) return;
+  const int chunk = blockIdx.y;
+  const int t0 = chunk * tiles_per_chunk;
+  const int t1 = min(n_tiles, t0 + tiles_per_chunk);
+  float m = -INFINITY, s = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const float pm = part_m[static_cast<int64_t>(t) * part_ld + row];
+    const float ps = part_s[static_cast<int64_t>(t) * part_ld + row];
+    const float mn = fmaxf(m, pm);
+    if (mn > -INFINITY) {
+      s = s * exp2f(m - mn) + ps * exp2f(pm - mn);
+      m = mn;
+    }
+  }
+  red_m[static_cast<int64_t>(chunk) * part_ld + row] = m;
+  red_s[static_cast<int64_t>(chunk) * part_ld + row] = s;
+}
+
+// stage 2: combine chunks (+ optional positive logit), natural-log lse, per-row loss
+__global__ void __launch_bounds__(128)
+head_reduce2_kernel(const float* __restrict__ red_m, const float* __restrict__ red_s, int n_chunks, int part_ld,
+                    int T_cap, const int32_t* __restrict__ t_dev, const float* __restrict__ pos_logit,
+                    const float* __restrict__ row_tgt, float* __restrict__ row_lse, float* __restrict__ row_loss) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= T_cap) return;
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  if (row >= T) {
+    if (row_lse) row_lse[row] = 0.f;
+    if (row_loss) row_loss[row] = 0.f;
+    return;
+  }
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kLn2 = 0.6931471805599453f;
+  float m = -INFINITY, s = 0.f;
+  if (pos_logit) {
+    m = pos_logit[row] * kLog2e;
+    s = 1.f;
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const float pm = red_m[static_cast<int64_t>(c) * part_ld + row];
+    const float ps = red_s[static_cast<int64_t>(c) * part_ld + row];
+    const float mn = fmaxf(m, pm);
+    if (mn > -INFINITY) {
+      s = s * exp2f(m - mn) + ps * exp2f(pm - mn);
+      m = mn;
+    }
+  }
+  const float lse = (m + log2f(s)) * kLn2;
+  if (row_lse) row_lse[row] = lse;
+  if (row_loss) row_loss[row] = lse - (pos_logit ? pos_logit[row] : row_tgt[row]);
+}
+
+// mean of the first T entries (single block; T is small)
+__global__ void __launch_bounds__(1024)
+mean_rows_kernel(const float* __restrict__ v, int T_cap, const int32_t* __restrict__ t_dev, float* __restrict__ out) {
+  __shared__ float ws[32];
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) acc += static_cast<double>(v[i]);
+  float a = static_cast<float>(acc);
+  a = warp_sum(a);
+  if (lane_id() == 0) ws[warp_id()] = a;
+  __syncthreads();
+  if (warp_id() == 0) {
+    float t = (lane_id() < (blockDim.x >> 5)) ? ws[lane_id()] : 0.f;
+    t = warp_sum(t);
+    if (lane_id() == 0) out[0] = (T > 0) ? t / static_cast<float>(T) : 0.f;
+  }
+}
+
+int launch_head_reduce(const float* part_m, const float* part_s, int n_tiles, int part_ld, int T_cap,
+                       const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in, float* row_lse,
+                       float* row_loss, float* loss, float* scratch, cudaStream_t s) {
+  // scratch: [2, n_chunks, part_ld]
+  int n_chunks = n_tiles < 64 ? n_tiles : 64;
+  const int tpc = (n_tiles + n_chunks - 1) / n_chunks;
+  n_chunks = (n_tiles + tpc - 1) / tpc;
+  float* red_m = scratch;
+  float* red_s = scratch + static_cast<int64_t>(n_chunks) * part_ld;
+  dim3 g1((T_cap + 127) / 128, n_chunks);
+  head_reduce1_kernel<<<g1, 128, 0, s>>>(part_m, part_s, n_tiles, part_ld, T_cap, t_dev, tpc, red_m, red_s);
+  T4R_LAUNCH_CHECK("head_reduce1_kernel");
+  head_reduce2_kernel<<<(T_cap + 127) / 128, 128, 0, s>>>(red_m, red_s, n_chunks, part_ld, T_cap, t_dev, pos_logit,
+                                                           row_tgt_in, row_lse, row_loss);
+  T4R_LAUNCH_CHECK("head_reduce2_kernel");
+  if (loss) {
+    mean_rows_kernel<<<1, 1024, 0, s>>>(row_loss, T_cap, t_dev, loss);
+    T4R_LAUNCH_CHECK("mean_rows_kernel");
+  }
+  return 0;
+}
+
+// Recall@k from ranks
+__global__ void __launch_bounds__(1024)
+recall_from_ranks_kernel(const int32_t* __restrict__ rank, const int32_t* __restrict__ t_dev, int T_cap, int k0, int k1,
+                         int k2, int k3, int n_ks, float* __restrict__ out) {
+  __shared__ int hits[4];
+  if (threadIdx.x < 4) hits[threadIdx.x] = 0;
+  __syncthreads();
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  int h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const int r = rank[i];
+    h0 += r < k0; h1 += r < k1; h2 += r < k2; h3 += r < k3;
+  }
+  atomicAdd(&hits[0], h0); atomicAdd(&hits[1], h1); atomicAdd(&hits[2], h2); atomicAdd(&hits[3], h3);
+  __syncthreads();
+  if (threadIdx.x < n_ks) out[threadIdx.x] = (T > 0) ? static_cast<float>(hits[threadIdx.x]) / static_cast<float>(T) : 0.f;
+}
+
+// top-k per row of materialised logits (k <= 64), one block per row, iterative
+// arg-max with "lower id first" tie-break.  Used on the inference path only.
+__global__ void __launch_bounds__(256)
+topk_kernel(const float* __restrict__ logits, int64_t V, int64_t ld, int k, float* __restrict__ out_scores,
+            int64_t* __restrict__ out_ids) {
+  __shared__ float wv[8];
+  __shared__ long long wi[8];
+  __shared__ float prev_v;
+  __shared__ long long prev_i;
+  const float* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
+  if (threadIdx.x == 0) { prev_v = INFINITY; prev_i = -1; }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    const float pv = prev_v;
+    const long long pi = prev_i;
+    float best = -INFINITY;
+    long long besti = 0x7fffffffffffffffll;
+    for (int64_t c = threadIdx.x; c < V; c += blockDim.x) {
+      const float v = row[c];
+      // strictly after (pv, pi) in the order (value desc, id asc)
+      const bool after = (v < pv) || (v == pv && c > pi);
+      if (after && (v > best || (v == best && c < besti))) { best = v; besti = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (lane_id() == 0) { wv[warp_id()] = best; wi[warp_id()] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float bv = wv[0];
+      long long bi = wi[0];
+      for (int w = 1; w < (blockDim.x >> 5); ++w)
+        if (wv[w] > bv || (wv[w] == bv && wi[w] < bi)) { bv = wv[w]; bi = wi[w]; }
+      prev_v = bv;
+      prev_i = bi;
+      out_scores[static_cast<int64_t>(blockIdx.x) * k + r] = bv;
+      out_ids[static_cast<int64_t>(blockIdx.x) * k + r] = bi;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+combine_shard_lse_kernel(const float* __restrict__ parts, int world, int T_cap, const int32_t* __restrict__ t_dev,
+                         float* __restrict__ row_loss) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= T_cap) return;
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  if (row >= T) { row_loss[row] = 0.f; return; }
+  float m = -INFINITY, s = 0.f, tgt = 0.f;
+  for (int w = 0; w < world; ++w) {
+    const float lse = parts[(static_cast<int64_t>(w) * T_cap + row) * 2 + 0];
+    tgt += parts[(static_cast<int64_t>(w) * T_cap + row) * 2 + 1];
+    const float mn = fmaxf(m, lse);
+    if (mn > -INFINITY) {
+      s = s * expf(m - mn) + expf(lse - mn);
+      m = mn;
+    }
+  }
+  row_loss[row] = (m + logf(s)) - tgt;
+}
+
+}  // namespace t4r
+
+extern "C" int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks,
+                                     int n_ks, float* out, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(row_rank && ks && out && T_cap > 0 && n_ks >= 1 && n_ks <= 4, "recall_from_ranks: 1..4 cut-offs");
+  int k[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n_ks; ++i) k[i] = ks[i];
+  recall_from_ranks_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(row_rank, t_dev, T_cap, k[0], k[1], k[2],
+                                                                              k[3], n_ks, out);
+  T4R_LAUNCH_CHECK("recall_from_ranks_kernel");
+  return 0;
+}
+
+extern "C" int t4r_topk(const float* logits, int64_t rows, int64_t V, int64_t ld, int k, float* out_scores,
+                        int64_t* out_ids, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(logits && out_scores && out_ids && rows > 0 && V > 0 && k >= 1 && k <= 64 && k <= V,
+              "topk: bad arguments (k <= 64)");
+  topk_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, V, ld, k, out_scores,
+                                                                                         out_ids);
+  T4R_LAUNCH_CHECK("topk_kernel");
+  return 0;
+}
+
+extern "C" int t4r_combine_shard_lse(const float* parts, int world, int T_cap, const int32_t* t_dev, float* row_loss,
+                                     float* loss, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(parts && row_loss && world >= 1 && T_cap > 0, "combine_shard_lse: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  combine_shard_lse_kernel<<<(T_cap + 255) / 256, 256, 0, s>>>(parts, world, T_cap, t_dev, row_loss);
+  T4R_LAUNCH_CHECK("combine_shard_lse_kernel");
+  if (loss) {
+    mean_rows_kernel<<<1, 1024, 0, s>>>(row_loss, T_cap, t_dev, loss);
+    T4R_LAUNCH_CHECK("mean_rows_kernel");
+  }
+  return 0;
+}
+
+extern "C" int t4r_label_logit(const float* xt_f32, const float* w_f32, const int64_t* labels, int T_cap,
+                               const int32_t* t_dev, int De, int64_t V, const float* class_bias, float inv_temperature,
+                               float* out, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(xt_f32 && w_f32 && labels && out && T_cap > 0 && De > 0 && V > 0, "label_logit: bad arguments");
+  return launch_target_logit(xt_f32, w_f32, labels, T_cap, t_dev, De, 0, V, class_bias,
+                             inv_temperature != 0.f ? inv_temperature : 1.f, out, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,374 @@
+"""Functional wrappers: torch CUDA tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory, streams); every computation below runs
+in ``libt4r_b200.so``.  All functions require CUDA tensors and raise otherwise --
+there is no eager/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def round_up64(k: int) -> int:
+    return (k + 63) // 64 * 64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.T4RError("t4r_b200 ops need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Workspace:
+    """Grow-only byte buffer per (device, tag) so steady-state steps never allocate."""
+
+    def __init__(self):
+        self._bufs: Dict[Tuple[str, str], torch.Tensor] = {}
+
+    def get(self, tag: str, nbytes: int, device) -> torch.Tensor:
+        key = (str(device), tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def tensor(self, tag: str, shape: Sequence[int], dtype, device) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        buf = self.get(tag, max(nbytes, 256), device)
+        return buf[:nbytes].view(dtype).view(*shape)
+
+
+WS = Workspace()
+# bench.py sets this to a (start, stop) pair of torch.cuda.Event(enable_timing=True) to time
+# the logits/LSE GEMM of every head call on its own stream
+HEAD_EVENTS = None
+
+
+# --------------------------------------------------------------------------- #
+# operand packing
+# --------------------------------------------------------------------------- #
+def split_planes(x: torch.Tensor, row_code: Optional[torch.Tensor] = None, mask_vec: Optional[torch.Tensor] = None,
+                 want_f32: bool = False, out: Optional[torch.Tensor] = None):
+    """fp32 [rows, K] -> bf16 planes [2, rows, Kp] (optionally applying row codes)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    rows, K = x.shape
+    Kp = round_up64(K)
+    planes = out if out is not None else torch.empty((2, rows, Kp), dtype=torch.bfloat16, device=x.device)
+    of = torch.empty((rows, K), dtype=torch.float32, device=x.device) if want_f32 else None
+    check(_lib.load().t4r_split_planes(ptr(x), rows, K, K, ptr(row_code), ptr(mask_vec), ptr(of), ptr(planes),
+                                       _stream()), "t4r_split_planes")
+    return (planes, of) if want_f32 else planes
+
+
+class PlaneCache:
+    """Split-bf16 copies of weights, refreshed when the parameter changes
+    (``data_ptr`` / ``_version``).  ``transform`` maps the parameter to its [N, K]
+    (nn.Linear-style) layout before packing."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, key: str, param: torch.Tensor, transform=None) -> torch.Tensor:
+        sig = (param.data_ptr(), param._version, tuple(param.shape), str(param.device))
+        ent = self._cache.get(key)
+        if ent is not None and ent[0] == sig:
+            return ent[1]
+        with torch.no_grad():
+            w = param.detach()
+            if transform is not None:
+                w = transform(w)
+            planes = split_planes(w)
+        self._cache[key] = (sig, planes)
+        return planes
+
+    def clear(self):
+        self._cache.clear()
+
+
+# --------------------------------------------------------------------------- #
+# K1
+# --------------------------------------------------------------------------- #
+def embed_concat(cats: List[Tuple[torch.Tensor, torch.Tensor, int]], conts: List[Tuple[torch.Tensor, int]], M: int,
+                 C_width: int, want_f32: bool, want_planes: bool):
+    """cats: (table [rows, dim], ids [M] int64, first column); conts: (values [M] f32, column)."""
+    lib = _lib.load()
+    fl = _lib.FeatureList()
+    fl.n_cat, fl.n_cont = len(cats), len(conts)
+    if len(cats) > _lib.T4R_MAX_FEATURES or len(conts) > _lib.T4R_MAX_FEATURES:
+        raise _lib.T4RError(f"at most {_lib.T4R_MAX_FEATURES} categorical / continuous features per call")
+    keep = []
+    dev = None
+    for i, (table, ids, col) in enumerate(cats):
+        _need_cuda(table, ids)
+        table = _f32c(table)
+        ids = ids.reshape(-1)
+        if ids.dtype != torch.int64:
+            ids = ids.long()
+        ids = ids.contiguous()
+        keep += [table, ids]
+        fl.table[i], fl.ids[i] = table.data_ptr(), ids.data_ptr()
+        fl.table_rows[i], fl.dim[i], fl.cat_col[i] = table.shape[0], table.shape[1], col
+        dev = table.device
+    for i, (vals, col) in enumerate(conts):
+        _need_cuda(vals)
+        vals = _f32c(vals.reshape(-1))
+        keep.append(vals)
+        fl.cont[i], fl.cont_col[i] = vals.data_ptr(), col
+        dev = dev or vals.device
+    out_f32 = torch.empty((M, C_width), dtype=torch.float32, device=dev) if want_f32 else None
+    planes = torch.empty((2, M, round_up64(C_width)), dtype=torch.bfloat16, device=dev) if want_planes else None
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.t4r_embed_concat_fwd(C.byref(fl), M, C_width, ptr(out_f32), ptr(planes), ptr(err), _stream()),
+          "t4r_embed_concat_fwd")
+    return out_f32, planes, err
+
+
+# --------------------------------------------------------------------------- #
+# K3
+# --------------------------------------------------------------------------- #
+def mask_mlm(item_ids: torch.Tensor, mode: int, padding_idx: int = 0, mlm_probability: float = 0.15,
+             u: Optional[torch.Tensor] = None):
+    _need_cuda(item_ids, u)
+    ids = item_ids.long().contiguous()
+    B, L = ids.shape
+    Lo = L + 1 if mode == _lib.MLM_INFERENCE else L
+    if mode == _lib.MLM_TRAIN:
+        if u is None:
+            u = torch.rand((B, L + 2), dtype=torch.float32, device=ids.device)
+        u = _f32c(u)
+        assert tuple(u.shape) == (B, L + 2), "u must be [B, L+2]"
+    mask = torch.empty((B, Lo), dtype=torch.bool, device=ids.device)
+    labels = torch.empty((B, Lo), dtype=torch.int64, device=ids.device)
+    code = torch.empty((B, Lo), dtype=torch.uint8, device=ids.device)
+    check(_lib.load().t4r_mask_mlm(ptr(ids), B, L, padding_idx, mode, mlm_probability, ptr(u), ptr(mask), ptr(labels),
+                                   ptr(code), _stream()), "t4r_mask_mlm")
+    return mask, labels, code
+
+
+def mask_clm(item_ids: torch.Tensor, mode: int, padding_idx: int = 0):
+    _need_cuda(item_ids)
+    ids = item_ids.long().contiguous()
+    B, L = ids.shape
+    mask = torch.empty((B, L), dtype=torch.bool, device=ids.device)
+    labels = torch.empty((B, L), dtype=torch.int64, device=ids.device)
+    code = torch.empty((B, L), dtype=torch.uint8, device=ids.device)
+    check(_lib.load().t4r_mask_clm(ptr(ids), B, L, padding_idx, mode, ptr(mask), ptr(labels), ptr(code), _stream()),
+          "t4r_mask_clm")
+    return mask, labels, code
+
+
+def compact_targets(masked_targets: torch.Tensor, padding_idx: int = 0):
+    _need_cuda(masked_targets)
+    mt = masked_targets.long().contiguous().reshape(-1)
+    n = mt.numel()
+    rows = torch.empty(n, dtype=torch.int32, device=mt.device)
+    labels = torch.empty(n, dtype=torch.int64, device=mt.device)
+    count = torch.empty(1, dtype=torch.int32, device=mt.device)
+    check(_lib.load().t4r_compact_targets(ptr(mt), n, padding_idx, ptr(rows), ptr(labels), ptr(count), _stream()),
+          "t4r_compact_targets")
+    return rows, labels, count
+
+
+def gather_rows_split(x2d: torch.Tensor, idx: torch.Tensor, count: Optional[torch.Tensor], cap: int,
+                      want_f32: bool = True):
+    _need_cuda(x2d, idx, count)
+    x2d = _f32c(x2d)
+    K = x2d.shape[1]
+    planes = torch.empty((2, cap, round_up64(K)), dtype=torch.bfloat16, device=x2d.device)
+    of = torch.empty((cap, K), dtype=torch.float32, device=x2d.device) if want_f32 else None
+    lib = _lib.load()
+    if idx.dtype == torch.int32:
+        check(lib.t4r_gather_rows_split(ptr(x2d), K, K, ptr(idx), ptr(count), cap, ptr(of), ptr(planes), _stream()),
+              "t4r_gather_rows_split")
+    else:
+        assert count is None
+        idx = idx.long().contiguous()
+        check(lib.t4r_gather_rows_split_i64(ptr(x2d), K, K, ptr(idx), cap, ptr(of), ptr(planes), _stream()),
+              "t4r_gather_rows_split_i64")
+    return planes, of
+
+
+# --------------------------------------------------------------------------- #
+# K2
+# --------------------------------------------------------------------------- #
+def linear(x_planes: torch.Tensor, w_planes: torch.Tensor, K: int, *, bias=None, act: int = _lib.ACT_NONE,
+           row_code=None, mask_vec=None, residual=None, ln=None, ln_eps: float = 0.0, want_f32=True,
+           want_planes=True, want_pre_ln=False, m_dev=None, nprod: int = 3):
+    """Y = epilogue(X W^T): x_planes [2, M, Kp], w_planes [2, N, Kp]."""
+    _need_cuda(x_planes, w_planes)
+    M, N = x_planes.shape[1], w_planes.shape[1]
+    dev = x_planes.device
+    a = _lib.LinearArgs()
+    a.M, a.N, a.K = M, N, K
+    a.x_planes, a.w_planes = ptr(x_planes), ptr(w_planes)
+    a.m_dev = ptr(m_dev)
+    keep = []
+    if bias is not None:
+        bias = _f32c(bias.detach()); keep.append(bias); a.bias = ptr(bias)
+    a.act = act
+    if row_code is not None:
+        rc = row_code.reshape(-1).contiguous(); mv = _f32c(mask_vec.detach()); keep += [rc, mv]
+        a.row_code, a.mask_vec = ptr(rc), ptr(mv)
+    if residual is not None:
+        residual = _f32c(residual); keep.append(residual); a.residual = ptr(residual)
+    if ln is not None:
+        g, b = _f32c(ln[0].detach()), _f32c(ln[1].detach()); keep += [g, b]
+        a.ln_gamma, a.ln_beta, a.ln_eps = ptr(g), ptr(b), ln_eps
+    out_f32 = torch.empty((M, N), dtype=torch.float32, device=dev) if want_f32 else None
+    out_pre = torch.empty((M, N), dtype=torch.float32, device=dev) if want_pre_ln else None
+    out_planes = torch.empty((2, M, round_up64(N)), dtype=torch.bfloat16, device=dev) if want_planes else None
+    a.out_f32, a.out_pre_ln, a.out_planes = ptr(out_f32), ptr(out_pre), ptr(out_planes)
+    a.nprod = nprod
+    check(_lib.load().t4r_linear_fwd(C.byref(a), _stream()), "t4r_linear_fwd")
+    return out_f32, out_planes, out_pre
+
+
+def debug_sgemm_nt(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(A, B, bias)
+    A, B = _f32c(A), _f32c(B)
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(_lib.load().t4r_debug_sgemm_nt(ptr(A), ptr(B), ptr(bias), ptr(Cm), M, N, K, _stream()), "t4r_debug_sgemm_nt")
+    return Cm
+
+
+# --------------------------------------------------------------------------- #
+# encoders
+# --------------------------------------------------------------------------- #
+def xlnet_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: int, eps: float, x_f32: torch.Tensor,
+                  x_planes: Optional[torch.Tensor], want_planes: bool = False):
+    _need_cuda(x_f32, x_planes)
+    lib = _lib.load()
+    x_f32 = _f32c(x_f32)
+    dev = x_f32.device
+    nbytes = lib.t4r_xlnet_encoder_workspace_bytes(B, L, d, n_head)
+    ws = WS.get("xlnet", nbytes, dev)
+    out = torch.empty((B * L, d), dtype=torch.float32, device=dev)
+    out_planes = torch.empty((2, B * L, d), dtype=torch.bfloat16, device=dev) if want_planes else None
+    check(lib.t4r_xlnet_encoder_fwd(layers_struct, n_layer, B, L, d, n_head, eps, ptr(x_f32), ptr(x_planes), ptr(out),
+                                    ptr(out_planes), ptr(ws), ws.numel(), _stream()), "t4r_xlnet_encoder_fwd")
+    return out, out_planes
+
+
+def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: int, eps: float, wpe, lnf_g, lnf_b,
+                 x_f32: torch.Tensor, want_planes: bool = False):
+    _need_cuda(x_f32)
+    lib = _lib.load()
+    x_f32 = _f32c(x_f32)
+    dev = x_f32.device
+    nbytes = lib.t4r_gpt2_encoder_workspace_bytes(B, L, d, n_head)
+    ws = WS.get("gpt2", nbytes, dev)
+    out = torch.empty((B * L, d), dtype=torch.float32, device=dev)
+    out_planes = torch.empty((2, B * L, d), dtype=torch.bfloat16, device=dev) if want_planes else None
+    check(lib.t4r_gpt2_encoder_fwd(layers_struct, n_layer, B, L, d, n_head, eps, ptr(wpe), ptr(lnf_g), ptr(lnf_b),
+                                   ptr(x_f32), ptr(out), ptr(out_planes), ptr(ws), ws.numel(), _stream()),
+          "t4r_gpt2_encoder_fwd")
+    return out, out_planes
+
+
+# --------------------------------------------------------------------------- #
+# head
+# --------------------------------------------------------------------------- #
+def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
+                    col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
+                    nprod=3, events=None):
+    """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank)."""
+    _need_cuda(xt_planes, w_planes)
+    lib = _lib.load()
+    T_cap = xt_planes.shape[1]
+    V = w_planes.shape[1]
+    dev = xt_planes.device
+    De = xt_f32.shape[1] if xt_f32 is not None else w_f32.shape[1]
+    a = _lib.HeadArgs()
+    a.T_cap, a.t_dev, a.De, a.V = T_cap, ptr(t_dev), De, V
+    a.xt_planes, a.xt_f32, a.labels = ptr(xt_planes), ptr(xt_f32), ptr(labels)
+    a.w_planes, a.w_f32 = ptr(w_planes), ptr(w_f32)
+    a.inv_temperature = inv_temperature
+    a.col_bias, a.col_ids, a.hit_value, a.pos_logit = ptr(col_bias), ptr(col_ids), hit_value, ptr(pos_logit)
+    a.v_offset = v_offset
+    row_lse = torch.empty(T_cap, dtype=torch.float32, device=dev)
+    row_tgt = torch.empty(T_cap, dtype=torch.float32, device=dev)
+    row_loss = torch.empty(T_cap, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev) if want_loss else None
+    row_rank = torch.empty(T_cap, dtype=torch.int32, device=dev) if want_rank else None
+    a.row_lse, a.row_tgt, a.row_loss, a.loss, a.row_rank = ptr(row_lse), ptr(row_tgt), ptr(row_loss), ptr(loss), ptr(row_rank)
+    nbytes = lib.t4r_head_workspace_bytes(T_cap, V, De)
+    ws = WS.get("head", nbytes, dev)
+    a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
+    a.nprod = nprod
+    ev = events if events is not None else HEAD_EVENTS
+    if ev is not None:
+        a.ev_gemm_start, a.ev_gemm_stop = ev[0].cuda_event, ev[1].cuda_event
+    check(lib.t4r_head_softmax_ce_fwd(C.byref(a), _stream()), "t4r_head_softmax_ce_fwd")
+    return {"row_lse": row_lse, "row_tgt": row_tgt, "row_loss": row_loss, "loss": loss, "row_rank": row_rank}
+
+
+def label_logit(xt_f32, w_f32, labels, *, t_dev=None, class_bias=None, inv_temperature=1.0):
+    _need_cuda(xt_f32, w_f32, labels)
+    T_cap, De = xt_f32.shape
+    out = torch.empty(T_cap, dtype=torch.float32, device=xt_f32.device)
+    check(_lib.load().t4r_label_logit(ptr(xt_f32), ptr(w_f32), ptr(labels), T_cap, ptr(t_dev), De, w_f32.shape[0],
+                                      ptr(class_bias), inv_temperature, ptr(out), _stream()), "t4r_label_logit")
+    return out
+
+
+def head_logits(xt_planes, w_planes, De: int, *, t_dev=None, inv_temperature=1.0, nprod=3) -> torch.Tensor:
+    _need_cuda(xt_planes, w_planes)
+    T_cap, V = xt_planes.shape[1], w_planes.shape[1]
+    out = torch.zeros((T_cap, V), dtype=torch.float32, device=xt_planes.device)
+    check(_lib.load().t4r_head_logits(ptr(xt_planes), ptr(w_planes), T_cap, ptr(t_dev), V, De, inv_temperature,
+                                      ptr(out), V, nprod, _stream()), "t4r_head_logits")
+    return out
+
+
+def recall_from_ranks(row_rank: torch.Tensor, ks: Sequence[int], t_dev=None) -> torch.Tensor:
+    _need_cuda(row_rank)
+    out = torch.empty(len(ks), dtype=torch.float32, device=row_rank.device)
+    arr = (C.c_int32 * len(ks))(*[int(k) for k in ks])
+    check(_lib.load().t4r_recall_from_ranks(ptr(row_rank), ptr(t_dev), row_rank.numel(), arr, len(ks), ptr(out),
+                                            _stream()), "t4r_recall_from_ranks")
+    return out
+
+
+def topk(logits: torch.Tensor, k: int):
+    _need_cuda(logits)
+    logits = _f32c(logits)
+    rows, V = logits.shape
+    scores = torch.empty((rows, k), dtype=torch.float32, device=logits.device)
+    ids = torch.empty((rows, k), dtype=torch.int64, device=logits.device)
+    check(_lib.load().t4r_topk(ptr(logits), rows, V, V, k, ptr(scores), ptr(ids), _stream()), "t4r_topk")
+    return scores, ids
+
+
+def combine_shard_lse(parts: torch.Tensor, t_dev=None):
+    """parts [world, T_cap, 2] (lse, label-logit) -> (row_loss [T_cap], loss [1])."""
+    _need_cuda(parts)
+    parts = _f32c(parts)
+    world, T_cap, _ = parts.shape
+    row_loss = torch.empty(T_cap, dtype=torch.float32, device=parts.device)
+    loss = torch.empty(1, dtype=torch.float32, device=parts.device)
+    check(_lib.load().t4r_combine_shard_lse(ptr(parts), world, T_cap, ptr(t_dev), ptr(row_loss), ptr(loss), _stream()),
+          "t4r_combine_shard_lse")
+    return row_loss, loss

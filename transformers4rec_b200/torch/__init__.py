@@ -1,0 +1,14 @@
+"""Drop-in namespace: ``import transformers4rec_b200.torch as tr`` exposes the names
+``transformers4rec.torch`` exports for the session-transformer path
+(reference: transformers4rec/torch/__init__.py:77-132)."""
+from ..block import (DenseBlock, GPT2Encoder, MLPBlock, SequentialBlock, TransformerBlock,  # noqa: F401
+                     XLNetEncoder)
+from ..config import GPT2Config, T4RecConfig, XLNetConfig, transformer_registry  # noqa: F401
+from ..features import (ContinuousFeatures, FeatureConfig, SequenceEmbeddingFeatures, TableConfig,  # noqa: F401
+                        TabularSequenceFeatures)
+from ..masking import (CausalLanguageModeling, MaskedLanguageModeling, MaskSequence,  # noqa: F401
+                       masking_registry)
+from ..model import Head, Model  # noqa: F401
+from ..prediction_task import (LogUniformSampler, NextItemPredictionTask, PredictionTask)  # noqa: F401
+from ..ranking_metric import AvgPrecisionAt, MeanReciprocalRankAt, NDCGAt, RecallAt  # noqa: F401
+from ..schema import ColumnSchema, Schema, Tags  # noqa: F401
