@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- sessions/sec (forward + loss) of the session-transformer hot path.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (N>1 via torchrun, one
+rank per GPU) prints ONE JSON line from rank 0.  A "step" is one pass of the hot
+path (gather -> projection -> masking -> encoder -> tied-weight softmax CE) over one
+batch of synthetic yoochoose-shaped sessions.  Workload at every N: BASELINE.json
+configs[1] (1M-item table, L=20, XLNet d=256 x4, MLM, B=2048 per GPU; weak scaling,
+independent replicas -- sessions are independent, no data-path collective).
+
+``--impl reference`` times the reference's own CPU implementation of the path (the
+oracle graph: stock torch ops + the Hugging Face encoder, all host threads) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1] as instantiated in SURVEY.md §8d
+    "config2": dict(V=1_000_001, De=256, d=256, H=8, NL=4, L=20, B=2048, arch="xlnet", masking="mlm",
+                    label="1M-item table, seq_len=20, XLNet-base d_model=256 4-layer, MLM, batch=2048"),
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case); used by --workload config1
+    "config1": dict(V=10_001, De=64, d=64, H=4, NL=2, L=20, B=512, arch="xlnet", masking="mlm",
+                    label="synthetic yoochoose schema, 10K-item table, seq_len=20, XLNet d_model=64 2-layer"),
+}
+METRIC = "sessions/sec (fwd+loss)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synth_ids(B, L, V, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(2, L + 1, (B,), generator=g)
+    ids = torch.randint(1, V, (B, L), generator=g)
+    return torch.where(torch.arange(L).unsqueeze(0) < lens.unsqueeze(1), ids, torch.zeros_like(ids))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_product_model(cfg, device):
+    import transformers4rec_b200.torch as tr
+
+    torch.manual_seed(1)
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", cfg["V"] - 1, tags=[tr.Tags.ITEM_ID])])
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=cfg["L"], d_output=cfg["d"],
+                                                    masking=cfg["masking"],
+                                                    embedding_dims={"item_id/list": cfg["De"]})
+    tcfg = (tr.XLNetConfig if cfg["arch"] == "xlnet" else tr.GPT2Config).build(
+        d_model=cfg["d"], n_head=cfg["H"], n_layer=cfg["NL"], total_seq_length=cfg["L"])
+    model = tcfg.to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
+    return model.to(device).eval()
+
+
+def build_oracle(cfg):
+    import t4r_oracle as O
+
+    torch.manual_seed(1)
+    return O.OracleSessionModel(cardinalities={"item_id/list": cfg["V"]}, embedding_dims={"item_id/list": cfg["De"]},
+                                item_id="item_id/list", continuous=(), d_model=cfg["d"], n_head=cfg["H"],
+                                n_layer=cfg["NL"], max_seq_len=cfg["L"], arch=cfg["arch"],
+                                masking=cfg["masking"]).eval()
+
+
+def time_oracle_cpu(cfg, B_cpu, steps, warmup):
+    """The reference's CPU torch path on a bounded sample (B_cpu sessions per step)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle = build_oracle(cfg)
+    ids = synth_ids(B_cpu, cfg["L"], cfg["V"], seed=0)
+    g = torch.Generator().manual_seed(2)
+    u = torch.rand((B_cpu, cfg["L"] + 2), generator=g)
+    draws = {"u_bern": u[:, :cfg["L"]], "u_force": u[:, cfg["L"]], "u_unmask": u[:, cfg["L"] + 1]}
+    batch = {"item_id/list": ids}
+    ts = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = oracle(batch, training=True, draws=draws)
+            float(out["loss"])
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return B_cpu / med, med, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-sessions", type=int, default=64, help="sessions per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity), 1 = plain bf16")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config_desc = {"workload": f"BASELINE.json {args.workload}: {cfg['label']}", "per_gpu_batch": cfg["B"],
+                   "global_batch": cfg["B"] * world, "seq_len": cfg["L"], "items": cfg["V"],
+                   "parallelism": f"{world} independent replicas (sessions are independent; no data-path collective)",
+                   "l2_policy": "inputs larger than L2 (1 GB item table + 1 GB split planes streamed per step)",
+                   "product_arithmetic": "split-bf16 x3 tcgen05 products, fp32 accumulate" if args.nprod == 3
+                   else "bf16 tcgen05, fp32 accumulate"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        warm = 1
+        v, med, threads = time_oracle_cpu(cfg, args.cpu_sessions, steps, warm)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "sessions/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_desc,
+                "cpu_baseline": {"value": v, "unit": "sessions/s", "cores": threads, "kind": "port",
+                                 "sample": f"{args.cpu_sessions} sessions/step of the same workload, "
+                                           f"{steps} timed steps (median), oracle graph = torch CPU ops + HF encoder"},
+                "e2e": {"value": v, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ product arm (B200)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import transformers4rec_b200 as t4r
+    from transformers4rec_b200 import ops
+
+    lib = t4r.load()
+    model = build_product_model(cfg, dev)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    task.nprod = args.nprod
+    B, L, V = cfg["B"], cfg["L"], cfg["V"]
+    ids_host = synth_ids(B, L, V, seed=rank).pin_memory()
+    ids_dev = ids_host.to(dev)
+    batch_dev = {"item_id/list": ids_dev}
+
+    def step(batch):
+        with torch.no_grad():
+            return model(batch, training=True)["loss"]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(batch_dev)
+    barrier()
+
+    # --- timed region 1: inputs resident in HBM
+    K = args.steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.t4r_launch_count()
+    barrier()
+    e0.record()
+    for i in range(K):
+        ops.HEAD_EVENTS = evs[i]
+        step(batch_dev)
+    e1.record()
+    barrier()
+    ops.HEAD_EVENTS = None
+    n1 = lib.t4r_launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    head_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    head_ms_avg = sum(head_ms) / len(head_ms)
+    T = int(task._last["count"].item())
+
+    # --- timed region 2: end to end through the public API with HOST inputs
+    loss_host = 0.0
+    for _ in range(2):
+        loss_host = step({"item_id/list": ids_host.to(dev, non_blocking=True)}).item()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss_host = step({"item_id/list": ids_host.to(dev, non_blocking=True)}).item()  # H2D + D2H every step
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    tt = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / K
+    value = B * world / (ms_per_step / 1e3)
+    e2e_value = B * world / (e2e_ms / K / 1e3)
+    peaks, peak_kind = load_peaks()
+    head_flops = 2.0 * T * V * cfg["De"]  # algorithmic (head_flop = 2*T*V*De)
+    achieved_tf = head_flops / (head_ms_avg * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,false,true> (tied logits + online LSE)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
+                "traffic": None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,
+                "algorithmic_flops_per_launch": head_flops, "label_rows_T": T,
+                "note": "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction"
+                if args.nprod == 3 else "plain bf16 product"}
+    line = {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)"
+            if args.nprod == 3 else "bf16", "data": "synthetic", "config": config_desc, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": int(ids_host.numel() * 8),
+                    "d2h_bytes_per_step": 4, "loss": loss_host},
+            "gpu_launches": int(n1 - n0), "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        v, med, threads = time_oracle_cpu(cfg, args.cpu_sessions, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "sessions/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_sessions} sessions/step of the same workload, 3 timed steps "
+                                          f"(median {med:.2f} s), oracle graph = torch CPU ops + HF encoder"}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/t4r_b200.h
+declares; host-side API surface (schema shim, from_schema, registries, state-dict
+names, error messages) mirrors the reference.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+
+    from transformers4rec_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    hdr = open(os.path.join(ROOT, "include", "t4r_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(t4r_[a-z0-9_]+)\s*\(", hdr)) - {"t4r_round_up64"}
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/t4r_b200.h but not exported"
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    assert _lib.load().t4r_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from transformers4rec_b200 import _lib
+    import ctypes as C
+    assert C.sizeof(_lib.XLNetLayer) == 13 * 8 and C.sizeof(_lib.GPT2Layer) == 12 * 8
+    # t4r_feature_list: 2 ints + 32 ptr + 32 ptr + 32 i64 + 32 int + 32 int + 32 ptr + 32 int
+    assert C.sizeof(_lib.FeatureList) == 8 + 32 * 8 * 3 + 32 * 4 * 2 + 32 * 8 + 32 * 4
+
+
+def test_no_cpu_fallback():
+    from transformers4rec_b200 import T4RError, ops
+    with pytest.raises(T4RError):
+        ops.split_planes(torch.randn(4, 8))
+    with pytest.raises(T4RError):
+        ops.mask_clm(torch.zeros(2, 3, dtype=torch.long), 0)
+
+
+def _schema(tr):
+    return tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 51996, tags=[tr.Tags.ITEM_ID]),
+                      tr.ColumnSchema.create_categorical("category/list", 332),
+                      tr.ColumnSchema.create_continuous("price/list")])
+
+
+def test_from_schema_surface_and_state_dict_names():
+    import transformers4rec_b200.torch as tr
+    s = _schema(tr)
+    inp = tr.TabularSequenceFeatures.from_schema(s, max_sequence_length=20, d_output=100, masking="causal")
+    assert isinstance(inp.masking, tr.CausalLanguageModeling)
+    assert inp.item_id == "item_id/list"
+    assert inp.item_embedding_table.num_embeddings == 51997  # int_domain.max + 1
+    assert inp.aggregation == "concat"
+    assert tuple(inp.output_size()) == (-1, 20, 100)
+    assert inp._layout()[1] == 64 + 64 + 1
+    names = [n for n, *_ in inp._layout()[0]]
+    assert names == sorted(names)  # concat order = sorted feature names
+    cfg = tr.XLNetConfig.build(d_model=64, n_head=4, n_layer=2, total_seq_length=20)
+    assert cfg.layer_norm_eps == 0.03 and cfg.d_inner == 256 and cfg.attn_type == "bi" and cfg.vocab_size == 1
+    body = tr.SequentialBlock(inp, tr.MLPBlock([64]).build(inp.output_size()), tr.TransformerBlock(cfg, masking=inp.masking))
+    model = tr.NextItemPredictionTask(weight_tying=True).to_model(body, inp)
+    keys = set(model.state_dict().keys())
+    for k in ("heads.0.body.0.to_merge.categorical_module.embedding_tables.item_id/list.weight",
+              "heads.0.body.0.projection_module.0.0.weight", "heads.0.body.0._masking.masked_item_embedding",
+              "heads.0.body.2.transformer.layer.0.rel_attn.q", "heads.0.body.2.transformer.layer.1.ff.layer_2.bias"):
+        assert k in keys, k
+    task = model.heads[0].prediction_task_dict["next-item"]
+    assert task.target_dim == 51997 and task.item_embedding_table is inp.item_embedding_table
+    # HF checkpoints load unchanged
+    import t4r_oracle as O
+    hf = O.build_hf_xlnet(64, 4, 2)
+    missing, unexpected = body[2].transformer.load_state_dict(hf.state_dict(), strict=True), None
+
+
+def test_reference_error_messages():
+    import transformers4rec_b200.torch as tr
+    s = _schema(tr)
+    with pytest.raises(ValueError, match="You cannot specify both d_output and projection"):
+        tr.TabularSequenceFeatures.from_schema(s, d_output=8, projection=tr.MLPBlock([8]))
+    no_item = tr.Schema([tr.ColumnSchema.create_categorical("category/list", 332)])
+    with pytest.raises(ValueError, match="For masking a categorical_module is required including an item_id"):
+        tr.TabularSequenceFeatures.from_schema(no_item, d_output=8, masking="mlm")
+    inp = tr.TabularSequenceFeatures.from_schema(s, max_sequence_length=20, d_output=64, masking="mlm")
+    gcfg = tr.GPT2Config.build(d_model=64, n_head=4, n_layer=1, total_seq_length=20)
+    with pytest.raises(ValueError, match="MaskedLanguageModeling is not supported by: the GPT2Config architecture"):
+        tr.TransformerBlock(gcfg, masking=inp.masking)
+    inp2 = tr.TabularSequenceFeatures.from_schema(s, max_sequence_length=20, d_output=64)
+    body = tr.SequentialBlock(inp2, tr.TransformerBlock(tr.XLNetConfig.build(64, 4, 1, 20)))
+    with pytest.raises(ValueError, match="The input block should contain a masking schema"):
+        tr.NextItemPredictionTask(weight_tying=True).to_model(body, inp2)
+    assert gcfg.layer_norm_epsilon == 1e-5 and gcfg.n_positions == 20
+
+
+def test_task_block_inserted_when_dims_differ():
+    import transformers4rec_b200.torch as tr
+    s = _schema(tr)
+    inp = tr.TabularSequenceFeatures.from_schema(s, max_sequence_length=20, d_output=256, masking="clm")
+    model = tr.GPT2Config.build(256, 8, 1, 20).to_torch_model(inp, tr.NextItemPredictionTask(weight_tying=True))
+    task = model.heads[0].prediction_task_dict["next-item"]
+    lin = task.task_block[0][0]
+    assert (lin.in_features, lin.out_features) == (256, 64) and len(task.task_block[0]) == 1  # no activation
+
+
+def test_schema_json_roundtrip(tmp_path):
+    import json
+
+    import transformers4rec_b200.torch as tr
+    doc = {"feature": [
+        {"name": "item_id/list", "type": "INT", "intDomain": {"name": "item_id/list", "min": "1", "max": "51996", "isCategorical": True},
+         "valueCount": {"min": "2", "max": "185"}, "annotation": {"tag": ["item_id", "list", "categorical", "item"]}},
+        {"name": "timestamp/hour/list", "type": "FLOAT", "valueCount": {"min": "2", "max": "185"},
+         "annotation": {"tag": ["continuous", "time", "list"]}}]}
+    p = tmp_path / "schema.json"
+    p.write_text(json.dumps(doc))
+    s = tr.Schema.from_json(str(p))
+    assert s.select_by_tag(tr.Tags.ITEM_ID).column_names == ["item_id/list"]
+    assert s.categorical_cardinalities() == {"item_id/list": 51997}
+    assert s.select_by_tag("continuous").column_names == ["timestamp/hour/list"]
+
+
+def test_log_uniform_sampler_host_side():
+    import t4r_oracle as O
+    import transformers4rec_b200.torch as tr
+    smp = tr.LogUniformSampler(max_n_samples=50, max_id=1000, min_id=1)
+    assert torch.equal(smp.dist, O.log_uniform_distr(1000, 1))
+    assert torch.equal(smp.unique_sampling_dist, O.unique_sampling_distr(smp.dist, 100))
+    assert smp.dist[0] == 0 and abs(smp.dist.sum().item() - 1.0) < 1e-5
+    with pytest.raises(ValueError):
+        tr.LogUniformSampler(max_n_samples=0, max_id=10)
