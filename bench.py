@@ -226,6 +226,8 @@ def main():
     # --- timed region 1: inputs resident in HBM
     K = args.steps
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in evs:  # torch creates the cudaEvent_t lazily: record once so .cuda_event is a live handle
+        a.record(); b.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
