@@ -1,0 +1,101 @@
+"""world_size-2 gloo tests (CPU) of the sharded lookup / sharded head choreography
+(SURVEY §8e): routing plan, all-to-all split sizes, un-permutation and the
+cross-shard log-sum-exp combination, checked against a single-process computation.
+The local compute steps are test-side stand-ins (the product's are CUDA kernels)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from transformers4rec_b200 import distributed as D
+
+V, De, B, L = 1001, 16, 6, 5
+
+
+def _full_table():
+    g = torch.Generator().manual_seed(0)
+    return torch.randn((V, De), generator=g)
+
+
+def _ids(rank):
+    g = torch.Generator().manual_seed(10 + rank)
+    ids = torch.randint(1, V, (B, L), generator=g)
+    ids[:, -1] = 0  # padding id lives in shard 0
+    return ids
+
+
+def _labels(rank):
+    g = torch.Generator().manual_seed(20 + rank)
+    T = 4 + 3 * rank  # ragged label counts per rank
+    return torch.randn((T, De), generator=g), torch.randint(1, V, (T,), generator=g)
+
+
+def _head_rows(xg, yg, local_table, w_planes, lo, inv_tau):
+    logits = (xg @ local_table.t()) * inv_tau
+    lse = torch.logsumexp(logits, dim=1)
+    loc = yg - lo
+    mine = (loc >= 0) & (loc < local_table.shape[0])
+    tgt = torch.where(mine, logits.gather(1, loc.clamp(0, local_table.shape[0] - 1).unsqueeze(1)).squeeze(1),
+                      torch.zeros_like(lse))
+    return torch.stack([lse, tgt], dim=1)
+
+
+def _combine(parts):
+    lse = torch.logsumexp(parts[:, :, 0], dim=0)
+    tgt = parts[:, :, 1].sum(dim=0)
+    row = lse - tgt
+    return row, row.mean().reshape(1)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        table = _full_table()
+        lo, hi = D.shard_bounds(V, rank, world)
+        local = table[lo:hi].contiguous()
+        ids = _ids(rank)
+        rows, _ = D.sharded_embedding_lookup(local, ids, V, gather_rows=lambda t, i: t[i],
+                                             place=lambda recv, unp: (recv[unp.long()], None))
+        ok_lookup = torch.equal(rows, table[ids.reshape(-1)])
+        xt, y = _labels(rank)
+        row_loss, loss, T_total = D.sharded_softmax_ce(xt, y, local, V, head_rows=_head_rows, combine=_combine)
+        # single-process reference over the global batch
+        xs, ys = zip(*[_labels(r) for r in range(world)])
+        xg, yg = torch.cat(xs), torch.cat(ys)
+        ref_rows = torch.nn.functional.cross_entropy(xg @ table.t(), yg, reduction="none")
+        start = sum(x.shape[0] for x in xs[:rank])
+        ok_head = (torch.allclose(row_loss, ref_rows[start:start + xt.shape[0]], atol=1e-5)
+                   and abs(loss.item() - ref_rows.mean().item()) < 1e-5 and T_total == xg.shape[0])
+        q.put((rank, ok_lookup, ok_head))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_lookup_and_head_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_lookup, ok_head in res:
+        assert ok_lookup, f"rank {rank}: sharded lookup differs from the replicated table"
+        assert ok_head, f"rank {rank}: sharded head differs from the single-process loss"
+
+
+def test_shard_bounds_and_plan():
+    assert D.shard_bounds(10, 0, 4) == (0, 3) and D.shard_bounds(10, 3, 4) == (9, 10)
+    assert D.shard_bounds(1_000_001, 7, 8) == (875_007, 1_000_001)
+    ids_all = torch.tensor([[0, 5, 9, 3], [7, 7, 1, 2]])
+    plan = D.LookupPlan(ids_all, rank=1, world=2, V=10)  # rank 1 owns rows [5, 10)
+    assert plan.send_counts == [2, 2] and plan.send_local_idx.tolist() == [0, 4, 2, 2]
+    assert plan.recv_counts == [2, 2]          # my ids [7,7,1,2]: two owned by rank 0, two by rank 1
+    assert plan.unpermute.tolist() == [2, 3, 0, 1]
+    assert torch.equal(D.owner_of(torch.tensor([0, 4, 5, 9]), 10, 2), torch.tensor([0, 0, 1, 1]))

@@ -345,7 +345,7 @@ static const int kHeadBN = 256;
 extern "C" size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De) {
   (void)De;
   const size_t part_ld = static_cast<size_t>((T_cap + 127) / 128) * 128;
-  const size_t n_tiles = static_cast<size_t>((V + kHeadBN - 1) / kHeadBN);
+  const size_t n_tiles = 2 * static_cast<size_t>((V + kHeadBN - 1) / kHeadBN);  // two column halves per tile
   return 2 * pad256(n_tiles * part_ld * 4) + pad256(2 * 64 * part_ld * 4) + 1024;
 }
 
@@ -360,7 +360,7 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   T4R_REQUIRE(a->workspace_bytes >= t4r_head_workspace_bytes(a->T_cap, a->V, a->De), "head: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int part_ld = (a->T_cap + 127) / 128 * 128;
-  const int n_tiles = static_cast<int>((a->V + kHeadBN - 1) / kHeadBN);
+  const int n_tiles = 2 * static_cast<int>((a->V + kHeadBN - 1) / kHeadBN);  // partials per (tile, column half)
   Arena ar(a->workspace, a->workspace_bytes);
   float* part_m = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
   float* part_s = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);

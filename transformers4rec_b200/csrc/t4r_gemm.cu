@@ -7,8 +7,9 @@
 // tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM; three products per K step:
 // hi*hi + hi*lo + lo*hi) and drained by four epilogue warps with tcgen05.ld.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 =
-// epilogue (TMEM lane quadrant = warp_id % 4).  Two accumulator stages in TMEM let
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 =
+// epilogue (TMEM lane quadrant = warp_id % 4; warps 2-5 own the first half of a
+// tile's columns, warps 6-9 the second half).  Two accumulator stages in TMEM let
 // the epilogue of tile i overlap the main loop of tile i+1.  Tiles are visited
 // m-fastest so CTAs running at the same time share the B tile in L2.
 //
@@ -19,6 +20,7 @@
 #include <mutex>
 
 #include "t4r_common.cuh"
+#include "t4r_tmem_ld.cuh"
 #include "t4r_internal.h"
 
 namespace t4r {
@@ -80,7 +82,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*LN exchange*/;
 };
 
 struct GemmDev {
@@ -160,79 +162,100 @@ __device__ __forceinline__ void store_planes_chunk(__nv_bfloat16* hi_dst, __nv_b
   }
 }
 
+// Each epilogue thread owns one output row (its TMEM lane) and COLS = BN/2 columns
+// (warps 2-5 take the first half of the tile's columns, warps 6-9 the second half).
 template <int BN, bool LN>
-__device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr, int64_t row, bool row_ok, int64_t n0) {
+__device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr, int64_t row, bool row_ok, int64_t n0,
+                                               float2* xch_mine, const float2* xch_other) {
+  constexpr int COLS = BN / 2;
   const GemmEpilogue& ep = p.ep;
   int code = 0;
   if (row_ok && ep.row_code) code = ep.row_code[row];
-  float mean = 0.f, rstd = 1.f;
-  if (LN) {
-    // pass 1: shifted sums for mean / biased variance over the N (= BN) outputs of the row
-    float shift = 0.f, sum = 0.f, sq = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(taddr + c * 32, v);
-      if (row_ok) {
-        dense_chunk(v, ep, row, n0 + c * 32, code);
-        if (c == 0) shift = v[0];
+  if constexpr (LN) {
+    // single pass: the thread's whole half-row lives in registers
+    float v[COLS];
+    tmem_ld<COLS>(taddr, v);
+    float mean_h = 0.f, m2_h = 0.f;
+    if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float d = v[j] - shift;
-          sum += d;
-          sq = fmaf(d, d, sq);
+      for (int c = 0; c < COLS / 32; ++c) {
+        float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
+        dense_chunk(vc, ep, row, n0 + c * 32, code);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) sum += v[j];
+      mean_h = sum * (1.f / COLS);
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) {
+        const float d = v[j] - mean_h;
+        m2_h = fmaf(d, d, m2_h);
+      }
+    }
+    // combine the two halves of the row (Chan et al. pairwise update, equal counts)
+    *xch_mine = make_float2(mean_h, m2_h);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float2 o = *xch_other;
+    const float delta = o.x - mean_h;
+    const float mean = 0.5f * (mean_h + o.x);
+    const float m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
+    const float rstd = rsqrtf(m2 * (1.f / BN) + ep.ln_eps);
+    if (row_ok) {
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c) {
+        float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
+        const int64_t ncol0 = n0 + c * 32;
+        if (ep.out_pre) store_f32_chunk(ep.out_pre + row * ep.ldp + ncol0, vc, 1.f);
+        const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
+        const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+          vc[4 * j + 0] = (vc[4 * j + 0] - mean) * rstd * g.x + b.x;
+          vc[4 * j + 1] = (vc[4 * j + 1] - mean) * rstd * g.y + b.y;
+          vc[4 * j + 2] = (vc[4 * j + 2] - mean) * rstd * g.z + b.z;
+          vc[4 * j + 3] = (vc[4 * j + 3] - mean) * rstd * g.w + b.w;
+        }
+        if (ep.out_f32) store_f32_chunk(ep.out_f32 + row * ep.ldo + ncol0, vc, ep.out_scale);
+        if (ep.out_planes) {
+          __nv_bfloat16* hi = ep.out_planes + row * ep.ldpl + ncol0;
+          store_planes_chunk(hi, hi + ep.plane_stride, vc);
         }
       }
     }
-    const float inv_n = 1.f / static_cast<float>(BN);
-    const float dm = sum * inv_n;
-    mean = shift + dm;
-    const float var = fmaxf(sq * inv_n - dm * dm, 0.f);
-    rstd = rsqrtf(var + ep.ln_eps);
-  }
+  } else {
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    float v[32];
-    tmem_ld32(taddr + c * 32, v);
-    if (!row_ok) continue;
-    const int64_t ncol0 = n0 + c * 32;
-    if (ncol0 >= p.N) continue;
-    dense_chunk(v, ep, row, ncol0, code);
-    if (LN) {
-      if (ep.out_pre) store_f32_chunk(ep.out_pre + row * ep.ldp + ncol0, v, 1.f);
-      const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
-      const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
+    for (int c = 0; c < COLS / 32; ++c) {
+      float v[32];
+      tmem_ld<32>(taddr + c * 32, v);
+      if (!row_ok) continue;
+      const int64_t ncol0 = n0 + c * 32;
+      if (ncol0 >= p.N) continue;
+      dense_chunk(v, ep, row, ncol0, code);
+      if (ep.out_f32) {
+        float* dst = ep.out_f32 + row * ep.ldo + ncol0;
+        if ((ep.ldo & 3) == 0 && ncol0 + 32 <= p.N) {
+          store_f32_chunk(dst, v, ep.out_scale);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-        v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
-        v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
-        v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
-        v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+          for (int j = 0; j < 32; ++j)
+            if (ncol0 + j < p.N) dst[j] = v[j] * ep.out_scale;
+        }
       }
-    }
-    if (ep.out_f32) {
-      float* dst = ep.out_f32 + row * ep.ldo + ncol0;
-      if ((ep.ldo & 3) == 0 && ncol0 + 32 <= p.N) {
-        store_f32_chunk(dst, v, ep.out_scale);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (ncol0 + j < p.N) dst[j] = v[j] * ep.out_scale;
+      if (ep.out_planes) {
+        __nv_bfloat16* hi = ep.out_planes + row * ep.ldpl + ncol0;
+        store_planes_chunk(hi, hi + ep.plane_stride, v);
       }
-    }
-    if (ep.out_planes) {
-      __nv_bfloat16* hi = ep.out_planes + row * ep.ldpl + ncol0;
-      store_planes_chunk(hi, hi + ep.plane_stride, v);
     }
   }
 }
 
-// head epilogue: per row, online log-sum-exp (base 2) over the BN classes of this
-// tile, optional logQ bias / accidental-hit removal (sampled softmax) and rank count.
+// head epilogue: per row, online log-sum-exp (base 2) over this thread's COLS classes
+// of the tile, optional logQ bias / accidental-hit removal (sampled softmax), rank count.
 template <int BN>
 __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, int64_t row, bool row_ok, int64_t n0,
-                                              int tile_n) {
+                                              int part_idx) {
+  constexpr int COLS = BN / 2;
   const GemmEpilogue& ep = p.ep;
   constexpr float kLog2e = 1.4426950408889634f;
   const float scale2 = ep.inv_tau * kLog2e;
@@ -243,11 +266,11 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   const bool want_rank = (ep.row_rank != nullptr);
   if (row_ok && ep.row_label) label = ep.row_label[row];
   if (row_ok && want_rank) tgt = ep.row_tgt[row];
-  const bool full_tile = (n0 + BN <= p.N);
+  const bool full_tile = (n0 + COLS <= p.N);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = 0; c < COLS / 32; ++c) {
     float v[32];
-    tmem_ld32(taddr + c * 32, v);
+    tmem_ld<32>(taddr + c * 32, v);
     if (!row_ok) continue;
     const int64_t ncol0 = n0 + c * 32;
     if (ncol0 >= p.N) continue;
@@ -290,14 +313,14 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
     }
   }
   if (row_ok) {
-    ep.part_m[static_cast<int64_t>(tile_n) * ep.part_ld + row] = m_run;
-    ep.part_s[static_cast<int64_t>(tile_n) * ep.part_ld + row] = s_run;
+    ep.part_m[static_cast<int64_t>(part_idx) * ep.part_ld + row] = m_run;
+    ep.part_s[static_cast<int64_t>(part_idx) * ep.part_ld + row] = s_run;
     if (want_rank && cnt) atomicAdd(ep.row_rank + row, cnt);
   }
 }
 
 template <int BN, bool LN, bool HEAD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const GemmDev p) {
@@ -309,6 +332,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* xch = reinterpret_cast<float2*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [2 parity][2 half][128]
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -332,7 +356,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -412,24 +436,31 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quad = warp & 3;
+    // ===================== epilogue warps (2..9) =====================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns
+    constexpr int COLS = BN / 2;
     int as = 0;
     uint32_t aph = 0;
+    uint32_t tile_parity = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tile_n = static_cast<int>(tile / tiles_m);
       const int64_t m0 = static_cast<int64_t>(tile % tiles_m) * BM;
-      const int64_t n0 = static_cast<int64_t>(tile_n) * BN;
+      const int64_t n0 = static_cast<int64_t>(tile_n) * BN + half * COLS;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + half * COLS);
       const int64_t row = m0 + quad * 32 + lane;
       const bool row_ok = row < M_eff;
       if (HEAD) {
-        epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n);
+        epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
       } else {
-        epilogue_dense<BN, LN>(p, taddr, row, row_ok, n0);
+        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
+        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        epilogue_dense<BN, LN>(p, taddr, row, row_ok, n0, xm, xo);
       }
+      tile_parity ^= 1;
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -471,7 +502,7 @@ static int launch_inst(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   }
   int grid = static_cast<int>(max_tiles < num_sms() ? max_tiles : num_sms());
   if (grid < 1) grid = 1;
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, dp);
+  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, dp);
   T4R_LAUNCH_CHECK("gemm_bf16x3_kernel");
   return 0;
 }

@@ -505,19 +505,29 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
 
   for (int b = b_begin + warp; b < b_end; b += nwarps) {
     const float* base = qkv + static_cast<int64_t>(b) * L * 3 * d + h * DH;
-    // stage q (+biases), k, v for this (b, h)
-    for (int idx = lane; idx < L * DH; idx += 32) {
-      const int i = idx / DH, c = idx % DH;
-      const float* rowp = base + static_cast<int64_t>(i) * 3 * d;
-      const float q = rowp[c];
-      if (REL) {
-        qw[i * DH + c] = q + __ldg(rw + h * DH + c);
-        qr[i * DH + c] = q + __ldg(rr + h * DH + c);
-      } else {
-        qw[i * DH + c] = q;
+    // stage q (+biases), k, v for this (b, h): 16-byte loads, several rows in flight per lane
+    // (a one-load-at-a-time loop makes the whole kernel DRAM-latency bound)
+    {
+      constexpr int V4 = DH / 4;  // float4 per row
+      const int total = L * V4;
+#pragma unroll 5
+      for (int idx = lane; idx < total; idx += 32) {
+        const int i = idx / V4, c = (idx % V4) * 4;
+        const float* rowp = base + static_cast<int64_t>(i) * 3 * d + c;
+        const float4 q4 = *reinterpret_cast<const float4*>(rowp);
+        const float4 k4 = *reinterpret_cast<const float4*>(rowp + d);
+        const float4 v4 = *reinterpret_cast<const float4*>(rowp + 2 * d);
+        if (REL) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(rw + h * DH + c));
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + h * DH + c));
+          *reinterpret_cast<float4*>(qw + i * DH + c) = make_float4(q4.x + w4.x, q4.y + w4.y, q4.z + w4.z, q4.w + w4.w);
+          *reinterpret_cast<float4*>(qr + i * DH + c) = make_float4(q4.x + r4.x, q4.y + r4.y, q4.z + r4.z, q4.w + r4.w);
+        } else {
+          *reinterpret_cast<float4*>(qw + i * DH + c) = q4;
+        }
+        *reinterpret_cast<float4*>(ks + i * DP + c) = k4;
+        *reinterpret_cast<float4*>(vs + i * DH + c) = v4;
       }
-      ks[i * DP + c] = rowp[d + c];
-      vs[i * DH + c] = rowp[2 * d + c];
     }
     __syncwarp();
 
@@ -532,15 +542,18 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
         kreg[c4] = jok ? *reinterpret_cast<const float4*>(ks + j * DP + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
       for (int i = 0; i < L; ++i) {
-        float acc = 0.f;
+        // four independent FMA chains per term (the dot product is latency-bound otherwise)
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* qwi = reinterpret_cast<const float4*>(qw + i * DH);
 #pragma unroll
         for (int c4 = 0; c4 < DH / 4; ++c4) {
           const float4 a = qwi[c4];
-          acc = fmaf(a.x, kreg[c4].x, acc); acc = fmaf(a.y, kreg[c4].y, acc);
-          acc = fmaf(a.z, kreg[c4].z, acc); acc = fmaf(a.w, kreg[c4].w, acc);
+          a4.x = fmaf(a.x, kreg[c4].x, a4.x); a4.y = fmaf(a.y, kreg[c4].y, a4.y);
+          a4.z = fmaf(a.z, kreg[c4].z, a4.z); a4.w = fmaf(a.w, kreg[c4].w, a4.w);
         }
+        float acc = (a4.x + a4.y) + (a4.z + a4.w);
         if (REL) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4* qri = reinterpret_cast<const float4*>(qr + i * DH);
           const int m = jok ? (j + L - i) : 0;
           const float4* rm = reinterpret_cast<const float4*>(Rs + m * DP);
@@ -548,9 +561,10 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
           for (int c4 = 0; c4 < DH / 4; ++c4) {
             const float4 a = qri[c4];
             const float4 bb = rm[c4];
-            acc = fmaf(a.x, bb.x, acc); acc = fmaf(a.y, bb.y, acc);
-            acc = fmaf(a.z, bb.z, acc); acc = fmaf(a.w, bb.w, acc);
+            b4.x = fmaf(a.x, bb.x, b4.x); b4.y = fmaf(a.y, bb.y, b4.y);
+            b4.z = fmaf(a.z, bb.z, b4.z); b4.w = fmaf(a.w, bb.w, b4.w);
           }
+          acc += (b4.x + b4.y) + (b4.z + b4.w);
         }
         acc *= scale;
         if (!REL && j > i) acc = -INFINITY;
@@ -639,9 +653,10 @@ static int launch_attn_inst(const float* qkv, const float* r, const float* rw, c
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
-  // sessions per block: enough blocks to fill the machine, enough sessions to amortise R staging
-  int spb = 8 * warps;
-  while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 4) spb >>= 1;
+  // sessions per block: R staging is small (2L x dh floats), so favour many resident warps
+  // (the per-session work is a chain of short dependent phases) over amortising it
+  int spb = 2 * warps;
+  while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
   dim3 grid((B + spb - 1) / spb, H);
   kern<<<grid, warps * 32, smem, s>>>(qkv, r, rw, rr, B, L, d, spb, out_planes, plane_stride);
   T4R_LAUNCH_CHECK("attn_kernel");

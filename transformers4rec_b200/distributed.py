@@ -1,0 +1,147 @@
+"""Row-sharded item table + sharded tied-weight head (BASELINE configs 4-5).
+
+The reference replicates the table and the logit GEMM on every rank (DDP only,
+SURVEY §2.1); at 10-50 M items both stop fitting, and under weight tying they are
+the same tensor.  It is sharded row-wise once and used from both ends with one
+collective per end:
+
+* lookup (K11): ranks all-gather their item ids (8 B/id), every rank gathers the rows
+  it owns for every peer (``t4r_gather_rows_split_i64``) and ONE all-to-all returns
+  them to the sessions' owners; a second ``t4r_gather_rows_split`` call un-permutes the
+  received rows and emits the split planes the projection GEMM consumes.
+* head (K12): label rows are all-gathered, every rank runs the fused logits+LSE
+  kernel over its V/world rows (``v_offset``), and ONE all-gather of the per-row
+  ``(lse, label-logit)`` pairs (8 B/row) is combined by ``t4r_combine_shard_lse``.
+
+Everything else (projection, masking, encoder) is data parallel with no collective.
+``torch.distributed`` (NCCL on GPUs) is the plumbing; the routing arithmetic below is
+integer index bookkeeping shared by all backends.  The local compute steps are
+injectable (``gather_rows`` / ``head_rows``): the product default is the CUDA kernels;
+the world_size-2 ``gloo`` tests on CPU pass test-side stand-ins to exercise the
+collective choreography (there is no CPU fallback in the product).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(V: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of the table owned by ``rank`` (block partition, ceil division)."""
+    per = (V + world - 1) // world
+    lo = min(V, rank * per)
+    return lo, min(V, lo + per)
+
+
+def owner_of(ids: torch.Tensor, V: int, world: int) -> torch.Tensor:
+    per = (V + world - 1) // world
+    return torch.div(ids, per, rounding_mode="floor").clamp_(max=world - 1)
+
+
+def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """all_gather_into_tensor with a flat output buffer (the form every backend accepts);
+    returns [world, *t.shape]."""
+    t = t.contiguous()
+    out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.reshape(-1), group=group)
+    return out.view((world,) + tuple(t.shape))
+
+
+class LookupPlan:
+    """Index bookkeeping for one sharded lookup step (pure integer work)."""
+
+    def __init__(self, ids_all: torch.Tensor, rank: int, world: int, V: int):
+        # ids_all [world, n]: flattened item ids of every rank
+        self.world, self.rank = world, rank
+        lo, hi = shard_bounds(V, rank, world)
+        n = ids_all.shape[1]
+        mine = (ids_all >= lo) & (ids_all < hi)                       # [world, n] rows I own, per requester
+        self.send_counts: List[int] = mine.sum(dim=1).tolist()         # rows I send to each peer
+        # local row index (within my shard) of every row I send, requester-major, position-ascending
+        self.send_local_idx = (ids_all[mine] - lo).contiguous()
+        own = owner_of(ids_all[rank], V, world)                        # owner of each of MY positions
+        self.recv_counts: List[int] = [int((own == q).sum()) for q in range(world)]
+        # received rows arrive owner-major, position-ascending: position p sits at perm_inv[p]
+        order = torch.argsort(own, stable=True)                        # positions grouped by owner
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(n, device=order.device)
+        self.unpermute = inv.to(torch.int32)                           # out[p] = recv[unpermute[p]]
+
+
+def _default_gather_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    from . import ops
+    if idx.numel() == 0:
+        return torch.empty((0, table.shape[1]), dtype=torch.float32, device=table.device)
+    _, rows = ops.gather_rows_split(table, idx, None, idx.numel(), want_f32=True)
+    return rows
+
+
+def _default_place(recv: torch.Tensor, unpermute: torch.Tensor):
+    from . import ops
+    planes, rows = ops.gather_rows_split(recv, unpermute, None, unpermute.numel(), want_f32=True)
+    return rows, planes
+
+
+def sharded_embedding_lookup(local_table: torch.Tensor, ids: torch.Tensor, V: int, group=None,
+                             gather_rows: Optional[Callable] = None, place: Optional[Callable] = None):
+    """Embedding rows for ``ids`` [B, L] from a table whose rows are block-sharded over
+    the group.  Returns (rows fp32 [B*L, De], planes or None)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gather_rows = gather_rows or _default_gather_rows
+    place = place or _default_place
+    flat = ids.reshape(-1).long().contiguous()
+    ids_all = _all_gather(flat, world, group)
+    plan = LookupPlan(ids_all, rank, world, V)
+    send = gather_rows(local_table, plan.send_local_idx)
+    De = local_table.shape[1]
+    recv = torch.empty((sum(plan.recv_counts), De), dtype=torch.float32, device=flat.device)
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=plan.recv_counts,
+                           input_split_sizes=plan.send_counts, group=group)
+    return place(recv, plan.unpermute)
+
+
+def _default_head_rows(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, w_planes, v_offset: int,
+                       inv_tau: float):
+    from . import ops
+    xp = ops.split_planes(xt)
+    res = ops.head_softmax_ce(xp, xt, labels, w_planes, local_table, inv_temperature=inv_tau, v_offset=v_offset,
+                              want_loss=False)
+    return torch.stack([res["row_lse"], res["row_tgt"]], dim=1)  # [T, 2]
+
+
+def _default_combine(parts: torch.Tensor):
+    from . import ops
+    return ops.combine_shard_lse(parts)
+
+
+def sharded_softmax_ce(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, V: int, group=None,
+                       w_planes=None, inv_tau: float = 1.0, head_rows: Optional[Callable] = None,
+                       combine: Optional[Callable] = None):
+    """Full-softmax CE of the label rows of ALL ranks against a row-sharded output
+    table.  ``xt`` [T_local, De] / ``labels`` [T_local] are this rank's label rows.
+    Returns (row_loss for this rank's rows, global mean loss, T_total)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    head_rows = head_rows or _default_head_rows
+    combine = combine or _default_combine
+    dev = xt.device
+    counts_l = _all_gather(torch.tensor([xt.shape[0]], dtype=torch.int64, device=dev), world, group).reshape(-1).tolist()
+    T_max = max(counts_l)
+    De = xt.shape[1]
+    pad_x = torch.zeros((T_max, De), dtype=torch.float32, device=dev)
+    pad_x[: xt.shape[0]] = xt
+    pad_y = torch.zeros((T_max,), dtype=torch.int64, device=dev)
+    pad_y[: xt.shape[0]] = labels
+    all_x = _all_gather(pad_x, world, group)
+    all_y = _all_gather(pad_y, world, group)
+    xg = torch.cat([all_x[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
+    yg = torch.cat([all_y[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
+    lo, _ = shard_bounds(V, rank, world)
+    part = head_rows(xg, yg, local_table, w_planes, lo, inv_tau)          # [T_total, 2]
+    parts = _all_gather(part, world, group)                               # the one head collective
+    row_loss, loss = combine(parts)
+    start = sum(counts_l[:rank])
+    return row_loss[start: start + counts_l[rank]], loss, int(sum(counts_l))
