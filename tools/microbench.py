@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Per-kernel timings at BASELINE config-2 shapes (B=2048, L=20, d=256, H=8): each op is
+run in isolation with CUDA events; also the target of the per-kernel ncu captures."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from transformers4rec_b200 import _lib, ops  # noqa: E402
+
+
+def timeit(name, fn, iters=20, warm=3, flops=None, bytes_=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    extra = ""
+    if flops:
+        extra += f"  {flops / us / 1e6:8.1f} TFLOP/s(alg)"
+    if bytes_:
+        extra += f"  {bytes_ / us / 1e3:8.1f} GB/s"
+    print(f"{name:34s} {us:9.1f} us{extra}", flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["all"]
+    B, L, d, H = 2048, 20, 256, 8
+    M = B * L
+    dev = "cuda"
+    torch.manual_seed(0)
+    x = torch.randn(M, d, device=dev)
+    xp = ops.split_planes(x)
+    w_qkv = ops.split_planes(torch.randn(3 * d, d, device=dev) * 0.05)
+    w_o = ops.split_planes(torch.randn(d, d, device=dev) * 0.05)
+    w_1 = ops.split_planes(torch.randn(4 * d, d, device=dev) * 0.05)
+    w_2 = ops.split_planes(torch.randn(d, 4 * d, device=dev) * 0.05)
+    b1, b2 = torch.randn(4 * d, device=dev), torch.randn(d, device=dev)
+    g, bt = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    ffp = ops.split_planes(torch.randn(M, 4 * d, device=dev))
+    on = lambda k: "all" in which or k in which
+    if on("qkv"):
+        timeit("qkv gemm N=768 K=256 (f32 out)", lambda: ops.linear(xp, w_qkv, d, want_planes=False),
+               flops=2 * M * 3 * d * d)
+    if on("ffn1"):
+        timeit("ffn1 gemm N=1024 K=256 gelu", lambda: ops.linear(xp, w_1, d, bias=b1, act=_lib.ACT_GELU, want_f32=False),
+               flops=2 * M * 4 * d * d)
+    if on("oproj"):
+        timeit("oproj gemm N=256 K=256 res+LN", lambda: ops.linear(xp, w_o, d, residual=x, ln=(g, bt), ln_eps=0.03),
+               flops=2 * M * d * d)
+    if on("ffn2"):
+        timeit("ffn2 gemm N=256 K=1024 res+LN", lambda: ops.linear(ffp, w_2, 4 * d, bias=b2, residual=x, ln=(g, bt), ln_eps=0.03),
+               flops=2 * M * 4 * d * d)
+    if on("proj"):
+        code = torch.zeros(M, dtype=torch.uint8, device=dev)
+        timeit("proj gemm N=256 K=256 relu+mask", lambda: ops.linear(xp, w_o, d, bias=b2, act=_lib.ACT_RELU, row_code=code, mask_vec=b2),
+               flops=2 * M * d * d)
+    if on("attn"):
+        import transformers4rec_b200.torch as tr
+        cfg = tr.XLNetConfig.build(d_model=d, n_head=H, n_layer=1, total_seq_length=L)
+        enc = tr.TransformerBlock(cfg).cuda()
+        xin = x.view(B, L, d)
+        timeit("xlnet layer (qkv+attn+o+ffn)", lambda: enc(xin))
+    if on("embed"):
+        V = 1_000_001
+        table = torch.randn(V, d, device=dev)
+        ids = torch.randint(1, V, (M,), device=dev)
+        timeit("embed_concat 1M x 256 (planes)", lambda: ops.embed_concat([(table, ids, 0)], [], M, d, False, True),
+               bytes_=M * (8 + 4 * d + 4 * d))
+    if on("head"):
+        V, T = 1_000_001, 5120
+        W = torch.randn(V, d, device=dev) * 0.05
+        wp = ops.split_planes(W)
+        xt = torch.randn(T, d, device=dev)
+        xtp = ops.split_planes(xt)
+        y = torch.randint(1, V, (T,), device=dev)
+        timeit("head 5120 x 1M x 256", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W), iters=5, flops=2 * T * V * d)
+
+
+if __name__ == "__main__":
+    main()
