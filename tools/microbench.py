@@ -28,6 +28,14 @@ def timeit(name, fn, iters=20, warm=3, flops=None, bytes_=None):
     if bytes_:
         extra += f"  {bytes_ / us / 1e3:8.1f} GB/s"
     print(f"{name:34s} {us:9.1f} us{extra}", flush=True)
+    if os.environ.get("T4R_GEMM_DEBUG", "0") not in ("0", "1"):
+        import ctypes
+        lib = _lib.load()
+        arr = (ctypes.c_ulonglong * 8)()
+        lib.t4r_debug_gemm_cycles(arr, 1)
+        n = max(1, arr[6])
+        print("    cta0/warp2 per tile: wait_tfull %d  epilogue %d  | per chunk-sum: tmem_ld %d math %d f32store %d planes %d (cycles; %d tiles)"
+              % (arr[0] // n, arr[1] // n, arr[2] // n, arr[3] // n, arr[4] // n, arr[5] // n, arr[6]), flush=True)
 
 
 def main():

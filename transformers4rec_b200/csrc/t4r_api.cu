@@ -198,9 +198,12 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
       pb.a_planes = attn_p; pb.a_rows = M;
       pb.b_planes = static_cast<const __nv_bfloat16*>(w.wo_planes); pb.b_rows = d;
       GemmEpilogue ep;
-      ep.residual = cur_f; ep.ldr = d;
+      // residual: the caller's fp32 x for the first layer, afterwards the split planes of the
+      // previous layer's output (hi + lo, exact to 16 mantissa bits) -- no fp32 copy of the
+      // residual stream is written between layers (the store path bounds these epilogues)
+      if (cur_f) { ep.residual = cur_f; ep.ldr = d; }
+      else { ep.residual_planes = cur_p; ep.ldrp = d; ep.residual_plane_stride = M * d; }
       ep.ln_gamma = w.ln1_gamma; ep.ln_beta = w.ln1_beta; ep.ln_eps = ln_eps;
-      ep.out_f32 = h1; ep.ldo = d;
       ep.out_planes = h1_p; ep.ldpl = d; ep.plane_stride = M * d;
       T4R_TRY(launch_gemm(pb, ep, s));
     }
@@ -217,7 +220,7 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
     }
     // out = LN(h1 + ff W2^T + b2)
     {
-      float* dst_f = last ? out_f32 : io_f[li & 1];
+      float* dst_f = last ? out_f32 : nullptr;
       __nv_bfloat16* dst_p = last ? static_cast<__nv_bfloat16*>(out_planes) : io_p[li & 1];
       GemmProblem pb;
       pb.M = M; pb.N = d; pb.Kp = 4 * d;
@@ -225,7 +228,7 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
       pb.b_planes = static_cast<const __nv_bfloat16*>(w.w2_planes); pb.b_rows = d;
       GemmEpilogue ep;
       ep.bias = w.b2;
-      ep.residual = h1; ep.ldr = d;
+      ep.residual_planes = h1_p; ep.ldrp = d; ep.residual_plane_stride = M * d;
       ep.ln_gamma = w.ln2_gamma; ep.ln_beta = w.ln2_beta; ep.ln_eps = ln_eps;
       ep.out_f32 = dst_f; ep.ldo = d;
       ep.out_planes = dst_p; ep.ldpl = d; ep.plane_stride = M * d;

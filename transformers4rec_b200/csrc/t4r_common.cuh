@@ -174,6 +174,29 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// 2^x on the SFU (ex2.approx.ftz: 2 ulp, exact 0 for x = -inf); used for the online softmax
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// erf via Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7; ~14 instructions with two SFU
+// ops instead of erff's ~30 with a branch).  The GELU epilogue of the 4d-wide FFN GEMM is
+// instruction-bound, and 1.5e-7 is far inside the 1e-3 parity budget.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  float t;  // 1 / (1 + p|x|): argument >= 1, so the branch-free SFU reciprocal (1 ulp) is safe
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = fast_exp2(-ax * ax * 1.4426950408889634f);
+  const float r = fmaf(-p, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f)); }
 
 }  // namespace t4r

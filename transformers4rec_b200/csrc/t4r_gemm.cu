@@ -17,6 +17,7 @@
 // and split-bf16 outputs) and head (online log-sum-exp partials + label rank).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "t4r_common.cuh"
@@ -82,8 +83,11 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*LN exchange*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*LN exchange*/ + 8 * 32 * 20 * 4 /*epilogue staging*/;
 };
+
+// T4R_GEMM_DEBUG & 2: cycle counters of one epilogue warp (CTA 0, warp 2), see tools/microbench.py
+__device__ unsigned long long g_dbg_cycles[8];
 
 struct GemmDev {
   int M;
@@ -100,9 +104,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// value of one 32-column chunk before LayerNorm: acc + bias -> act -> mask -> + residual
-__device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& ep, int64_t row, int64_t ncol0,
-                                            int code) {
+// value of one 32-column chunk: acc + bias -> act -> mask replace (residual is added separately)
+__device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& ep, int64_t ncol0, int code) {
   if (ep.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + ncol0);
 #pragma unroll
@@ -111,9 +114,15 @@ __device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& 
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
-  if (ep.act != T4R_ACT_NONE) {
+  // the activation switch stays OUTSIDE the element loops: a per-element branch splits the
+  // unrolled loop into 32 basic blocks and ptxas can no longer interleave the 32 independent
+  // chains (measured: 6.5k cycles per 32-element GELU chunk vs ~0.7k after hoisting)
+  if (ep.act == T4R_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (ep.act == T4R_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (code == 1) {
     const float4* m4 = reinterpret_cast<const float4*>(ep.mask_vec + ncol0);
@@ -126,24 +135,109 @@ __device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
-  if (ep.residual) {
-    const float4* r4 = reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + ncol0);
+}
+
+// ---------------------------------------------------------------------------
+// Coalesced global access for the epilogue.  After tcgen05.ld a thread holds one
+// output ROW (32 consecutive columns); storing that directly makes every warp store
+// touch 32 different 128-byte lines with 16 bytes each (measured: the store queue, not
+// the tensor pipe, then bounds the dense GEMMs).  Each warp therefore transposes
+// 32 rows x 16 columns at a time through a private 32 x 20-word shared-memory tile
+// (row stride 20 words: conflict-free row writes) and stores 8 rows x 64 contiguous
+// bytes per instruction.  All helpers are warp-collective.
+// ---------------------------------------------------------------------------
+constexpr int STG_LD = 20;                       // words per staged row
+constexpr int STG_WORDS = 32 * STG_LD;           // per warp
+
+// stage: thread-row -> row-segment ownership (registers), no global access
+__device__ __forceinline__ void warp_stage_f32(float* stg, const float (&v)[32], float scale, int lane, float4 (&t)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = r4[j];
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+          make_float4(v[h * 16 + 4 * j] * scale, v[h * 16 + 4 * j + 1] * scale, v[h * 16 + 4 * j + 2] * scale,
+                      v[h * 16 + 4 * j + 3] * scale);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c4 = lane & 3;
+      t[h * 4 + it] = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * c4);
+    }
+  }
+}
+__device__ __forceinline__ void warp_commit_f32(const float4 (&t)[8], float* gbase, int64_t ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c4 = lane & 3;
+      if (r < rows_valid) *reinterpret_cast<float4*>(gbase + r * ld + h * 16 + 4 * c4) = t[h * 4 + it];
+    }
+}
+__device__ __forceinline__ void warp_store_f32(float* stg, const float (&v)[32], float scale, float* gbase, int64_t ld,
+                                               int rows_valid, int lane) {
+  float4 t[8];
+  warp_stage_f32(stg, v, scale, lane, t);
+  warp_commit_f32(t, gbase, ld, rows_valid, lane);  // all 8 global stores back to back, after the last warp barrier
+}
+
+__device__ __forceinline__ void warp_load_f32(float* stg, const float* gbase, int64_t ld, int rows_valid, int lane,
+                                              float (&out)[32]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c4 = lane & 3;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows_valid) t = *reinterpret_cast<const float4*>(gbase + r * ld + h * 16 + 4 * c4);
+      *reinterpret_cast<float4*>(stg + r * STG_LD + 4 * c4) = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(stg + lane * STG_LD + 4 * j);
+      out[h * 16 + 4 * j] = t.x; out[h * 16 + 4 * j + 1] = t.y; out[h * 16 + 4 * j + 2] = t.z; out[h * 16 + 4 * j + 3] = t.w;
     }
   }
 }
 
-__device__ __forceinline__ void store_f32_chunk(float* dst, const float (&v)[32], float scale) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
+// residual kept only as split planes: out[j] = hi[j] + lo[j] (exact to 16 mantissa bits)
+__device__ __forceinline__ void warp_load_planes(float* stg_f, const __nv_bfloat16* hi_base, int64_t plane_stride,
+                                                 int64_t ld, int rows_valid, int lane, float (&out)[32]) {
+  uint32_t* stg = reinterpret_cast<uint32_t*>(stg_f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    d4[j] = make_float4(v[4 * j + 0] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale, v[4 * j + 3] * scale);
+  for (int pl = 0; pl < 2; ++pl) {
+    const __nv_bfloat16* base = hi_base + pl * plane_stride;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c = lane & 3;
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (r < rows_valid) t = *reinterpret_cast<const uint4*>(base + r * ld + 8 * c);
+      *reinterpret_cast<uint4*>(stg + r * STG_LD + 4 * c) = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = *reinterpret_cast<const uint4*>(stg + lane * STG_LD + 4 * j);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = __uint_as_float(w[k] << 16), b = __uint_as_float(w[k] & 0xffff0000u);
+        if (pl == 0) { out[8 * j + 2 * k] = a; out[8 * j + 2 * k + 1] = b; }
+        else { out[8 * j + 2 * k] += a; out[8 * j + 2 * k + 1] += b; }
+      }
+    }
+  }
 }
 
-__device__ __forceinline__ void store_planes_chunk(__nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst, const float (&v)[32]) {
+// split v into bf16 hi/lo and store both planes (32 columns = 64 bytes per row and plane)
+__device__ __forceinline__ void warp_store_planes(float* stg_f, const float (&v)[32], __nv_bfloat16* hi_base,
+                                                  int64_t plane_stride, int64_t ld, int rows_valid, int lane) {
+  uint32_t* stg = reinterpret_cast<uint32_t*>(stg_f);
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -153,44 +247,74 @@ __device__ __forceinline__ void store_planes_chunk(__nv_bfloat16* hi_dst, __nv_b
     h[j] = pack_bf16x2(h0, h1);
     l[j] = pack_bf16x2(l0, l1);
   }
-  uint4* hd = reinterpret_cast<uint4*>(hi_dst);
-  uint4* ld = reinterpret_cast<uint4*>(lo_dst);
+  uint4 t[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    hd[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-    ld[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+  for (int pl = 0; pl < 2; ++pl) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) =
+          pl == 0 ? make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3])
+                  : make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c = lane & 3;
+      t[pl * 4 + it] = *reinterpret_cast<const uint4*>(stg + r * STG_LD + 4 * c);
+    }
+  }
+  // global stores last, back to back (no warp barrier between them)
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl) {
+    __nv_bfloat16* base = hi_base + pl * plane_stride;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c = lane & 3;
+      if (r < rows_valid) *reinterpret_cast<uint4*>(base + r * ld + 8 * c) = t[pl * 4 + it];
+    }
   }
 }
 
 // Each epilogue thread owns one output row (its TMEM lane) and COLS = BN/2 columns
 // (warps 2-5 take the first half of the tile's columns, warps 6-9 the second half).
+// row0 = first row of the warp's 32-row block; n0 = first column of the warp's half.
 template <int BN, bool LN>
-__device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr, int64_t row, bool row_ok, int64_t n0,
-                                               float2* xch_mine, const float2* xch_other) {
+__device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr, int64_t row0, int rows_valid, int lane,
+                                               int64_t n0, float* stg, float2* xch_mine, const float2* xch_other) {
   constexpr int COLS = BN / 2;
   const GemmEpilogue& ep = p.ep;
+  if (ep.debug & 1) rows_valid = 0;  // timing experiment: no global traffic from the epilogue
+  const bool row_ok = lane < rows_valid;
+  const int64_t row = row0 + lane;
   int code = 0;
   if (row_ok && ep.row_code) code = ep.row_code[row];
   if constexpr (LN) {
     // single pass: the thread's whole half-row lives in registers
     float v[COLS];
     tmem_ld<COLS>(taddr, v);
-    float mean_h = 0.f, m2_h = 0.f;
-    if (row_ok) {
 #pragma unroll
-      for (int c = 0; c < COLS / 32; ++c) {
-        float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
-        dense_chunk(vc, ep, row, n0 + c * 32, code);
+    for (int c = 0; c < COLS / 32; ++c) {
+      float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
+      const int64_t ncol0 = n0 + c * 32;
+      dense_chunk(vc, ep, ncol0, code);
+      if (ep.residual || ep.residual_planes) {
+        float rs[32];
+        if (ep.residual) warp_load_f32(stg, ep.residual + row0 * ep.ldr + ncol0, ep.ldr, rows_valid, lane, rs);
+        else warp_load_planes(stg, ep.residual_planes + row0 * ep.ldrp + ncol0, ep.residual_plane_stride, ep.ldrp,
+                              rows_valid, lane, rs);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vc[j] += rs[j];
       }
-      float sum = 0.f;
+    }
+    float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < COLS; ++j) sum += v[j];
-      mean_h = sum * (1.f / COLS);
+    for (int j = 0; j < COLS; ++j) sum += v[j];
+    const float mean_h = sum * (1.f / COLS);
+    float m2_h = 0.f;
 #pragma unroll
-      for (int j = 0; j < COLS; ++j) {
-        const float d = v[j] - mean_h;
-        m2_h = fmaf(d, d, m2_h);
-      }
+    for (int j = 0; j < COLS; ++j) {
+      const float d = v[j] - mean_h;
+      m2_h = fmaf(d, d, m2_h);
     }
     // combine the two halves of the row (Chan et al. pairwise update, equal counts)
     *xch_mine = make_float2(mean_h, m2_h);
@@ -200,52 +324,60 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
     const float mean = 0.5f * (mean_h + o.x);
     const float m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
     const float rstd = rsqrtf(m2 * (1.f / BN) + ep.ln_eps);
-    if (row_ok) {
 #pragma unroll
-      for (int c = 0; c < COLS / 32; ++c) {
-        float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
-        const int64_t ncol0 = n0 + c * 32;
-        if (ep.out_pre) store_f32_chunk(ep.out_pre + row * ep.ldp + ncol0, vc, 1.f);
-        const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
-        const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
+    for (int c = 0; c < COLS / 32; ++c) {
+      float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
+      const int64_t ncol0 = n0 + c * 32;
+      if (ep.out_pre) warp_store_f32(stg, vc, 1.f, ep.out_pre + row0 * ep.ldp + ncol0, ep.ldp, rows_valid, lane);
+      const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
+      const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-          vc[4 * j + 0] = (vc[4 * j + 0] - mean) * rstd * g.x + b.x;
-          vc[4 * j + 1] = (vc[4 * j + 1] - mean) * rstd * g.y + b.y;
-          vc[4 * j + 2] = (vc[4 * j + 2] - mean) * rstd * g.z + b.z;
-          vc[4 * j + 3] = (vc[4 * j + 3] - mean) * rstd * g.w + b.w;
-        }
-        if (ep.out_f32) store_f32_chunk(ep.out_f32 + row * ep.ldo + ncol0, vc, ep.out_scale);
-        if (ep.out_planes) {
-          __nv_bfloat16* hi = ep.out_planes + row * ep.ldpl + ncol0;
-          store_planes_chunk(hi, hi + ep.plane_stride, vc);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+        vc[4 * j + 0] = (vc[4 * j + 0] - mean) * rstd * g.x + b.x;
+        vc[4 * j + 1] = (vc[4 * j + 1] - mean) * rstd * g.y + b.y;
+        vc[4 * j + 2] = (vc[4 * j + 2] - mean) * rstd * g.z + b.z;
+        vc[4 * j + 3] = (vc[4 * j + 3] - mean) * rstd * g.w + b.w;
       }
+      if (ep.out_f32) warp_store_f32(stg, vc, ep.out_scale, ep.out_f32 + row0 * ep.ldo + ncol0, ep.ldo, rows_valid, lane);
+      if (ep.out_planes)
+        warp_store_planes(stg, vc, ep.out_planes + row0 * ep.ldpl + ncol0, ep.plane_stride, ep.ldpl, rows_valid, lane);
     }
   } else {
+    const bool prof = (ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
 #pragma unroll 1
     for (int c = 0; c < COLS / 32; ++c) {
       float v[32];
+      long long t0 = prof ? clock64() : 0;
       tmem_ld<32>(taddr + c * 32, v);
-      if (!row_ok) continue;
+      long long t1 = prof ? clock64() : 0;
       const int64_t ncol0 = n0 + c * 32;
-      if (ncol0 >= p.N) continue;
-      dense_chunk(v, ep, row, ncol0, code);
+      if (ncol0 >= p.N) continue;  // warp-uniform
+      dense_chunk(v, ep, ncol0, code);
+      long long t2 = prof ? clock64() : 0;
+      if (prof) { g_dbg_cycles[2] += t1 - t0; g_dbg_cycles[3] += t2 - t1; }
+      if (ep.residual || ep.residual_planes) {
+        float rs[32];
+        if (ep.residual) warp_load_f32(stg, ep.residual + row0 * ep.ldr + ncol0, ep.ldr, rows_valid, lane, rs);
+        else warp_load_planes(stg, ep.residual_planes + row0 * ep.ldrp + ncol0, ep.residual_plane_stride, ep.ldrp,
+                              rows_valid, lane, rs);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += rs[j];
+      }
       if (ep.out_f32) {
-        float* dst = ep.out_f32 + row * ep.ldo + ncol0;
         if ((ep.ldo & 3) == 0 && ncol0 + 32 <= p.N) {
-          store_f32_chunk(dst, v, ep.out_scale);
-        } else {
+          warp_store_f32(stg, v, ep.out_scale, ep.out_f32 + row0 * ep.ldo + ncol0, ep.ldo, rows_valid, lane);
+        } else if (row_ok) {
+          float* dst = ep.out_f32 + row * ep.ldo + ncol0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (ncol0 + j < p.N) dst[j] = v[j] * ep.out_scale;
         }
       }
-      if (ep.out_planes) {
-        __nv_bfloat16* hi = ep.out_planes + row * ep.ldpl + ncol0;
-        store_planes_chunk(hi, hi + ep.plane_stride, v);
-      }
+      long long t3 = prof ? clock64() : 0;
+      if (ep.out_planes)
+        warp_store_planes(stg, v, ep.out_planes + row0 * ep.ldpl + ncol0, ep.plane_stride, ep.ldpl, rows_valid, lane);
+      if (prof) { long long t4 = clock64(); g_dbg_cycles[4] += t3 - t2; g_dbg_cycles[5] += t4 - t3; }
     }
   }
 }
@@ -307,8 +439,8 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
     if (m_new > -INFINITY) {
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(v[j], scale2, -m_new));
-      s_run = s_run * exp2f(m_run - m_new) + acc;
+      for (int j = 0; j < 32; ++j) acc += fast_exp2(fmaf(v[j], scale2, -m_new));
+      s_run = s_run * fast_exp2(m_run - m_new) + acc;
       m_run = m_new;
     }
   }
@@ -326,13 +458,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                    const GemmDev p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B-swizzled tiles, done with pointer arithmetic on the
+  // __shared__ array so the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* xch = reinterpret_cast<float2*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);  // [2 parity][2 half][128]
+  float* stg_all = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + 4096);  // [8 warps][32][20]
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -447,19 +582,26 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const int tile_n = static_cast<int>(tile / tiles_m);
       const int64_t m0 = static_cast<int64_t>(tile % tiles_m) * BM;
       const int64_t n0 = static_cast<int64_t>(tile_n) * BN + half * COLS;
+      const bool prof = (p.ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
+      const long long tw0 = prof ? clock64() : 0;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after_sync();
+      const long long tw1 = prof ? clock64() : 0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(as * BN + half * COLS);
-      const int64_t row = m0 + quad * 32 + lane;
+      const int64_t row0 = m0 + quad * 32;
+      const int64_t row = row0 + lane;
       const bool row_ok = row < M_eff;
       if (HEAD) {
         epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
       } else {
         float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
         const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
-        epilogue_dense<BN, LN>(p, taddr, row, row_ok, n0, xm, xo);
+        const int64_t left = static_cast<int64_t>(M_eff) - row0;
+        const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xm, xo);
       }
+      if (prof) { g_dbg_cycles[0] += tw1 - tw0; g_dbg_cycles[1] += clock64() - tw1; g_dbg_cycles[6] += 1; }
       tile_parity ^= 1;
       tc_fence_before_sync();
       __syncwarp();
@@ -507,6 +649,13 @@ static int launch_inst(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   return 0;
 }
 
+}  // namespace t4r
+extern "C" int t4r_debug_gemm_cycles(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, t4r::g_dbg_cycles, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(t4r::g_dbg_cycles, z, sizeof(z)); }
+  return 0;
+}
+namespace t4r {
 int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stream) {
   T4R_REQUIRE(pb.M > 0 && pb.N > 0 && pb.Kp > 0 && pb.Kp % 64 == 0, "gemm: bad shape M=%lld N=%lld Kp=%d",
               (long long)pb.M, (long long)pb.N, pb.Kp);
@@ -541,6 +690,11 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   dp.nprod = pb.nprod;
   dp.m_dev = pb.m_dev;
   dp.ep = ep;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    dp.ep.debug = dbg;
+  }
   const int64_t max_tiles = ((pb.M + BM - 1) / BM) * ((pb.N + bn - 1) / bn);
 
   if (ep.head) {

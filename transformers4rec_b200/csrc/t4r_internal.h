@@ -53,6 +53,9 @@ struct GemmEpilogue {
   const float* mask_vec = nullptr;     // [N]
   const float* residual = nullptr;     // [M, ldr]
   int ldr = 0;
+  const __nv_bfloat16* residual_planes = nullptr;  // alternative residual as split planes [2, rows, ldrp] (hi + lo)
+  int ldrp = 0;
+  int64_t residual_plane_stride = 0;
   const float* ln_gamma = nullptr;     // LayerNorm over N (requires BN == N)
   const float* ln_beta = nullptr;
   float ln_eps = 0.f;
@@ -77,6 +80,7 @@ struct GemmEpilogue {
   const float* row_tgt = nullptr;      // [M] label logit (already scaled), for ranks
   int* row_rank = nullptr;             // [M] atomically accumulated
   int64_t col_offset = 0;              // global class id of column 0 (shards)
+  int debug = 0;                       // T4R_GEMM_DEBUG: 1 = epilogue skips all global loads/stores (timing experiments)
 };
 
 struct GemmProblem {

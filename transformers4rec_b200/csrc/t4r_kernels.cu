@@ -467,35 +467,36 @@ int launch_rel_pos_proj(const float* wr, int L, int d, float* r_out, cudaStream_
 //   out = softmax_j(s) @ V, written as split-bf16 planes (A operand of the O-projection).
 // Layout: qkv fp32 [B*L, 3d] (q | k | v, head h at columns h*dh..), r [2L, d].
 // A block owns one head (R staged once in shared memory) and its warps loop over
-// sessions.  Lane j owns key j (and j+32): scores live in registers, softmax is a
-// warp reduction, P@V runs with lane = output column.
+// sessions.  Lane i owns QUERY i: q_i (+ biases) lives in registers, k_j / v_j are
+// broadcast reads from shared memory, R[j+L-i] is a lane-varying row read (padded
+// stride -> conflict-free float4), the softmax over keys is a serial loop in the
+// lane (no shuffles), and P@V accumulates the lane's dh outputs in registers.
 // ============================================================================
-template <int DH, int LT, bool REL>
+template <int DH, bool REL>
 __global__ void __launch_bounds__(128)
 attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const float* __restrict__ rw,
             const float* __restrict__ rr, int B, int L, int d, int sessions_per_block,
             __nv_bfloat16* __restrict__ out_planes, int64_t plane_stride) {
-  constexpr int DP = DH + 4;    // padded row stride (floats): conflict-free float4 row reads
-  constexpr int LMAX = 32 * LT;
+  constexpr int DP = DH + 4;  // padded row stride (floats) for lane-varying float4 row reads
+  constexpr int V4 = DH / 4;
   extern __shared__ __align__(16) float sm[];
   const int h = blockIdx.y;
   const int warp = warp_id(), lane = lane_id();
   const int nwarps = blockDim.x >> 5;
-  const int Lp = ((L + 3) / 4) * 4 + 4;  // pT row stride
-  float* Rs = sm;                                                  // [2L][DP]   (REL only)
+  const int LS = L | 1;  // odd stride for the per-lane score rows
+  float* Rs = sm;                                  // [2L][DP]   (REL only)
   float* wbase = sm + (REL ? 2 * L * DP : 0);
-  const int per_warp = 2 * L * DH + L * DP + L * DH + L * Lp + LMAX;
-  float* qw = wbase + warp * per_warp;  // [L][DH]  q + r_w_bias (or q)
-  float* qr = qw + L * DH;              // [L][DH]  q + r_r_bias
-  float* ks = qr + L * DH;              // [L][DP]
-  float* vs = ks + L * DP;              // [L][DH]
-  float* pT = vs + L * DH;              // [L (j)][Lp (i)]
-  float* inv_sum = pT + L * Lp;         // [LMAX]
+  const int per_warp = L * DP + 2 * L * DH + 32 * LS;
+  float* qs = wbase + warp * per_warp;  // [L][DP]
+  float* ks = qs + L * DP;              // [L][DH]
+  float* vs = ks + L * DH;              // [L][DH]
+  float* ps = vs + L * DH;              // [32][LS] scores / probabilities of the lane's query
 
   if (REL) {
-    for (int idx = threadIdx.x; idx < 2 * L * DH; idx += blockDim.x) {
-      const int m = idx / DH, c = idx % DH;
-      Rs[m * DP + c] = __ldg(r + static_cast<int64_t>(m) * d + h * DH + c);
+    for (int idx = threadIdx.x; idx < 2 * L * V4; idx += blockDim.x) {
+      const int m = idx / V4, c = (idx % V4) * 4;
+      *reinterpret_cast<float4*>(Rs + m * DP + c) =
+          __ldg(reinterpret_cast<const float4*>(r + static_cast<int64_t>(m) * d + h * DH + c));
     }
   }
   __syncthreads();
@@ -505,10 +506,8 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
 
   for (int b = b_begin + warp; b < b_end; b += nwarps) {
     const float* base = qkv + static_cast<int64_t>(b) * L * 3 * d + h * DH;
-    // stage q (+biases), k, v for this (b, h): 16-byte loads, several rows in flight per lane
-    // (a one-load-at-a-time loop makes the whole kernel DRAM-latency bound)
-    {
-      constexpr int V4 = DH / 4;  // float4 per row
+    __syncwarp();
+    {  // stage q, k, v: 16-byte loads, several rows in flight per lane
       const int total = L * V4;
 #pragma unroll 5
       for (int idx = lane; idx < total; idx += 32) {
@@ -517,144 +516,118 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
         const float4 q4 = *reinterpret_cast<const float4*>(rowp);
         const float4 k4 = *reinterpret_cast<const float4*>(rowp + d);
         const float4 v4 = *reinterpret_cast<const float4*>(rowp + 2 * d);
-        if (REL) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(rw + h * DH + c));
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + h * DH + c));
-          *reinterpret_cast<float4*>(qw + i * DH + c) = make_float4(q4.x + w4.x, q4.y + w4.y, q4.z + w4.z, q4.w + w4.w);
-          *reinterpret_cast<float4*>(qr + i * DH + c) = make_float4(q4.x + r4.x, q4.y + r4.y, q4.z + r4.z, q4.w + r4.w);
-        } else {
-          *reinterpret_cast<float4*>(qw + i * DH + c) = q4;
-        }
-        *reinterpret_cast<float4*>(ks + i * DP + c) = k4;
+        *reinterpret_cast<float4*>(qs + i * DP + c) = q4;
+        *reinterpret_cast<float4*>(ks + i * DH + c) = k4;
         *reinterpret_cast<float4*>(vs + i * DH + c) = v4;
       }
     }
     __syncwarp();
-
-    // ---- scores: lane owns key j = lane + 32 t; raw scores go to pT[j][i]
+    float* prow = ps + lane * LS;
+    for (int qt = 0; qt * 32 < L; ++qt) {
+      const int i = lane + 32 * qt;
+      const bool iok = i < L;
+      const int ii = iok ? i : 0;
+      // q_i (+ biases) in registers
+      float4 qw[V4], qr[V4];
 #pragma unroll
-    for (int t = 0; t < LT; ++t) {
-      const int j = lane + 32 * t;
-      const bool jok = j < L;
-      float4 kreg[DH / 4];
-#pragma unroll
-      for (int c4 = 0; c4 < DH / 4; ++c4)
-        kreg[c4] = jok ? *reinterpret_cast<const float4*>(ks + j * DP + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c4 = 0; c4 < V4; ++c4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + ii * DP + 4 * c4);
+        if (REL) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(rw + h * DH + 4 * c4));
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + h * DH + 4 * c4));
+          qw[c4] = make_float4(q4.x + w4.x, q4.y + w4.y, q4.z + w4.z, q4.w + w4.w);
+          qr[c4] = make_float4(q4.x + r4.x, q4.y + r4.y, q4.z + r4.z, q4.w + r4.w);
+        } else {
+          qw[c4] = q4;
+        }
+      }
+      // ---- scores over keys j
+      float mx = -INFINITY;
 #pragma unroll 2
-      for (int i = 0; i < L; ++i) {
-        // four independent FMA chains per term (the dot product is latency-bound otherwise)
+      for (int j = 0; j < L; ++j) {
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* qwi = reinterpret_cast<const float4*>(qw + i * DH);
+        const float4* kj = reinterpret_cast<const float4*>(ks + j * DH);
 #pragma unroll
-        for (int c4 = 0; c4 < DH / 4; ++c4) {
-          const float4 a = qwi[c4];
-          a4.x = fmaf(a.x, kreg[c4].x, a4.x); a4.y = fmaf(a.y, kreg[c4].y, a4.y);
-          a4.z = fmaf(a.z, kreg[c4].z, a4.z); a4.w = fmaf(a.w, kreg[c4].w, a4.w);
+        for (int c4 = 0; c4 < V4; ++c4) {
+          const float4 kk = kj[c4];
+          a4.x = fmaf(qw[c4].x, kk.x, a4.x); a4.y = fmaf(qw[c4].y, kk.y, a4.y);
+          a4.z = fmaf(qw[c4].z, kk.z, a4.z); a4.w = fmaf(qw[c4].w, kk.w, a4.w);
         }
         float acc = (a4.x + a4.y) + (a4.z + a4.w);
         if (REL) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4* qri = reinterpret_cast<const float4*>(qr + i * DH);
-          const int m = jok ? (j + L - i) : 0;
-          const float4* rm = reinterpret_cast<const float4*>(Rs + m * DP);
+          const float4* rm = reinterpret_cast<const float4*>(Rs + (j + L - ii) * DP);
 #pragma unroll
-          for (int c4 = 0; c4 < DH / 4; ++c4) {
-            const float4 a = qri[c4];
+          for (int c4 = 0; c4 < V4; ++c4) {
             const float4 bb = rm[c4];
-            b4.x = fmaf(a.x, bb.x, b4.x); b4.y = fmaf(a.y, bb.y, b4.y);
-            b4.z = fmaf(a.z, bb.z, b4.z); b4.w = fmaf(a.w, bb.w, b4.w);
+            b4.x = fmaf(qr[c4].x, bb.x, b4.x); b4.y = fmaf(qr[c4].y, bb.y, b4.y);
+            b4.z = fmaf(qr[c4].z, bb.z, b4.z); b4.w = fmaf(qr[c4].w, bb.w, b4.w);
           }
           acc += (b4.x + b4.y) + (b4.z + b4.w);
         }
         acc *= scale;
-        if (!REL && j > i) acc = -INFINITY;
-        if (jok) pT[j * Lp + i] = acc;
+        if (!REL && j > ii) acc = -INFINITY;
+        prow[j] = acc;
+        mx = fmaxf(mx, acc);
       }
-    }
-    __syncwarp();
-    // ---- softmax over keys (across lanes) for each query i; exp() overwrites the score
-#pragma unroll 1
-    for (int i = 0; i < L; ++i) {
-      float v[LT];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int t = 0; t < LT; ++t) {
-        const int j = lane + 32 * t;
-        v[t] = (j < L) ? pT[j * Lp + i] : -INFINITY;
-        mx = fmaxf(mx, v[t]);
-      }
-      mx = warp_max(mx);
+      // ---- softmax (serial in the lane)
       float sum = 0.f;
-#pragma unroll
-      for (int t = 0; t < LT; ++t) {
-        const int j = lane + 32 * t;
-        const float e = (v[t] == -INFINITY) ? 0.f : expf(v[t] - mx);
-        sum += e;
-        if (j < L) pT[j * Lp + i] = e;
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) inv_sum[i] = 1.f / sum;
-    }
-    __syncwarp();
-    // ---- out[i, c] = sum_j p[i, j] v[j, c]; lane owns column(s) c
-#pragma unroll
-    for (int ct = 0; ct < (DH + 31) / 32; ++ct) {
-      const int c = lane + 32 * ct;
-      const bool cok = c < DH;
-      float acc[LMAX];
-#pragma unroll
-      for (int i = 0; i < LMAX; ++i) acc[i] = 0.f;
       for (int j = 0; j < L; ++j) {
-        const float vj = cok ? vs[j * DH + c] : 0.f;
-        const float4* pj = reinterpret_cast<const float4*>(pT + j * Lp);
+        const float sj = prow[j];
+        const float e = (sj == -INFINITY) ? 0.f : expf(sj - mx);
+        prow[j] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      // ---- out_i = sum_j p_ij v_j
+      float4 o[V4];
 #pragma unroll
-        for (int i4 = 0; i4 < LMAX / 4; ++i4) {
-          if (4 * i4 < L) {
-            const float4 pp = pj[i4];
-            acc[4 * i4 + 0] = fmaf(pp.x, vj, acc[4 * i4 + 0]);
-            acc[4 * i4 + 1] = fmaf(pp.y, vj, acc[4 * i4 + 1]);
-            acc[4 * i4 + 2] = fmaf(pp.z, vj, acc[4 * i4 + 2]);
-            acc[4 * i4 + 3] = fmaf(pp.w, vj, acc[4 * i4 + 3]);
-          }
+      for (int c4 = 0; c4 < V4; ++c4) o[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int j = 0; j < L; ++j) {
+        const float pj = prow[j];
+        const float4* vj = reinterpret_cast<const float4*>(vs + j * DH);
+#pragma unroll
+        for (int c4 = 0; c4 < V4; ++c4) {
+          const float4 vv = vj[c4];
+          o[c4].x = fmaf(pj, vv.x, o[c4].x); o[c4].y = fmaf(pj, vv.y, o[c4].y);
+          o[c4].z = fmaf(pj, vv.z, o[c4].z); o[c4].w = fmaf(pj, vv.w, o[c4].w);
         }
       }
-      if (cok) {
+      if (iok) {
+        __nv_bfloat16* hi = out_planes + (static_cast<int64_t>(b) * L + i) * d + h * DH;
+        __nv_bfloat16* lo = hi + plane_stride;
 #pragma unroll
-        for (int i = 0; i < LMAX; ++i) {
-          if (i < L) {
-            const float o = acc[i] * inv_sum[i];
-            __nv_bfloat16 hi, lo;
-            split_bf16(o, hi, lo);
-            const int64_t off = (static_cast<int64_t>(b) * L + i) * d + h * DH + c;
-            out_planes[off] = hi;
-            out_planes[off + plane_stride] = lo;
-          }
+        for (int c4 = 0; c4 < V4; ++c4) {
+          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+          split_bf16(o[c4].x * inv, h0, l0); split_bf16(o[c4].y * inv, h1, l1);
+          split_bf16(o[c4].z * inv, h2, l2); split_bf16(o[c4].w * inv, h3, l3);
+          *reinterpret_cast<uint2*>(hi + 4 * c4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+          *reinterpret_cast<uint2*>(lo + 4 * c4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
         }
       }
     }
-    __syncwarp();
   }
 }
 
-template <int DH, int LT, bool REL>
+template <int DH, bool REL>
 static int launch_attn_inst(const float* qkv, const float* r, const float* rw, const float* rr, int B, int L, int d,
                             int H, __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s) {
   constexpr int DP = DH + 4;
-  const int Lp = ((L + 3) / 4) * 4 + 4;
-  const int per_warp = 2 * L * DH + L * DP + L * DH + L * Lp + 32 * LT;
+  const int LS = L | 1;
+  const int per_warp = L * DP + 2 * L * DH + 32 * LS;
   const int r_floats = REL ? 2 * L * DP : 0;
   int warps = 4;
   while (warps > 1 && (r_floats + warps * per_warp) * 4 > 200 * 1024) warps >>= 1;
   const size_t smem = static_cast<size_t>(r_floats + warps * per_warp) * 4;
   T4R_REQUIRE(smem <= 220 * 1024, "attention: L=%d dh=%d needs %zu bytes of shared memory", L, DH, smem);
-  auto kern = attn_kernel<DH, LT, REL>;
+  auto kern = attn_kernel<DH, REL>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
   // sessions per block: R staging is small (2L x dh floats), so favour many resident warps
-  // (the per-session work is a chain of short dependent phases) over amortising it
   int spb = 2 * warps;
   while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
   dim3 grid((B + spb - 1) / spb, H);
@@ -669,16 +642,9 @@ static int launch_attn_any(const float* qkv, const float* r, const float* rw, co
   T4R_REQUIRE(d % H == 0, "attention: d_model %d not divisible by n_head %d", d, H);
   const int dh = d / H;
   T4R_REQUIRE(L >= 1 && L <= 64, "attention: sequence length %d not supported (1..64)", L);
-  const int lt = (L <= 32) ? 1 : 2;
-#define T4R_ATTN_CASE(DHV)                                                                               \
-  if (dh == DHV) {                                                                                       \
-    if (lt == 1) return launch_attn_inst<DHV, 1, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s); \
-    return launch_attn_inst<DHV, 2, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);       \
-  }
-  T4R_ATTN_CASE(16)
-  T4R_ATTN_CASE(32)
-  T4R_ATTN_CASE(64)
-#undef T4R_ATTN_CASE
+  if (dh == 16) return launch_attn_inst<16, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);
+  if (dh == 32) return launch_attn_inst<32, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);
+  if (dh == 64) return launch_attn_inst<64, REL>(qkv, r, rw, rr, B, L, d, H, out_planes, plane_stride, s);
   set_error("attention: head dim %d not supported (16, 32, 64)", dh);
   return T4R_ERR_UNSUPPORTED;
 }
