@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -219,6 +219,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # started before warm-up so samples exist even for a short timed region
     for _ in range(max(args.warmup, 3)):
         step(batch_dev)
     barrier()
@@ -229,9 +232,8 @@ def main():
     for a, b in evs:  # torch creates the cudaEvent_t lazily: record once so .cuda_event is a live handle
         a.record(); b.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.lines.clear()  # keep only samples taken during the timed region (load already applied)
     n0 = lib.t4r_launch_count()
     barrier()
     e0.record()

@@ -144,6 +144,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same for rows of 64 bytes with the 64-byte swizzle (TMA SWIZZLE_64B, 32 bf16 per row):
+// layout type 4, stride byte offset = 8 rows * 64 B = 512.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+template <int RB>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return RB == 128 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
+}
 // Instruction descriptor, kind::f16: A,B = bf16 (format 1), D = f32 (format 1),
 // both operands K-major, M = 128, N = n.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {

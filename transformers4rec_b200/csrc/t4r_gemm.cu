@@ -45,8 +45,8 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, Kp] row-major, box = [box_rows, 64] with 128B swizzle.
-static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows) {
+// 2-D bf16 tensor [rows, Kp] row-major, box = [box_rows, rb/2 elements] with rb-byte swizzle.
+static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows, int rb) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -58,10 +58,11 @@ static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(Kp) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(rb / 2), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld Kp=%d box_rows=%d", (int)r, (long long)rows, Kp,
@@ -75,13 +76,18 @@ static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
 // kernel
 // ----------------------------------------------------------------------------
 constexpr int BM = 128;
-constexpr int A_PLANE_BYTES = BM * 128;  // 128 rows x 64 bf16
 
-template <int BN>
+// RB = bytes per shared-memory operand row = K extent of one pipeline stage (RB/2 bf16).
+// RB = 64 (SWIZZLE_64B) halves the stage and doubles the ring depth in the same shared memory
+// (4 stages of look-ahead instead of 2 at BN = 256).  Both variants are kept: they measure the
+// same on B200, see launch_gemm.
+template <int BN, int RB>
 struct GemmCfg {
-  static constexpr int B_PLANE_BYTES = BN * 128;
+  static constexpr int A_PLANE_BYTES = BM * RB;
+  static constexpr int B_PLANE_BYTES = BN * RB;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);
+  static constexpr int STAGES = (RB == 64) ? 4 : ((BN == 256) ? 2 : ((BN == 128) ? 3 : 4));
+  static constexpr int KSTEPS = RB / 32;   // UMMA K = 16 bf16 = 32 bytes
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (power of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*LN exchange*/ + 8 * 32 * 20 * 4 /*epilogue staging*/;
 };
@@ -451,12 +457,13 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   }
 }
 
-template <int BN, bool LN, bool HEAD>
+template <int BN, bool LN, bool HEAD, int RB>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RB>;
+  constexpr int A_PLANE_BYTES = Cfg::A_PLANE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles, done with pointer arithmetic on the
   // __shared__ array so the compiler keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -517,11 +524,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          tma_load_2d(st, &tmAh, &full_bar[stage], kb * 64, m0);
-          tma_load_2d(st + 2 * A_PLANE_BYTES, &tmBh, &full_bar[stage], kb * 64, n0);
+          constexpr int KE = RB / 2;  // bf16 elements of K per stage
+          tma_load_2d(st, &tmAh, &full_bar[stage], kb * KE, m0);
+          tma_load_2d(st + 2 * A_PLANE_BYTES, &tmBh, &full_bar[stage], kb * KE, n0);
           if (p.nprod == 3) {
-            tma_load_2d(st + A_PLANE_BYTES, &tmAl, &full_bar[stage], kb * 64, m0);
-            tma_load_2d(st + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tmBl, &full_bar[stage], kb * 64, n0);
+            tma_load_2d(st + A_PLANE_BYTES, &tmAl, &full_bar[stage], kb * KE, m0);
+            tma_load_2d(st + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tmBl, &full_bar[stage], kb * KE, n0);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -548,12 +556,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
           const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32);
-            const uint64_t db_hi = umma_desc_sw128(b_hi + k4 * 32);
+          for (int k4 = 0; k4 < Cfg::KSTEPS; ++k4) {
+            const uint64_t da_hi = umma_desc<RB>(a_hi + k4 * 32);
+            const uint64_t db_hi = umma_desc<RB>(b_hi + k4 * 32);
             if (p.nprod == 3) {
-              const uint64_t da_lo = umma_desc_sw128(a_lo + k4 * 32);
-              const uint64_t db_lo = umma_desc_sw128(b_lo + k4 * 32);
+              const uint64_t da_lo = umma_desc<RB>(a_lo + k4 * 32);
+              const uint64_t db_lo = umma_desc<RB>(b_lo + k4 * 32);
               umma_bf16(d_tmem, da_lo, db_hi, idesc, (kb | k4) != 0);
               umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
               umma_bf16(d_tmem, da_hi, db_hi, idesc, 1u);
@@ -632,11 +640,11 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool LN, bool HEAD>
+template <int BN, bool LN, bool HEAD, int RB>
 static int launch_inst(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const GemmDev& dp, int64_t max_tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16x3_kernel<BN, LN, HEAD>;
+  using Cfg = GemmCfg<BN, RB>;
+  auto kern = gemm_bf16x3_kernel<BN, LN, HEAD, RB>;
   static bool attr_set = false;
   if (!attr_set) {
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -677,16 +685,21 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   }
   T4R_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
 
+  // Row width of the shared-memory operand tiles.  Default 128 B (2 x 96 KB stages at BN = 256);
+  // T4R_GEMM_RB=64 selects 64-byte rows (4 x 48 KB stages).  Measured equal on B200 (head GEMM
+  // 4.98 ms vs 5.15 ms): the kernel runs at the power-capped tensor rate, not on TMA latency.
+  static int rb = 0;
+  if (rb == 0) { const char* e = getenv("T4R_GEMM_RB"); rb = (e && atoi(e) == 64) ? 64 : 128; }
   CUtensorMap ah, al, bh, bl;
-  T4R_TRY(make_tmap(&ah, pb.a_planes, pb.M, pb.Kp, BM));
-  T4R_TRY(make_tmap(&al, pb.a_planes + pb.a_rows * pb.Kp, pb.M, pb.Kp, BM));
-  T4R_TRY(make_tmap(&bh, pb.b_planes, pb.N, pb.Kp, bn));
-  T4R_TRY(make_tmap(&bl, pb.b_planes + pb.b_rows * pb.Kp, pb.N, pb.Kp, bn));
+  T4R_TRY(make_tmap(&ah, pb.a_planes, pb.M, pb.Kp, BM, rb));
+  T4R_TRY(make_tmap(&al, pb.a_planes + pb.a_rows * pb.Kp, pb.M, pb.Kp, BM, rb));
+  T4R_TRY(make_tmap(&bh, pb.b_planes, pb.N, pb.Kp, bn, rb));
+  T4R_TRY(make_tmap(&bl, pb.b_planes + pb.b_rows * pb.Kp, pb.N, pb.Kp, bn, rb));
 
   GemmDev dp;
   dp.M = static_cast<int>(pb.M);
   dp.N = pb.N;
-  dp.nkb = pb.Kp / 64;
+  dp.nkb = pb.Kp / (rb / 2);
   dp.nprod = pb.nprod;
   dp.m_dev = pb.m_dev;
   dp.ep = ep;
@@ -697,19 +710,25 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   }
   const int64_t max_tiles = ((pb.M + BM - 1) / BM) * ((pb.N + bn - 1) / bn);
 
-  if (ep.head) {
-    if (bn == 256) return launch_inst<256, false, true>(ah, al, bh, bl, dp, max_tiles, stream);
-    if (bn == 128) return launch_inst<128, false, true>(ah, al, bh, bl, dp, max_tiles, stream);
-    return launch_inst<64, false, true>(ah, al, bh, bl, dp, max_tiles, stream);
-  }
-  if (ln) {
-    if (bn == 256) return launch_inst<256, true, false>(ah, al, bh, bl, dp, max_tiles, stream);
-    if (bn == 128) return launch_inst<128, true, false>(ah, al, bh, bl, dp, max_tiles, stream);
-    return launch_inst<64, true, false>(ah, al, bh, bl, dp, max_tiles, stream);
-  }
-  if (bn == 256) return launch_inst<256, false, false>(ah, al, bh, bl, dp, max_tiles, stream);
-  if (bn == 128) return launch_inst<128, false, false>(ah, al, bh, bl, dp, max_tiles, stream);
-  return launch_inst<64, false, false>(ah, al, bh, bl, dp, max_tiles, stream);
+#define T4R_GEMM_DISPATCH(RBV)                                                                              \
+  do {                                                                                                      \
+    if (ep.head) {                                                                                          \
+      if (bn == 256) return launch_inst<256, false, true, RBV>(ah, al, bh, bl, dp, max_tiles, stream);      \
+      if (bn == 128) return launch_inst<128, false, true, RBV>(ah, al, bh, bl, dp, max_tiles, stream);      \
+      return launch_inst<64, false, true, RBV>(ah, al, bh, bl, dp, max_tiles, stream);                      \
+    }                                                                                                       \
+    if (ln) {                                                                                               \
+      if (bn == 256) return launch_inst<256, true, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);      \
+      if (bn == 128) return launch_inst<128, true, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);      \
+      return launch_inst<64, true, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);                      \
+    }                                                                                                       \
+    if (bn == 256) return launch_inst<256, false, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);       \
+    if (bn == 128) return launch_inst<128, false, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);       \
+    return launch_inst<64, false, false, RBV>(ah, al, bh, bl, dp, max_tiles, stream);                       \
+  } while (0)
+  if (rb == 64) T4R_GEMM_DISPATCH(64);
+  T4R_GEMM_DISPATCH(128);
+#undef T4R_GEMM_DISPATCH
 }
 
 }  // namespace t4r
