@@ -3,6 +3,7 @@
 // every launch goes to the caller's stream, nothing synchronises.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "t4r_common.cuh"
@@ -134,7 +135,8 @@ extern "C" size_t t4r_xlnet_encoder_workspace_bytes(int B, int L, int d, int n_h
   const size_t M = static_cast<size_t>(B) * L;
   size_t b = 0;
   b += pad256(M * 3 * d * 4);        // qkv fp32
-  b += pad256(static_cast<size_t>(2) * L * d * 4);  // r
+  b += pad256(static_cast<size_t>(T4R_MAX_FEATURES) * 2 * L * d * 4);      // r, all layers
+  b += pad256(static_cast<size_t>(T4R_MAX_FEATURES) * 2 * 2 * L * d * 2);  // r planes, all layers
   b += pad256(2 * M * d * 2);        // attention output planes
   b += pad256(M * d * 4);            // h1 fp32
   b += pad256(2 * M * d * 2);        // h1 planes
@@ -154,9 +156,15 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
   const int64_t M = static_cast<int64_t>(B) * L;
   Arena ar(workspace, workspace_bytes);
   float* qkv = ar.take<float>(M * 3 * d);
-  float* rbuf = ar.take<float>(static_cast<size_t>(2) * L * d);
+  float* rbuf = ar.take<float>(static_cast<size_t>(T4R_MAX_FEATURES) * 2 * L * d);
+  __nv_bfloat16* r_p = ar.take<__nv_bfloat16>(static_cast<size_t>(T4R_MAX_FEATURES) * 2 * 2 * L * d);
   __nv_bfloat16* attn_p = ar.take<__nv_bfloat16>(2 * M * d);
   float* h1 = ar.take<float>(M * d);
+  // tensor-path attention (mma.sync) consumes q|k|v as split planes; the SIMT kernel (L > 30) fp32
+  static int force_simt = -1;
+  if (force_simt < 0) { const char* e = getenv("T4R_ATTN_SIMT"); force_simt = (e && atoi(e)) ? 1 : 0; }
+  const bool tc_attn = !force_simt && attn_mma_supported(L, d, n_head, true);
+  __nv_bfloat16* qkv_p = reinterpret_cast<__nv_bfloat16*>(qkv);  // same bytes: [2, M, 3d] bf16
   __nv_bfloat16* h1_p = ar.take<__nv_bfloat16>(2 * M * d);
   __nv_bfloat16* ff_p = ar.take<__nv_bfloat16>(2 * M * 4 * d);
   __nv_bfloat16* x_p_own = ar.take<__nv_bfloat16>(2 * M * d);
@@ -174,9 +182,19 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
     T4R_TRY(launch_split_planes(x_f32, M, d, d, nullptr, nullptr, nullptr, x_p_own, s));
     cur_p = x_p_own;
   }
+  // R_l = pos_emb @ Wr_l (HF:xlnet:262) depends on the weights only: all layers in one launch, once
+  // per forward for the whole batch (the reference recomputes it per batch element and layer)
+  T4R_REQUIRE(n_layer <= T4R_MAX_FEATURES, "xlnet_encoder: at most %d layers", T4R_MAX_FEATURES);
+  {
+    const float* wrs[T4R_MAX_FEATURES];
+    for (int li = 0; li < n_layer; ++li) wrs[li] = layers[li].wr;
+    T4R_TRY(launch_rel_pos_proj(wrs, n_layer, L, d, rbuf, tc_attn ? r_p : nullptr, s));
+  }
   for (int li = 0; li < n_layer; ++li) {
     const t4r_xlnet_layer& w = layers[li];
     const bool last = (li == n_layer - 1);
+    const float* rbuf_l = rbuf + static_cast<size_t>(li) * 2 * L * d;
+    const __nv_bfloat16* r_p_l = r_p + static_cast<size_t>(li) * 4 * L * d;
     // Q | K | V projections (HF:xlnet:253-259), one GEMM over the fused [3d, d] weight
     {
       GemmProblem pb;
@@ -184,13 +202,16 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
       pb.a_planes = cur_p; pb.a_rows = M;
       pb.b_planes = static_cast<const __nv_bfloat16*>(w.wqkv_planes); pb.b_rows = 3 * d;
       GemmEpilogue ep;
-      ep.out_f32 = qkv; ep.ldo = 3 * d;
+      if (tc_attn) { ep.out_planes = qkv_p; ep.ldpl = 3 * d; ep.plane_stride = M * 3 * d; }
+      else { ep.out_f32 = qkv; ep.ldo = 3 * d; }
       T4R_TRY(launch_gemm(pb, ep, s));
     }
-    // R = pos_emb @ Wr (HF:xlnet:262), once per layer for the whole batch
-    T4R_TRY(launch_rel_pos_proj(w.wr, L, d, rbuf, s));
     // relative attention core (HF:xlnet:95-140)
-    T4R_TRY(launch_xlnet_attn(qkv, rbuf, w.r_w_bias, w.r_r_bias, B, L, d, n_head, attn_p, M * d, s));
+    if (tc_attn)
+      T4R_TRY(launch_attn_mma(true, qkv_p, M * 3 * d, r_p_l, static_cast<int64_t>(2) * L * d, w.r_w_bias, w.r_r_bias, B,
+                              L, d, n_head, attn_p, M * d, s));
+    else
+      T4R_TRY(launch_xlnet_attn(qkv, rbuf_l, w.r_w_bias, w.r_r_bias, B, L, d, n_head, attn_p, M * d, s));
     // post_attention: h1 = LN(x + attn @ Wo^T) (HF:xlnet:142-152)
     {
       GemmProblem pb;
@@ -272,6 +293,10 @@ extern "C" int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers, int n_layer, i
   float* hbuf[2] = {ar.take<float>(M * d), ar.take<float>(M * d)};
   __nv_bfloat16* lnp[2] = {ar.take<__nv_bfloat16>(2 * M * d), ar.take<__nv_bfloat16>(2 * M * d)};
   T4R_REQUIRE(ar.ok, "gpt2_encoder: workspace carve-up failed");
+  static int force_simt = -1;
+  if (force_simt < 0) { const char* e = getenv("T4R_ATTN_SIMT"); force_simt = (e && atoi(e)) ? 1 : 0; }
+  const bool tc_attn = !force_simt && attn_mma_supported(L, d, n_head, false);
+  __nv_bfloat16* qkv_p = reinterpret_cast<__nv_bfloat16*>(qkv);
 
   // h = x + wpe[0:L]; a = ln_1^{(0)}(h)   (HF:gpt2:579-585, :272)
   int hc = 0, pc = 0;
@@ -287,10 +312,14 @@ extern "C" int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers, int n_layer, i
       pb.b_planes = static_cast<const __nv_bfloat16*>(w.wqkv_planes); pb.b_rows = 3 * d;
       GemmEpilogue ep;
       ep.bias = w.bqkv;
-      ep.out_f32 = qkv; ep.ldo = 3 * d;
+      if (tc_attn) { ep.out_planes = qkv_p; ep.ldpl = 3 * d; ep.plane_stride = M * 3 * d; }
+      else { ep.out_f32 = qkv; ep.ldo = 3 * d; }
       T4R_TRY(launch_gemm(pb, ep, s));
     }
-    T4R_TRY(launch_causal_attn(qkv, B, L, d, n_head, attn_p, M * d, s));
+    if (tc_attn)
+      T4R_TRY(launch_attn_mma(false, qkv_p, M * 3 * d, nullptr, 0, nullptr, nullptr, B, L, d, n_head, attn_p, M * d, s));
+    else
+      T4R_TRY(launch_causal_attn(qkv, B, L, d, n_head, attn_p, M * d, s));
     {  // h = h + attn c_proj + b; m = ln_2(h)   (HF:gpt2:284-290)
       GemmProblem pb;
       pb.M = M; pb.N = d; pb.Kp = d;

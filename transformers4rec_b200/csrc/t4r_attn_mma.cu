@@ -1,0 +1,367 @@
+// t4r_attn_mma.cu -- K5 on the warp-level tensor path (mma.sync m16n8k16 bf16, fp32 accumulate).
+//
+// One warp owns one (session, head).  L <= 32 keys/queries are padded to a 32 x 32 problem:
+//   S1 = Qaug K^T            (32 x 32, k = dh)       Qaug = [q_0..q_{L-1}; r_w_bias; r_r_bias; 0...]
+//   S2 = Qaug R^T            (32 x 2L, k = dh)       XLNet only
+//   s[i,j] = (S1[i,j] + S1[L,j] + S2[i,j+L-i] + S2[L+1,j+L-i]) / sqrt(dh)
+//            = ((q_i + r_w_bias).k_j + (q_i + r_r_bias).R[j+L-i]) / sqrt(dh)      HF:xlnet:95-140, rel_shift :81-93
+//   P = softmax_j(s)  (no mask for XLNet 'bi'; j <= i for GPT-2, HF:gpt2:54-72)
+//   O = P V           (32 x dh, k = 32)
+// Appending the two bias vectors as extra query rows turns the bias terms into two more rows of
+// the same products, so every operand is a raw split-bf16 plane written by the QKV GEMM epilogue /
+// the positional projection.  All products are issued three times (hi*hi + hi*lo + lo*hi) like
+// the tcgen05 GEMMs, so the result stays fp32-grade.  The S1 accumulator fragments are reused in
+// place as the A operand of P V (C-fragment layout == A-fragment layout of two 8-wide tiles);
+// only S2 takes a shared-memory round trip (the relative shift moves data across lanes).
+#include <math.h>
+
+#include "t4r_common.cuh"
+#include "t4r_internal.h"
+
+namespace t4r {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// three split products: c += a_lo b_hi + a_hi b_lo + a_hi b_hi
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_bf16(c, al, bh);
+  mma_bf16(c, ah, bl);
+  mma_bf16(c, ah, bh);
+}
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 h0, l0, h1, l1;
+  split_bf16(x, h0, l0);
+  split_bf16(y, h1, l1);
+  hi = pack_bf16x2(h0, h1);
+  lo = pack_bf16x2(l0, l1);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Shared-memory tiles hold only the L (+2) real rows; every ldmatrix row address beyond them
+// points at one shared all-zero row, so the per-warp footprint stays small enough for 3-4
+// blocks per SM (the kernel is latency-bound: one cp.async batch + ~2k instructions per session).
+template <int DH, bool REL>
+__global__ void __launch_bounds__(128)
+attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride, const __nv_bfloat16* __restrict__ rpl,
+                int64_t r_plane_stride, const float* __restrict__ rw, const float* __restrict__ rr, int B, int L, int d,
+                int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride) {
+  constexpr int LDS = DH + 8;            // row stride (bf16): 16-byte rows, conflict-free ldmatrix
+  constexpr int KT = DH / 16;            // k tiles of the q.k / q.R products
+  constexpr int NTC = DH / 8;            // n tiles of the P V product
+  constexpr int C8 = DH / 8;             // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t smem_a[];
+  const int h = blockIdx.y;
+  const int warp = warp_id(), lane = lane_id();
+  const int nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int QR = REL ? L + 2 : L;                    // query rows incl. the two bias rows
+  const int RR = 2 * L;                              // rows of R
+  const int S2LD = ((2 * L + 7) / 8) * 8 + 1;        // fp32 stride of the shifted-term scratch
+  // block-shared: zero row, R planes; per warp: Q, K, V planes and the S2 scratch
+  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(smem_a);                  // [LDS]
+  __nv_bfloat16* Rs = zrow + LDS;                                                   // [2][RR][LDS]
+  const int warp_elems = 2 * QR * LDS + 4 * L * LDS;
+  const int s2_floats = REL ? QR * S2LD : 0;
+  uint8_t* wbase = smem_a + (LDS + (REL ? 2 * RR * LDS : 0)) * 2;
+  wbase += static_cast<size_t>(warp) * (((warp_elems * 2 + s2_floats * 4) + 15) / 16 * 16);
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(wbase);   // [2][QR][LDS]
+  __nv_bfloat16* Ks = Qs + 2 * QR * LDS;                         // [2][L][LDS]
+  __nv_bfloat16* Vs = Ks + 2 * L * LDS;                          // [2][L][LDS]
+  float* S2s = reinterpret_cast<float*>(Vs + 2 * L * LDS);       // [QR][S2LD]
+  const uint32_t zaddr = smem_u32(zrow);
+
+  for (int c = threadIdx.x; c < LDS; c += blockDim.x) zrow[c] = __float2bfloat16_rn(0.f);
+  if (REL) {
+    for (int idx = threadIdx.x; idx < 2 * RR * C8; idx += blockDim.x) {
+      const int pl = idx / (RR * C8), rem = idx % (RR * C8);
+      const int m = rem / C8, c8 = rem % C8;
+      *reinterpret_cast<uint4*>(Rs + (pl * RR + m) * LDS + 8 * c8) =
+          __ldg(reinterpret_cast<const uint4*>(rpl + pl * r_plane_stride + static_cast<int64_t>(m) * d + h * DH + 8 * c8));
+    }
+  }
+  __syncthreads();
+  const float scale = rsqrtf(static_cast<float>(DH));
+  const int b_begin = blockIdx.x * sessions_per_block;
+  const int b_end = min(B, b_begin + sessions_per_block);
+
+  for (int b = b_begin + warp; b < b_end; b += nwarps) {
+    __syncwarp();
+    // ---- stage q, k, v planes with one batch of 16-byte cp.async per lane
+    {
+      const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * L * 3 * d + h * DH;
+      for (int idx = lane; idx < 2 * L * C8; idx += 32) {
+        const int pl = idx / (L * C8), rem = idx % (L * C8);
+        const int i = rem / C8, c8 = rem % C8;
+        const __nv_bfloat16* rowp = base + pl * qkv_plane_stride + static_cast<int64_t>(i) * 3 * d + 8 * c8;
+        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp);
+        cp_async16(smem_u32(Ks + (pl * L + i) * LDS + 8 * c8), rowp + d);
+        cp_async16(smem_u32(Vs + (pl * L + i) * LDS + 8 * c8), rowp + 2 * d);
+      }
+      if (REL) {
+        // query rows L and L+1 carry r_w_bias / r_r_bias (split on the fly)
+        for (int c = lane; c < DH; c += 32) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(__ldg(rw + h * DH + c), hi, lo);
+          Qs[(0 * QR + L) * LDS + c] = hi;
+          Qs[(1 * QR + L) * LDS + c] = lo;
+          split_bf16(__ldg(rr + h * DH + c), hi, lo);
+          Qs[(0 * QR + L + 1) * LDS + c] = hi;
+          Qs[(1 * QR + L + 1) * LDS + c] = lo;
+        }
+      }
+      cp_async_wait_all();
+    }
+    __syncwarp();
+
+    // ---- A fragments of Qaug
+    uint32_t aq[2][2][KT][4];  // [plane][m tile][k tile]
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt)
+        {
+          const int row = mt * 16 + (lane & 15);
+          const int col = kt * 16 + (lane >> 4) * 8;
+          ldsm_x4(aq[pl][mt][kt], row < QR ? smem_u32(Qs + (pl * QR + row) * LDS + col) : zaddr);
+        }
+
+    // ---- S1 = Qaug K^T
+    float s1[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s1[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        uint32_t bh[2], bl[2];
+        const int row = nt * 8 + (lane & 7);
+        const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x2(bh, row < L ? smem_u32(Ks + row * LDS + col) : zaddr);
+        ldsm_x2(bl, row < L ? smem_u32(Ks + (L + row) * LDS + col) : zaddr);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma3(s1[mt][nt], aq[0][mt][kt], aq[1][mt][kt], bh, bl);
+      }
+
+    if (REL) {
+      // ---- S2 = Qaug R^T -> scratch
+      const int nt2_max = (2 * L + 7) / 8;
+#pragma unroll 1
+      for (int nt2 = 0; nt2 < nt2_max; ++nt2) {
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          uint32_t bh[2], bl[2];
+          const int row = nt2 * 8 + (lane & 7);
+          const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x2(bh, row < RR ? smem_u32(Rs + row * LDS + col) : zaddr);
+          ldsm_x2(bl, row < RR ? smem_u32(Rs + (RR + row) * LDS + col) : zaddr);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma3(acc[mt], aq[0][mt][kt], aq[1][mt][kt], bh, bl);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int col = nt2 * 8 + 2 * t;
+          const int r0 = mt * 16 + g, r1 = r0 + 8;
+          if (r0 < QR) { S2s[r0 * S2LD + col] = acc[mt][0]; S2s[r0 * S2LD + col + 1] = acc[mt][1]; }
+          if (r1 < QR) { S2s[r1 * S2LD + col] = acc[mt][2]; S2s[r1 * S2LD + col + 1] = acc[mt][3]; }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- scores -> probabilities (in place in s1)
+    const int mtL = L >> 4, rL = L & 15;             // where query row L (r_w_bias) sits in the fragments
+    const int srcL = ((rL & 7) << 2) | t;
+    float rmax[2][2], rsum[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) rmax[mt][hf] = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float wb0 = 0.f, wb1 = 0.f;
+      if (REL) {
+        // (r_w_bias . k_j) for this lane's two columns: row L of S1, held by lane 4*(rL%8)+t
+        const float v0 = (mtL == 0) ? ((rL < 8) ? s1[0][nt][0] : s1[0][nt][2]) : ((rL < 8) ? s1[1][nt][0] : s1[1][nt][2]);
+        const float v1 = (mtL == 0) ? ((rL < 8) ? s1[0][nt][1] : s1[0][nt][3]) : ((rL < 8) ? s1[1][nt][1] : s1[1][nt][3]);
+        wb0 = __shfl_sync(0xffffffffu, v0, srcL);
+        wb1 = __shfl_sync(0xffffffffu, v1, srcL);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = mt * 16 + g + ((e >> 1) << 3);
+          const int j = nt * 8 + 2 * t + (e & 1);
+          float v = s1[mt][nt][e];
+          if (REL) {
+            const int ii = i < L ? i : 0;
+            const int jj = j < L ? j : 0;
+            const int m = jj + L - ii;
+            v += ((e & 1) ? wb1 : wb0) + S2s[ii * S2LD + m] + S2s[(L + 1) * S2LD + m];
+          }
+          v *= scale;
+          if (j >= L || (!REL && j > i)) v = -INFINITY;
+          s1[mt][nt][e] = v;
+          rmax[mt][e >> 1] = fmaxf(rmax[mt][e >> 1], v);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float m = rmax[mt][hf];
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        rmax[mt][hf] = m;
+        rsum[mt][hf] = 0.f;
+      }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = s1[mt][nt][e];
+          const float p = (v == -INFINITY) ? 0.f : expf(v - rmax[mt][e >> 1]);
+          s1[mt][nt][e] = p;
+          rsum[mt][e >> 1] += p;
+        }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float sm = rsum[mt][hf];
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        rsum[mt][hf] = (sm > 0.f) ? 1.f / sm : 0.f;
+      }
+
+    // ---- O = P V : S1's C fragments are the A fragments of P (two 8-wide tiles per k tile)
+    float o[2][NTC][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nc = 0; nc < NTC; ++nc)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[mt][nc][e] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+      uint32_t ph[2][4], plo[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        split_pair(s1[mt][2 * kt][0], s1[mt][2 * kt][1], ph[mt][0], plo[mt][0]);
+        split_pair(s1[mt][2 * kt][2], s1[mt][2 * kt][3], ph[mt][1], plo[mt][1]);
+        split_pair(s1[mt][2 * kt + 1][0], s1[mt][2 * kt + 1][1], ph[mt][2], plo[mt][2]);
+        split_pair(s1[mt][2 * kt + 1][2], s1[mt][2 * kt + 1][3], ph[mt][3], plo[mt][3]);
+      }
+#pragma unroll
+      for (int nc = 0; nc < NTC; ++nc) {
+        uint32_t bh[2], bl[2];
+        const int row = kt * 16 + (lane & 15);
+        ldsm_x2_trans(bh, row < L ? smem_u32(Vs + row * LDS + nc * 8) : zaddr);
+        ldsm_x2_trans(bl, row < L ? smem_u32(Vs + (L + row) * LDS + nc * 8) : zaddr);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma3(o[mt][nc], ph[mt], plo[mt], bh, bl);
+      }
+    }
+
+    // ---- normalise, split, store (rows < L)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int i = mt * 16 + g + hf * 8;
+        if (i < L) {
+          const float inv = rsum[mt][hf];
+          __nv_bfloat16* hi = out_planes + (static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
+#pragma unroll
+          for (int nc = 0; nc < NTC; ++nc) {
+            uint32_t wh, wl;
+            split_pair(o[mt][nc][2 * hf] * inv, o[mt][nc][2 * hf + 1] * inv, wh, wl);
+            *reinterpret_cast<uint32_t*>(hi + nc * 8) = wh;
+            *reinterpret_cast<uint32_t*>(hi + out_plane_stride + nc * 8) = wl;
+          }
+        }
+      }
+  }
+}
+
+template <int DH, bool REL>
+static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const __nv_bfloat16* rpl, int64_t r_ps,
+                                const float* rw, const float* rr, int B, int L, int d, int H,
+                                __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s) {
+  constexpr int LDS = DH + 8;
+  const int QR = REL ? L + 2 : L;
+  const int S2LD = ((2 * L + 7) / 8) * 8 + 1;
+  const size_t per_warp = ((static_cast<size_t>(2 * QR * LDS + 4 * L * LDS) * 2 + (REL ? QR * S2LD * 4 : 0)) + 15) / 16 * 16;
+  const size_t shared_part = static_cast<size_t>(LDS + (REL ? 2 * 2 * L * LDS : 0)) * 2;
+  const int warps = 4;
+  const size_t smem = shared_part + warps * per_warp;
+  T4R_REQUIRE(smem <= 200 * 1024, "attn_mma: shared memory %zu too large", smem);
+  auto kern = attn_mma_kernel<DH, REL>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  int spb = 2 * warps;
+  while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
+  dim3 grid((B + spb - 1) / spb, H);
+  kern<<<grid, warps * 32, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps);
+  T4R_LAUNCH_CHECK("attn_mma_kernel");
+  return 0;
+}
+
+bool attn_mma_supported(int L, int d, int H, bool rel) {
+  if (d % H) return false;
+  const int dh = d / H;
+  if (dh != 16 && dh != 32 && dh != 64) return false;
+  return rel ? (L + 2 <= 32) : (L <= 32);
+}
+
+int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
+                    int64_t r_plane_stride, const float* rw, const float* rr, int B, int L, int d, int H,
+                    __nv_bfloat16* out_planes, int64_t out_plane_stride, cudaStream_t s) {
+  T4R_REQUIRE(attn_mma_supported(L, d, H, rel), "attn_mma: unsupported shape L=%d d=%d H=%d", L, d, H);
+  const int dh = d / H;
+#define T4R_AM(DHV)                                                                                                  \
+  if (dh == DHV) {                                                                                                   \
+    if (rel) return launch_attn_mma_inst<DHV, true>(qkv_planes, qkv_plane_stride, r_planes, r_plane_stride, rw, rr,   \
+                                                    B, L, d, H, out_planes, out_plane_stride, s);                     \
+    return launch_attn_mma_inst<DHV, false>(qkv_planes, qkv_plane_stride, nullptr, 0, nullptr, nullptr, B, L, d, H,   \
+                                            out_planes, out_plane_stride, s);                                         \
+  }
+  T4R_AM(16) T4R_AM(32) T4R_AM(64)
+#undef T4R_AM
+  return T4R_ERR_UNSUPPORTED;
+}
+
+}  // namespace t4r

@@ -103,7 +103,14 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
 // ---------------------------------------------------------------------------
 int launch_split_planes(const float* x, int64_t rows, int K, int64_t ld, const uint8_t* row_code,
                         const float* mask_vec, float* out_f32, __nv_bfloat16* planes, cudaStream_t s);
-int launch_rel_pos_proj(const float* wr, int L, int d, float* r_out /*[2L, d]*/, cudaStream_t s);
+// all layers in one launch: r_out [n_layer, 2L, d] fp32, r_planes [n_layer, 2, 2L, d] bf16 (or null)
+int launch_rel_pos_proj(const float* const* wr_layers, int n_layer, int L, int d, float* r_out,
+                        __nv_bfloat16* r_planes, cudaStream_t s);
+// tensor-path attention (t4r_attn_mma.cu): operands as split planes
+bool attn_mma_supported(int L, int d, int H, bool rel);
+int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
+                    int64_t r_plane_stride, const float* rw, const float* rr, int B, int L, int d, int H,
+                    __nv_bfloat16* out_planes, int64_t out_plane_stride, cudaStream_t s);
 int launch_xlnet_attn(const float* qkv /*[M, 3d]*/, const float* r /*[2L, d]*/, const float* rw, const float* rr,
                       int B, int L, int d, int H, __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s);
 int launch_causal_attn(const float* qkv, int B, int L, int d, int H, __nv_bfloat16* out_planes,

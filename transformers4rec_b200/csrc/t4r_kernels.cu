@@ -434,27 +434,51 @@ namespace t4r {
 //   pos(m) = [sin(p w) || cos(p w)], p = L - m, w_k = 10000^(-2k/d)
 //   HF:models/xlnet/modeling_xlnet.py:930-976 (bi_data=False, clamp_len=-1)
 // ============================================================================
-__global__ void rel_pos_proj_kernel(const float* __restrict__ wr, int L, int d, float* __restrict__ r_out) {
+struct RelPosLayers {
+  const float* wr[T4R_MAX_FEATURES];  // per layer [d, d]
+};
+
+// grid = (2L, d/32, n_layer); one warp computes 32 outputs of one relative position for one layer
+__global__ void __launch_bounds__(32)
+rel_pos_proj_kernel(const __grid_constant__ RelPosLayers lw, int L, int d, float* __restrict__ r_out,
+                    __nv_bfloat16* __restrict__ r_planes) {
   extern __shared__ float pos_s[];  // [d]
-  const int m = blockIdx.x;
+  const int m = blockIdx.x, layer = blockIdx.z;
+  const int n = blockIdx.y * 32 + threadIdx.x;
+  const float* __restrict__ wr = lw.wr[layer];
   const float p = static_cast<float>(L - m);
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+  for (int k = threadIdx.x; k < d; k += 32) {
     const int kk = (k < d / 2) ? k : k - d / 2;
     const float inv_freq = 1.0f / powf(10000.0f, static_cast<float>(2 * kk) / static_cast<float>(d));
     const float a = p * inv_freq;
     pos_s[k] = (k < d / 2) ? sinf(a) : cosf(a);
   }
-  __syncthreads();
-  for (int n = threadIdx.x; n < d; n += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < d; ++k) acc = fmaf(pos_s[k], __ldg(wr + static_cast<int64_t>(k) * d + n), acc);
-    r_out[static_cast<int64_t>(m) * d + n] = acc;
+  __syncwarp();
+  if (n >= d) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < d; k += 4) {  // d % 64 == 0: four independent chains, four loads in flight
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = fmaf(pos_s[k + u], __ldg(wr + static_cast<int64_t>(k + u) * d + n), acc[u]);
+  }
+  const float r = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  const int64_t o = (static_cast<int64_t>(layer) * 2 * L + m) * d + n;
+  r_out[o] = r;
+  if (r_planes) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(r, hi, lo);
+    // per layer [2, 2L, d]
+    r_planes[(static_cast<int64_t>(layer) * 4 * L + m) * d + n] = hi;
+    r_planes[(static_cast<int64_t>(layer) * 4 * L + 2 * L + m) * d + n] = lo;
   }
 }
 
-int launch_rel_pos_proj(const float* wr, int L, int d, float* r_out, cudaStream_t s) {
-  const int threads = d < 256 ? d : 256;
-  rel_pos_proj_kernel<<<2 * L, threads, d * sizeof(float), s>>>(wr, L, d, r_out);
+int launch_rel_pos_proj(const float* const* wr_layers, int n_layer, int L, int d, float* r_out,
+                        __nv_bfloat16* r_planes, cudaStream_t s) {
+  T4R_REQUIRE(n_layer >= 1 && n_layer <= T4R_MAX_FEATURES, "rel_pos_proj: at most %d layers per call", T4R_MAX_FEATURES);
+  RelPosLayers lw;
+  for (int i = 0; i < n_layer; ++i) lw.wr[i] = wr_layers[i];
+  dim3 grid(2 * L, (d + 31) / 32, n_layer);
+  rel_pos_proj_kernel<<<grid, 32, d * sizeof(float), s>>>(lw, L, d, r_out, r_planes);
   T4R_LAUNCH_CHECK("rel_pos_proj_kernel");
   return 0;
 }
