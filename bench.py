@@ -47,6 +47,17 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def head_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the head GEMM from the committed ncu capture
+    (profiles/r1_head_traffic.json; config2 only) -- None when no capture is on record."""
+    p = os.path.join(ROOT, "profiles", "r1_head_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def synth_ids(B, L, V, seed=0):
     g = torch.Generator().manual_seed(seed)
     lens = torch.randint(2, L + 1, (B,), generator=g)
@@ -282,7 +293,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,false,true> (tied logits + online LSE)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
-                "traffic": None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,
+                "traffic": head_traffic() if args.workload == "config2" else None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,
                 "algorithmic_flops_per_launch": head_flops, "label_rows_T": T,
                 "note": "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction"
                 if args.nprod == 3 else "plain bf16 product"}

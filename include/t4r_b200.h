@@ -106,6 +106,16 @@ int t4r_compact_targets(const int64_t* masked_targets, int64_t n, int64_t paddin
                         int64_t* tgt_labels, int32_t* count_dev, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * N1  ragged (values, offsets) -> dense right-padded / truncated [rows, pad_len]
+ *     replaces: _pad_ragged_tensor / _pad_dense_tensor  utils/padding.py:20-68 (sparse_coo -> to_dense
+ *               + F.pad), called by pad_batch :71-122 and pad_inputs :125-164 (model/base.py:551).
+ *     offsets == NULL means a dense input [rows, in_len] that is padded / truncated to pad_len.
+ *     elem_bytes is 8 (int64 ids) or 4 (fp32 continuous features).
+ * ------------------------------------------------------------------------- */
+int t4r_pad_ragged(const void* values, const int64_t* offsets, int64_t rows, int in_len, int pad_len, int elem_bytes,
+                   void* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * operand packing / elementwise helpers
  * ------------------------------------------------------------------------- */
 /* fp32 [rows, K] (row stride ld) -> planes bf16 [2, rows, Kp].  Optional row_code/
@@ -133,7 +143,7 @@ int t4r_gather_rows_split_i64(const float* x, int K, int ld, const int64_t* idx,
 #define T4R_ACT_GELU 2
 typedef struct {
   int64_t M;                 /* rows of X (capacity if m_dev != NULL)                    */
-  int N;                     /* output features, multiple of 64                          */
+  int N;                     /* output features (any; LayerNorm needs 64, 128 or 256)    */
   int K;                     /* input features (planes are padded to round_up64(K))      */
   const void* x_planes;      /* bf16 [2, M, Kp]                                          */
   const void* w_planes;      /* bf16 [2, N, Kp]  (W is [N, K] like nn.Linear.weight)     */

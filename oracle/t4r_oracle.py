@@ -58,6 +58,46 @@ def pick_kth_set(weights01: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- #
+# ragged ingest
+# --------------------------------------------------------------------------- #
+
+
+def pad_ragged(values: torch.Tensor, offsets: torch.Tensor, padding_length: int) -> torch.Tensor:
+    """utils/padding.py:48-68: ragged rows -> dense, right-padded with zeros, truncated to
+    ``padding_length`` (the reference densifies a sparse COO tensor, then F.pad's it)."""
+    rows = offsets.numel() - 1
+    out = torch.zeros((rows, padding_length), dtype=values.dtype)
+    for r in range(rows):
+        seg = values[int(offsets[r]): int(offsets[r + 1])][:padding_length]
+        out[r, : seg.numel()] = seg
+    return out
+
+
+def pad_dense(t: torch.Tensor, length: int) -> torch.Tensor:
+    """utils/padding.py:20-30."""
+    return F.pad(t, (0, length - t.shape[1], 0, 0)) if t.dim() == 2 else t
+
+
+def pad_inputs(inputs: Dict[str, torch.Tensor], max_sequence_length: Optional[int] = None):
+    """utils/padding.py:125-164 (+ pad_batch :71-122)."""
+    batch_max = 0
+    for k, v in inputs.items():
+        if k.endswith("__offsets"):
+            batch_max = max(int((v[1:] - v[:-1]).max()), batch_max)
+    length = batch_max if max_sequence_length is None else min(max_sequence_length, batch_max)
+    if length <= 0:
+        return inputs
+    out = {}
+    for k, v in inputs.items():
+        if k.endswith("__offsets"):
+            col = k[: -len("__offsets")]
+            out[col] = pad_ragged(inputs[col + "__values"], v, length)
+        elif not k.endswith("__values"):
+            out[k] = v
+    return out
+
+
+# --------------------------------------------------------------------------- #
 # input block
 # --------------------------------------------------------------------------- #
 

@@ -246,6 +246,19 @@ def main():
                    "logits_full_tau2": logits_full, "loss_full_tau2": loss_full,
                    "logits_sampled": logits_s, "loss_sampled": loss_s}
 
+    # ---------------------------------------------------------------- ragged padding (N1)
+    padding = importlib.import_module("transformers4rec.torch.utils.padding")
+    lens = torch.randint(0, 12, (40,), generator=g)
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    ids = torch.randint(1, 1000, (int(offs[-1]),), generator=g)
+    fl = torch.rand(int(offs[-1]), generator=g)
+    dense = torch.randint(1, 50, (40, 6), generator=g)
+    inp = {"i__values": ids, "i__offsets": offs, "f__values": fl, "f__offsets": offs, "d": dense}
+    out["padding"] = {"inputs": inp,
+                      "pad_inputs_none": dict(padding.pad_inputs(dict(inp))),
+                      "pad_inputs_8": dict(padding.pad_inputs(dict(inp), 8)),
+                      "pad_batch_15_4": dict(padding.pad_batch(dict(inp), {"i": 15, "f": 15, "d": 4}))}
+
     torch.save(out, os.path.join(HERE, "reference_vectors.pt"))
     sizes = {k: sum(v.numel() for v in _flatten(vs)) for k, vs in out.items()}
     print("wrote reference_vectors.pt", sizes)

@@ -21,7 +21,8 @@ def ops():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 64, 133), (1000, 192, 256), (257, 128, 64),
-                                   (4096, 256, 256), (513, 1024, 256), (640, 256, 1024)])
+                                   (4096, 256, 256), (513, 1024, 256), (640, 256, 1024), (333, 100, 203),
+                                   (130, 36, 100)])
 @pytest.mark.parametrize("nprod", [3, 1])
 def test_linear_matches_fp32(ops, M, N, K, nprod):
     torch.manual_seed(0)
@@ -39,6 +40,7 @@ def test_linear_matches_fp32(ops, M, N, K, nprod):
     # planes output reproduces y: hi + lo
     rec = yp[0].float() + yp[1].float()
     assert (rec[:, :N] - y).abs().max().item() < 1e-3 * max(1.0, y.abs().max().item()) * 0.01 + 1e-4
+    assert (rec[:, N:] == 0).all()  # zero padding of the planes up to a multiple of 64 columns
 
 
 def test_linear_epilogues(ops):
@@ -343,3 +345,119 @@ def test_inference_topk():
     rs, ri = torch.topk(ref_scores, 10)
     assert (s.cpu() - rs).abs().max().item() < TOL
     assert (i.cpu() == ri).float().mean().item() > 0.98
+
+
+def test_padding_known_answers_on_gpu():
+    """The reference's padding known answers (tests/unit/utils/test_padding.py:34-151) through
+    t4r_pad_ragged, plus a randomised comparison with the oracle."""
+    from itertools import accumulate
+
+    import transformers4rec_b200.torch as tr
+
+    def vo(data, dtype=torch.int64):
+        vals = [x for row in data for x in row]
+        return torch.tensor(vals, dtype=dtype).cuda(), torch.tensor([0] + list(accumulate(len(r) for r in data))).cuda()
+
+    v, o = vo([[1, 2], [], [3, 4, 5]])
+    out = tr.pad_batch({"a__values": v, "a__offsets": o, "b": torch.tensor([[3, 6], [4, 1], [8, 4]]).cuda()}, {"a": 7, "b": 3})
+    assert torch.equal(out["a"].cpu(), torch.tensor([[1, 2, 0, 0, 0, 0, 0], [0] * 7, [3, 4, 5, 0, 0, 0, 0]]))
+    assert torch.equal(out["b"].cpu(), torch.tensor([[3, 6, 0], [4, 1, 0], [8, 4, 0]]))
+    v, o = vo([[1, 2], [], [3, 4, 5, 4, 7]])
+    out = tr.pad_batch({"a__values": v, "a__offsets": o, "b": torch.tensor([[1, 2, 3, 4], [6, 7, 8, 9]]).cuda()}, {"a": 3, "b": 2})
+    assert torch.equal(out["a"].cpu(), torch.tensor([[1, 2, 0], [0, 0, 0], [3, 4, 5]]))
+    assert torch.equal(out["b"].cpu(), torch.tensor([[1, 2], [6, 7]]))
+    v, o = vo([[1, 2, 3, 4, 5], [6, 7, 8, 9]])
+    b = torch.tensor([[3, 6], [4, 1]]).cuda()
+    out = tr.pad_inputs({"a__values": v, "a__offsets": o, "b": b}, max_sequence_length=3)
+    assert torch.equal(out["a"].cpu(), torch.tensor([[1, 2, 3], [6, 7, 8]])) and torch.equal(out["b"], b)
+    with pytest.raises(ValueError, match="unspecified padding length"):
+        tr.pad_batch({"a__values": v, "a__offsets": o}, {})
+    # randomised, int64 ids and fp32 continuous values
+    g = torch.Generator().manual_seed(9)
+    lens = torch.randint(0, 30, (500,), generator=g)
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    ids = torch.randint(1, 1000, (int(offs[-1]),), generator=g)
+    fl = torch.rand(int(offs[-1]), generator=g)
+    got = tr.pad_inputs({"i__values": ids.cuda(), "i__offsets": offs.cuda(), "f__values": fl.cuda(), "f__offsets": offs.cuda()}, 20)
+    ref = O.pad_inputs({"i__values": ids, "i__offsets": offs, "f__values": fl, "f__offsets": offs}, 20)
+    assert torch.equal(got["i"].cpu(), ref["i"]) and torch.equal(got["f"].cpu(), ref["f"])
+
+
+def test_reference_fixture_body_with_standalone_mlp_and_ragged_inputs():
+    """The reference's canonical model fixture (tests/unit/torch/_conftest.py:143-155):
+    inputs(d_output=100, masking="causal") >> MLPBlock([64]) >> XLNet(d=64, 4 heads, 2 layers)
+    >> NextItemPredictionTask(weight_tying=True); fed with ragged __values/__offsets inputs."""
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(21)
+    cards = {"item_id/list": 5001, "category/list": 333}
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 5000, tags=[tr.Tags.ITEM_ID]),
+                        tr.ColumnSchema.create_categorical("category/list", 332),
+                        tr.ColumnSchema.create_continuous("price/list")])
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, d_output=100, masking="causal")
+    cfg = tr.XLNetConfig.build(d_model=64, n_head=4, n_layer=2, total_seq_length=20)
+    body = tr.SequentialBlock(inputs, tr.MLPBlock([64]), tr.TransformerBlock(cfg, masking=inputs.masking))
+    model = tr.NextItemPredictionTask(weight_tying=True).to_model(body, inputs, max_sequence_length=20).cuda().eval()
+    with torch.no_grad():
+        for n, p in body[2].transformer.named_parameters():
+            if p.ndim >= 2 and "layer_norm" not in n:
+                p.normal_(0.0, 0.08)
+    B, L = 40, 20
+    dense = synth_batch(B, L, cards, ("price/list",), seed=5)
+    lens = (dense["item_id/list"] != 0).sum(1)
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    valid = dense["item_id/list"] != 0
+    ragged = {}
+    for k, v in dense.items():
+        ragged[k + "__values"] = v[valid].cuda()
+        ragged[k + "__offsets"] = offs.cuda()
+    with torch.no_grad():
+        out_r = model(ragged, training=True)
+        out_d = model({k: v[:, : int(lens.max())].cuda() for k, v in dense.items()}, training=True)
+    assert abs(out_r["loss"].item() - out_d["loss"].item()) < 1e-6  # ragged ingest == dense padded input
+    # oracle for the whole stack
+    Lm = int(lens.max())
+    d_in = {k: v[:, :Lm] for k, v in dense.items()}
+    emb = inputs.categorical_module.embedding_tables
+    with torch.no_grad():
+        x = O.embed_concat({n: emb[n].weight.cpu() for n in cards}, {n: d_in[n] for n in cards},
+                           {"price/list": d_in["price/list"]})
+        lin = inputs.projection_module[0][0]
+        x = O.project_relu(x, lin.weight.cpu(), lin.bias.cpu())
+        mask, labels = O.clm_compute_masked_targets(d_in["item_id/list"], True, False)
+        x = O.clm_apply_mask_to_inputs(x, mask, inputs.masking.masked_item_embedding.detach().cpu(), True, False)
+        lin2 = body[1][0][0]
+        x = O.project_relu(x, lin2.weight.cpu(), lin2.bias.cpu())
+        hf = O.build_hf_xlnet(64, 4, 2).eval()
+        hf.load_state_dict({k: v.cpu() for k, v in body[2].transformer.state_dict().items()}, strict=False)
+        h = O.hf_encoder_forward(hf, x)
+        xt, y = O.select_targets(h, labels)
+        ref_loss, _ = O.full_softmax_head(xt, y, emb["item_id/list"].weight.cpu(), 1.0)
+    assert abs(out_r["loss"].item() - ref_loss.item()) < TOL
+    assert torch.equal(out_r["labels"].cpu(), y)
+
+
+def test_no_projection_path():
+    """No d_output: aggregation + masking only (embedding dim = d_model), XLNet MLM."""
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(22)
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 3000, tags=[tr.Tags.ITEM_ID])])
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, masking="mlm",
+                                                    embedding_dims={"item_id/list": 64})
+    assert inputs.projection_module is None and tuple(inputs.output_size()) == (-1, 20, 64)
+    cfg = tr.XLNetConfig.build(d_model=64, n_head=4, n_layer=1, total_seq_length=20)
+    model = cfg.to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True)).cuda().eval()
+    B, L = 50, 20
+    batch = synth_batch(B, L, {"item_id/list": 3001}, seed=6)
+    u, draws = mlm_draws(B, L)
+    inputs.masking.set_draws(u.cuda())
+    with torch.no_grad():
+        out = model({k: v.cuda() for k, v in batch.items()}, training=True)
+        table = inputs.item_embedding_table.weight.cpu()
+        x = torch.nn.functional.embedding(batch["item_id/list"], table)
+        mask, labels = O.mlm_compute_masked_targets(batch["item_id/list"], True, False, **draws)
+        x = O.mlm_apply_mask_to_inputs(x, mask, inputs.masking.masked_item_embedding.detach().cpu(), True, False)
+        hf = O.build_hf_xlnet(64, 4, 1).eval()
+        hf.load_state_dict({k: v.cpu() for k, v in model.heads[0].body[1].transformer.state_dict().items()}, strict=False)
+        xt, y = O.select_targets(O.hf_encoder_forward(hf, x), labels)
+        ref_loss, _ = O.full_softmax_head(xt, y, table, 1.0)
+    assert abs(out["loss"].item() - ref_loss.item()) < TOL

@@ -115,6 +115,7 @@ SIGNATURES = {
     "t4r_version": (c_int, []),
     "t4r_launch_count": (C.c_longlong, []),
     "t4r_embed_concat_fwd": (c_int, [C.POINTER(FeatureList), c_int64, c_int, _P, _P, _P, _P]),
+    "t4r_pad_ragged": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "t4r_mask_mlm": (c_int, [_P, c_int, c_int, c_int64, c_int, c_float, _P, _P, _P, _P, _P]),
     "t4r_mask_clm": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P]),
     "t4r_compact_targets": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),

@@ -28,7 +28,16 @@ class SequentialBlock(nn.Sequential):
     layers whose ``forward`` names them."""
 
     def __init__(self, *args, output_size=None):
-        super().__init__(*args)
+        # block/base.py:174-203: buildable blocks (e.g. ``MLPBlock([64])``) are built against the
+        # output size of the layer in front of them
+        built = []
+        for layer in args:
+            if not isinstance(layer, nn.Module) and hasattr(layer, "build"):
+                if not built or not hasattr(built[-1], "output_size") or built[-1].output_size() is None:
+                    raise ValueError("a buildable block needs a preceding layer with a known output size")
+                layer = layer.build(built[-1].output_size())
+            built.append(layer)
+        super().__init__(*built)
         self._static_output_size = output_size
         self.input_size = None
 

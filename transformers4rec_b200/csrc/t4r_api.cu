@@ -91,7 +91,7 @@ extern "C" int t4r_debug_sgemm_nt(const float* A, const float* B, const float* b
 extern "C" int t4r_linear_fwd(const t4r_linear_args* a, void* stream) {
   T4R_REQUIRE(a != nullptr, "linear_fwd: null args");
   T4R_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->x_planes && a->w_planes, "linear_fwd: bad shape/pointers");
-  T4R_REQUIRE(a->N % 64 == 0, "linear_fwd: N must be a multiple of 64 (got %d)", a->N);
+  T4R_REQUIRE(a->ln_gamma == nullptr || a->N % 64 == 0, "linear_fwd: LayerNorm needs N in {64,128,256} (got %d)", a->N);
   T4R_REQUIRE(a->out_f32 || a->out_planes || a->out_pre_ln, "linear_fwd: no output requested");
   T4R_REQUIRE(a->row_code == nullptr || a->mask_vec != nullptr, "linear_fwd: row_code needs mask_vec");
   T4R_REQUIRE((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "linear_fwd: ln_gamma and ln_beta go together");

@@ -104,14 +104,26 @@ struct GemmDev {
   GemmEpilogue ep;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == T4R_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == T4R_ACT_GELU) return gelu_erf(v);
-  return v;
-}
-
-// value of one 32-column chunk: acc + bias -> act -> mask replace (residual is added separately)
-__device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& ep, int64_t ncol0, int code) {
+// value of one 32-column chunk: acc + bias -> act -> mask replace (residual is added separately).
+// nvalid < 32 only for the last chunk of an N that is not a multiple of 32: those columns read
+// nothing and come out as exact zeros (they are the zero padding of the split planes).
+__device__ __forceinline__ void dense_chunk(float (&v)[32], const GemmEpilogue& ep, int64_t ncol0, int code,
+                                            int nvalid = 32) {
+  if (nvalid < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = 0.f;
+      if (j < nvalid) {
+        x = v[j] + (ep.bias ? __ldg(ep.bias + ncol0 + j) : 0.f);
+        if (ep.act == T4R_ACT_GELU) x = gelu_erf(x);
+        else if (ep.act == T4R_ACT_RELU) x = fmaxf(x, 0.f);
+        if (code == 1) x = __ldg(ep.mask_vec + ncol0 + j);
+        else if (code == 2) x = 0.f;
+      }
+      v[j] = x;
+    }
+    return;
+  }
   if (ep.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + ncol0);
 #pragma unroll
@@ -358,8 +370,10 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
       tmem_ld<32>(taddr + c * 32, v);
       long long t1 = prof ? clock64() : 0;
       const int64_t ncol0 = n0 + c * 32;
-      if (ncol0 >= p.N) continue;  // warp-uniform
-      dense_chunk(v, ep, ncol0, code);
+      const int64_t n_pad = (p.N + 63) / 64 * 64;  // planes are zero padded to a multiple of 64 columns
+      if (ncol0 >= n_pad) continue;                // warp-uniform
+      const int nvalid = (p.N - ncol0 >= 32) ? 32 : (p.N > ncol0 ? static_cast<int>(p.N - ncol0) : 0);
+      dense_chunk(v, ep, ncol0, code, nvalid);
       long long t2 = prof ? clock64() : 0;
       if (prof) { g_dbg_cycles[2] += t1 - t0; g_dbg_cycles[3] += t2 - t1; }
       if (ep.residual || ep.residual_planes) {
@@ -370,8 +384,8 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += rs[j];
       }
-      if (ep.out_f32) {
-        if ((ep.ldo & 3) == 0 && ncol0 + 32 <= p.N) {
+      if (ep.out_f32 && nvalid > 0) {
+        if ((ep.ldo & 3) == 0 && nvalid == 32) {
           warp_store_f32(stg, v, ep.out_scale, ep.out_f32 + row0 * ep.ldo + ncol0, ep.ldo, rows_valid, lane);
         } else if (row_ok) {
           float* dst = ep.out_f32 + row * ep.ldo + ncol0;
@@ -678,10 +692,12 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   } else if (ep.head) {
     if (bn == 0) bn = 256;
   } else {
-    if (bn == 0) bn = (pb.N % 256 == 0) ? 256 : ((pb.N % 128 == 0) ? 128 : 64);
-    T4R_REQUIRE(ep.out_planes == nullptr || pb.N % 64 == 0, "gemm: planes output needs N %% 64 == 0");
-    T4R_REQUIRE((ep.bias == nullptr && ep.residual == nullptr && ep.row_code == nullptr) || pb.N % 32 == 0,
-                "gemm: dense epilogue needs N %% 32 == 0");
+    if (bn == 0) {
+      const int64_t np = (pb.N + 63) / 64 * 64;
+      bn = (np % 256 == 0) ? 256 : ((np % 128 == 0) ? 128 : 64);
+    }
+    T4R_REQUIRE((ep.residual == nullptr && ep.residual_planes == nullptr) || pb.N % 32 == 0,
+                "gemm: a residual needs N %% 32 == 0");
   }
   T4R_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: bad BN %d", bn);
 

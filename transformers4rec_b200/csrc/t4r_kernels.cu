@@ -121,6 +121,49 @@ extern "C" int t4r_embed_concat_fwd(const t4r_feature_list* feats, int64_t M, in
 namespace t4r {
 
 // ============================================================================
+// N1: ragged (values, offsets) or dense [rows, in_len] -> dense [rows, pad_len], zeros on the right
+// ============================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad_ragged_kernel(const T* __restrict__ values, const int64_t* __restrict__ offsets, int64_t rows, int in_len,
+                  int pad_len, T* __restrict__ out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * pad_len) return;
+  const int64_t row = idx / pad_len;
+  const int l = static_cast<int>(idx % pad_len);
+  T v = 0;
+  if (offsets) {
+    const int64_t beg = offsets[row], end = offsets[row + 1];
+    if (l < end - beg) v = values[beg + l];
+  } else if (l < in_len) {
+    v = values[row * in_len + l];
+  }
+  out[idx] = v;
+}
+
+}  // namespace t4r
+
+extern "C" int t4r_pad_ragged(const void* values, const int64_t* offsets, int64_t rows, int in_len, int pad_len,
+                              int elem_bytes, void* out, void* stream) {
+  using namespace t4r;
+  T4R_REQUIRE(out && rows > 0 && pad_len > 0 && (elem_bytes == 4 || elem_bytes == 8), "pad_ragged: bad arguments");
+  T4R_REQUIRE(values != nullptr || offsets != nullptr, "pad_ragged: no input");
+  const int64_t n = rows * pad_len;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 8)
+    pad_ragged_kernel<long long><<<blocks, 256, 0, s>>>(static_cast<const long long*>(values), offsets, rows, in_len,
+                                                         pad_len, static_cast<long long*>(out));
+  else
+    pad_ragged_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(values), offsets, rows, in_len, pad_len,
+                                                     static_cast<float*>(out));
+  T4R_LAUNCH_CHECK("pad_ragged_kernel");
+  return 0;
+}
+
+namespace t4r {
+
+// ============================================================================
 // K3: masks / labels (integer).  One thread per session.
 // ============================================================================
 __device__ __forceinline__ int kth_pick(double u, int n) {

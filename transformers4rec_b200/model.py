@@ -100,12 +100,17 @@ class Model(nn.Module):
         self.head_weights = head_weights or [1.0] * len(head)
         self.head_reduction = head_reduction
         self.top_k = kwargs.get("top_k", None)
+        self.max_sequence_length = kwargs.get("max_sequence_length", None)
 
     def forward(self, inputs: Dict[str, torch.Tensor], targets=None, training=False, testing=False, **kwargs):
         # model/base.py:546-548: floating inputs are cast to fp32
         for name, val in inputs.items():
             if torch.is_floating_point(val) and val.dtype != torch.float32:
                 inputs[name] = val.to(torch.float32)
+        # model/base.py:551: ragged (__values/__offsets) inputs become dense padded tensors
+        if any(k.endswith("__offsets") for k in inputs):
+            from .padding import pad_inputs
+            inputs = pad_inputs(inputs, max_sequence_length=self.max_sequence_length)
         if len(self.heads) == 1:
             # :574-576 stack().mean() over one head is the identity
             return self.heads[0](inputs, call_body=True, targets=targets, training=training, testing=testing,

@@ -12,3 +12,4 @@ from ..model import Head, Model  # noqa: F401
 from ..prediction_task import (LogUniformSampler, NextItemPredictionTask, PredictionTask)  # noqa: F401
 from ..ranking_metric import AvgPrecisionAt, MeanReciprocalRankAt, NDCGAt, RecallAt  # noqa: F401
 from ..schema import ColumnSchema, Schema, Tags  # noqa: F401
+from ..padding import pad_batch, pad_inputs  # noqa: F401
