@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest"; timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest.log
