@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--cpu-sessions", type=int, default=64, help="sessions per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity), 1 = plain bf16")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -261,6 +262,26 @@ def main():
     head_ms_avg = sum(head_ms) / len(head_ms)
     T = int(task._last["count"].item())
 
+    # --- optional: the same step captured once and replayed from a CUDA graph (no host work at all)
+    graph_ms = None
+    if args.graph:
+        try:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                loss_static = step(batch_dev)
+            for _ in range(3):
+                gph.replay()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(K):
+                gph.replay()
+            g1.record()
+            barrier()
+            graph_ms = g0.elapsed_time(g1) / K
+        except Exception as exc:  # capture is best-effort; the eager number above stands on its own
+            graph_ms = f"capture failed: {type(exc).__name__}: {exc}"[:200]
+
     # --- timed region 2: end to end through the public API with HOST inputs
     loss_host = 0.0
     for _ in range(2):
@@ -304,6 +325,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": int(ids_host.numel() * 8),
                     "d2h_bytes_per_step": 4, "loss": loss_host},
             "gpu_launches": int(n1 - n0), "roofline": roofline}
+    if graph_ms is not None:
+        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": (B * world / (graph_ms / 1e3)) if isinstance(graph_ms, float) else None}
     if not args.no_cpu_baseline and world == 1:
         v, med, threads = time_oracle_cpu(cfg, args.cpu_sessions, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "sessions/s", "cores": threads, "kind": "port",

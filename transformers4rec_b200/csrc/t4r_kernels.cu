@@ -17,75 +17,109 @@ struct FeatDev {
   t4r_feature_list f;
 };
 
+// ROWS positions per warp: the ids of all ROWS rows are fetched first and all table-row loads
+// are issued before any store, so a warp keeps ROWS x (dim/128) 16-byte loads per lane in flight
+// (with one row per warp the id -> row dependency makes the kernel latency-bound at ~58 % of HBM).
+constexpr int kGatherRows = 4;
+
 __global__ void __launch_bounds__(256)
 embed_concat_kernel(const __grid_constant__ FeatDev fd, int64_t M, int C, int Cp, float* __restrict__ out_f32,
                     __nv_bfloat16* __restrict__ planes, int32_t* err_flag) {
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
-  if (row >= M) return;
+  constexpr int R = kGatherRows;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id()) * R;
+  if (row0 >= M) return;
   const int lane = lane_id();
   const t4r_feature_list& f = fd.f;
-  __nv_bfloat16* hi = planes ? planes + row * Cp : nullptr;
-  __nv_bfloat16* lo = planes ? planes + (M + row) * Cp : nullptr;
-  float* of = out_f32 ? out_f32 + row * C : nullptr;
   const bool out_vec_ok = (C % 4 == 0);
+  const int nrows = (M - row0 < R) ? static_cast<int>(M - row0) : R;
 
   for (int t = 0; t < f.n_cat; ++t) {
-    int64_t id = f.ids[t][row];
     const int dim = f.dim[t];
     const int col = f.cat_col[t];
-    if (id < 0 || id >= f.table_rows[t]) {
-      if (err_flag && lane == 0) *err_flag = 1;
-      id = 0;
+    int64_t id[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      id[r] = (r < nrows) ? f.ids[t][row0 + r] : 0;
+      if (id[r] < 0 || id[r] >= f.table_rows[t]) {
+        if (err_flag && lane == 0) *err_flag = 1;
+        id[r] = 0;
+      }
     }
-    const float* src = f.table[t] + id * dim;
     if ((dim & 3) == 0 && (col & 3) == 0) {
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      for (int q = lane; q < dim / 4; q += 32) {
-        const float4 v = __ldg(s4 + q);
-        const int c = col + 4 * q;
-        if (of) {
-          if (out_vec_ok) {
-            *reinterpret_cast<float4*>(of + c) = v;
-          } else {
-            of[c] = v.x; of[c + 1] = v.y; of[c + 2] = v.z; of[c + 3] = v.w;
+      for (int q0 = 0; q0 < dim / 4; q0 += 64) {  // up to two 16-byte chunks per lane and row per pass
+        float4 v[R][2];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int q = q0 + lane + 32 * k;
+            if (r < nrows && q < dim / 4)
+              v[r][k] = __ldg(reinterpret_cast<const float4*>(f.table[t] + id[r] * dim) + q);
           }
-        }
-        if (hi) {
-          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-          split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-          *reinterpret_cast<uint2*>(hi + c) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-          *reinterpret_cast<uint2*>(lo + c) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
-        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int q = q0 + lane + 32 * k;
+            if (r < nrows && q < dim / 4) {
+              const int c = col + 4 * q;
+              const int64_t row = row0 + r;
+              const float4 x = v[r][k];
+              if (out_f32) {
+                float* of = out_f32 + row * C;
+                if (out_vec_ok) {
+                  *reinterpret_cast<float4*>(of + c) = x;
+                } else {
+                  of[c] = x.x; of[c + 1] = x.y; of[c + 2] = x.z; of[c + 3] = x.w;
+                }
+              }
+              if (planes) {
+                __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1); split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
+                *reinterpret_cast<uint2*>(planes + row * Cp + c) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                *reinterpret_cast<uint2*>(planes + (M + row) * Cp + c) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+              }
+            }
+          }
       }
     } else {
-      for (int e = lane; e < dim; e += 32) {
-        const float v = __ldg(src + e);
-        if (of) of[col + e] = v;
-        if (hi) {
-          __nv_bfloat16 h, l;
-          split_bf16(v, h, l);
-          hi[col + e] = h;
-          lo[col + e] = l;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (r >= nrows) break;
+        const float* src = f.table[t] + id[r] * dim;
+        const int64_t row = row0 + r;
+        for (int e = lane; e < dim; e += 32) {
+          const float v = __ldg(src + e);
+          if (out_f32) out_f32[row * C + col + e] = v;
+          if (planes) {
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            planes[row * Cp + col + e] = h;
+            planes[(M + row) * Cp + col + e] = l;
+          }
         }
       }
     }
   }
-  for (int t = lane; t < f.n_cont; t += 32) {
-    const float v = f.cont[t][row];
-    const int c = f.cont_col[t];
-    if (of) of[c] = v;
-    if (hi) {
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
-      hi[c] = h;
-      lo[c] = l;
+  for (int r = 0; r < nrows; ++r) {
+    const int64_t row = row0 + r;
+    for (int t = lane; t < f.n_cont; t += 32) {
+      const float v = f.cont[t][row];
+      const int c = f.cont_col[t];
+      if (out_f32) out_f32[row * C + c] = v;
+      if (planes) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        planes[row * Cp + c] = h;
+        planes[(M + row) * Cp + c] = l;
+      }
     }
-  }
-  if (hi) {
-    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-    for (int c = C + lane; c < Cp; c += 32) {
-      hi[c] = z;
-      lo[c] = z;
+    if (planes) {
+      const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+      for (int c = C + lane; c < Cp; c += 32) {
+        planes[row * Cp + c] = z;
+        planes[(M + row) * Cp + c] = z;
+      }
     }
   }
 }
@@ -111,7 +145,8 @@ extern "C" int t4r_embed_concat_fwd(const t4r_feature_list* feats, int64_t M, in
   fd.f = *feats;
   const int Cp = t4r_round_up64(C);
   const int warps = 8;
-  const int64_t blocks = (M + warps - 1) / warps;
+  const int64_t rows_per_block = static_cast<int64_t>(warps) * kGatherRows;
+  const int64_t blocks = (M + rows_per_block - 1) / rows_per_block;
   embed_concat_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       fd, M, C, Cp, out_f32, static_cast<__nv_bfloat16*>(out_planes), err_flag);
   T4R_LAUNCH_CHECK("embed_concat_kernel");
