@@ -269,6 +269,9 @@ typedef struct {
    * GEMM launch (bench.py's per-kernel roofline timing); NULL = off */
   void* ev_gemm_start;
   void* ev_gemm_stop;
+  /* nn.CrossEntropyLoss(label_smoothing=e) (transformers4rec/torch/losses.py:4-20): row_loss =
+   * lse - (1-e) z_label - (e/V) sum_j z_j.  Full, unsharded softmax only; 0 = off. */
+  float label_smoothing;
 } t4r_head_args;
 size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De);
 int t4r_head_softmax_ce_fwd(const t4r_head_args* a /*host*/, void* stream);

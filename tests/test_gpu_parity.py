@@ -461,3 +461,41 @@ def test_no_projection_path():
         xt, y = O.select_targets(O.hf_encoder_forward(hf, x), labels)
         ref_loss, _ = O.full_softmax_head(xt, y, table, 1.0)
     assert abs(out["loss"].item() - ref_loss.item()) < TOL
+
+
+def test_head_label_smoothing(ops):
+    """nn.CrossEntropyLoss(label_smoothing=e) (transformers4rec/torch/losses.py:4-20) in the fused head."""
+    torch.manual_seed(31)
+    T, V, De, eps = 300, 7001, 64, 0.1
+    xt = torch.randn(T, De)
+    W = torch.randn(V, De) * 0.1
+    y = torch.randint(1, V, (T,))
+    ref_loss, _ = O.full_softmax_head(xt, y, W, 1.0, label_smoothing=eps)
+    res = ops.head_softmax_ce(ops.split_planes(xt.cuda()), xt.cuda(), y.cuda(), ops.split_planes(W.cuda()), W.cuda(),
+                              label_smoothing=eps)
+    assert abs(res["loss"].item() - ref_loss.item()) < 1e-4
+
+
+def test_context_features_are_repeated_along_the_sequence():
+    """tabular/base.py:53-63: non-sequential features [B] are expanded to [B, L] before the concat."""
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(32)
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 500, tags=[tr.Tags.ITEM_ID]),
+                        tr.ColumnSchema.create_categorical("user_country", 60, is_list=False),
+                        tr.ColumnSchema.create_continuous("user_age", is_list=False)])
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=12, d_output=64, masking="clm").cuda()
+    B, L = 9, 12
+    batch = synth_batch(B, L, {"item_id/list": 501}, seed=8)
+    batch["user_country"] = torch.randint(1, 61, (B,))
+    batch["user_age"] = torch.rand(B)
+    with torch.no_grad():
+        x = inputs({k: v.cuda() for k, v in batch.items()}, training=True).cpu()
+        emb = inputs.categorical_module.embedding_tables
+        ref = O.embed_concat({"item_id/list": emb["item_id/list"].weight.cpu(), "user_country": emb["user_country"].weight.cpu()},
+                             {"item_id/list": batch["item_id/list"], "user_country": batch["user_country"].unsqueeze(1).expand(B, L)},
+                             {"user_age": batch["user_age"].unsqueeze(1).expand(B, L)})
+        lin = inputs.projection_module[0][0]
+        ref = O.project_relu(ref, lin.weight.cpu(), lin.bias.cpu())
+        mask, _ = O.clm_compute_masked_targets(batch["item_id/list"], True, False)
+        ref = O.clm_apply_mask_to_inputs(ref, mask, inputs.masking.masked_item_embedding.detach().cpu(), True, False)
+    assert (x - ref).abs().max().item() < 1e-4

@@ -105,6 +105,7 @@ class HeadArgs(C.Structure):
         ("nprod", c_int),
         ("ev_gemm_start", c_void_p),
         ("ev_gemm_stop", c_void_p),
+        ("label_smoothing", c_float),
     ]
 
 

@@ -378,7 +378,7 @@ extern "C" size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De) {
   (void)De;
   const size_t part_ld = static_cast<size_t>((T_cap + 127) / 128) * 128;
   const size_t n_tiles = 2 * static_cast<size_t>((V + kHeadBN - 1) / kHeadBN);  // two column halves per tile
-  return 2 * pad256(n_tiles * part_ld * 4) + pad256(2 * 64 * part_ld * 4) + 1024;
+  return 3 * pad256(n_tiles * part_ld * 4) + pad256(3 * 64 * part_ld * 4) + 1024;
 }
 
 extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
@@ -396,7 +396,12 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   Arena ar(a->workspace, a->workspace_bytes);
   float* part_m = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
   float* part_s = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
-  float* scratch = ar.take<float>(static_cast<size_t>(2) * 64 * part_ld);
+  float* scratch = ar.take<float>(static_cast<size_t>(3) * 64 * part_ld);
+  float* part_z = nullptr;
+  if (a->label_smoothing != 0.f) {
+    T4R_REQUIRE(a->pos_logit == nullptr && a->v_offset == 0, "head: label smoothing needs the unsharded full softmax");
+    part_z = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
+  }
   T4R_REQUIRE(ar.ok, "head: workspace carve-up failed");
   const float inv_tau = a->inv_temperature != 0.f ? a->inv_temperature : 1.f;
 
@@ -422,6 +427,7 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   ep.head = true;
   ep.part_m = part_m;
   ep.part_s = part_s;
+  ep.part_z = part_z;
   ep.part_ld = part_ld;
   ep.inv_tau = inv_tau;
   ep.col_bias = a->col_bias;
@@ -434,8 +440,8 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   if (a->ev_gemm_start) T4R_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_gemm_start), s));
   T4R_TRY(launch_gemm(pb, ep, s));
   if (a->ev_gemm_stop) T4R_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_gemm_stop), s));
-  return launch_head_reduce(part_m, part_s, n_tiles, part_ld, a->T_cap, a->t_dev, a->pos_logit, a->row_tgt, a->row_lse,
-                            a->row_loss, a->loss, scratch, s);
+  return launch_head_reduce(part_m, part_s, part_z, n_tiles, part_ld, a->T_cap, a->t_dev, a->pos_logit, a->row_tgt,
+                            a->label_smoothing, a->V, a->row_lse, a->row_loss, a->loss, scratch, s);
 }
 
 extern "C" int t4r_head_logits(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V,

@@ -411,7 +411,8 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   const GemmEpilogue& ep = p.ep;
   constexpr float kLog2e = 1.4426950408889634f;
   const float scale2 = ep.inv_tau * kLog2e;
-  float m_run = -INFINITY, s_run = 0.f;
+  float m_run = -INFINITY, s_run = 0.f, z_run = 0.f;
+  const bool want_z = (ep.part_z != nullptr);
   int cnt = 0;
   int64_t label = -1;
   float tgt = 0.f;
@@ -451,6 +452,13 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
         cnt += (col != lab_col) && ((x > tgt) || (x == tgt && col < lab_col));
       }
     }
+    if (want_z) {
+      // label smoothing needs sum_j z_j; masked columns are -inf and must not enter the sum
+      float zs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) zs += (v[j] == -INFINITY) ? 0.f : v[j];
+      z_run = fmaf(zs, ep.inv_tau, z_run);
+    }
     float cmax = v[0];
 #pragma unroll
     for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
@@ -467,6 +475,7 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   if (row_ok) {
     ep.part_m[static_cast<int64_t>(part_idx) * ep.part_ld + row] = m_run;
     ep.part_s[static_cast<int64_t>(part_idx) * ep.part_ld + row] = s_run;
+    if (want_z) ep.part_z[static_cast<int64_t>(part_idx) * ep.part_ld + row] = z_run;
     if (want_rank && cnt) atomicAdd(ep.row_rank + row, cnt);
   }
 }

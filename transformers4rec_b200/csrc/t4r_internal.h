@@ -71,6 +71,7 @@ struct GemmEpilogue {
   bool head = false;
   float* part_m = nullptr;             // [n_tiles, part_ld]   running max  (log2 domain)
   float* part_s = nullptr;             // [n_tiles, part_ld]   sum of 2^(x - max)
+  float* part_z = nullptr;             // [n_tiles, part_ld]   plain sum of the scaled logits (label smoothing) or null
   int part_ld = 0;
   float inv_tau = 1.f;
   const float* col_bias = nullptr;     // [N]
@@ -117,9 +118,10 @@ int launch_causal_attn(const float* qkv, int B, int L, int d, int H, __nv_bfloat
                        int64_t plane_stride, cudaStream_t s);
 int launch_addpos_ln(const float* x, const float* wpe, int B, int L, int d, const float* g, const float* b,
                      float eps, float* h_out, __nv_bfloat16* planes, int64_t plane_stride, cudaStream_t s);
-int launch_head_reduce(const float* part_m, const float* part_s, int n_tiles, int part_ld, int T_cap,
-                       const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in, float* row_lse,
-                       float* row_loss, float* loss, float* scratch, cudaStream_t s);
+int launch_head_reduce(const float* part_m, const float* part_s, const float* part_z, int n_tiles, int part_ld,
+                       int T_cap, const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in,
+                       float label_smoothing, int64_t n_classes, float* row_lse, float* row_loss, float* loss,
+                       float* scratch, cudaStream_t s);
 int launch_target_logit(const float* xt, const float* w, const int64_t* labels, int T_cap, const int32_t* t_dev,
                         int De, int64_t v_offset, int64_t V, const float* class_bias, float inv_tau, float* out,
                         cudaStream_t s);

@@ -847,19 +847,21 @@ int launch_target_logit(const float* xt, const float* w, const int64_t* labels, 
 
 // stage 1: thread = row, block column = chunk of column tiles -> (m, s) per (chunk, row)
 __global__ void __launch_bounds__(128)
-head_reduce1_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s, int n_tiles, int part_ld,
-                    int T_cap, const int32_t* __restrict__ t_dev, int tiles_per_chunk, float* __restrict__ red_m,
-                    float* __restrict__ red_s) {
+head_reduce1_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                    const float* __restrict__ part_z, int n_tiles, int part_ld, int T_cap,
+                    const int32_t* __restrict__ t_dev, int tiles_per_chunk, float* __restrict__ red_m,
+                    float* __restrict__ red_s, float* __restrict__ red_z) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
   if (row >= T) return;
   const int chunk = blockIdx.y;
   const int t0 = chunk * tiles_per_chunk;
   const int t1 = min(n_tiles, t0 + tiles_per_chunk);
-  float m = -INFINITY, s = 0.f;
+  float m = -INFINITY, s = 0.f, z = 0.f;
   for (int t = t0; t < t1; ++t) {
     const float pm = part_m[static_cast<int64_t>(t) * part_ld + row];
     const float ps = part_s[static_cast<int64_t>(t) * part_ld + row];
+    if (part_z) z += part_z[static_cast<int64_t>(t) * part_ld + row];
     const float mn = fmaxf(m, pm);
     if (mn > -INFINITY) {
       s = s * exp2f(m - mn) + ps * exp2f(pm - mn);
@@ -868,13 +870,15 @@ head_reduce1_kernel(const float* __restrict__ part_m, const float* __restrict__ 
   }
   red_m[static_cast<int64_t>(chunk) * part_ld + row] = m;
   red_s[static_cast<int64_t>(chunk) * part_ld + row] = s;
+  if (part_z) red_z[static_cast<int64_t>(chunk) * part_ld + row] = z;
 }
 
 // stage 2: combine chunks (+ optional positive logit), natural-log lse, per-row loss
 __global__ void __launch_bounds__(128)
-head_reduce2_kernel(const float* __restrict__ red_m, const float* __restrict__ red_s, int n_chunks, int part_ld,
-                    int T_cap, const int32_t* __restrict__ t_dev, const float* __restrict__ pos_logit,
-                    const float* __restrict__ row_tgt, float* __restrict__ row_lse, float* __restrict__ row_loss) {
+head_reduce2_kernel(const float* __restrict__ red_m, const float* __restrict__ red_s, const float* __restrict__ red_z,
+                    int n_chunks, int part_ld, int T_cap, const int32_t* __restrict__ t_dev,
+                    const float* __restrict__ pos_logit, const float* __restrict__ row_tgt, float label_smoothing,
+                    float inv_classes, float* __restrict__ row_lse, float* __restrict__ row_loss) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= T_cap) return;
   const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
@@ -890,9 +894,11 @@ head_reduce2_kernel(const float* __restrict__ red_m, const float* __restrict__ r
     m = pos_logit[row] * kLog2e;
     s = 1.f;
   }
+  float z = 0.f;
   for (int c = 0; c < n_chunks; ++c) {
     const float pm = red_m[static_cast<int64_t>(c) * part_ld + row];
     const float ps = red_s[static_cast<int64_t>(c) * part_ld + row];
+    if (red_z) z += red_z[static_cast<int64_t>(c) * part_ld + row];
     const float mn = fmaxf(m, pm);
     if (mn > -INFINITY) {
       s = s * exp2f(m - mn) + ps * exp2f(pm - mn);
@@ -901,7 +907,9 @@ head_reduce2_kernel(const float* __restrict__ red_m, const float* __restrict__ r
   }
   const float lse = (m + log2f(s)) * kLn2;
   if (row_lse) row_lse[row] = lse;
-  if (row_loss) row_loss[row] = lse - (pos_logit ? pos_logit[row] : row_tgt[row]);
+  const float tgt = pos_logit ? pos_logit[row] : row_tgt[row];
+  // nn.CrossEntropyLoss(label_smoothing=e): lse - (1-e) z_y - (e/V) sum_j z_j   (losses.py:4-20)
+  if (row_loss) row_loss[row] = red_z ? lse - (1.f - label_smoothing) * tgt - label_smoothing * inv_classes * z : lse - tgt;
 }
 
 // mean of the first T entries (single block; T is small)
@@ -922,20 +930,24 @@ mean_rows_kernel(const float* __restrict__ v, int T_cap, const int32_t* __restri
   }
 }
 
-int launch_head_reduce(const float* part_m, const float* part_s, int n_tiles, int part_ld, int T_cap,
-                       const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in, float* row_lse,
-                       float* row_loss, float* loss, float* scratch, cudaStream_t s) {
-  // scratch: [2, n_chunks, part_ld]
+int launch_head_reduce(const float* part_m, const float* part_s, const float* part_z, int n_tiles, int part_ld,
+                       int T_cap, const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in,
+                       float label_smoothing, int64_t n_classes, float* row_lse, float* row_loss, float* loss,
+                       float* scratch, cudaStream_t s) {
+  // scratch: [3, n_chunks, part_ld]
   int n_chunks = n_tiles < 64 ? n_tiles : 64;
   const int tpc = (n_tiles + n_chunks - 1) / n_chunks;
   n_chunks = (n_tiles + tpc - 1) / tpc;
   float* red_m = scratch;
   float* red_s = scratch + static_cast<int64_t>(n_chunks) * part_ld;
+  float* red_z = part_z ? scratch + static_cast<int64_t>(2) * 64 * part_ld : nullptr;
   dim3 g1((T_cap + 127) / 128, n_chunks);
-  head_reduce1_kernel<<<g1, 128, 0, s>>>(part_m, part_s, n_tiles, part_ld, T_cap, t_dev, tpc, red_m, red_s);
+  head_reduce1_kernel<<<g1, 128, 0, s>>>(part_m, part_s, part_z, n_tiles, part_ld, T_cap, t_dev, tpc, red_m, red_s,
+                                         red_z);
   T4R_LAUNCH_CHECK("head_reduce1_kernel");
-  head_reduce2_kernel<<<(T_cap + 127) / 128, 128, 0, s>>>(red_m, red_s, n_chunks, part_ld, T_cap, t_dev, pos_logit,
-                                                           row_tgt_in, row_lse, row_loss);
+  head_reduce2_kernel<<<(T_cap + 127) / 128, 128, 0, s>>>(red_m, red_s, red_z, n_chunks, part_ld, T_cap, t_dev,
+                                                           pos_logit, row_tgt_in, label_smoothing,
+                                                           1.f / static_cast<float>(n_classes), row_lse, row_loss);
   T4R_LAUNCH_CHECK("head_reduce2_kernel");
   if (loss) {
     mean_rows_kernel<<<1, 1024, 0, s>>>(row_loss, T_cap, t_dev, loss);

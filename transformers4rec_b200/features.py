@@ -271,8 +271,9 @@ class TabularSequenceFeatures(nn.Module):
     def forward(self, inputs: Dict[str, torch.Tensor], training: bool = False, testing: bool = False, **kwargs):
         layout, C_width = self._layout()
         cm = self.categorical_module
-        any_t = inputs[layout[0][0]]
-        B, L = any_t.shape[0], any_t.shape[1]
+        seq_t = inputs[cm.item_id] if (cm is not None and cm.item_id) else max(
+            (inputs[n] for n, *_ in layout), key=lambda t: t.dim())
+        B, L = seq_t.shape[0], seq_t.shape[1]
         M = B * L
         if cm is not None and cm.item_id:
             cm.item_seq = inputs[cm.item_id]  # features/embedding.py:244-245 (side channel for the head)
@@ -296,12 +297,19 @@ class TabularSequenceFeatures(nn.Module):
             mask_vec = self.masking.masked_item_embedding.detach().float()
             inference_mlm = row_code.shape[1] != L  # MLM inference appends one position
 
+        def seq(v):
+            # TabularAggregation._expand_non_sequential_features (tabular/base.py:53-63): context
+            # features [B] are repeated for every position of the sequence
+            if v.dim() == 1 or (v.dim() == 2 and v.shape[1] == 1 and L != 1):
+                v = v.reshape(B, 1).expand(B, L)
+            return v.reshape(-1)
+
         cats, conts = [], []
         for name, kind, col, width in layout:
             if kind == "cat":
-                cats.append((cm.embedding_tables[name].weight.detach(), inputs[name].reshape(-1), col))
+                cats.append((cm.embedding_tables[name].weight.detach(), seq(inputs[name]), col))
             else:
-                conts.append((inputs[name].reshape(-1), col))
+                conts.append((seq(inputs[name]), col))
 
         proj = self._projection_linear()
         if proj is not None:

@@ -293,7 +293,7 @@ def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: in
 # --------------------------------------------------------------------------- #
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
-                    nprod=3, events=None):
+                    nprod=3, events=None, label_smoothing=0.0):
     """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank)."""
     _need_cuda(xt_planes, w_planes)
     lib = _lib.load()
@@ -318,6 +318,7 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     ws = WS.get("head", nbytes, dev)
     a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
     a.nprod = nprod
+    a.label_smoothing = float(label_smoothing)
     ev = events if events is not None else HEAD_EVENTS
     if ev is not None:
         a.ev_gemm_start, a.ev_gemm_stop = ev[0].cuda_event, ev[1].cuda_event

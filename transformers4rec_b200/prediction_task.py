@@ -149,13 +149,17 @@ class NextItemPredictionTask(PredictionTask):
                  weight_tying: bool = False, softmax_temperature: float = 1, padding_idx: int = 0,
                  target_dim: int = None, sampled_softmax: Optional[bool] = False, max_n_samples: Optional[int] = 100):
         loss = loss if loss is not None else nn.CrossEntropyLoss()
-        if not isinstance(loss, nn.CrossEntropyLoss) or getattr(loss, "label_smoothing", 0.0) != 0.0 \
-                or loss.reduction != "mean" or loss.weight is not None:
-            raise NotImplementedError("the fused head implements nn.CrossEntropyLoss() with mean reduction")
+        if not isinstance(loss, nn.CrossEntropyLoss) or loss.reduction != "mean" or loss.weight is not None:
+            raise NotImplementedError("the fused head implements nn.CrossEntropyLoss(label_smoothing=...) with mean "
+                                      "reduction and no class weights")
+        label_smoothing = float(getattr(loss, "label_smoothing", 0.0))
+        if label_smoothing and sampled_softmax:
+            raise NotImplementedError("label smoothing with sampled softmax is not on the t4r_b200 hot path")
         if metrics is None:
             metrics = (NDCGAt(top_ks=[10, 20], labels_onehot=True), AvgPrecisionAt(top_ks=[10, 20], labels_onehot=True),
                        RecallAt(top_ks=[10, 20], labels_onehot=True))
         super().__init__(loss=loss, metrics=metrics, task_block=task_block, task_name=task_name)
+        self.label_smoothing = label_smoothing
         self.softmax_temperature = softmax_temperature
         self.weight_tying = weight_tying
         self.padding_idx = padding_idx
@@ -265,7 +269,8 @@ class NextItemPredictionTask(PredictionTask):
                                   col_bias=col_bias, labels=tgt_labels, De=Wd.shape[1], sampled=True)
             else:
                 res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, w_planes, Wd, t_dev=count,
-                                          inv_temperature=inv_tau, want_rank=want_rank, nprod=self.nprod)
+                                          inv_temperature=inv_tau, want_rank=want_rank, nprod=self.nprod,
+                                          label_smoothing=self.label_smoothing)
                 self._last = dict(xt_planes=xt_planes, w_planes=w_planes, count=count, labels=tgt_labels,
                                   De=Wd.shape[1], sampled=False)
             self._last.update(res)
