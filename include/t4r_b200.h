@@ -163,6 +163,23 @@ typedef struct {
 } t4r_linear_args;
 int t4r_linear_fwd(const t4r_linear_args* a /*host*/, void* stream);
 
+/* Fused feed-forward block (K7): out = LayerNorm(residual + gelu_erf(X W1^T + b1) W2^T + b2).
+ * Replaces XLNetFeedForward (HF modeling_xlnet.py:297-305) and GPT2MLP + residual + the following
+ * LayerNorm (HF modeling_gpt2.py:229-243, :305-309).  The [M, hidden] intermediate never reaches HBM:
+ * it is produced in TMEM, GELU'd in registers and fed back to the tensor core from TMEM.
+ *   x_planes  bf16 [2, M, d]       w1_planes bf16 [2, hidden, d]     w2_planes bf16 [2, d, hidden]
+ *   b1 [hidden], b2 [d] (b2 may be NULL), ln_gamma/ln_beta [d]
+ *   residual: fp32 [M, d], or NULL to use x itself (hi + lo of x_planes; the XLNet post-LN form)
+ *   out_f32 [M, d] / out_pre_ln [M, d] / out_planes [2, M, d]: each optional, at least one.
+ * d in {64, 128, 256}; hidden a multiple of 128. */
+int t4r_ffn_fwd(const void* x_planes, int64_t M, int d, int hidden, const void* w1_planes, const float* b1,
+                const void* w2_planes, const float* b2, const float* residual, const float* ln_gamma,
+                const float* ln_beta, float ln_eps, float* out_pre_ln, float* out_f32, void* out_planes, void* stream);
+
+/* debug: probe of the A-from-TMEM form of tcgen05.mma: D[128, N] = bf16(A[128, 64]) * B_hi[N, 64]^T,
+ * B given as planes [2, N, 64]; N in {64, 128, 256}. */
+int t4r_debug_ts_mma(const float* A, const void* b_planes, int N, float* D, void* stream);
+
 /* debug/reference: plain fp32 SIMT GEMM  C[M,N] = A[M,K] * B[N,K]^T (+bias). Used by
  * the GPU tests to check the tensor-core path at sizes the CPU oracle cannot reach. */
 int t4r_debug_sgemm_nt(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,

@@ -74,6 +74,29 @@ def test_linear_epilogues(ops):
         assert ((yp[0].float() + yp[1].float()) - y).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("M,d", [(1, 64), (333, 64), (700, 128), (129, 256), (40960 // 8 + 5, 256)])
+def test_fused_ffn(ops, M, d):
+    """K7: LayerNorm(res + gelu(x W1^T + b1) W2^T + b2), intermediate kept in TMEM -- vs torch fp64."""
+    torch.manual_seed(3)
+    hidden = 4 * d
+    x = torch.randn(M, d, device="cuda")
+    w1 = torch.randn(hidden, d, device="cuda") * 0.08
+    w2 = torch.randn(d, hidden, device="cuda") * 0.05
+    b1, b2 = torch.randn(hidden, device="cuda") * 0.3, torch.randn(d, device="cuda") * 0.3
+    g, beta = torch.rand(d, device="cuda") + 0.5, torch.randn(d, device="cuda")
+    res = torch.randn(M, d, device="cuda")
+    xp, w1p, w2p = ops.split_planes(x), ops.split_planes(w1), ops.split_planes(w2)
+    xd = x.double()
+    inner = torch.nn.functional.gelu(xd @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+    for eps, residual in ((0.03, None), (1e-5, res)):
+        y, yp, pre = ops.ffn(xp, w1p, b1, w2p, b2, (g, beta), eps, residual=residual, want_planes=True, want_pre_ln=True)
+        t = inner + (xd if residual is None else residual.double())
+        ref = torch.nn.functional.layer_norm(t, (d,), g.double(), beta.double(), eps)
+        assert (pre - t.float()).abs().max().item() < 5e-4
+        assert (y - ref.float()).abs().max().item() < 5e-4
+        assert ((yp[0].float() + yp[1].float()) - y).abs().max().item() < 1e-4
+
+
 def test_embed_concat_bit_exact(ops):
     cards = {"item": 1001, "cat": 37, "brand": 500}
     dims = {"item": 64, "cat": 13, "brand": 32}

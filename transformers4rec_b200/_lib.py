@@ -124,6 +124,8 @@ SIGNATURES = {
     "t4r_gather_rows_split": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "t4r_gather_rows_split_i64": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "t4r_linear_fwd": (c_int, [C.POINTER(LinearArgs), _P]),
+    "t4r_ffn_fwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
+    "t4r_debug_ts_mma": (c_int, [_P, _P, c_int, _P, _P]),
     "t4r_debug_sgemm_nt": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "t4r_xlnet_encoder_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "t4r_xlnet_encoder_fwd": (c_int, [C.POINTER(XLNetLayer), c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,

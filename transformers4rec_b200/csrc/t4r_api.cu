@@ -9,6 +9,10 @@
 #include "t4r_common.cuh"
 #include "t4r_internal.h"
 
+#ifndef T4R_FFN_FUSED_DEFAULT
+#define T4R_FFN_FUSED_DEFAULT 1
+#endif
+
 namespace t4r {
 
 static thread_local char g_err[1024] = "";
@@ -127,9 +131,38 @@ extern "C" int t4r_linear_fwd(const t4r_linear_args* a, void* stream) {
   return launch_gemm(pb, ep, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int t4r_ffn_fwd(const void* x_planes, int64_t M, int d, int hidden, const void* w1_planes, const float* b1,
+                           const void* w2_planes, const float* b2, const float* residual, const float* ln_gamma,
+                           const float* ln_beta, float ln_eps, float* out_pre_ln, float* out_f32, void* out_planes,
+                           void* stream) {
+  T4R_REQUIRE(x_planes && w1_planes && w2_planes && b1 && ln_gamma && ln_beta && M > 0, "ffn_fwd: bad arguments");
+  T4R_REQUIRE(out_f32 || out_planes || out_pre_ln, "ffn_fwd: no output requested");
+  T4R_REQUIRE(ffn_fused_supported(d, hidden), "ffn_fwd: d must be 64, 128 or 256 and hidden a multiple of 128 (got %d, %d)",
+              d, hidden);
+  GemmEpilogue ep;
+  ep.bias = b2;
+  if (residual) { ep.residual = residual; ep.ldr = d; }
+  else { ep.residual_planes = static_cast<const __nv_bfloat16*>(x_planes); ep.ldrp = d; ep.residual_plane_stride = M * d; }
+  ep.ln_gamma = ln_gamma; ep.ln_beta = ln_beta; ep.ln_eps = ln_eps;
+  ep.out_pre = out_pre_ln; ep.ldp = d;
+  ep.out_f32 = out_f32; ep.ldo = d;
+  ep.out_planes = static_cast<__nv_bfloat16*>(out_planes); ep.ldpl = d; ep.plane_stride = M * d;
+  return launch_ffn_fused(static_cast<const __nv_bfloat16*>(x_planes), M, d, hidden,
+                          static_cast<const __nv_bfloat16*>(w1_planes), b1, static_cast<const __nv_bfloat16*>(w2_planes), ep,
+                          static_cast<cudaStream_t>(stream));
+}
+
 // ----------------------------------------------------------------------------
 // XLNet encoder
 // ----------------------------------------------------------------------------
+// T4R_FFN_FUSED=0 selects the two-GEMM feed-forward (intermediate planes through HBM) instead of the
+// fused kernel that keeps the GELU'd intermediate in TMEM.
+static bool use_ffn_fused(int d) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("T4R_FFN_FUSED"); on = e ? atoi(e) : T4R_FFN_FUSED_DEFAULT; }
+  return on && ffn_fused_supported(d, 4 * d);
+}
+
 extern "C" size_t t4r_xlnet_encoder_workspace_bytes(int B, int L, int d, int n_head) {
   (void)n_head;
   const size_t M = static_cast<size_t>(B) * L;
@@ -228,32 +261,36 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
       ep.out_planes = h1_p; ep.ldpl = d; ep.plane_stride = M * d;
       T4R_TRY(launch_gemm(pb, ep, s));
     }
-    // feed-forward (HF:xlnet:297-305): gelu(h1 W1^T + b1)
-    {
-      GemmProblem pb;
-      pb.M = M; pb.N = 4 * d; pb.Kp = d;
-      pb.a_planes = h1_p; pb.a_rows = M;
-      pb.b_planes = static_cast<const __nv_bfloat16*>(w.w1_planes); pb.b_rows = 4 * d;
-      GemmEpilogue ep;
-      ep.bias = w.b1; ep.act = T4R_ACT_GELU;
-      ep.out_planes = ff_p; ep.ldpl = 4 * d; ep.plane_stride = M * 4 * d;
-      T4R_TRY(launch_gemm(pb, ep, s));
-    }
-    // out = LN(h1 + ff W2^T + b2)
+    // feed-forward (HF:xlnet:297-305): out = LN(h1 + gelu(h1 W1^T + b1) W2^T + b2)
     {
       float* dst_f = last ? out_f32 : nullptr;
       __nv_bfloat16* dst_p = last ? static_cast<__nv_bfloat16*>(out_planes) : io_p[li & 1];
-      GemmProblem pb;
-      pb.M = M; pb.N = d; pb.Kp = 4 * d;
-      pb.a_planes = ff_p; pb.a_rows = M;
-      pb.b_planes = static_cast<const __nv_bfloat16*>(w.w2_planes); pb.b_rows = d;
       GemmEpilogue ep;
       ep.bias = w.b2;
       ep.residual_planes = h1_p; ep.ldrp = d; ep.residual_plane_stride = M * d;
       ep.ln_gamma = w.ln2_gamma; ep.ln_beta = w.ln2_beta; ep.ln_eps = ln_eps;
       ep.out_f32 = dst_f; ep.ldo = d;
       ep.out_planes = dst_p; ep.ldpl = d; ep.plane_stride = M * d;
-      T4R_TRY(launch_gemm(pb, ep, s));
+      if (use_ffn_fused(d)) {
+        T4R_TRY(launch_ffn_fused(h1_p, M, d, 4 * d, static_cast<const __nv_bfloat16*>(w.w1_planes), w.b1,
+                                 static_cast<const __nv_bfloat16*>(w.w2_planes), ep, s));
+      } else {
+        {
+          GemmProblem pb;
+          pb.M = M; pb.N = 4 * d; pb.Kp = d;
+          pb.a_planes = h1_p; pb.a_rows = M;
+          pb.b_planes = static_cast<const __nv_bfloat16*>(w.w1_planes); pb.b_rows = 4 * d;
+          GemmEpilogue e1;
+          e1.bias = w.b1; e1.act = T4R_ACT_GELU;
+          e1.out_planes = ff_p; e1.ldpl = 4 * d; e1.plane_stride = M * 4 * d;
+          T4R_TRY(launch_gemm(pb, e1, s));
+        }
+        GemmProblem pb;
+        pb.M = M; pb.N = d; pb.Kp = 4 * d;
+        pb.a_planes = ff_p; pb.a_rows = M;
+        pb.b_planes = static_cast<const __nv_bfloat16*>(w.w2_planes); pb.b_rows = d;
+        T4R_TRY(launch_gemm(pb, ep, s));
+      }
       cur_f = dst_f;
       cur_p = dst_p;
     }
@@ -334,21 +371,7 @@ extern "C" int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers, int n_layer, i
       T4R_TRY(launch_gemm(pb, ep, s));
       hc ^= 1; pc ^= 1;
     }
-    {  // c_fc + gelu (HF:gpt2:237-239)
-      GemmProblem pb;
-      pb.M = M; pb.N = 4 * d; pb.Kp = d;
-      pb.a_planes = lnp[pc]; pb.a_rows = M;
-      pb.b_planes = static_cast<const __nv_bfloat16*>(w.w1_planes); pb.b_rows = 4 * d;
-      GemmEpilogue ep;
-      ep.bias = w.b1; ep.act = T4R_ACT_GELU;
-      ep.out_planes = ff_p; ep.ldpl = 4 * d; ep.plane_stride = M * 4 * d;
-      T4R_TRY(launch_gemm(pb, ep, s));
-    }
-    {  // h = h + ff c_proj + b; next = ln_1^{(i+1)}(h) or ln_f(h)  (HF:gpt2:305-309, :617)
-      GemmProblem pb;
-      pb.M = M; pb.N = d; pb.Kp = 4 * d;
-      pb.a_planes = ff_p; pb.a_rows = M;
-      pb.b_planes = static_cast<const __nv_bfloat16*>(w.w2_planes); pb.b_rows = d;
+    {  // c_fc + gelu (HF:gpt2:237-239); h = h + ff c_proj + b; next = ln_1^{(i+1)}(h) or ln_f(h)  (HF:gpt2:305-309, :617)
       GemmEpilogue ep;
       ep.bias = w.b2;
       ep.residual = hbuf[hc]; ep.ldr = d;
@@ -362,7 +385,26 @@ extern "C" int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers, int n_layer, i
         ep.out_pre = hbuf[hc ^ 1]; ep.ldp = d;
         ep.out_planes = lnp[pc ^ 1]; ep.ldpl = d; ep.plane_stride = M * d;
       }
-      T4R_TRY(launch_gemm(pb, ep, s));
+      if (use_ffn_fused(d)) {
+        T4R_TRY(launch_ffn_fused(lnp[pc], M, d, 4 * d, static_cast<const __nv_bfloat16*>(w.w1_planes), w.b1,
+                                 static_cast<const __nv_bfloat16*>(w.w2_planes), ep, s));
+      } else {
+        {
+          GemmProblem pb;
+          pb.M = M; pb.N = 4 * d; pb.Kp = d;
+          pb.a_planes = lnp[pc]; pb.a_rows = M;
+          pb.b_planes = static_cast<const __nv_bfloat16*>(w.w1_planes); pb.b_rows = 4 * d;
+          GemmEpilogue e1;
+          e1.bias = w.b1; e1.act = T4R_ACT_GELU;
+          e1.out_planes = ff_p; e1.ldpl = 4 * d; e1.plane_stride = M * 4 * d;
+          T4R_TRY(launch_gemm(pb, e1, s));
+        }
+        GemmProblem pb;
+        pb.M = M; pb.N = d; pb.Kp = 4 * d;
+        pb.a_planes = ff_p; pb.a_rows = M;
+        pb.b_planes = static_cast<const __nv_bfloat16*>(w.w2_planes); pb.b_rows = d;
+        T4R_TRY(launch_gemm(pb, ep, s));
+      }
       hc ^= 1; pc ^= 1;
     }
   }

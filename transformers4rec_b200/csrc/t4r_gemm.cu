@@ -72,6 +72,10 @@ static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
   return 0;
 }
 
+int make_tmap_public(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows, int rb) {
+  return make_tmap(map, base, rows, Kp, box_rows, rb);
+}
+
 // ----------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------
@@ -754,6 +758,318 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   if (rb == 64) T4R_GEMM_DISPATCH(64);
   T4R_GEMM_DISPATCH(128);
 #undef T4R_GEMM_DISPATCH
+}
+
+
+// ============================================================================
+// K7: fused feed-forward block
+//     Y = epilogue( gelu(X W1^T + b1) W2^T )          epilogue = + b2 + residual -> LayerNorm -> stores
+//     (HF:xlnet:297-305 XLNetFeedForward; HF:gpt2:229-243 GPT2MLP + the residual / next LayerNorm)
+// The 4d-wide intermediate never leaves the SM: per 128-row tile the hidden units are processed in
+// chunks of 128.  GEMM1 (SS form: X and W1 chunk from shared memory via TMA) accumulates the chunk in
+// TMEM; the epilogue warps apply bias + GELU, split to bf16 hi/lo and write the result back to TMEM
+// as the A operand of GEMM2 (TS form: A from TMEM, W2 chunk from shared memory), which accumulates
+// the d-wide output in TMEM across all chunks.  The MMA warp issues GEMM1(c+1) before GEMM2(c), so
+// the GELU of chunk c runs under GEMM1(c+1).  All products are issued three times (split bf16).
+// TMEM columns: Y [0,256)  S [256,384)  G_hi [384,448)  G_lo [448,512).
+// ============================================================================
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct FfnDev {
+  int M;
+  int n_chunks;          // hidden / 128
+  const float* b1;       // [hidden]
+  GemmEpilogue ep;       // final epilogue (bias = b2, residual, LayerNorm, outputs)
+};
+
+constexpr int FFN_HC = 128;                 // hidden units per chunk
+constexpr int FFN_STAGE_BYTES = 64 * 1024;  // one ring stage (see below)
+constexpr int FFN_STAGES = 3;
+constexpr int FFN_SMEM_BYTES = FFN_STAGES * FFN_STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                 const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+                 const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnDev p) {
+  constexpr int KB1 = D / 64;                       // k blocks of GEMM1 (K = d)
+  constexpr int KB2 = FFN_HC / 64;                  // k blocks of GEMM2 per chunk (K = 128)
+  constexpr int XP = BM * 128;                      // X plane bytes per k block
+  constexpr int W1P = FFN_HC * 128;                 // W1 chunk plane bytes per k block
+  constexpr int W2P = D * 128;                      // W2 chunk plane bytes per k block
+  constexpr uint32_t Y_COL = 0, S_COL = 256, GH_COL = 384, GL_COL = 448;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FFN_STAGES * FFN_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + FFN_STAGES;
+  uint64_t* s_full = empty_bar + FFN_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* g_full = s_empty + 1;
+  uint64_t* g_empty = g_full + 1;
+  uint64_t* y_full = g_empty + 1;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+  float2* xch = reinterpret_cast<float2*>(smem + FFN_STAGES * FFN_STAGE_BYTES + 256);
+  float* stg_all = reinterpret_cast<float*>(smem + FFN_STAGES * FFN_STAGE_BYTES + 256 + 4096);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int NC = p.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl);
+    tma_prefetch_desc(&tmW1h); tma_prefetch_desc(&tmW1l);
+    tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < FFN_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 8);
+    mbar_init(g_full, 8); mbar_init(g_empty, 1);
+    mbar_init(y_full, 1); mbar_init(y_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: stages in the exact order the MMA warp consumes them =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_g1 = [&](int m0, int c, int kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * FFN_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], 2 * XP + 2 * W1P);
+        tma_load_2d(st, &tmXh, &full_bar[stage], kb * 64, m0);
+        tma_load_2d(st + XP, &tmXl, &full_bar[stage], kb * 64, m0);
+        tma_load_2d(st + 2 * XP, &tmW1h, &full_bar[stage], kb * 64, c * FFN_HC);
+        tma_load_2d(st + 2 * XP + W1P, &tmW1l, &full_bar[stage], kb * 64, c * FFN_HC);
+        if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto load_g2 = [&](int c, int kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * FFN_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], 2 * W2P);
+        tma_load_2d(st, &tmW2h, &full_bar[stage], c * FFN_HC + kb * 64, 0);
+        tma_load_2d(st + W2P, &tmW2l, &full_bar[stage], c * FFN_HC + kb * 64, 0);
+        if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < KB1; ++kb) load_g1(m0, 0, kb);
+        for (int c = 0; c < NC; ++c) {
+          if (c + 1 < NC)
+            for (int kb = 0; kb < KB1; ++kb) load_g1(m0, c + 1, kb);
+          for (int kb = 0; kb < KB2; ++kb) load_g2(c, kb);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(BM, FFN_HC);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(BM, D);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t ph_s_empty = 0, ph_g_full = 0, ph_y_empty = 0;
+      auto gemm1 = [&]() {  // S = X W1c^T
+        mbar_wait(s_empty, ph_s_empty ^ 1);
+        ph_s_empty ^= 1;
+        tc_fence_after_sync();
+        for (int kb = 0; kb < KB1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(smem + stage * FFN_STAGE_BYTES);
+          const uint32_t a_lo = a_hi + XP, b_hi = a_hi + 2 * XP, b_lo = b_hi + W1P;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_bf16(tmem_base + S_COL, umma_desc_sw128(a_lo + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, (kb | k4) != 0);
+            umma_bf16(tmem_base + S_COL, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_lo + k4 * 32), idesc1, 1u);
+            umma_bf16(tmem_base + S_COL, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(s_full);
+      };
+      for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+        gemm1();
+        for (int c = 0; c < NC; ++c) {
+          if (c + 1 < NC) gemm1();  // runs on the tensor pipe while the epilogue warps GELU chunk c
+          mbar_wait(g_full, ph_g_full);
+          ph_g_full ^= 1;
+          if (c == 0) {  // Y of the previous tile must have been drained
+            mbar_wait(y_empty, ph_y_empty ^ 1);
+            ph_y_empty ^= 1;
+          }
+          tc_fence_after_sync();
+          for (int kb = 0; kb < KB2; ++kb) {  // Y += G_c W2c^T, A (= G) from TMEM
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t b_hi = smem_u32(smem + stage * FFN_STAGE_BYTES);
+            const uint32_t b_lo = b_hi + W2P;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t acol = static_cast<uint32_t>(kb * 32 + k4 * 8);
+              umma_bf16_ts(tmem_base + Y_COL, tmem_base + GL_COL + acol, umma_desc_sw128(b_hi + k4 * 32), idesc2, (c | kb | k4) != 0);
+              umma_bf16_ts(tmem_base + Y_COL, tmem_base + GH_COL + acol, umma_desc_sw128(b_lo + k4 * 32), idesc2, 1u);
+              umma_bf16_ts(tmem_base + Y_COL, tmem_base + GH_COL + acol, umma_desc_sw128(b_hi + k4 * 32), idesc2, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(g_empty);
+          if (c == NC - 1) umma_commit(y_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..9) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t ph_s_full = 0, ph_g_empty = 0, ph_y_full = 0, tile_parity = 0;
+    GemmDev gp;  // view of the final epilogue for epilogue_dense
+    gp.M = p.M; gp.N = D; gp.nkb = 0; gp.nprod = 3; gp.m_dev = nullptr; gp.ep = p.ep;
+    for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
+      const int64_t row0 = static_cast<int64_t>(tile) * BM + quad * 32;
+      for (int c = 0; c < NC; ++c) {
+        // ---- S chunk -> bias + GELU -> split -> G (A operand of GEMM2) in TMEM
+        mbar_wait(s_full, ph_s_full);
+        ph_s_full ^= 1;
+        tc_fence_after_sync();
+        float v[64];
+        tmem_ld<64>(tmem_base + lane_base + S_COL + half * 64, v);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by GEMM1(c+1)
+        const float* b1 = p.b1 + c * FFN_HC + half * 64;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + j);
+          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+        uint32_t gh[32], gl[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[2 * j], h0, l0);
+          split_bf16(v[2 * j + 1], h1, l1);
+          gh[j] = pack_bf16x2(h0, h1);
+          gl[j] = pack_bf16x2(l0, l1);
+        }
+        mbar_wait(g_empty, ph_g_empty ^ 1);  // GEMM2(c-1) has finished reading G
+        ph_g_empty ^= 1;
+        tc_fence_after_sync();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = gh[q * 8 + j];
+          tmem_st8(tmem_base + lane_base + GH_COL + half * 32 + q * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = gl[q * 8 + j];
+          tmem_st8(tmem_base + lane_base + GL_COL + half * 32 + q * 8, r);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_full);
+      }
+      // ---- final epilogue of the tile: Y + b2 + residual -> LayerNorm -> stores
+      mbar_wait(y_full, ph_y_full);
+      ph_y_full ^= 1;
+      tc_fence_after_sync();
+      {
+        const int64_t left = static_cast<int64_t>(p.M) - row0;
+        const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
+        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        epilogue_dense<D, true>(gp, tmem_base + lane_base + Y_COL + half * (D / 2), row0, rows_valid, lane,
+                                static_cast<int64_t>(half) * (D / 2), stg_all + (warp - 2) * STG_WORDS, xm, xo);
+        tile_parity ^= 1;
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(y_empty);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D>
+static int launch_ffn_inst(const CUtensorMap (&tm)[6], const FfnDev& dp, cudaStream_t stream) {
+  auto kern = ffn_fused_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = (dp.M + BM - 1) / BM;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 320, FFN_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dp);
+  T4R_LAUNCH_CHECK("ffn_fused_kernel");
+  return 0;
+}
+
+bool ffn_fused_supported(int d, int hidden) { return (d == 64 || d == 128 || d == 256) && hidden % FFN_HC == 0; }
+
+// x_planes [2, M, d], w1_planes [2, hidden, d], w2_planes [2, d, hidden]; `ep` = final epilogue (bias = b2,
+// residual / residual_planes, ln_gamma/beta/eps, out_f32 / out_pre / out_planes, all with row length d).
+int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden, const __nv_bfloat16* w1_planes,
+                     const float* b1, const __nv_bfloat16* w2_planes, const GemmEpilogue& ep, cudaStream_t stream) {
+  T4R_REQUIRE(ffn_fused_supported(d, hidden), "ffn_fused: unsupported d=%d hidden=%d", d, hidden);
+  T4R_REQUIRE(ep.ln_gamma && ep.ln_beta && b1, "ffn_fused: needs b1 and a LayerNorm epilogue");
+  T4R_REQUIRE(M > 0 && M < (1ll << 31), "ffn_fused: bad M");
+  CUtensorMap tm[6];
+  T4R_TRY(make_tmap(&tm[0], x_planes, M, d, BM, 128));
+  T4R_TRY(make_tmap(&tm[1], x_planes + M * d, M, d, BM, 128));
+  T4R_TRY(make_tmap(&tm[2], w1_planes, hidden, d, FFN_HC, 128));
+  T4R_TRY(make_tmap(&tm[3], w1_planes + static_cast<int64_t>(hidden) * d, hidden, d, FFN_HC, 128));
+  T4R_TRY(make_tmap(&tm[4], w2_planes, d, hidden, d, 128));
+  T4R_TRY(make_tmap(&tm[5], w2_planes + static_cast<int64_t>(d) * hidden, d, hidden, d, 128));
+  FfnDev dp;
+  dp.M = static_cast<int>(M);
+  dp.n_chunks = hidden / FFN_HC;
+  dp.b1 = b1;
+  dp.ep = ep;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    dp.ep.debug = dbg & 1;
+  }
+  if (d == 256) return launch_ffn_inst<256>(tm, dp, stream);
+  if (d == 128) return launch_ffn_inst<128>(tm, dp, stream);
+  return launch_ffn_inst<64>(tm, dp, stream);
 }
 
 }  // namespace t4r

@@ -99,6 +99,11 @@ struct GemmProblem {
 
 int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stream);
 
+// fused feed-forward block (t4r_gemm.cu): Y = epilogue(gelu(X W1^T + b1) W2^T), intermediate kept in TMEM
+bool ffn_fused_supported(int d, int hidden);
+int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden, const __nv_bfloat16* w1_planes,
+                     const float* b1, const __nv_bfloat16* w2_planes, const GemmEpilogue& ep, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------
 // SIMT kernels (t4r_kernels.cu)
 // ---------------------------------------------------------------------------

@@ -244,6 +244,26 @@ def linear(x_planes: torch.Tensor, w_planes: torch.Tensor, K: int, *, bias=None,
     return out_f32, out_planes, out_pre
 
 
+def ffn(x_planes: torch.Tensor, w1_planes: torch.Tensor, b1: torch.Tensor, w2_planes: torch.Tensor, b2, ln, ln_eps: float,
+        *, residual=None, want_f32=True, want_planes=False, want_pre_ln=False):
+    """LayerNorm(residual + gelu(X W1^T + b1) W2^T + b2) in one kernel; residual None -> X itself."""
+    _need_cuda(x_planes, w1_planes, w2_planes)
+    M, d = x_planes.shape[1], x_planes.shape[2]
+    hidden = w1_planes.shape[1]
+    dev = x_planes.device
+    b1 = _f32c(b1.detach())
+    b2 = _f32c(b2.detach()) if b2 is not None else None
+    g, b = _f32c(ln[0].detach()), _f32c(ln[1].detach())
+    residual = _f32c(residual) if residual is not None else None
+    out_f32 = torch.empty((M, d), dtype=torch.float32, device=dev) if want_f32 else None
+    out_pre = torch.empty((M, d), dtype=torch.float32, device=dev) if want_pre_ln else None
+    out_planes = torch.empty((2, M, d), dtype=torch.bfloat16, device=dev) if want_planes else None
+    check(_lib.load().t4r_ffn_fwd(ptr(x_planes), M, d, hidden, ptr(w1_planes), ptr(b1), ptr(w2_planes), ptr(b2),
+                                  ptr(residual), ptr(g), ptr(b), ln_eps, ptr(out_pre), ptr(out_f32), ptr(out_planes),
+                                  _stream()), "t4r_ffn_fwd")
+    return out_f32, out_planes, out_pre
+
+
 def debug_sgemm_nt(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(A, B, bias)
     A, B = _f32c(A), _f32c(B)
