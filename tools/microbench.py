@@ -57,6 +57,9 @@ def main():
     if on("qkv"):
         timeit("qkv gemm N=768 K=256 (f32 out)", lambda: ops.linear(xp, w_qkv, d, want_planes=False),
                flops=2 * M * 3 * d * d)
+    if on("qkvp"):
+        timeit("qkv gemm N=768 K=256 (planes out)", lambda: ops.linear(xp, w_qkv, d, want_f32=False, want_planes=True),
+               flops=2 * M * 3 * d * d)
     if on("ffn1"):
         timeit("ffn1 gemm N=1024 K=256 gelu", lambda: ops.linear(xp, w_1, d, bias=b1, act=_lib.ACT_GELU, want_f32=False),
                flops=2 * M * 4 * d * d)
@@ -66,6 +69,9 @@ def main():
     if on("ffn2"):
         timeit("ffn2 gemm N=256 K=1024 res+LN", lambda: ops.linear(ffp, w_2, 4 * d, bias=b2, residual=x, ln=(g, bt), ln_eps=0.03),
                flops=2 * M * 4 * d * d)
+    if on("ffn"):
+        timeit("fused ffn d=256 hidden=1024 res+LN", lambda: ops.ffn(xp, w_1, b1, w_2, b2, (g, bt), 0.03, want_f32=False, want_planes=True),
+               flops=2 * 2 * M * 4 * d * d)
     if on("proj"):
         code = torch.zeros(M, dtype=torch.uint8, device=dev)
         timeit("proj gemm N=256 K=256 relu+mask", lambda: ops.linear(xp, w_o, d, bias=b2, act=_lib.ACT_RELU, row_code=code, mask_vec=b2),

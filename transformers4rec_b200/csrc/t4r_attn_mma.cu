@@ -44,11 +44,7 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
   mma_bf16(c, ah, bh);
 }
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(x, h0, l0);
-  split_bf16(y, h1, l1);
-  hi = pack_bf16x2(h0, h1);
-  lo = pack_bf16x2(l0, l1);
+  split_bf16x2(x, y, hi, lo);
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {

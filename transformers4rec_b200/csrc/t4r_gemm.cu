@@ -262,13 +262,7 @@ __device__ __forceinline__ void warp_store_planes(float* stg_f, const float (&v)
   uint32_t* stg = reinterpret_cast<uint32_t*>(stg_f);
   uint32_t h[16], l[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[2 * j], h0, l0);
-    split_bf16(v[2 * j + 1], h1, l1);
-    h[j] = pack_bf16x2(h0, h1);
-    l[j] = pack_bf16x2(l0, l1);
-  }
+  for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], h[j], l[j]);
   uint4 t[8];
 #pragma unroll
   for (int pl = 0; pl < 2; ++pl) {
@@ -903,6 +897,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           tc_fence_after_sync();
           const uint32_t a_hi = smem_u32(smem + stage * FFN_STAGE_BYTES);
           const uint32_t a_lo = a_hi + XP, b_hi = a_hi + 2 * XP, b_lo = b_hi + W1P;
+          if (!(p.ep.debug & 4))  // timing experiment: no GEMM1 MMAs
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             umma_bf16(tmem_base + S_COL, umma_desc_sw128(a_lo + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, (kb | k4) != 0);
@@ -930,6 +925,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             tc_fence_after_sync();
             const uint32_t b_hi = smem_u32(smem + stage * FFN_STAGE_BYTES);
             const uint32_t b_lo = b_hi + W2P;
+            if (!(p.ep.debug & 8))  // timing experiment: no GEMM2 MMAs
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint32_t acol = static_cast<uint32_t>(kb * 32 + k4 * 8);
@@ -976,13 +972,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
         uint32_t gh[32], gl[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * j], h0, l0);
-          split_bf16(v[2 * j + 1], h1, l1);
-          gh[j] = pack_bf16x2(h0, h1);
-          gl[j] = pack_bf16x2(l0, l1);
-        }
+        for (int j = 0; j < 32; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], gh[j], gl[j]);
         mbar_wait(g_empty, ph_g_empty ^ 1);  // GEMM2(c-1) has finished reading G
         ph_g_empty ^= 1;
         tc_fence_after_sync();
@@ -1065,7 +1055,7 @@ int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    dp.ep.debug = dbg & 1;
+    dp.ep.debug = dbg & (1 | 4 | 8);
   }
   if (d == 256) return launch_ffn_inst<256>(tm, dp, stream);
   if (d == 128) return launch_ffn_inst<128>(tm, dp, stream);

@@ -74,10 +74,11 @@ embed_concat_kernel(const __grid_constant__ FeatDev fd, int64_t M, int C, int Cp
                 }
               }
               if (planes) {
-                __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-                split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1); split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
-                *reinterpret_cast<uint2*>(planes + row * Cp + c) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-                *reinterpret_cast<uint2*>(planes + (M + row) * Cp + c) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+                uint32_t h01, l01, h23, l23;
+                split_bf16x2(x.x, x.y, h01, l01);
+                split_bf16x2(x.z, x.w, h23, l23);
+                *reinterpret_cast<uint2*>(planes + row * Cp + c) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(planes + (M + row) * Cp + c) = make_uint2(l01, l23);
               }
             }
           }
@@ -701,11 +702,11 @@ attn_kernel(const float* __restrict__ qkv, const float* __restrict__ r, const fl
         __nv_bfloat16* lo = hi + plane_stride;
 #pragma unroll
         for (int c4 = 0; c4 < V4; ++c4) {
-          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-          split_bf16(o[c4].x * inv, h0, l0); split_bf16(o[c4].y * inv, h1, l1);
-          split_bf16(o[c4].z * inv, h2, l2); split_bf16(o[c4].w * inv, h3, l3);
-          *reinterpret_cast<uint2*>(hi + 4 * c4) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-          *reinterpret_cast<uint2*>(lo + 4 * c4) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+          uint32_t h01, l01, h23, l23;
+          split_bf16x2(o[c4].x * inv, o[c4].y * inv, h01, l01);
+          split_bf16x2(o[c4].z * inv, o[c4].w * inv, h23, l23);
+          *reinterpret_cast<uint2*>(hi + 4 * c4) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(lo + 4 * c4) = make_uint2(l01, l23);
         }
       }
     }
