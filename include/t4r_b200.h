@@ -74,6 +74,53 @@ int t4r_embed_concat_fwd(const t4r_feature_list* feats /*host*/, int64_t M, int 
                          void* out_planes, int32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * K1b general input block: every feature kind, per-feature LayerNorm and aggregation that
+ *     TabularSequenceFeatures can be configured with, one kernel.
+ *     replaces: SoftEmbedding.forward            features/embedding.py:517-556
+ *               TabularLayerNorm.forward         tabular/transformations.py:95-141
+ *               ConcatFeatures / ElementwiseSum / ElementwiseSumItemMulti
+ *                                                tabular/aggregation.py:35-47,139-193
+ *               _expand_non_sequential_features  tabular/base.py:53-63 (per_session)
+ *               the "continuous_projection" branch features/tabular.py:88-118 enters as a DENSE
+ *               feature (its MLP runs through t4r_linear_fwd first)
+ *     Features are listed in sorted-name order (aggregation.py:42-47).  For the element-wise
+ *     aggregations every feature must have width C (the reference raises otherwise).
+ * ------------------------------------------------------------------------- */
+#define T4R_FEAT_CAT 0   /* input: int64 ids; table [card, dim]                                  */
+#define T4R_FEAT_CONT 1  /* input: fp32 scalars; dim = 1                                         */
+#define T4R_FEAT_SOFT 2  /* input: fp32 scalars; softmax(x*soft_w + soft_b) [card] @ table [card, dim] */
+#define T4R_FEAT_DENSE 3 /* input: fp32 [rows, dim] already computed                             */
+#define T4R_AGG_CONCAT 0
+#define T4R_AGG_SUM 1            /* "element-wise-sum"            */
+#define T4R_AGG_SUM_ITEM_MULTI 2 /* "element-wise-sum-item-multi": item * sum(others) */
+typedef struct {
+  int kind;
+  int dim;               /* output width of the feature                                  */
+  int col;               /* first output column (concat only)                            */
+  int card;              /* CAT: table rows (ids outside [0, card) raise err_flag); SOFT: bins */
+  int per_session;       /* 1: one input entry per session, repeated over its L positions */
+  int reserved;
+  const void* input;
+  const float* table;
+  const float* soft_w;   /* [card]  Linear(1, card).weight                                */
+  const float* soft_b;   /* [card]                                                        */
+  const float* ln_gamma; /* [dim] or NULL: LayerNorm over this feature before aggregation */
+  const float* ln_beta;
+} t4r_feature;
+/* M = B*L output rows; C = output width (sum of widths for concat, the common width otherwise). */
+int t4r_input_block_fwd(const t4r_feature* feats /*host, n_feats*/, int n_feats, int64_t M, int L, int agg,
+                        int item_feature /*index into feats, item-multi only*/, float ln_eps, int C, float* out_f32,
+                        void* out_planes, int32_t* err_flag, void* stream);
+
+/* StochasticSwapNoise.augment (tabular/transformations.py:54-92) on one tensor of n 4- or 8-byte
+ * elements: positions with keep_mask and u < replacement_prob take values drawn (through `perm`,
+ * a permutation of the kept positions' count) from the kept values of the same tensor.
+ * keep_mask (uint8, NULL = all) is read at [(i / inner) * keep_stride]; scratch: int32 [n]. */
+int t4r_swap_noise(const void* values, int elem_bytes, int64_t n, const uint8_t* keep_mask, int64_t keep_stride,
+                   int inner, const float* u, float replacement_prob, const int64_t* perm, int32_t* scratch_pool_pos,
+                   void* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K3  mask / label generation (integer, bit-exact)
  *     replaces: MaskedLanguageModeling._compute_masked_targets masking.py:376-470
  *               CausalLanguageModeling._compute_masked_targets masking.py:274-300
@@ -308,6 +355,16 @@ int t4r_head_logits(const void* xt_planes, const void* w_planes, int T_cap, cons
  * replaces RecallAt._metric + RankingMetric.update ranking_metric.py:52-63,111-147 */
 int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks /*host*/,
                           int n_ks, float* out, void* stream);
+
+/* The other ranking metrics of ranking_metric.py:73-319 from the same ranks (one relevant item per
+ * row): precision = [r<k]/k, reciprocal rank (avg_precision == mrr) = [r<k]/(r+1),
+ * dcg (== ndcg) = [r<k]/log2(r+2); out[j] = mean over rows. */
+#define T4R_METRIC_RECALL 0
+#define T4R_METRIC_PRECISION 1
+#define T4R_METRIC_RR 2
+#define T4R_METRIC_DCG 3
+int t4r_metrics_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, int kind,
+                           const int32_t* ks /*host*/, int n_ks, float* out, void* stream);
 
 /* top-k (k <= 64) scores and ids of materialised logits, lower id first on ties
  * (model/prediction_task.py:467-470 torch.topk on the inference path). */

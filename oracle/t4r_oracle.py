@@ -120,6 +120,65 @@ def embed_concat(
     return torch.cat([outs[k] for k in sorted(outs.keys())], dim=-1)
 
 
+def expand_non_sequential(features: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """tabular/base.py:53-63: features without a sequence axis ([B, dim]) are repeated
+    over the L positions of the sequential ones."""
+    seq = {k: v for k, v in features.items() if v.dim() >= 3}
+    if not seq:
+        return dict(features)
+    L = next(iter(seq.values())).shape[1]
+    return {k: (v if v.dim() >= 3 else v.unsqueeze(1).repeat(1, L, 1)) for k, v in features.items()}
+
+
+def tabular_layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """tabular/transformations.py:95-141: ``nn.LayerNorm(dim)`` on one feature, before aggregation."""
+    return F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+
+
+def soft_embedding(x: torch.Tensor, proj_weight: torch.Tensor, proj_bias: torch.Tensor,
+                   table: torch.Tensor) -> torch.Tensor:
+    """features/embedding.py:517-556 (SoftEmbedding.forward): ``softmax(Linear(1, n)(x))``
+    weighted mean of the n embedding rows.  proj_weight [n, 1], proj_bias [n], table [n, dim]."""
+    w = torch.softmax(F.linear(x.float().unsqueeze(-1), proj_weight, proj_bias), dim=-1)
+    return (w.unsqueeze(-1) * table).sum(-2)
+
+
+def aggregate(features: Dict[str, torch.Tensor], mode: str = "concat", item_name: Optional[str] = None) -> torch.Tensor:
+    """tabular/aggregation.py:35-47 (concat), :139-157 (element-wise-sum), :160-193
+    (element-wise-sum-item-multi); all iterate the features in sorted-name order."""
+    feats = expand_non_sequential(features)
+    names = sorted(feats.keys())
+    if mode == "concat":
+        return torch.cat([feats[n] for n in names], dim=-1)
+    if len(set(v.shape for v in feats.values())) != 1:
+        raise ValueError("The shapes of all input features are not equal, which is required for"
+                         " element-wise aggregation: {}".format({k: v.shape for k, v in feats.items()}))
+    if mode == "element-wise-sum":
+        return torch.stack([feats[n] for n in names], dim=0).sum(dim=0)
+    if mode == "element-wise-sum-item-multi":
+        others = torch.stack([feats[n] for n in names if n != item_name], dim=0).sum(dim=0)
+        return feats[item_name].multiply(others)
+    raise ValueError(mode)
+
+
+def stochastic_swap_noise(values: torch.Tensor, mask: Optional[torch.Tensor], u: torch.Tensor, perm: torch.Tensor,
+                          replacement_prob: float) -> torch.Tensor:
+    """tabular/transformations.py:54-92 (StochasticSwapNoise.augment, training mode) with the
+    draws made explicit: ``u`` replaces ``torch.bernoulli`` (replace where u < p), ``perm``
+    replaces ``torch.randperm(number of kept values)``."""
+    if mask is not None and values.dim() == mask.dim() - 1:
+        mask = mask[:, 0]
+    rep = bernoulli_from_uniform(u, replacement_prob)
+    if mask is not None:
+        rep = rep & mask
+    n_rep = int(rep.sum())
+    pool = torch.masked_select(values, mask) if mask is not None else values.reshape(-1).clone()
+    sampled = pool[perm][:n_rep]
+    out = values.clone()
+    out[rep] = sampled
+    return out
+
+
 def project_relu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """block/mlp.py:123-144: ``Linear`` + ``ReLU`` (the projection MLPBlock built at
     features/sequence.py:213-219)."""
@@ -467,6 +526,55 @@ def recall_at(ks, scores: torch.Tensor, labels: torch.Tensor, labels_onehot: boo
 def recall_at_mean(ks, scores, labels, labels_onehot=True) -> torch.Tensor:
     """ranking_metric.py:52-63: one update = mean over rows of the batch."""
     return recall_at(ks, scores, labels, labels_onehot).mean(0)
+
+
+def _topk_labels(ks, scores: torch.Tensor, labels: torch.Tensor, labels_onehot: bool):
+    """utils/torch_utils.py:226-238 (extract_topk / tranform_label_to_onehot)."""
+    if labels_onehot:
+        labels = F.one_hot(labels.reshape(-1).long(), scores.size(-1)).float()
+    scores = scores.view(-1, scores.size(-1))
+    labels = labels.view(-1, labels.size(-1)).float()
+    topk_scores, topk_indices = torch.topk(scores, int(max(ks)))
+    return topk_scores, torch.gather(labels, 1, topk_indices), labels
+
+
+def precision_at(ks, scores, labels, labels_onehot=True) -> torch.Tensor:
+    """ranking_metric.py:73-103."""
+    _, tl, _ = _topk_labels(ks, scores, labels, labels_onehot)
+    return torch.stack([tl[:, : int(k)].sum(dim=1) / float(k) for k in ks], dim=1)
+
+
+def avg_precision_at(ks, scores, labels, labels_onehot=True) -> torch.Tensor:
+    """ranking_metric.py:150-190."""
+    _, tl, lab = _topk_labels(ks, scores, labels, labels_onehot)
+    max_k = int(max(ks))
+    prec = torch.stack([tl[:, :j].sum(dim=1) / float(j) for j in range(1, max_k + 1)], dim=1)
+    rel = prec * tl
+    num_relevant = lab.sum(dim=1)
+    return torch.stack([rel[:, : int(k)].sum(dim=1) / num_relevant.clamp(min=1, max=int(k)) for k in ks], dim=1)
+
+
+def dcg_at(ks, scores, labels, labels_onehot=True, log_base: int = 2) -> torch.Tensor:
+    """ranking_metric.py:193-238."""
+    _, tl, _ = _topk_labels(ks, scores, labels, labels_onehot)
+    pos = torch.arange(int(max(ks)), dtype=torch.float32)
+    base = torch.log(torch.tensor([float(log_base)])).item()
+    disc = 1 / (torch.log(pos + 2) / base)
+    return torch.stack([(tl[:, : int(k)] * disc[: int(k)]).sum(dim=1) for k in ks], dim=1)
+
+
+def ndcg_at(ks, scores, labels, labels_onehot=True) -> torch.Tensor:
+    """ranking_metric.py:241-281: DCG of the ranking / DCG of the ideal ranking."""
+    ts, tl, _ = _topk_labels(ks, scores, labels, labels_onehot)
+    gains = dcg_at(ks, ts, tl, labels_onehot=False)
+    ideal = dcg_at(ks, tl, tl, labels_onehot=False)
+    return torch.where(ideal != 0, gains / ideal.clamp(min=1e-30), torch.zeros_like(gains))
+
+
+def mrr_at(ks, scores, labels, labels_onehot=True) -> torch.Tensor:
+    """ranking_metric.py:284-319."""
+    _, tl, _ = _topk_labels(ks, scores, labels, labels_onehot)
+    return torch.stack([(tl[:, : int(k)] / (torch.arange(int(k)) + 1)).max(dim=1).values for k in ks], dim=1)
 
 
 # --------------------------------------------------------------------------- #

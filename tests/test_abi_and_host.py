@@ -133,3 +133,31 @@ def test_log_uniform_sampler_host_side():
     assert smp.dist[0] == 0 and abs(smp.dist.sum().item() - 1.0) < 1e-5
     with pytest.raises(ValueError):
         tr.LogUniformSampler(max_n_samples=0, max_id=10)
+
+
+def test_widened_input_block_surface():
+    """SURVEY §8f N4 options of TabularSequenceFeatures.from_schema: layout, widths, reference errors."""
+    import ctypes as C
+    import transformers4rec_b200.torch as tr
+    from transformers4rec_b200 import _lib
+    assert C.sizeof(_lib.Feature) == 6 * 4 + 6 * 8
+    schema = _schema(tr)
+    soft = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_soft_embeddings=True,
+                                                  aggregation="concat", post="layer-norm")
+    assert isinstance(soft.continuous_module, tr.SoftEmbeddingFeatures)
+    assert soft.output_size()[-1] == 64 + 64 + 8  # two categorical tables + one soft embedding (dim 8 default)
+    assert set(soft.categorical_module.post.feature_layer_norm.keys()) == {"item_id/list", "category/list"}
+    assert "to_merge.continuous_module.embedding_tables.price/list.projection_layer.weight" in soft.state_dict()
+    proj = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_projection=32,
+                                                  aggregation="concat")
+    assert [n for n, *_ in proj._layout()[0]] == ["category/list", "continuous_projection", "item_id/list"]
+    assert proj.output_size()[-1] == 64 + 32 + 64
+    with pytest.raises(ValueError, match="required for element-wise aggregation"):
+        tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, aggregation="element-wise-sum").output_size()
+    ok = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, aggregation="element-wise-sum-item-multi",
+                                                continuous_soft_embeddings=True, soft_embedding_dim_default=64)
+    assert ok.output_size()[-1] == 64
+    with pytest.raises(NotImplementedError):
+        tr.TabularSequenceFeatures.from_schema(schema, aggregation="stack")
+    assert set(tr.ranking_metrics_registry) >= {"precision_at", "recall_at", "avg_precision_at", "map", "dcg_at",
+                                                "ndcg_at", "mrr_at"}

@@ -43,6 +43,19 @@ class FeatureList(C.Structure):
     ]
 
 
+class Feature(C.Structure):
+    _fields_ = [
+        ("kind", c_int), ("dim", c_int), ("col", c_int), ("card", c_int), ("per_session", c_int), ("reserved", c_int),
+        ("input", c_void_p), ("table", c_void_p), ("soft_w", c_void_p), ("soft_b", c_void_p),
+        ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+    ]
+
+
+FEAT_CAT, FEAT_CONT, FEAT_SOFT, FEAT_DENSE = 0, 1, 2, 3
+AGG_CONCAT, AGG_SUM, AGG_SUM_ITEM_MULTI = 0, 1, 2
+METRIC_RECALL, METRIC_PRECISION, METRIC_RR, METRIC_DCG = 0, 1, 2, 3
+
+
 class LinearArgs(C.Structure):
     _fields_ = [
         ("M", c_int64),
@@ -124,6 +137,9 @@ SIGNATURES = {
     "t4r_gather_rows_split": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "t4r_gather_rows_split_i64": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "t4r_linear_fwd": (c_int, [C.POINTER(LinearArgs), _P]),
+    "t4r_input_block_fwd": (c_int, [C.POINTER(Feature), c_int, c_int64, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P]),
+    "t4r_swap_noise": (c_int, [_P, c_int, c_int64, _P, c_int64, c_int, _P, c_float, _P, _P, _P, _P]),
+    "t4r_metrics_from_ranks": (c_int, [_P, _P, c_int, c_int, C.POINTER(C.c_int32), c_int, _P, _P]),
     "t4r_ffn_fwd": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "t4r_debug_ts_mma": (c_int, [_P, _P, c_int, _P, _P]),
     "t4r_debug_sgemm_nt": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P]),

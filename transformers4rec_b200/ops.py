@@ -144,6 +144,94 @@ def embed_concat(cats: List[Tuple[torch.Tensor, torch.Tensor, int]], conts: List
     return out_f32, planes, err
 
 
+def input_block(feats: List[dict], M: int, L: int, C_width: int, agg: int = _lib.AGG_CONCAT, item_feature: int = -1,
+                ln_eps: float = 1e-5, want_f32: bool = True, want_planes: bool = False):
+    """General input block (t4r_input_block_fwd).  ``feats``: dicts in sorted-name order with keys
+    kind, dim, col, input and, by kind, table / soft_w / soft_b / card, optional ln=(gamma, beta),
+    per_session."""
+    if not feats or len(feats) > _lib.T4R_MAX_FEATURES:
+        raise _lib.T4RError(f"1..{_lib.T4R_MAX_FEATURES} features per call")
+    arr = (_lib.Feature * len(feats))()
+    keep = []
+    dev = None
+
+    def f32(t):
+        t = _f32c(t.detach())
+        keep.append(t)
+        return t.data_ptr()
+
+    for i, f in enumerate(feats):
+        a = arr[i]
+        a.kind, a.dim, a.col = int(f["kind"]), int(f["dim"]), int(f.get("col", 0))
+        a.per_session = 1 if f.get("per_session") else 0
+        x = f["input"]
+        _need_cuda(x)
+        dev = x.device
+        if a.kind == _lib.FEAT_CAT:
+            x = x.reshape(-1)
+            x = (x if x.dtype == torch.int64 else x.long()).contiguous()
+            keep.append(x)
+            a.input = x.data_ptr()
+        else:
+            a.input = f32(x.reshape(-1) if a.kind != _lib.FEAT_DENSE else x.reshape(-1, a.dim))
+        if a.kind in (_lib.FEAT_CAT, _lib.FEAT_SOFT):
+            _need_cuda(f["table"])
+            a.table = f32(f["table"])
+            a.card = int(f["table"].shape[0])
+        if a.kind == _lib.FEAT_SOFT:
+            a.soft_w, a.soft_b = f32(f["soft_w"].reshape(-1)), f32(f["soft_b"].reshape(-1))
+        if f.get("ln") is not None:
+            a.ln_gamma, a.ln_beta = f32(f["ln"][0]), f32(f["ln"][1])
+    out_f32 = torch.empty((M, C_width), dtype=torch.float32, device=dev) if want_f32 else None
+    planes = torch.empty((2, M, round_up64(C_width)), dtype=torch.bfloat16, device=dev) if want_planes else None
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().t4r_input_block_fwd(arr, len(feats), M, L, agg, item_feature, ln_eps, C_width, ptr(out_f32),
+                                          ptr(planes), ptr(err), _stream()), "t4r_input_block_fwd")
+    return out_f32, planes, err
+
+
+def swap_noise(values: torch.Tensor, keep_mask: Optional[torch.Tensor], u: torch.Tensor, perm: torch.Tensor,
+               replacement_prob: float) -> torch.Tensor:
+    """StochasticSwapNoise.augment with explicit draws: ``u`` uniforms (shape of ``values``), ``perm`` a
+    permutation of range(number of kept positions)."""
+    _need_cuda(values, keep_mask, u, perm)
+    if values.dtype not in (torch.int64, torch.float32):
+        raise _lib.T4RError(f"swap_noise: int64 or float32 tensors (got {values.dtype})")
+    v = values.contiguous()
+    n = v.numel()
+    inner, stride, km = 1, 1, None
+    if keep_mask is not None:
+        km = keep_mask
+        if v.dim() == km.dim() - 1:  # transformations.py:63-65: context feature, mask[:, 0]
+            stride = km.shape[1] if km.dim() > 1 else 1
+            km = km.contiguous()
+        else:
+            km = km.contiguous()
+            inner = max(1, n // km.numel())
+        km = km.view(torch.uint8) if km.dtype == torch.bool else km.to(torch.uint8)
+    u = _f32c(u).reshape(-1)
+    perm = perm.long().contiguous()
+    out = torch.empty_like(v)
+    scratch = torch.empty(n, dtype=torch.int32, device=v.device)
+    check(_lib.load().t4r_swap_noise(ptr(v), v.element_size(), n, ptr(km), stride, inner, ptr(u), float(replacement_prob),
+                                     ptr(perm), ptr(scratch), ptr(out), _stream()), "t4r_swap_noise")
+    return out
+
+
+def metrics_from_ranks(row_rank: torch.Tensor, ks: Sequence[int], kind: int, t_dev=None) -> torch.Tensor:
+    _need_cuda(row_rank)
+    outs = []
+    ks = [int(k) for k in ks]
+    for i in range(0, len(ks), 4):
+        part = ks[i:i + 4]
+        out = torch.empty(len(part), dtype=torch.float32, device=row_rank.device)
+        arr = (C.c_int32 * len(part))(*part)
+        check(_lib.load().t4r_metrics_from_ranks(ptr(row_rank), ptr(t_dev), row_rank.numel(), kind, arr, len(part),
+                                                 ptr(out), _stream()), "t4r_metrics_from_ranks")
+        outs.append(out)
+    return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+
 # --------------------------------------------------------------------------- #
 # K3
 # --------------------------------------------------------------------------- #

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class RankingMetric:
@@ -54,7 +54,7 @@ class RankingMetric:
 
 
 class RecallAt(RankingMetric):
-    """ranking_metric.py:111-147."""
+    """ranking_metric.py:106-147."""
 
     def _from_ranks(self, row_rank, t_dev):
         outs = []
@@ -64,28 +64,40 @@ class RecallAt(RankingMetric):
         return torch.cat(outs)
 
 
-class NDCGAt(RankingMetric):
-    """ranking_metric.py:247-319 specialised to one relevant item: 1/log2(rank+2) if rank < k."""
+class PrecisionAt(RankingMetric):
+    """ranking_metric.py:73-103 with one relevant item per row: [rank < k] / k."""
 
     def _from_ranks(self, row_rank, t_dev):
-        r = row_rank.float()
-        n = row_rank.numel() if t_dev is None else None
-        valid = torch.ones_like(r, dtype=torch.bool) if t_dev is None else (
-            torch.arange(r.numel(), device=r.device) < t_dev)
-        gain = 1.0 / torch.log2(r + 2.0)
-        cnt = valid.sum().clamp(min=1)
-        return torch.stack([(gain * ((r < k) & valid)).sum() / cnt for k in self.top_ks])
+        return ops.metrics_from_ranks(row_rank, self.top_ks, _lib.METRIC_PRECISION, t_dev)
 
 
 class AvgPrecisionAt(RankingMetric):
-    """ranking_metric.py:150-196 specialised to one relevant item: 1/(rank+1) if rank < k."""
+    """ranking_metric.py:150-190 with one relevant item per row: [rank < k] / (rank + 1)."""
 
     def _from_ranks(self, row_rank, t_dev):
-        r = row_rank.float()
-        valid = torch.ones_like(r, dtype=torch.bool) if t_dev is None else (
-            torch.arange(r.numel(), device=r.device) < t_dev)
-        cnt = valid.sum().clamp(min=1)
-        return torch.stack([((1.0 / (r + 1.0)) * ((r < k) & valid)).sum() / cnt for k in self.top_ks])
+        return ops.metrics_from_ranks(row_rank, self.top_ks, _lib.METRIC_RR, t_dev)
 
 
-MeanReciprocalRankAt = AvgPrecisionAt  # identical for a single relevant item
+class MeanReciprocalRankAt(AvgPrecisionAt):
+    """ranking_metric.py:284-319: identical to AvgPrecisionAt when a row has a single relevant item."""
+
+
+class DCGAt(RankingMetric):
+    """ranking_metric.py:193-238 with one relevant item per row: [rank < k] / log2(rank + 2)."""
+
+    def _from_ranks(self, row_rank, t_dev):
+        return ops.metrics_from_ranks(row_rank, self.top_ks, _lib.METRIC_DCG, t_dev)
+
+
+class NDCGAt(DCGAt):
+    """ranking_metric.py:241-281: the ideal DCG of a single relevant item is 1, so NDCG == DCG."""
+
+
+ranking_metrics_registry = {
+    "precision_at": PrecisionAt, "precision": PrecisionAt,
+    "recall_at": RecallAt, "recall": RecallAt,
+    "avg_precision_at": AvgPrecisionAt, "avg_precision": AvgPrecisionAt, "map": AvgPrecisionAt,
+    "dcg_at": DCGAt, "dcg": DCGAt,
+    "ndcg_at": NDCGAt, "ndcg": NDCGAt,
+    "mrr_at": MeanReciprocalRankAt, "mrr": MeanReciprocalRankAt,
+}
