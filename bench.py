@@ -34,6 +34,12 @@ CONFIGS = {
     # BASELINE.json configs[0] (the reference's own CPU-runnable case); used by --workload config1
     "config1": dict(V=10_001, De=64, d=64, H=4, NL=2, L=20, B=512, arch="xlnet", masking="mlm",
                     label="synthetic yoochoose schema, 10K-item table, seq_len=20, XLNet d_model=64 2-layer"),
+    # BASELINE.json configs[3]: the item table (= tied output layer) row-sharded over the ranks;
+    # one all-to-all on the lookup, one all-gather of (lse, label-logit) pairs on the head.  Parity-test case and
+    # scaling probe (`--workload config4 --gpus N`), not the default bench line.
+    "config4": dict(V=10_000_001, De=256, d=256, H=8, NL=4, L=20, B=2048, arch="xlnet", masking="mlm", sharded=True,
+                    label="10M-item table row-sharded, tied-weight full softmax, XLNet-base d_model=256 4-layer, MLM, "
+                          "batch=2048 per GPU"),
 }
 METRIC = "sessions/sec (fwd+loss)"
 
@@ -121,9 +127,10 @@ def build_product_model(cfg, device):
 
     torch.manual_seed(1)
     schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", cfg["V"] - 1, tags=[tr.Tags.ITEM_ID])])
+    extra = dict(shard_item_table=True, device=device) if cfg.get("sharded") else {}  # allocate only this rank's rows
     inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=cfg["L"], d_output=cfg["d"],
                                                     masking=cfg["masking"],
-                                                    embedding_dims={"item_id/list": cfg["De"]})
+                                                    embedding_dims={"item_id/list": cfg["De"]}, **extra)
     tcfg = (tr.XLNetConfig if cfg["arch"] == "xlnet" else tr.GPT2Config).build(
         d_model=cfg["d"], n_head=cfg["H"], n_layer=cfg["NL"], total_seq_length=cfg["L"])
     model = tcfg.to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
@@ -180,7 +187,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config_desc = {"workload": f"BASELINE.json {args.workload}: {cfg['label']}", "per_gpu_batch": cfg["B"],
                    "global_batch": cfg["B"] * world, "seq_len": cfg["L"], "items": cfg["V"],
-                   "parallelism": f"{world} independent replicas (sessions are independent; no data-path collective)",
+                   "parallelism": (f"item table + tied head row-sharded over {world} ranks (1 all-to-all + 1 all-gather per "
+                                   f"step), everything else data parallel") if cfg.get("sharded") else
+                   f"{world} independent replicas (sessions are independent; no data-path collective)",
                    "l2_policy": "inputs larger than L2 (1 GB item table + 1 GB split planes streamed per step)",
                    "product_arithmetic": "split-bf16 x3 tcgen05 products, fp32 accumulate" if args.nprod == 3
                    else "bf16 tcgen05, fp32 accumulate"}
@@ -206,9 +215,11 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 or cfg.get("sharded"):
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
     import transformers4rec_b200 as t4r
     from transformers4rec_b200 import ops
 
@@ -309,6 +320,8 @@ def main():
     e2e_value = B * world / (e2e_ms / K / 1e3)
     peaks, peak_kind = load_peaks()
     head_flops = 2.0 * T * V * cfg["De"]  # algorithmic (head_flop = 2*T*V*De)
+    if cfg.get("sharded"):  # per launch: the label rows of ALL ranks against this rank's V/world table rows
+        head_flops = 2.0 * (T * world) * (V / world) * cfg["De"]
     achieved_tf = head_flops / (head_ms_avg * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,false,true> (tied logits + online LSE)",

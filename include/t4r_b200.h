@@ -336,15 +336,21 @@ typedef struct {
   /* nn.CrossEntropyLoss(label_smoothing=e) (transformers4rec/torch/losses.py:4-20): row_loss =
    * lse - (1-e) z_label - (e/V) sum_j z_j.  Full, unsharded softmax only; 0 = off. */
   float label_smoothing;
+  /* sharded evaluation: the label's logit over the WHOLE table (summed over shards by the caller)
+   * that row_rank counts against; NULL = this call's own row_tgt (single shard) */
+  const float* rank_tgt;
 } t4r_head_args;
 size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De);
 int t4r_head_softmax_ce_fwd(const t4r_head_args* a /*host*/, void* stream);
 
 /* exact fp32 logit of each row's label plus an optional per-class bias:
  * out[t] = (xt[t] . W[label] + class_bias[label]) * inv_temperature -- the positive
- * score of the sampled softmax incl. its logQ term (model/prediction_task.py:681-687). */
+ * score of the sampled softmax incl. its logQ term (model/prediction_task.py:681-687).
+ * w_f32 holds table rows [v_offset, v_offset + V); labels outside that range give 0 (so that
+ * the per-shard results of a row-sharded table can be summed). */
 int t4r_label_logit(const float* xt_f32, const float* w_f32, const int64_t* labels, int T_cap, const int32_t* t_dev,
-                    int De, int64_t V, const float* class_bias, float inv_temperature, float* out, void* stream);
+                    int De, int64_t V, const float* class_bias, float inv_temperature, int64_t v_offset, float* out,
+                    void* stream);
 
 /* materialise logits [T_cap, V] = xt * W^T * inv_temperature (the reference's
  * "predictions" output, model/prediction_task.py:447-451) -- optional, on demand. */

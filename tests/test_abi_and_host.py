@@ -161,3 +161,34 @@ def test_widened_input_block_surface():
         tr.TabularSequenceFeatures.from_schema(schema, aggregation="stack")
     assert set(tr.ranking_metrics_registry) >= {"precision_at", "recall_at", "avg_precision_at", "map", "dcg_at",
                                                 "ndcg_at", "mrr_at"}
+
+
+def _testing_schema(tr):
+    """The shape of the reference's testing schema (transformers4rec/data/testing/schema.json): two list
+    categoricals (item max 51996, category max 332), one context categorical (max 62), ten list
+    continuous features and one context continuous feature."""
+    cont = ["timestamp/age_days/LogOp/Normalize/list", "timestamp/hour/list", "timestamp/weekday/list",
+            "timestamp/day/list", "timestamp/month/list", "timestamp/year/list", "timestamp/hour/sin/list",
+            "timestamp/hour/cos/list", "timestamp/weekday/sin/list", "timestamp/weekday/cos/list"]
+    return tr.Schema([tr.ColumnSchema.create_continuous(n) for n in cont] + [
+        tr.ColumnSchema.create_categorical("item_id/list", 51996, tags=[tr.Tags.ITEM_ID]),
+        tr.ColumnSchema.create_categorical("category/list", 332),
+        tr.ColumnSchema.create_categorical("user_country", 62, is_list=False),
+        tr.ColumnSchema.create_continuous("user_age", is_list=False)])
+
+
+def test_known_answers_of_the_reference_feature_tests():
+    import transformers4rec_b200.torch as tr
+    schema = _testing_schema(tr)
+    # tests/unit/torch/features/test_sequential.py:217-223: concat width 203 = 3 x 64 + 11 scalars
+    tab = tr.TabularSequenceFeatures.from_schema(schema, aggregation="concat")
+    assert tab.output_size()[-1] == 203
+    # tests/unit/torch/features/test_embedding.py:106-119: infer_embedding_sizes with multiplier 3 -> 46 and 13
+    emb = tr.SequenceEmbeddingFeatures.from_schema(schema.select_by_tag(tr.Tags.CATEGORICAL), infer_embedding_sizes=True,
+                                                   infer_embedding_sizes_multiplier=3.0)
+    assert emb.embedding_tables["item_id/list"].weight.shape[1] == 46
+    assert emb.embedding_tables["category/list"].weight.shape[1] == 13
+    # tests/unit/torch/features/test_embedding.py:73-87: defaults and the item table size (max + 1)
+    emb = tr.SequenceEmbeddingFeatures.from_schema(schema.select_by_tag(tr.Tags.CATEGORICAL))
+    assert all(t.weight.shape[1] == 64 for t in emb.embedding_tables.values())
+    assert emb.item_id == "item_id/list" and emb.item_embedding_table.num_embeddings == 51997

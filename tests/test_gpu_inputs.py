@@ -228,3 +228,19 @@ def test_stochastic_swap_noise_as_pre_transform():
         for n in cont.features:
             feats[n] = batch[n].unsqueeze(-1)
     assert torch.equal(x_eval, O.aggregate(feats, "concat"))
+
+
+def test_reference_feature_test_shape_203():
+    """tests/unit/torch/features/test_sequential.py:217-223 on the testing schema: [100, 20, 203]."""
+    import transformers4rec_b200.torch as tr
+    from test_abi_and_host import _testing_schema
+    schema = _testing_schema(tr)
+    tab = tr.TabularSequenceFeatures.from_schema(schema, aggregation="concat").cuda()
+    g = torch.Generator().manual_seed(0)
+    batch = {}
+    for col in schema:
+        shape = (100, 20) if col.is_list else (100,)
+        batch[col.name] = (torch.randint(1, col.int_max + 1, shape, generator=g) if col.int_max
+                           else torch.rand(shape, generator=g)).cuda()
+    out = tab(batch)
+    assert list(out.shape) == [100, 20, 203]

@@ -77,3 +77,80 @@ def test_sharded_lookup_and_head_nccl():
     for rank, ok_lookup, ok_planes, err_rows, err_loss, ok_T in res:
         assert ok_lookup and ok_planes and ok_T, f"rank {rank}: lookup/planes/T mismatch"
         assert err_rows < 1e-3 and err_loss < 1e-4, f"rank {rank}: loss rows {err_rows} mean {err_loss}"
+
+
+# --------------------------------------------------------------------------- #
+# model level: TabularSequenceFeatures + XLNet + NextItemPredictionTask over a row-sharded item table
+# (BASELINE configs 4-5 at test size), each rank with its own sessions; reference = the single-process
+# CPU oracle on the GLOBAL batch ("multi-GPU parity is defined against the single-process
+# oracle on the global batch")
+# --------------------------------------------------------------------------- #
+def _model_worker(rank, world, port, q, sampled):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import torch.distributed as dist
+
+    import t4r_oracle as O
+    from _util import make_pair, mlm_draws, synth_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cards, dims = {"item_id/list": 12001}, {"item_id/list": 64}
+        B, L, S = 24, 20, 300
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 1, L, sampled=sampled, max_n_samples=S,
+                                  weight_scale=0.08, device=f"cuda:{rank}")
+        inputs = model.heads[0].body[0]
+        inputs.categorical_module.shard_item_table()
+        task = model.heads[0].prediction_task_dict["next-item"]
+        batches = [synth_batch(B, L, cards, seed=100 + r) for r in range(world)]
+        us = [mlm_draws(B, L, seed=200 + r) for r in range(world)]
+        gb = {k: torch.cat([b[k] for b in batches]) for k in batches[0]}
+        gdraws = {k: torch.cat([u[1][k] for u in us]) for k in us[0][1]}
+        res = {}
+        with torch.no_grad():
+            inputs.masking.set_draws(us[rank][0].cuda())
+            if sampled:
+                torch.manual_seed(3)
+                raw = torch.multinomial(oracle.dist, 2 * S, replacement=True)
+                task.set_negative_draws(raw.cuda())
+                ref = oracle(gb, training=True, draws=gdraws, neg_samples=O.negatives_from_draws(raw, S))
+                out = model({k: v.cuda() for k, v in batches[rank].items()}, training=True)
+                res["train"] = abs(out["loss"].item() - ref["loss"].item())
+            else:
+                ref = oracle(gb, training=True, draws=gdraws)
+                out = model({k: v.cuda() for k, v in batches[rank].items()}, training=True)
+                res["train"] = abs(out["loss"].item() - ref["loss"].item())
+                # evaluation: loss over the global batch, Recall@k of THIS rank's sessions from cross-shard ranks
+                ref_e = oracle(gb, training=False, testing=True)
+                out_e = model({k: v.cuda() for k, v in batches[rank].items()}, training=False, testing=True)
+                res["eval"] = abs(out_e["loss"].item() - ref_e["loss"].item())
+                mine = slice(rank * B, (rank + 1) * B)  # eval: one label (the last item) per session
+                ref_rec = O.recall_at_mean([1, 5, 20], ref_e["predictions"][mine], ref_e["labels"][mine])
+                import transformers4rec_b200.torch as tr
+                m = tr.RecallAt(top_ks=[1, 5, 20], labels_onehot=True)
+                m.update_from_ranks(out_e.row_rank, None)
+                res["recall"] = (m.metric_mean[-1].cpu() - ref_rec).abs().max().item()
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("sampled", [False, True])
+def test_model_over_sharded_item_table_nccl(sampled):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000) + (50 if sampled else 0)
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q, sampled)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r["train"] < 1e-3, (rank, r)
+        if not sampled:
+            assert r["eval"] < 1e-3 and r["recall"] < 1e-6, (rank, r)

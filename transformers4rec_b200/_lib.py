@@ -119,6 +119,7 @@ class HeadArgs(C.Structure):
         ("ev_gemm_start", c_void_p),
         ("ev_gemm_stop", c_void_p),
         ("label_smoothing", c_float),
+        ("rank_tgt", c_void_p),
     ]
 
 
@@ -151,7 +152,7 @@ SIGNATURES = {
                                      _P, _P, _P, c_size_t, _P]),
     "t4r_head_workspace_bytes": (c_size_t, [c_int, c_int64, c_int]),
     "t4r_head_softmax_ce_fwd": (c_int, [C.POINTER(HeadArgs), _P]),
-    "t4r_label_logit": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int64, _P, c_float, _P, _P]),
+    "t4r_label_logit": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int64, _P, c_float, c_int64, _P, _P]),
     "t4r_head_logits": (c_int, [_P, _P, c_int, _P, c_int64, c_int, c_float, _P, c_int64, c_int, _P]),
     "t4r_recall_from_ranks": (c_int, [_P, _P, c_int, C.POINTER(C.c_int32), c_int, _P, _P]),
     "t4r_topk": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),

@@ -476,7 +476,7 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   ep.col_ids = a->col_ids;
   ep.row_label = a->labels;
   ep.hit_value = a->hit_value;
-  ep.row_tgt = a->row_tgt;
+  ep.row_tgt = a->rank_tgt ? a->rank_tgt : a->row_tgt;
   ep.row_rank = a->row_rank;
   ep.col_offset = a->v_offset;
   if (a->ev_gemm_start) T4R_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_gemm_start), s));

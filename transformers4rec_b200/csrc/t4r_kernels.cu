@@ -1081,9 +1081,9 @@ extern "C" int t4r_combine_shard_lse(const float* parts, int world, int T_cap, c
 
 extern "C" int t4r_label_logit(const float* xt_f32, const float* w_f32, const int64_t* labels, int T_cap,
                                const int32_t* t_dev, int De, int64_t V, const float* class_bias, float inv_temperature,
-                               float* out, void* stream) {
+                               int64_t v_offset, float* out, void* stream) {
   using namespace t4r;
   T4R_REQUIRE(xt_f32 && w_f32 && labels && out && T_cap > 0 && De > 0 && V > 0, "label_logit: bad arguments");
-  return launch_target_logit(xt_f32, w_f32, labels, T_cap, t_dev, De, 0, V, class_bias,
+  return launch_target_logit(xt_f32, w_f32, labels, T_cap, t_dev, De, v_offset, V, class_bias,
                              inv_temperature != 0.f ? inv_temperature : 1.f, out, static_cast<cudaStream_t>(stream));
 }

@@ -104,12 +104,20 @@ def sharded_embedding_lookup(local_table: torch.Tensor, ids: torch.Tensor, V: in
 
 
 def _default_head_rows(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, w_planes, v_offset: int,
-                       inv_tau: float):
+                       inv_tau: float, rank_tgt: Optional[torch.Tensor] = None):
+    """-> [T, 2] (lse over this shard, label logit if the label lives here else 0); with ``rank_tgt`` (the
+    label's logit over the whole table) also the per-row count of this shard's classes scoring above it."""
     from . import ops
     xp = ops.split_planes(xt)
     res = ops.head_softmax_ce(xp, xt, labels, w_planes, local_table, inv_temperature=inv_tau, v_offset=v_offset,
-                              want_loss=False)
-    return torch.stack([res["row_lse"], res["row_tgt"]], dim=1)  # [T, 2]
+                              want_loss=False, want_rank=rank_tgt is not None, rank_tgt=rank_tgt)
+    part = torch.stack([res["row_lse"], res["row_tgt"]], dim=1)
+    return part if rank_tgt is None else (part, res["row_rank"])
+
+
+def _default_label_logit(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, v_offset: int, inv_tau: float):
+    from . import ops
+    return ops.label_logit(xt, local_table, labels, inv_temperature=inv_tau, v_offset=v_offset)
 
 
 def _default_combine(parts: torch.Tensor):
@@ -119,10 +127,14 @@ def _default_combine(parts: torch.Tensor):
 
 def sharded_softmax_ce(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, V: int, group=None,
                        w_planes=None, inv_tau: float = 1.0, head_rows: Optional[Callable] = None,
-                       combine: Optional[Callable] = None):
+                       combine: Optional[Callable] = None, want_rank: bool = False,
+                       label_logit: Optional[Callable] = None):
     """Full-softmax CE of the label rows of ALL ranks against a row-sharded output
     table.  ``xt`` [T_local, De] / ``labels`` [T_local] are this rank's label rows.
-    Returns (row_loss for this rank's rows, global mean loss, T_total)."""
+    Returns (row_loss for this rank's rows, global mean loss, T_total) and, with ``want_rank``
+    (evaluation), a 4th item: the rank of each of this rank's labels over the WHOLE table
+    (two more small collectives: the label logits are summed over shards first -- only the
+    owner contributes -- then the per-shard counts of higher-scoring classes are summed)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     head_rows = head_rows or _default_head_rows
@@ -140,8 +152,69 @@ def sharded_softmax_ce(xt: torch.Tensor, labels: torch.Tensor, local_table: torc
     xg = torch.cat([all_x[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
     yg = torch.cat([all_y[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
     lo, _ = shard_bounds(V, rank, world)
-    part = head_rows(xg, yg, local_table, w_planes, lo, inv_tau)          # [T_total, 2]
+    start = sum(counts_l[:rank])
+    mine = slice(start, start + counts_l[rank])
+    if want_rank:
+        label_logit = label_logit or _default_label_logit
+        tgt = label_logit(xg, yg, local_table, lo, inv_tau).contiguous()  # 0 where the label is not mine
+        dist.all_reduce(tgt, group=group)
+        part, cnt = head_rows(xg, yg, local_table, w_planes, lo, inv_tau, tgt)
+        cnt = cnt.contiguous()
+        dist.all_reduce(cnt, group=group)
+    else:
+        part = head_rows(xg, yg, local_table, w_planes, lo, inv_tau)      # [T_total, 2]
     parts = _all_gather(part, world, group)                               # the one head collective
     row_loss, loss = combine(parts)
-    start = sum(counts_l[:rank])
-    return row_loss[start: start + counts_l[rank]], loss, int(sum(counts_l))
+    if want_rank:
+        return row_loss[mine], loss, int(sum(counts_l)), cnt[mine]
+    return row_loss[mine], loss, int(sum(counts_l))
+
+
+class ShardedEmbedding(torch.nn.Module):
+    """Rows [lo, hi) of an item table of ``num_embeddings`` rows, block-partitioned over the process
+    group: the drop-in for the item feature's ``nn.Embedding`` (and, under weight tying, for the output
+    layer of the head) in BASELINE configs 4-5.  ``weight`` is the LOCAL shard."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: int = 0, group=None,
+                 initializer: Optional[Callable] = None, device=None):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedEmbedding needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.num_embeddings, self.embedding_dim, self.padding_idx = int(num_embeddings), int(embedding_dim), padding_idx
+        self.lo, self.hi = shard_bounds(self.num_embeddings, self.rank, self.world)
+        self.weight = torch.nn.Parameter(torch.empty((self.hi - self.lo, embedding_dim), device=device))
+        (initializer or (lambda w: torch.nn.init.normal_(w, mean=0.0, std=0.05)))(self.weight)
+
+    @classmethod
+    def from_full(cls, full_weight: torch.Tensor, group=None, padding_idx: int = 0) -> "ShardedEmbedding":
+        """Take this rank's block of a replicated table (tests / converting a trained model)."""
+        m = cls(full_weight.shape[0], full_weight.shape[1], padding_idx, group, initializer=lambda w: None,
+                device=full_weight.device)
+        with torch.no_grad():
+            m.weight.copy_(full_weight[m.lo:m.hi])
+        return m
+
+    def lookup(self, ids: torch.Tensor, ragged: bool = False):
+        """-> (rows fp32 [ids.numel(), dim], split planes) for arbitrary global ids (one all-gather of the
+        ids + one all-to-all of the rows).  ``ragged``: the ranks pass different numbers of ids (label
+        rows); they are padded to the longest with the padding id for the exchange."""
+        flat = ids.reshape(-1)
+        n = flat.numel()
+        if ragged:
+            counts = _all_gather(torch.tensor([n], dtype=torch.int64, device=flat.device), self.world, self.group)
+            n_max = int(counts.max())
+            if n_max > n:
+                flat = torch.cat([flat, flat.new_full((n_max - n,), self.padding_idx)])
+        rows, planes = sharded_embedding_lookup(self.weight.detach(), flat, self.num_embeddings, self.group)
+        if ragged and rows.shape[0] != n:
+            rows, planes = rows[:n], (planes[:, :n] if planes is not None else None)
+        return rows, planes
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        rows, _ = self.lookup(ids)
+        return rows.view(*ids.shape, self.embedding_dim)
+
+    def extra_repr(self) -> str:
+        return f"{self.num_embeddings}, {self.embedding_dim}, rows [{self.lo}, {self.hi}) of rank {self.rank}/{self.world}"

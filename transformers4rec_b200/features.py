@@ -252,7 +252,7 @@ class SequenceEmbeddingFeatures(nn.Module):
     ``embedding_tables.<feature>.weight``) and remembers ``item_seq``."""
 
     def __init__(self, feature_config: Dict[str, FeatureConfig], item_id: Optional[str] = None, padding_idx: int = 0,
-                 post=None):
+                 post=None, shard_item_table: bool = False, device=None):
         super().__init__()
         self.post = _parse_post(post, feature_config)
         self.padding_idx = padding_idx
@@ -260,7 +260,13 @@ class SequenceEmbeddingFeatures(nn.Module):
         self.feature_config = feature_config
         tables = {}
         for name, feature in feature_config.items():
-            emb = nn.Embedding(feature.table.vocabulary_size, feature.table.dim, padding_idx=padding_idx)
+            if shard_item_table and name == item_id:
+                # BASELINE configs 4-5: the item table (= the tied output layer) is row-sharded over the ranks
+                from .distributed import ShardedEmbedding
+                tables[name] = ShardedEmbedding(feature.table.vocabulary_size, feature.table.dim, padding_idx,
+                                                initializer=feature.table.initializer, device=device)
+                continue
+            emb = nn.Embedding(feature.table.vocabulary_size, feature.table.dim, padding_idx=padding_idx, device=device)
             if feature.table.initializer is not None:
                 feature.table.initializer(emb.weight)
             tables[name] = emb
@@ -276,7 +282,7 @@ class SequenceEmbeddingFeatures(nn.Module):
     def from_schema(cls, schema: Schema, embedding_dims=None, embedding_dim_default: int = 64,
                     infer_embedding_sizes: bool = False, infer_embedding_sizes_multiplier: float = 2.0,
                     embeddings_initializers=None, combiner="mean", tags=None, item_id=None, padding_idx=0, post=None,
-                    **kwargs):
+                    shard_item_table: bool = False, device=None, **kwargs):
         """features/embedding.py:103-221."""
         if tags:
             schema = schema.select_by_tag(tags)
@@ -301,10 +307,24 @@ class SequenceEmbeddingFeatures(nn.Module):
                 combiner=combiner, initializer=embeddings_initializers.get(key, None)))
         if not feature_config:
             return None
-        return cls(feature_config, item_id=item_id, padding_idx=padding_idx, post=post)
+        return cls(feature_config, item_id=item_id, padding_idx=padding_idx, post=post,
+                   shard_item_table=shard_item_table, device=device)
 
     def item_ids(self, inputs) -> torch.Tensor:
         return inputs[self.item_id]
+
+    def is_sharded(self, name: str) -> bool:
+        return hasattr(self.embedding_tables[name], "lookup")
+
+    def shard_item_table(self, group=None):
+        """Replace the replicated item table by this rank's row block.  A head built with
+        ``weight_tying=True`` follows automatically: it reads ``item_embedding_table`` at call time."""
+        from .distributed import ShardedEmbedding
+        assert self.item_id is not None
+        if not self.is_sharded(self.item_id):
+            full = self.embedding_tables[self.item_id].weight.detach()
+            self.embedding_tables[self.item_id] = ShardedEmbedding.from_full(full, group, self.padding_idx)
+        return self
 
     def output_dims(self) -> Dict[str, int]:
         return {n: f.table.dim for n, f in self.feature_config.items()}
@@ -316,6 +336,9 @@ class SequenceEmbeddingFeatures(nn.Module):
         for name in self.feature_config:
             ids = inputs[name]
             shp = tuple(ids.shape)
+            if self.is_sharded(name):
+                out[name] = self.embedding_tables[name](ids)
+                continue
             table = self.embedding_tables[name].weight
             of, _, _ = ops.embed_concat([(table.detach(), ids.reshape(-1), 0)], [], ids.numel(), table.shape[1], True,
                                         False)
@@ -399,7 +422,7 @@ class TabularSequenceFeatures(nn.Module):
                 cont = cls.CONTINUOUS_MODULE_CLASS.from_schema(schema, tags=continuous_tags)
         emb_kwargs = {k: v for k, v in kwargs.items() if k in (
             "embedding_dims", "embedding_dim_default", "infer_embedding_sizes", "infer_embedding_sizes_multiplier",
-            "embeddings_initializers", "combiner", "item_id", "padding_idx", "post")}
+            "embeddings_initializers", "combiner", "item_id", "padding_idx", "post", "shard_item_table", "device")}
         cat = cls.EMBEDDING_MODULE_CLASS.from_schema(schema, tags=categorical_tags, **emb_kwargs) if categorical_tags else None
         if continuous_projection:
             if not automatic_build:
@@ -544,8 +567,9 @@ class TabularSequenceFeatures(nn.Module):
         agg = self.AGGREGATIONS[self.aggregation or "concat"]
         cat_ln = getattr(cm, "post", None) if cm is not None else None
         cont_ln = getattr(cont, "post", None) if cont is not None else None
+        sharded = [n for n, kind, *_ in layout if kind == "cat" and cm.is_sharded(n)]
         plain = agg == _lib.AGG_CONCAT and all(kind in ("cat", "cont") for _, kind, *_ in layout) and not (
-            cat_ln is not None and len(cat_ln.feature_layer_norm) > 0)
+            cat_ln is not None and len(cat_ln.feature_layer_norm) > 0) and not sharded
 
         def gather(want_f32: bool, want_planes: bool):
             if plain:  # the specialised HBM-roofline gather
@@ -558,11 +582,21 @@ class TabularSequenceFeatures(nn.Module):
                 return ops.embed_concat(cats, conts, M, C_width, want_f32=want_f32, want_planes=want_planes)
             feats = []
             item_feature = -1
+            if sharded and len(layout) == 1 and agg == _lib.AGG_CONCAT and not (cat_ln is not None and cat_ln.params(sharded[0])):
+                # item-only input block over a row-sharded table (config 4): the exchange's second gather
+                # already emits the rows in session order, fp32 and split planes
+                rows, planes = cm.embedding_tables[sharded[0]].lookup(seq(inputs[sharded[0]]))
+                return (rows if want_f32 else None), (planes if want_planes else None), None
             for i, (name, kind, col, width) in enumerate(layout):
                 if kind == "cat":
                     v = inputs[name]
-                    f = dict(kind=_lib.FEAT_CAT, dim=width, col=col, input=v, per_session=is_context(v),
-                             table=cm.embedding_tables[name].weight, ln=cat_ln.params(name) if cat_ln is not None else None)
+                    ln = cat_ln.params(name) if cat_ln is not None else None
+                    if name in sharded:  # rows arrive through the all-to-all, then enter as a dense feature
+                        rows, _ = cm.embedding_tables[name].lookup(v)
+                        f = dict(kind=_lib.FEAT_DENSE, dim=width, col=col, input=rows, per_session=is_context(v), ln=ln)
+                    else:
+                        f = dict(kind=_lib.FEAT_CAT, dim=width, col=col, input=v, per_session=is_context(v),
+                                 table=cm.embedding_tables[name].weight, ln=ln)
                     if name == cm.item_id:
                         item_feature = i
                 elif kind == "cont":

@@ -401,7 +401,7 @@ def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: in
 # --------------------------------------------------------------------------- #
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
-                    nprod=3, events=None, label_smoothing=0.0):
+                    nprod=3, events=None, label_smoothing=0.0, rank_tgt=None):
     """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank)."""
     _need_cuda(xt_planes, w_planes)
     lib = _lib.load()
@@ -427,6 +427,7 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     a.workspace, a.workspace_bytes = ptr(ws), ws.numel()
     a.nprod = nprod
     a.label_smoothing = float(label_smoothing)
+    a.rank_tgt = ptr(rank_tgt)
     ev = events if events is not None else HEAD_EVENTS
     if ev is not None:
         a.ev_gemm_start, a.ev_gemm_stop = ev[0].cuda_event, ev[1].cuda_event
@@ -434,12 +435,12 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     return {"row_lse": row_lse, "row_tgt": row_tgt, "row_loss": row_loss, "loss": loss, "row_rank": row_rank}
 
 
-def label_logit(xt_f32, w_f32, labels, *, t_dev=None, class_bias=None, inv_temperature=1.0):
+def label_logit(xt_f32, w_f32, labels, *, t_dev=None, class_bias=None, inv_temperature=1.0, v_offset=0):
     _need_cuda(xt_f32, w_f32, labels)
     T_cap, De = xt_f32.shape
     out = torch.empty(T_cap, dtype=torch.float32, device=xt_f32.device)
     check(_lib.load().t4r_label_logit(ptr(xt_f32), ptr(w_f32), ptr(labels), T_cap, ptr(t_dev), De, w_f32.shape[0],
-                                      ptr(class_bias), inv_temperature, ptr(out), _stream()), "t4r_label_logit")
+                                      ptr(class_bias), inv_temperature, v_offset, ptr(out), _stream()), "t4r_label_logit")
     return out
 
 

@@ -10,6 +10,8 @@ written.  ``predictions`` stays available lazily (``t4r_head_logits``).
 """
 from __future__ import annotations
 
+import math
+
 import logging
 from typing import Dict, Iterable, Optional
 
@@ -100,6 +102,7 @@ class LogUniformSampler(nn.Module):
         if max_n_samples <= 0:
             raise ValueError("n_sample must be a positive integer.")
         self.max_id = max_id
+        self.min_id = min_id
         self.unique_sampling = unique_sampling
         self.max_n_samples = max_n_samples
         self.n_sample = max_n_samples
@@ -125,7 +128,15 @@ class LogUniformSampler(nn.Module):
         return (-(-dist.double().log1p_() * n_sample).expm1_()).float()
 
     def draw(self) -> torch.Tensor:
-        return torch.multinomial(self.dist, self.n_sample, replacement=True)
+        if self.dist.numel() <= (1 << 24):
+            return torch.multinomial(self.dist, self.n_sample, replacement=True)
+        # torch.multinomial stops at 2^24 categories (the reference's sampler cannot run BASELINE config 5's
+        # 50 M items at all).  Same distribution by inverting its CDF, log(k + 2) / log(R + 1) for the k-th id
+        # of the range (:766-787): k = floor(exp(u * log(R + 1))) - 1, in fp64.
+        R = self.max_id - self.min_id
+        u = torch.rand(self.n_sample, dtype=torch.float64, device=self.dist.device)
+        k = torch.exp(u * math.log(R + 1.0)).floor().long().sub_(1).clamp_(0, R - 1)
+        return k + self.min_id
 
     def sample(self, labels: torch.Tensor, raw_draws: Optional[torch.Tensor] = None):
         if not torch.is_tensor(labels):
@@ -214,7 +225,10 @@ class NextItemPredictionTask(PredictionTask):
 
     # ------------------------------------------------------------------ helpers
     def output_weight(self) -> torch.Tensor:
-        return self.item_embedding_table.weight if self.weight_tying else self.output_layer
+        if self.weight_tying:
+            self.item_embedding_table = self.embeddings.item_embedding_table  # may have been swapped for its shard
+            return self.item_embedding_table.weight
+        return self.output_layer
 
     def set_negative_draws(self, raw_draws: Optional[torch.Tensor]):
         """Test hook: the multinomial output ids the sampler would have drawn."""
@@ -254,6 +268,8 @@ class NextItemPredictionTask(PredictionTask):
             if self.task_block is not None:
                 xt_f32, xt_planes = self._task_block_rows(xt_planes, count)
             want_rank = bool(testing and not training)
+            if self._sharded():
+                return self._forward_sharded(xt_planes, xt_f32, tgt_labels, count, training, want_rank, w_planes, inv_tau)
             if self.sampled_softmax and training:
                 neg, _, _ = self.sampler.sample(tgt_labels[:1], raw_draws=self._neg_draws)
                 S = neg.numel()
@@ -280,6 +296,9 @@ class NextItemPredictionTask(PredictionTask):
             return out
 
         # inference (:452-470): hidden state at the next-item position, full scores
+        if self._sharded():
+            raise NotImplementedError("inference over a row-sharded item table is not built yet: gather the shards "
+                                      "(ShardedEmbedding.weight) into a replicated table for serving")
         item_seq = self.embeddings.item_seq
         non_pad = item_seq != self.padding_idx
         rows_ids = torch.arange(item_seq.size(0), dtype=torch.long, device=item_seq.device)
@@ -292,6 +311,62 @@ class NextItemPredictionTask(PredictionTask):
         if top_k is None:
             return scores
         return ops.topk(scores, top_k)
+
+    # ------------------------------------------------------------------ row-sharded table (configs 4-5)
+    def _sharded(self) -> bool:
+        return self.weight_tying and hasattr(self.item_embedding_table, "lookup")
+
+    def _forward_sharded(self, xt_planes, xt_f32, tgt_labels, count, training, want_rank, w_planes, inv_tau):
+        """the label rows of all ranks against every rank's rows of the tied table.  Full softmax:
+        all-gather of the label rows + one all-gather of per-row (lse, label-logit) pairs.  Sampled softmax:
+        identical negatives on every rank (rank 0's draws are broadcast), their rows and the positives' rows
+        arrive through the table's row exchange, after which the head is data parallel."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        table = self.item_embedding_table
+        Wd = table.weight.detach()
+        if self.label_smoothing:
+            raise NotImplementedError("label smoothing over a row-sharded table is not on the t4r_b200 path")
+        T = int(count.item())  # the collectives need host-side sizes
+        xt = xt_f32[:T].contiguous()
+        y = tgt_labels[:T].contiguous()
+        if self.sampled_softmax and training:
+            if self._neg_draws is not None:
+                raw = self._neg_draws
+            else:
+                raw = self.sampler.draw()
+                dist.broadcast(raw, src=dist.get_global_rank(table.group, 0) if table.group is not None else 0,
+                               group=table.group)
+            neg, _, _ = self.sampler.sample(y[:1], raw_draws=raw)
+            S = neg.numel()
+            _, neg_planes = table.lookup(neg)
+            wy, _ = table.lookup(y, ragged=True)
+            col_bias = self.sampler.neg_log_q[neg].contiguous()
+            pos = ops.label_logit(xt, wy, torch.arange(T, device=xt.device), class_bias=self.sampler.neg_log_q[y].contiguous(),
+                                  inv_temperature=inv_tau)
+            xp = xt_planes[:, :T].contiguous()
+            res = ops.head_softmax_ce(xp, xt, y, neg_planes, None, inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg,
+                                      hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos,
+                                      nprod=self.nprod)
+            tot = torch.stack([res["row_loss"][:T].sum(), torch.tensor(float(T), device=xt.device)])
+            dist.all_reduce(tot, group=table.group)
+            loss = (tot[0] / tot[1].clamp(min=1.0)).reshape(())
+            self._last = dict(count=count, labels=tgt_labels, sampled=True, sharded=True, S=S)
+            out = LazyOutputs({"loss": loss}, {"labels": self._lazy_labels, "predictions": self._no_sharded_predictions})
+            out.row_rank, out.count = None, count
+            return out
+        res = D.sharded_softmax_ce(xt, y, Wd, table.num_embeddings, table.group, w_planes=w_planes, inv_tau=inv_tau,
+                                   want_rank=want_rank)
+        loss = res[1].reshape(())
+        self._last = dict(count=count, labels=tgt_labels, sampled=False, sharded=True)
+        out = LazyOutputs({"loss": loss}, {"labels": self._lazy_labels, "predictions": self._no_sharded_predictions})
+        out.row_rank = res[3] if want_rank else None
+        out.count = None if want_rank else count  # ranks are already trimmed to this rank's T rows
+        return out
+
+    def _no_sharded_predictions(self):
+        raise NotImplementedError("predictions [T, V] are not materialised over a row-sharded table")
 
     def _lazy_labels(self):
         T = int(self._last["count"].item())
