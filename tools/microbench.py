@@ -103,7 +103,9 @@ def main():
         xt = torch.randn(T, d, device=dev)
         xtp = ops.split_planes(xt)
         y = torch.randint(1, V, (T,), device=dev)
-        timeit("head 5120 x 1M x 256", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W), iters=5, flops=2 * T * V * d)
+        for nprod in (3, 1):  # 1 = plain bf16: same operand traffic, a third of the MMAs -> separates tensor- from L2-bound
+            timeit(f"head 5120 x 1M x 256 nprod={nprod}", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=nprod),
+                   iters=5, flops=2 * T * V * d)
 
 
 if __name__ == "__main__":
