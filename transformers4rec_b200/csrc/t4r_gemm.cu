@@ -425,6 +425,7 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
     if (!row_ok) continue;
     const int64_t ncol0 = n0 + c * 32;
     if (ncol0 >= p.N) continue;
+    if (ep.debug & 32) { m_run = fmaxf(m_run, v[c]); continue; }  // timing experiment: TMEM reads only
     if (ep.col_bias) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -457,16 +458,28 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
       for (int j = 0; j < 32; ++j) zs += (v[j] == -INFINITY) ? 0.f : v[j];
       z_run = fmaf(zs, ep.inv_tau, z_run);
     }
-    float cmax = v[0];
+    // four independent chains each for the max and the sum: with two epilogue warps per scheduler a single
+    // 32-long dependent FMNMX / FADD chain (4 cycles per link) left this loop latency-bound at ~5k cycles per
+    // 128x256 tile, 2.4x its SFU (ex2) floor
+    float mx[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-    for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
-    cmax *= scale2;  // scale2 > 0
+    for (int j = 4; j < 32; j += 4) {
+      mx[0] = fmaxf(mx[0], v[j]); mx[1] = fmaxf(mx[1], v[j + 1]);
+      mx[2] = fmaxf(mx[2], v[j + 2]); mx[3] = fmaxf(mx[3], v[j + 3]);
+    }
+    const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale2;  // scale2 > 0
     const float m_new = fmaxf(m_run, cmax);
+    if (ep.debug & 16) { m_run = m_new; continue; }  // timing experiment: no exponentials
     if (m_new > -INFINITY) {
-      float acc = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc += fast_exp2(fmaf(v[j], scale2, -m_new));
-      s_run = s_run * fast_exp2(m_run - m_new) + acc;
+      for (int j = 0; j < 32; j += 4) {
+        acc[0] += fast_exp2(fmaf(v[j], scale2, -m_new));
+        acc[1] += fast_exp2(fmaf(v[j + 1], scale2, -m_new));
+        acc[2] += fast_exp2(fmaf(v[j + 2], scale2, -m_new));
+        acc[3] += fast_exp2(fmaf(v[j + 3], scale2, -m_new));
+      }
+      s_run = s_run * fast_exp2(m_run - m_new) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
       m_run = m_new;
     }
   }
