@@ -80,6 +80,9 @@ int make_tmap_public(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
 // kernel
 // ----------------------------------------------------------------------------
 constexpr int BM = 128;
+#ifndef T4R_GEMM_2CTA_DEFAULT
+#define T4R_GEMM_2CTA_DEFAULT 1
+#endif
 
 // RB = bytes per shared-memory operand row = K extent of one pipeline stage (RB/2 bf16).
 // RB = 64 (SWIZZLE_64B) halves the stage and doubles the ring depth in the same shared memory
@@ -659,6 +662,191 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ============================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two SMs of a TPC share one 256 x BN tile.  Each CTA loads its own 128
+// rows of A and HALF of the B tile (BN/2 rows), so per SM the L2->SM operand stream and the shared-memory operand
+// reads of the tensor core drop by a third (BN = 256) -- the bound of every GEMM on this path except the K = 256 head
+// (DESIGN.md section 5).  Protocol (leader = cluster rank 0):
+//   * both TMA warps wait on their OWN empty[s]; the leader arms full[s] with the bytes of both CTAs and all eight
+//     loads credit the leader's full[s];
+//   * the leader's MMA warp issues M = 256 MMAs and commits with a 2-CTA multicast: empty[s] and tfull[as] fire in both;
+//   * the 16 epilogue warps of both CTAs read their own TMEM and arrive on the LEADER's tempty[as].
+// ============================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_PLANE_BYTES = BM * 128;
+  static constexpr int B_PLANE_BYTES = (BN / 2) * 128;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
+};
+
+template <int BN, bool LN, bool HEAD>
+__global__ void __launch_bounds__(320, 1)
+gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                    const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int A_PLANE_BYTES = Cfg::A_PLANE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* xch = reinterpret_cast<float2*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  float* stg_all = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + 4096);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  int M_eff = p.M;
+  if (p.m_dev) M_eff = min(p.M, *p.m_dev);
+  const int tiles_m = (M_eff + 2 * BM - 1) / (2 * BM);
+  const int tiles_n = static_cast<int>((p.N + BN - 1) / BN);
+  const int64_t num_tiles = static_cast<int64_t>(tiles_m) * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps of each CTA (only the leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA credit
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (p.nprod == 3) ? Cfg::STAGE_BYTES : (A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
+      for (int64_t tile = pair; tile < num_tiles; tile += npairs) {
+        const int m0 = static_cast<int>(tile % tiles_m) * (2 * BM) + rank * BM;
+        const int n0 = static_cast<int>(tile / tiles_m) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
+          tma_load_2d_pair(st, &tmAh, &full_bar[stage], kb * 64, m0);
+          tma_load_2d_pair(st + 2 * A_PLANE_BYTES, &tmBh, &full_bar[stage], kb * 64, n0);
+          if (p.nprod == 3) {
+            tma_load_2d_pair(st + A_PLANE_BYTES, &tmAl, &full_bar[stage], kb * 64, m0);
+            tma_load_2d_pair(st + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tmBl, &full_bar[stage], kb * 64, n0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int64_t tile = pair; tile < num_tiles; tile += npairs) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_PLANE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
+          const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32);
+            const uint64_t db_hi = umma_desc_sw128(b_hi + k4 * 32);
+            if (p.nprod == 3) {
+              const uint64_t da_lo = umma_desc_sw128(a_lo + k4 * 32);
+              const uint64_t db_lo = umma_desc_sw128(b_lo + k4 * 32);
+              umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, (kb | k4) != 0);
+              umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, (kb | k4) != 0);
+            }
+          }
+          umma_commit_pair(&empty_bar[stage]);  // the stage is free in BOTH CTAs once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[as]);  // both CTAs' halves of the accumulator are ready
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..9) of both CTAs =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = BN / 2;
+    int as = 0;
+    uint32_t aph = 0;
+    uint32_t tile_parity = 0;
+    for (int64_t tile = pair; tile < num_tiles; tile += npairs) {
+      const int tile_n = static_cast<int>(tile / tiles_m);
+      const int64_t m0 = static_cast<int64_t>(tile % tiles_m) * (2 * BM) + rank * BM;
+      const int64_t n0 = static_cast<int64_t>(tile_n) * BN + half * COLS;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + half * COLS);
+      const int64_t row0 = m0 + quad * 32;
+      const int64_t row = row0 + lane;
+      const bool row_ok = row < M_eff;
+      if (HEAD) {
+        epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
+      } else {
+        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
+        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        const int64_t left = static_cast<int64_t>(M_eff) - row0;
+        const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xm, xo);
+      }
+      tile_parity ^= 1;
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // no CTA tears down its barriers / TMEM while the peer may still signal or read them
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
 // ----------------------------------------------------------------------------
 // host launcher
 // ----------------------------------------------------------------------------
@@ -688,6 +876,37 @@ static int launch_inst(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   if (grid < 1) grid = 1;
   kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(ah, al, bh, bl, dp);
   T4R_LAUNCH_CHECK("gemm_bf16x3_kernel");
+  return 0;
+}
+
+
+template <int BN, bool LN, bool HEAD>
+static int launch_inst2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                        const GemmDev& dp, int64_t max_pair_tiles, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm2_bf16x3_kernel<BN, LN, HEAD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  int pairs = static_cast<int>(max_pair_tiles < max_pairs ? max_pair_tiles : max_pairs);
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  T4R_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dp));
+  T4R_LAUNCH_CHECK("gemm2_bf16x3_kernel");
   return 0;
 }
 
@@ -745,6 +964,29 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
     dp.ep.debug = dbg;
   }
   const int64_t max_tiles = ((pb.M + BM - 1) / BM) * ((pb.N + bn - 1) / bn);
+
+  // T4R_GEMM_2CTA=1: CTA-pair kernel (cta_group::2, 256-row tiles).  Needs 128-byte rows and more than one 128-row tile.
+  static int two_cta = -1;
+  if (two_cta < 0) { const char* e = getenv("T4R_GEMM_2CTA"); two_cta = e ? atoi(e) : T4R_GEMM_2CTA_DEFAULT; }
+  if (two_cta && rb == 128 && pb.M > BM) {
+    CUtensorMap bh2, bl2;
+    T4R_TRY(make_tmap(&bh2, pb.b_planes, pb.N, pb.Kp, bn / 2, rb));
+    T4R_TRY(make_tmap(&bl2, pb.b_planes + pb.b_rows * pb.Kp, pb.N, pb.Kp, bn / 2, rb));
+    const int64_t pair_tiles = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((pb.N + bn - 1) / bn);
+    if (ep.head) {
+      if (bn == 256) return launch_inst2<256, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+      if (bn == 128) return launch_inst2<128, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+      return launch_inst2<64, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+    }
+    if (ln) {
+      if (bn == 256) return launch_inst2<256, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+      if (bn == 128) return launch_inst2<128, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+      return launch_inst2<64, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+    }
+    if (bn == 256) return launch_inst2<256, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+    if (bn == 128) return launch_inst2<128, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+    return launch_inst2<64, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+  }
 
 #define T4R_GEMM_DISPATCH(RBV)                                                                              \
   do {                                                                                                      \
