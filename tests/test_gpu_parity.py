@@ -97,6 +97,31 @@ def test_fused_ffn(ops, M, d):
         assert ((yp[0].float() + yp[1].float()) - y).abs().max().item() < 1e-4
 
 
+@pytest.fixture
+def kernel_variant(request, monkeypatch):
+    """Select a non-default kernel through its environment switch (read per launch by the library)."""
+    for k, v in request.param.items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
+@pytest.mark.parametrize("kernel_variant", [{"T4R_GEMM_2CTA": "0"}, {"T4R_GEMM_2CTA": "1"}, {"T4R_FFN_2CTA": "1"},
+                                            {"T4R_GEMM_2CTA": "0", "T4R_FFN_FUSED": "0"}], indirect=True,
+                         ids=["gemm-1cta", "gemm-cta-pair", "ffn-cta-pair", "unfused-ffn-1cta"])
+def test_kernel_variants_hold_parity(ops, kernel_variant):
+    """Every GEMM flavour that can be selected (single-CTA, CTA pair = tcgen05 cta_group::2; fused feed-forward as a
+    CTA pair) against the same references as the defaults: plain GEMM with an odd shape, LayerNorm epilogue, fused
+    FFN, one XLNet layer stack vs HF, and the head."""
+    test_linear_matches_fp32(ops, 1000, 192, 256, 3)
+    test_linear_matches_fp32(ops, 333, 100, 203, 3)
+    test_linear_epilogues(ops)
+    if "T4R_FFN_FUSED" not in kernel_variant:
+        test_fused_ffn(ops, 700, 128)
+        test_fused_ffn(ops, 40960 // 8 + 5, 256)
+    test_xlnet_encoder_matches_hf(256, 8, 2, 16, 20)
+    test_head_full_softmax(ops, 517, 30011, 256, 1.0)
+
+
 def test_embed_concat_bit_exact(ops):
     cards = {"item": 1001, "cat": 37, "brand": 500}
     dims = {"item": 64, "cat": 13, "brand": 32}

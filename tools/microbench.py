@@ -32,6 +32,15 @@ def timeit(name, fn, iters=20, warm=3, flops=None, bytes_=None):
         import ctypes
         lib = _lib.load()
         arr = (ctypes.c_ulonglong * 8)()
+        if "ffn" in name:
+            a16 = (ctypes.c_ulonglong * 16)()
+            lib.t4r_debug_ffn_cycles(a16, 1)
+            n, t = max(1, a16[7]), max(1, a16[13])
+            print("    epilogue warp per chunk: wait_S %d  tmem_ld %d  gelu+split %d  wait_G_free %d  tmem_st %d | per tile: wait_Y %d  final epilogue %d  (%d chunks)"
+                  % (a16[0] // n, a16[1] // n, a16[2] // n, a16[3] // n, a16[4] // n, a16[5] // t, a16[6] // t, a16[7]), flush=True)
+            print("    mma thread per chunk: wait_S_free %d  gemm1 %d  wait_G %d  wait_Y_free %d  gemm2 %d  (%d tiles)"
+                  % (a16[8] // n, a16[9] // n, a16[10] // n, a16[11] // n, a16[12] // n, a16[13]), flush=True)
+            return
         lib.t4r_debug_gemm_cycles(arr, 1)
         n = max(1, arr[6])
         print("    cta0/warp2 per tile: wait_tfull %d  epilogue %d  | per chunk-sum: tmem_ld %d math %d f32store %d planes %d (cycles; %d tiles)"

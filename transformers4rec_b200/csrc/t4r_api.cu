@@ -158,8 +158,8 @@ extern "C" int t4r_ffn_fwd(const void* x_planes, int64_t M, int d, int hidden, c
 // T4R_FFN_FUSED=0 selects the two-GEMM feed-forward (intermediate planes through HBM) instead of the
 // fused kernel that keeps the GELU'd intermediate in TMEM.
 static bool use_ffn_fused(int d) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("T4R_FFN_FUSED"); on = e ? atoi(e) : T4R_FFN_FUSED_DEFAULT; }
+  int on = T4R_FFN_FUSED_DEFAULT;  // read per call (tests toggle it)
+  if (const char* e = getenv("T4R_FFN_FUSED")) on = atoi(e);
   return on && ffn_fused_supported(d, 4 * d);
 }
 

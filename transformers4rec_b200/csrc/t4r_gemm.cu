@@ -80,6 +80,9 @@ int make_tmap_public(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
 // kernel
 // ----------------------------------------------------------------------------
 constexpr int BM = 128;
+#ifndef T4R_FFN_2CTA_DEFAULT
+#define T4R_FFN_2CTA_DEFAULT 0
+#endif
 #ifndef T4R_GEMM_2CTA_DEFAULT
 #define T4R_GEMM_2CTA_DEFAULT 1
 #endif
@@ -101,6 +104,10 @@ struct GemmCfg {
 
 // T4R_GEMM_DEBUG & 2: cycle counters of one epilogue warp (CTA 0, warp 2), see tools/microbench.py
 __device__ unsigned long long g_dbg_cycles[8];
+// T4R_GEMM_DEBUG & 2 in ffn_fused_kernel: [0..7] one epilogue warp of CTA 0 (wait S, tmem_ld, GELU math, wait G free,
+// tmem_st, wait Y, final epilogue, chunks); [8..15] its MMA thread (wait S free, GEMM1 issue incl. TMA waits, wait G,
+// wait Y free, GEMM2 issue incl. TMA waits, tiles)
+__device__ unsigned long long g_dbg_ffn[16];
 
 struct GemmDev {
   int M;
@@ -911,6 +918,11 @@ static int launch_inst2(const CUtensorMap& ah, const CUtensorMap& al, const CUte
 }
 
 }  // namespace t4r
+extern "C" int t4r_debug_ffn_cycles(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, t4r::g_dbg_ffn, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(t4r::g_dbg_ffn, z, sizeof(z)); }
+  return 0;
+}
 extern "C" int t4r_debug_gemm_cycles(unsigned long long* out8, int reset) {
   if (out8) cudaMemcpyFromSymbol(out8, t4r::g_dbg_cycles, sizeof(unsigned long long) * 8);
   if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(t4r::g_dbg_cycles, z, sizeof(z)); }
@@ -966,8 +978,8 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   const int64_t max_tiles = ((pb.M + BM - 1) / BM) * ((pb.N + bn - 1) / bn);
 
   // T4R_GEMM_2CTA=1: CTA-pair kernel (cta_group::2, 256-row tiles).  Needs 128-byte rows and more than one 128-row tile.
-  static int two_cta = -1;
-  if (two_cta < 0) { const char* e = getenv("T4R_GEMM_2CTA"); two_cta = e ? atoi(e) : T4R_GEMM_2CTA_DEFAULT; }
+  int two_cta = T4R_GEMM_2CTA_DEFAULT;  // read per call so that tests can exercise both kernels in one process
+  if (const char* e = getenv("T4R_GEMM_2CTA")) two_cta = atoi(e);
   if (two_cta && rb == 128 && pb.M > BM) {
     CUtensorMap bh2, bl2;
     T4R_TRY(make_tmap(&bh2, pb.b_planes, pb.N, pb.Kp, bn / 2, rb));
@@ -1143,8 +1155,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t ph_s_empty = 0, ph_g_full = 0, ph_y_empty = 0;
+      const bool mprof = (p.ep.debug & 2) && blockIdx.x == 0;
       auto gemm1 = [&]() {  // S = X W1c^T
+        const long long q0 = mprof ? clock64() : 0;
         mbar_wait(s_empty, ph_s_empty ^ 1);
+        const long long q1 = mprof ? clock64() : 0;
         ph_s_empty ^= 1;
         tc_fence_after_sync();
         for (int kb = 0; kb < KB1; ++kb) {
@@ -1163,17 +1178,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(s_full);
+        if (mprof) { g_dbg_ffn[8] += q1 - q0; g_dbg_ffn[9] += clock64() - q1; }
       };
       for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
         gemm1();
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) gemm1();  // runs on the tensor pipe while the epilogue warps GELU chunk c
+          const long long r0 = mprof ? clock64() : 0;
           mbar_wait(g_full, ph_g_full);
+          const long long r1 = mprof ? clock64() : 0;
           ph_g_full ^= 1;
           if (c == 0) {  // Y of the previous tile must have been drained
             mbar_wait(y_empty, ph_y_empty ^ 1);
             ph_y_empty ^= 1;
           }
+          const long long r2 = mprof ? clock64() : 0;
           tc_fence_after_sync();
           for (int kb = 0; kb < KB2; ++kb) {  // Y += G_c W2c^T, A (= G) from TMEM
             mbar_wait(&full_bar[stage], phase);
@@ -1193,6 +1212,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           }
           umma_commit(g_empty);
           if (c == NC - 1) umma_commit(y_full);
+          if (mprof) { g_dbg_ffn[10] += r1 - r0; g_dbg_ffn[11] += r2 - r1; g_dbg_ffn[12] += clock64() - r2; g_dbg_ffn[13] += (c == NC - 1); }
         }
       }
     }
@@ -1205,11 +1225,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     uint32_t ph_s_full = 0, ph_g_empty = 0, ph_y_full = 0, tile_parity = 0;
     GemmDev gp;  // view of the final epilogue for epilogue_dense
     gp.M = p.M; gp.N = D; gp.nkb = 0; gp.nprod = 3; gp.m_dev = nullptr; gp.ep = p.ep;
+    const bool eprof = (p.ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
     for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
       const int64_t row0 = static_cast<int64_t>(tile) * BM + quad * 32;
       for (int c = 0; c < NC; ++c) {
         // ---- S chunk -> bias + GELU -> split -> G (A operand of GEMM2) in TMEM
+        const long long e0 = eprof ? clock64() : 0;
         mbar_wait(s_full, ph_s_full);
+        const long long e1 = eprof ? clock64() : 0;
         ph_s_full ^= 1;
         tc_fence_after_sync();
         float v[64];
@@ -1217,18 +1240,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by GEMM1(c+1)
+        const long long e2 = eprof ? clock64() : 0;
         const float* b1 = p.b1 + c * FFN_HC + half * 64;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + j);
-          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
         uint32_t gh[32], gl[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], gh[j], gl[j]);
+        for (int j = 0; j < 16; ++j) {  // bias + GELU + hi/lo split on packed fp32 pairs (fma.rn.f32x2)
+          const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + j);
+          const float2 g0 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 0], v[4 * j + 1]), make_float2(b.x, b.y)));
+          const float2 g1 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w)));
+          split_bf16x2(g0, gh[2 * j], gl[2 * j]);
+          split_bf16x2(g1, gh[2 * j + 1], gl[2 * j + 1]);
+        }
+        const long long e3 = eprof ? clock64() : 0;
         mbar_wait(g_empty, ph_g_empty ^ 1);  // GEMM2(c-1) has finished reading G
+        const long long e4 = eprof ? clock64() : 0;
         ph_g_empty ^= 1;
         tc_fence_after_sync();
 #pragma unroll
@@ -1245,9 +1270,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(g_full);
+        if (eprof) {
+          g_dbg_ffn[0] += e1 - e0; g_dbg_ffn[1] += e2 - e1; g_dbg_ffn[2] += e3 - e2; g_dbg_ffn[3] += e4 - e3;
+          g_dbg_ffn[4] += clock64() - e4; g_dbg_ffn[7] += 1;
+        }
       }
       // ---- final epilogue of the tile: Y + b2 + residual -> LayerNorm -> stores
+      const long long f0 = eprof ? clock64() : 0;
       mbar_wait(y_full, ph_y_full);
+      const long long f1 = eprof ? clock64() : 0;
       ph_y_full ^= 1;
       tc_fence_after_sync();
       {
@@ -1262,6 +1293,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(y_empty);
+      if (eprof) { g_dbg_ffn[5] += f1 - f0; g_dbg_ffn[6] += clock64() - f1; }
     }
   }
 
@@ -1283,6 +1315,280 @@ static int launch_ffn_inst(const CUtensorMap (&tm)[6], const FfnDev& dp, cudaStr
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 320, FFN_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dp);
   T4R_LAUNCH_CHECK("ffn_fused_kernel");
+  return 0;
+}
+
+
+// ----------------------------------------------------------------------------
+// CTA-pair variant of the fused feed-forward (cta_group::2, 256 rows per pair): each CTA streams its own 128 rows
+// of X but only HALF of every W1 / W2 chunk, so the weight stream per SM halves.  Same schedule as
+// ffn_fused_kernel; the six hand-off barriers live in the leader (rank 0) for the epilogue -> MMA direction
+// (s_empty, g_full, y_empty: 16 arrivals = 8 warps x 2 CTAs) and are multicast to both CTAs for the MMA -> epilogue
+// direction (s_full, g_empty, y_full).  GEMM2 takes its A operand (the GELU'd chunk) from each CTA's own TMEM.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+constexpr int FFN2_STAGE_BYTES = 48 * 1024;  // GEMM1: X kb hi/lo (2 x 16 KB) + half W1 chunk hi/lo (2 x 8 KB); GEMM2: half W2 hi/lo (2 x 16 KB at d = 256)
+constexpr int FFN2_STAGES = 4;
+constexpr int FFN2_SMEM_BYTES = FFN2_STAGES * FFN2_STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                  const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+                  const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnDev p) {
+  constexpr int KB1 = D / 64;
+  constexpr int KB2 = FFN_HC / 64;
+  constexpr int XP = BM * 128;                // X plane bytes per k block (own 128 rows)
+  constexpr int W1P = (FFN_HC / 2) * 128;     // this CTA's half of the W1 chunk
+  constexpr int W2P = (D / 2) * 128;          // this CTA's half of the W2 chunk
+  constexpr uint32_t Y_COL = 0, S_COL = 256, GH_COL = 384, GL_COL = 448;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FFN2_STAGES * FFN2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + FFN2_STAGES;
+  uint64_t* s_full = empty_bar + FFN2_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* g_full = s_empty + 1;
+  uint64_t* g_empty = g_full + 1;
+  uint64_t* y_full = g_empty + 1;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+  float2* xch = reinterpret_cast<float2*>(smem + FFN2_STAGES * FFN2_STAGE_BYTES + 256);
+  float* stg_all = reinterpret_cast<float*>(smem + FFN2_STAGES * FFN2_STAGE_BYTES + 256 + 4096);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int NC = p.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl);
+    tma_prefetch_desc(&tmW1h); tma_prefetch_desc(&tmW1l);
+    tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < FFN2_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 16);
+    mbar_init(g_full, 16); mbar_init(g_empty, 1);
+    mbar_init(y_full, 1); mbar_init(y_empty, 16);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes credited to the leader's full barrier) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_g1 = [&](int m0, int c, int kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * FFN2_STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * XP + 2 * W1P));
+        tma_load_2d_pair(st, &tmXh, &full_bar[stage], kb * 64, m0);
+        tma_load_2d_pair(st + XP, &tmXl, &full_bar[stage], kb * 64, m0);
+        tma_load_2d_pair(st + 2 * XP, &tmW1h, &full_bar[stage], kb * 64, c * FFN_HC + rank * (FFN_HC / 2));
+        tma_load_2d_pair(st + 2 * XP + W1P, &tmW1l, &full_bar[stage], kb * 64, c * FFN_HC + rank * (FFN_HC / 2));
+        if (++stage == FFN2_STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto load_g2 = [&](int c, int kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * FFN2_STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (2 * W2P));
+        tma_load_2d_pair(st, &tmW2h, &full_bar[stage], c * FFN_HC + kb * 64, rank * (D / 2));
+        tma_load_2d_pair(st + W2P, &tmW2l, &full_bar[stage], c * FFN_HC + kb * 64, rank * (D / 2));
+        if (++stage == FFN2_STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = pair; tile < tiles_m; tile += npairs) {
+        const int m0 = tile * (2 * BM) + rank * BM;
+        for (int kb = 0; kb < KB1; ++kb) load_g1(m0, 0, kb);
+        for (int c = 0; c < NC; ++c) {
+          if (c + 1 < NC)
+            for (int kb = 0; kb < KB1; ++kb) load_g1(m0, c + 1, kb);
+          for (int kb = 0; kb < KB2; ++kb) load_g2(c, kb);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(2 * BM, FFN_HC);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BM, D);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t ph_s_empty = 0, ph_g_full = 0, ph_y_empty = 0;
+      auto gemm1 = [&]() {
+        mbar_wait(s_empty, ph_s_empty ^ 1);
+        ph_s_empty ^= 1;
+        tc_fence_after_sync();
+        for (int kb = 0; kb < KB1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(smem + stage * FFN2_STAGE_BYTES);
+          const uint32_t a_lo = a_hi + XP, b_hi = a_hi + 2 * XP, b_lo = b_hi + W1P;
+          if (!(p.ep.debug & 4))
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_bf16_pair(tmem_base + S_COL, umma_desc_sw128(a_lo + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, (kb | k4) != 0);
+            umma_bf16_pair(tmem_base + S_COL, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_lo + k4 * 32), idesc1, 1u);
+            umma_bf16_pair(tmem_base + S_COL, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, 1u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == FFN2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(s_full);
+      };
+      for (int tile = pair; tile < tiles_m; tile += npairs) {
+        gemm1();
+        for (int c = 0; c < NC; ++c) {
+          if (c + 1 < NC) gemm1();
+          mbar_wait(g_full, ph_g_full);
+          ph_g_full ^= 1;
+          if (c == 0) {
+            mbar_wait(y_empty, ph_y_empty ^ 1);
+            ph_y_empty ^= 1;
+          }
+          tc_fence_after_sync();
+          for (int kb = 0; kb < KB2; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t b_hi = smem_u32(smem + stage * FFN2_STAGE_BYTES);
+            const uint32_t b_lo = b_hi + W2P;
+            if (!(p.ep.debug & 8))
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t acol = static_cast<uint32_t>(kb * 32 + k4 * 8);
+              umma_bf16_ts_pair(tmem_base + Y_COL, tmem_base + GL_COL + acol, umma_desc_sw128(b_hi + k4 * 32), idesc2, (c | kb | k4) != 0);
+              umma_bf16_ts_pair(tmem_base + Y_COL, tmem_base + GH_COL + acol, umma_desc_sw128(b_lo + k4 * 32), idesc2, 1u);
+              umma_bf16_ts_pair(tmem_base + Y_COL, tmem_base + GH_COL + acol, umma_desc_sw128(b_hi + k4 * 32), idesc2, 1u);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+            if (++stage == FFN2_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(g_empty);
+          if (c == NC - 1) umma_commit_pair(y_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..9) of both CTAs =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t ph_s_full = 0, ph_g_empty = 0, ph_y_full = 0, tile_parity = 0;
+    GemmDev gp;
+    gp.M = p.M; gp.N = D; gp.nkb = 0; gp.nprod = 3; gp.m_dev = nullptr; gp.ep = p.ep;
+    for (int tile = pair; tile < tiles_m; tile += npairs) {
+      const int64_t row0 = static_cast<int64_t>(tile) * (2 * BM) + rank * BM + quad * 32;
+      for (int c = 0; c < NC; ++c) {
+        mbar_wait(s_full, ph_s_full);
+        ph_s_full ^= 1;
+        tc_fence_after_sync();
+        float v[64];
+        tmem_ld<64>(tmem_base + lane_base + S_COL + half * 64, v);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(s_empty);
+        const float* b1 = p.b1 + c * FFN_HC + half * 64;
+        uint32_t gh[32], gl[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {  // bias + GELU + hi/lo split on packed fp32 pairs (fma.rn.f32x2)
+          const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + j);
+          const float2 g0 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 0], v[4 * j + 1]), make_float2(b.x, b.y)));
+          const float2 g1 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w)));
+          split_bf16x2(g0, gh[2 * j], gl[2 * j]);
+          split_bf16x2(g1, gh[2 * j + 1], gl[2 * j + 1]);
+        }
+        mbar_wait(g_empty, ph_g_empty ^ 1);
+        ph_g_empty ^= 1;
+        tc_fence_after_sync();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = gh[q * 8 + j];
+          tmem_st8(tmem_base + lane_base + GH_COL + half * 32 + q * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = gl[q * 8 + j];
+          tmem_st8(tmem_base + lane_base + GL_COL + half * 32 + q * 8, r);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(g_full);
+      }
+      mbar_wait(y_full, ph_y_full);
+      ph_y_full ^= 1;
+      tc_fence_after_sync();
+      {
+        const int64_t left = static_cast<int64_t>(p.M) - row0;
+        const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
+        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        epilogue_dense<D, true>(gp, tmem_base + lane_base + Y_COL + half * (D / 2), row0, rows_valid, lane,
+                                static_cast<int64_t>(half) * (D / 2), stg_all + (warp - 2) * STG_WORDS, xm, xo);
+        tile_parity ^= 1;
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(y_empty);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+template <int D>
+static int launch_ffn2_inst(const CUtensorMap (&tm)[6], const FfnDev& dp, cudaStream_t stream) {
+  auto kern = ffn_fused2_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int pair_tiles = (dp.M + 2 * BM - 1) / (2 * BM);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = FFN2_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  T4R_CUDA(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dp));
+  T4R_LAUNCH_CHECK("ffn_fused2_kernel");
   return 0;
 }
 
@@ -1310,7 +1616,19 @@ int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    dp.ep.debug = dbg & (1 | 4 | 8);
+    dp.ep.debug = dbg & (1 | 2 | 4 | 8);
+  }
+  int two_cta = T4R_FFN_2CTA_DEFAULT;  // measured slower than the single-CTA kernel: opt-in, kept parity-tested
+  if (const char* e = getenv("T4R_FFN_2CTA")) two_cta = atoi(e);
+  if (two_cta && M > BM) {  // CTA pairs: each CTA streams half of every weight chunk
+    CUtensorMap t2[6] = {tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]};
+    T4R_TRY(make_tmap(&t2[2], w1_planes, hidden, d, FFN_HC / 2, 128));
+    T4R_TRY(make_tmap(&t2[3], w1_planes + static_cast<int64_t>(hidden) * d, hidden, d, FFN_HC / 2, 128));
+    T4R_TRY(make_tmap(&t2[4], w2_planes, d, hidden, d / 2, 128));
+    T4R_TRY(make_tmap(&t2[5], w2_planes + static_cast<int64_t>(d) * hidden, d, hidden, d / 2, 128));
+    if (d == 256) return launch_ffn2_inst<256>(t2, dp, stream);
+    if (d == 128) return launch_ffn2_inst<128>(t2, dp, stream);
+    return launch_ffn2_inst<64>(t2, dp, stream);
   }
   if (d == 256) return launch_ffn_inst<256>(tm, dp, stream);
   if (d == 128) return launch_ffn_inst<128>(tm, dp, stream);
