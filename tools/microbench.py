@@ -40,6 +40,9 @@ def timeit(name, fn, iters=20, warm=3, flops=None, bytes_=None):
                   % (a16[0] // n, a16[1] // n, a16[2] // n, a16[3] // n, a16[4] // n, a16[5] // t, a16[6] // t, a16[7]), flush=True)
             print("    mma thread per chunk: wait_S_free %d  gemm1 %d  wait_G %d  wait_Y_free %d  gemm2 %d  (%d tiles)"
                   % (a16[8] // n, a16[9] // n, a16[10] // n, a16[11] // n, a16[12] // n, a16[13]), flush=True)
+            lib.t4r_debug_gemm_cycles(arr, 1)
+            print("    final LN epilogue per tile: tmem_ld %d  bias+residual %d  stats+exchange %d  normalise+stores %d"
+                  % (arr[2] // t, arr[3] // t, arr[4] // t, arr[5] // t), flush=True)
             return
         lib.t4r_debug_gemm_cycles(arr, 1)
         n = max(1, arr[6])

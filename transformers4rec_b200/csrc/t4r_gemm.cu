@@ -301,6 +301,159 @@ __device__ __forceinline__ void warp_store_planes(float* stg_f, const float (&v)
   }
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// LayerNorm epilogue, chunked: the half-row is processed 32 columns at a time and parked back in its TMEM columns
+// between the two passes (tcgen05.st), instead of living in 128 registers.  That removes the spills of the
+// single-pass form and leaves room to issue the coalesced residual loads of chunk c + 1 before chunk c is processed:
+// the staged residual read used to expose the global-load latency twice per 32 columns (measured 18-22 k of the
+// 35-40 k cycles this epilogue cost per 128 x 256 tile).  Statistics: exact two-pass mean / M2 per 32-column chunk,
+// chunks and the two half-rows merged with the pairwise (Chan et al.) update.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[q * 8 + j]);
+    tmem_st8(taddr + q * 8, r);
+  }
+}
+// coalesced loads of one 32-row x 32-column residual block into registers (8 rows x 64 B per instruction)
+__device__ __forceinline__ void residual_issue(const GemmEpilogue& ep, int64_t row0, int64_t ncol0, int rows_valid, int lane,
+                                               uint4 (&raw)[8]) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2), c = lane & 3;
+    const bool ok = r < rows_valid;
+    if (ep.residual) {
+      const float* g = ep.residual + (row0 + r) * ep.ldr + ncol0 + 4 * c;
+      raw[it] = ok ? __ldg(reinterpret_cast<const uint4*>(g)) : make_uint4(0u, 0u, 0u, 0u);
+      raw[4 + it] = ok ? __ldg(reinterpret_cast<const uint4*>(g + 16)) : make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      const __nv_bfloat16* g = ep.residual_planes + (row0 + r) * ep.ldrp + ncol0 + 8 * c;
+      raw[it] = ok ? __ldg(reinterpret_cast<const uint4*>(g)) : make_uint4(0u, 0u, 0u, 0u);
+      raw[4 + it] = ok ? __ldg(reinterpret_cast<const uint4*>(g + ep.residual_plane_stride)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+// transpose the block through the warp's staging tile and add it to the thread's row
+__device__ __forceinline__ void residual_add(const GemmEpilogue& ep, float* stg_f, const uint4 (&raw)[8], int lane,
+                                             float (&v)[32]) {
+  uint32_t* stg = reinterpret_cast<uint32_t*>(stg_f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2), c = lane & 3;
+      *reinterpret_cast<uint4*>(stg + r * STG_LD + 4 * c) = raw[h * 4 + it];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = *reinterpret_cast<const uint4*>(stg + lane * STG_LD + 4 * j);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+      if (ep.residual) {  // fp32: half h holds columns [16 h, 16 h + 16)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[h * 16 + 4 * j + k] += __uint_as_float(w[k]);
+      } else {            // planes: half 0 = hi, half 1 = lo, eight bf16 per 16 bytes
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+          v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+        }
+      }
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_ln_chunked(const GemmDev& p, uint32_t taddr, int64_t row0, int rows_valid, int lane,
+                                                    int64_t n0, float* stg, float2* xch_mine, const float2* xch_other) {
+  constexpr int COLS = BN / 2, NCH = COLS / 32;
+  const GemmEpilogue& ep = p.ep;
+  if (ep.debug & 1) rows_valid = 0;
+  const bool row_ok = lane < rows_valid;
+  const int64_t row = row0 + lane;
+  int code = 0;
+  if (row_ok && ep.row_code) code = ep.row_code[row];
+  const bool has_res = ep.residual || ep.residual_planes;
+  const bool lprof = (ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
+  const long long l0 = lprof ? clock64() : 0;
+  // ---- pass 1: bias (+act, mask) + residual, statistics, park the pre-LN values in TMEM
+  uint4 nxt[8];
+  if (has_res) residual_issue(ep, row0, n0, rows_valid, lane, nxt);
+  float mean_h = 0.f, m2_h = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    uint4 cur[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    if (has_res && c + 1 < NCH) residual_issue(ep, row0, n0 + (c + 1) * 32, rows_valid, lane, nxt);
+    float v[32];
+    tmem_ld<32>(taddr + c * 32, v);
+    dense_chunk(v, ep, n0 + c * 32, code);
+    if (has_res) residual_add(ep, stg, cur, lane, v);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
+    const float mc = s * (1.f / 32.f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = v[j] - mc;
+      q = fmaf(d, d, q);
+    }
+    // merge chunk c (32 values) into the running (mean, M2) of 32 c values
+    const float delta = mc - mean_h;
+    mean_h += delta * (1.f / static_cast<float>(c + 1));
+    m2_h += q + delta * delta * (32.f * static_cast<float>(c) / static_cast<float>(c + 1));
+    tmem_st32(taddr + c * 32, v);
+  }
+  tmem_st_wait();
+  const long long l1 = lprof ? clock64() : 0;
+  // ---- combine the two halves of the row (equal counts)
+  *xch_mine = make_float2(mean_h, m2_h);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float2 o = *xch_other;
+  const float delta = o.x - mean_h;
+  const float mean = 0.5f * (mean_h + o.x);
+  const float m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
+  const float rstd = rsqrtf(m2 * (1.f / BN) + ep.ln_eps);
+  const long long l2 = lprof ? clock64() : 0;
+  // ---- pass 2: normalise and store
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float v[32];
+    tmem_ld<32>(taddr + c * 32, v);
+    const int64_t ncol0 = n0 + c * 32;
+    if (ep.out_pre) warp_store_f32(stg, v, 1.f, ep.out_pre + row0 * ep.ldp + ncol0, ep.ldp, rows_valid, lane);
+    const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
+    const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+      v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
+      v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+      v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
+      v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+    }
+    if (ep.out_f32) warp_store_f32(stg, v, ep.out_scale, ep.out_f32 + row0 * ep.ldo + ncol0, ep.ldo, rows_valid, lane);
+    if (ep.out_planes)
+      warp_store_planes(stg, v, ep.out_planes + row0 * ep.ldpl + ncol0, ep.plane_stride, ep.ldpl, rows_valid, lane);
+  }
+  if (lprof) {  // phases: pass 1 (bias + residual + stats + park) | exchange | pass 2 (normalise + stores)
+    g_dbg_cycles[2] += 0; g_dbg_cycles[3] += l1 - l0; g_dbg_cycles[4] += l2 - l1; g_dbg_cycles[5] += clock64() - l2;
+  }
+}
+
 // Each epilogue thread owns one output row (its TMEM lane) and COLS = BN/2 columns
 // (warps 2-5 take the first half of the tile's columns, warps 6-9 the second half).
 // row0 = first row of the warp's 32-row block; n0 = first column of the warp's half.
@@ -315,60 +468,7 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
   int code = 0;
   if (row_ok && ep.row_code) code = ep.row_code[row];
   if constexpr (LN) {
-    // single pass: the thread's whole half-row lives in registers
-    float v[COLS];
-    tmem_ld<COLS>(taddr, v);
-#pragma unroll
-    for (int c = 0; c < COLS / 32; ++c) {
-      float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
-      const int64_t ncol0 = n0 + c * 32;
-      dense_chunk(vc, ep, ncol0, code);
-      if (ep.residual || ep.residual_planes) {
-        float rs[32];
-        if (ep.residual) warp_load_f32(stg, ep.residual + row0 * ep.ldr + ncol0, ep.ldr, rows_valid, lane, rs);
-        else warp_load_planes(stg, ep.residual_planes + row0 * ep.ldrp + ncol0, ep.residual_plane_stride, ep.ldrp,
-                              rows_valid, lane, rs);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) vc[j] += rs[j];
-      }
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < COLS; ++j) sum += v[j];
-    const float mean_h = sum * (1.f / COLS);
-    float m2_h = 0.f;
-#pragma unroll
-    for (int j = 0; j < COLS; ++j) {
-      const float d = v[j] - mean_h;
-      m2_h = fmaf(d, d, m2_h);
-    }
-    // combine the two halves of the row (Chan et al. pairwise update, equal counts)
-    *xch_mine = make_float2(mean_h, m2_h);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float2 o = *xch_other;
-    const float delta = o.x - mean_h;
-    const float mean = 0.5f * (mean_h + o.x);
-    const float m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
-    const float rstd = rsqrtf(m2 * (1.f / BN) + ep.ln_eps);
-#pragma unroll
-    for (int c = 0; c < COLS / 32; ++c) {
-      float (&vc)[32] = *reinterpret_cast<float (*)[32]>(&v[c * 32]);
-      const int64_t ncol0 = n0 + c * 32;
-      if (ep.out_pre) warp_store_f32(stg, vc, 1.f, ep.out_pre + row0 * ep.ldp + ncol0, ep.ldp, rows_valid, lane);
-      const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + ncol0);
-      const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + ncol0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-        vc[4 * j + 0] = (vc[4 * j + 0] - mean) * rstd * g.x + b.x;
-        vc[4 * j + 1] = (vc[4 * j + 1] - mean) * rstd * g.y + b.y;
-        vc[4 * j + 2] = (vc[4 * j + 2] - mean) * rstd * g.z + b.z;
-        vc[4 * j + 3] = (vc[4 * j + 3] - mean) * rstd * g.w + b.w;
-      }
-      if (ep.out_f32) warp_store_f32(stg, vc, ep.out_scale, ep.out_f32 + row0 * ep.ldo + ncol0, ep.ldo, rows_valid, lane);
-      if (ep.out_planes)
-        warp_store_planes(stg, vc, ep.out_planes + row0 * ep.ldpl + ncol0, ep.plane_stride, ep.ldpl, rows_valid, lane);
-    }
+    epilogue_ln_chunked<BN>(p, taddr, row0, rows_valid, lane, n0, stg, xch_mine, xch_other);
   } else {
     const bool prof = (ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
 #pragma unroll 1
@@ -1034,12 +1134,6 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
 // the GELU of chunk c runs under GEMM1(c+1).  All products are issued three times (split bf16).
 // TMEM columns: Y [0,256)  S [256,384)  G_hi [384,448)  G_lo [448,512).
 // ============================================================================
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -1616,7 +1710,7 @@ int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    dp.ep.debug = dbg & (1 | 2 | 4 | 8);
+    dp.ep.debug = dbg & (1 | 2 | 4 | 8 | 64);
   }
   int two_cta = T4R_FFN_2CTA_DEFAULT;  // measured slower than the single-CTA kernel: opt-in, kept parity-tested
   if (const char* e = getenv("T4R_FFN_2CTA")) two_cta = atoi(e);
