@@ -55,8 +55,8 @@ def load_peaks():
 
 def head_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the head GEMM from the committed ncu capture
-    (profiles/r1_head_traffic.json; config2 only) -- None when no capture is on record."""
-    p = os.path.join(ROOT, "profiles", "r1_head_traffic.json")
+    (profiles/r1c_head_traffic.json; config2 only) -- None when no capture is on record."""
+    p = os.path.join(ROOT, "profiles", "r1c_head_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)["dram_bytes_per_launch"]
@@ -324,7 +324,7 @@ def main():
         head_flops = 2.0 * (T * world) * (V / world) * cfg["De"]
     achieved_tf = head_flops / (head_ms_avg * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel<256,false,true> (tied logits + online LSE)",
+    roofline = {"bound": "tensor", "kernel": "gemm2_bf16x3_kernel<256,false,true> (CTA-pair tcgen05 GEMM: tied logits + online LSE)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
                 "traffic": head_traffic() if args.workload == "config2" else None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,

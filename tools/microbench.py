@@ -108,6 +108,16 @@ def main():
             outs = [ops.embed_concat([(table, ids, 0)], [], M, d, False, True) for ids in id_sets]
         timeit("embed_concat 1M x 256 (8 id sets, graph)", gph.replay, iters=10,
                bytes_=8 * M * (8 + 4 * d + 4 * d))
+    if on("head4"):
+        # config-4-like shard: 10 240 label rows (two ranks' worth) against 2.5 M local table rows
+        V, T = 2_500_001, 10240
+        W = torch.randn(V, d, device=dev) * 0.05
+        wp = ops.split_planes(W)
+        xt = torch.randn(T, d, device=dev)
+        xtp = ops.split_planes(xt)
+        y = torch.randint(1, V, (T,), device=dev)
+        timeit("head 10240 x 2.5M x 256", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W), iters=3, flops=2 * T * V * d)
+        del W, wp
     if on("head64"):
         # config-3-like head: De = 64 puts a single 64-wide K block under each 128x256 tile, so the online-LSE
         # epilogue, not the MMA main loop, is what bounds it
