@@ -32,14 +32,28 @@ def _labels(rank):
     return torch.randn((T, De), generator=g), torch.randint(1, V, (T,), generator=g)
 
 
-def _head_rows(xg, yg, local_table, w_planes, lo, inv_tau):
+def _head_rows(xg, yg, local_table, w_planes, lo, inv_tau, rank_tgt=None):
     logits = (xg @ local_table.t()) * inv_tau
     lse = torch.logsumexp(logits, dim=1)
     loc = yg - lo
     mine = (loc >= 0) & (loc < local_table.shape[0])
     tgt = torch.where(mine, logits.gather(1, loc.clamp(0, local_table.shape[0] - 1).unsqueeze(1)).squeeze(1),
                       torch.zeros_like(lse))
-    return torch.stack([lse, tgt], dim=1)
+    part = torch.stack([lse, tgt], dim=1)
+    if rank_tgt is None:
+        return part
+    # classes of THIS shard scoring above the label's global logit (ties: lower id first), the label itself excluded
+    col = torch.arange(local_table.shape[0]).unsqueeze(0) + lo
+    above = (logits > rank_tgt.unsqueeze(1)) | ((logits == rank_tgt.unsqueeze(1)) & (col < yg.unsqueeze(1)))
+    above &= col != yg.unsqueeze(1)
+    return part, above.sum(dim=1).to(torch.int32)
+
+
+def _label_logit(xg, yg, local_table, lo, inv_tau):
+    loc = yg - lo
+    mine = (loc >= 0) & (loc < local_table.shape[0])
+    rows = local_table[loc.clamp(0, local_table.shape[0] - 1)]
+    return torch.where(mine, (xg * rows).sum(dim=1) * inv_tau, torch.zeros(xg.shape[0]))
 
 
 def _combine(parts):
@@ -69,6 +83,20 @@ def _worker(rank, world, port, q):
         start = sum(x.shape[0] for x in xs[:rank])
         ok_head = (torch.allclose(row_loss, ref_rows[start:start + xt.shape[0]], atol=1e-5)
                    and abs(loss.item() - ref_rows.mean().item()) < 1e-5 and T_total == xg.shape[0])
+        # evaluation: cross-shard label ranks (two more all-reduces) against a single-process count
+        _, loss_e, _, ranks = D.sharded_softmax_ce(xt, y, local, V, head_rows=_head_rows, combine=_combine,
+                                                   want_rank=True, label_logit=_label_logit)
+        full = xt @ table.t()
+        tgt = full.gather(1, y.unsqueeze(1))
+        ids = torch.arange(V).unsqueeze(0)
+        ref_rank = (((full > tgt) | ((full == tgt) & (ids < y.unsqueeze(1)))) & (ids != y.unsqueeze(1))).sum(dim=1)
+        ok_head = ok_head and torch.equal(ranks.long(), ref_rank) and abs(loss_e.item() - ref_rows.mean().item()) < 1e-5
+        # module form: ShardedEmbedding with ragged (per-rank different) id counts, as the sampled-softmax head uses it
+        emb = D.ShardedEmbedding.from_full(table)
+        emb.gather_rows, emb.place = (lambda t, i: t[i]), (lambda recv, unp: (recv[unp.long()], None))
+        some = y[: 3 + 2 * rank]
+        got, _ = emb.lookup(some, ragged=True)
+        ok_lookup = ok_lookup and torch.equal(got, table[some]) and emb.weight.shape[0] == hi - lo
         q.put((rank, ok_lookup, ok_head))
     finally:
         dist.destroy_process_group()

@@ -186,6 +186,9 @@ class ShardedEmbedding(torch.nn.Module):
         self.lo, self.hi = shard_bounds(self.num_embeddings, self.rank, self.world)
         self.weight = torch.nn.Parameter(torch.empty((self.hi - self.lo, embedding_dim), device=device))
         (initializer or (lambda w: torch.nn.init.normal_(w, mean=0.0, std=0.05)))(self.weight)
+        # local compute steps of the exchange; None = the CUDA kernels (the gloo tests inject stand-ins)
+        self.gather_rows: Optional[Callable] = None
+        self.place: Optional[Callable] = None
 
     @classmethod
     def from_full(cls, full_weight: torch.Tensor, group=None, padding_idx: int = 0) -> "ShardedEmbedding":
@@ -207,7 +210,8 @@ class ShardedEmbedding(torch.nn.Module):
             n_max = int(counts.max())
             if n_max > n:
                 flat = torch.cat([flat, flat.new_full((n_max - n,), self.padding_idx)])
-        rows, planes = sharded_embedding_lookup(self.weight.detach(), flat, self.num_embeddings, self.group)
+        rows, planes = sharded_embedding_lookup(self.weight.detach(), flat, self.num_embeddings, self.group,
+                                                gather_rows=self.gather_rows, place=self.place)
         if ragged and rows.shape[0] != n:
             rows, planes = rows[:n], (planes[:, :n] if planes is not None else None)
         return rows, planes
