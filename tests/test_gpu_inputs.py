@@ -244,3 +244,24 @@ def test_reference_feature_test_shape_203():
                            else torch.rand(shape, generator=g)).cuda()
     out = tab(batch)
     assert list(out.shape) == [100, 20, 203]
+
+
+def test_out_of_range_ids_surface_as_the_reference_error(monkeypatch):
+    """nn.Embedding raises IndexError for an id outside the table; the fused gather flags it (and reads row 0)."""
+    import transformers4rec_b200.torch as tr
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 100, tags=[tr.Tags.ITEM_ID]),
+                        tr.ColumnSchema.create_categorical("category/list", 10)])
+    for kwargs in ({}, {"post": "layer-norm"}):  # specialised gather and general input-block kernel
+        tab = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=6, aggregation="concat", **kwargs).cuda()
+        batch = synth_batch(4, 6, {"item_id/list": 101, "category/list": 11}, seed=1)
+        tab({k: v.cuda() for k, v in batch.items()})
+        tab.check_ids()  # in range: no error
+        bad = {k: v.clone() for k, v in batch.items()}
+        bad["category/list"][2, 1] = 11  # one past the last row of the 11-row table
+        tab({k: v.cuda() for k, v in bad.items()})
+        with pytest.raises(IndexError, match="index out of range in self"):
+            tab.check_ids()
+        monkeypatch.setenv("T4R_CHECK_IDS", "1")
+        with pytest.raises(IndexError):
+            tab({k: v.cuda() for k, v in bad.items()})
+        monkeypatch.delenv("T4R_CHECK_IDS")

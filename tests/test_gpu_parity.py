@@ -122,6 +122,18 @@ def test_kernel_variants_hold_parity(ops, kernel_variant):
     test_head_full_softmax(ops, 517, 30011, 256, 1.0)
 
 
+def test_unsupported_shapes_fail_loudly():
+    """no silent fallback: shapes outside the kernels' envelope raise T4RError with the limit in the message"""
+    import transformers4rec_b200.torch as tr
+    from transformers4rec_b200 import T4RError
+    hf = O.build_hf_xlnet(64, 4, 1).eval()
+    blk = tr.TransformerBlock(hf).cuda()
+    with pytest.raises(T4RError, match="1..64"):
+        blk(torch.randn(2, 65, 64, device="cuda"))
+    with pytest.raises(T4RError, match="d_model must be 64, 128 or 256"):
+        tr.TransformerBlock(O.build_hf_xlnet(96, 4, 1).eval()).cuda()(torch.randn(2, 8, 96, device="cuda"))
+
+
 def test_embed_concat_bit_exact(ops):
     cards = {"item": 1001, "cat": 37, "brand": 500}
     dims = {"item": 64, "cat": 13, "brand": 32}
@@ -198,8 +210,11 @@ def test_compact_targets(ops):
     assert (rows[T:] == 0).all() and (labs[T:] == 0).all()
 
 
-@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 8, 1, 9, 50), (64, 1, 1, 5, 21)])
+@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 8, 1, 9, 50), (64, 1, 1, 5, 21),
+                                        (64, 4, 1, 1, 2), (64, 2, 1, 3, 64), (256, 4, 1, 2, 30), (128, 4, 1, 7, 31)])
 def test_xlnet_encoder_matches_hf(d, H, NL, B, L):
+    """incl. the edges: one session of two items, the longest supported sequence (64, FFMA attention), the last length
+    of the tensor-path attention (30) and the first of the fallback (31), dh = 64."""
     import transformers4rec_b200.torch as tr
     torch.manual_seed(10)
     hf = O.build_hf_xlnet(d, H, NL).eval()
@@ -215,12 +230,13 @@ def test_xlnet_encoder_matches_hf(d, H, NL, B, L):
         ref = O.hf_encoder_forward(hf, x)
         ref2 = O.xlnet_forward_restated(x, hf.state_dict(), NL, H)
         got = blk(x.cuda()).cpu()
-    assert (ref - ref2).abs().max().item() < 1e-4
+    assert (ref - ref2).abs().max().item() < 3e-4  # HF vs the restated math, both CPU fp32 (different op order)
     err = (got - ref).abs().max().item()
     assert err < TOL, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 2, 1, 7, 40)])
+@pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 2, 1, 7, 40), (64, 4, 1, 1, 2),
+                                        (64, 1, 1, 2, 64), (128, 4, 1, 5, 32), (128, 4, 1, 5, 33)])
 def test_gpt2_encoder_matches_hf(d, H, NL, B, L):
     import transformers4rec_b200.torch as tr
     torch.manual_seed(11)
@@ -237,7 +253,7 @@ def test_gpt2_encoder_matches_hf(d, H, NL, B, L):
         ref = O.hf_encoder_forward(hf, x)
         ref2 = O.gpt2_forward_restated(x, hf.state_dict(), NL, H)
         got = blk(x.cuda()).cpu()
-    assert (ref - ref2).abs().max().item() < 1e-4
+    assert (ref - ref2).abs().max().item() < 3e-4  # HF vs the restated math, both CPU fp32 (different op order)
     err = (got - ref).abs().max().item()
     assert err < TOL, f"max abs err {err}"
 

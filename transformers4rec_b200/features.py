@@ -16,6 +16,7 @@ element-wise aggregations (tabular/aggregation.py:139-193) and StochasticSwapNoi
 """
 from __future__ import annotations
 
+import os
 from functools import partial
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
@@ -614,9 +615,12 @@ class TabularSequenceFeatures(nn.Module):
             return ops.input_block(feats, M, L, C_width, agg=agg, item_feature=item_feature, want_f32=want_f32,
                                    want_planes=want_planes)
 
+        check = os.environ.get("T4R_CHECK_IDS", "0") == "1"
         proj = self._projection_linear()
         if proj is not None:
             _, planes, self._id_err = gather(False, True)
+            if check:
+                self.check_ids()
             w_planes = self._planes.get("proj", proj.weight)
             fuse_mask = row_code is not None and not inference_mlm
             x, x_planes, _ = ops.linear(planes, w_planes, C_width, bias=proj.bias, act=self._projection_act(),
@@ -630,12 +634,23 @@ class TabularSequenceFeatures(nn.Module):
             return x
 
         concat, _, self._id_err = gather(True, False)
+        if check:
+            self.check_ids()
         x = concat.view(B, L, C_width)
         if self.projection_module is not None:
             x = self.projection_module(x)
         if self.masking:
             x = self.masking.apply_mask_to_inputs(x, self.masking.mask_schema, training=training, testing=testing)
         return x
+
+    def check_ids(self) -> None:
+        """``nn.Embedding`` raises on ids outside the table (features/embedding.py:226-249 -> ``IndexError: index out of
+        range in self``).  The fused gather cannot raise from the device: it reads row 0 for such an id and raises a
+        flag that this method turns into the reference's error (one host sync; also run on every forward when
+        ``T4R_CHECK_IDS=1``)."""
+        err = getattr(self, "_id_err", None)
+        if err is not None and int(err.item()) != 0:
+            raise IndexError("index out of range in self")
 
     def _projection_linear(self) -> Optional[nn.Linear]:
         """The fused path handles the reference's default projection: a single
