@@ -229,7 +229,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sessions", type=int, default=64, help="sessions per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity), 1 = plain bf16")
+    ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity, default), 2 = fp16 + two e4m3 cross terms in the "
+                         "training head (2 tensor units per MAC, opt-in), 1 = plain bf16")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
@@ -245,8 +246,10 @@ def main():
                                  f"split planes; the full-softmax head streams the planes once per step)")
                    if cfg["V"] * cfg["De"] * 8 > 126e6 else
                    "working set fits the 126 MB L2 and is not flushed (parity-test case, not the bench line)",
-                   "product_arithmetic": "split-bf16 x3 tcgen05 products, fp32 accumulate" if args.nprod == 3
-                   else "bf16 tcgen05, fp32 accumulate"}
+                   "product_arithmetic": {3: "split-bf16 x3 tcgen05 products, fp32 accumulate",
+                                          2: "head: fp16 x fp16 + 2 e4m3 cross-term tcgen05 products (2 units per MAC), "
+                                             "rest: split-bf16 x3; fp32 accumulate",
+                                          1: "bf16 tcgen05, fp32 accumulate"}[args.nprod]}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -389,12 +392,14 @@ def main():
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
                 "traffic": head_traffic() if args.workload == "config2" else None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,
                 "algorithmic_flops_per_launch": head_flops, "label_rows_T": T,
-                "note": "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction"
-                if args.nprod == 3 else "plain bf16 product"}
+                "note": {3: "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction",
+                         2: "fp16 + 2 x e4m3 cross terms: 2 bf16-equivalent tensor passes per MAC: frac <= 1/2",
+                         1: "plain bf16 product"}[args.nprod]}
     line = {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)"
-            if args.nprod == 3 else "bf16", "data": "synthetic", "config": config_desc, "clocks": clocks,
+            "vs_baseline": None, "dtype": {3: "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)",
+                                           2: "f32 (head: fp16 + e4m3 cross terms on tcgen05; rest bf16 hi/lo split)",
+                                           1: "bf16"}[args.nprod], "data": "synthetic", "config": config_desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "loss": loss_host},
             "gpu_launches": int(n1 - n0), "roofline": roofline}

@@ -170,6 +170,18 @@ int t4r_pad_ragged(const void* values, const int64_t* offsets, int64_t rows, int
  * fuse it into); out_f32 (optional, [rows, K]) receives the masked fp32 rows. */
 int t4r_split_planes(const float* x, int64_t rows, int K, int ld, const uint8_t* row_code, const float* mask_vec,
                      float* out_f32, void* out_planes, void* stream);
+/* Operands of the 2-unit product (nprod = 2 of t4r_head_softmax_ce_fwd): fp32 [rows, K] (row stride ld) ->
+ * 16-bit words [2, rows, Kp]: plane 0 = fp16(x * s_row); plane 1 = per 64-wide K block and row 64 e4m3 bytes
+ * of the fp16 value (x 2^-6) followed by 64 e4m3 bytes of the fp16 rounding residual (x 2^6);
+ * s_row = the power of two that brings max|x_row| into [2^13, 2^14); out_inv_scale[row] = 1 / s_row.
+ * Same footprint as the split-bf16 planes.  Layout and rounding are defined in csrc/t4r_mixed_pack.cuh;
+ * tools/precision_study.py holds the error analysis (about 2.3x the error of the 3-product bf16 split at
+ * 2/3 of its tensor time).  t4r_debug_split_planes_mixed_host is the same code compiled for the host
+ * (HOST pointers, no CUDA call) -- test infrastructure. */
+int t4r_split_planes_mixed(const float* x, int64_t rows, int K, int ld, void* out_planes, float* out_inv_scale,
+                           void* stream);
+int t4r_debug_split_planes_mixed_host(const float* x, int64_t rows, int K, int ld, void* out_planes,
+                                      float* out_inv_scale);
 /* gather rows then split: out[i] = x[idx[i]] for i < *count_dev (all `cap` rows when
  * count_dev is NULL); rows >= count are zero.  out_f32 optional. */
 int t4r_gather_rows_split(const float* x, int K, int ld, const int32_t* idx, const int32_t* count_dev, int cap,
@@ -339,6 +351,11 @@ typedef struct {
   /* sharded evaluation: the label's logit over the WHOLE table (summed over shards by the caller)
    * that row_rank counts against; NULL = this call's own row_tgt (single shard) */
   const float* rank_tgt;
+  /* nprod = 2 (the 2-unit product: fp16 x fp16 plus two e4m3 cross terms, t4r_split_planes_mixed below):
+   * xt_planes / w_planes are then in the mixed format and these are the per-row inverse scales it returns
+   * ([T_cap] and [V]); both NULL otherwise.  Full and sampled softmax alike; not for t4r_head_logits. */
+  const float* xt_inv_scale;
+  const float* w_inv_scale;
 } t4r_head_args;
 size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De);
 int t4r_head_softmax_ce_fwd(const t4r_head_args* a /*host*/, void* stream);

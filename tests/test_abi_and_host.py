@@ -192,3 +192,57 @@ def test_known_answers_of_the_reference_feature_tests():
     emb = tr.SequenceEmbeddingFeatures.from_schema(schema.select_by_tag(tr.Tags.CATEGORICAL))
     assert all(t.weight.shape[1] == 64 for t in emb.embedding_tables.values())
     assert emb.item_id == "item_id/list" and emb.item_embedding_table.num_embeddings == 51997
+
+
+# --------------------------------------------------------------------------- #
+# 2-unit product operands (nprod = 2): layout + rounding of the packing code, on the host twin of the kernel
+# --------------------------------------------------------------------------- #
+def _mixed_cases():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(37, 200, generator=g)
+    x[3] = 0.0                                   # all-zero row -> scale 1
+    x[4] *= 1e-38                                # tiny row: scale clamps at 2^126
+    x[5] *= 1e20                                 # huge row: negative shift
+    x[6, :] = torch.exp2(torch.randint(-20, 4, (200,), generator=g).float())  # wide in-row dynamic range
+    x[7, 10] = 16383.999                         # rounds up to 2^14 in fp16
+    return x
+
+
+def test_mixed_planes_host_twin_matches_reference_bit_exactly():
+    import _mixed_ref as R
+    from transformers4rec_b200 import ops
+    x = _mixed_cases()
+    planes, inv = ops.split_planes_mixed_host(x)
+    assert planes.shape == (2, 37, 256)
+    ref = R.pack(x)
+    h16, hi8, lo8 = R.unpack_planes(planes)
+    assert torch.equal(inv, ref["inv_scale"])
+    assert torch.equal(h16.view(torch.int16), ref["h16"].view(torch.int16))
+    assert torch.equal(hi8.view(torch.uint8), ref["hi8"].view(torch.uint8))
+    assert torch.equal(lo8.view(torch.uint8), ref["lo8"].view(torch.uint8))
+    # zero padding of K up to Kp and the scale of special rows
+    assert not h16[:, 200:].any() and not hi8.view(torch.uint8)[:, 200:].any() and not lo8.view(torch.uint8)[:, 200:].any()
+    assert inv[3].item() == 1.0 and inv[4].item() == 2.0 ** -126
+    m = (x.abs().amax(1) / inv)[[0, 1, 2, 5, 6, 7]]
+    assert ((m >= 2 ** 13) & (m < 2 ** 14)).all()
+    assert h16.float().abs().max().item() <= 2.0 ** 14 and hi8.float().abs().max().item() <= 256.0
+    assert lo8.float().abs().max().item() <= 256.0
+
+
+def test_mixed_product_is_fp32_grade():
+    """hi*hi (fp16) + lo8*hi8 + hi8*lo8 (e4m3), scaled back, against fp64: the error budget of nprod = 2."""
+    import _mixed_ref as R
+    g = torch.Generator().manual_seed(12)
+    T, V, K = 96, 4000, 256
+    x = torch.randn(T, K, generator=g)
+    x = (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True)       # LayerNorm-ed hidden rows
+    w = torch.randn(V, K, generator=g) * 0.05                          # features/embedding.py:461-462
+    ref = x.double() @ w.double().t()
+    got = R.product(R.pack(x), R.pack(w))
+    err = (got - ref).abs().max().item()
+    bf = lambda a: a.to(torch.bfloat16).float()
+    xh, wh = bf(x), bf(w)
+    x3 = xh.double() @ wh.double().t() + xh.double() @ bf(w - wh).double().t() + bf(x - xh).double() @ wh.double().t()
+    err3 = (x3 - ref).abs().max().item()
+    assert err < 1e-4, err                    # two orders inside the 1e-3 parity bar at |logit| ~ 1
+    assert err < 4 * err3, (err, err3)        # within a small factor of the shipped 3-product bf16 split

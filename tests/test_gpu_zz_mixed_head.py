@@ -1,0 +1,101 @@
+"""GPU tests of the 2-unit product head (``nprod=2``: fp16 x fp16 + two e4m3 cross terms,
+csrc/t4r_mixed_pack.cuh).
+
+STATUS: this path was written after the round's GPU budget was spent -- the operand packing is pinned on
+the CPU (tests/test_abi_and_host.py, host twin of the kernel), the tcgen05 side compiles for sm_100a but has
+NOT run on hardware yet.  The tests are therefore opt-in (``T4R_TEST_EXPERIMENTAL=1``) so that an unproven
+kernel cannot take the proven suite down with it (a trap poisons the CUDA context of the whole pytest
+process); they sort last for the same reason.  First item of the next round: run them, then drop the gate.
+"""
+import math
+import os
+
+import pytest
+import torch
+
+import t4r_oracle as O
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("T4R_TEST_EXPERIMENTAL") != "1",
+                                 reason="nprod=2 head not yet validated on hardware (set T4R_TEST_EXPERIMENTAL=1)")]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from transformers4rec_b200 import ops as _ops
+    return _ops
+
+
+def test_device_packing_matches_host_twin_bit_exactly(ops):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(300, 200, generator=g)
+    x[3] = 0.0
+    x[5] *= 1e20
+    x[6, :] = torch.exp2(torch.randint(-20, 4, (200,), generator=g).float())
+    ph, ih = ops.split_planes_mixed_host(x)
+    pd, idv = ops.split_planes_mixed(x.cuda())
+    assert torch.equal(idv.cpu(), ih)
+    assert torch.equal(pd.cpu(), ph)
+
+
+@pytest.mark.parametrize("two_cta", ["0", "1"])
+@pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5)])
+def test_head_full_softmax_nprod2(ops, monkeypatch, T, V, De, tau, two_cta):
+    """Same cases and bars as test_gpu_parity.py::test_head_full_softmax, both GEMM kernels."""
+    monkeypatch.setenv("T4R_GEMM_2CTA", two_cta)
+    torch.manual_seed(12)
+    xt = torch.randn(T, De)
+    W = torch.randn(V, De) * 0.1
+    y = torch.randint(1, V, (T,))
+    ref_loss, ref_logits = O.full_softmax_head(xt, y, W, tau)
+    cap = T + 37
+    xt_pad = torch.zeros(cap, De); xt_pad[:T] = xt
+    y_pad = torch.zeros(cap, dtype=torch.long); y_pad[:T] = y
+    count = torch.tensor([T], dtype=torch.int32, device="cuda")
+    xp, xi = ops.split_planes_mixed(xt_pad.cuda())
+    wp, wi = ops.split_planes_mixed(W.cuda())
+    res = ops.head_softmax_ce(xp, xt_pad.cuda(), y_pad.cuda(), wp, W.cuda(), t_dev=count, inv_temperature=1.0 / tau,
+                              want_rank=True, nprod=2, xt_inv_scale=xi, w_inv_scale=wi)
+    assert abs(res["loss"].item() - ref_loss.item()) < 1e-4
+    ref_lse = torch.logsumexp(ref_logits, dim=1)
+    assert (res["row_lse"][:T].cpu() - ref_lse).abs().max().item() < 2e-4
+    ks = [1, 5, 10, 20]
+    ref_rec = O.recall_at_mean(ks, ref_logits, y)
+    got_rec = ops.recall_from_ranks(res["row_rank"], ks, count).cpu()
+    assert (got_rec - ref_rec).abs().max().item() < 1e-6
+
+
+def test_nprod2_requires_its_scales(ops):
+    from transformers4rec_b200 import T4RError
+    xt = torch.randn(64, 64, device="cuda")
+    W = torch.randn(500, 64, device="cuda")
+    xp, xi = ops.split_planes_mixed(xt)
+    wp, wi = ops.split_planes_mixed(W)
+    y = torch.randint(1, 500, (64,), device="cuda")
+    with pytest.raises(T4RError):
+        ops.head_softmax_ce(xp, xt, y, wp, W, nprod=2)
+
+
+def test_model_training_loss_with_mixed_head():
+    """Whole model, config-1 shape: task.nprod = 2 must reproduce the oracle's training loss within the parity bar
+    and agree with the default arithmetic to 1e-4."""
+    from _util import make_pair, mlm_draws, synth_batch
+    cards = {"item_id/list": 10001, "category/list": 337}
+    dims = {"item_id/list": 64, "category/list": 64}
+    cont = tuple(f"cont{i}/list" for i in range(5))
+    B, L = 256, 20
+    oracle, model = make_pair(cards, dims, "item_id/list", cont, 64, 4, 2, L, weight_scale=0.08)
+    batch = synth_batch(B, L, cards, cont, seed=0)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    dev = {k: v.cuda() for k, v in batch.items()}
+    task = model.heads[0].prediction_task_dict["next-item"]
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws)["loss"].item()
+        l3 = model(dev, training=True)["loss"].item()
+        task.nprod = 2
+        out = model(dev, training=True)
+        l2 = out["loss"].item()
+        preds = out["predictions"]  # lazily materialised through the 3-product planes
+    assert math.isfinite(l2) and abs(l2 - ref) < 1e-3 and abs(l2 - l3) < 1e-4
+    assert preds.shape[1] == 10001

@@ -65,6 +65,8 @@ def main():
     b1, b2 = torch.randn(4 * d, device=dev), torch.randn(d, device=dev)
     g, bt = torch.ones(d, device=dev), torch.zeros(d, device=dev)
     ffp = ops.split_planes(torch.randn(M, 4 * d, device=dev))
+    if "head2" in which and "head" not in which:
+        which.append("head")
     on = lambda k: "all" in which or k in which
     if on("qkv"):
         timeit("qkv gemm N=768 K=256 (f32 out)", lambda: ops.linear(xp, w_qkv, d, want_planes=False),
@@ -139,6 +141,16 @@ def main():
         for nprod in (3, 1):  # 1 = plain bf16: same operand traffic, a third of the MMAs -> separates tensor- from L2-bound
             timeit(f"head 5120 x 1M x 256 nprod={nprod}", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=nprod),
                    iters=5, flops=2 * T * V * d)
+        if "head2" in which:  # 2-unit product (fp16 + two e4m3 cross terms): same operand bytes, 2/3 of the tensor passes
+            ref = ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=3)
+            del wp
+            wm, wi = ops.split_planes_mixed(W)
+            xm, xi = ops.split_planes_mixed(xt)
+            got = ops.head_softmax_ce(xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi, w_inv_scale=wi)
+            print("    nprod=2 vs nprod=3: loss %.7f vs %.7f, max |row_lse diff| %.3e" % (
+                got["loss"].item(), ref["loss"].item(), (got["row_lse"] - ref["row_lse"]).abs().max().item()), flush=True)
+            timeit("head 5120 x 1M x 256 nprod=2", lambda: ops.head_softmax_ce(xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi,
+                                                                                w_inv_scale=wi), iters=5, flops=2 * T * V * d)
 
 
 if __name__ == "__main__":

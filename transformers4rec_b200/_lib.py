@@ -120,6 +120,8 @@ class HeadArgs(C.Structure):
         ("ev_gemm_stop", c_void_p),
         ("label_smoothing", c_float),
         ("rank_tgt", c_void_p),
+        ("xt_inv_scale", c_void_p),
+        ("w_inv_scale", c_void_p),
     ]
 
 
@@ -135,6 +137,8 @@ SIGNATURES = {
     "t4r_mask_clm": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P]),
     "t4r_compact_targets": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
     "t4r_split_planes": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "t4r_split_planes_mixed": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
+    "t4r_debug_split_planes_mixed_host": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "t4r_gather_rows_split": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "t4r_gather_rows_split_i64": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),
     "t4r_linear_fwd": (c_int, [C.POINTER(LinearArgs), _P]),

@@ -479,6 +479,11 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   ep.row_tgt = a->rank_tgt ? a->rank_tgt : a->row_tgt;
   ep.row_rank = a->row_rank;
   ep.col_offset = a->v_offset;
+  if (pb.nprod == 2) {
+    T4R_REQUIRE(a->xt_inv_scale && a->w_inv_scale, "head: nprod = 2 needs xt_inv_scale and w_inv_scale");
+    ep.row_scale = a->xt_inv_scale;
+    ep.col_scale = a->w_inv_scale;
+  }
   if (a->ev_gemm_start) T4R_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_gemm_start), s));
   T4R_TRY(launch_gemm(pb, ep, s));
   if (a->ev_gemm_stop) T4R_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev_gemm_stop), s));

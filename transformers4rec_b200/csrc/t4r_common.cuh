@@ -201,6 +201,36 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// kind::f16 with fp16 operands (format 0) and kind::f8f6f4 with e4m3 operands (format 0): the bit patterns
+// coincide -- the KIND in the instruction selects the interpretation (cute/arch/mma_sm100_desc.hpp:
+// F32F16Format F16 = 0, MXF8F6F4Format E4M3 = 0).  Used by the 2-unit product (nprod = 2, t4r_mixed_pack.cuh).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// D[tmem] (+)= A * B with 8-bit operands: K = 32 per instruction (32 bytes of each K-major operand row, the same
+// shared-memory footprint per instruction as a K = 16 bf16 MMA), twice the MACs of a kind::f16 MMA per issue slot.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // split-bf16 helpers: x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
 // (three bf16 products hi*hi + hi*lo + lo*hi carry ~2^-16 relative error)

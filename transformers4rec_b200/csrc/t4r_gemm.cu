@@ -527,6 +527,7 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   const bool want_rank = (ep.row_rank != nullptr);
   if (row_ok && ep.row_label) label = ep.row_label[row];
   if (row_ok && want_rank) tgt = ep.row_tgt[row];
+  const float row_scale = (row_ok && ep.row_scale) ? ep.row_scale[row] : 1.f;
   const bool full_tile = (n0 + COLS <= p.N);
 #pragma unroll 1
   for (int c = 0; c < COLS / 32; ++c) {
@@ -536,6 +537,21 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
     const int64_t ncol0 = n0 + c * 32;
     if (ncol0 >= p.N) continue;
     if (ep.debug & 32) { m_run = fmaxf(m_run, v[c]); continue; }  // timing experiment: TMEM reads only
+    if (ep.col_scale) {  // 2-unit product: undo the power-of-two row scales of both operands (exact)
+      if (full_tile) {
+        const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + ncol0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cs = __ldg(c4 + j);
+          v[4 * j + 0] *= row_scale * cs.x; v[4 * j + 1] *= row_scale * cs.y;
+          v[4 * j + 2] *= row_scale * cs.z; v[4 * j + 3] *= row_scale * cs.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ncol0 + j < p.N) v[j] *= row_scale * __ldg(ep.col_scale + ncol0 + j);
+      }
+    }
     if (ep.col_bias) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -660,7 +676,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = (p.nprod == 3) ? Cfg::STAGE_BYTES : (A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
+      const uint32_t bytes = (p.nprod != 1) ? Cfg::STAGE_BYTES : (A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = static_cast<int>(tile % tiles_m) * BM;
         const int n0 = static_cast<int>(tile / tiles_m) * BN;
@@ -671,7 +687,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           constexpr int KE = RB / 2;  // bf16 elements of K per stage
           tma_load_2d(st, &tmAh, &full_bar[stage], kb * KE, m0);
           tma_load_2d(st + 2 * A_PLANE_BYTES, &tmBh, &full_bar[stage], kb * KE, n0);
-          if (p.nprod == 3) {
+          if (p.nprod != 1) {
             tma_load_2d(st + A_PLANE_BYTES, &tmAl, &full_bar[stage], kb * KE, m0);
             tma_load_2d(st + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tmBl, &full_bar[stage], kb * KE, n0);
           }
@@ -699,6 +715,21 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           const uint32_t a_lo = a_hi + A_PLANE_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
           const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
+          if (RB == 128 && p.nprod == 2) {
+            // 2-unit product (t4r_mixed_pack.cuh): plane 0 = fp16, plane 1 = [64 x hi8 | 64 x lo8] e4m3 per row.
+            // Four K = 16 fp16 MMAs, then lo8(A) x hi8(B) and hi8(A) x lo8(B) as two K = 32 e4m3 MMAs each,
+            // all into the same fp32 accumulator.
+            constexpr uint32_t idesc_h = umma_idesc_f16(BM, BN);
+            constexpr uint32_t idesc_8 = umma_idesc_e4m3(BM, BN);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_bf16(d_tmem, umma_desc<RB>(a_hi + k4 * 32), umma_desc<RB>(b_hi + k4 * 32), idesc_h, (kb | k4) != 0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              umma_f8(d_tmem, umma_desc<RB>(a_lo + 64 + j * 32), umma_desc<RB>(b_lo + j * 32), idesc_8, 1u);
+              umma_f8(d_tmem, umma_desc<RB>(a_lo + j * 32), umma_desc<RB>(b_lo + 64 + j * 32), idesc_8, 1u);
+            }
+          } else {
 #pragma unroll
           for (int k4 = 0; k4 < Cfg::KSTEPS; ++k4) {
             const uint64_t da_hi = umma_desc<RB>(a_hi + k4 * 32);
@@ -712,6 +743,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             } else {
               umma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | k4) != 0);
             }
+          }
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -849,7 +881,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = (p.nprod == 3) ? Cfg::STAGE_BYTES : (A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
+      const uint32_t bytes = (p.nprod != 1) ? Cfg::STAGE_BYTES : (A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
       for (int64_t tile = pair; tile < num_tiles; tile += npairs) {
         const int m0 = static_cast<int>(tile % tiles_m) * (2 * BM) + rank * BM;
         const int n0 = static_cast<int>(tile / tiles_m) * BN + rank * (BN / 2);
@@ -859,7 +891,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
           tma_load_2d_pair(st, &tmAh, &full_bar[stage], kb * 64, m0);
           tma_load_2d_pair(st + 2 * A_PLANE_BYTES, &tmBh, &full_bar[stage], kb * 64, n0);
-          if (p.nprod == 3) {
+          if (p.nprod != 1) {
             tma_load_2d_pair(st + A_PLANE_BYTES, &tmAl, &full_bar[stage], kb * 64, m0);
             tma_load_2d_pair(st + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tmBl, &full_bar[stage], kb * 64, n0);
           }
@@ -887,6 +919,19 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           const uint32_t a_lo = a_hi + A_PLANE_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_PLANE_BYTES;
           const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
+          if (p.nprod == 2) {  // 2-unit product: see the single-CTA kernel
+            constexpr uint32_t idesc_h = umma_idesc_f16(2 * BM, BN);
+            constexpr uint32_t idesc_8 = umma_idesc_e4m3(2 * BM, BN);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h,
+                             (kb | k4) != 0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, 1u);
+              umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, 1u);
+            }
+          } else {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32);
@@ -900,6 +945,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
             } else {
               umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, (kb | k4) != 0);
             }
+          }
           }
           umma_commit_pair(&empty_bar[stage]);  // the stage is free in BOTH CTAs once these MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -1033,7 +1079,9 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   T4R_REQUIRE(pb.M > 0 && pb.N > 0 && pb.Kp > 0 && pb.Kp % 64 == 0, "gemm: bad shape M=%lld N=%lld Kp=%d",
               (long long)pb.M, (long long)pb.N, pb.Kp);
   T4R_REQUIRE(pb.M < (1ll << 31), "gemm: M too large");
-  T4R_REQUIRE(pb.nprod == 1 || pb.nprod == 3, "gemm: nprod must be 1 or 3");
+  T4R_REQUIRE(pb.nprod == 1 || pb.nprod == 3 || pb.nprod == 2, "gemm: nprod must be 1, 2 or 3");
+  T4R_REQUIRE(pb.nprod != 2 || (ep.head && ep.row_scale && ep.col_scale),
+              "gemm: nprod = 2 (fp16 + e4m3 cross terms) is a head-only mode and needs both row-scale vectors");
   const bool ln = ep.ln_gamma != nullptr;
   int bn = pb.bn;
   if (ln) {
@@ -1057,6 +1105,7 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   // 4.98 ms vs 5.15 ms): the kernel runs at the power-capped tensor rate, not on TMA latency.
   static int rb = 0;
   if (rb == 0) { const char* e = getenv("T4R_GEMM_RB"); rb = (e && atoi(e) == 64) ? 64 : 128; }
+  T4R_REQUIRE(pb.nprod != 2 || rb == 128, "gemm: nprod = 2 needs 128-byte operand rows (unset T4R_GEMM_RB)");
   CUtensorMap ah, al, bh, bl;
   T4R_TRY(make_tmap(&ah, pb.a_planes, pb.M, pb.Kp, BM, rb));
   T4R_TRY(make_tmap(&al, pb.a_planes + pb.a_rows * pb.Kp, pb.M, pb.Kp, BM, rb));

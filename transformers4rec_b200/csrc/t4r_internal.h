@@ -81,6 +81,8 @@ struct GemmEpilogue {
   const float* row_tgt = nullptr;      // [M] label logit (already scaled), for ranks
   int* row_rank = nullptr;             // [M] atomically accumulated
   int64_t col_offset = 0;              // global class id of column 0 (shards)
+  const float* row_scale = nullptr;    // [M] nprod = 2: 1 / (power-of-two scale of A's row)
+  const float* col_scale = nullptr;    // [N] nprod = 2: 1 / (power-of-two scale of B's row)
   int debug = 0;                       // T4R_GEMM_DEBUG: 1 = epilogue skips all global loads/stores (timing experiments)
 };
 

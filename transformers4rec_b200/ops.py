@@ -81,6 +81,33 @@ def split_planes(x: torch.Tensor, row_code: Optional[torch.Tensor] = None, mask_
     return (planes, of) if want_f32 else planes
 
 
+def split_planes_mixed(x: torch.Tensor):
+    """fp32 [rows, K] -> (int16 words [2, rows, Kp], fp32 [rows] inverse row scales): the operands of the 2-unit
+    product (``nprod=2``: fp16 x fp16 + two e4m3 cross terms, csrc/t4r_mixed_pack.cuh)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    rows, K = x.shape
+    Kp = round_up64(K)
+    planes = torch.empty((2, rows, Kp), dtype=torch.int16, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_split_planes_mixed(ptr(x), rows, K, K, ptr(planes), ptr(inv), _stream()),
+          "t4r_split_planes_mixed")
+    return planes, inv
+
+
+def split_planes_mixed_host(x: torch.Tensor):
+    """The same packing code compiled for the host (CPU tensors; test infrastructure, no CUDA call)."""
+    assert not x.is_cuda
+    x = _f32c(x)
+    rows, K = x.shape
+    Kp = round_up64(K)
+    planes = torch.empty((2, rows, Kp), dtype=torch.int16)
+    inv = torch.empty((rows,), dtype=torch.float32)
+    check(_lib.load().t4r_debug_split_planes_mixed_host(ptr(x), rows, K, K, ptr(planes), ptr(inv)),
+          "t4r_debug_split_planes_mixed_host")
+    return planes, inv
+
+
 class PlaneCache:
     """Split-bf16 copies of weights, refreshed when the parameter changes
     (``data_ptr`` / ``_version``).  ``transform`` maps the parameter to its [N, K]
@@ -101,6 +128,21 @@ class PlaneCache:
             planes = split_planes(w)
         self._cache[key] = (sig, planes)
         return planes
+
+    def get_mixed(self, key: str, param: torch.Tensor):
+        """(mixed planes, inverse row scales) of a parameter for the 2-unit product, cached like ``get``."""
+        sig = (param.data_ptr(), param._version, tuple(param.shape), str(param.device), "mixed")
+        ent = self._cache.get(key + "#mixed")
+        if ent is not None and ent[0] == sig:
+            return ent[1]
+        with torch.no_grad():
+            val = split_planes_mixed(param.detach())
+        self._cache[key + "#mixed"] = (sig, val)
+        return val
+
+    def drop(self, key: str):
+        self._cache.pop(key, None)
+        self._cache.pop(key + "#mixed", None)
 
     def clear(self):
         self._cache.clear()
@@ -401,7 +443,7 @@ def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: in
 # --------------------------------------------------------------------------- #
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
-                    nprod=3, events=None, label_smoothing=0.0, rank_tgt=None):
+                    nprod=3, events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None):
     """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank)."""
     _need_cuda(xt_planes, w_planes)
     lib = _lib.load()
@@ -428,6 +470,10 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     a.nprod = nprod
     a.label_smoothing = float(label_smoothing)
     a.rank_tgt = ptr(rank_tgt)
+    if nprod == 2:
+        if xt_inv_scale is None or w_inv_scale is None:
+            raise _lib.T4RError("head_softmax_ce: nprod=2 needs the mixed planes' inverse row scales")
+        a.xt_inv_scale, a.w_inv_scale = ptr(xt_inv_scale), ptr(w_inv_scale)
     ev = events if events is not None else HEAD_EVENTS
     if ev is not None:
         a.ev_gemm_start, a.ev_gemm_stop = ev[0].cuda_event, ev[1].cuda_event

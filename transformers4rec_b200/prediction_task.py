@@ -181,6 +181,10 @@ class NextItemPredictionTask(PredictionTask):
         self.masking = None
         self.output_layer = None
         self.sampler = None
+        # tensor-core arithmetic of the GEMMs on this task: 3 = split-bf16, three products (fp32-grade, default);
+        # 1 = plain bf16; 2 = the 2-unit product of the TRAINING full-softmax head only (fp16 x fp16 + two e4m3
+        # cross terms, ~2.3x the error of 3 at 2/3 of its tensor time, csrc/t4r_mixed_pack.cuh) -- every other
+        # GEMM of the task (task_block, sampled / sharded heads, evaluation ranks, predictions) then runs with 3.
         self.nprod = 3
         self._planes = ops.PlaneCache()
         self._last = None
@@ -234,6 +238,9 @@ class NextItemPredictionTask(PredictionTask):
         """Test hook: the multinomial output ids the sampler would have drawn."""
         self._neg_draws = raw_draws
 
+    def _dense_nprod(self) -> int:
+        return 3 if self.nprod == 2 else self.nprod
+
     def _inv_tau(self) -> float:
         return 1.0 / float(self.softmax_temperature) if self.softmax_temperature else 1.0
 
@@ -246,7 +253,7 @@ class NextItemPredictionTask(PredictionTask):
             lin = blk[0]
             K = lin.in_features
             xf, planes, _ = ops.linear(planes, blk._planes.get("w", lin.weight), K, bias=lin.bias, act=blk.act_code(),
-                                       m_dev=m_dev, nprod=self.nprod)
+                                       m_dev=m_dev, nprod=self._dense_nprod())
         return xf, planes
 
     # ------------------------------------------------------------------ forward
@@ -257,7 +264,9 @@ class NextItemPredictionTask(PredictionTask):
         B, L, d = x.shape
         W = self.output_weight()
         Wd = W.detach()
-        w_planes = self._planes.get("W", W)
+        mixed_head = (self.nprod == 2 and training and not self._sharded()
+                      and not (self.sampled_softmax and training))
+        w_planes = None if mixed_head else self._planes.get("W", W)  # the mixed head keeps only its own 1x copy
         inv_tau = self._inv_tau()
 
         if training or testing:
@@ -280,12 +289,20 @@ class NextItemPredictionTask(PredictionTask):
                 res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, neg_planes, None, t_dev=count,
                                           inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg,
                                           hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos,
-                                          nprod=self.nprod)
+                                          nprod=self._dense_nprod())
                 self._last = dict(xt_planes=xt_planes, w_planes=neg_planes, count=count, neg=neg, pos=pos,
                                   col_bias=col_bias, labels=tgt_labels, De=Wd.shape[1], sampled=True)
+            elif mixed_head:
+                w_mixed, w_inv = self._planes.get_mixed("W", W)
+                xt_mixed, xt_inv = ops.split_planes_mixed(xt_f32)
+                res = ops.head_softmax_ce(xt_mixed, xt_f32, tgt_labels, w_mixed, Wd, t_dev=count,
+                                          inv_temperature=inv_tau, want_rank=want_rank, nprod=2,
+                                          label_smoothing=self.label_smoothing, xt_inv_scale=xt_inv, w_inv_scale=w_inv)
+                self._last = dict(xt_planes=xt_planes, w_planes=None, count=count, labels=tgt_labels,
+                                  De=Wd.shape[1], sampled=False)
             else:
                 res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, w_planes, Wd, t_dev=count,
-                                          inv_temperature=inv_tau, want_rank=want_rank, nprod=self.nprod,
+                                          inv_temperature=inv_tau, want_rank=want_rank, nprod=self._dense_nprod(),
                                           label_smoothing=self.label_smoothing)
                 self._last = dict(xt_planes=xt_planes, w_planes=w_planes, count=count, labels=tgt_labels,
                                   De=Wd.shape[1], sampled=False)
@@ -307,7 +324,7 @@ class NextItemPredictionTask(PredictionTask):
         xs_planes, xs_f32 = ops.gather_rows_split(x.reshape(-1, d), flat_idx, None, B, want_f32=True)
         if self.task_block is not None:
             xs_f32, xs_planes = self._task_block_rows(xs_planes, None)
-        scores = ops.head_logits(xs_planes, w_planes, Wd.shape[1], inv_temperature=inv_tau, nprod=self.nprod)
+        scores = ops.head_logits(xs_planes, w_planes, Wd.shape[1], inv_temperature=inv_tau, nprod=self._dense_nprod())
         if top_k is None:
             return scores
         return ops.topk(scores, top_k)
@@ -348,7 +365,7 @@ class NextItemPredictionTask(PredictionTask):
             xp = xt_planes[:, :T].contiguous()
             res = ops.head_softmax_ce(xp, xt, y, neg_planes, None, inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg,
                                       hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos,
-                                      nprod=self.nprod)
+                                      nprod=self._dense_nprod())
             tot = torch.stack([res["row_loss"][:T].sum(), torch.tensor(float(T), device=xt.device)])
             dist.all_reduce(tot, group=table.group)
             loss = (tot[0] / tot[1].clamp(min=1.0)).reshape(())
@@ -375,8 +392,9 @@ class NextItemPredictionTask(PredictionTask):
     def _lazy_predictions(self):
         st = self._last
         T = int(st["count"].item())
-        logits = ops.head_logits(st["xt_planes"], st["w_planes"], st["De"], t_dev=st["count"],
-                                 inv_temperature=self._inv_tau(), nprod=self.nprod)[:T]
+        w_planes = st["w_planes"] if st["w_planes"] is not None else self._planes.get("W", self.output_weight())
+        logits = ops.head_logits(st["xt_planes"], w_planes, st["De"], t_dev=st["count"],
+                                 inv_temperature=self._inv_tau(), nprod=self._dense_nprod())[:T]
         if not st["sampled"]:
             return logits
         # sampled softmax layout of :693: [positive | negatives], logQ-corrected, hits removed
