@@ -63,6 +63,17 @@ def _combine(parts):
     return row, row.mean().reshape(1)
 
 
+def _stable_topk(scores, k):
+    """(value desc, index asc) -- the order of t4r_topk; torch.topk leaves ties unspecified."""
+    order = torch.sort(-scores, dim=1, stable=True).indices[:, :k]
+    return scores.gather(1, order), order
+
+
+def _sessions(rank):
+    g = torch.Generator().manual_seed(30 + rank)
+    return torch.randn((5, De), generator=g)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -97,6 +108,20 @@ def _worker(rank, world, port, q):
         some = y[: 3 + 2 * rank]
         got, _ = emb.lookup(some, ragged=True)
         ok_lookup = ok_lookup and torch.equal(got, table[some]) and emb.weight.shape[0] == hi - lo
+        # serving: top-k over the sharded table == top-k over the replicated one, ties (two identical rows living in
+        # different shards) resolved towards the lower item id
+        table_t = table.clone()
+        table_t[700] = table_t[3]
+        local_t = table_t[lo:hi].contiguous()
+        xs = _sessions(rank)
+        xs[0] = 10.0 * table_t[3]  # rows 3 (shard 0) and 700 (shard 1) tie for the best score of session 0
+        for k in (1, 7, 20):
+            sc, ids = D.sharded_topk(xs, local_t, V, k, inv_tau=0.5,
+                                     local_topk=lambda xa, t, wp, tau, kk: _stable_topk((xa @ t.t()) * tau, kk),
+                                     merge=_stable_topk)
+            ref_sc, ref_ids = _stable_topk((xs @ table_t.t()) * 0.5, k)
+            ok_head = ok_head and torch.equal(ids, ref_ids) and torch.allclose(sc, ref_sc, atol=1e-6)
+            ok_head = ok_head and ids[0, 0].item() == 3 and (k == 1 or ids[0, 1].item() == 700)
         q.put((rank, ok_lookup, ok_head))
     finally:
         dist.destroy_process_group()

@@ -154,3 +154,54 @@ def test_model_over_sharded_item_table_nccl(sampled):
         assert r["train"] < 1e-3, (rank, r)
         if not sampled:
             assert r["eval"] < 1e-3 and r["recall"] < 1e-6, (rank, r)
+
+
+# --------------------------------------------------------------------------- #
+# serving over the sharded table: Model.top_k through per-shard top-k + one candidate exchange
+# --------------------------------------------------------------------------- #
+def _topk_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import torch.distributed as dist
+
+    import t4r_oracle as O
+    from _util import make_pair, synth_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cards, dims = {"item_id/list": 12001}, {"item_id/list": 64}
+        B, L, K = 24, 20, 10
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 1, L, weight_scale=0.08, device=f"cuda:{rank}")
+        model.heads[0].body[0].categorical_module.shard_item_table()
+        batch = synth_batch(B, L - 1, cards, seed=300 + rank)  # room for the extra [MASK] position
+        batch = {k: torch.nn.functional.pad(v, (0, 1)) for k, v in batch.items()}
+        with torch.no_grad():
+            x, _, _ = oracle.input_block(batch, False, False)
+            h = O.hf_encoder_forward(oracle.transformer, x)
+            last = (batch["item_id/list"] != 0).sum(1)
+            ref_scores = h[torch.arange(B), last] @ oracle.item_table().t()
+            model.top_k = K
+            s, i = model({k: v.cuda() for k, v in batch.items()}, training=False, testing=False)
+        rs, ri = torch.topk(ref_scores, K)
+        q.put((rank, (s.cpu() - rs).abs().max().item(), (i.cpu() == ri).float().mean().item(),
+               bool((s[:, :-1] >= s[:, 1:]).all())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_topk_over_sharded_item_table_nccl():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_topk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, agree, sorted_desc in res:
+        assert err < 1e-3 and agree > 0.98 and sorted_desc, (rank, err, agree, sorted_desc)

@@ -170,6 +170,73 @@ def sharded_softmax_ce(xt: torch.Tensor, labels: torch.Tensor, local_table: torc
     return row_loss[mine], loss, int(sum(counts_l))
 
 
+def _default_local_topk(x_all: torch.Tensor, local_table: torch.Tensor, w_planes, inv_tau: float, k: int,
+                        max_score_bytes: int = 4 << 30):
+    """(scores, local row ids) of the k best rows of THIS shard for every session row; the [rows, V_local]
+    scores are materialised a block of session rows at a time (<= max_score_bytes) by the tensor-core GEMM."""
+    from . import ops
+    if w_planes is None:
+        w_planes = ops.split_planes(local_table)
+    n, De = x_all.shape
+    v_loc = local_table.shape[0]
+    step = max(1, min(n, max_score_bytes // (4 * max(v_loc, 1))))
+    sc, ids = [], []
+    for r0 in range(0, n, step):
+        xp = ops.split_planes(x_all[r0:r0 + step])
+        scores = ops.head_logits(xp, w_planes, De, inv_temperature=inv_tau)
+        a, b = ops.topk(scores, k)
+        sc.append(a)
+        ids.append(b)
+    return torch.cat(sc), torch.cat(ids)
+
+
+def _default_merge_topk(cand_scores: torch.Tensor, k: int):
+    from . import ops
+    return ops.topk(cand_scores, k)
+
+
+def sharded_topk(xs: torch.Tensor, local_table: torch.Tensor, V: int, k: int, group=None, w_planes=None,
+                 inv_tau: float = 1.0, local_topk: Optional[Callable] = None, merge: Optional[Callable] = None):
+    """Top-k items of every one of this rank's sessions over a row-sharded output table (serving over
+    BASELINE configs 4-5; the reference's ``top_k`` path, model/prediction_task.py:452-470, on a replicated table).
+
+    ``xs`` [B, De]: hidden row at the next-item position of each of THIS rank's sessions (same B on every rank).
+    One all-gather of the rows (B*De*4 bytes per rank), every rank scores all sessions against its V/world
+    rows and keeps its k best per session, ONE all-to-all returns the (score, global id) candidates to the
+    sessions' owner, which merges world*k candidates.  Order: score descending, ties by lower item id -- the
+    order of ``t4r_topk`` on a replicated table (candidates arrive shard-major, i.e. id-ascending among ties).
+    Returns (scores [B, k] fp32, ids [B, k] int64)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    local_topk = local_topk or _default_local_topk
+    merge = merge or _default_merge_topk
+    B, De = xs.shape
+    lo, hi = shard_bounds(V, rank, world)
+    if not 1 <= k <= V:
+        raise ValueError(f"top_k={k} must be in [1, {V}]")
+    x_all = _all_gather(xs.float().contiguous(), world, group).reshape(world * B, De)
+    k_loc = min(k, hi - lo)
+    neg_inf = float("-inf")
+    if k_loc > 0:
+        sc, ids = local_topk(x_all, local_table, w_planes, inv_tau, k_loc)
+        ids = ids.long() + lo
+    else:  # more ranks than rows: this shard is empty
+        sc = torch.empty((world * B, 0), dtype=torch.float32, device=xs.device)
+        ids = torch.empty((world * B, 0), dtype=torch.int64, device=xs.device)
+    if k_loc < k:  # pad so that every shard sends k candidates (-inf never wins against a real score)
+        sc = torch.cat([sc, sc.new_full((world * B, k - k_loc), neg_inf)], dim=1)
+        ids = torch.cat([ids, ids.new_full((world * B, k - k_loc), -1)], dim=1)
+    # one exchange: score bits and ids travel in the same int64 buffer
+    send = torch.stack([sc.contiguous().view(torch.int32).long(), ids], dim=-1).contiguous()  # [world*B, k, 2]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                                         # recv[s*B + b] = shard s, my session b
+    recv = recv.view(world, B, k, 2)
+    cand_sc = recv[..., 0].to(torch.int32).view(torch.float32).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    cand_id = recv[..., 1].permute(1, 0, 2).reshape(B, world * k).contiguous()
+    top_sc, pos = merge(cand_sc, k)
+    return top_sc, cand_id.gather(1, pos.long())
+
+
 class ShardedEmbedding(torch.nn.Module):
     """Rows [lo, hi) of an item table of ``num_embeddings`` rows, block-partitioned over the process
     group: the drop-in for the item feature's ``nn.Embedding`` (and, under weight tying, for the output

@@ -313,9 +313,6 @@ class NextItemPredictionTask(PredictionTask):
             return out
 
         # inference (:452-470): hidden state at the next-item position, full scores
-        if self._sharded():
-            raise NotImplementedError("inference over a row-sharded item table is not built yet: gather the shards "
-                                      "(ShardedEmbedding.weight) into a replicated table for serving")
         item_seq = self.embeddings.item_seq
         non_pad = item_seq != self.padding_idx
         rows_ids = torch.arange(item_seq.size(0), dtype=torch.long, device=item_seq.device)
@@ -324,6 +321,15 @@ class NextItemPredictionTask(PredictionTask):
         xs_planes, xs_f32 = ops.gather_rows_split(x.reshape(-1, d), flat_idx, None, B, want_f32=True)
         if self.task_block is not None:
             xs_f32, xs_planes = self._task_block_rows(xs_planes, None)
+        if self._sharded():
+            # serving over the row-sharded table: per-shard top-k + one exchange of (score, id) candidates
+            if top_k is None:
+                raise NotImplementedError("scores [B, V] are not materialised over a row-sharded item table: "
+                                          "pass top_k (Model.top_k / forward(..., top_k=k))")
+            from . import distributed as D
+            table = self.item_embedding_table
+            return D.sharded_topk(xs_f32, table.weight.detach(), table.num_embeddings, int(top_k), table.group,
+                                  w_planes=w_planes, inv_tau=inv_tau)
         scores = ops.head_logits(xs_planes, w_planes, Wd.shape[1], inv_temperature=inv_tau, nprod=self._dense_nprod())
         if top_k is None:
             return scores
