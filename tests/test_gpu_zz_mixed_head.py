@@ -38,11 +38,15 @@ def test_device_packing_matches_host_twin_bit_exactly(ops):
     assert torch.equal(pd.cpu(), ph)
 
 
-@pytest.mark.parametrize("two_cta", ["0", "1"])
-@pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5)])
-def test_head_full_softmax_nprod2(ops, monkeypatch, T, V, De, tau, two_cta):
-    """Same cases and bars as test_gpu_parity.py::test_head_full_softmax, both GEMM kernels."""
-    monkeypatch.setenv("T4R_GEMM_2CTA", two_cta)
+@pytest.mark.parametrize("kernel", ["single", "pair", "resident"])
+@pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5),
+                                        (600, 123001, 256, 1.0)])
+def test_head_full_softmax_nprod2(ops, monkeypatch, T, V, De, tau, kernel):
+    """Same cases and bars as test_gpu_parity.py::test_head_full_softmax, on all three head kernels (single CTA,
+    CTA pair, CTA pair with the resident A tile); the last case has more (row block x column chunk) units than
+    CTA pairs, so the resident kernel's unit-to-unit hand-over of the A slots is exercised."""
+    monkeypatch.setenv("T4R_GEMM_2CTA", "0" if kernel == "single" else "1")
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "1" if kernel == "resident" else "0")
     torch.manual_seed(12)
     xt = torch.randn(T, De)
     W = torch.randn(V, De) * 0.1
@@ -63,6 +67,25 @@ def test_head_full_softmax_nprod2(ops, monkeypatch, T, V, De, tau, two_cta):
     ref_rec = O.recall_at_mean(ks, ref_logits, y)
     got_rec = ops.recall_from_ranks(res["row_rank"], ks, count).cpu()
     assert (got_rec - ref_rec).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("nprod", [3, 1])
+def test_resident_head_kernel_matches_the_default_kernel(ops, monkeypatch, nprod):
+    """T4R_HEAD_RESIDENT=1 with the shipped arithmetic: same operands, same products, only the operand staging
+    differs -> row_lse / loss / ranks must agree with the default CTA-pair kernel to accumulation-order noise."""
+    torch.manual_seed(5)
+    T, V, De = 700, 140001, 256
+    xt = torch.randn(T, De, device="cuda")
+    W = torch.randn(V, De, device="cuda") * 0.1
+    y = torch.randint(1, V, (T,), device="cuda")
+    xp, wp = ops.split_planes(xt), ops.split_planes(W)
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "0")
+    a = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=True, nprod=nprod)
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "1")
+    b = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=True, nprod=nprod)
+    assert (a["row_lse"] - b["row_lse"]).abs().max().item() < 1e-5
+    assert abs(a["loss"].item() - b["loss"].item()) < 1e-6
+    assert torch.equal(a["row_rank"], b["row_rank"])
 
 
 def test_nprod2_requires_its_scales(ops):

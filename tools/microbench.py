@@ -65,7 +65,7 @@ def main():
     b1, b2 = torch.randn(4 * d, device=dev), torch.randn(d, device=dev)
     g, bt = torch.ones(d, device=dev), torch.zeros(d, device=dev)
     ffp = ops.split_planes(torch.randn(M, 4 * d, device=dev))
-    if "head2" in which and "head" not in which:
+    if ("head2" in which or "headres" in which) and "head" not in which:
         which.append("head")
     on = lambda k: "all" in which or k in which
     if on("qkv"):
@@ -141,6 +141,12 @@ def main():
         for nprod in (3, 1):  # 1 = plain bf16: same operand traffic, a third of the MMAs -> separates tensor- from L2-bound
             timeit(f"head 5120 x 1M x 256 nprod={nprod}", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=nprod),
                    iters=5, flops=2 * T * V * d)
+        if "headres" in which:  # A-resident head kernel (T4R_HEAD_RESIDENT=1), all three arithmetics
+            os.environ["T4R_HEAD_RESIDENT"] = "1"
+            for nprod in (3, 1):
+                timeit(f"head 5120 x 1M x 256 nprod={nprod} resident-A", lambda: ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=nprod),
+                       iters=5, flops=2 * T * V * d)
+            os.environ["T4R_HEAD_RESIDENT"] = "0"
         if "head2" in which:  # 2-unit product (fp16 + two e4m3 cross terms): same operand bytes, 2/3 of the tensor passes
             ref = ops.head_softmax_ce(xtp, xt, y, wp, W, nprod=3)
             del wp
@@ -151,6 +157,10 @@ def main():
                 got["loss"].item(), ref["loss"].item(), (got["row_lse"] - ref["row_lse"]).abs().max().item()), flush=True)
             timeit("head 5120 x 1M x 256 nprod=2", lambda: ops.head_softmax_ce(xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi,
                                                                                 w_inv_scale=wi), iters=5, flops=2 * T * V * d)
+            os.environ["T4R_HEAD_RESIDENT"] = "1"
+            timeit("head 5120 x 1M x 256 nprod=2 resident-A", lambda: ops.head_softmax_ce(
+                xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi, w_inv_scale=wi), iters=5, flops=2 * T * V * d)
+            os.environ["T4R_HEAD_RESIDENT"] = "0"
 
 
 if __name__ == "__main__":

@@ -1000,6 +1000,225 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ============================================================================
+// Head GEMM with a RESIDENT A tile (CTA pairs, K <= 256; opt-in: T4R_HEAD_RESIDENT=1).
+// The tied-logits GEMM multiplies a small A (T label rows) by a huge B (the item table).  In gemm2_bf16x3_kernel
+// every 256 x 256 output tile re-streams both operands from L2: 64 KB per CTA and K block, half of it A -- the same
+// A rows over and over.  Here a CTA pair works on UNITS of (one 256-row block of A) x (HEAD_CHUNK consecutive column
+// tiles): A (all K blocks, 4 x 32 KB per CTA) is loaded once per unit and stays in shared memory, only the B half-tiles
+// (32 KB per K block) stream through a 3-stage ring.  L2->SM traffic per launch drops from 2 x (A + B) to
+// ~(1 + 1/HEAD_CHUNK) x ... half (config 2: 41 GB -> ~22 GB), which matters once the products get cheaper than the
+// operand stream (nprod = 2: 1024 tensor cycles per 64 KB; nprod = 1: 512).  Units are numbered column-chunk-major,
+// row-block-minor and dealt round-robin to the pairs, so the ~20 row blocks of one column chunk run at the same time
+// on neighbouring pairs and share the chunk's B tiles in L2.  The A slot of K block kb is released by a commit after the
+// LAST tile's MMAs on it, so the next unit's A[kb] load overlaps the tail of the current unit (no drain bubble).
+// Barriers: a_full/a_empty[4] (per K block, one phase per unit), b_full/b_empty[3], tfull/tempty[2] as in gemm2.
+// ============================================================================
+constexpr int HEAD_CHUNK = 16;
+struct HeadResCfg {
+  static constexpr int BN = 256;
+  static constexpr int A_PLANE_BYTES = BM * 128;             // 16 KB: 128 rows x 64 K elements, one plane
+  static constexpr int A_SLOT_BYTES = 2 * A_PLANE_BYTES;     // both planes of one K block
+  static constexpr int MAX_KB = 4;                           // K <= 256
+  static constexpr int B_PLANE_BYTES = (BN / 2) * 128;       // this CTA's half of the B tile, one plane
+  static constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int DATA_BYTES = MAX_KB * A_SLOT_BYTES + STAGES * B_STAGE_BYTES;  // 224 KB
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__global__ void __launch_bounds__(320, 1)
+head_resident_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                     const GemmDev p) {
+  using Cfg = HeadResCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + Cfg::MAX_KB * Cfg::A_SLOT_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+  uint64_t* a_empty = a_full + Cfg::MAX_KB;
+  uint64_t* b_full = a_empty + Cfg::MAX_KB;
+  uint64_t* b_empty = b_full + Cfg::STAGES;
+  uint64_t* tfull_bar = b_empty + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  int M_eff = p.M;
+  if (p.m_dev) M_eff = min(p.M, *p.m_dev);
+  const int tiles_m = (M_eff + 2 * BM - 1) / (2 * BM);
+  const int tiles_n = static_cast<int>((p.N + BN - 1) / BN);
+  const int chunks_n = (tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK;
+  const int64_t num_units = static_cast<int64_t>(tiles_m) * chunks_n;
+  const int nkb = p.nkb;  // <= MAX_KB (checked by the launcher)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::MAX_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool two_planes = (p.nprod != 1);
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t uphase = 0;  // parity of the unit count: one a_full / a_empty phase per unit and K block
+      const uint32_t a_bytes = two_planes ? Cfg::A_SLOT_BYTES : Cfg::A_PLANE_BYTES;
+      const uint32_t b_bytes = two_planes ? Cfg::B_STAGE_BYTES : Cfg::B_PLANE_BYTES;
+      for (int64_t unit = pair; unit < num_units; unit += npairs) {
+        const int tm = static_cast<int>(unit % tiles_m);
+        const int chunk = static_cast<int>(unit / tiles_m);
+        const int m0 = tm * (2 * BM) + rank * BM;
+        const int t_begin = chunk * HEAD_CHUNK;
+        const int t_end = min(t_begin + HEAD_CHUNK, tiles_n);
+        for (int tn = t_begin; tn < t_end; ++tn) {
+          const int n0 = tn * BN + rank * (BN / 2);
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (tn == t_begin) {  // this unit's A, K block kb: wait until the previous unit's last MMAs on the slot retired
+              mbar_wait(&a_empty[kb], uphase ^ 1);
+              uint8_t* sa = a_base + kb * Cfg::A_SLOT_BYTES;
+              if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * a_bytes);
+              tma_load_2d_pair(sa, &tmAh, &a_full[kb], kb * 64, m0);
+              if (two_planes) tma_load_2d_pair(sa + Cfg::A_PLANE_BYTES, &tmAl, &a_full[kb], kb * 64, m0);
+            }
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            uint8_t* sb = b_base + stage * Cfg::B_STAGE_BYTES;
+            if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * b_bytes);
+            tma_load_2d_pair(sb, &tmBh, &b_full[stage], kb * 64, n0);
+            if (two_planes) tma_load_2d_pair(sb + Cfg::B_PLANE_BYTES, &tmBl, &b_full[stage], kb * 64, n0);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        uphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc_h = umma_idesc_f16(2 * BM, BN);
+      constexpr uint32_t idesc_8 = umma_idesc_e4m3(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t uphase = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int64_t unit = pair; unit < num_units; unit += npairs) {
+        const int chunk = static_cast<int>(unit / tiles_m);
+        const int t_begin = chunk * HEAD_CHUNK;
+        const int t_end = min(t_begin + HEAD_CHUNK, tiles_n);
+        for (int tn = t_begin; tn < t_end; ++tn) {
+          mbar_wait(&tempty_bar[as], aph ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (tn == t_begin) mbar_wait(&a_full[kb], uphase);
+            mbar_wait(&b_full[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t a_hi = smem_u32(a_base + kb * Cfg::A_SLOT_BYTES);
+            const uint32_t a_lo = a_hi + Cfg::A_PLANE_BYTES;
+            const uint32_t b_hi = smem_u32(b_base + stage * Cfg::B_STAGE_BYTES);
+            const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
+            if (p.nprod == 2) {  // fp16 x fp16 + two e4m3 cross terms (t4r_mixed_pack.cuh)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h,
+                               (kb | k4) != 0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, 1u);
+                umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32);
+                const uint64_t db_hi = umma_desc_sw128(b_hi + k4 * 32);
+                if (p.nprod == 3) {
+                  umma_bf16_pair(d_tmem, umma_desc_sw128(a_lo + k4 * 32), db_hi, idesc, (kb | k4) != 0);
+                  umma_bf16_pair(d_tmem, da_hi, umma_desc_sw128(b_lo + k4 * 32), idesc, 1u);
+                  umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, 1u);
+                } else {
+                  umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, (kb | k4) != 0);
+                }
+              }
+            }
+            umma_commit_pair(&b_empty[stage]);                       // B stage free in both CTAs
+            if (tn == t_end - 1) umma_commit_pair(&a_empty[kb]);      // last use of this unit's A[kb]
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&tfull_bar[as]);
+          as ^= 1;
+          if (as == 0) aph ^= 1;
+        }
+        uphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (2..9) of both CTAs =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS = BN / 2;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int64_t unit = pair; unit < num_units; unit += npairs) {
+      const int tm = static_cast<int>(unit % tiles_m);
+      const int chunk = static_cast<int>(unit / tiles_m);
+      const int t_begin = chunk * HEAD_CHUNK;
+      const int t_end = min(t_begin + HEAD_CHUNK, tiles_n);
+      const int64_t m0 = static_cast<int64_t>(tm) * (2 * BM) + rank * BM;
+      const int64_t row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M_eff;
+      for (int tn = t_begin; tn < t_end; ++tn) {
+        const int64_t n0 = static_cast<int64_t>(tn) * BN + half * COLS;
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(as * BN + half * COLS);
+        epilogue_head<BN>(p, taddr, row, row_ok, n0, tn * 2 + half);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
 // ----------------------------------------------------------------------------
 // host launcher
 // ----------------------------------------------------------------------------
@@ -1060,6 +1279,34 @@ static int launch_inst2(const CUtensorMap& ah, const CUtensorMap& al, const CUte
   cfg.numAttrs = 1;
   T4R_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dp));
   T4R_LAUNCH_CHECK("gemm2_bf16x3_kernel");
+  return 0;
+}
+
+static int launch_head_resident(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                                const GemmDev& dp, int64_t units, cudaStream_t stream) {
+  using Cfg = HeadResCfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T4R_CUDA(cudaFuncSetAttribute(head_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  int pairs = static_cast<int>(units < max_pairs ? units : max_pairs);
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  T4R_CUDA(cudaLaunchKernelEx(&cfg, head_resident_kernel, ah, al, bh, bl, dp));
+  T4R_LAUNCH_CHECK("head_resident_kernel");
   return 0;
 }
 
@@ -1134,6 +1381,14 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
     T4R_TRY(make_tmap(&bh2, pb.b_planes, pb.N, pb.Kp, bn / 2, rb));
     T4R_TRY(make_tmap(&bl2, pb.b_planes + pb.b_rows * pb.Kp, pb.N, pb.Kp, bn / 2, rb));
     const int64_t pair_tiles = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((pb.N + bn - 1) / bn);
+    // T4R_HEAD_RESIDENT=1: the head kernel that keeps the A tile in shared memory (K <= 256, BN = 256); opt-in
+    int resident = 0;
+    if (const char* e = getenv("T4R_HEAD_RESIDENT")) resident = atoi(e);
+    if (resident && ep.head && bn == 256 && dp.nkb <= HeadResCfg::MAX_KB) {
+      const int64_t tiles_n = (pb.N + bn - 1) / bn;
+      const int64_t units = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK);
+      return launch_head_resident(ah, al, bh2, bl2, dp, units, stream);
+    }
     if (ep.head) {
       if (bn == 256) return launch_inst2<256, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream);
       if (bn == 128) return launch_inst2<128, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream);
