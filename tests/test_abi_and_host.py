@@ -246,3 +246,17 @@ def test_mixed_product_is_fp32_grade():
     err3 = (x3 - ref).abs().max().item()
     assert err < 1e-4, err                    # two orders inside the 1e-3 parity bar at |logit| ~ 1
     assert err < 4 * err3, (err, err3)        # within a small factor of the shipped 3-product bf16 split
+
+
+def test_head_resident_kernel_barrier_protocol_model():
+    """Discrete-event model of head_resident_kernel's producer / MMA / epilogue loops (tools/sim_head_resident.py):
+    no deadlock, and every MMA reads the A slot / B stage contents of its own (unit, tile, K block)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "sim_head_resident", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "sim_head_resident.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for tiles_m, tiles_n, nkb, npairs, chunk in [(3, 17, 4, 2, 4), (20, 40, 4, 7, 16), (1, 5, 1, 1, 16), (3, 100, 2, 2, 16)]:
+        for pair in range(npairs):
+            assert sim.simulate(tiles_m, tiles_n, nkb, npairs, pair, chunk=chunk, seed=pair) > 0
