@@ -44,6 +44,11 @@ const char* t4r_last_error(void);
 int t4r_version(void);
 /* number of kernels this library has launched since load (all threads). */
 long long t4r_launch_count(void);
+/* sizeof() of the argument structs below as this library was compiled (0 t4r_head_args, 1 t4r_linear_args,
+ * 2 t4r_feature_list, 3 t4r_feature, 4 t4r_xlnet_layer, 5 t4r_gpt2_layer; 0 for anything else) and the byte offset
+ * of the LAST field of t4r_head_args -- lets a binding check its mirror of the layouts before the first call. */
+size_t t4r_sizeof_struct(int which);
+size_t t4r_head_args_last_offset(void);
 
 static inline int t4r_round_up64(int k) { return (k + 63) / 64 * 64; }
 

@@ -260,3 +260,16 @@ def test_head_resident_kernel_barrier_protocol_model():
     for tiles_m, tiles_n, nkb, npairs, chunk in [(3, 17, 4, 2, 4), (20, 40, 4, 7, 16), (1, 5, 1, 1, 16), (3, 100, 2, 2, 16)]:
         for pair in range(npairs):
             assert sim.simulate(tiles_m, tiles_n, nkb, npairs, pair, chunk=chunk, seed=pair) > 0
+
+
+def test_ctypes_structs_mirror_the_compiled_layouts():
+    """Every argument struct of the ABI: ctypes mirror vs sizeof() inside the compiled library, and the offset of
+    the last (most recently added) field of t4r_head_args."""
+    import ctypes as C
+    from transformers4rec_b200 import _lib
+    lib = _lib.load()
+    mirrors = [_lib.HeadArgs, _lib.LinearArgs, _lib.FeatureList, _lib.Feature, _lib.XLNetLayer, _lib.GPT2Layer]
+    for which, cls in enumerate(mirrors):
+        assert lib.t4r_sizeof_struct(which) == C.sizeof(cls), (cls.__name__, lib.t4r_sizeof_struct(which), C.sizeof(cls))
+    assert lib.t4r_sizeof_struct(99) == 0
+    assert lib.t4r_head_args_last_offset() == _lib.HeadArgs.w_inv_scale.offset

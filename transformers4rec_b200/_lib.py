@@ -131,6 +131,8 @@ SIGNATURES = {
     "t4r_last_error": (C.c_char_p, []),
     "t4r_version": (c_int, []),
     "t4r_launch_count": (C.c_longlong, []),
+    "t4r_sizeof_struct": (c_size_t, [c_int]),
+    "t4r_head_args_last_offset": (c_size_t, []),
     "t4r_embed_concat_fwd": (c_int, [C.POINTER(FeatureList), c_int64, c_int, _P, _P, _P, _P]),
     "t4r_pad_ragged": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "t4r_mask_mlm": (c_int, [_P, c_int, c_int, c_int64, c_int, c_float, _P, _P, _P, _P, _P]),

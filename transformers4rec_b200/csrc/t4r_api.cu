@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "t4r_common.cuh"
+#include <stddef.h>
 #include "t4r_internal.h"
 
 #ifndef T4R_FFN_FUSED_DEFAULT
@@ -422,6 +423,19 @@ extern "C" size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De) {
   const size_t n_tiles = 2 * static_cast<size_t>((V + kHeadBN - 1) / kHeadBN);  // two column halves per tile
   return 3 * pad256(n_tiles * part_ld * 4) + pad256(3 * 64 * part_ld * 4) + 1024;
 }
+
+extern "C" size_t t4r_sizeof_struct(int which) {
+  switch (which) {
+    case 0: return sizeof(t4r_head_args);
+    case 1: return sizeof(t4r_linear_args);
+    case 2: return sizeof(t4r_feature_list);
+    case 3: return sizeof(t4r_feature);
+    case 4: return sizeof(t4r_xlnet_layer);
+    case 5: return sizeof(t4r_gpt2_layer);
+    default: return 0;
+  }
+}
+extern "C" size_t t4r_head_args_last_offset(void) { return offsetof(t4r_head_args, w_inv_scale); }
 
 extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   T4R_REQUIRE(a != nullptr, "head: null args");
