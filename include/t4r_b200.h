@@ -379,6 +379,11 @@ int t4r_label_logit(const float* xt_f32, const float* w_f32, const int64_t* labe
 int t4r_head_logits(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V, int De,
                     float inv_temperature, float* out /*[T_cap, ldo]*/, int64_t ldo, int nprod, void* stream);
 
+/* the same from the operands of the 2-unit product (t4r_split_planes_mixed) */
+int t4r_head_logits_mixed(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V, int De,
+                          float inv_temperature, float* out /*[T_cap, ldo]*/, int64_t ldo, const float* xt_inv_scale,
+                          const float* w_inv_scale, void* stream);
+
 /* K10 Recall@k from label ranks: out[j] = mean_t(rank[t] < ks[j]).
  * replaces RecallAt._metric + RankingMetric.update ranking_metric.py:52-63,111-147 */
 int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks /*host*/,

@@ -38,6 +38,27 @@ def test_device_packing_matches_host_twin_bit_exactly(ops):
     assert torch.equal(pd.cpu(), ph)
 
 
+@pytest.mark.parametrize("two_cta", ["0", "1"])
+@pytest.mark.parametrize("T,V,De", [(128, 256, 64), (300, 1000, 64), (257, 777, 200), (513, 2049, 256)])
+def test_materialised_logits_nprod2(ops, monkeypatch, T, V, De, two_cta):
+    """Element-wise check of the 2-unit product through the dense epilogue: the first thing to look at if the
+    fused head disagrees (one K block, one tile in the smallest case).  Bar: the emulated product itself
+    (tests/_mixed_ref.py) to accumulation-order noise, and fp64 to the scheme's error budget."""
+    import _mixed_ref as R
+    monkeypatch.setenv("T4R_GEMM_2CTA", two_cta)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(T, De, generator=g)
+    w = torch.randn(V, De, generator=g) * 0.1
+    xp, xi = ops.split_planes_mixed(x.cuda())
+    wp, wi = ops.split_planes_mixed(w.cuda())
+    got = ops.head_logits_mixed(xp, xi, wp, wi, De, inv_temperature=0.5).cpu().double()
+    emu = R.product(R.pack(x), R.pack(w)) * 0.5
+    ref = (x.double() @ w.double().t()) * 0.5
+    scale = ref.abs().max().item()
+    assert (got - emu).abs().max().item() < 2e-6 * max(scale, 1.0)
+    assert (got - ref).abs().max().item() < 1e-4 * max(scale, 1.0)
+
+
 @pytest.mark.parametrize("kernel", ["single", "pair", "resident"])
 @pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5),
                                         (600, 123001, 256, 1.0)])

@@ -160,6 +160,7 @@ SIGNATURES = {
     "t4r_head_softmax_ce_fwd": (c_int, [C.POINTER(HeadArgs), _P]),
     "t4r_label_logit": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int64, _P, c_float, c_int64, _P, _P]),
     "t4r_head_logits": (c_int, [_P, _P, c_int, _P, c_int64, c_int, c_float, _P, c_int64, c_int, _P]),
+    "t4r_head_logits_mixed": (c_int, [_P, _P, c_int, _P, c_int64, c_int, c_float, _P, c_int64, _P, _P, _P]),
     "t4r_recall_from_ranks": (c_int, [_P, _P, c_int, C.POINTER(C.c_int32), c_int, _P, _P]),
     "t4r_topk": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "t4r_combine_shard_lse": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),

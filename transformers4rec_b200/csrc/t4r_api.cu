@@ -505,8 +505,25 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
                             a->label_smoothing, a->V, a->row_lse, a->row_loss, a->loss, scratch, s);
 }
 
+static int head_logits_impl(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V,
+                            int De, float inv_temperature, float* out, int64_t ldo, int nprod, const float* xt_inv_scale,
+                            const float* w_inv_scale, void* stream);
 extern "C" int t4r_head_logits(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V,
                                int De, float inv_temperature, float* out, int64_t ldo, int nprod, void* stream) {
+  T4R_REQUIRE(nprod != 2, "head_logits: nprod = 2 operands go through t4r_head_logits_mixed");
+  return head_logits_impl(xt_planes, w_planes, T_cap, t_dev, V, De, inv_temperature, out, ldo, nprod, nullptr, nullptr,
+                          stream);
+}
+extern "C" int t4r_head_logits_mixed(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev,
+                                     int64_t V, int De, float inv_temperature, float* out, int64_t ldo,
+                                     const float* xt_inv_scale, const float* w_inv_scale, void* stream) {
+  T4R_REQUIRE(xt_inv_scale && w_inv_scale, "head_logits_mixed: the inverse row scales of both operands are required");
+  return head_logits_impl(xt_planes, w_planes, T_cap, t_dev, V, De, inv_temperature, out, ldo, 2, xt_inv_scale,
+                          w_inv_scale, stream);
+}
+static int head_logits_impl(const void* xt_planes, const void* w_planes, int T_cap, const int32_t* t_dev, int64_t V,
+                            int De, float inv_temperature, float* out, int64_t ldo, int nprod, const float* xt_inv_scale,
+                            const float* w_inv_scale, void* stream) {
   T4R_REQUIRE(xt_planes && w_planes && out && T_cap > 0 && V > 0 && De > 0 && ldo >= V, "head_logits: bad arguments");
   GemmProblem pb;
   pb.M = T_cap;
@@ -523,6 +540,8 @@ extern "C" int t4r_head_logits(const void* xt_planes, const void* w_planes, int 
   ep.out_f32 = out;
   ep.ldo = ldo;
   ep.out_scale = inv_temperature != 0.f ? inv_temperature : 1.f;
+  ep.row_scale = xt_inv_scale;
+  ep.col_scale = w_inv_scale;
   return launch_gemm(pb, ep, static_cast<cudaStream_t>(stream));
 }
 

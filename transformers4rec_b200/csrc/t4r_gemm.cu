@@ -481,6 +481,12 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
       const int64_t n_pad = (p.N + 63) / 64 * 64;  // planes are zero padded to a multiple of 64 columns
       if (ncol0 >= n_pad) continue;                // warp-uniform
       const int nvalid = (p.N - ncol0 >= 32) ? 32 : (p.N > ncol0 ? static_cast<int>(p.N - ncol0) : 0);
+      if (ep.col_scale) {  // 2-unit product: undo the power-of-two row scales of both operands (exact)
+        const float rs = row_ok ? ep.row_scale[row] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] *= rs * __ldg(ep.col_scale + ncol0 + j);
+      }
       dense_chunk(v, ep, ncol0, code, nvalid);
       long long t2 = prof ? clock64() : 0;
       if (prof) { g_dbg_cycles[2] += t1 - t0; g_dbg_cycles[3] += t2 - t1; }
@@ -1327,8 +1333,8 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
               (long long)pb.M, (long long)pb.N, pb.Kp);
   T4R_REQUIRE(pb.M < (1ll << 31), "gemm: M too large");
   T4R_REQUIRE(pb.nprod == 1 || pb.nprod == 3 || pb.nprod == 2, "gemm: nprod must be 1, 2 or 3");
-  T4R_REQUIRE(pb.nprod != 2 || (ep.head && ep.row_scale && ep.col_scale),
-              "gemm: nprod = 2 (fp16 + e4m3 cross terms) is a head-only mode and needs both row-scale vectors");
+  T4R_REQUIRE(pb.nprod != 2 || (ep.row_scale && ep.col_scale && ep.ln_gamma == nullptr),
+              "gemm: nprod = 2 (fp16 + e4m3 cross terms) needs both row-scale vectors and has no LayerNorm epilogue");
   const bool ln = ep.ln_gamma != nullptr;
   int bn = pb.bn;
   if (ln) {

@@ -499,6 +499,18 @@ def head_logits(xt_planes, w_planes, De: int, *, t_dev=None, inv_temperature=1.0
     return out
 
 
+def head_logits_mixed(xt_planes, xt_inv_scale, w_planes, w_inv_scale, De: int, *, t_dev=None,
+                      inv_temperature=1.0) -> torch.Tensor:
+    """Materialised logits from the operands of the 2-unit product (``split_planes_mixed``)."""
+    _need_cuda(xt_planes, w_planes, xt_inv_scale, w_inv_scale)
+    T_cap, V = xt_planes.shape[1], w_planes.shape[1]
+    out = torch.zeros((T_cap, V), dtype=torch.float32, device=xt_planes.device)
+    check(_lib.load().t4r_head_logits_mixed(ptr(xt_planes), ptr(w_planes), T_cap, ptr(t_dev), V, De, inv_temperature,
+                                            ptr(out), V, ptr(xt_inv_scale), ptr(w_inv_scale), _stream()),
+          "t4r_head_logits_mixed")
+    return out
+
+
 def recall_from_ranks(row_rank: torch.Tensor, ks: Sequence[int], t_dev=None) -> torch.Tensor:
     _need_cuda(row_rank)
     out = torch.empty(len(ks), dtype=torch.float32, device=row_rank.device)
