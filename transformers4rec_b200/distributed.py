@@ -108,9 +108,15 @@ def _default_head_rows(xt: torch.Tensor, labels: torch.Tensor, local_table: torc
     """-> [T, 2] (lse over this shard, label logit if the label lives here else 0); with ``rank_tgt`` (the
     label's logit over the whole table) also the per-row count of this shard's classes scoring above it."""
     from . import ops
-    xp = ops.split_planes(xt)
-    res = ops.head_softmax_ce(xp, xt, labels, w_planes, local_table, inv_temperature=inv_tau, v_offset=v_offset,
-                              want_loss=False, want_rank=rank_tgt is not None, rank_tgt=rank_tgt)
+    if isinstance(w_planes, tuple):  # (mixed planes, inverse row scales): the 2-unit product (ops.split_planes_mixed)
+        xp, xi = ops.split_planes_mixed(xt)
+        res = ops.head_softmax_ce(xp, xt, labels, w_planes[0], local_table, inv_temperature=inv_tau, v_offset=v_offset,
+                                  want_loss=False, want_rank=rank_tgt is not None, rank_tgt=rank_tgt, nprod=2,
+                                  xt_inv_scale=xi, w_inv_scale=w_planes[1])
+    else:
+        xp = ops.split_planes(xt)
+        res = ops.head_softmax_ce(xp, xt, labels, w_planes, local_table, inv_temperature=inv_tau, v_offset=v_offset,
+                                  want_loss=False, want_rank=rank_tgt is not None, rank_tgt=rank_tgt)
     part = torch.stack([res["row_lse"], res["row_tgt"]], dim=1)
     return part if rank_tgt is None else (part, res["row_rank"])
 

@@ -182,9 +182,10 @@ class NextItemPredictionTask(PredictionTask):
         self.output_layer = None
         self.sampler = None
         # tensor-core arithmetic of the GEMMs on this task: 3 = split-bf16, three products (fp32-grade, default);
-        # 1 = plain bf16; 2 = the 2-unit product of the TRAINING full-softmax head only (fp16 x fp16 + two e4m3
-        # cross terms, ~2.3x the error of 3 at 2/3 of its tensor time, csrc/t4r_mixed_pack.cuh) -- every other
-        # GEMM of the task (task_block, sampled / sharded heads, evaluation ranks, predictions) then runs with 3.
+        # 1 = plain bf16; 2 = the 2-unit product of the TRAINING full-softmax head only, replicated or row-sharded
+        # (fp16 x fp16 + two e4m3 cross terms, ~2.3x the error of 3 at 2/3 of its tensor time,
+        # csrc/t4r_mixed_pack.cuh) -- every other GEMM of the task (task_block, sampled head, evaluation ranks,
+        # predictions, serving) then runs with 3.
         self.nprod = 3
         self._planes = ops.PlaneCache()
         self._last = None
@@ -264,9 +265,14 @@ class NextItemPredictionTask(PredictionTask):
         B, L, d = x.shape
         W = self.output_weight()
         Wd = W.detach()
-        mixed_head = (self.nprod == 2 and training and not self._sharded()
-                      and not (self.sampled_softmax and training))
-        w_planes = None if mixed_head else self._planes.get("W", W)  # the mixed head keeps only its own 1x copy
+        mixed_ok = self.nprod == 2 and training and not self.sampled_softmax
+        mixed_head = mixed_ok and not self._sharded()
+        if mixed_head:
+            w_planes = None                                # the mixed head keeps only its own 1x copy of the table
+        elif mixed_ok:
+            w_planes = self._planes.get_mixed("W", W)      # sharded full softmax: (planes, inverse scales) of the shard
+        else:
+            w_planes = self._planes.get("W", W)
         inv_tau = self._inv_tau()
 
         if training or testing:
