@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round 2, first gpurun call: validate what was written after round 1's GPU budget ran out.
+#   gpurun --timeout 1500 -- 'bash tools/runs/r2_first.sh'
+# Order: proven suite first (must stay green), then the element-wise check of the 2-unit product, then the fused
+# heads on all three kernels, then timings.  Every step has its own timeout; a trap in an experimental kernel only
+# loses that step (separate processes).
+mkdir -p gpurun_out
+{
+echo "== proven GPU suite"; timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider 2>&1 | tail -5
+echo "== device packing == host twin"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -x -k "packing" -p no:cacheprovider 2>&1 | tail -5
+echo "== 2-unit product, element-wise (dense epilogue)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "materialised" -p no:cacheprovider 2>&1 | tail -12
+echo "== resident-A kernel vs default kernel (shipped arithmetic)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "resident_head_kernel" -p no:cacheprovider 2>&1 | tail -8
+echo "== fused head nprod=2 on single / pair / resident"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "full_softmax_nprod2 or requires or model_training" -p no:cacheprovider 2>&1 | tail -15
+echo "== timings (config-2 head shape): nprod 3 / 1, resident-A, nprod 2"; timeout 600 python tools/microbench.py head headres head2 2>&1 | tail -12
+echo "== bench A/B"; for a in "" "--nprod 2"; do timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline $a 2>&1 | tail -1 | cut -c1-700; done
+echo "== bench with the resident-A head"; T4R_HEAD_RESIDENT=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-700
+T4R_HEAD_RESIDENT=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --nprod 2 2>&1 | tail -1 | cut -c1-700
+} > gpurun_out/r2_first.log 2>&1
+tail -60 gpurun_out/r2_first.log
