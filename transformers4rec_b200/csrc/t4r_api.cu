@@ -448,7 +448,9 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   T4R_REQUIRE(a->workspace_bytes >= t4r_head_workspace_bytes(a->T_cap, a->V, a->De), "head: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int part_ld = (a->T_cap + 127) / 128 * 128;
-  const int n_tiles = 2 * static_cast<int>((a->V + kHeadBN - 1) / kHeadBN);  // partials per (tile, column half)
+  int n_tiles = 2 * static_cast<int>((a->V + kHeadBN - 1) / kHeadBN);  // partials per (tile, column half)
+  const int res_parts = head_resident_partials(a->T_cap, a->V, t4r_round_up64(a->De));
+  if (res_parts > 0) n_tiles = res_parts;  // resident-A kernel: one partial per (16-tile column chunk, half)
   Arena ar(a->workspace, a->workspace_bytes);
   float* part_m = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
   float* part_s = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
@@ -493,6 +495,7 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   ep.row_tgt = a->rank_tgt ? a->rank_tgt : a->row_tgt;
   ep.row_rank = a->row_rank;
   ep.col_offset = a->v_offset;
+  ep.head_resident = res_parts > 0;
   if (pb.nprod == 2) {
     T4R_REQUIRE(a->xt_inv_scale && a->w_inv_scale, "head: nprod = 2 needs xt_inv_scale and w_inv_scale");
     ep.row_scale = a->xt_inv_scale;

@@ -1007,6 +1007,113 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 }
 
 
+// Per-row running state of the online log-sum-exp, carried ACROSS the column tiles of one unit by the resident-A
+// kernel: one partial per (unit, column half, row) instead of one per (tile, half, row) -- 16x fewer partials to
+// write, read back and reduce (config 2: 0.64 GB -> 40 MB of DRAM traffic per launch).  Same arithmetic per tile as
+// epilogue_head (which the other kernels keep using).
+struct HeadRowState {
+  float m_run, s_run, z_run, tgt, row_scale;
+  int cnt;
+  int64_t label;
+};
+__device__ __forceinline__ void head_state_init(HeadRowState& st, const GemmEpilogue& ep, int64_t row, bool row_ok) {
+  st.m_run = -INFINITY; st.s_run = 0.f; st.z_run = 0.f; st.cnt = 0; st.label = -1; st.tgt = 0.f;
+  if (row_ok && ep.row_label) st.label = ep.row_label[row];
+  if (row_ok && ep.row_rank) st.tgt = ep.row_tgt[row];
+  st.row_scale = (row_ok && ep.row_scale) ? ep.row_scale[row] : 1.f;
+}
+template <int BN>
+__device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev& p, uint32_t taddr, bool row_ok, int64_t n0) {
+  constexpr int COLS = BN / 2;
+  const GemmEpilogue& ep = p.ep;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float scale2 = ep.inv_tau * kLog2e;
+  const bool want_z = (ep.part_z != nullptr);
+  const bool want_rank = (ep.row_rank != nullptr);
+  const bool full_tile = (n0 + COLS <= p.N);
+#pragma unroll 1
+  for (int c = 0; c < COLS / 32; ++c) {
+    float v[32];
+    tmem_ld<32>(taddr + c * 32, v);
+    if (!row_ok) continue;
+    const int64_t ncol0 = n0 + c * 32;
+    if (ncol0 >= p.N) continue;
+    if (ep.col_scale) {
+      if (full_tile) {
+        const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + ncol0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cs = __ldg(c4 + j);
+          v[4 * j + 0] *= st.row_scale * cs.x; v[4 * j + 1] *= st.row_scale * cs.y;
+          v[4 * j + 2] *= st.row_scale * cs.z; v[4 * j + 3] *= st.row_scale * cs.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ncol0 + j < p.N) v[j] *= st.row_scale * __ldg(ep.col_scale + ncol0 + j);
+      }
+    }
+    if (ep.col_bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full_tile || ncol0 + j < p.N) v[j] += __ldg(ep.col_bias + ncol0 + j);
+    }
+    if (ep.col_ids) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if ((full_tile || ncol0 + j < p.N) && __ldg(ep.col_ids + ncol0 + j) == st.label) v[j] = ep.hit_value;
+    }
+    if (!full_tile) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ncol0 + j >= p.N) v[j] = -INFINITY;
+    }
+    if (want_rank) {
+      const int64_t lab_col = st.label - ep.col_offset;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = v[j] * ep.inv_tau;
+        const int64_t col = ncol0 + j;
+        st.cnt += (col != lab_col) && ((x > st.tgt) || (x == st.tgt && col < lab_col));
+      }
+    }
+    if (want_z) {
+      float zs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) zs += (v[j] == -INFINITY) ? 0.f : v[j];
+      st.z_run = fmaf(zs, ep.inv_tau, st.z_run);
+    }
+    float mx[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+    for (int j = 4; j < 32; j += 4) {
+      mx[0] = fmaxf(mx[0], v[j]); mx[1] = fmaxf(mx[1], v[j + 1]);
+      mx[2] = fmaxf(mx[2], v[j + 2]); mx[3] = fmaxf(mx[3], v[j + 3]);
+    }
+    const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale2;
+    const float m_new = fmaxf(st.m_run, cmax);
+    if (m_new > -INFINITY) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        acc[0] += fast_exp2(fmaf(v[j], scale2, -m_new));
+        acc[1] += fast_exp2(fmaf(v[j + 1], scale2, -m_new));
+        acc[2] += fast_exp2(fmaf(v[j + 2], scale2, -m_new));
+        acc[3] += fast_exp2(fmaf(v[j + 3], scale2, -m_new));
+      }
+      st.s_run = st.s_run * fast_exp2(st.m_run - m_new) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+      st.m_run = m_new;
+    }
+  }
+}
+__device__ __forceinline__ void head_state_flush(const HeadRowState& st, const GemmEpilogue& ep, int64_t row, bool row_ok,
+                                                 int part_idx) {
+  if (!row_ok) return;
+  ep.part_m[static_cast<int64_t>(part_idx) * ep.part_ld + row] = st.m_run;
+  ep.part_s[static_cast<int64_t>(part_idx) * ep.part_ld + row] = st.s_run;
+  if (ep.part_z) ep.part_z[static_cast<int64_t>(part_idx) * ep.part_ld + row] = st.z_run;
+  if (ep.row_rank && st.cnt) atomicAdd(ep.row_rank + row, st.cnt);
+}
+
 // ============================================================================
 // Head GEMM with a RESIDENT A tile (CTA pairs, K <= 256; opt-in: T4R_HEAD_RESIDENT=1).
 // The tied-logits GEMM multiplies a small A (T label rows) by a huge B (the item table).  In gemm2_bf16x3_kernel
@@ -1202,19 +1309,22 @@ head_resident_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
       const int64_t m0 = static_cast<int64_t>(tm) * (2 * BM) + rank * BM;
       const int64_t row = m0 + quad * 32 + lane;
       const bool row_ok = row < M_eff;
+      HeadRowState st;
+      head_state_init(st, p.ep, row, row_ok);
       for (int tn = t_begin; tn < t_end; ++tn) {
         const int64_t n0 = static_cast<int64_t>(tn) * BN + half * COLS;
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + half * COLS);
-        epilogue_head<BN>(p, taddr, row, row_ok, n0, tn * 2 + half);
+        head_state_tile<BN>(st, p, taddr, row_ok, n0);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
         as ^= 1;
         if (as == 0) aph ^= 1;
       }
+      head_state_flush(st, p.ep, row, row_ok, chunk * 2 + half);  // ONE partial per (column chunk, half, row)
     }
   }
 
@@ -1328,6 +1438,21 @@ extern "C" int t4r_debug_gemm_cycles(unsigned long long* out8, int reset) {
   return 0;
 }
 namespace t4r {
+// T4R_HEAD_RESIDENT=1 (opt-in) and a shape the resident-A head kernel covers: K <= 256, more than one 128-row
+// block, CTA pairs and 128-byte rows enabled.  Returns the number of LSE partials per row the head call must size
+// for (2 per column CHUNK), or 0 when the regular kernels run (2 per column TILE).
+int head_resident_partials(int64_t M, int64_t V, int Kp) {
+  int resident = 0;
+  if (const char* e = getenv("T4R_HEAD_RESIDENT")) resident = atoi(e);
+  int two_cta = T4R_GEMM_2CTA_DEFAULT;
+  if (const char* e = getenv("T4R_GEMM_2CTA")) two_cta = atoi(e);
+  const char* rbe = getenv("T4R_GEMM_RB");
+  const bool rb128 = !(rbe && atoi(rbe) == 64);
+  if (!resident || !two_cta || !rb128 || M <= BM || Kp > 64 * HeadResCfg::MAX_KB) return 0;
+  const int64_t tiles_n = (V + HeadResCfg::BN - 1) / HeadResCfg::BN;
+  return 2 * static_cast<int>((tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK);
+}
+
 int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stream) {
   T4R_REQUIRE(pb.M > 0 && pb.N > 0 && pb.Kp > 0 && pb.Kp % 64 == 0, "gemm: bad shape M=%lld N=%lld Kp=%d",
               (long long)pb.M, (long long)pb.N, pb.Kp);
@@ -1387,10 +1512,10 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
     T4R_TRY(make_tmap(&bh2, pb.b_planes, pb.N, pb.Kp, bn / 2, rb));
     T4R_TRY(make_tmap(&bl2, pb.b_planes + pb.b_rows * pb.Kp, pb.N, pb.Kp, bn / 2, rb));
     const int64_t pair_tiles = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((pb.N + bn - 1) / bn);
-    // T4R_HEAD_RESIDENT=1: the head kernel that keeps the A tile in shared memory (K <= 256, BN = 256); opt-in
-    int resident = 0;
-    if (const char* e = getenv("T4R_HEAD_RESIDENT")) resident = atoi(e);
-    if (resident && ep.head && bn == 256 && dp.nkb <= HeadResCfg::MAX_KB) {
+    // the head kernel that keeps the A tile in shared memory (the head entry point decided it: head_resident_partials)
+    T4R_REQUIRE(!ep.head_resident || (ep.head && bn == 256 && dp.nkb <= HeadResCfg::MAX_KB),
+                "gemm: resident head requested for an unsupported shape");
+    if (ep.head_resident) {
       const int64_t tiles_n = (pb.N + bn - 1) / bn;
       const int64_t units = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK);
       return launch_head_resident(ah, al, bh2, bl2, dp, units, stream);
@@ -1410,6 +1535,7 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
     return launch_inst2<64, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
   }
 
+  T4R_REQUIRE(!ep.head_resident, "gemm: resident head needs the CTA-pair path (T4R_GEMM_2CTA=1, 128-byte rows, M > 128)");
 #define T4R_GEMM_DISPATCH(RBV)                                                                              \
   do {                                                                                                      \
     if (ep.head) {                                                                                          \

@@ -81,6 +81,7 @@ struct GemmEpilogue {
   const float* row_tgt = nullptr;      // [M] label logit (already scaled), for ranks
   int* row_rank = nullptr;             // [M] atomically accumulated
   int64_t col_offset = 0;              // global class id of column 0 (shards)
+  bool head_resident = false;          // run head_resident_kernel: ONE partial per (column chunk of 16 tiles, half, row)
   const float* row_scale = nullptr;    // [M] nprod = 2: 1 / (power-of-two scale of A's row)
   const float* col_scale = nullptr;    // [N] nprod = 2: 1 / (power-of-two scale of B's row)
   int debug = 0;                       // T4R_GEMM_DEBUG: 1 = epilogue skips all global loads/stores (timing experiments)
@@ -100,6 +101,7 @@ struct GemmProblem {
 };
 
 int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stream);
+int head_resident_partials(int64_t M, int64_t V, int Kp);  // > 0: the resident-A head kernel will run (t4r_gemm.cu)
 
 // fused feed-forward block (t4r_gemm.cu): Y = epilogue(gelu(X W1^T + b1) W2^T), intermediate kept in TMEM
 bool ffn_fused_supported(int d, int hidden);
