@@ -387,7 +387,10 @@ def main():
         head_flops = 2.0 * T * (int(task._last["neg"].numel()) + 1) * cfg["De"]
     achieved_tf = head_flops / (head_ms_avg * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    roofline = {"bound": "tensor", "kernel": "gemm2_bf16x3_kernel<256,false,true> (CTA-pair tcgen05 GEMM: tied logits + online LSE)",
+    head_kernel = ("head_resident_kernel (CTA-pair tcgen05 GEMM with the A tile resident in shared memory: tied logits + "
+                   "online LSE)" if os.environ.get("T4R_HEAD_RESIDENT") == "1" and cfg["De"] <= 256 else
+                   "gemm2_bf16x3_kernel<256,false,true> (CTA-pair tcgen05 GEMM: tied logits + online LSE)")
+    roofline = {"bound": "tensor", "kernel": head_kernel,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
                 "traffic": head_traffic() if args.workload == "config2" else None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,

@@ -273,3 +273,24 @@ def test_ctypes_structs_mirror_the_compiled_layouts():
         assert lib.t4r_sizeof_struct(which) == C.sizeof(cls), (cls.__name__, lib.t4r_sizeof_struct(which), C.sizeof(cls))
     assert lib.t4r_sizeof_struct(99) == 0
     assert lib.t4r_head_args_last_offset() == _lib.HeadArgs.w_inv_scale.offset
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU torch path; needs no GPU): one JSON line with the keys the
+    driver reads, on the smallest workload so that the CPU suite stays fast."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "config1",
+                          "--steps", "2", "--cpu-sessions", "32"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sessions/sec (fwd+loss)" and d["unit"] == "sessions/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sessions/step" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("BASELINE.json config1")
