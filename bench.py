@@ -220,6 +220,57 @@ def time_oracle_cpu(cfg, B_cpu, steps, warmup, budget_s=8.0):
     return B_run / med, med, best_threads, B_run
 
 
+def recall_agreement(cfg, model, batch_dev, batch_host, n_sample=64):
+    """BASELINE.json's accuracy anchor: Recall@20 of the evaluation forward (`testing=True`: the last item of every
+    session is the label, full scores over V).  Ours = the fused head's label ranks on the whole bench batch; the
+    oracle (reference CPU path, THE SAME weights copied over) scores the first `n_sample` sessions, and the label
+    ranks of those sessions are compared one by one (with random-init weights Recall@20 itself is ~20/V for both,
+    so the rank agreement is the informative part).  Best effort: never fails the bench line."""
+    with torch.no_grad():
+        out = model(batch_dev, training=False, testing=True)
+        T = int(out.count.item()) if out.count is not None else int(out.row_rank.numel())
+        ranks = out.row_rank[:T].long().cpu()
+        oracle = oracle_with_model_weights(cfg, model)
+        small = {k: v[:n_sample] for k, v in batch_host.items()}
+        ref_rank = oracle_label_ranks(oracle, small)
+        n = ref_rank.numel()
+        mine = ranks[:n]
+        return {"k": 20, "ours_full_batch": float((ranks < 20).float().mean()), "label_rows": T,
+                "ours_sample": float((mine < 20).float().mean()), "oracle_sample": float((ref_rank < 20).float().mean()),
+                "sample": f"first {n_sample} sessions, eval mode, oracle with the product's weights",
+                "label_rank_max_abs_diff": int((mine - ref_rank).abs().max()),
+                "label_rank_median_rel_diff": float(((mine - ref_rank).abs().float() / ref_rank.clamp(min=1).float()).median())}
+
+
+def oracle_label_ranks(oracle, batch):
+    """Rank of every evaluation label among the oracle's full scores (ties towards the lower id, the label excluded)."""
+    with torch.no_grad():
+        ref = oracle(batch, training=False, testing=True)
+    pred, y = ref["predictions"], ref["labels"]
+    tgt = pred.gather(1, y.unsqueeze(1))
+    ids = torch.arange(pred.shape[1]).unsqueeze(0)
+    return (((pred > tgt) | ((pred == tgt) & (ids < y.unsqueeze(1)))) & (ids != y.unsqueeze(1))).sum(1)
+
+
+def oracle_with_model_weights(cfg, model):
+    """The oracle graph of `cfg` carrying the product model's parameters (device -> host copies)."""
+    with torch.no_grad():
+        oracle = build_oracle(cfg)
+        head = model.heads[0]
+        inputs, tblock = head.body[0], head.body[1]
+        for name in oracle.table_names:
+            oracle.tables[name.replace("/", "__")].weight.copy_(inputs.categorical_module.embedding_tables[name].weight.cpu())
+        lin = inputs.projection_module[0][0]
+        oracle.proj.weight.copy_(lin.weight.cpu()); oracle.proj.bias.copy_(lin.bias.cpu())
+        oracle.masked_item_embedding.copy_(inputs.masking.masked_item_embedding.cpu())
+        oracle.transformer.load_state_dict({k: v.cpu() for k, v in tblock.transformer.state_dict().items()}, strict=False)
+        task = head.prediction_task_dict["next-item"]
+        if oracle.task_block is not None:
+            tl = task.task_block[0][0]
+            oracle.task_block.weight.copy_(tl.weight.cpu()); oracle.task_block.bias.copy_(tl.bias.cpu())
+    return oracle
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -414,6 +465,11 @@ def main():
                                 "sample": f"{b_run} sessions/step of the same workload, 3 timed steps "
                                           f"(median {med:.2f} s), oracle graph = torch CPU ops + HF encoder, {threads} of "
                                           f"{os.cpu_count()} host threads (best of a calibration sweep)"}
+    if not args.no_cpu_baseline and world == 1 and not cfg.get("sharded"):
+        try:
+            line["recall_at_20"] = recall_agreement(cfg, model, batch_dev, batch_host)
+        except Exception as exc:  # an accuracy side-note must never cost the throughput line
+            line["recall_at_20"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

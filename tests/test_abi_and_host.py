@@ -294,3 +294,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sessions/step" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("BASELINE.json config1")
+
+
+def test_bench_recall_leg_helpers_on_cpu():
+    """bench.py's Recall@20 leg: the oracle must really carry the product model's weights (built here on the CPU --
+    only the forward needs a GPU), for the item-only XLNet shape and for a side-feature GPT-2 shape with task_block."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for cfg in (dict(bench.CONFIGS["config1"]),
+                dict(V=3001, De=32, d=64, H=4, NL=1, L=12, B=8, arch="gpt2", masking="clm",
+                     side={"category/list": 37, "brand/list": 11}, label="test")):
+        model = bench.build_product_model(cfg, torch.device("cpu"))
+        with torch.no_grad():
+            for prm in model.parameters():
+                prm.add_(torch.randn_like(prm) * 0.01)   # make sure "same seed" cannot explain equal weights
+        oracle = bench.oracle_with_model_weights(cfg, model)
+        inputs = model.heads[0].body[0]
+        for name in oracle.table_names:
+            assert torch.equal(oracle.tables[name.replace("/", "__")].weight,
+                               inputs.categorical_module.embedding_tables[name].weight)
+        assert torch.equal(oracle.proj.weight, inputs.projection_module[0][0].weight)
+        sd_o, sd_m = oracle.transformer.state_dict(), model.heads[0].body[1].transformer.state_dict()
+        shared = [k for k in sd_o if k in sd_m]
+        assert len(shared) >= 10 and all(torch.equal(sd_o[k], sd_m[k]) for k in shared)
+        if oracle.task_block is not None:
+            tl = model.heads[0].prediction_task_dict["next-item"].task_block[0][0]
+            assert torch.equal(oracle.task_block.weight, tl.weight)
+        batch = bench.synth_batch(6, cfg["L"], cfg, seed=0)
+        ranks = bench.oracle_label_ranks(oracle, batch)
+        assert ranks.shape == (6,) and int(ranks.min()) >= 0 and int(ranks.max()) < cfg["V"]
