@@ -38,10 +38,16 @@ def unpack_planes(planes: torch.Tensor):
     return h16, hi8, lo8
 
 
-def product(pa, pb):
-    """What the tensor core accumulates (exact products, here summed in fp64), scaled back: [rows_a, rows_b]."""
+def product(pa, pb, terms=("main", "cross1", "cross2")):
+    """What the tensor core accumulates (exact products, here summed in fp64), scaled back: [rows_a, rows_b].
+    ``terms`` selects the partial products (the kernel's T4R_GEMM_DEBUG bring-up switches 64 / 128 / 256 drop
+    main / cross1 / cross2)."""
     d = torch.float64
-    acc = pa["h16"].to(d) @ pb["h16"].to(d).t()
-    acc += pa["lo8"].to(d) @ pb["hi8"].to(d).t()
-    acc += pa["hi8"].to(d) @ pb["lo8"].to(d).t()
+    acc = torch.zeros((pa["h16"].shape[0], pb["h16"].shape[0]), dtype=d)
+    if "main" in terms:
+        acc += pa["h16"].to(d) @ pb["h16"].to(d).t()
+    if "cross1" in terms:
+        acc += pa["lo8"].to(d) @ pb["hi8"].to(d).t()
+    if "cross2" in terms:
+        acc += pa["hi8"].to(d) @ pb["lo8"].to(d).t()
     return acc * pa["inv_scale"].to(d)[:, None] * pb["inv_scale"].to(d)[None, :]

@@ -59,6 +59,26 @@ def test_materialised_logits_nprod2(ops, monkeypatch, T, V, De, two_cta):
     assert (got - ref).abs().max().item() < 1e-4 * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("two_cta", ["0", "1"])
+@pytest.mark.parametrize("drop,terms", [(128 + 256, ("main",)), (64 + 256, ("cross1",)), (64 + 128, ("cross2",))])
+def test_each_partial_product_alone(ops, monkeypatch, drop, terms, two_cta):
+    """Bring-up aid: T4R_GEMM_DEBUG bits 64 / 128 / 256 drop the fp16 main product / lo8(A) x hi8(B) / hi8(A) x lo8(B);
+    each remaining term alone must equal its emulation (exact products, fp32 vs fp64 accumulation).  If the full
+    product is off, this says which instruction descriptor / operand offset is to blame."""
+    import _mixed_ref as R
+    monkeypatch.setenv("T4R_GEMM_2CTA", two_cta)
+    monkeypatch.setenv("T4R_GEMM_DEBUG", str(drop))
+    g = torch.Generator().manual_seed(8)
+    T, V, De = 257, 777, 200
+    x = torch.randn(T, De, generator=g)
+    w = torch.randn(V, De, generator=g) * 0.1
+    xp, xi = ops.split_planes_mixed(x.cuda())
+    wp, wi = ops.split_planes_mixed(w.cuda())
+    got = ops.head_logits_mixed(xp, xi, wp, wi, De).cpu().double()
+    emu = R.product(R.pack(x), R.pack(w), terms)
+    assert (got - emu).abs().max().item() < 2e-6 * max(emu.abs().max().item(), 1e-3)
+
+
 @pytest.mark.parametrize("kernel", ["single", "pair", "resident"])
 @pytest.mark.parametrize("T,V,De,tau", [(200, 10001, 64, 1.0), (517, 30011, 256, 1.0), (64, 999, 128, 0.5),
                                         (600, 123001, 256, 1.0)])

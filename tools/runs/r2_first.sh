@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 {
 echo "== proven GPU suite"; timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider 2>&1 | tail -5
 echo "== device packing == host twin"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -x -k "packing" -p no:cacheprovider 2>&1 | tail -5
-echo "== 2-unit product, element-wise (dense epilogue)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "materialised" -p no:cacheprovider 2>&1 | tail -12
+echo "== 2-unit product, element-wise (dense epilogue), then each partial product alone"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "materialised or partial_product" -p no:cacheprovider 2>&1 | tail -12
 echo "== resident-A kernel vs default kernel (shipped arithmetic)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "resident_head_kernel" -p no:cacheprovider 2>&1 | tail -8
 echo "== fused head nprod=2 on single / pair / resident"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "full_softmax_nprod2 or requires or model_training" -p no:cacheprovider 2>&1 | tail -15
 echo "== timings (config-2 head shape): nprod 3 / 1, resident-A, nprod 2"; timeout 600 python tools/microbench.py head headres head2 2>&1 | tail -12

@@ -727,13 +727,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             // all into the same fp32 accumulator.
             constexpr uint32_t idesc_h = umma_idesc_f16(BM, BN);
             constexpr uint32_t idesc_8 = umma_idesc_e4m3(BM, BN);
+            // bring-up switches (T4R_GEMM_DEBUG): 64 / 128 / 256 drop the main / first / second cross product
+            const int dbg = p.ep.debug;
+            uint32_t acc = (kb != 0) ? 1u : 0u;
+            if (!(dbg & 64)) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16(d_tmem, umma_desc<RB>(a_hi + k4 * 32), umma_desc<RB>(b_hi + k4 * 32), idesc_h, (kb | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16(d_tmem, umma_desc<RB>(a_hi + k4 * 32), umma_desc<RB>(b_hi + k4 * 32), idesc_h, acc);
+                acc = 1u;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              umma_f8(d_tmem, umma_desc<RB>(a_lo + 64 + j * 32), umma_desc<RB>(b_lo + j * 32), idesc_8, 1u);
-              umma_f8(d_tmem, umma_desc<RB>(a_lo + j * 32), umma_desc<RB>(b_lo + 64 + j * 32), idesc_8, 1u);
+              if (!(dbg & 128)) { umma_f8(d_tmem, umma_desc<RB>(a_lo + 64 + j * 32), umma_desc<RB>(b_lo + j * 32), idesc_8, acc); acc = 1u; }
+              if (!(dbg & 256)) { umma_f8(d_tmem, umma_desc<RB>(a_lo + j * 32), umma_desc<RB>(b_lo + 64 + j * 32), idesc_8, acc); acc = 1u; }
             }
           } else {
 #pragma unroll
@@ -928,14 +935,19 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           if (p.nprod == 2) {  // 2-unit product: see the single-CTA kernel
             constexpr uint32_t idesc_h = umma_idesc_f16(2 * BM, BN);
             constexpr uint32_t idesc_8 = umma_idesc_e4m3(2 * BM, BN);
+            const int dbg = p.ep.debug;  // bring-up switches: 64 / 128 / 256 drop the main / first / second cross product
+            uint32_t acc = (kb != 0) ? 1u : 0u;
+            if (!(dbg & 64)) {
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h,
-                             (kb | k4) != 0);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h, acc);
+                acc = 1u;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, 1u);
-              umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, 1u);
+              if (!(dbg & 128)) { umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, acc); acc = 1u; }
+              if (!(dbg & 256)) { umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, acc); acc = 1u; }
             }
           } else {
 #pragma unroll
@@ -1259,14 +1271,19 @@ head_resident_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
             const uint32_t b_hi = smem_u32(b_base + stage * Cfg::B_STAGE_BYTES);
             const uint32_t b_lo = b_hi + Cfg::B_PLANE_BYTES;
             if (p.nprod == 2) {  // fp16 x fp16 + two e4m3 cross terms (t4r_mixed_pack.cuh)
+              const int dbg = p.ep.debug;
+              uint32_t acc = (kb != 0) ? 1u : 0u;
+              if (!(dbg & 64)) {
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h,
-                               (kb | k4) != 0);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  umma_bf16_pair(d_tmem, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc_h, acc);
+                  acc = 1u;
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, 1u);
-                umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, 1u);
+                if (!(dbg & 128)) { umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + 64 + j * 32), umma_desc_sw128(b_lo + j * 32), idesc_8, acc); acc = 1u; }
+                if (!(dbg & 256)) { umma_f8_pair(d_tmem, umma_desc_sw128(a_lo + j * 32), umma_desc_sw128(b_lo + 64 + j * 32), idesc_8, acc); acc = 1u; }
               }
             } else {
 #pragma unroll
@@ -1498,9 +1515,8 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   dp.m_dev = pb.m_dev;
   dp.ep = ep;
   {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("T4R_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    dp.ep.debug = dbg;
+    const char* e = getenv("T4R_GEMM_DEBUG");  // read per call: tests flip the bring-up switches within one process
+    dp.ep.debug = e ? atoi(e) : 0;
   }
   const int64_t max_tiles = ((pb.M + BM - 1) / BM) * ((pb.N + bn - 1) / bn);
 
