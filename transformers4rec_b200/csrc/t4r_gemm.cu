@@ -110,6 +110,7 @@ __device__ unsigned long long g_dbg_cycles[8];
 __device__ unsigned long long g_dbg_ffn[16];
 
 struct GemmDev {
+  int head_chunk;  // resident-A head kernel: column tiles per unit
   int M;
   int64_t N;
   int nkb;
@@ -1140,7 +1141,13 @@ __device__ __forceinline__ void head_state_flush(const HeadRowState& st, const G
 // LAST tile's MMAs on it, so the next unit's A[kb] load overlaps the tail of the current unit (no drain bubble).
 // Barriers: a_full/a_empty[4] (per K block, one phase per unit), b_full/b_empty[3], tfull/tempty[2] as in gemm2.
 // ============================================================================
-constexpr int HEAD_CHUNK = 16;
+constexpr int HEAD_CHUNK_DEFAULT = 16;
+// column tiles per unit: T4R_HEAD_CHUNK (1..256) for tuning without a rebuild; read per call
+static int head_chunk() {
+  int c = HEAD_CHUNK_DEFAULT;
+  if (const char* e = getenv("T4R_HEAD_CHUNK")) c = atoi(e);
+  return c < 1 ? 1 : (c > 256 ? 256 : c);
+}
 struct HeadResCfg {
   static constexpr int BN = 256;
   static constexpr int A_PLANE_BYTES = BM * 128;             // 16 KB: 128 rows x 64 K elements, one plane
@@ -1183,6 +1190,7 @@ head_resident_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
   if (p.m_dev) M_eff = min(p.M, *p.m_dev);
   const int tiles_m = (M_eff + 2 * BM - 1) / (2 * BM);
   const int tiles_n = static_cast<int>((p.N + BN - 1) / BN);
+  const int HEAD_CHUNK = p.head_chunk;
   const int chunks_n = (tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK;
   const int64_t num_units = static_cast<int64_t>(tiles_m) * chunks_n;
   const int nkb = p.nkb;  // <= MAX_KB (checked by the launcher)
@@ -1467,7 +1475,8 @@ int head_resident_partials(int64_t M, int64_t V, int Kp) {
   const bool rb128 = !(rbe && atoi(rbe) == 64);
   if (!resident || !two_cta || !rb128 || M <= BM || Kp > 64 * HeadResCfg::MAX_KB) return 0;
   const int64_t tiles_n = (V + HeadResCfg::BN - 1) / HeadResCfg::BN;
-  return 2 * static_cast<int>((tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK);
+  const int hc = head_chunk();
+  return 2 * static_cast<int>((tiles_n + hc - 1) / hc);
 }
 
 int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stream) {
@@ -1512,6 +1521,7 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
   dp.N = pb.N;
   dp.nkb = pb.Kp / (rb / 2);
   dp.nprod = pb.nprod;
+  dp.head_chunk = head_chunk();
   dp.m_dev = pb.m_dev;
   dp.ep = ep;
   {
@@ -1533,7 +1543,7 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
                 "gemm: resident head requested for an unsupported shape");
     if (ep.head_resident) {
       const int64_t tiles_n = (pb.N + bn - 1) / bn;
-      const int64_t units = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((tiles_n + HEAD_CHUNK - 1) / HEAD_CHUNK);
+      const int64_t units = ((pb.M + 2 * BM - 1) / (2 * BM)) * ((tiles_n + dp.head_chunk - 1) / dp.head_chunk);
       return launch_head_resident(ah, al, bh2, bl2, dp, units, stream);
     }
     if (ep.head) {
