@@ -9,20 +9,8 @@ NPROD=${NPROD:-3}
 export $HEADCFG
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --nprod $NPROD > gpurun_out/r2_launches_bench.log 2>&1
-python tools/summarize_ncu.py gpurun_out/r2_launches.csv > gpurun_out/r2_launches.txt 2>&1 || true
+python tools/summarize_ncu.py launches gpurun_out/r2_launches.csv gpurun_out/r2_launches.txt || true
 ncu --set full --clock-control none --import-source on -k regex:"head_resident_kernel|gemm2_bf16x3_kernel" -s 6 -c 1 \
     -o gpurun_out/r2_head -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --nprod $NPROD > gpurun_out/r2_head_ncu.log 2>&1
-ncu -i gpurun_out/r2_head.ncu-rep --page raw --csv 2>/dev/null | python - <<'PY' > gpurun_out/r2_head_summary.txt
-import csv, sys
-rows = list(csv.reader(sys.stdin))
-if len(rows) >= 3:
-    hdr, vals = rows[0], rows[-1]
-    want = ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.sum", "launch__registers_per_thread",
-            "launch__shared_mem_per_block_dynamic")
-    for h, v in zip(hdr, vals):
-        if any(w in h for w in want):
-            print(f"{h:100s} {v}")
-PY
+python tools/summarize_ncu.py full gpurun_out/r2_head.ncu-rep gpurun_out/r2_head_summary.txt || true
 tail -5 gpurun_out/r2_launches.txt; cat gpurun_out/r2_head_summary.txt | head -20
