@@ -1,0 +1,305 @@
+"""TEST DOUBLES for ``transformers4rec_b200.ops`` (plain torch, CPU).
+
+The product has no CPU path: every op in ``ops.py`` hands device pointers to ``libt4r_b200.so``.  To exercise the
+HOST logic of the package (module wiring, state side channels, lazy outputs, masking modes, the sharded
+choreography through the model, bench helpers) in the ``-m "not gpu"`` suite, the tests -- and only the tests --
+swap those ops for the stand-ins below with ``install(monkeypatch)``.  Each stand-in mirrors the signature, the output
+shapes / dtypes and the padding conventions of its kernel; the arithmetic is the oracle's.  The 2-unit product
+(``nprod=2``) is emulated bit-for-bit from the packed operands (tests/_mixed_ref.py), so the control flow that
+selects it sees what the tensor core would produce.  Nothing here is imported by the package.
+"""
+import torch
+import torch.nn.functional as F
+
+import _mixed_ref as R
+import t4r_oracle as O
+from transformers4rec_b200 import _lib
+
+
+def _r64(k):
+    return (k + 63) // 64 * 64
+
+
+def make_planes(x, Kp=None):
+    rows, K = x.shape
+    Kp = Kp or _r64(K)
+    xp = torch.zeros((rows, Kp), dtype=torch.float32)
+    xp[:, :K] = x
+    hi = xp.to(torch.bfloat16)
+    lo = (xp - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo])
+
+
+def from_planes(p, K=None):
+    x = p[0].float() + p[1].float()
+    return x if K is None else x[:, :K]
+
+
+def _count(t_dev, cap):
+    return cap if t_dev is None else min(int(t_dev.reshape(-1)[0]), cap)
+
+
+# ---------------------------------------------------------------------------------------------------- packing
+def split_planes(x, row_code=None, mask_vec=None, want_f32=False, out=None):
+    v = x.float().clone()
+    if row_code is not None:
+        rc = row_code.reshape(-1)
+        v[rc == 1] = mask_vec.float()
+        v[rc == 2] = 0.0
+    planes = make_planes(v)
+    if out is not None:
+        out.copy_(planes)
+        planes = out
+    return (planes, v) if want_f32 else planes
+
+
+def split_planes_mixed(x):
+    from transformers4rec_b200 import ops
+    return ops.split_planes_mixed_host(x)  # the kernel's own packing code, compiled for the host
+
+
+def gather_rows_split(x2d, idx, count, cap, want_f32=True):
+    n = _count(count, cap) if idx.dtype == torch.int32 else cap
+    K = x2d.shape[1]
+    of = torch.zeros((cap, K), dtype=torch.float32)
+    of[:n] = x2d.float()[idx[:n].long()]
+    return make_planes(of), (of if want_f32 else None)
+
+
+def compact_targets(masked_targets, padding_idx=0):
+    mt = masked_targets.long().reshape(-1)
+    nz = (mt != padding_idx).nonzero().squeeze(1)
+    rows = torch.zeros(mt.numel(), dtype=torch.int32)
+    labels = torch.zeros(mt.numel(), dtype=torch.int64)
+    rows[: nz.numel()] = nz.int()
+    labels[: nz.numel()] = mt[nz]
+    return rows, labels, torch.tensor([nz.numel()], dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------------- K1 / K3
+def embed_concat(cats, conts, M, C_width, want_f32, want_planes):
+    out = torch.zeros((M, C_width), dtype=torch.float32)
+    err = torch.zeros(1, dtype=torch.int32)
+    for table, ids, col in cats:
+        ids = ids.reshape(-1).long()
+        bad = (ids < 0) | (ids >= table.shape[0])
+        if bad.any():
+            err[0] = 1
+        out[:, col:col + table.shape[1]] = table.detach().float()[torch.where(bad, torch.zeros_like(ids), ids)]
+    for vals, col in conts:
+        out[:, col] = vals.reshape(-1).float()
+    return (out if want_f32 else None), (make_planes(out) if want_planes else None), err
+
+
+def mask_mlm(item_ids, mode, padding_idx=0, mlm_probability=0.15, u=None):
+    ids = item_ids.long()
+    B, L = ids.shape
+    if mode == _lib.MLM_TRAIN:
+        if u is None:
+            u = torch.rand((B, L + 2))
+        m, l = O.mlm_compute_masked_targets(ids, True, False, mlm_probability=mlm_probability, padding_idx=padding_idx,
+                                            u_bern=u[:, :L], u_force=u[:, L], u_unmask=u[:, L + 1])
+    elif mode == _lib.MLM_INFERENCE:
+        m, l = O.mlm_compute_masked_targets(ids, False, False, padding_idx=padding_idx)
+    else:
+        m, l = O.mlm_compute_masked_targets(ids, False, True, padding_idx=padding_idx,
+                                            eval_on_last_item_seq_only=(mode == _lib.MLM_EVAL_LAST))
+    return m, l, m.to(torch.uint8)
+
+
+def mask_clm(item_ids, mode, padding_idx=0):
+    ids = item_ids.long()
+    training, testing = (mode == _lib.CLM_ALL), (mode == _lib.CLM_LAST)
+    m, l = O.clm_compute_masked_targets(ids, training, testing, padding_idx=padding_idx) if mode != _lib.CLM_INFERENCE \
+        else O.clm_compute_masked_targets(ids, False, False, padding_idx=padding_idx)
+    probe = O.clm_apply_mask_to_inputs(torch.ones(ids.shape + (1,)), m, torch.tensor([2.0]), training=training,
+                                       testing=testing)[..., 0]
+    code = torch.zeros(ids.shape, dtype=torch.uint8)
+    code[probe == 2.0] = 1
+    code[probe == 0.0] = 2
+    return m, l, code
+
+
+# ---------------------------------------------------------------------------------------------------- K2
+def linear(x_planes, w_planes, K, *, bias=None, act=_lib.ACT_NONE, row_code=None, mask_vec=None, residual=None, ln=None,
+           ln_eps=0.0, want_f32=True, want_planes=True, want_pre_ln=False, m_dev=None, nprod=3):
+    x, w = from_planes(x_planes, K), from_planes(w_planes, K)
+    M = x.shape[0]
+    n = _count(m_dev, M)
+    y = x @ w.t()
+    if bias is not None:
+        y = y + bias.detach().float()
+    if act == _lib.ACT_RELU:
+        y = torch.relu(y)
+    elif act == _lib.ACT_GELU:
+        y = F.gelu(y)
+    if row_code is not None:
+        rc = row_code.reshape(-1)
+        y[rc == 1] = mask_vec.detach().float()
+        y[rc == 2] = 0.0
+    if residual is not None:
+        y = y + residual.float()
+    pre = y.clone()
+    if ln is not None:
+        y = F.layer_norm(y, (y.shape[1],), ln[0].detach().float(), ln[1].detach().float(), ln_eps)
+    y[n:] = 0.0
+    return (y if want_f32 else None), (make_planes(y) if want_planes else None), (pre if want_pre_ln else None)
+
+
+# ---------------------------------------------------------------------------------------------------- head
+def _logits(xt_planes, w_planes, De, nprod, xt_inv, w_inv):
+    if nprod == 2:
+        ha, h8a, l8a = R.unpack_planes(xt_planes)
+        hb, h8b, l8b = R.unpack_planes(w_planes)
+        pa = {"h16": ha, "hi8": h8a, "lo8": l8a, "inv_scale": xt_inv}
+        pb = {"h16": hb, "hi8": h8b, "lo8": l8b, "inv_scale": w_inv}
+        return R.product(pa, pb).float()
+    return from_planes(xt_planes, De) @ from_planes(w_planes, De).t()
+
+
+def label_logit(xt_f32, w_f32, labels, *, t_dev=None, class_bias=None, inv_temperature=1.0, v_offset=0):
+    T_cap = xt_f32.shape[0]
+    n = _count(t_dev, T_cap)
+    loc = labels.long() - v_offset
+    mine = (loc >= 0) & (loc < w_f32.shape[0])
+    rows = w_f32.detach().float()[loc.clamp(0, w_f32.shape[0] - 1)]
+    val = (xt_f32.float() * rows).sum(1)
+    if class_bias is not None:
+        val = val + class_bias[loc.clamp(0, w_f32.shape[0] - 1)]
+    out = torch.where(mine, val * inv_temperature, torch.zeros_like(val))
+    out[n:] = 0.0
+    return out
+
+
+def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
+                    col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True, nprod=3,
+                    events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None):
+    if nprod == 2 and (xt_inv_scale is None or w_inv_scale is None):
+        raise _lib.T4RError("head_softmax_ce: nprod=2 needs the mixed planes' inverse row scales")
+    T_cap, V = xt_planes.shape[1], w_planes.shape[1]
+    De = xt_f32.shape[1] if xt_f32 is not None else w_f32.shape[1]
+    n = _count(t_dev, T_cap)
+    z = _logits(xt_planes, w_planes, De, nprod, xt_inv_scale, w_inv_scale)
+    if col_bias is not None:
+        z = z + col_bias.unsqueeze(0)
+    y = labels.long() if labels is not None else None
+    if col_ids is not None:
+        z = torch.where(col_ids.unsqueeze(0) == y.unsqueeze(1), torch.full_like(z, hit_value), z)
+    z = z * inv_temperature
+    row_tgt = torch.zeros(T_cap)
+    if pos_logit is not None:  # sampled softmax: class 0 = the positive
+        full = torch.cat([pos_logit.reshape(-1, 1).float(), z], dim=1)
+        row_lse = torch.logsumexp(full, dim=1)
+        row_tgt = pos_logit.float().clone()
+    else:
+        row_lse = torch.logsumexp(z, dim=1)
+        row_tgt = label_logit(xt_f32, w_f32, y, inv_temperature=inv_temperature, v_offset=v_offset)
+    row_loss = row_lse - row_tgt
+    if label_smoothing:
+        row_loss = row_lse - (1 - label_smoothing) * row_tgt - (label_smoothing / V) * z.sum(1)
+    row_rank = None
+    if want_rank:
+        tgt = (rank_tgt if rank_tgt is not None else row_tgt).unsqueeze(1)
+        col = torch.arange(V).unsqueeze(0) + v_offset
+        above = ((z > tgt) | ((z == tgt) & (col < y.unsqueeze(1)))) & (col != y.unsqueeze(1))
+        row_rank = above.sum(1).to(torch.int32)
+        row_rank[n:] = 0
+    for t in (row_lse, row_tgt, row_loss):
+        t[n:] = 0.0
+    loss = (row_loss[:n].sum() / max(n, 1)).reshape(1) if want_loss else None
+    return {"row_lse": row_lse, "row_tgt": row_tgt, "row_loss": row_loss, "loss": loss, "row_rank": row_rank}
+
+
+def head_logits(xt_planes, w_planes, De, *, t_dev=None, inv_temperature=1.0, nprod=3):
+    if nprod == 2:
+        raise _lib.T4RError("head_logits: nprod = 2 operands go through t4r_head_logits_mixed")
+    out = _logits(xt_planes, w_planes, De, nprod, None, None) * inv_temperature
+    out[_count(t_dev, out.shape[0]):] = 0.0
+    return out
+
+
+def head_logits_mixed(xt_planes, xt_inv_scale, w_planes, w_inv_scale, De, *, t_dev=None, inv_temperature=1.0):
+    out = _logits(xt_planes, w_planes, De, 2, xt_inv_scale, w_inv_scale) * inv_temperature
+    out[_count(t_dev, out.shape[0]):] = 0.0
+    return out
+
+
+def topk(logits, k):
+    order = torch.sort(-logits.float(), dim=1, stable=True).indices[:, :k]  # value desc, index asc: t4r_topk's order
+    return logits.float().gather(1, order), order
+
+
+def recall_from_ranks(row_rank, ks, t_dev=None):
+    n = _count(t_dev, row_rank.numel())
+    r = row_rank[:n]
+    return torch.tensor([float((r < k).float().mean()) if n else 0.0 for k in ks])
+
+
+def metrics_from_ranks(row_rank, ks, kind, t_dev=None):
+    n = _count(t_dev, row_rank.numel())
+    r = row_rank[:n].float()
+    outs = []
+    for k in ks:
+        hit = (r < k).float()
+        if kind == _lib.METRIC_RECALL:
+            v = hit
+        elif kind == _lib.METRIC_PRECISION:
+            v = hit / k
+        elif kind == _lib.METRIC_RR:
+            v = hit / (r + 1)
+        else:
+            v = hit / torch.log2(r + 2)
+        outs.append(v.mean() if n else torch.tensor(0.0))
+    return torch.stack(outs)
+
+
+def combine_shard_lse(parts, t_dev=None):
+    n = _count(t_dev, parts.shape[1])
+    row = torch.logsumexp(parts[:, :, 0], dim=0) - parts[:, :, 1].sum(0)
+    row[n:] = 0.0
+    return row, (row[:n].sum() / max(n, 1)).reshape(1)
+
+
+# ---------------------------------------------------------------------------------------------------- encoders
+def _xlnet_forward(self, inputs_embeds, **kwargs):
+    hf = O.build_hf_xlnet(self.config.d_model, self.config.n_head, self.config.n_layer).eval()
+    missing, _ = hf.load_state_dict(self.state_dict(), strict=False)
+    assert not [m for m in missing if "mask_emb" not in m and "word_embedding" not in m], missing
+    with torch.no_grad():
+        return (O.hf_encoder_forward(hf, inputs_embeds.float()),)
+
+
+def _gpt2_forward(self, inputs_embeds, **kwargs):
+    B, L, d = inputs_embeds.shape
+    if L > self.config.n_positions:
+        raise ValueError(f"sequence length {L} exceeds n_positions {self.config.n_positions}")
+    hf = O.build_hf_gpt2(self.config.n_embd, self.config.n_head, self.config.n_layer, self.config.n_positions).eval()
+    missing, _ = hf.load_state_dict(self.state_dict(), strict=False)
+    assert not [m for m in missing if "wte" not in m], missing
+    with torch.no_grad():
+        return (O.hf_encoder_forward(hf, inputs_embeds.float()),)
+
+
+OPS = dict(split_planes=split_planes, split_planes_mixed=split_planes_mixed, gather_rows_split=gather_rows_split,
+           compact_targets=compact_targets, embed_concat=embed_concat, mask_mlm=mask_mlm, mask_clm=mask_clm, linear=linear,
+           label_logit=label_logit, head_softmax_ce=head_softmax_ce, head_logits=head_logits,
+           head_logits_mixed=head_logits_mixed, topk=topk, recall_from_ranks=recall_from_ranks,
+           metrics_from_ranks=metrics_from_ranks, combine_shard_lse=combine_shard_lse)
+
+
+def install(monkeypatch):
+    """Swap the kernels for the stand-ins for the duration of one test."""
+    from transformers4rec_b200 import block, ops
+    for name, fn in OPS.items():
+        monkeypatch.setattr(ops, name, fn)
+    monkeypatch.setattr(block.XLNetEncoder, "forward", _xlnet_forward)
+    monkeypatch.setattr(block.GPT2Encoder, "forward", _gpt2_forward)
+
+
+def install_plain():
+    """Same without pytest (spawned gloo workers): returns nothing, patches for the life of the process."""
+    from transformers4rec_b200 import block, ops
+    for name, fn in OPS.items():
+        setattr(ops, name, fn)
+    block.XLNetEncoder.forward = _xlnet_forward
+    block.GPT2Encoder.forward = _gpt2_forward

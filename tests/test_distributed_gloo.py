@@ -152,3 +152,83 @@ def test_shard_bounds_and_plan():
     assert plan.recv_counts == [2, 2]          # my ids [7,7,1,2]: two owned by rank 0, two by rank 1
     assert plan.unpermute.tolist() == [2, 3, 0, 1]
     assert torch.equal(D.owner_of(torch.tensor([0, 4, 5, 9]), 10, 2), torch.tensor([0, 0, 1, 1]))
+
+
+# --------------------------------------------------------------------------- #
+# model level over gloo, kernels replaced by the test doubles (tests/_ops_double.py): TabularSequenceFeatures +
+# XLNet + NextItemPredictionTask over a row-sharded item table -- training loss with the 3-product and the 2-unit
+# head, evaluation loss + cross-shard Recall, top-k serving -- against the single-process oracle on the GLOBAL batch.
+# --------------------------------------------------------------------------- #
+def _model_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import _ops_double
+    import t4r_oracle as O
+    from _util import make_pair, mlm_draws, synth_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _ops_double.install_plain()
+        cards, dims = {"item_id/list": 2001}, {"item_id/list": 32}
+        Bm, Lm, K = 6, 10, 5
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 32, 2, 1, Lm, weight_scale=0.08, device="cpu")
+        inputs = model.heads[0].body[0]
+        inputs.categorical_module.shard_item_table()
+        task = model.heads[0].prediction_task_dict["next-item"]
+        batches = [synth_batch(Bm, Lm, cards, seed=100 + r) for r in range(world)]
+        us = [mlm_draws(Bm, Lm, seed=200 + r) for r in range(world)]
+        gb = {k: torch.cat([b[k] for b in batches]) for k in batches[0]}
+        gdraws = {k: torch.cat([u[1][k] for u in us]) for k in us[0][1]}
+        res = {}
+        with torch.no_grad():
+            inputs.masking.set_draws(us[rank][0])
+            ref = oracle(gb, training=True, draws=gdraws)
+            res["train3"] = abs(model(batches[rank], training=True)["loss"].item() - ref["loss"].item())
+            task.nprod = 2   # sharded full softmax through the 2-unit product (emulated from the packed operands)
+            res["train2"] = abs(model(batches[rank], training=True)["loss"].item() - ref["loss"].item())
+            ref_e = oracle(gb, training=False, testing=True)
+            out_e = model(batches[rank], training=False, testing=True)
+            res["eval"] = abs(out_e["loss"].item() - ref_e["loss"].item())
+            mine = slice(rank * Bm, (rank + 1) * Bm)
+            ref_rec = O.recall_at_mean([1, 5, 20], ref_e["predictions"][mine], ref_e["labels"][mine])
+            import transformers4rec_b200.torch as tr
+            m = tr.RecallAt(top_ks=[1, 5, 20], labels_onehot=True)
+            m.update_from_ranks(out_e.row_rank, None)
+            res["recall"] = (m.metric_mean[-1] - ref_rec).abs().max().item()
+            # serving
+            short = {k: torch.nn.functional.pad(v[:, :-1], (0, 1)) for k, v in batches[rank].items()}
+            x, _, _ = oracle.input_block(short, False, False)
+            h = O.hf_encoder_forward(oracle.transformer, x)
+            last = (short["item_id/list"] != 0).sum(1)
+            ref_scores = h[torch.arange(Bm), last] @ oracle.item_table().t()
+            model.top_k = K
+            s, i = model(short, training=False, testing=False)
+            rs, ri = torch.topk(ref_scores, K)
+            res["topk_scores"] = (s - rs).abs().max().item()
+            res["topk_ids"] = (i == ri).float().mean().item()
+            try:
+                model.top_k = None
+                model(short, training=False, testing=False)
+                res["scores_error"] = "no error"
+            except NotImplementedError as exc:
+                res["scores_error"] = str(exc)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_model_over_sharded_item_table_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r["train3"] < 1e-4 and r["train2"] < 1e-3 and r["eval"] < 1e-4 and r["recall"] < 1e-6, (rank, r)
+        assert r["topk_scores"] < 1e-4 and r["topk_ids"] == 1.0, (rank, r)
+        assert "top_k" in r["scores_error"], (rank, r)

@@ -1,0 +1,132 @@
+"""Host logic of the package end to end on the CPU, with the kernels replaced by test doubles
+(tests/_ops_double.py): module wiring, masking modes, state side channels, lazy outputs, metrics, the arithmetic
+switches of the head (nprod = 3 / 2) and bench.py's accuracy leg.  The doubles compute with the oracle's arithmetic,
+so the results are compared with the oracle graph itself."""
+import math
+
+import pytest
+import torch
+
+import _ops_double as D
+import t4r_oracle as O
+from _util import make_pair, mlm_draws, synth_batch
+
+CARDS = {"item_id/list": 3001, "category/list": 37}
+DIMS = {"item_id/list": 64, "category/list": 64}
+CONT = ("cont0/list", "cont1/list")
+
+
+def _pair(arch="xlnet", masking="mlm", dims=DIMS, **kw):
+    return make_pair(CARDS, dims, "item_id/list", CONT, 64, 4, 1, 12, arch=arch, masking=masking, device="cpu",
+                     weight_scale=0.08, **kw)
+
+
+@pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("xlnet", "clm"), ("gpt2", "clm")])
+def test_training_eval_inference_flows(monkeypatch, arch, masking):
+    D.install(monkeypatch)
+    oracle, model = _pair(arch, masking)
+    B, L = 9, 12
+    batch = synth_batch(B, L, CARDS, CONT, seed=1)
+    u, draws = mlm_draws(B, L)
+    inputs = model.heads[0].body[0]
+    inputs.masking.set_draws(u)
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws)
+        out = model(batch, training=True)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-4
+    assert torch.equal(inputs.masking.masked_targets, ref["masked_targets"])      # state side channel
+    assert torch.equal(out["labels"], ref["labels"])                             # lazy outputs
+    assert (out["predictions"] - ref["predictions"]).abs().max().item() < 1e-3
+    assert torch.equal(inputs.to_merge["categorical_module"].item_seq, batch["item_id/list"])
+    # evaluation: ranks -> metrics through the task
+    with torch.no_grad():
+        ref_e = oracle(batch, training=False, testing=True)
+        out_e = model(batch, training=False, testing=True)
+    assert abs(out_e["loss"].item() - ref_e["loss"].item()) < 1e-4
+    task = model.heads[0].prediction_task_dict["next-item"]
+    got = task.calculate_metrics(out_e)
+    ref_rec = O.recall_at_mean([10, 20], ref_e["predictions"], ref_e["labels"])
+    name = [k for k in got if "recall" in k][0]
+    assert (got[name] - ref_rec).abs().max().item() < 1e-6
+    # inference: scores and top-k
+    if masking == "mlm":
+        short = {k: torch.nn.functional.pad(v[:, :-1], (0, 1)) for k, v in batch.items()}
+    else:
+        short = batch
+    with torch.no_grad():
+        scores = model(short, training=False, testing=False)
+        model.top_k = 5
+        s, i = model(short, training=False, testing=False)
+        model.top_k = None
+    assert scores.shape == (B, CARDS["item_id/list"])
+    rs, ri = torch.sort(-scores, dim=1, stable=True)
+    assert torch.equal(i, ri[:, :5]) and torch.allclose(s, -rs[:, :5])
+
+
+def test_task_block_and_mixed_head_arithmetic(monkeypatch):
+    """item dim != d_model -> task_block; task.nprod = 2 routes the TRAINING head through the 2-unit product (emulated
+    bit-for-bit from the packed operands) and everything else through the 3-product planes."""
+    D.install(monkeypatch)
+    oracle, model = _pair(dims={"item_id/list": 32, "category/list": 64})
+    B, L = 8, 12
+    batch = synth_batch(B, L, CARDS, CONT, seed=2)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    assert task.task_block is not None
+    from transformers4rec_b200 import ops
+    calls = []
+    real = ops.head_softmax_ce
+    monkeypatch.setattr(ops, "head_softmax_ce", lambda *a, **k: (calls.append((k.get("nprod"), k.get("want_rank"))), real(*a, **k))[1])
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws)["loss"].item()
+        l3 = model(batch, training=True)["loss"].item()
+        lse3 = task._last["row_lse"].clone()
+        task.nprod = 2
+        out = model(batch, training=True)
+        l2 = out["loss"].item()
+        lse2 = task._last["row_lse"].clone()
+        assert task._last["w_planes"] is None and ("W#mixed" in task._planes._cache) and ("W" in task._planes._cache)
+        preds = out["predictions"]                      # lazily, from the 3-product planes
+        out_e = model(batch, training=False, testing=True)  # evaluation ignores nprod = 2
+    assert abs(l3 - ref) < 1e-4 and abs(l2 - ref) < 1e-3 and abs(l2 - l3) < 2e-4
+    assert (lse2 - lse3).abs().max().item() < 1e-4
+    assert calls == [(3, False), (2, False), (3, True)]   # train default, train mixed, evaluation (ranks) back on 3
+    assert preds.shape[1] == CARDS["item_id/list"] and math.isfinite(out_e["loss"].item())
+
+
+def test_sampled_softmax_flow(monkeypatch):
+    D.install(monkeypatch)
+    oracle, model = _pair(sampled=True, max_n_samples=200)
+    B, L, S = 8, 12, 200
+    batch = synth_batch(B, L, CARDS, CONT, seed=3)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    torch.manual_seed(4)
+    raw = torch.multinomial(oracle.dist, 2 * S, replacement=True)
+    task.set_negative_draws(raw)
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws, neg_samples=O.negatives_from_draws(raw, S))
+        task.nprod = 2   # the sampled head keeps the 3-product planes
+        out = model(batch, training=True)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-4
+    assert (out["predictions"] - ref["predictions"]).abs().max().item() < 1e-3
+
+
+def test_bench_recall_agreement_leg(monkeypatch):
+    """bench.py's accuracy leg end to end (product forward = doubles here): ranks of the two sides must agree."""
+    import importlib.util
+    import os
+    D.install(monkeypatch)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = dict(V=2001, De=32, d=64, H=4, NL=1, L=12, B=16, arch="gpt2", masking="clm",
+               side={"category/list": 37}, label="test")
+    model = bench.build_product_model(cfg, torch.device("cpu"))
+    batch = bench.synth_batch(cfg["B"], cfg["L"], cfg, seed=0)
+    res = bench.recall_agreement(cfg, model, batch, batch, n_sample=8)
+    assert res["label_rows"] == cfg["B"] and res["label_rank_max_abs_diff"] <= 1
+    assert res["ours_sample"] == res["oracle_sample"]
