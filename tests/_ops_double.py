@@ -91,6 +91,49 @@ def embed_concat(cats, conts, M, C_width, want_f32, want_planes):
     return (out if want_f32 else None), (make_planes(out) if want_planes else None), err
 
 
+def input_block(feats, M, L, C_width, agg=_lib.AGG_CONCAT, item_feature=-1, ln_eps=1e-5, want_f32=True, want_planes=False):
+    err = torch.zeros(1, dtype=torch.int32)
+    vals = []
+    for f in feats:
+        kind, dim, x = int(f["kind"]), int(f["dim"]), f["input"]
+        per_session = bool(f.get("per_session"))
+
+        def rows(t):  # [B(, ...)] per-session values are repeated for every position of the sequence
+            return t.repeat_interleave(L, dim=0) if per_session else t
+        if kind == _lib.FEAT_CAT:
+            ids = rows(x.reshape(-1).long())
+            table = f["table"].detach().float()
+            bad = (ids < 0) | (ids >= table.shape[0])
+            if bad.any():
+                err[0] = 1
+            v = table[torch.where(bad, torch.zeros_like(ids), ids)]
+        elif kind == _lib.FEAT_CONT:
+            v = rows(x.reshape(-1).float()).unsqueeze(-1)
+        elif kind == _lib.FEAT_SOFT:
+            v = O.soft_embedding(rows(x.reshape(-1).float()), f["soft_w"].detach().reshape(-1, 1).float(),
+                                 f["soft_b"].detach().reshape(-1).float(), f["table"].detach().float())
+        else:
+            v = rows(x.reshape(-1, dim).float())
+        assert v.shape == (M, dim), (v.shape, M, dim)
+        if f.get("ln") is not None:
+            v = F.layer_norm(v, (dim,), f["ln"][0].detach().float(), f["ln"][1].detach().float(), ln_eps)
+        vals.append((int(f.get("col", 0)), dim, v))
+    if agg == _lib.AGG_CONCAT:
+        out = torch.zeros((M, C_width), dtype=torch.float32)
+        for col, dim, v in vals:
+            out[:, col:col + dim] = v
+    elif agg == _lib.AGG_SUM:
+        out = torch.stack([v for _, _, v in vals]).sum(0)
+    else:
+        others = torch.stack([v for i, (_, _, v) in enumerate(vals) if i != item_feature]).sum(0)
+        out = vals[item_feature][2] * others
+    return (out if want_f32 else None), (make_planes(out) if want_planes else None), err
+
+
+def swap_noise(values, keep_mask, u, perm, replacement_prob):
+    return O.stochastic_swap_noise(values, keep_mask, u, perm.long(), replacement_prob)
+
+
 def mask_mlm(item_ids, mode, padding_idx=0, mlm_probability=0.15, u=None):
     ids = item_ids.long()
     B, L = ids.shape
@@ -260,6 +303,20 @@ def combine_shard_lse(parts, t_dev=None):
     return row, (row[:n].sum() / max(n, 1)).reshape(1)
 
 
+def _pad(values, offsets, rows, in_len, pad_len):
+    """padding._pad: ragged (values, offsets) or dense [rows, in_len] -> [rows, pad_len], zeros on the right."""
+    if values.dtype in (torch.int32, torch.int16, torch.uint8, torch.bool):
+        values = values.long()
+    elif values.dtype not in (torch.int64, torch.float32):
+        values = values.float()
+    if offsets is not None:
+        return O.pad_ragged(values, offsets.long(), pad_len)
+    out = torch.zeros((rows, pad_len), dtype=values.dtype)
+    n = min(in_len, pad_len)
+    out[:, :n] = values.reshape(rows, in_len)[:, :n]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------- encoders
 def _xlnet_forward(self, inputs_embeds, **kwargs):
     hf = O.build_hf_xlnet(self.config.d_model, self.config.n_head, self.config.n_layer).eval()
@@ -280,7 +337,7 @@ def _gpt2_forward(self, inputs_embeds, **kwargs):
         return (O.hf_encoder_forward(hf, inputs_embeds.float()),)
 
 
-OPS = dict(split_planes=split_planes, split_planes_mixed=split_planes_mixed, gather_rows_split=gather_rows_split,
+OPS = dict(input_block=input_block, swap_noise=swap_noise, split_planes=split_planes, split_planes_mixed=split_planes_mixed, gather_rows_split=gather_rows_split,
            compact_targets=compact_targets, embed_concat=embed_concat, mask_mlm=mask_mlm, mask_clm=mask_clm, linear=linear,
            label_logit=label_logit, head_softmax_ce=head_softmax_ce, head_logits=head_logits,
            head_logits_mixed=head_logits_mixed, topk=topk, recall_from_ranks=recall_from_ranks,
@@ -294,6 +351,8 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, fn)
     monkeypatch.setattr(block.XLNetEncoder, "forward", _xlnet_forward)
     monkeypatch.setattr(block.GPT2Encoder, "forward", _gpt2_forward)
+    from transformers4rec_b200 import padding
+    monkeypatch.setattr(padding, "_pad", _pad)
 
 
 def install_plain():
