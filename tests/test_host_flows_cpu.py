@@ -130,3 +130,39 @@ def test_bench_recall_agreement_leg(monkeypatch):
     res = bench.recall_agreement(cfg, model, batch, batch, n_sample=8)
     assert res["label_rows"] == cfg["B"] and res["label_rank_max_abs_diff"] <= 1
     assert res["ours_sample"] == res["oracle_sample"]
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(V=2001, De=16, d=32, H=2, NL=1, L=10, B=6, arch="gpt2", masking="clm", label="config3-like",
+         side={"category/list": 37, "brand/list": 11, "shop/list": 53, "price_bin/list": 10, "weekday/list": 8, "hour_bin/list": 7}),
+    dict(V=4001, De=32, d=32, H=2, NL=1, L=50, B=4, arch="xlnet", masking="mlm", sampled=300, label="config5-like"),
+], ids=["config3-like", "config5-like"])
+def test_bench_workload_builders_train_like_the_oracle(monkeypatch, cfg):
+    """bench.py's model builders for BASELINE configs[2] / configs[4] (tiny sizes): the product model they build and
+    the oracle carrying its weights must produce the same training loss."""
+    import importlib.util
+    import os
+    D.install(monkeypatch)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod3", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    model = bench.build_product_model(cfg, torch.device("cpu"))
+    oracle = bench.oracle_with_model_weights(cfg, model)
+    batch = bench.synth_batch(cfg["B"], cfg["L"], cfg, seed=0)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    kw = {}
+    if cfg["masking"] == "mlm":
+        u, draws = mlm_draws(cfg["B"], cfg["L"])
+        model.heads[0].body[0].masking.set_draws(u)
+        kw["draws"] = draws
+    if cfg.get("sampled"):
+        torch.manual_seed(4)
+        raw = torch.multinomial(oracle.dist, 2 * cfg["sampled"], replacement=True)
+        task.set_negative_draws(raw)
+        kw["neg_samples"] = O.negatives_from_draws(raw, cfg["sampled"])
+    with torch.no_grad():
+        ref = oracle(batch, training=True, **kw)["loss"].item()
+        got = model(batch, training=True)["loss"].item()
+    assert abs(got - ref) < 1e-4, (got, ref)
+    assert (task.task_block is not None) == (cfg["De"] != cfg["d"])
