@@ -1,0 +1,27 @@
+"""GPU tests of the two-warp tensor-path attention for 32 < L <= 64 (``attn_mma64_kernel``, BASELINE configs[4]:
+L = 50).  Written after the round's GPU budget was spent: compiles for sm_100a, NOT yet run on hardware, hence
+opt-in twice -- the kernel by ``T4R_ATTN_MMA64=1`` (without it these lengths keep the proven FFMA kernel) and these
+tests by ``T4R_TEST_EXPERIMENTAL=1``.  Same bodies and tolerances as the encoder parity tests of test_gpu_parity.py."""
+import os
+
+import pytest
+
+import test_gpu_parity as GP
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("T4R_TEST_EXPERIMENTAL") != "1",
+                                 reason="attn_mma64_kernel not yet validated on hardware (set T4R_TEST_EXPERIMENTAL=1)")]
+
+
+@pytest.mark.parametrize("d,H,NL,B,L", [(128, 8, 1, 9, 50), (64, 4, 2, 5, 33), (256, 8, 1, 7, 62), (64, 1, 1, 3, 40),
+                                        (256, 4, 1, 4, 47), (128, 8, 2, 130, 50)])
+def test_xlnet_encoder_two_warp_attention(monkeypatch, d, H, NL, B, L):
+    monkeypatch.setenv("T4R_ATTN_MMA64", "1")
+    GP.test_xlnet_encoder_matches_hf(d, H, NL, B, L)
+
+
+@pytest.mark.parametrize("d,H,NL,B,L", [(128, 2, 1, 7, 40), (64, 4, 2, 5, 33), (256, 8, 1, 6, 64), (128, 8, 1, 131, 50),
+                                        (64, 4, 1, 3, 63)])
+def test_gpt2_encoder_two_warp_attention(monkeypatch, d, H, NL, B, L):
+    monkeypatch.setenv("T4R_ATTN_MMA64", "1")
+    GP.test_gpt2_encoder_matches_hf(d, H, NL, B, L)

@@ -96,6 +96,17 @@ def main():
         enc = tr.TransformerBlock(cfg).cuda()
         xin = x.view(B, L, d)
         timeit("xlnet layer (qkv+attn+o+ffn)", lambda: enc(xin))
+    if "attn50" in which:
+        # BASELINE configs[4] shape (L = 50): FFMA attention vs the two-warp tensor-path kernel (T4R_ATTN_MMA64=1)
+        import transformers4rec_b200.torch as tr
+        L50 = 50
+        cfg = tr.XLNetConfig.build(d_model=d, n_head=H, n_layer=1, total_seq_length=L50)
+        enc = tr.TransformerBlock(cfg).cuda()
+        x50 = torch.randn(B, L50, d, device=dev)
+        for flag in ("0", "1"):
+            os.environ["T4R_ATTN_MMA64"] = flag
+            timeit(f"xlnet layer L=50 (T4R_ATTN_MMA64={flag})", lambda: enc(x50))
+        os.environ["T4R_ATTN_MMA64"] = "0"
     if on("embed"):
         # HBM-honest: 8 different id sets (8 x 42 MB of random 1 KB rows > L2) replayed from a CUDA graph
         # so neither L2 residency of the rows nor host launch overhead flatters / hides the kernel

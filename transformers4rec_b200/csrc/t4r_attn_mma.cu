@@ -14,6 +14,7 @@
 // place as the A operand of P V (C-fragment layout == A-fragment layout of two 8-wide tiles);
 // only S2 takes a shared-memory round trip (the relative shift moves data across lanes).
 #include <math.h>
+#include <stdlib.h>
 
 #include "t4r_common.cuh"
 #include "t4r_internal.h"
@@ -336,11 +337,315 @@ static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const 
   return 0;
 }
 
+
+// ============================================================================
+// 32 < L <= 64 (BASELINE configs[4]: L = 50): the same scheme with TWO warps per (session, head).  The 64 x 64 score
+// problem does not fit one warp's registers (S1 alone would be 128 accumulators), so the query rows are split:
+// warp w of a pair owns m tiles 2w, 2w+1 (rows 32w .. 32w+31 of Qaug); K, V, R and the staged Q are shared by the
+// pair through shared memory.  What crossed lanes by shuffle in the one-warp kernel crosses warps through shared
+// memory here: the (r_w_bias . k_j) row of S1 goes to WB[64], the (r_r_bias . R) row of S2 is read from the pair's S2
+// scratch like every other row; named barriers (one id per pair, 64 threads) order the stages.  A block holds one or
+// two pairs (shared-memory footprint decides) which share the head's R planes.  Opt-in (T4R_ATTN_MMA64=1) until it
+// has run on hardware; without it 32 < L <= 64 keeps the FFMA kernel (attn_kernel in t4r_kernels.cu).
+// ============================================================================
+__device__ __forceinline__ void pair_bar(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+template <int DH, bool REL>
+__global__ void __launch_bounds__(128)
+attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride, const __nv_bfloat16* __restrict__ rpl,
+                  int64_t r_plane_stride, const float* __restrict__ rw, const float* __restrict__ rr, int B, int L, int d,
+                  int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride) {
+  constexpr int LDS = DH + 8;
+  constexpr int KT = DH / 16;
+  constexpr int NTC = DH / 8;
+  constexpr int C8 = DH / 8;
+  constexpr int NT = 8;                              // key tiles: 64 keys
+  extern __shared__ __align__(16) uint8_t smem_a[];
+  const int h = blockIdx.y;
+  const int warp = warp_id(), lane = lane_id();
+  const int npairs = blockDim.x >> 6;
+  const int pair = warp >> 1, wp = warp & 1;        // warp pair, warp within the pair
+  const int pt = threadIdx.x & 63;                   // thread within the pair
+  const int g = lane >> 2, t = lane & 3;
+  const int QR = REL ? L + 2 : L;
+  const int RR = 2 * L;
+  const int S2LD = ((2 * L + 7) / 8) * 8 + 1;
+  __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(smem_a);                  // [LDS]
+  __nv_bfloat16* Rs = zrow + LDS;                                                   // [2][RR][LDS]
+  const int pair_elems = 2 * QR * LDS + 4 * L * LDS;
+  const int pair_floats = REL ? QR * S2LD + 64 : 0;
+  uint8_t* pbase = smem_a + (LDS + (REL ? 2 * RR * LDS : 0)) * 2;
+  pbase = smem_a + (((pbase - smem_a) + 15) / 16 * 16);
+  pbase += static_cast<size_t>(pair) * (((pair_elems * 2 + pair_floats * 4) + 15) / 16 * 16);
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(pbase);   // [2][QR][LDS]
+  __nv_bfloat16* Ks = Qs + 2 * QR * LDS;                         // [2][L][LDS]
+  __nv_bfloat16* Vs = Ks + 2 * L * LDS;                          // [2][L][LDS]
+  float* S2s = reinterpret_cast<float*>(Vs + 2 * L * LDS);       // [QR][S2LD]
+  float* WB = S2s + (REL ? QR * S2LD : 0);                       // [64]  (r_w_bias . k_j)
+  const uint32_t zaddr = smem_u32(zrow);
+
+  for (int c = threadIdx.x; c < LDS; c += blockDim.x) zrow[c] = __float2bfloat16_rn(0.f);
+  if (REL) {
+    for (int idx = threadIdx.x; idx < 2 * RR * C8; idx += blockDim.x) {
+      const int pl = idx / (RR * C8), rem = idx % (RR * C8);
+      const int m = rem / C8, c8 = rem % C8;
+      *reinterpret_cast<uint4*>(Rs + (pl * RR + m) * LDS + 8 * c8) =
+          __ldg(reinterpret_cast<const uint4*>(rpl + pl * r_plane_stride + static_cast<int64_t>(m) * d + h * DH + 8 * c8));
+    }
+  }
+  __syncthreads();
+  const float scale = rsqrtf(static_cast<float>(DH));
+  const int b_begin = blockIdx.x * sessions_per_block;
+  const int b_end = min(B, b_begin + sessions_per_block);
+  const int mt0 = 2 * wp;                            // first of this warp's two m tiles
+
+  for (int b = b_begin + pair; b < b_end; b += npairs) {   // same trip count for both warps of a pair
+    pair_bar(pair);                                          // the previous session's tiles are no longer read
+    {
+      const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * L * 3 * d + h * DH;
+      for (int idx = pt; idx < 2 * L * C8; idx += 64) {
+        const int pl = idx / (L * C8), rem = idx % (L * C8);
+        const int i = rem / C8, c8 = rem % C8;
+        const __nv_bfloat16* rowp = base + pl * qkv_plane_stride + static_cast<int64_t>(i) * 3 * d + 8 * c8;
+        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp);
+        cp_async16(smem_u32(Ks + (pl * L + i) * LDS + 8 * c8), rowp + d);
+        cp_async16(smem_u32(Vs + (pl * L + i) * LDS + 8 * c8), rowp + 2 * d);
+      }
+      if (REL) {
+        for (int c = pt; c < DH; c += 64) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(__ldg(rw + h * DH + c), hi, lo);
+          Qs[(0 * QR + L) * LDS + c] = hi;
+          Qs[(1 * QR + L) * LDS + c] = lo;
+          split_bf16(__ldg(rr + h * DH + c), hi, lo);
+          Qs[(0 * QR + L + 1) * LDS + c] = hi;
+          Qs[(1 * QR + L + 1) * LDS + c] = lo;
+        }
+      }
+      cp_async_wait_all();
+    }
+    pair_bar(pair);
+
+    // ---- A fragments of this warp's 32 rows of Qaug
+    uint32_t aq[2][2][KT][4];  // [plane][local m tile][k tile]
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          const int row = (mt0 + ml) * 16 + (lane & 15);
+          const int col = kt * 16 + (lane >> 4) * 8;
+          ldsm_x4(aq[pl][ml][kt], row < QR ? smem_u32(Qs + (pl * QR + row) * LDS + col) : zaddr);
+        }
+
+    // ---- S1 = Qaug K^T (this warp's rows x 64 keys)
+    float s1[2][NT][4];
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s1[ml][nt][e] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt) {
+        uint32_t bh[2], bl[2];
+        const int row = nt * 8 + (lane & 7);
+        const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x2(bh, row < L ? smem_u32(Ks + row * LDS + col) : zaddr);
+        ldsm_x2(bl, row < L ? smem_u32(Ks + (L + row) * LDS + col) : zaddr);
+#pragma unroll
+        for (int ml = 0; ml < 2; ++ml) mma3(s1[ml][nt], aq[0][ml][kt], aq[1][ml][kt], bh, bl);
+      }
+
+    if (REL) {
+      // ---- S2 = Qaug R^T for this warp's rows -> the pair's scratch
+      const int nt2_max = (2 * L + 7) / 8;
+#pragma unroll 1
+      for (int nt2 = 0; nt2 < nt2_max; ++nt2) {
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          uint32_t bh[2], bl[2];
+          const int row = nt2 * 8 + (lane & 7);
+          const int col = kt * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x2(bh, row < RR ? smem_u32(Rs + row * LDS + col) : zaddr);
+          ldsm_x2(bl, row < RR ? smem_u32(Rs + (RR + row) * LDS + col) : zaddr);
+#pragma unroll
+          for (int ml = 0; ml < 2; ++ml) mma3(acc[ml], aq[0][ml][kt], aq[1][ml][kt], bh, bl);
+        }
+#pragma unroll
+        for (int ml = 0; ml < 2; ++ml) {
+          const int col = nt2 * 8 + 2 * t;
+          const int r0 = (mt0 + ml) * 16 + g, r1 = r0 + 8;
+          if (r0 < QR) { S2s[r0 * S2LD + col] = acc[ml][0]; S2s[r0 * S2LD + col + 1] = acc[ml][1]; }
+          if (r1 < QR) { S2s[r1 * S2LD + col] = acc[ml][2]; S2s[r1 * S2LD + col + 1] = acc[ml][3]; }
+        }
+      }
+      // ---- row L of S1 (r_w_bias . k_j) -> WB, written by the warp and lanes that hold it
+      const int mtL = L >> 4, rL = L & 15;
+      if ((mtL >> 1) == wp && g == (rL & 7)) {
+        const int mlL = mtL & 1;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float v0 = (mlL == 0) ? ((rL < 8) ? s1[0][nt][0] : s1[0][nt][2]) : ((rL < 8) ? s1[1][nt][0] : s1[1][nt][2]);
+          const float v1 = (mlL == 0) ? ((rL < 8) ? s1[0][nt][1] : s1[0][nt][3]) : ((rL < 8) ? s1[1][nt][1] : s1[1][nt][3]);
+          WB[nt * 8 + 2 * t] = v0;
+          WB[nt * 8 + 2 * t + 1] = v1;
+        }
+      }
+      pair_bar(pair);   // both warps' S2 rows (incl. row L + 1) and WB are visible
+    }
+
+    // ---- scores -> probabilities (in place in s1)
+    float rmax[2][2], rsum[2][2];
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) rmax[ml][hf] = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = (mt0 + ml) * 16 + g + ((e >> 1) << 3);
+          const int j = nt * 8 + 2 * t + (e & 1);
+          float v = s1[ml][nt][e];
+          if (REL) {
+            const int ii = i < L ? i : 0;
+            const int jj = j < L ? j : 0;
+            const int m = jj + L - ii;
+            v += WB[j] + S2s[ii * S2LD + m] + S2s[(L + 1) * S2LD + m];
+          }
+          v *= scale;
+          if (j >= L || (!REL && j > i)) v = -INFINITY;
+          s1[ml][nt][e] = v;
+          rmax[ml][e >> 1] = fmaxf(rmax[ml][e >> 1], v);
+        }
+    }
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float m = rmax[ml][hf];
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        rmax[ml][hf] = m;
+        rsum[ml][hf] = 0.f;
+      }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = s1[ml][nt][e];
+          const float p = (v == -INFINITY) ? 0.f : expf(v - rmax[ml][e >> 1]);
+          s1[ml][nt][e] = p;
+          rsum[ml][e >> 1] += p;
+        }
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float sm = rsum[ml][hf];
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+        rsum[ml][hf] = (sm > 0.f) ? 1.f / sm : 0.f;
+      }
+
+    // ---- O = P V (k = 64 keys = 4 k tiles)
+    float o[2][NTC][4];
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int nc = 0; nc < NTC; ++nc)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[ml][nc][e] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      uint32_t ph[2][4], plo[2][4];
+#pragma unroll
+      for (int ml = 0; ml < 2; ++ml) {
+        split_pair(s1[ml][2 * kt][0], s1[ml][2 * kt][1], ph[ml][0], plo[ml][0]);
+        split_pair(s1[ml][2 * kt][2], s1[ml][2 * kt][3], ph[ml][1], plo[ml][1]);
+        split_pair(s1[ml][2 * kt + 1][0], s1[ml][2 * kt + 1][1], ph[ml][2], plo[ml][2]);
+        split_pair(s1[ml][2 * kt + 1][2], s1[ml][2 * kt + 1][3], ph[ml][3], plo[ml][3]);
+      }
+#pragma unroll
+      for (int nc = 0; nc < NTC; ++nc) {
+        uint32_t bh[2], bl[2];
+        const int row = kt * 16 + (lane & 15);
+        ldsm_x2_trans(bh, row < L ? smem_u32(Vs + row * LDS + nc * 8) : zaddr);
+        ldsm_x2_trans(bl, row < L ? smem_u32(Vs + (L + row) * LDS + nc * 8) : zaddr);
+#pragma unroll
+        for (int ml = 0; ml < 2; ++ml) mma3(o[ml][nc], ph[ml], plo[ml], bh, bl);
+      }
+    }
+
+    // ---- normalise, split, store (rows < L)
+#pragma unroll
+    for (int ml = 0; ml < 2; ++ml)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int i = (mt0 + ml) * 16 + g + hf * 8;
+        if (i < L) {
+          const float inv = rsum[ml][hf];
+          __nv_bfloat16* hi = out_planes + (static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
+#pragma unroll
+          for (int nc = 0; nc < NTC; ++nc) {
+            uint32_t wh, wl;
+            split_pair(o[ml][nc][2 * hf] * inv, o[ml][nc][2 * hf + 1] * inv, wh, wl);
+            *reinterpret_cast<uint32_t*>(hi + nc * 8) = wh;
+            *reinterpret_cast<uint32_t*>(hi + out_plane_stride + nc * 8) = wl;
+          }
+        }
+      }
+  }
+}
+
+template <int DH, bool REL>
+static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const __nv_bfloat16* rpl, int64_t r_ps,
+                                  const float* rw, const float* rr, int B, int L, int d, int H,
+                                  __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s) {
+  constexpr int LDS = DH + 8;
+  const int QR = REL ? L + 2 : L;
+  const int S2LD = ((2 * L + 7) / 8) * 8 + 1;
+  const size_t per_pair = ((static_cast<size_t>(2 * QR * LDS + 4 * L * LDS) * 2 + (REL ? (QR * S2LD + 64) * 4 : 0)) + 15) / 16 * 16;
+  const size_t shared_part = (static_cast<size_t>(LDS + (REL ? 2 * 2 * L * LDS : 0)) * 2 + 15) / 16 * 16;
+  int pairs = 2;
+  if (shared_part + pairs * per_pair > 200 * 1024) pairs = 1;
+  const size_t smem = shared_part + pairs * per_pair;
+  T4R_REQUIRE(smem <= 200 * 1024, "attn_mma64: shared memory %zu too large", smem);
+  auto kern = attn_mma64_kernel<DH, REL>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  int spb = 2 * pairs;
+  while (spb > pairs && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
+  dim3 grid((B + spb - 1) / spb, H);
+  kern<<<grid, pairs * 64, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps);
+  T4R_LAUNCH_CHECK("attn_mma64_kernel");
+  return 0;
+}
+
+// one warp per (session, head) up to 32 (augmented) query rows; with T4R_ATTN_MMA64=1 (opt-in: not yet run on
+// hardware) two warps per (session, head) up to 64
+static bool attn_mma64_enabled() {
+  const char* e = getenv("T4R_ATTN_MMA64");
+  return e && atoi(e) != 0;
+}
 bool attn_mma_supported(int L, int d, int H, bool rel) {
   if (d % H) return false;
   const int dh = d / H;
   if (dh != 16 && dh != 32 && dh != 64) return false;
-  return rel ? (L + 2 <= 32) : (L <= 32);
+  const int rows = rel ? L + 2 : L;
+  return rows <= 32 || (rows <= 64 && attn_mma64_enabled());
 }
 
 int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
@@ -348,6 +653,18 @@ int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane
                     __nv_bfloat16* out_planes, int64_t out_plane_stride, cudaStream_t s) {
   T4R_REQUIRE(attn_mma_supported(L, d, H, rel), "attn_mma: unsupported shape L=%d d=%d H=%d", L, d, H);
   const int dh = d / H;
+  if ((rel ? L + 2 : L) > 32) {
+#define T4R_AM64(DHV)                                                                                                \
+  if (dh == DHV) {                                                                                                   \
+    if (rel) return launch_attn_mma64_inst<DHV, true>(qkv_planes, qkv_plane_stride, r_planes, r_plane_stride, rw, rr, \
+                                                      B, L, d, H, out_planes, out_plane_stride, s);                   \
+    return launch_attn_mma64_inst<DHV, false>(qkv_planes, qkv_plane_stride, nullptr, 0, nullptr, nullptr, B, L, d, H, \
+                                              out_planes, out_plane_stride, s);                                       \
+  }
+    T4R_AM64(16) T4R_AM64(32) T4R_AM64(64)
+#undef T4R_AM64
+    return T4R_ERR_UNSUPPORTED;
+  }
 #define T4R_AM(DHV)                                                                                                  \
   if (dh == DHV) {                                                                                                   \
     if (rel) return launch_attn_mma_inst<DHV, true>(qkv_planes, qkv_plane_stride, r_planes, r_plane_stride, rw, rr,   \
