@@ -327,3 +327,19 @@ def test_bench_recall_leg_helpers_on_cpu():
         batch = bench.synth_batch(6, cfg["L"], cfg, seed=0)
         ranks = bench.oracle_label_ranks(oracle, batch)
         assert ranks.shape == (6,) and int(ranks.min()) >= 0 and int(ranks.max()) < cfg["V"]
+
+
+def test_attention_kernels_index_algebra_emulated():
+    """tools/emu_attn_mma.py: lane-level emulation (ldmatrix / mma.sync fragment layouts) of the index algebra of the
+    tensor-path attention kernels, transcribed from the CUDA source.  The one-warp kernel (proven on hardware)
+    validates the emulator; the two-warp kernel for 32 < L <= 64 is held to the same plain-formula reference."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "emu_attn_mma", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "emu_attn_mma.py"))
+    emu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(emu)
+    assert emu.check(20, 16, True, two_warp=False) < 1e-9
+    assert emu.check(9, 16, False, two_warp=False) < 1e-9
+    for L, DH, rel in [(50, 16, True), (33, 16, True), (62, 16, True), (64, 16, False)]:
+        assert emu.check(L, DH, rel, two_warp=True) < 1e-9, (L, DH, rel)
