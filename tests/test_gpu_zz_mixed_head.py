@@ -123,9 +123,11 @@ def test_resident_head_kernel_matches_the_default_kernel(ops, monkeypatch, nprod
     monkeypatch.setenv("T4R_HEAD_RESIDENT", "0")
     a = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=True, nprod=nprod)
     monkeypatch.setenv("T4R_HEAD_RESIDENT", "1")
-    b = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=True, nprod=nprod)
-    assert (a["row_lse"] - b["row_lse"]).abs().max().item() < 1e-5
-    assert abs(a["loss"].item() - b["loss"].item()) < 1e-6
+    b = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=True, nprod=nprod)    # general epilogue (ranks)
+    c = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=False, nprod=nprod)   # packed-pair fast path
+    for r in (b, c):
+        assert (a["row_lse"] - r["row_lse"]).abs().max().item() < 1e-5
+        assert abs(a["loss"].item() - r["loss"].item()) < 1e-6
     assert torch.equal(a["row_rank"], b["row_rank"])
 
 

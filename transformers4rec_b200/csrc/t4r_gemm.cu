@@ -1044,6 +1044,50 @@ __device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev&
   const bool want_z = (ep.part_z != nullptr);
   const bool want_rank = (ep.row_rank != nullptr);
   const bool full_tile = (n0 + COLS <= p.N);
+  // Fast path of the training full softmax (no logQ bias, no hit removal, no ranks, no label smoothing, whole tile
+  // inside V): packed fp32 pairs (fmul2 / ffma2 / fadd2) halve the FMA-pipe instructions per logit and the row scale
+  // of the 2-unit product rides in the exponent's scale factor instead of costing a multiply per logit.  With K = 64
+  // (config 3) or nprod = 2 the main loop is short enough for this epilogue to be on the critical path.
+  if (full_tile && !ep.col_bias && !ep.col_ids && !want_rank && !want_z) {
+    const float scale2r = scale2 * st.row_scale;  // > 0: power-of-two row scale
+#pragma unroll 1
+    for (int c = 0; c < COLS / 32; ++c) {
+      float v[32];
+      tmem_ld<32>(taddr + c * 32, v);
+      if (!row_ok) continue;
+      float2* v2 = reinterpret_cast<float2*>(v);
+      if (ep.col_scale) {
+        const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + n0 + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 cs = __ldg(c4 + j);
+          v2[2 * j] = __fmul2_rn(v2[2 * j], make_float2(cs.x, cs.y));
+          v2[2 * j + 1] = __fmul2_rn(v2[2 * j + 1], make_float2(cs.z, cs.w));
+        }
+      }
+      float mx[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+      for (int j = 4; j < 32; j += 4) {
+        mx[0] = fmaxf(mx[0], v[j]); mx[1] = fmaxf(mx[1], v[j + 1]);
+        mx[2] = fmaxf(mx[2], v[j + 2]); mx[3] = fmaxf(mx[3], v[j + 3]);
+      }
+      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale2r;
+      const float m_new = fmaxf(st.m_run, cmax);
+      if (m_new > -INFINITY) {
+        const float2 sc = make_float2(scale2r, scale2r), nm = make_float2(-m_new, -m_new);
+        float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float2 a0 = __ffma2_rn(v2[j], sc, nm), a1 = __ffma2_rn(v2[j + 1], sc, nm);
+          acc2[0] = __fadd2_rn(acc2[0], make_float2(fast_exp2(a0.x), fast_exp2(a0.y)));
+          acc2[1] = __fadd2_rn(acc2[1], make_float2(fast_exp2(a1.x), fast_exp2(a1.y)));
+        }
+        st.s_run = st.s_run * fast_exp2(st.m_run - m_new) + ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y));
+        st.m_run = m_new;
+      }
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c = 0; c < COLS / 32; ++c) {
     float v[32];
