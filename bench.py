@@ -187,7 +187,13 @@ def _oracle_step_seconds(oracle, cfg, B_cpu, steps, warmup):
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out = oracle(batch, training=True, draws=draws)
+            kw = {}
+            if getattr(oracle, "sampled_softmax", False):
+                # the reference draws its negatives inside the forward (model/prediction_task.py:843-845): timed
+                import t4r_oracle as O
+                raw = torch.multinomial(oracle.dist, 2 * oracle.max_n_samples, replacement=True)
+                kw["neg_samples"] = O.negatives_from_draws(raw, oracle.max_n_samples)
+            out = oracle(batch, training=True, draws=draws, **kw)
             float(out["loss"])
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)

@@ -343,3 +343,16 @@ def test_attention_kernels_index_algebra_emulated():
     assert emu.check(9, 16, False, two_warp=False) < 1e-9
     for L, DH, rel in [(50, 16, True), (33, 16, True), (62, 16, True), (64, 16, False)]:
         assert emu.check(L, DH, rel, two_warp=True) < 1e-9, (L, DH, rel)
+
+
+def test_bench_cpu_arm_handles_the_sampled_softmax_workload():
+    """time_oracle_cpu on a config5-like (sampled softmax) shape: negatives are drawn inside the timed step."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod4", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = dict(V=4001, De=32, d=32, H=2, NL=1, L=50, B=4, arch="xlnet", masking="mlm", sampled=300, label="t")
+    v, med, threads, b_run = bench.time_oracle_cpu(cfg, 4, 1, 0, budget_s=0.01)
+    assert v > 0 and b_run % 4 == 0 and threads >= 1
