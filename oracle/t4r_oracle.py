@@ -284,6 +284,102 @@ def clm_apply_mask_to_inputs(x, mask_schema, masked_item_embedding, training=Fal
     return torch.where(mask_schema.unsqueeze(-1).bool(), pos_emb_inp, masked_item_embedding.to(pos_emb_inp.dtype))
 
 
+def randint_from_uniform(u: float, n: int) -> int:
+    """Stand-in for ``torch.randint(n, (1,)).item()``: min(floor(u * n), n - 1), in double like pick_kth_set."""
+    return min(int(math.floor(float(u) * n)), n - 1)
+
+
+def plm_context_lengths(max_span_length: int, plm_probability: float):
+    """masking.py:608: ``int(span_length / plm_probability)`` for span_length = 0..max (index 0 unused)."""
+    return [0] + [int(sp / plm_probability) for sp in range(1, max_span_length + 1)]
+
+
+def plm_compute_masked_targets(item_ids: torch.Tensor, training: bool = False, padding_idx: int = 0,
+                               eval_on_last_item_seq_only: bool = True, plm_probability: float = 1 / 6,
+                               max_span_length: int = 5, permute_all: bool = False, draws: Optional[dict] = None):
+    """masking.py:548-727 (PermutationLanguageModeling._compute_masked_targets_extended).
+
+    Returns (mask_labels bool [B,L], labels i64 [B,L], target_mapping f32 [B,L,L], perm_mask [B,L,L] (f32 in
+    training, i64 in evaluation, like the reference), info) where ``info`` records how many draws each session
+    consumed (the golden generator needs it to line the upstream code's sequential draws up with these
+    per-session ones).
+
+    Draws (training; the reference calls torch.randint twice per loop iteration, torch.multinomial and
+    torch.randperm): ``u_span`` / ``u_start`` [B, NMAX] uniforms for the span length / start offset of iteration
+    n of session b (span = 1 + floor(u*max_span), start = cur_len + floor(u*(context - span + 1))), ``u_force``
+    [B] (one position when nothing got masked), ``u_unmask`` [B] (one label removed when everything is a label),
+    ``perm`` [B, L] the factorisation order (a permutation of 0..L-1 per session)."""
+    B, L = item_ids.shape
+    labels = torch.full(item_ids.shape, padding_idx, dtype=item_ids.dtype)
+    non_padded_mask = item_ids != padding_idx
+    rows_ids = torch.arange(B, dtype=torch.long)
+    mask_labels = torch.zeros(labels.shape, dtype=torch.bool)
+    info = {"n_iter": [0] * B, "forced": [False] * B}
+    if training:
+        target_mapping = torch.zeros((B, L, L), dtype=torch.float32)
+        perm_mask = torch.zeros((B, L, L), dtype=torch.float32)
+        ctx = plm_context_lengths(max_span_length, plm_probability)
+        if permute_all:
+            mask_labels = non_padded_mask.clone()
+        else:
+            for i in range(B):
+                cur_len, n = 0, 0
+                max_len = int(non_padded_mask[i].sum())
+                while cur_len < max_len:
+                    span_length = 1 + randint_from_uniform(draws["u_span"][i, n], max_span_length)
+                    context_length = ctx[span_length]
+                    start_index = cur_len + randint_from_uniform(draws["u_start"][i, n], context_length - span_length + 1)
+                    if start_index < max_len:
+                        mask_labels[i, start_index: start_index + span_length] = True
+                    cur_len += context_length
+                    n += 1
+                info["n_iter"][i] = n
+                if mask_labels[i].sum() == 0:
+                    k = pick_kth_set(non_padded_mask[i: i + 1], draws["u_force"][i: i + 1])[0]
+                    mask_labels[i, k] = bool(item_ids[i, k] != 0)  # the reference assigns the item id into a bool tensor
+                    info["forced"][i] = True
+                target_mapping[i] = torch.eye(L)
+        labels = torch.where(mask_labels, item_ids, torch.full_like(item_ids, padding_idx))
+        sequences_with_only_labels = mask_labels.sum(dim=1) == non_padded_mask.sum(dim=1)
+        sampled_labels_to_unmask = pick_kth_set(mask_labels, draws["u_unmask"])
+        labels_to_unmask = torch.masked_select(sampled_labels_to_unmask, sequences_with_only_labels)
+        rows_to_unmask = torch.masked_select(rows_ids, sequences_with_only_labels)
+        labels[rows_to_unmask, labels_to_unmask] = padding_idx
+        mask_labels = labels != padding_idx
+        for i in range(B):
+            perm_index = draws["perm"][i].long().clone()          # arange(L)[randperm(L)]
+            perm_index.masked_fill_(~mask_labels[i], -1)
+            perm_mask[i] = ((perm_index.reshape((L, 1)) <= perm_index.reshape((1, L))) & mask_labels[i]).float()
+    else:
+        causal = torch.triu(torch.ones([L, L]), diagonal=1)
+        if eval_on_last_item_seq_only:
+            last_item_sessions = non_padded_mask.sum(dim=1) - 1
+            labels[rows_ids, last_item_sessions] = item_ids[rows_ids, last_item_sessions]
+            mask_labels = labels != padding_idx
+            perm_mask = torch.zeros((B, L, L), dtype=torch.float32)
+            perm_mask[rows_ids, :, last_item_sessions] = 1
+            perm_mask = ((causal.expand((B, L, L)) + perm_mask) > 0).long()
+            target_mapping = torch.diag(torch.ones(L, dtype=torch.float32)).expand((B, L, L))
+        else:
+            mask_labels, labels = predict_all(item_ids, padding_idx)
+            target_mapping = F.one_hot(torch.arange(0, L, dtype=torch.long), num_classes=L).expand((B, L, L))
+            perm_mask = ((causal.expand((B, L, L)) + torch.zeros((B, L, L))) > 0).long()
+    return mask_labels, labels, target_mapping, perm_mask, info
+
+
+def plm_apply_mask_to_inputs(x, mask_schema, masked_item_embedding, training=False, testing=False):
+    """masking.py:155-180 (the base-class rule PLM inherits): nothing at inference."""
+    if not training and not testing:
+        return x
+    return torch.where(mask_schema.unsqueeze(-1).bool(), masked_item_embedding.to(x.dtype), x)
+
+
+def hf_encoder_forward_plm(model, x: torch.Tensor, perm_mask: torch.Tensor, target_mapping: torch.Tensor) -> torch.Tensor:
+    """block/transformer.py:179-199 with masking.transformer_arguments = {target_mapping, perm_mask} (masking.py:739-740):
+    HF returns the query stream g (one row per target position) as output[0]."""
+    return model(inputs_embeds=x, perm_mask=perm_mask.float(), target_mapping=target_mapping.float())[0]
+
+
 # --------------------------------------------------------------------------- #
 # encoders: (1) the installed HF models built with the reference's kwargs,
 #           (2) a literal restatement of the math (SURVEY Appendix A) used as
