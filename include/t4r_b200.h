@@ -150,6 +150,27 @@ int t4r_mask_mlm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int
 int t4r_mask_clm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode, uint8_t* mask_schema,
                  int64_t* masked_targets, uint8_t* row_code, void* stream);
 
+/* Permutation Language Modeling (XLNet): PermutationLanguageModeling._compute_masked_targets_extended
+ * masking.py:548-727.  One thread per session (the reference loops over the sessions in python).  Outputs:
+ * mask_schema / masked_targets [B, L] and perm_mask [B, L, L] bytes (1 = query i may NOT attend key j);
+ * target_mapping is the identity in every mode the reference builds it in and is not materialised.
+ * Training consumes explicit draws, per session: u_span / u_start [B, L] (iteration n of the span loop:
+ * span = 1 + floor(u_span * max_span), start = cur + floor(u_start * (ctx - span + 1))), u_force / u_unmask [B],
+ * perm [B, L] int32 = the factorisation order (torch.randperm(L) per session).  ctx_len[span] (HOST array,
+ * max_span + 1 entries) = int(span / plm_probability) as the reference computes it.  L <= 64, max_span <= 15.
+ * t4r_debug_mask_plm_host is the same code compiled for the host (HOST pointers) -- test infrastructure. */
+#define T4R_PLM_TRAIN 0
+#define T4R_PLM_EVAL_LAST 1
+#define T4R_PLM_EVAL_ALL 2
+int t4r_mask_plm(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode, int max_span,
+                 const int32_t* ctx_len /*host*/, const float* u_span, const float* u_start, const float* u_force,
+                 const float* u_unmask, const int32_t* perm, uint8_t* mask_schema, int64_t* masked_targets,
+                 uint8_t* perm_mask, void* stream);
+int t4r_debug_mask_plm_host(const int64_t* item_ids, int B, int L, int64_t padding_idx, int mode, int max_span,
+                            const int32_t* ctx_len, const float* u_span, const float* u_start, const float* u_force,
+                            const float* u_unmask, const int32_t* perm, uint8_t* mask_schema, int64_t* masked_targets,
+                            uint8_t* perm_mask);
+
 /* Row compaction of label positions (row-major order), replaces the
  * masked_select pair at model/prediction_task.py:436-443,472-479.
  * tgt_rows[i] = flat index (b*L+l) of the i-th non-pad label, tgt_labels[i] its id,
@@ -301,6 +322,17 @@ typedef struct {
   const void* w2_planes;     /* bf16 [2, d, 4d] = mlp.c_proj.weight^T                     */
   const float* b2;
 } t4r_gpt2_layer;
+/* XLNet two-stream forward for Permutation Language Modeling (HF XLNetModel.forward with perm_mask and
+ * target_mapping = identity, as block/transformer.py:179-199 passes masking.transformer_arguments): the caller
+ * stacks the content stream h (the masked input embeddings) and the query stream g (mask_emb in every row) into
+ * x_f32 [2 B L, d]; both streams go through every layer's GEMMs together, attention reads keys / values from the
+ * h rows for both and applies perm_mask [B, L, L] bytes (h: except on the diagonal).  out_f32 [2 B L, d]: the g
+ * rows (second half) are what HF returns as output[0].  Workspace: t4r_xlnet_encoder_workspace_bytes(2 B, ...).
+ * Needs the tensor-path attention (L + 2 <= 32, or <= 64 with T4R_ATTN_MMA64=1). */
+int t4r_xlnet_encoder_plm_fwd(const t4r_xlnet_layer* layers /*host*/, int n_layer, int B, int L, int d, int n_head,
+                              float ln_eps, const float* x_f32, const uint8_t* perm_mask, float* out_f32,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 size_t t4r_gpt2_encoder_workspace_bytes(int B, int L, int d, int n_head);
 int t4r_gpt2_encoder_fwd(const t4r_gpt2_layer* layers /*host*/, int n_layer, int B, int L, int d, int n_head,
                          float ln_eps, const float* wpe /*[n_positions, d]*/, const float* lnf_gamma,

@@ -356,3 +356,52 @@ def test_bench_cpu_arm_handles_the_sampled_softmax_workload():
     cfg = dict(V=4001, De=32, d=32, H=2, NL=1, L=50, B=4, arch="xlnet", masking="mlm", sampled=300, label="t")
     v, med, threads, b_run = bench.time_oracle_cpu(cfg, 4, 1, 0, budget_s=0.01)
     assert v > 0 and b_run % 4 == 0 and threads >= 1
+
+
+# --------------------------------------------------------------------------- #
+# Permutation Language Modeling masks: the kernel's per-session code (host twin) vs the upstream code's outputs
+# (tests/golden/reference_vectors_plm.pt) and vs the oracle on a larger seeded batch, bit-exact
+# --------------------------------------------------------------------------- #
+def _plm_modes(_lib):
+    return (("train", _lib.PLM_TRAIN, True, {}), ("eval", _lib.PLM_EVAL_LAST, False, {}))
+
+
+@pytest.mark.parametrize("case", ["default", "p0.5_span3", "evalall"])
+def test_plm_mask_host_twin_matches_upstream_vectors(case):
+    import os
+    from transformers4rec_b200 import _lib, ops
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_plm.pt"), weights_only=False)
+    ids, c = gold["item_ids"], gold["cases"][case]
+    kw = dict(c["kwargs"])
+    eval_all = kw.pop("eval_on_last_item_seq_only", True) is False
+    span, prob = kw.get("max_span_length", 5), kw.get("plm_probability", 1 / 6)
+    m, l, pm = ops.mask_plm_host(ids, _lib.PLM_TRAIN, 0, span, prob, c["draws"])
+    ref = c["train"]
+    assert torch.equal(m, ref["mask_schema"]) and torch.equal(l, ref["masked_targets"]) and torch.equal(pm, ref["perm_mask"])
+    m, l, pm = ops.mask_plm_host(ids, _lib.PLM_EVAL_ALL if eval_all else _lib.PLM_EVAL_LAST)
+    ref = c["eval"]
+    assert torch.equal(m, ref["mask_schema"]) and torch.equal(l, ref["masked_targets"]) and torch.equal(pm, ref["perm_mask"])
+    assert bool((ref["target_mapping"] == torch.eye(ids.shape[1], dtype=torch.uint8)).all())  # why it is not materialised
+
+
+def test_plm_mask_host_twin_matches_oracle_large():
+    import t4r_oracle as O
+    from transformers4rec_b200 import _lib, ops
+    g = torch.Generator().manual_seed(77)
+    B, L = 700, 20
+    lens = torch.randint(0, L + 1, (B,), generator=g)      # incl. empty sessions
+    ids = torch.randint(1, 1000, (B, L), generator=g)
+    ids = torch.where(torch.arange(L)[None] < lens[:, None], ids, torch.zeros_like(ids))
+    draws = {"u_span": torch.rand((B, L), generator=g), "u_start": torch.rand((B, L), generator=g),
+             "u_force": torch.rand((B,), generator=g), "u_unmask": torch.rand((B,), generator=g),
+             "perm": torch.stack([torch.randperm(L, generator=g) for _ in range(B)])}
+    for span, prob in ((5, 1 / 6), (2, 0.3), (7, 0.9)):
+        m, l, pm = ops.mask_plm_host(ids, _lib.PLM_TRAIN, 0, span, prob, draws)
+        rm, rl, _, rpm, _ = O.plm_compute_masked_targets(ids, True, draws=draws, max_span_length=span, plm_probability=prob)
+        assert torch.equal(m, rm) and torch.equal(l, rl) and torch.equal(pm, rpm.to(torch.uint8)), (span, prob)
+    nonempty = lens > 0   # (an empty session makes the reference index column -1; not meaningful input)
+    for mode, last in ((_lib.PLM_EVAL_LAST, True), (_lib.PLM_EVAL_ALL, False)):
+        m, l, pm = ops.mask_plm_host(ids, mode)
+        rm, rl, _, rpm, _ = O.plm_compute_masked_targets(ids, False, eval_on_last_item_seq_only=last)
+        assert torch.equal(m, rm) and torch.equal(l, rl) and torch.equal(pm, rpm.to(torch.uint8))
+        assert nonempty.any()

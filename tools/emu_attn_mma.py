@@ -55,13 +55,16 @@ def mma(c, a, b):
         c[lane] += (C[g, 2 * t], C[g, 2 * t + 1], C[g + 8, 2 * t], C[g + 8, 2 * t + 1])
 
 
-def reference(q, k, v, R, rw, rr, rel):
+def reference(q, k, v, R, rw, rr, rel, mask=None, stream=0):
+    """mask / stream: XLNet two-stream attention (HF `score - 1e30 * mask`; the content stream h ignores the diagonal)."""
     L, dh = q.shape
     s = np.full((L, L), -np.inf)
     for i in range(L):
         for j in range(L):
             if rel:
                 s[i, j] = ((q[i] + rw) @ k[j] + (q[i] + rr) @ R[j + L - i]) / math.sqrt(dh)
+                if mask is not None and mask[i, j] and not (stream == 0 and i == j):
+                    s[i, j] = -1e30
             elif j <= i:
                 s[i, j] = q[i] @ k[j] / math.sqrt(dh)
     p = np.exp(s - s.max(1, keepdims=True))
@@ -69,7 +72,7 @@ def reference(q, k, v, R, rw, rr, rel):
     return p @ v
 
 
-def run(L, DH, rel, q, k, v, R, rw, rr, two_warp):
+def run(L, DH, rel, q, k, v, R, rw, rr, two_warp, mask=None, stream=0):
     """Transcription of attn_mma_kernel (two_warp=False) / attn_mma64_kernel (two_warp=True), hi plane only."""
     LDS, KT, NTC = DH + 8, DH // 16, DH // 8
     NT = 8 if two_warp else 4
@@ -178,6 +181,9 @@ def run(L, DH, rel, q, k, v, R, rw, rr, two_warp):
                     m = jj + L - ii
                     val += (WB[j] if two_warp else wb[lane, e & 1]) + S2[ii, m] + S2[L + 1, m]
                 val *= scale
+                if mask is not None:   # MASKED instantiation
+                    if i < L and j < L and not (stream == 0 and i == j) and mask[i, j]:
+                        val = -1e30
                 if j >= L or (not rel and j > i):
                     val = -np.inf
                 s1[ml, nt, lane, e] = val
@@ -223,14 +229,26 @@ def run(L, DH, rel, q, k, v, R, rw, rr, two_warp):
     return out
 
 
-def check(L, DH, rel, two_warp, seed=0):
+def check(L, DH, rel, two_warp, seed=0, masked=False):
+    """masked: the two-stream (PLM) instantiation -- random permutation-style mask incl. a fully masked row; both the
+    content stream (queries = the keys' own rows, diagonal exempt) and the query stream (separate query rows)."""
     rng = np.random.default_rng(seed)
     q, k, v = (rng.standard_normal((L, DH)) for _ in range(3))
     R = rng.standard_normal((2 * L, DH))
     rw, rr = rng.standard_normal(DH), rng.standard_normal(DH)
-    got = run(L, DH, rel, q, k, v, R, rw, rr, two_warp)
-    ref = reference(q, k, v, R, rw, rr, rel)
-    return float(np.abs(got - ref).max())
+    if not masked:
+        got = run(L, DH, rel, q, k, v, R, rw, rr, two_warp)
+        ref = reference(q, k, v, R, rw, rr, rel)
+        return float(np.abs(got - ref).max())
+    mask = rng.random((L, L)) < 0.4
+    mask[min(3, L - 1), :] = True                      # a query that sees nothing: uniform attention (HF's -1e30 rule)
+    qg = rng.standard_normal((L, DH))
+    err = 0.0
+    for stream, qs in ((0, q), (1, qg)):
+        got = run(L, DH, rel, qs, k, v, R, rw, rr, two_warp, mask=mask, stream=stream)
+        ref = reference(qs, k, v, R, rw, rr, rel, mask=mask, stream=stream)
+        err = max(err, float(np.abs(got - ref).max()))
+    return err
 
 
 if __name__ == "__main__":
@@ -244,5 +262,9 @@ if __name__ == "__main__":
                        (64, 32, False), (33, 16, False), (50, 64, False)]:
         e = check(L, DH, rel, two_warp=True)
         print(f"two-warp kernel  L={L:2d} dh={DH:2d} rel={int(rel)}: max err {e:.2e}")
+        assert e < 1e-9
+    for L, DH, two in [(20, 32, False), (30, 16, False), (50, 32, True), (62, 16, True)]:
+        e = check(L, DH, True, two_warp=two, masked=True)
+        print(f"two-stream (PLM) {'two' if two else 'one'}-warp  L={L:2d} dh={DH:2d}: max err {e:.2e}")
         assert e < 1e-9
     print("attention index algebra: OK")

@@ -20,6 +20,7 @@ T4R_MAX_FEATURES = 32
 # modes (include/t4r_b200.h)
 MLM_TRAIN, MLM_EVAL_LAST, MLM_EVAL_ALL, MLM_INFERENCE = 0, 1, 2, 3
 CLM_ALL, CLM_LAST, CLM_INFERENCE = 0, 1, 2
+PLM_TRAIN, PLM_EVAL_LAST, PLM_EVAL_ALL = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -137,6 +138,11 @@ SIGNATURES = {
     "t4r_pad_ragged": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "t4r_mask_mlm": (c_int, [_P, c_int, c_int, c_int64, c_int, c_float, _P, _P, _P, _P, _P]),
     "t4r_mask_clm": (c_int, [_P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P]),
+    "t4r_mask_plm": (c_int, [_P, c_int, c_int, c_int64, c_int, c_int, C.POINTER(C.c_int32), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "t4r_debug_mask_plm_host": (c_int, [_P, c_int, c_int, c_int64, c_int, c_int, C.POINTER(C.c_int32), _P, _P, _P, _P, _P,
+                                        _P, _P, _P]),
+    "t4r_xlnet_encoder_plm_fwd": (c_int, [C.POINTER(XLNetLayer), c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,
+                                          _P, c_size_t, _P]),
     "t4r_compact_targets": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
     "t4r_split_planes": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "t4r_split_planes_mixed": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),

@@ -180,9 +180,31 @@ extern "C" size_t t4r_xlnet_encoder_workspace_bytes(int B, int L, int d, int n_h
   return b + 1024;
 }
 
+// plm_mask != nullptr: the two-stream PLM forward -- B counts the stacked row sessions (2 x the real batch: h rows, then
+// g rows) and only the attention step knows about the streams (everything else is row-wise).
+static int xlnet_encoder_impl(const t4r_xlnet_layer* layers, int n_layer, int B, int L, int d, int n_head,
+                              float ln_eps, const float* x_f32, const void* x_planes, float* out_f32,
+                              void* out_planes, void* workspace, size_t workspace_bytes, void* stream,
+                              const uint8_t* plm_mask);
 extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer, int B, int L, int d, int n_head,
                                      float ln_eps, const float* x_f32, const void* x_planes, float* out_f32,
                                      void* out_planes, void* workspace, size_t workspace_bytes, void* stream) {
+  return xlnet_encoder_impl(layers, n_layer, B, L, d, n_head, ln_eps, x_f32, x_planes, out_f32, out_planes, workspace,
+                            workspace_bytes, stream, nullptr);
+}
+extern "C" int t4r_xlnet_encoder_plm_fwd(const t4r_xlnet_layer* layers, int n_layer, int B, int L, int d, int n_head,
+                                         float ln_eps, const float* x_f32, const uint8_t* perm_mask, float* out_f32,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  T4R_REQUIRE(perm_mask != nullptr, "xlnet_encoder_plm: perm_mask is required");
+  T4R_REQUIRE(attn_mma_supported(L, d, n_head, true),
+              "xlnet_encoder_plm: needs the tensor-path attention (L + 2 <= 32, or <= 64 with T4R_ATTN_MMA64=1); L=%d", L);
+  return xlnet_encoder_impl(layers, n_layer, 2 * B, L, d, n_head, ln_eps, x_f32, nullptr, out_f32, nullptr, workspace,
+                            workspace_bytes, stream, perm_mask);
+}
+static int xlnet_encoder_impl(const t4r_xlnet_layer* layers, int n_layer, int B, int L, int d, int n_head,
+                              float ln_eps, const float* x_f32, const void* x_planes, float* out_f32,
+                              void* out_planes, void* workspace, size_t workspace_bytes, void* stream,
+                              const uint8_t* plm_mask) {
   T4R_REQUIRE(layers && n_layer >= 1 && B > 0 && L > 0 && x_f32 && out_f32 && workspace, "xlnet_encoder: bad arguments");
   T4R_REQUIRE(d == 64 || d == 128 || d == 256, "xlnet_encoder: d_model must be 64, 128 or 256 (got %d)", d);
   T4R_REQUIRE(workspace_bytes >= t4r_xlnet_encoder_workspace_bytes(B, L, d, n_head), "xlnet_encoder: workspace too small");
@@ -241,7 +263,11 @@ extern "C" int t4r_xlnet_encoder_fwd(const t4r_xlnet_layer* layers, int n_layer,
       T4R_TRY(launch_gemm(pb, ep, s));
     }
     // relative attention core (HF:xlnet:95-140)
-    if (tc_attn)
+    if (plm_mask) {
+      T4R_REQUIRE(tc_attn, "xlnet_encoder_plm: the FFMA attention fallback has no two-stream form (unset T4R_ATTN_SIMT)");
+      T4R_TRY(launch_attn_mma_plm(qkv_p, M * 3 * d, r_p_l, static_cast<int64_t>(2) * L * d, w.r_w_bias, w.r_r_bias, B / 2,
+                                  L, d, n_head, attn_p, M * d, plm_mask, s));
+    } else if (tc_attn)
       T4R_TRY(launch_attn_mma(true, qkv_p, M * 3 * d, r_p_l, static_cast<int64_t>(2) * L * d, w.r_w_bias, w.r_r_bias, B,
                               L, d, n_head, attn_p, M * d, s));
     else

@@ -58,11 +58,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Shared-memory tiles hold only the L (+2) real rows; every ldmatrix row address beyond them
 // points at one shared all-zero row, so the per-warp footprint stays small enough for 3-4
 // blocks per SM (the kernel is latency-bound: one cp.async batch + ~2k instructions per session).
-template <int DH, bool REL>
+// MASKED (XLNet permutation language modeling, HF:xlnet two-stream attention): blockIdx.z is the stream -- 0 = content
+// stream h, 1 = query stream g.  The planes then hold 2 B L rows (h rows, then g rows); queries come from the stream's
+// own rows, keys / values always from the h rows, and score (i, j) of session b is replaced by -1e30 where
+// plm_mask[b, i, j] != 0 (for h: except on the diagonal -- HF's non_tgt_mask).  -1e30, not -inf: a fully masked row
+// then softmaxes to the uniform distribution exactly as HF's fp32 `score - 1e30 * mask` does.
+template <int DH, bool REL, bool MASKED = false>
 __global__ void __launch_bounds__(128)
 attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride, const __nv_bfloat16* __restrict__ rpl,
                 int64_t r_plane_stride, const float* __restrict__ rw, const float* __restrict__ rr, int B, int L, int d,
-                int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride) {
+                int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride,
+                const uint8_t* __restrict__ plm_mask = nullptr) {
+  const int stream = MASKED ? static_cast<int>(blockIdx.z) : 0;
+  const int64_t stream_rows = MASKED ? static_cast<int64_t>(stream) * B * L : 0;
   constexpr int LDS = DH + 8;            // row stride (bf16): 16-byte rows, conflict-free ldmatrix
   constexpr int KT = DH / 16;            // k tiles of the q.k / q.R products
   constexpr int NTC = DH / 8;            // n tiles of the P V product
@@ -111,7 +119,7 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
         const int pl = idx / (L * C8), rem = idx % (L * C8);
         const int i = rem / C8, c8 = rem % C8;
         const __nv_bfloat16* rowp = base + pl * qkv_plane_stride + static_cast<int64_t>(i) * 3 * d + 8 * c8;
-        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp);
+        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp + stream_rows * 3 * d);  // queries: this stream's rows
         cp_async16(smem_u32(Ks + (pl * L + i) * LDS + 8 * c8), rowp + d);
         cp_async16(smem_u32(Vs + (pl * L + i) * LDS + 8 * c8), rowp + 2 * d);
       }
@@ -225,6 +233,9 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
             v += ((e & 1) ? wb1 : wb0) + S2s[ii * S2LD + m] + S2s[(L + 1) * S2LD + m];
           }
           v *= scale;
+          if (MASKED) {
+            if (i < L && j < L && !(stream == 0 && i == j) && plm_mask[(static_cast<int64_t>(b) * L + i) * L + j]) v = -1e30f;
+          }
           if (j >= L || (!REL && j > i)) v = -INFINITY;
           s1[mt][nt][e] = v;
           rmax[mt][e >> 1] = fmaxf(rmax[mt][e >> 1], v);
@@ -298,7 +309,7 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
         const int i = mt * 16 + g + hf * 8;
         if (i < L) {
           const float inv = rsum[mt][hf];
-          __nv_bfloat16* hi = out_planes + (static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
+          __nv_bfloat16* hi = out_planes + (stream_rows + static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
 #pragma unroll
           for (int nc = 0; nc < NTC; ++nc) {
             uint32_t wh, wl;
@@ -311,10 +322,11 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
   }
 }
 
-template <int DH, bool REL>
+template <int DH, bool REL, bool MASKED = false>
 static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const __nv_bfloat16* rpl, int64_t r_ps,
                                 const float* rw, const float* rr, int B, int L, int d, int H,
-                                __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s) {
+                                __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s,
+                                const uint8_t* plm_mask = nullptr) {
   constexpr int LDS = DH + 8;
   const int QR = REL ? L + 2 : L;
   const int S2LD = ((2 * L + 7) / 8) * 8 + 1;
@@ -323,7 +335,7 @@ static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const 
   const int warps = 4;
   const size_t smem = shared_part + warps * per_warp;
   T4R_REQUIRE(smem <= 200 * 1024, "attn_mma: shared memory %zu too large", smem);
-  auto kern = attn_mma_kernel<DH, REL>;
+  auto kern = attn_mma_kernel<DH, REL, MASKED>;
   static size_t attr = 0;
   if (smem > attr) {
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -331,8 +343,8 @@ static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const 
   }
   int spb = 2 * warps;
   while (spb > warps && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
-  dim3 grid((B + spb - 1) / spb, H);
-  kern<<<grid, warps * 32, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps);
+  dim3 grid((B + spb - 1) / spb, H, MASKED ? 2 : 1);
+  kern<<<grid, warps * 32, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps, plm_mask);
   T4R_LAUNCH_CHECK("attn_mma_kernel");
   return 0;
 }
@@ -350,11 +362,14 @@ static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const 
 // ============================================================================
 __device__ __forceinline__ void pair_bar(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
-template <int DH, bool REL>
+template <int DH, bool REL, bool MASKED = false>
 __global__ void __launch_bounds__(128)
 attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride, const __nv_bfloat16* __restrict__ rpl,
                   int64_t r_plane_stride, const float* __restrict__ rw, const float* __restrict__ rr, int B, int L, int d,
-                  int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride) {
+                  int sessions_per_block, __nv_bfloat16* __restrict__ out_planes, int64_t out_plane_stride,
+                  const uint8_t* __restrict__ plm_mask = nullptr) {
+  const int stream = MASKED ? static_cast<int>(blockIdx.z) : 0;
+  const int64_t stream_rows = MASKED ? static_cast<int64_t>(stream) * B * L : 0;
   constexpr int LDS = DH + 8;
   constexpr int KT = DH / 16;
   constexpr int NTC = DH / 8;
@@ -407,7 +422,7 @@ attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_strid
         const int pl = idx / (L * C8), rem = idx % (L * C8);
         const int i = rem / C8, c8 = rem % C8;
         const __nv_bfloat16* rowp = base + pl * qkv_plane_stride + static_cast<int64_t>(i) * 3 * d + 8 * c8;
-        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp);
+        cp_async16(smem_u32(Qs + (pl * QR + i) * LDS + 8 * c8), rowp + stream_rows * 3 * d);
         cp_async16(smem_u32(Ks + (pl * L + i) * LDS + 8 * c8), rowp + d);
         cp_async16(smem_u32(Vs + (pl * L + i) * LDS + 8 * c8), rowp + 2 * d);
       }
@@ -521,6 +536,9 @@ attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_strid
             v += WB[j] + S2s[ii * S2LD + m] + S2s[(L + 1) * S2LD + m];
           }
           v *= scale;
+          if (MASKED) {
+            if (i < L && j < L && !(stream == 0 && i == j) && plm_mask[(static_cast<int64_t>(b) * L + i) * L + j]) v = -1e30f;
+          }
           if (j >= L || (!REL && j > i)) v = -INFINITY;
           s1[ml][nt][e] = v;
           rmax[ml][e >> 1] = fmaxf(rmax[ml][e >> 1], v);
@@ -594,7 +612,7 @@ attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_strid
         const int i = (mt0 + ml) * 16 + g + hf * 8;
         if (i < L) {
           const float inv = rsum[ml][hf];
-          __nv_bfloat16* hi = out_planes + (static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
+          __nv_bfloat16* hi = out_planes + (stream_rows + static_cast<int64_t>(b) * L + i) * d + h * DH + 2 * t;
 #pragma unroll
           for (int nc = 0; nc < NTC; ++nc) {
             uint32_t wh, wl;
@@ -607,10 +625,11 @@ attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_strid
   }
 }
 
-template <int DH, bool REL>
+template <int DH, bool REL, bool MASKED = false>
 static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const __nv_bfloat16* rpl, int64_t r_ps,
                                   const float* rw, const float* rr, int B, int L, int d, int H,
-                                  __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s) {
+                                  __nv_bfloat16* out_planes, int64_t out_ps, cudaStream_t s,
+                                  const uint8_t* plm_mask = nullptr) {
   constexpr int LDS = DH + 8;
   const int QR = REL ? L + 2 : L;
   const int S2LD = ((2 * L + 7) / 8) * 8 + 1;
@@ -620,7 +639,7 @@ static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, cons
   if (shared_part + pairs * per_pair > 200 * 1024) pairs = 1;
   const size_t smem = shared_part + pairs * per_pair;
   T4R_REQUIRE(smem <= 200 * 1024, "attn_mma64: shared memory %zu too large", smem);
-  auto kern = attn_mma64_kernel<DH, REL>;
+  auto kern = attn_mma64_kernel<DH, REL, MASKED>;
   static size_t attr = 0;
   if (smem > attr) {
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -628,8 +647,8 @@ static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, cons
   }
   int spb = 2 * pairs;
   while (spb > pairs && static_cast<int64_t>((B + spb - 1) / spb) * H < 148 * 8) spb >>= 1;
-  dim3 grid((B + spb - 1) / spb, H);
-  kern<<<grid, pairs * 64, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps);
+  dim3 grid((B + spb - 1) / spb, H, MASKED ? 2 : 1);
+  kern<<<grid, pairs * 64, smem, s>>>(qkv, qkv_ps, rpl, r_ps, rw, rr, B, L, d, spb, out_planes, out_ps, plm_mask);
   T4R_LAUNCH_CHECK("attn_mma64_kernel");
   return 0;
 }
@@ -674,6 +693,27 @@ int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane
   }
   T4R_AM(16) T4R_AM(32) T4R_AM(64)
 #undef T4R_AM
+  return T4R_ERR_UNSUPPORTED;
+}
+
+// XLNet two-stream attention for permutation language modeling: planes hold 2 B L rows (h, then g), see attn_mma_kernel
+int launch_attn_mma_plm(const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
+                        int64_t r_plane_stride, const float* rw, const float* rr, int B, int L, int d, int H,
+                        __nv_bfloat16* out_planes, int64_t out_plane_stride, const uint8_t* plm_mask, cudaStream_t s) {
+  T4R_REQUIRE(plm_mask != nullptr, "attn_mma_plm: the permutation mask is required");
+  T4R_REQUIRE(attn_mma_supported(L, d, H, true),
+              "PLM needs the tensor-path attention: L + 2 <= 32 (or <= 64 with T4R_ATTN_MMA64=1), got L=%d d=%d H=%d", L, d, H);
+  const int dh = d / H;
+  const bool big = L + 2 > 32;
+#define T4R_AMP(DHV)                                                                                                   \
+  if (dh == DHV) {                                                                                                     \
+    if (big) return launch_attn_mma64_inst<DHV, true, true>(qkv_planes, qkv_plane_stride, r_planes, r_plane_stride, rw, \
+                                                            rr, B, L, d, H, out_planes, out_plane_stride, s, plm_mask); \
+    return launch_attn_mma_inst<DHV, true, true>(qkv_planes, qkv_plane_stride, r_planes, r_plane_stride, rw, rr, B, L,  \
+                                                 d, H, out_planes, out_plane_stride, s, plm_mask);                      \
+  }
+  T4R_AMP(16) T4R_AMP(32) T4R_AMP(64)
+#undef T4R_AMP
   return T4R_ERR_UNSUPPORTED;
 }
 

@@ -121,6 +121,9 @@ bool attn_mma_supported(int L, int d, int H, bool rel);
 int launch_attn_mma(bool rel, const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
                     int64_t r_plane_stride, const float* rw, const float* rr, int B, int L, int d, int H,
                     __nv_bfloat16* out_planes, int64_t out_plane_stride, cudaStream_t s);
+int launch_attn_mma_plm(const __nv_bfloat16* qkv_planes, int64_t qkv_plane_stride, const __nv_bfloat16* r_planes,
+                        int64_t r_plane_stride, const float* rw, const float* rr, int B, int L, int d, int H,
+                        __nv_bfloat16* out_planes, int64_t out_plane_stride, const uint8_t* plm_mask, cudaStream_t s);
 int launch_xlnet_attn(const float* qkv /*[M, 3d]*/, const float* r /*[2L, d]*/, const float* rw, const float* rr,
                       int B, int L, int d, int H, __nv_bfloat16* out_planes, int64_t plane_stride, cudaStream_t s);
 int launch_causal_attn(const float* qkv, int B, int L, int d, int H, __nv_bfloat16* out_planes,

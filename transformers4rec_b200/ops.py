@@ -308,6 +308,58 @@ def mask_clm(item_ids: torch.Tensor, mode: int, padding_idx: int = 0):
     return mask, labels, code
 
 
+def plm_context_lengths(max_span_length: int, plm_probability: float):
+    """masking.py:608 ``int(span_length / plm_probability)`` for span 0..max (index 0 unused), python float math."""
+    return [0] + [int(sp / plm_probability) for sp in range(1, max_span_length + 1)]
+
+
+def _plm_call(fn, ids, mode, padding_idx, max_span, ctx_len, draws, stream_arg):
+    B, L = ids.shape
+    dev = ids.device
+    mask = torch.empty((B, L), dtype=torch.bool, device=dev)
+    labels = torch.empty((B, L), dtype=torch.int64, device=dev)
+    perm_mask = torch.empty((B, L, L), dtype=torch.uint8, device=dev)
+    keep = []
+    ptrs = [None] * 5
+    if mode == _lib.PLM_TRAIN:
+        for i, (key, dt) in enumerate((("u_span", torch.float32), ("u_start", torch.float32), ("u_force", torch.float32),
+                                       ("u_unmask", torch.float32), ("perm", torch.int32))):
+            t = draws[key].to(dt).contiguous()
+            assert tuple(t.shape) == ((B, L) if key in ("u_span", "u_start", "perm") else (B,)), key
+            keep.append(t)
+            ptrs[i] = ptr(t)
+    arr = (C.c_int32 * (max_span + 1))(*[int(v) for v in ctx_len]) if mode == _lib.PLM_TRAIN else None
+    check(fn(ptr(ids), B, L, padding_idx, mode, max_span, arr, *ptrs, ptr(mask), ptr(labels), ptr(perm_mask), *stream_arg),
+          "t4r_mask_plm")
+    return mask, labels, perm_mask
+
+
+def mask_plm(item_ids: torch.Tensor, mode: int, padding_idx: int = 0, max_span_length: int = 5,
+             plm_probability: float = 1 / 6, draws: Optional[dict] = None):
+    """PLM labels + permutation mask (t4r_mask_plm).  ``draws`` (training): dict(u_span, u_start [B, L], u_force,
+    u_unmask [B], perm [B, L]); generated on the device when omitted.  Returns (mask_schema bool, masked_targets i64,
+    perm_mask uint8 [B, L, L])."""
+    _need_cuda(item_ids)
+    ids = item_ids.long().contiguous()
+    B, L = ids.shape
+    if mode == _lib.PLM_TRAIN and draws is None:
+        dev = ids.device
+        draws = {"u_span": torch.rand((B, L), device=dev), "u_start": torch.rand((B, L), device=dev),
+                 "u_force": torch.rand((B,), device=dev), "u_unmask": torch.rand((B,), device=dev),
+                 "perm": torch.argsort(torch.rand((B, L), device=dev), dim=1)}   # a uniform random permutation per row
+    return _plm_call(_lib.load().t4r_mask_plm, ids, mode, padding_idx, max_span_length,
+                     plm_context_lengths(max_span_length, plm_probability), draws, (_stream(),))
+
+
+def mask_plm_host(item_ids: torch.Tensor, mode: int, padding_idx: int = 0, max_span_length: int = 5,
+                  plm_probability: float = 1 / 6, draws: Optional[dict] = None):
+    """The same code compiled for the host (CPU tensors; test infrastructure)."""
+    assert not item_ids.is_cuda
+    ids = item_ids.long().contiguous()
+    return _plm_call(_lib.load().t4r_debug_mask_plm_host, ids, mode, padding_idx, max_span_length,
+                     plm_context_lengths(max_span_length, plm_probability), draws, ())
+
+
 def compact_targets(masked_targets: torch.Tensor, padding_idx: int = 0):
     _need_cuda(masked_targets)
     mt = masked_targets.long().contiguous().reshape(-1)
@@ -420,6 +472,23 @@ def xlnet_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: i
     check(lib.t4r_xlnet_encoder_fwd(layers_struct, n_layer, B, L, d, n_head, eps, ptr(x_f32), ptr(x_planes), ptr(out),
                                     ptr(out_planes), ptr(ws), ws.numel(), _stream()), "t4r_xlnet_encoder_fwd")
     return out, out_planes
+
+
+def xlnet_encoder_plm(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: int, eps: float, x2_f32: torch.Tensor,
+                      perm_mask: torch.Tensor):
+    """Two-stream XLNet forward (PLM): ``x2_f32`` [2 B L, d] = content-stream rows then query-stream rows; returns the
+    same layout (the second half is HF's output[0])."""
+    _need_cuda(x2_f32, perm_mask)
+    lib = _lib.load()
+    x2_f32 = _f32c(x2_f32)
+    pm = perm_mask.to(torch.uint8).contiguous()
+    dev = x2_f32.device
+    nbytes = lib.t4r_xlnet_encoder_workspace_bytes(2 * B, L, d, n_head)
+    ws = WS.get("xlnet_plm", nbytes, dev)
+    out = torch.empty((2 * B * L, d), dtype=torch.float32, device=dev)
+    check(lib.t4r_xlnet_encoder_plm_fwd(layers_struct, n_layer, B, L, d, n_head, eps, ptr(x2_f32), ptr(pm), ptr(out),
+                                        ptr(ws), ws.numel(), _stream()), "t4r_xlnet_encoder_plm_fwd")
+    return out
 
 
 def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: int, eps: float, wpe, lnf_g, lnf_b,
