@@ -696,6 +696,8 @@ class OracleSessionModel(torch.nn.Module):
         self.masking = masking
         self.arch = arch
         self.mlm_probability = mlm_probability
+        self.plm_kwargs: dict = {}      # plm_probability / max_span_length / eval_on_last_item_seq_only overrides
+        self._plm = None
         self.softmax_temperature = softmax_temperature
         self.sampled_softmax = sampled_softmax
         self.max_n_samples = max_n_samples
@@ -741,6 +743,11 @@ class OracleSessionModel(torch.nn.Module):
                                                       u_bern=d.get("u_bern"), u_force=d.get("u_force"),
                                                       u_unmask=d.get("u_unmask"))
             x = mlm_apply_mask_to_inputs(x, mask, self.masked_item_embedding, training, testing)
+        elif self.masking == "plm":
+            # masking.py:729-740: PLM's compute_masked_targets only looks at `training`
+            mask, labels, tm, pm, _ = plm_compute_masked_targets(ids, training, draws=draws, **self.plm_kwargs)
+            self._plm = (pm, tm)
+            x = plm_apply_mask_to_inputs(x, mask, self.masked_item_embedding, training, testing)
         else:
             mask, labels = clm_compute_masked_targets(ids, training, testing)
             x = clm_apply_mask_to_inputs(x, mask, self.masked_item_embedding, training, testing)
@@ -748,7 +755,10 @@ class OracleSessionModel(torch.nn.Module):
 
     def forward(self, inputs, training=True, testing=False, draws=None, neg_samples=None):
         x, mask, labels = self.input_block(inputs, training, testing, draws)
-        h = hf_encoder_forward(self.transformer, x)
+        if self.masking == "plm":
+            h = hf_encoder_forward_plm(self.transformer, x, *self._plm)   # output[0] = the query stream g
+        else:
+            h = hf_encoder_forward(self.transformer, x)
         hs = h
         if self.task_block is not None:
             h = self.task_block(h.float())

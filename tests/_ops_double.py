@@ -150,6 +150,19 @@ def mask_mlm(item_ids, mode, padding_idx=0, mlm_probability=0.15, u=None):
     return m, l, m.to(torch.uint8)
 
 
+def mask_plm(item_ids, mode, padding_idx=0, max_span_length=5, plm_probability=1 / 6, draws=None):
+    ids = item_ids.long()
+    B, L = ids.shape
+    if mode == _lib.PLM_TRAIN and draws is None:
+        draws = {"u_span": torch.rand((B, L)), "u_start": torch.rand((B, L)), "u_force": torch.rand((B,)),
+                 "u_unmask": torch.rand((B,)), "perm": torch.argsort(torch.rand((B, L)), dim=1)}
+    m, l, _, pm, _ = O.plm_compute_masked_targets(ids, mode == _lib.PLM_TRAIN, padding_idx=padding_idx,
+                                                  eval_on_last_item_seq_only=(mode != _lib.PLM_EVAL_ALL),
+                                                  plm_probability=plm_probability, max_span_length=max_span_length,
+                                                  draws=draws)
+    return m, l, pm.to(torch.uint8)
+
+
 def mask_clm(item_ids, mode, padding_idx=0):
     ids = item_ids.long()
     training, testing = (mode == _lib.CLM_ALL), (mode == _lib.CLM_LAST)
@@ -318,11 +331,15 @@ def _pad(values, offsets, rows, in_len, pad_len):
 
 
 # ---------------------------------------------------------------------------------------------------- encoders
-def _xlnet_forward(self, inputs_embeds, **kwargs):
+def _xlnet_forward(self, inputs_embeds, perm_mask=None, target_mapping=None, **kwargs):
     hf = O.build_hf_xlnet(self.config.d_model, self.config.n_head, self.config.n_layer).eval()
     missing, _ = hf.load_state_dict(self.state_dict(), strict=False)
-    assert not [m for m in missing if "mask_emb" not in m and "word_embedding" not in m], missing
+    assert not [m for m in missing if "word_embedding" not in m], missing
     with torch.no_grad():
+        if perm_mask is not None:   # permutation language modeling: HF's two-stream forward, output[0] = g
+            L = inputs_embeds.shape[1]
+            tm = torch.eye(L).expand(inputs_embeds.shape[0], L, L)
+            return (O.hf_encoder_forward_plm(hf, inputs_embeds.float(), perm_mask, tm),)
         return (O.hf_encoder_forward(hf, inputs_embeds.float()),)
 
 
@@ -337,7 +354,7 @@ def _gpt2_forward(self, inputs_embeds, **kwargs):
         return (O.hf_encoder_forward(hf, inputs_embeds.float()),)
 
 
-OPS = dict(input_block=input_block, swap_noise=swap_noise, split_planes=split_planes, split_planes_mixed=split_planes_mixed, gather_rows_split=gather_rows_split,
+OPS = dict(mask_plm=mask_plm, input_block=input_block, swap_noise=swap_noise, split_planes=split_planes, split_planes_mixed=split_planes_mixed, gather_rows_split=gather_rows_split,
            compact_targets=compact_targets, embed_concat=embed_concat, mask_mlm=mask_mlm, mask_clm=mask_clm, linear=linear,
            label_logit=label_logit, head_softmax_ce=head_softmax_ce, head_logits=head_logits,
            head_logits_mixed=head_logits_mixed, topk=topk, recall_from_ranks=recall_from_ranks,

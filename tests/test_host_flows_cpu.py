@@ -166,3 +166,42 @@ def test_bench_workload_builders_train_like_the_oracle(monkeypatch, cfg):
         got = model(batch, training=True)["loss"].item()
     assert abs(got - ref) < 1e-4, (got, ref)
     assert (task.task_block is not None) == (cfg["De"] != cfg["d"])
+
+
+def test_permutation_language_modeling_flow(monkeypatch):
+    """masking="plm" end to end (kernels = doubles): labels / masks / side channels, training and evaluation loss
+    against the oracle graph, whose encoder is HF XLNet's two-stream forward with perm_mask + target_mapping."""
+    import transformers4rec_b200.torch as tr
+    D.install(monkeypatch)
+    oracle, model = make_pair({"item_id/list": 1001}, {"item_id/list": 32}, "item_id/list", (), 32, 2, 2, 12,
+                              masking="plm", device="cpu", weight_scale=0.08)
+    with torch.no_grad():   # the query stream starts from mask_emb: make it matter and share it with the oracle
+        model.heads[0].body[1].transformer.mask_emb.normal_(0.0, 0.5)
+        oracle.transformer.mask_emb.copy_(model.heads[0].body[1].transformer.mask_emb)
+    B, L = 10, 12
+    batch = synth_batch(B, L, {"item_id/list": 1001}, seed=5)
+    g = torch.Generator().manual_seed(3)
+    draws = {"u_span": torch.rand((B, L), generator=g), "u_start": torch.rand((B, L), generator=g),
+             "u_force": torch.rand((B,), generator=g), "u_unmask": torch.rand((B,), generator=g),
+             "perm": torch.stack([torch.randperm(L, generator=g) for _ in range(B)])}
+    inputs = model.heads[0].body[0]
+    assert isinstance(inputs.masking, tr.PermutationLanguageModeling)
+    inputs.masking.set_draws(draws)
+    with torch.no_grad():
+        ref = oracle(batch, training=True, draws=draws)
+        out = model(batch, training=True)
+    assert torch.equal(inputs.masking.masked_targets, ref["masked_targets"])
+    assert torch.equal(inputs.masking.perm_mask, oracle._plm[0].to(torch.uint8))
+    assert inputs.masking.target_mapping.shape == (B, L, L)
+    assert set(inputs.masking.transformer_required_arguments()) == {"target_mapping", "perm_mask"}
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-4
+    with torch.no_grad():
+        ref_e = oracle(batch, training=False, testing=True)
+        out_e = model(batch, training=False, testing=True)
+    assert abs(out_e["loss"].item() - ref_e["loss"].item()) < 1e-4
+    with pytest.raises(NotImplementedError):
+        tr.PermutationLanguageModeling(hidden_size=8, permute_all=True)
+    # GPT-2 cannot take PLM (block/transformer.py:119-134 message)
+    with pytest.raises(ValueError, match="requires the parameters"):
+        tr.TransformerBlock(tr.GPT2Config.build(d_model=32, n_head=2, n_layer=1, total_seq_length=12),
+                            masking=tr.PermutationLanguageModeling(hidden_size=32))

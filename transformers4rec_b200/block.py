@@ -228,9 +228,18 @@ class XLNetEncoder(nn.Module):
                 setattr(arr[i], fname, t.data_ptr())
         return arr, keep
 
-    def forward(self, inputs_embeds: torch.Tensor, **kwargs):
+    def forward(self, inputs_embeds: torch.Tensor, perm_mask: Optional[torch.Tensor] = None, target_mapping=None, **kwargs):
         B, L, d = inputs_embeds.shape
         arr, keep = self._layer_structs()
+        if perm_mask is not None:
+            # permutation language modeling (HF:xlnet two-stream attention with target_mapping = identity): the
+            # content stream h and the query stream g (mask_emb in every row) go through the layers stacked; HF
+            # returns g
+            x2 = torch.cat([inputs_embeds.reshape(B * L, d).float(),
+                            self.mask_emb.detach().reshape(1, d).float().expand(B * L, d)], dim=0)
+            out2 = ops.xlnet_encoder_plm(arr, len(self.layer), B, L, d, self.config.n_head,
+                                         float(self.config.layer_norm_eps), x2, perm_mask)
+            return (out2[B * L:].view(B, L, d),)
         planes = _planes_of(inputs_embeds)
         out, out_planes = ops.xlnet_encoder(arr, len(self.layer), B, L, d, self.config.n_head,
                                             float(self.config.layer_norm_eps), inputs_embeds.reshape(B * L, d), planes,
@@ -356,6 +365,8 @@ class TransformerBlock(nn.Module):
             if isinstance(self.transformer, GPT2Encoder) and isinstance(masking, MaskedLanguageModeling):
                 raise ValueError(f"{masking.__class__.__name__} is not supported by: the GPT2Config architecture")
             required = list(masking.transformer_required_arguments().keys())
+            if required and isinstance(self.transformer, XLNetEncoder) and set(required) <= {"target_mapping", "perm_mask"}:
+                required = []  # permutation language modeling: XLNet's two-stream forward takes both
             if required:
                 raise ValueError(f"{masking.__class__.__name__} requires the parameters: {', '.join(required)} "
                                  f"in the {type(self.transformer)} signature")
@@ -371,6 +382,10 @@ class TransformerBlock(nn.Module):
         return cls(_t, masking)
 
     def forward(self, inputs_embeds, **kwargs):
+        # block/transformer.py:185-196: the masking's transformer arguments travel with the call
+        perm_mask = getattr(self.masking, "perm_mask", None) if self.masking is not None else None
+        if perm_mask is not None:
+            return self.transformer(inputs_embeds=inputs_embeds, perm_mask=perm_mask)[0]
         return self.transformer(inputs_embeds=inputs_embeds)[0]
 
     def _get_name(self):

@@ -1,4 +1,4 @@
-"""Host-side mirror of ``transformers4rec/torch/masking.py`` for MLM and CLM.
+"""Host-side mirror of ``transformers4rec/torch/masking.py`` for MLM, CLM and PLM.
 
 Same class names, constructor arguments, attributes (``mask_schema``,
 ``masked_targets``, ``padding_idx``, ``masked_item_embedding``,
@@ -162,3 +162,55 @@ class MaskedLanguageModeling(MaskSequence):
             # masking.py:489-492: one extra [MASK] position (copy of the last one, then replaced)
             inputs = torch.cat([inputs, inputs[:, -1, :].unsqueeze(1)], dim=1)
         return self._apply_codes(inputs, self.row_code)
+
+
+@masking_registry.register_with_multiple_names("plm", "permutation")
+class PermutationLanguageModeling(MaskSequence):
+    """masking.py:501-740 (XLNet permutation language modeling).  Labels, mask and the permutation attention mask come
+    from one kernel (``t4r_mask_plm``, one thread per session; the reference loops over the sessions in python);
+    ``target_mapping`` is the identity in every mode the reference builds it in and is only materialised when
+    somebody reads the attribute.  ``permute_all=True`` is not supported: the reference leaves ``target_mapping`` all
+    zero in that mode (masking.py:592-596), which silences the query stream."""
+
+    def __init__(self, hidden_size: int, padding_idx: int = 0, eval_on_last_item_seq_only: bool = True,
+                 plm_probability: float = 1 / 6, max_span_length: int = 5, permute_all: bool = False, **kwargs):
+        super().__init__(hidden_size=hidden_size, padding_idx=padding_idx,
+                         eval_on_last_item_seq_only=eval_on_last_item_seq_only)
+        if permute_all:
+            raise NotImplementedError("PermutationLanguageModeling(permute_all=True) is outside the t4r_b200 path: the "
+                                      "reference builds an all-zero target_mapping in that mode")
+        self.plm_probability = plm_probability
+        self.max_span_length = max_span_length
+        self.permute_all = permute_all
+        self.perm_mask: Optional[torch.Tensor] = None      # uint8 [B, L, L], 1 = query i may not attend key j
+        self._plm_draws: Optional[dict] = None
+
+    def set_draws(self, draws: Optional[dict]):
+        """Test hook: dict(u_span, u_start [B, L], u_force, u_unmask [B], perm [B, L]) (DESIGN.md "Random draws")."""
+        self._plm_draws = draws
+
+    @property
+    def target_mapping(self) -> Optional[torch.Tensor]:
+        if self.perm_mask is None:
+            return None
+        B, L, _ = self.perm_mask.shape
+        return torch.eye(L, dtype=torch.float32, device=self.perm_mask.device).expand(B, L, L)
+
+    def _compute_masked_targets(self, item_ids, training=False, testing=False) -> MaskingInfo:
+        # masking.py:729-737: only `training` selects the mode (evaluation and inference share the masks)
+        mode = _lib.PLM_TRAIN if training else (_lib.PLM_EVAL_LAST if self.eval_on_last_item_seq_only
+                                                 else _lib.PLM_EVAL_ALL)
+        mask, labels, perm_mask = ops.mask_plm(item_ids, mode, self.padding_idx, self.max_span_length,
+                                               self.plm_probability, self._plm_draws if training else None)
+        self.perm_mask = perm_mask
+        # masking.py:155-180 (the base rule PLM inherits): masked rows are replaced in training and evaluation only
+        self.row_code = mask.to(torch.uint8) if (training or testing) else torch.zeros_like(mask, dtype=torch.uint8)
+        return MaskingInfo(mask, labels)
+
+    def apply_mask_to_inputs(self, inputs, mask_schema, training=False, testing=False):
+        if not training and not testing:
+            return inputs
+        return self._apply_codes(inputs, self.row_code)
+
+    def transformer_required_arguments(self) -> Dict[str, Any]:
+        return dict(target_mapping=self.target_mapping, perm_mask=self.perm_mask)

@@ -8,7 +8,7 @@ from ..features import (ContinuousFeatures, ContinuousProjection, FeatureConfig,
                         SoftEmbedding, SoftEmbeddingFeatures, StochasticSwapNoise, TableConfig, TabularLayerNorm,
                         TabularSequenceFeatures)
 from ..masking import (CausalLanguageModeling, MaskedLanguageModeling, MaskSequence,  # noqa: F401
-                       masking_registry)
+                       PermutationLanguageModeling, masking_registry)
 from ..model import Head, Model  # noqa: F401
 from ..prediction_task import (LogUniformSampler, NextItemPredictionTask, PredictionTask)  # noqa: F401
 from ..ranking_metric import (AvgPrecisionAt, DCGAt, MeanReciprocalRankAt, NDCGAt, PrecisionAt, RecallAt,  # noqa: F401
