@@ -330,6 +330,145 @@ def _pad(values, offsets, rows, in_len, pad_len):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------- training (N3)
+def transpose(x):
+    return x.t().contiguous()
+
+
+def col_sum(x):
+    return x.sum(0)
+
+
+def rel_pos_table(L, d, device=None):
+    return O.xlnet_relative_positions(L, d)
+
+
+def rel_pos_proj(wr_list, L, d):
+    pos = O.xlnet_relative_positions(L, d)
+    return torch.stack([pos @ w for w in wr_list])
+
+
+def _xl_scores(qkv, R, rw, rr, B, L, H):
+    d = qkv.shape[1] // 3
+    dh = d // H
+    q, k, v = (t.reshape(B, L, H, dh) for t in qkv.split(d, dim=1))
+    r = R.reshape(2 * L, H, dh)
+    ac = torch.einsum("bihd,bjhd->bhij", q + rw.view(H, dh), k)
+    bd_full = torch.einsum("bihd,mhd->bhim", q + rr.view(H, dh), r)
+    idx = (torch.arange(L).view(1, L) + L - torch.arange(L).view(L, 1))
+    bd = torch.gather(bd_full, 3, idx.view(1, 1, L, L).expand(B, H, L, L))
+    return (ac + bd) / dh ** 0.5, v
+
+
+def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H):
+    s, v = _xl_scores(qkv, R, rw, rr, B, L, H)
+    return torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(B * L, -1)
+
+
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H):
+    with torch.enable_grad():
+        a, b, c, e = (t.detach().clone().requires_grad_(True) for t in (qkv, R, rw, rr))
+        out = xlnet_attn_fwd(a, b, c, e, B, L, H)
+        out.backward(dout)
+    return a.grad, b.grad, c.grad, e.grad
+
+
+def causal_attn_fwd(qkv, B, L, H):
+    d = qkv.shape[1] // 3
+    dh = d // H
+    q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1))
+    s = (q @ k.transpose(-1, -2)) / dh ** 0.5
+    s = s.masked_fill(~torch.tril(torch.ones(L, L, dtype=torch.bool)), float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, d)
+
+
+def causal_attn_bwd(qkv, dout, B, L, H):
+    with torch.enable_grad():
+        a = qkv.detach().clone().requires_grad_(True)
+        causal_attn_fwd(a, B, L, H).backward(dout)
+    return a.grad
+
+
+def layer_norm_fwd(x, gamma, beta, eps):
+    return F.layer_norm(x, (x.shape[1],), gamma.float(), beta.float(), eps)
+
+
+def layer_norm_bwd(x_pre, gamma, eps, dy, add=None):
+    with torch.enable_grad():
+        a = x_pre.detach().clone().requires_grad_(True)
+        g = gamma.detach().clone().float().requires_grad_(True)
+        b = torch.zeros_like(g, requires_grad=True)
+        F.layer_norm(a, (a.shape[1],), g, b, eps).backward(dy)
+    return (a.grad if add is None else a.grad + add), g.grad, b.grad
+
+
+def act_fwd(kind, x):
+    return F.gelu(x) if kind == _lib.ACT_GELU else (torch.relu(x) if kind == _lib.ACT_RELU else x)
+
+
+def act_bwd(kind, pre, dy):
+    with torch.enable_grad():
+        a = pre.detach().clone().requires_grad_(True)
+        act_fwd(kind, a).backward(dy)
+    return a.grad
+
+
+def add_positions(x, wpe, B, L):
+    return (x.reshape(B, L, -1) + wpe[:L].float().unsqueeze(0)).reshape(B * L, -1)
+
+
+def sum_over_sessions(x, B, L):
+    return x.reshape(B, L, -1).sum(0)
+
+
+def apply_row_codes(y, code, mask_vec):
+    out = y.clone()
+    out[code == 1] = mask_vec
+    out[code == 2] = 0.0
+    return out
+
+
+def row_codes_bwd(dx, code):
+    dmask = dx[code == 1].sum(0)
+    dy = dx.clone()
+    dy[code != 0] = 0.0
+    return dmask, dy
+
+
+def gather_rows(x, idx):
+    return x[idx.long()].contiguous()
+
+
+def scatter_rows(src, idx, n_rows):
+    out = torch.zeros((n_rows, src.shape[1]), dtype=src.dtype)
+    out[idx.long()] = src
+    return out
+
+
+def softmax_ce_bwd(z, row_lse, labels, v0, scale):
+    P = torch.exp(z - row_lse[: z.shape[0]].unsqueeze(1)) * scale
+    loc = labels.long() - v0
+    mine = (loc >= 0) & (loc < z.shape[1])
+    rows = torch.arange(z.shape[0])[mine]
+    P[rows, loc[mine]] -= scale
+    return P
+
+
+def index_add_rows(dst, idx, src, col, width, skip_index=None):
+    idx = idx.long()
+    keep = torch.ones_like(idx, dtype=torch.bool) if skip_index is None else idx != skip_index
+    dst.index_add_(0, idx[keep], src[keep][:, col:col + width].to(dst.dtype))
+    return dst
+
+
+TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_table, rel_pos_proj=rel_pos_proj,
+                 xlnet_attn_fwd=xlnet_attn_fwd, xlnet_attn_bwd=xlnet_attn_bwd, causal_attn_fwd=causal_attn_fwd,
+                 causal_attn_bwd=causal_attn_bwd, layer_norm_fwd=layer_norm_fwd, layer_norm_bwd=layer_norm_bwd,
+                 act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
+                 apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,
+                 scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, index_add_rows=index_add_rows)
+
+
 # ---------------------------------------------------------------------------------------------------- encoders
 def _xlnet_forward(self, inputs_embeds, perm_mask=None, target_mapping=None, **kwargs):
     hf = O.build_hf_xlnet(self.config.d_model, self.config.n_head, self.config.n_layer).eval()
@@ -364,8 +503,8 @@ OPS = dict(mask_plm=mask_plm, input_block=input_block, swap_noise=swap_noise, sp
 def install(monkeypatch):
     """Swap the kernels for the stand-ins for the duration of one test."""
     from transformers4rec_b200 import block, ops
-    for name, fn in OPS.items():
-        monkeypatch.setattr(ops, name, fn)
+    for name, fn in list(OPS.items()) + list(TRAIN_OPS.items()):
+        monkeypatch.setattr(ops, name, fn, raising=False)
     monkeypatch.setattr(block.XLNetEncoder, "forward", _xlnet_forward)
     monkeypatch.setattr(block.GPT2Encoder, "forward", _gpt2_forward)
     from transformers4rec_b200 import padding

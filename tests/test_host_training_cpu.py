@@ -1,0 +1,83 @@
+"""N3 on the CPU: the COMPOSITION of the fused training step (transformers4rec_b200/training.py) -- every backward
+formula, transposition, residual branch, mask / code / tied-weight bookkeeping -- against torch autograd of the oracle
+graph, with the kernels replaced by the test doubles (tests/_ops_double.py: each primitive is a few lines of torch, the
+backward ones obtained from autograd of the forward one).  What runs on the GPU instead of the doubles is covered by the
+host twins (tests/test_abi_and_host.py) and the gated GPU tests."""
+import pytest
+import torch
+
+import _ops_double as D
+import t4r_oracle as O
+from _util import make_pair, mlm_draws, synth_batch
+
+CARDS = {"item_id/list": 1501, "category/list": 37}
+CONT = ("cont0/list",)
+
+
+def _oracle_grads(oracle, batch, draws):
+    for p in oracle.parameters():
+        p.grad = None
+    out = oracle(batch, training=True, draws=draws)
+    out["loss"].backward()
+    return out["loss"].item()
+
+
+def _pairs(oracle, model):
+    """(name, oracle parameter, product parameter) for every trainable tensor of the path."""
+    head = model.heads[0]
+    inputs, tblock = head.body[0], head.body[1]
+    yield "masked_item_embedding", oracle.masked_item_embedding, inputs.masking.masked_item_embedding
+    for name in oracle.table_names:
+        yield f"table[{name}]", oracle.tables[name.replace("/", "__")].weight, inputs.categorical_module.embedding_tables[name].weight
+    lin = inputs.projection_module[0][0]
+    yield "proj.weight", oracle.proj.weight, lin.weight
+    yield "proj.bias", oracle.proj.bias, lin.bias
+    od, md = dict(oracle.transformer.named_parameters()), dict(tblock.transformer.named_parameters())
+    for k, v in md.items():
+        if k in od and k not in ("word_embedding.weight", "mask_emb", "wte.weight"):
+            yield "transformer." + k, od[k], v
+    if oracle.task_block is not None:
+        tl = head.prediction_task_dict["next-item"].task_block[0][0]
+        yield "task_block.weight", oracle.task_block.weight, tl.weight
+        yield "task_block.bias", oracle.task_block.bias, tl.bias
+
+
+@pytest.mark.parametrize("arch,masking,dims", [("xlnet", "mlm", {"item_id/list": 32, "category/list": 32}),
+                                               ("xlnet", "clm", {"item_id/list": 32, "category/list": 16}),
+                                               ("gpt2", "clm", {"item_id/list": 16, "category/list": 32})])
+def test_training_step_gradients_match_autograd(monkeypatch, arch, masking, dims):
+    from transformers4rec_b200.training import FusedTrainingStep, training_loss
+    D.install(monkeypatch)
+    oracle, model = make_pair(CARDS, dims, "item_id/list", CONT, 32, 2, 2, 10, arch=arch, masking=masking, device="cpu",
+                              weight_scale=0.08)
+    oracle.train(False)   # dropout off, gradients on
+    B, L = 7, 10
+    batch = synth_batch(B, L, CARDS, CONT, seed=3)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    ref_loss = _oracle_grads(oracle, batch, draws)
+    step = FusedTrainingStep(model, head_chunk=400)     # several column chunks of the 1501-row table
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref_loss) < 1e-4
+    checked = 0
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue            # parameters the path never touches (XLNet segment embeddings)
+        assert pm.grad is not None, name
+        go = po.grad if po.grad is not None else torch.zeros_like(po)
+        err = (pm.grad - go.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 2e-4 * max(1.0, go.abs().max().item()), (name, err, go.abs().max().item())
+        checked += 1
+    assert checked >= 20
+    # the autograd bridge: loss.backward() delivers the same gradients (scaled by the upstream gradient)
+    saved = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for p in model.parameters():
+        p.grad = None
+    out = training_loss(model, batch, step) * 2.0
+    out.backward()
+    for n, p in model.named_parameters():
+        if n in saved:
+            assert torch.allclose(p.grad, 2.0 * saved[n], atol=1e-6), n

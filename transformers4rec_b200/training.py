@@ -1,0 +1,358 @@
+"""N3: backward of the fused path, so that a training step can run on it.
+
+``FusedTrainingStep(model)`` runs forward + backward of
+
+    TabularSequenceFeatures (concat + Linear/ReLU projection + MLM / CLM masking)
+      -> XLNet / GPT-2 encoder -> NextItemPredictionTask (tied weights, full softmax, optional task_block)
+
+with the t4r kernels and leaves the gradients in ``param.grad`` (accumulating, like autograd), so any
+``torch.optim`` optimizer -- plumbing, not the product -- can step.  ``training_loss(model, batch)`` wraps it
+in one ``torch.autograd.Function`` whose ``backward`` hands those gradients to autograd: ``loss.backward()``
+(HF Trainer's ``training_step``, trainer.py:315-338 in the reference) then works unchanged.
+
+How it is built: the training forward is the same math as the inference kernels' but written as a sequence of
+primitive ops that keep what the backward needs (layer inputs, q|k|v, attention output, pre-LayerNorm sums,
+pre-GELU activations); every matmul of the backward is the existing tcgen05 split-bf16 GEMM on transposed
+operands (``dX = dY W``, ``dW = dY^T X``), the rest are small element / row kernels (t4r_train.cu): transpose,
+GELU / ReLU derivative, LayerNorm backward, column sums, attention backward (XLNet relative and GPT-2 causal),
+softmax-cross-entropy backward, row scatter-add.  The head never materialises [T, V]: the table is walked in
+column chunks, logits are recomputed per chunk from the saved log-sum-exp, turned into ``(softmax - onehot) / T``
+in place and consumed by two GEMMs (``dX_t += P W_c``, ``dW_c = P^T X_t``).
+
+Status: written without access to a GPU.  The COMPOSITION (every formula, every transposition, the bookkeeping of
+masks / codes / tied weights) is verified on the CPU against torch autograd of the oracle graph with the kernels
+replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a one-thread-per-row/element call of
+a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
+nothing in the inference path uses this module.  Not covered: sampled softmax, row-sharded tables, soft embeddings /
+element-wise aggregations, label smoothing, PLM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from .block import GPT2Encoder, XLNetEncoder
+from .masking import CausalLanguageModeling, MaskedLanguageModeling
+
+
+# --------------------------------------------------------------------------------------------------------------
+# matmul helpers on top of the tcgen05 GEMM:  C = A B^T with A [M, K], B [N, K] fp32
+# --------------------------------------------------------------------------------------------------------------
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias=None, residual=None) -> torch.Tensor:
+    K = a.shape[1]
+    y, _, _ = ops.linear(ops.split_planes(a), ops.split_planes(b), K, bias=bias, residual=residual, want_planes=False)
+    return y
+
+
+def _acc(param: torch.nn.Parameter, grad: torch.Tensor):
+    grad = grad.reshape(param.shape).to(param.dtype)
+    param.grad = grad.clone() if param.grad is None else param.grad + grad
+
+
+class _Linear:
+    """y = x W^T (+ b), W in nn.Linear layout [N, K]; saves x for dW."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor] = None):
+        self.w, self.b = w.detach().float().contiguous(), (b.detach().float() if b is not None else None)
+
+    def fwd(self, x, residual=None):
+        self.x = x
+        return gemm_nt(x, self.w, bias=self.b, residual=residual)
+
+    def bwd(self, dy, add_to_dx=None):
+        """-> (dx (+ add_to_dx), dW [N, K], db or None)"""
+        dx = gemm_nt(dy, ops.transpose(self.w), residual=add_to_dx)
+        dw = gemm_nt(ops.transpose(dy), ops.transpose(self.x))
+        db = ops.col_sum(dy) if self.b is not None else None
+        return dx, dw, db
+
+
+# --------------------------------------------------------------------------------------------------------------
+# encoders
+# --------------------------------------------------------------------------------------------------------------
+class _XLNetGraph:
+    """HF:xlnet:979-1205 as exercised by the reference (oracle: xlnet_forward_restated)."""
+
+    def __init__(self, enc: XLNetEncoder):
+        self.enc = enc
+        cfg = enc.config
+        self.d, self.H, self.eps = cfg.d_model, cfg.n_head, float(cfg.layer_norm_eps)
+
+    def fwd(self, x: torch.Tensor, B: int, L: int) -> torch.Tensor:
+        d, H = self.d, self.H
+        self.B, self.L = B, L
+        self.tape = []
+        R_all = ops.rel_pos_proj([lyr.rel_attn.r.detach().reshape(d, d).contiguous() for lyr in self.enc.layer], L, d)
+        h = x
+        for li, lyr in enumerate(self.enc.layer):
+            ra, ff = lyr.rel_attn, lyr.ff
+            t = {}
+            wqkv = torch.cat([p.detach().reshape(d, d).t() for p in (ra.q, ra.k, ra.v)], dim=0)   # [3d, d]
+            t["qkv_lin"] = _Linear(wqkv)
+            qkv = t["qkv_lin"].fwd(h)
+            t["qkv"], t["R"] = qkv, R_all[li]
+            t["rw"], t["rr"] = ra.r_w_bias.detach().reshape(-1).float(), ra.r_r_bias.detach().reshape(-1).float()
+            a = ops.xlnet_attn_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H)
+            t["o_lin"] = _Linear(ra.o.detach().reshape(d, d))
+            h1_pre = t["o_lin"].fwd(a, residual=h)
+            t["h1_pre"] = h1_pre
+            h1 = ops.layer_norm_fwd(h1_pre, ra.layer_norm.weight.detach(), ra.layer_norm.bias.detach(), self.eps)
+            t["w1"] = _Linear(ff.layer_1.weight, ff.layer_1.bias)
+            ffp = t["w1"].fwd(h1)
+            t["ffp"] = ffp
+            g = ops.act_fwd(_lib.ACT_GELU, ffp)
+            t["w2"] = _Linear(ff.layer_2.weight, ff.layer_2.bias)
+            y_pre = t["w2"].fwd(g, residual=h1)
+            t["y_pre"] = y_pre
+            h = ops.layer_norm_fwd(y_pre, ff.layer_norm.weight.detach(), ff.layer_norm.bias.detach(), self.eps)
+            self.tape.append(t)
+        return h
+
+    def bwd(self, dh: torch.Tensor) -> torch.Tensor:
+        d, H, B, L = self.d, self.H, self.B, self.L
+        for li in reversed(range(len(self.enc.layer))):
+            lyr, t = self.enc.layer[li], self.tape[li]
+            ra, ff = lyr.rel_attn, lyr.ff
+            dy_pre, dg2, db2 = ops.layer_norm_bwd(t["y_pre"], ff.layer_norm.weight.detach(), self.eps, dh)
+            _acc(ff.layer_norm.weight, dg2); _acc(ff.layer_norm.bias, db2)
+            dgel, dw2, dbias2 = t["w2"].bwd(dy_pre)
+            _acc(ff.layer_2.weight, dw2); _acc(ff.layer_2.bias, dbias2)
+            dffp = ops.act_bwd(_lib.ACT_GELU, t["ffp"], dgel)
+            dh1, dw1, dbias1 = t["w1"].bwd(dffp, add_to_dx=dy_pre)   # + the residual branch of the feed-forward block
+            _acc(ff.layer_1.weight, dw1); _acc(ff.layer_1.bias, dbias1)
+            dh1_pre, dg1, db1 = ops.layer_norm_bwd(t["h1_pre"], ra.layer_norm.weight.detach(), self.eps, dh1)
+            _acc(ra.layer_norm.weight, dg1); _acc(ra.layer_norm.bias, db1)
+            da, dwo, _ = t["o_lin"].bwd(dh1_pre)
+            _acc(ra.o, dwo)                                       # o: [d_model, H, dh] == Linear weight [d, HD]
+            dqkv, dR, drw, drr = ops.xlnet_attn_bwd(t["qkv"], t["R"], t["rw"], t["rr"], da, B, L, H)
+            _acc(ra.r_w_bias, drw); _acc(ra.r_r_bias, drr)
+            # R = pos @ Wr  (Wr = r.reshape(d, HD)):  dWr = pos^T dR
+            pos = ops.rel_pos_table(L, d, dh.device)
+            _acc(ra.r, gemm_nt(ops.transpose(pos), ops.transpose(dR)))
+            dh, dwqkv, _ = t["qkv_lin"].bwd(dqkv, add_to_dx=dh1_pre)  # + the residual branch of the attention block
+            for j, p in enumerate((ra.q, ra.k, ra.v)):            # rows [j d, (j+1) d) of the fused weight = W_j^T
+                _acc(p, dwqkv[j * d:(j + 1) * d].t().contiguous())
+        return dh
+
+
+class _GPT2Graph:
+    """HF:gpt2:522-636 as exercised by the reference (oracle: gpt2_forward_restated); Conv1D weights are [in, out]."""
+
+    def __init__(self, enc: GPT2Encoder):
+        self.enc = enc
+        cfg = enc.config
+        self.d, self.H, self.eps = cfg.n_embd, cfg.n_head, float(cfg.layer_norm_epsilon)
+
+    def fwd(self, x: torch.Tensor, B: int, L: int) -> torch.Tensor:
+        d, H, enc = self.d, self.H, self.enc
+        self.B, self.L = B, L
+        self.tape = []
+        h = ops.add_positions(x, enc.wpe.weight.detach(), B, L)
+        for blk in enc.h:
+            t = {"h_in": h}
+            a = ops.layer_norm_fwd(h, blk.ln_1.weight.detach(), blk.ln_1.bias.detach(), self.eps)
+            t["qkv_lin"] = _Linear(blk.attn.c_attn.weight.detach().t(), blk.attn.c_attn.bias)
+            qkv = t["qkv_lin"].fwd(a)
+            t["qkv"] = qkv
+            o = ops.causal_attn_fwd(qkv, B, L, H)
+            t["o_lin"] = _Linear(blk.attn.c_proj.weight.detach().t(), blk.attn.c_proj.bias)
+            h = t["o_lin"].fwd(o, residual=h)
+            t["h_mid"] = h
+            m = ops.layer_norm_fwd(h, blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), self.eps)
+            t["fc"] = _Linear(blk.mlp.c_fc.weight.detach().t(), blk.mlp.c_fc.bias)
+            fp = t["fc"].fwd(m)
+            t["fp"] = fp
+            g = ops.act_fwd(_lib.ACT_GELU, fp)
+            t["pr"] = _Linear(blk.mlp.c_proj.weight.detach().t(), blk.mlp.c_proj.bias)
+            h = t["pr"].fwd(g, residual=h)
+            self.tape.append(t)
+        self.h_last = h
+        return ops.layer_norm_fwd(h, enc.ln_f.weight.detach(), enc.ln_f.bias.detach(), self.eps)
+
+    def bwd(self, dout: torch.Tensor) -> torch.Tensor:
+        enc, H, B, L = self.enc, self.H, self.B, self.L
+        dh, dg, db = ops.layer_norm_bwd(self.h_last, enc.ln_f.weight.detach(), self.eps, dout)
+        _acc(enc.ln_f.weight, dg); _acc(enc.ln_f.bias, db)
+        for li in reversed(range(len(enc.h))):
+            blk, t = enc.h[li], self.tape[li]
+            dgel, dwp, dbp = t["pr"].bwd(dh)
+            _acc(blk.mlp.c_proj.weight, dwp.t()); _acc(blk.mlp.c_proj.bias, dbp)
+            dfp = ops.act_bwd(_lib.ACT_GELU, t["fp"], dgel)
+            dm, dwf, dbf = t["fc"].bwd(dfp)
+            _acc(blk.mlp.c_fc.weight, dwf.t()); _acc(blk.mlp.c_fc.bias, dbf)
+            dh, dg2, db2 = ops.layer_norm_bwd(t["h_mid"], blk.ln_2.weight.detach(), self.eps, dm, add=dh)
+            _acc(blk.ln_2.weight, dg2); _acc(blk.ln_2.bias, db2)
+            do, dwo, dbo = t["o_lin"].bwd(dh)
+            _acc(blk.attn.c_proj.weight, dwo.t()); _acc(blk.attn.c_proj.bias, dbo)
+            dqkv = ops.causal_attn_bwd(t["qkv"], do, B, L, H)
+            da, dwq, dbq = t["qkv_lin"].bwd(dqkv)
+            _acc(blk.attn.c_attn.weight, dwq.t()); _acc(blk.attn.c_attn.bias, dbq)
+            dh, dg1, db1 = ops.layer_norm_bwd(t["h_in"], blk.ln_1.weight.detach(), self.eps, da, add=dh)
+            _acc(blk.ln_1.weight, dg1); _acc(blk.ln_1.bias, db1)
+        # h0 = x + wpe[:L]
+        _acc_rows(enc.wpe.weight, ops.sum_over_sessions(dh, B, L), L)
+        return dh
+
+
+def _acc_rows(param, rows, n):
+    g = torch.zeros_like(param)
+    g[:n] = rows
+    param.grad = g if param.grad is None else param.grad + g
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the whole step
+# --------------------------------------------------------------------------------------------------------------
+class FusedTrainingStep:
+    def __init__(self, model, head_chunk: int = 32768):
+        if len(model.heads) != 1 or len(model.heads[0].prediction_task_dict) != 1:
+            raise NotImplementedError("FusedTrainingStep: one head with one NextItemPredictionTask")
+        head = model.heads[0]
+        self.inputs, self.tblock = head.body[0], head.body[1]
+        self.task = next(iter(head.prediction_task_dict.values()))
+        inp, task = self.inputs, self.task
+        layout, self.C = inp._layout()
+        if (inp.aggregation or "concat") != "concat" or any(kind not in ("cat", "cont") for _, kind, *_ in layout):
+            raise NotImplementedError("FusedTrainingStep: categorical / continuous features with concat aggregation")
+        if inp._projection_linear() is None or inp.pre is not None:
+            raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
+        if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling)):
+            raise NotImplementedError("FusedTrainingStep: MLM or CLM masking")
+        if not task.weight_tying or task.sampled_softmax or task._sharded() or task.label_smoothing:
+            raise NotImplementedError("FusedTrainingStep: tied weights, full softmax, replicated table, no label smoothing")
+        enc = self.tblock.transformer
+        self.graph = _XLNetGraph(enc) if isinstance(enc, XLNetEncoder) else _GPT2Graph(enc)
+        self.layout = layout
+        self.head_chunk = int(head_chunk)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        inp, task = self.inputs, self.task
+        cm = inp.categorical_module
+        ids = batch[cm.item_id]
+        B, L = ids.shape
+        M = B * L
+        self.B, self.L, self.M = B, L, M
+        cm.item_seq = ids
+        inp.masking.compute_masked_targets(ids, training=True, testing=False)
+        code = inp.masking.row_code.reshape(-1)
+        self.code = code
+        # K1 gather + concat (fp32 rows; the gather is recomputed in the backward instead of being kept)
+        cats, conts = [], []
+        for name, kind, col, width in self.layout:
+            v = batch[name].reshape(-1)
+            if kind == "cat":
+                cats.append((cm.embedding_tables[name].weight.detach(), v, col))
+            else:
+                conts.append((v, col))
+        self.cats, self.conts = cats, conts
+        concat, _, _ = ops.embed_concat(cats, conts, M, self.C, want_f32=True, want_planes=False)
+        # K2 projection + activation, then the mask replace (apply_mask_to_inputs)
+        lin = inp._projection_linear()
+        self.proj = _Linear(lin.weight, lin.bias)
+        self.proj_pre = self.proj.fwd(concat)
+        self.proj_act = inp._projection_act()
+        y = ops.act_fwd(self.proj_act, self.proj_pre) if self.proj_act != _lib.ACT_NONE else self.proj_pre
+        x0 = ops.apply_row_codes(y, code, inp.masking.masked_item_embedding.detach().float())
+        # encoder
+        h = self.graph.fwd(x0, B, L)
+        # head: label rows, optional task_block, fused loss (keeps the per-row log-sum-exp)
+        self.tgt_rows, self.labels, count = ops.compact_targets(inp.masking.masked_targets, task.padding_idx)
+        T = int(count.item())                                  # the reference's masked_select synchronises too
+        self.T = T
+        xt = ops.gather_rows(h, self.tgt_rows[:T])
+        self.tb = []
+        if task.task_block is not None:
+            for blk in task.task_block:
+                if blk.act_code() != _lib.ACT_NONE:
+                    raise NotImplementedError("FusedTrainingStep: task_block without activation (the reference default)")
+                lin_tb = _Linear(blk[0].weight, blk[0].bias)
+                xt = lin_tb.fwd(xt)
+                self.tb.append((blk[0], lin_tb))
+        self.xt = xt
+        W = task.output_weight().detach().float()
+        inv_tau = task._inv_tau()
+        y_lab = self.labels[:T]
+        res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(W), W, inv_temperature=inv_tau)
+        self.row_lse = res["row_lse"]
+        self.loss = res["loss"].reshape(())
+        return self.loss
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def backward(self, grad_loss: float = 1.0):
+        inp, task = self.inputs, self.task
+        cm = inp.categorical_module
+        T, M = self.T, self.M
+        Wp = task.output_weight()
+        W = Wp.detach().float()
+        V, De = W.shape
+        inv_tau = task._inv_tau()
+        y_lab = self.labels[:T]
+        scale = float(grad_loss) / max(T, 1)
+        dxt = torch.zeros_like(self.xt)
+        dW = torch.zeros_like(W)
+        xt_t = ops.transpose(self.xt)                                   # [De, T]
+        xt_planes = ops.split_planes(self.xt)
+        for v0 in range(0, V, self.head_chunk):
+            v1 = min(V, v0 + self.head_chunk)
+            Wc = W[v0:v1].contiguous()
+            z = ops.head_logits(xt_planes, ops.split_planes(Wc), De, inv_temperature=inv_tau)          # [T, Vc]
+            P = ops.softmax_ce_bwd(z, self.row_lse, y_lab, v0, scale * inv_tau)   # (softmax - onehot) * dL/dz scale
+            dxt = gemm_nt(P, ops.transpose(Wc), residual=dxt)              # dX_t += P W_c
+            dW[v0:v1] = gemm_nt(ops.transpose(P), xt_t)                      # dW_c = P^T X_t
+        _acc(Wp, dW)                                                        # tied: the item table's grad starts here
+        for lin_mod, lin_tb in reversed(self.tb):
+            dxt, dwt, dbt = lin_tb.bwd(dxt)
+            _acc(lin_mod.weight, dwt)
+            if lin_mod.bias is not None:
+                _acc(lin_mod.bias, dbt)
+        dh = ops.scatter_rows(dxt, self.tgt_rows[:T], M)                    # zero outside the label rows
+        dx0 = self.graph.bwd(dh)
+        # mask replace: rows with code 1 took masked_item_embedding, code 2 are constant zero
+        dmask, dy = ops.row_codes_bwd(dx0, self.code)
+        _acc(inp.masking.masked_item_embedding, dmask)
+        dpre = ops.act_bwd(self.proj_act, self.proj_pre, dy) if self.proj_act != _lib.ACT_NONE else dy
+        dconcat, dwp, dbp = self.proj.bwd(dpre)
+        lin = inp._projection_linear()
+        _acc(lin.weight, dwp)
+        if lin.bias is not None:
+            _acc(lin.bias, dbp)
+        # embedding rows: scatter-add the column slice of every categorical feature (padding row gets no gradient)
+        for table, ids, col in self.cats:
+            param = next(p for p in cm.parameters() if p.data_ptr() == table.data_ptr())
+            g = torch.zeros_like(table) if param.grad is None else param.grad
+            ops.index_add_rows(g, ids.reshape(-1), dconcat, col, table.shape[1], skip_index=inp.masking.padding_idx)
+            param.grad = g
+        return self.loss
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """loss = FusedTrainingStep(...) as ONE autograd node over all parameters: the forward runs the step's forward AND
+    backward eagerly (gradients parked aside), ``backward`` scales and returns them."""
+
+    @staticmethod
+    def forward(ctx, step: FusedTrainingStep, batch, *params):
+        saved = [p.grad for p in params]
+        for p in params:
+            p.grad = None
+        with torch.no_grad():
+            loss = step.forward(batch)
+            step.backward(1.0)
+        ctx.grads = [p.grad for p in params]
+        for p, g in zip(params, saved):
+            p.grad = g
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None, None) + tuple(None if g is None else g * grad_out for g in ctx.grads)
+
+
+def training_loss(model, batch, step: Optional[FusedTrainingStep] = None) -> torch.Tensor:
+    """Differentiable training loss of the fused path: ``training_loss(model, batch).backward()`` fills ``.grad``."""
+    step = step or FusedTrainingStep(model)
+    params = [p for p in model.parameters() if p.requires_grad]
+    return _FusedLossFn.apply(step, batch, *params)
