@@ -416,6 +416,48 @@ int t4r_head_logits_mixed(const void* xt_planes, const void* w_planes, int T_cap
                           float inv_temperature, float* out /*[T_cap, ldo]*/, int64_t ldo, const float* xt_inv_scale,
                           const float* w_inv_scale, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * N3  element / row kernels of the training step (csrc/t4r_train.cu; composed by
+ *     transformers4rec_b200/training.py with the GEMMs above on transposed operands).  All fp32, row-major.
+ *     `on_host` != 0 runs the same per-item code in a loop on HOST pointers (no CUDA call): test infrastructure.
+ *     Reference counterparts: torch autograd of the modules at block/mlp.py:123-144, HF XLNet / GPT-2 layers,
+ *     masking.py:473-498 / :302-337, model/prediction_task.py:648-671 + :446, features/embedding.py:226-249.
+ * ------------------------------------------------------------------------- */
+int t4r_train_transpose(const float* x, int64_t R, int64_t C, float* out /*[C, R]*/, void* stream, int on_host);
+int t4r_train_act_fwd(int kind, const float* x, float* y, int64_t n, void* stream, int on_host);  /* exact erf GELU / ReLU */
+int t4r_train_act_bwd(int kind, const float* pre, const float* dy, float* dx, int64_t n, void* stream, int on_host);
+int t4r_train_add_positions(const float* x, const float* wpe, int B, int L, int d, float* y, void* stream, int on_host);
+int t4r_train_sum_sessions(const float* x, int B, int L, int d, float* out /*[L, d]*/, void* stream, int on_host);
+int t4r_train_row_codes_fwd(const float* y, const uint8_t* code, const float* mask_vec, int64_t M, int d, float* out,
+                            void* stream, int on_host);
+int t4r_train_row_codes_bwd(const float* dx, const uint8_t* code, int64_t M, int d, float* dy, float* dmask /*[d]*/,
+                            void* stream, int on_host);
+int t4r_train_gather_rows(const float* x, const int32_t* idx, int64_t n, int d, float* out, void* stream, int on_host);
+int t4r_train_scatter_rows(const float* src, const int32_t* idx, int64_t n, int d, int64_t out_rows, float* out,
+                           void* stream, int on_host);
+/* in place: z[t, j] <- (exp(z[t, j] - lse[t]) - [labels[t] == v0 + j]) * scale */
+int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_t* labels, int64_t T, int64_t Vc, int64_t v0,
+                             float scale, void* stream, int on_host);
+/* dst[idx[r], :] += src[r, col : col + width] (dst rows are `width` wide); rows with idx == skip_index are skipped */
+int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src, int col,
+                             int width, int64_t skip_index, void* stream, int on_host);
+int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out /*[N]*/, void* stream, int on_host);
+int t4r_train_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t M, int d, float eps, float* y,
+                             void* stream, int on_host);
+/* dx = LayerNorm backward of dy at x (+ add, optional); dgamma / dbeta [d] are overwritten */
+int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int64_t M, int d, float eps, const float* dy,
+                             const float* add, float* dx, float* dgamma, float* dbeta, void* stream, int on_host);
+/* attention backward, scores recomputed (L <= 64).  qkv / dqkv [M, 3d] (q | k | v), dout [M, d].  XLNet relative
+ * form: R [2L, d], rw / rr [d] and their gradients; all six NULL selects GPT-2's causal form. */
+int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B, int L,
+                       int d, int H, float* dqkv, float* dR, float* drw, float* drr, void* stream, int on_host);
+/* forward pieces of the training graph that reuse inference kernels on fp32 q|k|v (device only) */
+int t4r_train_xlnet_attn_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d, int H,
+                             void* out_planes /*[2, M, d]*/, void* stream);
+int t4r_train_causal_attn_fwd(const float* qkv, int B, int L, int d, int H, void* out_planes, void* stream);
+int t4r_train_rel_pos_proj(const float* const* wr /*host array of device ptrs*/, int n_layer, int L, int d,
+                           float* r_out /*[n_layer, 2L, d]*/, void* stream);
+
 /* K10 Recall@k from label ranks: out[j] = mean_t(rank[t] < ks[j]).
  * replaces RecallAt._metric + RankingMetric.update ranking_metric.py:52-63,111-147 */
 int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks /*host*/,

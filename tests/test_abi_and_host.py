@@ -405,3 +405,73 @@ def test_plm_mask_host_twin_matches_oracle_large():
         rm, rl, _, rpm, _ = O.plm_compute_masked_targets(ids, False, eval_on_last_item_seq_only=last)
         assert torch.equal(m, rm) and torch.equal(l, rl) and torch.equal(pm, rpm.to(torch.uint8))
         assert nonempty.any()
+
+
+# --------------------------------------------------------------------------- #
+# N3: the training kernels' per-item code on its host twins vs torch (the doubles of tests/_ops_double.py are the
+# specification the composition test uses; here the real code is held to them)
+# --------------------------------------------------------------------------- #
+def test_training_kernels_host_twins_match_torch():
+    import _ops_double as DD
+    from transformers4rec_b200 import _lib, ops
+    g = torch.Generator().manual_seed(31)
+    H = ops.host_twin
+    x = torch.randn(37, 24, generator=g)
+    dy = torch.randn(37, 24, generator=g)
+    close = lambda a, b, tol=2e-6: (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    assert torch.equal(H("transpose")(x), DD.transpose(x))
+    for kind in (_lib.ACT_GELU, _lib.ACT_RELU):
+        assert close(H("act_fwd")(kind, x), DD.act_fwd(kind, x))
+        assert close(H("act_bwd")(kind, x, dy), DD.act_bwd(kind, x, dy))
+    big = torch.randn(700, 24, generator=g)
+    assert close(H("col_sum")(big), DD.col_sum(big), 1e-5)
+    gamma, beta = torch.rand(24, generator=g) + 0.5, torch.randn(24, generator=g)
+    assert close(H("layer_norm_fwd")(x, gamma, beta, 0.03), DD.layer_norm_fwd(x, gamma, beta, 0.03), 1e-5)
+    add = torch.randn(37, 24, generator=g)
+    for a in (None, add):
+        got, ref = H("layer_norm_bwd")(x, gamma, 0.03, dy, add=a), DD.layer_norm_bwd(x, gamma, 0.03, dy, add=a)
+        assert all(close(u, v, 1e-5) for u, v in zip(got, ref))
+    B, L = 3, 4
+    xs = torch.randn(B * L, 24, generator=g)
+    wpe = torch.randn(9, 24, generator=g)
+    assert close(H("add_positions")(xs, wpe, B, L), DD.add_positions(xs, wpe, B, L))
+    assert close(H("sum_over_sessions")(xs, B, L), DD.sum_over_sessions(xs, B, L), 1e-5)
+    code = torch.randint(0, 3, (37,), generator=g).to(torch.uint8)
+    mv = torch.randn(24, generator=g)
+    assert torch.equal(H("apply_row_codes")(x, code, mv), DD.apply_row_codes(x, code, mv))
+    dm, dyy = H("row_codes_bwd")(dy, code)
+    rm, ry = DD.row_codes_bwd(dy, code)
+    assert close(dm, rm, 1e-5) and torch.equal(dyy, ry)
+    idx = torch.randperm(37, generator=g)[:11].int()
+    assert torch.equal(H("gather_rows")(x, idx), DD.gather_rows(x, idx))
+    src = torch.randn(11, 24, generator=g)
+    assert torch.equal(H("scatter_rows")(src, idx, 37), DD.scatter_rows(src, idx, 37))
+    T, Vc, v0 = 9, 50, 100
+    z = torch.randn(T, Vc, generator=g)
+    lse = torch.logsumexp(z, 1) + 0.3
+    labels = torch.randint(90, 160, (T,), generator=g)
+    assert close(H("softmax_ce_bwd")(z.clone(), lse, labels, v0, 0.25), DD.softmax_ce_bwd(z.clone(), lse, labels, v0, 0.25))
+    ids = torch.randint(0, 20, (37,), generator=g)
+    dst1, dst2 = torch.zeros(20, 8), torch.zeros(20, 8)
+    H("index_add_rows")(dst1, ids, x, 5, 8, skip_index=0)
+    DD.index_add_rows(dst2, ids, x, 5, 8, skip_index=0)
+    assert close(dst1, dst2, 1e-5) and not dst1[0].any()
+
+
+@pytest.mark.parametrize("L,H,dh", [(5, 2, 8), (12, 3, 4), (20, 1, 16)])
+def test_attention_backward_host_twin_matches_autograd(L, H, dh):
+    import _ops_double as DD
+    from transformers4rec_b200 import ops
+    g = torch.Generator().manual_seed(32)
+    B, d = 3, H * dh
+    qkv = torch.randn(B * L, 3 * d, generator=g)
+    R = torch.randn(2 * L, d, generator=g)
+    rw, rr = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    dout = torch.randn(B * L, d, generator=g)
+    got = ops.host_twin("xlnet_attn_bwd")(qkv, R, rw, rr, dout, B, L, H)
+    ref = DD.xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H)
+    for name, a, b in zip(("dqkv", "dR", "drw", "drr"), got, ref):
+        assert (a - b).abs().max().item() < 2e-4 * max(1.0, b.abs().max().item()), name
+    got = ops.host_twin("causal_attn_bwd")(qkv, dout, B, L, H)
+    ref = DD.causal_attn_bwd(qkv, dout, B, L, H)
+    assert (got - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())

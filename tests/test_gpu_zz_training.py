@@ -1,0 +1,79 @@
+"""GPU tests of the training step (transformers4rec_b200/training.py, csrc/t4r_train.cu).  Written after
+the round's GPU budget was spent; CPU-side evidence: the composition matches torch autograd of the oracle graph with
+kernel doubles AND with the kernels' real per-item code on their host twins (tests/test_host_training_cpu.py,
+tests/test_abi_and_host.py).  Opt-in (``T4R_TEST_EXPERIMENTAL=1``) until it has run once on hardware."""
+import os
+
+import pytest
+import torch
+
+import _ops_double as DD
+from _util import make_pair, mlm_draws, synth_batch
+from test_host_training_cpu import _oracle_grads, _pairs
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("T4R_TEST_EXPERIMENTAL") != "1",
+                                 reason="training step not yet validated on hardware (set T4R_TEST_EXPERIMENTAL=1)")]
+
+
+def test_training_primitives_device_vs_host_twin():
+    from transformers4rec_b200 import _lib, ops
+    g = torch.Generator().manual_seed(41)
+    H = ops.host_twin
+    close = lambda a, b, tol=1e-5: (a.cpu() - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    x, dy = torch.randn(300, 96, generator=g), torch.randn(300, 96, generator=g)
+    assert torch.equal(ops.transpose(x.cuda()).cpu(), H("transpose")(x))
+    for kind in (_lib.ACT_GELU, _lib.ACT_RELU):
+        assert close(ops.act_fwd(kind, x.cuda()), H("act_fwd")(kind, x))
+        assert close(ops.act_bwd(kind, x.cuda(), dy.cuda()), H("act_bwd")(kind, x, dy))
+    assert close(ops.col_sum(x.cuda()), H("col_sum")(x), 1e-4)
+    gam, bet = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g)
+    assert close(ops.layer_norm_fwd(x.cuda(), gam.cuda(), bet.cuda(), 0.03), H("layer_norm_fwd")(x, gam, bet, 0.03))
+    got = ops.layer_norm_bwd(x.cuda(), gam.cuda(), 0.03, dy.cuda(), add=x.cuda())
+    ref = H("layer_norm_bwd")(x, gam, 0.03, dy, add=x)
+    assert all(close(a, b, 1e-4) for a, b in zip(got, ref))
+    B, L, Hh, dh = 5, 20, 4, 16
+    d = Hh * dh
+    qkv = torch.randn(B * L, 3 * d, generator=g)
+    R, rw, rr = torch.randn(2 * L, d, generator=g), torch.randn(d, generator=g), torch.randn(d, generator=g)
+    dout = torch.randn(B * L, d, generator=g)
+    got = ops.xlnet_attn_bwd(qkv.cuda(), R.cuda(), rw.cuda(), rr.cuda(), dout.cuda(), B, L, Hh)
+    ref = H("xlnet_attn_bwd")(qkv, R, rw, rr, dout, B, L, Hh)
+    assert all(close(a, b, 1e-4) for a, b in zip(got, ref))
+    assert close(ops.causal_attn_bwd(qkv.cuda(), dout.cuda(), B, L, Hh), H("causal_attn_bwd")(qkv, dout, B, L, Hh), 1e-4)
+    # the forward attention wrappers (inference kernels on fp32 q|k|v) against the doubles
+    assert close(ops.xlnet_attn_fwd(qkv.cuda(), R.cuda(), rw.cuda(), rr.cuda(), B, L, Hh), DD.xlnet_attn_fwd(qkv, R, rw, rr, B, L, Hh), 1e-4)
+    assert close(ops.causal_attn_fwd(qkv.cuda(), B, L, Hh), DD.causal_attn_fwd(qkv, B, L, Hh), 1e-4)
+
+
+@pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("gpt2", "clm")])
+def test_training_step_gradients_on_gpu(arch, masking):
+    from transformers4rec_b200.training import FusedTrainingStep, training_loss
+    cards = {"item_id/list": 3001, "category/list": 37}
+    dims = {"item_id/list": 64, "category/list": 64}
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 2, 20, arch=arch, masking=masking, weight_scale=0.08)
+    oracle.train(False)
+    B, L = 32, 20
+    batch = synth_batch(B, L, cards, seed=3)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    ref_loss = _oracle_grads(oracle, batch, draws)
+    step = FusedTrainingStep(model, head_chunk=1024)
+    dev = {k: v.cuda() for k, v in batch.items()}
+    loss = training_loss(model, dev, step)
+    loss.backward()
+    assert abs(loss.item() - ref_loss) < 1e-3
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)
+    # a few optimizer steps (torch.optim is plumbing) must lower the loss on the same batch
+    opt = torch.optim.SGD(model.parameters(), lr=0.5)
+    first = loss.item()
+    for _ in range(5):
+        opt.zero_grad()
+        l = training_loss(model, dev, step)
+        l.backward()
+        opt.step()
+    assert l.item() < first

@@ -81,3 +81,37 @@ def test_training_step_gradients_match_autograd(monkeypatch, arch, masking, dims
     for n, p in model.named_parameters():
         if n in saved:
             assert torch.allclose(p.grad, 2.0 * saved[n], atol=1e-6), n
+
+
+def test_training_step_with_the_real_per_item_code(monkeypatch):
+    """Same gradient check, but every element / row primitive of t4r_train.cu runs its REAL per-item code through the
+    host twins (only the GEMMs, the gathers and the forward attention / head kernels stay doubles)."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    names = ("transpose", "act_fwd", "act_bwd", "add_positions", "sum_over_sessions", "apply_row_codes", "row_codes_bwd",
+             "gather_rows", "scatter_rows", "softmax_ce_bwd", "index_add_rows", "col_sum", "layer_norm_fwd",
+             "layer_norm_bwd", "xlnet_attn_bwd", "causal_attn_bwd")
+    twins = {name: ops.host_twin(name) for name in names}   # bound to the real entry points before the doubles go in
+    D.install(monkeypatch)
+    for name in names:
+        monkeypatch.setattr(ops, name, twins[name])
+    for arch, masking in (("xlnet", "mlm"), ("gpt2", "clm")):
+        oracle, model = make_pair(CARDS, {"item_id/list": 16, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                                  arch=arch, masking=masking, device="cpu", weight_scale=0.08)
+        oracle.train(False)
+        B, L = 5, 8
+        batch = synth_batch(B, L, CARDS, CONT, seed=4)
+        u, draws = mlm_draws(B, L)
+        model.heads[0].body[0].masking.set_draws(u)
+        ref_loss = _oracle_grads(oracle, batch, draws)
+        step = FusedTrainingStep(model, head_chunk=512)
+        for p in model.parameters():
+            p.grad = None
+        loss = step.forward(batch)
+        step.backward()
+        assert abs(loss.item() - ref_loss) < 1e-4
+        for name, po, pm in _pairs(oracle, model):
+            if po.grad is None and pm.grad is None:
+                continue
+            err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+            assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (arch, name, err)

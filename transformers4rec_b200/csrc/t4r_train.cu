@@ -1,0 +1,348 @@
+// t4r_train.cu -- element / row kernels of the training step (transformers4rec_b200/training.py).
+//
+// Every matmul of the backward is the tcgen05 GEMM of t4r_gemm.cu on transposed operands; what is left are the small
+// pieces below.  Each is written as a __host__ __device__ function of ONE work item (element, row, column slab,
+// or attention query row) that a trivial kernel calls once per thread -- and that the same entry point calls in a
+// plain loop when `on_host` is set (HOST pointers, no CUDA call), so that the CPU suite can pin the arithmetic
+// against torch without a GPU.  Accumulations across work items use atomicAdd on the device (plain += on the host).
+// These are first, correct versions: the attention backward in particular trades speed for simplicity (one thread
+// per query row, atomics for dK / dV / dR); none of this is on the inference path.
+#include <math.h>
+
+#include "t4r_common.cuh"
+#include "t4r_internal.h"
+
+namespace t4r {
+
+#if defined(__CUDA_ARCH__)
+#define T4R_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
+#else
+#define T4R_ATOMIC_ADD(ptr, val) (*(ptr) += (val))
+#endif
+#define T4R_HD __host__ __device__ inline
+
+// ---------------------------------------------------------------------------------------------- element-wise
+T4R_HD float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+T4R_HD float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+T4R_HD void transpose_item(const float* x, int64_t R, int64_t C, float* out, int64_t i) {
+  const int64_t r = i / C, c = i % C;
+  out[c * R + r] = x[i];
+}
+T4R_HD void act_fwd_item(int kind, const float* x, float* y, int64_t i) {
+  const float v = x[i];
+  y[i] = kind == T4R_ACT_GELU ? gelu_exact(v) : (kind == T4R_ACT_RELU ? fmaxf(v, 0.f) : v);
+}
+T4R_HD void act_bwd_item(int kind, const float* pre, const float* dy, float* dx, int64_t i) {
+  const float v = pre[i];
+  dx[i] = dy[i] * (kind == T4R_ACT_GELU ? gelu_grad(v) : (kind == T4R_ACT_RELU ? (v > 0.f ? 1.f : 0.f) : 1.f));
+}
+// y[b, l, :] = x[b, l, :] + wpe[l, :]
+T4R_HD void add_pos_item(const float* x, const float* wpe, int L, int d, float* y, int64_t i) {
+  const int64_t row = i / d;
+  y[i] = x[i] + wpe[(row % L) * d + (i % d)];
+}
+// out[l, c] = sum_b x[b, l, c]
+T4R_HD void sum_sessions_item(const float* x, int B, int L, int d, float* out, int64_t i) {
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += x[static_cast<int64_t>(b) * L * d + i];
+  out[i] = s;
+}
+// apply_mask_to_inputs as row codes: 0 keep, 1 -> mask_vec, 2 -> 0
+T4R_HD void row_codes_fwd_item(const float* y, const uint8_t* code, const float* mask_vec, int d, float* out, int64_t i) {
+  const int c = code[i / d];
+  out[i] = c == 0 ? y[i] : (c == 1 ? mask_vec[i % d] : 0.f);
+}
+T4R_HD void row_codes_bwd_item(const float* dx, const uint8_t* code, int d, float* dy, float* dmask, int64_t i) {
+  const int c = code[i / d];
+  dy[i] = c == 0 ? dx[i] : 0.f;
+  if (c == 1) T4R_ATOMIC_ADD(dmask + (i % d), dx[i]);
+}
+T4R_HD void gather_rows_item(const float* x, const int32_t* idx, int d, float* out, int64_t i) {
+  out[i] = x[static_cast<int64_t>(idx[i / d]) * d + (i % d)];
+}
+T4R_HD void scatter_rows_item(const float* src, const int32_t* idx, int d, float* out, int64_t i) {
+  out[static_cast<int64_t>(idx[i / d]) * d + (i % d)] = src[i];  // label rows are unique
+}
+// P = exp(z - lse) * scale, minus scale at the label's column (if it falls in this column chunk)
+T4R_HD void softmax_ce_bwd_item(float* z, const float* lse, const int64_t* labels, int64_t Vc, int64_t v0, float scale,
+                                int64_t i) {
+  const int64_t t = i / Vc, j = i % Vc;
+  float p = expf(z[i] - lse[t]) * scale;
+  if (labels[t] - v0 == j) p -= scale;
+  z[i] = p;
+}
+// dst[idx[r], 0:width] += src[r, col:col+width]   (skip rows whose index is skip_index)
+T4R_HD void index_add_item(float* dst, const int64_t* idx, const float* src, int64_t ld_src, int col, int width,
+                           int64_t skip_index, int64_t i) {
+  const int64_t r = i / width;
+  const int c = static_cast<int>(i % width);
+  const int64_t row = idx[r];
+  if (row == skip_index) return;
+  T4R_ATOMIC_ADD(dst + row * width + c, src[r * ld_src + col + c]);
+}
+// column sums over a slab of rows: one item = (column, slab)
+T4R_HD void col_sum_item(const float* x, int64_t M, int64_t N, int rows_per_slab, float* out, int64_t i) {
+  const int64_t c = i % N, slab = i / N;
+  const int64_t r0 = slab * rows_per_slab, r1 = (r0 + rows_per_slab < M) ? r0 + rows_per_slab : M;
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += x[r * N + c];
+  T4R_ATOMIC_ADD(out + c, s);
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm (rows)
+T4R_HD void ln_fwd_row(const float* x, const float* g, const float* b, int d, float eps, float* y, int64_t row) {
+  const float* xr = x + row * d;
+  float mean = 0.f;
+  for (int c = 0; c < d; ++c) mean += xr[c];
+  mean /= d;
+  float var = 0.f;
+  for (int c = 0; c < d; ++c) { const float t = xr[c] - mean; var += t * t; }
+  const float rstd = 1.0f / sqrtf(var / d + eps);
+  for (int c = 0; c < d; ++c) y[row * d + c] = (xr[c] - mean) * rstd * g[c] + b[c];
+}
+// dx = rstd (g dy - mean(g dy) - xhat mean(g dy xhat)) (+ add);  dgamma += dy xhat;  dbeta += dy
+T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const float* dy, const float* add, float* dx,
+                       float* dgamma, float* dbeta, int64_t row) {
+  const float* xr = x + row * d;
+  const float* dyr = dy + row * d;
+  float mean = 0.f;
+  for (int c = 0; c < d; ++c) mean += xr[c];
+  mean /= d;
+  float var = 0.f;
+  for (int c = 0; c < d; ++c) { const float t = xr[c] - mean; var += t * t; }
+  const float rstd = 1.0f / sqrtf(var / d + eps);
+  float m1 = 0.f, m2 = 0.f;
+  for (int c = 0; c < d; ++c) {
+    const float xh = (xr[c] - mean) * rstd, gd = g[c] * dyr[c];
+    m1 += gd;
+    m2 += gd * xh;
+  }
+  m1 /= d;
+  m2 /= d;
+  for (int c = 0; c < d; ++c) {
+    const float xh = (xr[c] - mean) * rstd, gd = g[c] * dyr[c];
+    float v = rstd * (gd - m1 - xh * m2);
+    if (add) v += add[row * d + c];
+    dx[row * d + c] = v;
+    T4R_ATOMIC_ADD(dgamma + c, dyr[c] * xh);
+    T4R_ATOMIC_ADD(dbeta + c, dyr[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- attention backward
+// One item = (session b, head h, query row i).  qkv [M, 3d] fp32 (q | k | v), R [2L, d], rw / rr [d] (XLNet; null for
+// the causal GPT-2 form), dout [M, d].  Scores are recomputed (L <= 64), then
+//   dp_j = do_i . v_j ;  ds_j = p_j (dp_j - sum_k p_k dp_k) / sqrt(dh)
+//   dq_i = sum_j ds_j (k_j + R_m)        dk_j += ds_j (q_i + rw)        dv_j += p_j do_i
+//   dR_m += ds_j (q_i + rr)              drw  += ds_j k_j               drr  += ds_j R_m          m = j + L - i
+constexpr int kAttnMaxL = 64;
+T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
+                          int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, int64_t item) {
+  const int dh = d / H;
+  const int i = static_cast<int>(item % L);
+  const int h = static_cast<int>((item / L) % H);
+  const int64_t b = item / (static_cast<int64_t>(L) * H);
+  const bool rel = R != nullptr;
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  const float* q = qkv + (b * L + i) * 3 * d + h * dh;
+  const float* dor = dout + (b * L + i) * d + h * dh;
+  float s[kAttnMaxL], dp[kAttnMaxL];
+  float mx = -INFINITY;
+  for (int j = 0; j < L; ++j) {
+    if (!rel && j > i) { s[j] = -INFINITY; continue; }
+    const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
+    float acc = 0.f;
+    if (rel) {
+      const float* Rm = R + static_cast<int64_t>(j + L - i) * d + h * dh;
+      for (int c = 0; c < dh; ++c) acc += (q[c] + rw[h * dh + c]) * k[c] + (q[c] + rr[h * dh + c]) * Rm[c];
+    } else {
+      for (int c = 0; c < dh; ++c) acc += q[c] * k[c];
+    }
+    s[j] = acc * scale;
+    mx = fmaxf(mx, s[j]);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < L; ++j) { s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx); sum += s[j]; }
+  const float inv = 1.0f / sum;
+  float dot = 0.f;
+  for (int j = 0; j < L; ++j) {
+    s[j] *= inv;                                            // p_j
+    const float* v = qkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+    float acc = 0.f;
+    for (int c = 0; c < dh; ++c) acc += dor[c] * v[c];
+    dp[j] = acc;
+    dot += s[j] * acc;
+  }
+  float* dq = dqkv + (b * L + i) * 3 * d + h * dh;
+  for (int c = 0; c < dh; ++c) dq[c] = 0.f;                 // this item owns dq_i of its head
+  for (int j = 0; j < L; ++j) {
+    const float p = s[j];
+    if (p == 0.f && (!rel && j > i)) continue;
+    const float ds = p * (dp[j] - dot) * scale;
+    const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
+    float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
+    float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+    if (rel) {
+      const int64_t m = j + L - i;
+      const float* Rm = R + m * d + h * dh;
+      for (int c = 0; c < dh; ++c) {
+        dq[c] += ds * (k[c] + Rm[c]);
+        T4R_ATOMIC_ADD(dk + c, ds * (q[c] + rw[h * dh + c]));
+        T4R_ATOMIC_ADD(dv + c, p * dor[c]);
+        T4R_ATOMIC_ADD(dR + m * d + h * dh + c, ds * (q[c] + rr[h * dh + c]));
+        T4R_ATOMIC_ADD(drw + h * dh + c, ds * k[c]);
+        T4R_ATOMIC_ADD(drr + h * dh + c, ds * Rm[c]);
+      }
+    } else {
+      for (int c = 0; c < dh; ++c) {
+        dq[c] += ds * k[c];
+        T4R_ATOMIC_ADD(dk + c, ds * q[c]);
+        T4R_ATOMIC_ADD(dv + c, p * dor[c]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- launch plumbing
+template <typename F>
+__global__ void __launch_bounds__(256) items_kernel(int64_t n, F f) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+template <typename F>
+static int run_items(int64_t n, F f, const char* name, void* stream, int on_host) {
+  if (n <= 0) return 0;
+  if (on_host) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return 0;
+  }
+  T4R_REQUIRE(n < (1ll << 31) * 256, "%s: too many work items", name);
+  items_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(n, f);
+  T4R_LAUNCH_CHECK(name);
+  return 0;
+}
+static int zero(void* p, size_t bytes, void* stream, int on_host) {
+  if (on_host) { memset(p, 0, bytes); return 0; }
+  T4R_CUDA(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // namespace t4r
+
+using namespace t4r;
+#define T4R_ITEMS(n, name, ...) return run_items((n), [=] __host__ __device__(int64_t i) { __VA_ARGS__; }, name, stream, on_host)
+
+extern "C" int t4r_train_transpose(const float* x, int64_t R, int64_t C, float* out, void* stream, int on_host) {
+  T4R_REQUIRE(x && out && R > 0 && C > 0, "train_transpose: bad arguments");
+  T4R_ITEMS(R * C, "train_transpose", transpose_item(x, R, C, out, i));
+}
+extern "C" int t4r_train_act_fwd(int kind, const float* x, float* y, int64_t n, void* stream, int on_host) {
+  T4R_REQUIRE(x && y && n > 0, "train_act_fwd: bad arguments");
+  T4R_ITEMS(n, "train_act_fwd", act_fwd_item(kind, x, y, i));
+}
+extern "C" int t4r_train_act_bwd(int kind, const float* pre, const float* dy, float* dx, int64_t n, void* stream,
+                                 int on_host) {
+  T4R_REQUIRE(pre && dy && dx && n > 0, "train_act_bwd: bad arguments");
+  T4R_ITEMS(n, "train_act_bwd", act_bwd_item(kind, pre, dy, dx, i));
+}
+extern "C" int t4r_train_add_positions(const float* x, const float* wpe, int B, int L, int d, float* y, void* stream,
+                                       int on_host) {
+  T4R_REQUIRE(x && wpe && y && B > 0 && L > 0 && d > 0, "train_add_positions: bad arguments");
+  T4R_ITEMS(static_cast<int64_t>(B) * L * d, "train_add_positions", add_pos_item(x, wpe, L, d, y, i));
+}
+extern "C" int t4r_train_sum_sessions(const float* x, int B, int L, int d, float* out, void* stream, int on_host) {
+  T4R_REQUIRE(x && out && B > 0 && L > 0 && d > 0, "train_sum_sessions: bad arguments");
+  T4R_ITEMS(static_cast<int64_t>(L) * d, "train_sum_sessions", sum_sessions_item(x, B, L, d, out, i));
+}
+extern "C" int t4r_train_row_codes_fwd(const float* y, const uint8_t* code, const float* mask_vec, int64_t M, int d,
+                                       float* out, void* stream, int on_host) {
+  T4R_REQUIRE(y && code && mask_vec && out && M > 0 && d > 0, "train_row_codes_fwd: bad arguments");
+  T4R_ITEMS(M * d, "train_row_codes_fwd", row_codes_fwd_item(y, code, mask_vec, d, out, i));
+}
+extern "C" int t4r_train_row_codes_bwd(const float* dx, const uint8_t* code, int64_t M, int d, float* dy, float* dmask,
+                                       void* stream, int on_host) {
+  T4R_REQUIRE(dx && code && dy && dmask && M > 0 && d > 0, "train_row_codes_bwd: bad arguments");
+  T4R_TRY(zero(dmask, sizeof(float) * d, stream, on_host));
+  T4R_ITEMS(M * d, "train_row_codes_bwd", row_codes_bwd_item(dx, code, d, dy, dmask, i));
+}
+extern "C" int t4r_train_gather_rows(const float* x, const int32_t* idx, int64_t n, int d, float* out, void* stream,
+                                     int on_host) {
+  T4R_REQUIRE(x && idx && out && n >= 0 && d > 0, "train_gather_rows: bad arguments");
+  T4R_ITEMS(n * d, "train_gather_rows", gather_rows_item(x, idx, d, out, i));
+}
+extern "C" int t4r_train_scatter_rows(const float* src, const int32_t* idx, int64_t n, int d, int64_t out_rows, float* out,
+                                      void* stream, int on_host) {
+  T4R_REQUIRE(src && idx && out && n >= 0 && d > 0 && out_rows > 0, "train_scatter_rows: bad arguments");
+  T4R_TRY(zero(out, sizeof(float) * out_rows * d, stream, on_host));
+  T4R_ITEMS(n * d, "train_scatter_rows", scatter_rows_item(src, idx, d, out, i));
+}
+extern "C" int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_t* labels, int64_t T, int64_t Vc,
+                                        int64_t v0, float scale, void* stream, int on_host) {
+  T4R_REQUIRE(z && lse && labels && T > 0 && Vc > 0, "train_softmax_ce_bwd: bad arguments");
+  T4R_ITEMS(T * Vc, "train_softmax_ce_bwd", softmax_ce_bwd_item(z, lse, labels, Vc, v0, scale, i));
+}
+extern "C" int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src,
+                                        int col, int width, int64_t skip_index, void* stream, int on_host) {
+  T4R_REQUIRE(dst && idx && src && n > 0 && width > 0 && col >= 0 && col + width <= ld_src, "train_index_add_rows: bad arguments");
+  T4R_ITEMS(n * width, "train_index_add_rows", index_add_item(dst, idx, src, ld_src, col, width, skip_index, i));
+}
+extern "C" int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out, void* stream, int on_host) {
+  T4R_REQUIRE(x && out && M > 0 && N > 0, "train_col_sum: bad arguments");
+  T4R_TRY(zero(out, sizeof(float) * N, stream, on_host));
+  const int rows_per_slab = 256;
+  const int64_t slabs = (M + rows_per_slab - 1) / rows_per_slab;
+  T4R_ITEMS(slabs * N, "train_col_sum", col_sum_item(x, M, N, rows_per_slab, out, i));
+}
+extern "C" int t4r_train_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
+                                        float* y, void* stream, int on_host) {
+  T4R_REQUIRE(x && gamma && beta && y && M > 0 && d > 0, "train_layer_norm_fwd: bad arguments");
+  T4R_ITEMS(M, "train_layer_norm_fwd", ln_fwd_row(x, gamma, beta, d, eps, y, i));
+}
+extern "C" int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int64_t M, int d, float eps, const float* dy,
+                                        const float* add, float* dx, float* dgamma, float* dbeta, void* stream,
+                                        int on_host) {
+  T4R_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && M > 0 && d > 0, "train_layer_norm_bwd: bad arguments");
+  T4R_TRY(zero(dgamma, sizeof(float) * d, stream, on_host));
+  T4R_TRY(zero(dbeta, sizeof(float) * d, stream, on_host));
+  T4R_ITEMS(M, "train_layer_norm_bwd", ln_bwd_row(x, gamma, d, eps, dy, add, dx, dgamma, dbeta, i));
+}
+// R / rw / rr / dR / drw / drr all NULL selects the causal (GPT-2) form
+extern "C" int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout,
+                                  int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, void* stream,
+                                  int on_host) {
+  T4R_REQUIRE(qkv && dout && dqkv && B > 0 && L > 0 && L <= kAttnMaxL && H > 0 && d % H == 0, "train_attn_bwd: bad arguments (L <= 64)");
+  const bool rel = R != nullptr;
+  T4R_REQUIRE(!rel || (rw && rr && dR && drw && drr), "train_attn_bwd: the relative form needs R, both biases and their gradients");
+  const int64_t M = static_cast<int64_t>(B) * L;
+  T4R_TRY(zero(dqkv, sizeof(float) * M * 3 * d, stream, on_host));
+  if (rel) {
+    T4R_TRY(zero(dR, sizeof(float) * 2 * L * d, stream, on_host));
+    T4R_TRY(zero(drw, sizeof(float) * d, stream, on_host));
+    T4R_TRY(zero(drr, sizeof(float) * d, stream, on_host));
+  }
+  T4R_ITEMS(M * H, "train_attn_bwd", attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR, drw, drr, i));
+}
+
+// ---------------------------------------------------------------------------------------------- forward pieces reused
+// The training forward keeps q|k|v in fp32, so it runs the fp32-input attention kernels of the inference path
+// (attn_kernel, t4r_kernels.cu: any L <= 64); outputs are split planes [2, M, d] like everywhere else.
+extern "C" int t4r_train_xlnet_attn_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L,
+                                        int d, int H, void* out_planes, void* stream) {
+  T4R_REQUIRE(qkv && R && rw && rr && out_planes && B > 0 && L > 0, "train_xlnet_attn_fwd: bad arguments");
+  return launch_xlnet_attn(qkv, R, rw, rr, B, L, d, H, static_cast<__nv_bfloat16*>(out_planes),
+                           static_cast<int64_t>(B) * L * d, static_cast<cudaStream_t>(stream));
+}
+extern "C" int t4r_train_causal_attn_fwd(const float* qkv, int B, int L, int d, int H, void* out_planes, void* stream) {
+  T4R_REQUIRE(qkv && out_planes && B > 0 && L > 0, "train_causal_attn_fwd: bad arguments");
+  return launch_causal_attn(qkv, B, L, d, H, static_cast<__nv_bfloat16*>(out_planes), static_cast<int64_t>(B) * L * d,
+                            static_cast<cudaStream_t>(stream));
+}
+// R_l = pos(L, d) @ Wr_l for every layer: r_out [n_layer, 2L, d] fp32 (wr: HOST array of n_layer device pointers [d, d])
+extern "C" int t4r_train_rel_pos_proj(const float* const* wr, int n_layer, int L, int d, float* r_out, void* stream) {
+  T4R_REQUIRE(wr && r_out && n_layer >= 1 && n_layer <= T4R_MAX_FEATURES && L > 0 && d > 0, "train_rel_pos_proj: bad arguments");
+  return launch_rel_pos_proj(wr, n_layer, L, d, r_out, nullptr, static_cast<cudaStream_t>(stream));
+}

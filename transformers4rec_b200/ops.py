@@ -609,3 +609,222 @@ def combine_shard_lse(parts: torch.Tensor, t_dev=None):
     check(_lib.load().t4r_combine_shard_lse(ptr(parts), world, T_cap, ptr(t_dev), ptr(row_loss), ptr(loss), _stream()),
           "t4r_combine_shard_lse")
     return row_loss, loss
+
+
+# --------------------------------------------------------------------------- #
+# N3: primitives of the training step (csrc/t4r_train.cu; composed in training.py).
+# Public functions take CUDA tensors only.  ``host_twin(name)`` returns the same entry point running its per-item code
+# in a host loop on CPU tensors -- test infrastructure (tests/test_abi_and_host.py), never used by the package.
+# --------------------------------------------------------------------------- #
+def _tr(on_host, *ts):
+    if on_host:
+        assert all(t is None or not t.is_cuda for t in ts)
+        return (None, 1)
+    _need_cuda(*ts)
+    return (_stream(), 0)
+
+
+def transpose(x, _on_host=False):
+    x = _f32c(x)
+    tail = _tr(_on_host, x)
+    R, Cc = x.shape
+    out = torch.empty((Cc, R), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_transpose(ptr(x), R, Cc, ptr(out), *tail), "t4r_train_transpose")
+    return out
+
+
+def act_fwd(kind, x, _on_host=False):
+    x = _f32c(x)
+    tail = _tr(_on_host, x)
+    y = torch.empty_like(x)
+    check(_lib.load().t4r_train_act_fwd(int(kind), ptr(x), ptr(y), x.numel(), *tail), "t4r_train_act_fwd")
+    return y
+
+
+def act_bwd(kind, pre, dy, _on_host=False):
+    pre, dy = _f32c(pre), _f32c(dy)
+    tail = _tr(_on_host, pre, dy)
+    dx = torch.empty_like(pre)
+    check(_lib.load().t4r_train_act_bwd(int(kind), ptr(pre), ptr(dy), ptr(dx), pre.numel(), *tail), "t4r_train_act_bwd")
+    return dx
+
+
+def add_positions(x, wpe, B, L, _on_host=False):
+    x, wpe = _f32c(x), _f32c(wpe)
+    tail = _tr(_on_host, x, wpe)
+    d = x.shape[1]
+    y = torch.empty_like(x)
+    check(_lib.load().t4r_train_add_positions(ptr(x), ptr(wpe), B, L, d, ptr(y), *tail), "t4r_train_add_positions")
+    return y
+
+
+def sum_over_sessions(x, B, L, _on_host=False):
+    x = _f32c(x)
+    tail = _tr(_on_host, x)
+    d = x.shape[1]
+    out = torch.empty((L, d), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_sum_sessions(ptr(x), B, L, d, ptr(out), *tail), "t4r_train_sum_sessions")
+    return out
+
+
+def apply_row_codes(y, code, mask_vec, _on_host=False):
+    y, mask_vec = _f32c(y), _f32c(mask_vec)
+    code = code.reshape(-1).to(torch.uint8).contiguous()
+    tail = _tr(_on_host, y, code, mask_vec)
+    out = torch.empty_like(y)
+    check(_lib.load().t4r_train_row_codes_fwd(ptr(y), ptr(code), ptr(mask_vec), y.shape[0], y.shape[1], ptr(out), *tail),
+          "t4r_train_row_codes_fwd")
+    return out
+
+
+def row_codes_bwd(dx, code, _on_host=False):
+    dx = _f32c(dx)
+    code = code.reshape(-1).to(torch.uint8).contiguous()
+    tail = _tr(_on_host, dx, code)
+    dy = torch.empty_like(dx)
+    dmask = torch.empty((dx.shape[1],), dtype=torch.float32, device=dx.device)
+    check(_lib.load().t4r_train_row_codes_bwd(ptr(dx), ptr(code), dx.shape[0], dx.shape[1], ptr(dy), ptr(dmask), *tail),
+          "t4r_train_row_codes_bwd")
+    return dmask, dy
+
+
+def gather_rows(x, idx, _on_host=False):
+    x = _f32c(x)
+    idx = idx.to(torch.int32).contiguous()
+    tail = _tr(_on_host, x, idx)
+    out = torch.empty((idx.numel(), x.shape[1]), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_gather_rows(ptr(x), ptr(idx), idx.numel(), x.shape[1], ptr(out), *tail), "t4r_train_gather_rows")
+    return out
+
+
+def scatter_rows(src, idx, n_rows, _on_host=False):
+    src = _f32c(src)
+    idx = idx.to(torch.int32).contiguous()
+    tail = _tr(_on_host, src, idx)
+    out = torch.empty((n_rows, src.shape[1]), dtype=torch.float32, device=src.device)
+    check(_lib.load().t4r_train_scatter_rows(ptr(src), ptr(idx), idx.numel(), src.shape[1], n_rows, ptr(out), *tail),
+          "t4r_train_scatter_rows")
+    return out
+
+
+def softmax_ce_bwd(z, row_lse, labels, v0, scale, _on_host=False):
+    """In place on ``z`` [T, Vc]: (softmax - onehot) * scale; returns ``z``."""
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    row_lse, labels = _f32c(row_lse), labels.long().contiguous()
+    tail = _tr(_on_host, z, row_lse, labels)
+    T, Vc = z.shape
+    check(_lib.load().t4r_train_softmax_ce_bwd(ptr(z), ptr(row_lse), ptr(labels), T, Vc, int(v0), float(scale), *tail),
+          "t4r_train_softmax_ce_bwd")
+    return z
+
+
+def index_add_rows(dst, idx, src, col, width, skip_index=None, _on_host=False):
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.shape[1] == width
+    src, idx = _f32c(src), idx.long().contiguous()
+    tail = _tr(_on_host, dst, idx, src)
+    check(_lib.load().t4r_train_index_add_rows(ptr(dst), ptr(idx), ptr(src), idx.numel(), src.shape[1], int(col), int(width),
+                                               -1 if skip_index is None else int(skip_index), *tail),
+          "t4r_train_index_add_rows")
+    return dst
+
+
+def col_sum(x, _on_host=False):
+    x = _f32c(x)
+    tail = _tr(_on_host, x)
+    out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_col_sum(ptr(x), x.shape[0], x.shape[1], ptr(out), *tail), "t4r_train_col_sum")
+    return out
+
+
+def layer_norm_fwd(x, gamma, beta, eps, _on_host=False):
+    x, gamma, beta = _f32c(x), _f32c(gamma), _f32c(beta)
+    tail = _tr(_on_host, x, gamma, beta)
+    y = torch.empty_like(x)
+    check(_lib.load().t4r_train_layer_norm_fwd(ptr(x), ptr(gamma), ptr(beta), x.shape[0], x.shape[1], float(eps), ptr(y),
+                                               *tail), "t4r_train_layer_norm_fwd")
+    return y
+
+
+def layer_norm_bwd(x_pre, gamma, eps, dy, add=None, _on_host=False):
+    x_pre, gamma, dy = _f32c(x_pre), _f32c(gamma), _f32c(dy)
+    add = _f32c(add) if add is not None else None
+    tail = _tr(_on_host, x_pre, gamma, dy, add)
+    d = x_pre.shape[1]
+    dx = torch.empty_like(x_pre)
+    dg = torch.empty((d,), dtype=torch.float32, device=x_pre.device)
+    db = torch.empty((d,), dtype=torch.float32, device=x_pre.device)
+    check(_lib.load().t4r_train_layer_norm_bwd(ptr(x_pre), ptr(gamma), x_pre.shape[0], d, float(eps), ptr(dy), ptr(add),
+                                               ptr(dx), ptr(dg), ptr(db), *tail), "t4r_train_layer_norm_bwd")
+    return dx, dg, db
+
+
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, _on_host=False):
+    qkv, R, rw, rr, dout = (_f32c(t) for t in (qkv, R, rw, rr, dout))
+    tail = _tr(_on_host, qkv, R, rw, rr, dout)
+    d = dout.shape[1]
+    dev = qkv.device
+    dqkv = torch.empty_like(qkv)
+    dR = torch.empty((2 * L, d), dtype=torch.float32, device=dev)
+    drw = torch.empty((d,), dtype=torch.float32, device=dev)
+    drr = torch.empty((d,), dtype=torch.float32, device=dev)
+    check(_lib.load().t4r_train_attn_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv), ptr(dR),
+                                         ptr(drw), ptr(drr), *tail), "t4r_train_attn_bwd")
+    return dqkv, dR, drw, drr
+
+
+def causal_attn_bwd(qkv, dout, B, L, H, _on_host=False):
+    qkv, dout = _f32c(qkv), _f32c(dout)
+    tail = _tr(_on_host, qkv, dout)
+    dqkv = torch.empty_like(qkv)
+    check(_lib.load().t4r_train_attn_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv), None,
+                                         None, None, *tail), "t4r_train_attn_bwd")
+    return dqkv
+
+
+def _planes_to_f32(planes, d):
+    return planes[0, :, :d].float() + planes[1, :, :d].float()
+
+
+def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H):
+    qkv, R, rw, rr = (_f32c(t) for t in (qkv, R, rw, rr))
+    _need_cuda(qkv, R, rw, rr)
+    d = qkv.shape[1] // 3
+    out = torch.empty((2, B * L, d), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.load().t4r_train_xlnet_attn_fwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), B, L, d, H, ptr(out), _stream()),
+          "t4r_train_xlnet_attn_fwd")
+    return _planes_to_f32(out, d)
+
+
+def causal_attn_fwd(qkv, B, L, H):
+    qkv = _f32c(qkv)
+    _need_cuda(qkv)
+    d = qkv.shape[1] // 3
+    out = torch.empty((2, B * L, d), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.load().t4r_train_causal_attn_fwd(ptr(qkv), B, L, d, H, ptr(out), _stream()), "t4r_train_causal_attn_fwd")
+    return _planes_to_f32(out, d)
+
+
+def rel_pos_proj(wr_list, L, d):
+    """R_l = pos(L, d) @ Wr_l for every layer -> [n_layer, 2L, d] (the inference path's positional kernel)."""
+    ws = [_f32c(w) for w in wr_list]
+    _need_cuda(*ws)
+    out = torch.empty((len(ws), 2 * L, d), dtype=torch.float32, device=ws[0].device)
+    arr = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+    check(_lib.load().t4r_train_rel_pos_proj(arr, len(ws), L, d, ptr(out), _stream()), "t4r_train_rel_pos_proj")
+    return out
+
+
+def rel_pos_table(L, d, device=None):
+    """XLNet's relative position table [2L, d] (HF:xlnet:930-976, sin || cos of positions L .. -L+1): a constant of
+    (L, d), built once with torch."""
+    freq = torch.arange(0, d, 2.0, dtype=torch.float32, device=device)
+    inv_freq = 1.0 / torch.pow(10000, freq / d)
+    pos = torch.arange(L, -L, -1.0, dtype=torch.float32, device=device)
+    sinusoid = torch.einsum("i,d->id", pos, inv_freq)
+    return torch.cat([torch.sin(sinusoid), torch.cos(sinusoid)], dim=-1)
+
+
+def host_twin(name: str):
+    """The primitive ``name`` with its per-item code run in a host loop on CPU tensors (test infrastructure)."""
+    fn = globals()[name]
+    return lambda *a, **k: fn(*a, _on_host=True, **k)
