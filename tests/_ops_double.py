@@ -514,7 +514,7 @@ def install(monkeypatch):
 def install_plain():
     """Same without pytest (spawned gloo workers): returns nothing, patches for the life of the process."""
     from transformers4rec_b200 import block, ops
-    for name, fn in OPS.items():
+    for name, fn in list(OPS.items()) + list(TRAIN_OPS.items()):
         setattr(ops, name, fn)
     block.XLNetEncoder.forward = _xlnet_forward
     block.GPT2Encoder.forward = _gpt2_forward

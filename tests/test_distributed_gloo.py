@@ -232,3 +232,68 @@ def test_model_over_sharded_item_table_world2():
         assert r["train3"] < 1e-4 and r["train2"] < 1e-3 and r["eval"] < 1e-4 and r["recall"] < 1e-6, (rank, r)
         assert r["topk_scores"] < 1e-4 and r["topk_ids"] == 1.0, (rank, r)
         assert "top_k" in r["scores_error"], (rank, r)
+
+
+# --------------------------------------------------------------------------- #
+# training step over the row-sharded table (N3: "sharded-table grads via the transposed all-to-all"): every rank
+# back-propagates its own sessions; gradients against torch autograd of the single-process oracle on the GLOBAL batch
+# --------------------------------------------------------------------------- #
+def _train_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import _ops_double
+    from _util import make_pair, mlm_draws, synth_batch
+    from test_host_training_cpu import _pairs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _ops_double.install_plain()
+        from transformers4rec_b200.training import FusedTrainingStep
+        cards, dims = {"item_id/list": 1201, "category/list": 23}, {"item_id/list": 32, "category/list": 32}
+        Bm, Lm = 5, 8
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 32, 2, 1, Lm, weight_scale=0.08, device="cpu")
+        oracle.train(False)
+        inputs = model.heads[0].body[0]
+        full_item = inputs.categorical_module.embedding_tables["item_id/list"].weight.detach().clone()
+        inputs.categorical_module.shard_item_table()
+        table = inputs.categorical_module.embedding_tables["item_id/list"]
+        batches = [synth_batch(Bm, Lm, cards, seed=100 + r) for r in range(world)]
+        us = [mlm_draws(Bm, Lm, seed=200 + r) for r in range(world)]
+        gb = {k: torch.cat([b[k] for b in batches]) for k in batches[0]}
+        gdraws = {k: torch.cat([u[1][k] for u in us]) for k in us[0][1]}
+        ref = oracle(gb, training=True, draws=gdraws)
+        ref["loss"].backward()
+        inputs.masking.set_draws(us[rank][0])
+        step = FusedTrainingStep(model, head_chunk=256)
+        for p in model.parameters():
+            p.grad = None
+        loss = step.forward(batches[rank])
+        step.backward()
+        res = {"loss": abs(loss.item() - ref["loss"].item()), "worst": 0.0, "n": 0}
+        og = oracle.tables["item_id__list"].weight.grad
+        res["table"] = (table.weight.grad - og[table.lo:table.hi]).abs().max().item() / max(1.0, og.abs().max().item())
+        res["table_rows"] = tuple(table.weight.grad.shape) == (table.hi - table.lo, 32)
+        for name, po, pm in _pairs(oracle, model):
+            if "item_id" in name or (po.grad is None and pm.grad is None):
+                continue
+            err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item() / max(1.0, po.grad.abs().max().item())
+            res["worst"] = max(res["worst"], err)
+            res["n"] += 1
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_step_over_sharded_item_table_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r["loss"] < 1e-4 and r["table"] < 3e-4 and r["table_rows"] and r["worst"] < 3e-4 and r["n"] >= 15, (rank, r)

@@ -85,7 +85,8 @@ def _default_place(recv: torch.Tensor, unpermute: torch.Tensor):
 
 
 def sharded_embedding_lookup(local_table: torch.Tensor, ids: torch.Tensor, V: int, group=None,
-                             gather_rows: Optional[Callable] = None, place: Optional[Callable] = None):
+                             gather_rows: Optional[Callable] = None, place: Optional[Callable] = None,
+                             plan_out: Optional[list] = None):
     """Embedding rows for ``ids`` [B, L] from a table whose rows are block-sharded over
     the group.  Returns (rows fp32 [B*L, De], planes or None)."""
     world = dist.get_world_size(group)
@@ -100,7 +101,32 @@ def sharded_embedding_lookup(local_table: torch.Tensor, ids: torch.Tensor, V: in
     recv = torch.empty((sum(plan.recv_counts), De), dtype=torch.float32, device=flat.device)
     dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=plan.recv_counts,
                            input_split_sizes=plan.send_counts, group=group)
+    if plan_out is not None:
+        plan_out.append(plan)
     return place(recv, plan.unpermute)
+
+
+def sharded_embedding_lookup_bwd(d_rows: torch.Tensor, plan: "LookupPlan", local_grad: torch.Tensor, group=None,
+                                 skip_local_index: int = -1, scatter_rows: Optional[Callable] = None,
+                                 index_add: Optional[Callable] = None):
+    """Backward of ``sharded_embedding_lookup`` ("sharded-table grads via the transposed all-to-all"):
+    ``d_rows`` [n, De] are the gradients of the rows this rank looked up (position order).  They are put back into
+    arrival order (the inverse of the un-permutation), ONE all-to-all with the forward's split sizes swapped returns them
+    to the rows' owners, and each owner scatter-adds what it receives into ``local_grad`` [rows of its shard, De] at the
+    local indices it had served.  ``skip_local_index``: local index of the padding row (no gradient), -1 if not here."""
+    if scatter_rows is None or index_add is None:
+        from . import ops
+        scatter_rows = scatter_rows or (lambda src, idx, n: ops.scatter_rows(src, idx, n))
+        index_add = index_add or (lambda dst, idx, src, skip: ops.index_add_rows(dst, idx, src, 0, dst.shape[1],
+                                                                                skip_index=skip if skip >= 0 else None))
+    n, De = d_rows.shape
+    d_recv = scatter_rows(d_rows.contiguous(), plan.unpermute, n)              # d_recv[unpermute[p]] = d_rows[p]
+    d_send = torch.empty((sum(plan.send_counts), De), dtype=torch.float32, device=d_rows.device)
+    dist.all_to_all_single(d_send, d_recv.contiguous(), output_split_sizes=plan.send_counts,
+                           input_split_sizes=plan.recv_counts, group=group)
+    if d_send.shape[0]:
+        index_add(local_grad, plan.send_local_idx, d_send, skip_local_index)
+    return local_grad
 
 
 def _default_head_rows(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, w_planes, v_offset: int,
@@ -108,6 +134,8 @@ def _default_head_rows(xt: torch.Tensor, labels: torch.Tensor, local_table: torc
     """-> [T, 2] (lse over this shard, label logit if the label lives here else 0); with ``rank_tgt`` (the
     label's logit over the whole table) also the per-row count of this shard's classes scoring above it."""
     from . import ops
+    if w_planes is None:             # training: the table changes every step, its planes are made on the spot
+        w_planes = ops.split_planes(local_table)
     if isinstance(w_planes, tuple):  # (mixed planes, inverse row scales): the 2-unit product (ops.split_planes_mixed)
         xp, xi = ops.split_planes_mixed(xt)
         res = ops.head_softmax_ce(xp, xt, labels, w_planes[0], local_table, inv_temperature=inv_tau, v_offset=v_offset,
@@ -243,6 +271,60 @@ def sharded_topk(xs: torch.Tensor, local_table: torch.Tensor, V: int, k: int, gr
     return top_sc, cand_id.gather(1, pos.long())
 
 
+def _default_train_head(xg, yg, local_table, lo, inv_tau, lse_global, scale, head_chunk):
+    """This shard's part of the head backward for ALL label rows: (dX partial [T, De], dW_local [rows, De])."""
+    from . import ops
+    from .training import gemm_nt
+    Vl, De = local_table.shape
+    dx = torch.zeros_like(xg)
+    dW = torch.zeros_like(local_table)
+    xg_planes, xg_t = ops.split_planes(xg), ops.transpose(xg)
+    for v0 in range(0, Vl, head_chunk):
+        v1 = min(Vl, v0 + head_chunk)
+        Wc = local_table[v0:v1].contiguous()
+        z = ops.head_logits(xg_planes, ops.split_planes(Wc), De, inv_temperature=inv_tau)
+        P = ops.softmax_ce_bwd(z, lse_global, yg, lo + v0, scale * inv_tau)
+        dx = gemm_nt(P, ops.transpose(Wc), residual=dx)
+        dW[v0:v1] = gemm_nt(ops.transpose(P), xg_t)
+    return dx, dW
+
+
+def sharded_softmax_ce_train(xt: torch.Tensor, labels: torch.Tensor, local_table: torch.Tensor, V: int, group=None,
+                             w_planes=None, inv_tau: float = 1.0, head_chunk: int = 32768,
+                             head_rows: Optional[Callable] = None, train_head: Optional[Callable] = None):
+    """Forward AND backward of the row-sharded full-softmax head for a training step (the loss is a leaf: its upstream
+    gradient is 1).  Returns (global mean loss, dX_t for THIS rank's label rows, dW for this rank's table rows).
+    Collectives: the forward's all-gathers of the label rows and of the per-shard (lse, label logit) pairs, plus ONE
+    all-reduce of the partial dX [T_total, De] (every shard contributes P_s W_s); dW needs none -- each rank holds all
+    label rows and only its own table rows."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    head_rows = head_rows or _default_head_rows
+    train_head = train_head or _default_train_head
+    dev = xt.device
+    counts_l = _all_gather(torch.tensor([xt.shape[0]], dtype=torch.int64, device=dev), world, group).reshape(-1).tolist()
+    T_max, De = max(counts_l), xt.shape[1]
+    pad_x = torch.zeros((T_max, De), dtype=torch.float32, device=dev)
+    pad_x[: xt.shape[0]] = xt
+    pad_y = torch.zeros((T_max,), dtype=torch.int64, device=dev)
+    pad_y[: xt.shape[0]] = labels
+    all_x, all_y = _all_gather(pad_x, world, group), _all_gather(pad_y, world, group)
+    xg = torch.cat([all_x[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
+    yg = torch.cat([all_y[r, : counts_l[r]] for r in range(world)], dim=0).contiguous()
+    lo, _ = shard_bounds(V, rank, world)
+    part = head_rows(xg, yg, local_table, w_planes, lo, inv_tau)           # [T_total, 2] (lse_s, label logit_s)
+    parts = _all_gather(part, world, group)
+    lse_global = torch.logsumexp(parts[:, :, 0], dim=0)
+    tgt = parts[:, :, 1].sum(dim=0)
+    T_total = xg.shape[0]
+    loss = ((lse_global - tgt).sum() / max(T_total, 1)).reshape(())
+    dx, dW = train_head(xg, yg, local_table, lo, inv_tau, lse_global, 1.0 / max(T_total, 1), head_chunk)
+    dx = dx.contiguous()
+    dist.all_reduce(dx, group=group)
+    start = sum(counts_l[:rank])
+    return loss, dx[start:start + counts_l[rank]].contiguous(), dW
+
+
 class ShardedEmbedding(torch.nn.Module):
     """Rows [lo, hi) of an item table of ``num_embeddings`` rows, block-partitioned over the process
     group: the drop-in for the item feature's ``nn.Embedding`` (and, under weight tying, for the output
@@ -272,7 +354,7 @@ class ShardedEmbedding(torch.nn.Module):
             m.weight.copy_(full_weight[m.lo:m.hi])
         return m
 
-    def lookup(self, ids: torch.Tensor, ragged: bool = False):
+    def lookup(self, ids: torch.Tensor, ragged: bool = False, plan_out: Optional[list] = None):
         """-> (rows fp32 [ids.numel(), dim], split planes) for arbitrary global ids (one all-gather of the
         ids + one all-to-all of the rows).  ``ragged``: the ranks pass different numbers of ids (label
         rows); they are padded to the longest with the padding id for the exchange."""
@@ -284,7 +366,7 @@ class ShardedEmbedding(torch.nn.Module):
             if n_max > n:
                 flat = torch.cat([flat, flat.new_full((n_max - n,), self.padding_idx)])
         rows, planes = sharded_embedding_lookup(self.weight.detach(), flat, self.num_embeddings, self.group,
-                                                gather_rows=self.gather_rows, place=self.place)
+                                                gather_rows=self.gather_rows, place=self.place, plan_out=plan_out)
         if ragged and rows.shape[0] != n:
             rows, planes = rows[:n], (planes[:, :n] if planes is not None else None)
         return rows, planes

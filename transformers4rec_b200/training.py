@@ -221,8 +221,10 @@ class FusedTrainingStep:
             raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
         if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling)):
             raise NotImplementedError("FusedTrainingStep: MLM or CLM masking")
-        if not task.weight_tying or task.sampled_softmax or task._sharded() or task.label_smoothing:
-            raise NotImplementedError("FusedTrainingStep: tied weights, full softmax, replicated table, no label smoothing")
+        if not task.weight_tying or task.sampled_softmax or task.label_smoothing:
+            raise NotImplementedError("FusedTrainingStep: tied weights, full softmax, no label smoothing")
+        task.output_weight()             # refreshes task.item_embedding_table (the table may have been sharded after build)
+        self.sharded = task._sharded()   # row-sharded item table (BASELINE configs 4-5): see _forward/_backward_sharded
         enc = self.tblock.transformer
         self.graph = _XLNetGraph(enc) if isinstance(enc, XLNetEncoder) else _GPT2Graph(enc)
         self.layout = layout
@@ -249,7 +251,24 @@ class FusedTrainingStep:
             else:
                 conts.append((v, col))
         self.cats, self.conts = cats, conts
-        concat, _, _ = ops.embed_concat(cats, conts, M, self.C, want_f32=True, want_planes=False)
+        self.item_plan = None
+        if self.sharded:
+            # the item rows come through the table's exchange (all-gather of ids + one all-to-all); the other features
+            # are gathered locally into the same [M, C] buffer
+            table = cm.embedding_tables[cm.item_id]
+            item = next(c for c in cats if c[0].data_ptr() == table.weight.data_ptr())
+            local = [c for c in cats if c is not item]
+            plans: list = []
+            rows, _ = table.lookup(batch[cm.item_id], plan_out=plans)
+            self.item_plan, self.item_col = plans[0], item[2]
+            if local or conts:
+                concat, _, _ = ops.embed_concat(local, conts, M, self.C, want_f32=True, want_planes=False)
+            else:
+                concat = torch.empty((M, self.C), dtype=torch.float32, device=rows.device)
+            concat[:, item[2]:item[2] + rows.shape[1]] = rows
+            self.cats = local
+        else:
+            concat, _, _ = ops.embed_concat(cats, conts, M, self.C, want_f32=True, want_planes=False)
         # K2 projection + activation, then the mask replace (apply_mask_to_inputs)
         lin = inp._projection_linear()
         self.proj = _Linear(lin.weight, lin.bias)
@@ -276,6 +295,15 @@ class FusedTrainingStep:
         W = task.output_weight().detach().float()
         inv_tau = task._inv_tau()
         y_lab = self.labels[:T]
+        if self.sharded:
+            # forward and backward of the sharded head in one go (its only upstream gradient is d loss = 1)
+            from . import distributed as D
+            table = task.item_embedding_table
+            self.loss, self.dxt_sharded, self.dW_sharded = D.sharded_softmax_ce_train(
+                xt, y_lab, W, table.num_embeddings, table.group, w_planes=None, inv_tau=inv_tau,
+                head_chunk=self.head_chunk, head_rows=getattr(table, "train_head_rows", None),
+                train_head=getattr(table, "train_head", None))
+            return self.loss
         res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(W), W, inv_temperature=inv_tau)
         self.row_lse = res["row_lse"]
         self.loss = res["loss"].reshape(())
@@ -291,6 +319,8 @@ class FusedTrainingStep:
         V, De = W.shape
         inv_tau = task._inv_tau()
         y_lab = self.labels[:T]
+        if self.sharded:
+            return self._backward_sharded(float(grad_loss))
         scale = float(grad_loss) / max(T, 1)
         dxt = torch.zeros_like(self.xt)
         dW = torch.zeros_like(W)
@@ -304,6 +334,49 @@ class FusedTrainingStep:
             dxt = gemm_nt(P, ops.transpose(Wc), residual=dxt)              # dX_t += P W_c
             dW[v0:v1] = gemm_nt(ops.transpose(P), xt_t)                      # dW_c = P^T X_t
         _acc(Wp, dW)                                                        # tied: the item table's grad starts here
+        self._backward_body(dxt)
+        return self.loss
+
+    def _backward_sharded(self, grad_loss: float):
+        """Row-sharded table: the head's gradients were produced with the forward; the item rows' gradients travel back
+        through the transposed all-to-all; the replicated parameters' gradients are summed over the ranks (every rank
+        back-propagated its own sessions of the global mean loss)."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        task, inp = self.task, self.inputs
+        table = task.item_embedding_table
+        Wp = table.weight
+        _acc(Wp, self.dW_sharded * grad_loss)
+        dconcat = self._backward_body(self.dxt_sharded * grad_loss)
+        De = Wp.shape[1]
+        g = torch.zeros_like(Wp.detach(), dtype=torch.float32)
+        pad_local = inp.masking.padding_idx - table.lo
+        D.sharded_embedding_lookup_bwd(dconcat[:, self.item_col:self.item_col + De].contiguous(), self.item_plan, g,
+                                       table.group, skip_local_index=pad_local if 0 <= pad_local < Wp.shape[0] else -1,
+                                       scatter_rows=getattr(table, "train_scatter_rows", None),
+                                       index_add=getattr(table, "train_index_add", None))
+        _acc(Wp, g)
+        sharded_ptr = Wp.data_ptr()
+        for p in self._all_params():
+            if p.grad is not None and p.data_ptr() != sharded_ptr:
+                dist.all_reduce(p.grad, group=table.group)
+        return self.loss
+
+    def _all_params(self):
+        seen = set()
+        for mod in (self.inputs, self.tblock, self.task):
+            for p in mod.parameters():
+                if p.data_ptr() not in seen:
+                    seen.add(p.data_ptr())
+                    yield p
+
+    def _backward_body(self, dxt):
+        """Everything below the head: task_block, label-row scatter, encoder, mask replace, projection, embedding rows.
+        Returns d concat [M, C]."""
+        inp, task = self.inputs, self.task
+        cm = inp.categorical_module
+        M, T = self.M, self.T
         for lin_mod, lin_tb in reversed(self.tb):
             dxt, dwt, dbt = lin_tb.bwd(dxt)
             _acc(lin_mod.weight, dwt)
@@ -326,7 +399,7 @@ class FusedTrainingStep:
             g = torch.zeros_like(table) if param.grad is None else param.grad
             ops.index_add_rows(g, ids.reshape(-1), dconcat, col, table.shape[1], skip_index=inp.masking.padding_idx)
             param.grad = g
-        return self.loss
+        return dconcat
 
 
 class _FusedLossFn(torch.autograd.Function):
