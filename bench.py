@@ -289,6 +289,9 @@ def main():
     ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity, default), 2 = fp16 + two e4m3 cross terms in the "
                          "training head (2 tensor units per MAC, opt-in), 1 = plain bf16")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
+    ap.add_argument("--train", action="store_true",
+                    help="time a TRAINING step instead (forward + backward through transformers4rec_b200.training + one "
+                         "torch.optim.SGD step); not BASELINE.json's metric -- the line says so in `metric`")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -350,7 +353,19 @@ def main():
     def to_device():
         return {k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}
 
+    train_step = opt = None
+    if args.train:
+        from transformers4rec_b200.training import FusedTrainingStep, training_loss
+        train_step = FusedTrainingStep(model)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+
     def step(batch):
+        if train_step is not None:
+            opt.zero_grad(set_to_none=True)
+            loss = training_loss(model, batch, train_step)
+            loss.backward()
+            opt.step()
+            return loss.detach()
         with torch.no_grad():
             return model(batch, training=True)["loss"]
 
@@ -389,11 +404,11 @@ def main():
     ms_total = e0.elapsed_time(e1)
     head_ms = sorted(a.elapsed_time(b) for a, b in evs)
     head_ms_avg = sum(head_ms) / len(head_ms)
-    T = int(task._last["count"].item())
+    T = train_step.T if train_step is not None else int(task._last["count"].item())
 
     # --- optional: the same step captured once and replayed from a CUDA graph (no host work at all)
     graph_ms = None
-    if args.graph:
+    if args.graph and not args.train:
         try:
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
@@ -455,7 +470,7 @@ def main():
                 "note": {3: "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction",
                          2: "fp16 + 2 x e4m3 cross terms: 2 bf16-equivalent tensor passes per MAC: frac <= 1/2",
                          1: "plain bf16 product"}[args.nprod]}
-    line = {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
+    line = {"metric": METRIC if not args.train else "sessions/sec (fwd+bwd+SGD step; NOT the BASELINE metric)", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {3: "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)",
                                            2: "f32 (head: fp16 + e4m3 cross terms on tcgen05; rest bf16 hi/lo split)",
@@ -471,7 +486,7 @@ def main():
                                 "sample": f"{b_run} sessions/step of the same workload, 3 timed steps "
                                           f"(median {med:.2f} s), oracle graph = torch CPU ops + HF encoder, {threads} of "
                                           f"{os.cpu_count()} host threads (best of a calibration sweep)"}
-    if not args.no_cpu_baseline and world == 1 and not cfg.get("sharded"):
+    if not args.no_cpu_baseline and world == 1 and not cfg.get("sharded") and not args.train:
         try:
             line["recall_at_20"] = recall_agreement(cfg, model, batch_dev, batch_host)
         except Exception as exc:  # an accuracy side-note must never cost the throughput line
