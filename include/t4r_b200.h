@@ -431,7 +431,7 @@ int t4r_train_sum_sessions(const float* x, int B, int L, int d, float* out /*[L,
 int t4r_train_row_codes_fwd(const float* y, const uint8_t* code, const float* mask_vec, int64_t M, int d, float* out,
                             void* stream, int on_host);
 int t4r_train_row_codes_bwd(const float* dx, const uint8_t* code, int64_t M, int d, float* dy, float* dmask /*[d]*/,
-                            void* stream, int on_host);
+                            float* tmp /*[M, d] scratch*/, void* stream, int on_host);
 int t4r_train_gather_rows(const float* x, const int32_t* idx, int64_t n, int d, float* out, void* stream, int on_host);
 int t4r_train_scatter_rows(const float* src, const int32_t* idx, int64_t n, int d, int64_t out_rows, float* out,
                            void* stream, int on_host);
@@ -444,13 +444,17 @@ int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, i
 int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out /*[N]*/, void* stream, int on_host);
 int t4r_train_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t M, int d, float eps, float* y,
                              void* stream, int on_host);
-/* dx = LayerNorm backward of dy at x (+ add, optional); dgamma / dbeta [d] are overwritten */
+/* dx = LayerNorm backward of dy at x (+ add, optional); dgamma / dbeta [d] are overwritten (column sums of dy * xhat,
+ * kept in tmp, and of dy: no per-element atomics) */
 int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int64_t M, int d, float eps, const float* dy,
-                             const float* add, float* dx, float* dgamma, float* dbeta, void* stream, int on_host);
-/* attention backward, scores recomputed (L <= 64).  qkv / dqkv [M, 3d] (q | k | v), dout [M, d].  XLNet relative
- * form: R [2L, d], rw / rr [d] and their gradients; all six NULL selects GPT-2's causal form. */
+                             const float* add, float* dx, float* dgamma, float* dbeta, float* tmp /*[M, d] scratch*/,
+                             void* stream, int on_host);
+/* attention backward, scores recomputed (L <= 64), one work item per (session, head) owning its slices of dq / dk / dv and
+ * of the per-session partials of dR / drw / drr (no atomics; the partials are then reduced over the sessions).
+ * qkv / dqkv [M, 3d] (q | k | v), dout [M, d].  XLNet relative form: R [2L, d], rw / rr [d], their gradients and
+ * part = scratch of B (2L + 2) d floats; all seven NULL selects GPT-2's causal form. */
 int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B, int L,
-                       int d, int H, float* dqkv, float* dR, float* drw, float* drr, void* stream, int on_host);
+                       int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part, void* stream, int on_host);
 /* forward pieces of the training graph that reuse inference kernels on fp32 q|k|v (device only) */
 int t4r_train_xlnet_attn_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d, int H,
                              void* out_planes /*[2, M, d]*/, void* stream);

@@ -173,15 +173,15 @@ SIGNATURES = {
     "t4r_train_add_positions": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int]),
     "t4r_train_sum_sessions": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int]),
     "t4r_train_row_codes_fwd": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P, c_int]),
-    "t4r_train_row_codes_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, c_int]),
+    "t4r_train_row_codes_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int]),
     "t4r_train_gather_rows": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int]),
     "t4r_train_scatter_rows": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P, c_int]),
     "t4r_train_softmax_ce_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, c_int]),
     "t4r_train_index_add_rows": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int64, _P, c_int]),
     "t4r_train_col_sum": (c_int, [_P, c_int64, c_int64, _P, _P, c_int]),
     "t4r_train_layer_norm_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, c_int]),
-    "t4r_train_layer_norm_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P, _P, c_int]),
-    "t4r_train_attn_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int]),
+    "t4r_train_layer_norm_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int]),
+    "t4r_train_attn_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int]),
     "t4r_train_xlnet_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "t4r_train_causal_attn_fwd": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "t4r_train_rel_pos_proj": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, _P, _P]),

@@ -4,9 +4,10 @@
 // pieces below.  Each is written as a __host__ __device__ function of ONE work item (element, row, column slab,
 // or attention query row) that a trivial kernel calls once per thread -- and that the same entry point calls in a
 // plain loop when `on_host` is set (HOST pointers, no CUDA call), so that the CPU suite can pin the arithmetic
-// against torch without a GPU.  Accumulations across work items use atomicAdd on the device (plain += on the host).
-// These are first, correct versions: the attention backward in particular trades speed for simplicity (one thread
-// per query row, atomics for dK / dV / dR); none of this is on the inference path.
+// against torch without a GPU.  Work items own what they write; the few cross-item sums (column sums, the row
+// scatter-add into embedding tables) use one atomicAdd per item / per duplicate row on the device (plain += on the
+// host), never one per element.  These are first, correct versions, not tuned (one thread per row or per (session,
+// head) leaves bandwidth on the table); none of this is on the inference path.
 #include <math.h>
 
 #include "t4r_common.cuh"
@@ -56,10 +57,11 @@ T4R_HD void row_codes_fwd_item(const float* y, const uint8_t* code, const float*
   const int c = code[i / d];
   out[i] = c == 0 ? y[i] : (c == 1 ? mask_vec[i % d] : 0.f);
 }
-T4R_HD void row_codes_bwd_item(const float* dx, const uint8_t* code, int d, float* dy, float* dmask, int64_t i) {
+// dy = dx on kept rows; tmp = dx on rows that took the mask embedding (its gradient is their column sum)
+T4R_HD void row_codes_bwd_item(const float* dx, const uint8_t* code, int d, float* dy, float* tmp, int64_t i) {
   const int c = code[i / d];
   dy[i] = c == 0 ? dx[i] : 0.f;
-  if (c == 1) T4R_ATOMIC_ADD(dmask + (i % d), dx[i]);
+  tmp[i] = c == 1 ? dx[i] : 0.f;
 }
 T4R_HD void gather_rows_item(const float* x, const int32_t* idx, int d, float* out, int64_t i) {
   out[i] = x[static_cast<int64_t>(idx[i / d]) * d + (i % d)];
@@ -104,9 +106,9 @@ T4R_HD void ln_fwd_row(const float* x, const float* g, const float* b, int d, fl
   const float rstd = 1.0f / sqrtf(var / d + eps);
   for (int c = 0; c < d; ++c) y[row * d + c] = (xr[c] - mean) * rstd * g[c] + b[c];
 }
-// dx = rstd (g dy - mean(g dy) - xhat mean(g dy xhat)) (+ add);  dgamma += dy xhat;  dbeta += dy
+// dx = rstd (g dy - mean(g dy) - xhat mean(g dy xhat)) (+ add);  dy_xhat = dy xhat
 T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const float* dy, const float* add, float* dx,
-                       float* dgamma, float* dbeta, int64_t row) {
+                       float* dy_xhat, int64_t row) {
   const float* xr = x + row * d;
   const float* dyr = dy + row * d;
   float mean = 0.f;
@@ -128,80 +130,93 @@ T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const f
     float v = rstd * (gd - m1 - xh * m2);
     if (add) v += add[row * d + c];
     dx[row * d + c] = v;
-    T4R_ATOMIC_ADD(dgamma + c, dyr[c] * xh);
-    T4R_ATOMIC_ADD(dbeta + c, dyr[c]);
+    dy_xhat[row * d + c] = dyr[c] * xh;   // dgamma = its column sum (dbeta = the column sum of dy): no atomics per element
   }
 }
 
 // ---------------------------------------------------------------------------------------------- attention backward
-// One item = (session b, head h, query row i).  qkv [M, 3d] fp32 (q | k | v), R [2L, d], rw / rr [d] (XLNet; null for
-// the causal GPT-2 form), dout [M, d].  Scores are recomputed (L <= 64), then
+// One item = (session b, head h): it owns the head's slices of dq / dk / dv for all rows of its session, its own
+// [2L, dh] slice of dR_part[b] and [dh] slices of drw_part[b] / drr_part[b], so nothing is shared between items and
+// there is no atomic; dR / drw / drr are the sums of the partials over the sessions (separate reductions).
+// qkv [M, 3d] fp32 (q | k | v), R [2L, d], rw / rr [d] (XLNet; null for the causal GPT-2 form), dout [M, d].
+// Scores are recomputed per query row (L <= 64), then
 //   dp_j = do_i . v_j ;  ds_j = p_j (dp_j - sum_k p_k dp_k) / sqrt(dh)
 //   dq_i = sum_j ds_j (k_j + R_m)        dk_j += ds_j (q_i + rw)        dv_j += p_j do_i
 //   dR_m += ds_j (q_i + rr)              drw  += ds_j k_j               drr  += ds_j R_m          m = j + L - i
 constexpr int kAttnMaxL = 64;
 T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
-                          int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, int64_t item) {
+                          int L, int d, int H, float* dqkv, float* dR_part, float* drw_part, float* drr_part,
+                          int64_t item) {
   const int dh = d / H;
-  const int i = static_cast<int>(item % L);
-  const int h = static_cast<int>((item / L) % H);
-  const int64_t b = item / (static_cast<int64_t>(L) * H);
+  const int h = static_cast<int>(item % H);
+  const int64_t b = item / H;
   const bool rel = R != nullptr;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  const float* q = qkv + (b * L + i) * 3 * d + h * dh;
-  const float* dor = dout + (b * L + i) * d + h * dh;
+  // zero what this item owns
+  for (int r = 0; r < L; ++r)
+    for (int part = 0; part < 3; ++part)
+      for (int c = 0; c < dh; ++c) dqkv[(b * L + r) * 3 * d + part * d + h * dh + c] = 0.f;
+  if (rel) {
+    for (int m = 0; m < 2 * L; ++m)
+      for (int c = 0; c < dh; ++c) dR_part[(b * 2 * L + m) * d + h * dh + c] = 0.f;
+    for (int c = 0; c < dh; ++c) { drw_part[b * d + h * dh + c] = 0.f; drr_part[b * d + h * dh + c] = 0.f; }
+  }
   float s[kAttnMaxL], dp[kAttnMaxL];
-  float mx = -INFINITY;
-  for (int j = 0; j < L; ++j) {
-    if (!rel && j > i) { s[j] = -INFINITY; continue; }
-    const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
-    float acc = 0.f;
-    if (rel) {
-      const float* Rm = R + static_cast<int64_t>(j + L - i) * d + h * dh;
-      for (int c = 0; c < dh; ++c) acc += (q[c] + rw[h * dh + c]) * k[c] + (q[c] + rr[h * dh + c]) * Rm[c];
-    } else {
-      for (int c = 0; c < dh; ++c) acc += q[c] * k[c];
-    }
-    s[j] = acc * scale;
-    mx = fmaxf(mx, s[j]);
-  }
-  float sum = 0.f;
-  for (int j = 0; j < L; ++j) { s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx); sum += s[j]; }
-  const float inv = 1.0f / sum;
-  float dot = 0.f;
-  for (int j = 0; j < L; ++j) {
-    s[j] *= inv;                                            // p_j
-    const float* v = qkv + (b * L + j) * 3 * d + 2 * d + h * dh;
-    float acc = 0.f;
-    for (int c = 0; c < dh; ++c) acc += dor[c] * v[c];
-    dp[j] = acc;
-    dot += s[j] * acc;
-  }
-  float* dq = dqkv + (b * L + i) * 3 * d + h * dh;
-  for (int c = 0; c < dh; ++c) dq[c] = 0.f;                 // this item owns dq_i of its head
-  for (int j = 0; j < L; ++j) {
-    const float p = s[j];
-    if (p == 0.f && (!rel && j > i)) continue;
-    const float ds = p * (dp[j] - dot) * scale;
-    const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
-    float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
-    float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
-    if (rel) {
-      const int64_t m = j + L - i;
-      const float* Rm = R + m * d + h * dh;
-      for (int c = 0; c < dh; ++c) {
-        dq[c] += ds * (k[c] + Rm[c]);
-        T4R_ATOMIC_ADD(dk + c, ds * (q[c] + rw[h * dh + c]));
-        T4R_ATOMIC_ADD(dv + c, p * dor[c]);
-        T4R_ATOMIC_ADD(dR + m * d + h * dh + c, ds * (q[c] + rr[h * dh + c]));
-        T4R_ATOMIC_ADD(drw + h * dh + c, ds * k[c]);
-        T4R_ATOMIC_ADD(drr + h * dh + c, ds * Rm[c]);
+  for (int i = 0; i < L; ++i) {
+    const float* q = qkv + (b * L + i) * 3 * d + h * dh;
+    const float* dor = dout + (b * L + i) * d + h * dh;
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) {
+      if (!rel && j > i) { s[j] = -INFINITY; continue; }
+      const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
+      float acc = 0.f;
+      if (rel) {
+        const float* Rm = R + static_cast<int64_t>(j + L - i) * d + h * dh;
+        for (int c = 0; c < dh; ++c) acc += (q[c] + rw[h * dh + c]) * k[c] + (q[c] + rr[h * dh + c]) * Rm[c];
+      } else {
+        for (int c = 0; c < dh; ++c) acc += q[c] * k[c];
       }
-    } else {
-      for (int c = 0; c < dh; ++c) {
-        dq[c] += ds * k[c];
-        T4R_ATOMIC_ADD(dk + c, ds * q[c]);
-        T4R_ATOMIC_ADD(dv + c, p * dor[c]);
+      s[j] = acc * scale;
+      mx = fmaxf(mx, s[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < L; ++j) { s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+    for (int j = 0; j < L; ++j) {
+      s[j] *= inv;                                            // p_j
+      const float* v = qkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+      float acc = 0.f;
+      for (int c = 0; c < dh; ++c) acc += dor[c] * v[c];
+      dp[j] = acc;
+      dot += s[j] * acc;
+    }
+    float* dq = dqkv + (b * L + i) * 3 * d + h * dh;
+    for (int j = 0; j < L; ++j) {
+      const float p = s[j];
+      if (!rel && j > i) continue;
+      const float ds = p * (dp[j] - dot) * scale;
+      const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
+      float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
+      float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+      if (rel) {
+        const int64_t m = j + L - i;
+        const float* Rm = R + m * d + h * dh;
+        float* dRm = dR_part + (b * 2 * L + m) * d + h * dh;
+        for (int c = 0; c < dh; ++c) {
+          dq[c] += ds * (k[c] + Rm[c]);
+          dk[c] += ds * (q[c] + rw[h * dh + c]);
+          dv[c] += p * dor[c];
+          dRm[c] += ds * (q[c] + rr[h * dh + c]);
+          drw_part[b * d + h * dh + c] += ds * k[c];
+          drr_part[b * d + h * dh + c] += ds * Rm[c];
+        }
+      } else {
+        for (int c = 0; c < dh; ++c) {
+          dq[c] += ds * k[c];
+          dk[c] += ds * q[c];
+          dv[c] += p * dor[c];
+        }
       }
     }
   }
@@ -263,11 +278,13 @@ extern "C" int t4r_train_row_codes_fwd(const float* y, const uint8_t* code, cons
   T4R_REQUIRE(y && code && mask_vec && out && M > 0 && d > 0, "train_row_codes_fwd: bad arguments");
   T4R_ITEMS(M * d, "train_row_codes_fwd", row_codes_fwd_item(y, code, mask_vec, d, out, i));
 }
+static int col_sum_impl(const float* x, int64_t M, int64_t N, float* out, void* stream, int on_host);
 extern "C" int t4r_train_row_codes_bwd(const float* dx, const uint8_t* code, int64_t M, int d, float* dy, float* dmask,
-                                       void* stream, int on_host) {
-  T4R_REQUIRE(dx && code && dy && dmask && M > 0 && d > 0, "train_row_codes_bwd: bad arguments");
-  T4R_TRY(zero(dmask, sizeof(float) * d, stream, on_host));
-  T4R_ITEMS(M * d, "train_row_codes_bwd", row_codes_bwd_item(dx, code, d, dy, dmask, i));
+                                       float* tmp /*[M, d] scratch*/, void* stream, int on_host) {
+  T4R_REQUIRE(dx && code && dy && dmask && tmp && M > 0 && d > 0, "train_row_codes_bwd: bad arguments");
+  T4R_TRY(run_items(M * d, [=] __host__ __device__(int64_t i) { row_codes_bwd_item(dx, code, d, dy, tmp, i); },
+                    "train_row_codes_bwd", stream, on_host));
+  return col_sum_impl(tmp, M, d, dmask, stream, on_host);
 }
 extern "C" int t4r_train_gather_rows(const float* x, const int32_t* idx, int64_t n, int d, float* out, void* stream,
                                      int on_host) {
@@ -290,12 +307,16 @@ extern "C" int t4r_train_index_add_rows(float* dst, const int64_t* idx, const fl
   T4R_REQUIRE(dst && idx && src && n > 0 && width > 0 && col >= 0 && col + width <= ld_src, "train_index_add_rows: bad arguments");
   T4R_ITEMS(n * width, "train_index_add_rows", index_add_item(dst, idx, src, ld_src, col, width, skip_index, i));
 }
-extern "C" int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out, void* stream, int on_host) {
-  T4R_REQUIRE(x && out && M > 0 && N > 0, "train_col_sum: bad arguments");
+// column sums: one item per (column, slab of 256 rows), one atomicAdd per item -> (M / 256) N atomics in total
+static int col_sum_impl(const float* x, int64_t M, int64_t N, float* out, void* stream, int on_host) {
   T4R_TRY(zero(out, sizeof(float) * N, stream, on_host));
   const int rows_per_slab = 256;
   const int64_t slabs = (M + rows_per_slab - 1) / rows_per_slab;
   T4R_ITEMS(slabs * N, "train_col_sum", col_sum_item(x, M, N, rows_per_slab, out, i));
+}
+extern "C" int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out, void* stream, int on_host) {
+  T4R_REQUIRE(x && out && M > 0 && N > 0, "train_col_sum: bad arguments");
+  return col_sum_impl(x, M, N, out, stream, on_host);
 }
 extern "C" int t4r_train_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t M, int d, float eps,
                                         float* y, void* stream, int on_host) {
@@ -303,28 +324,33 @@ extern "C" int t4r_train_layer_norm_fwd(const float* x, const float* gamma, cons
   T4R_ITEMS(M, "train_layer_norm_fwd", ln_fwd_row(x, gamma, beta, d, eps, y, i));
 }
 extern "C" int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int64_t M, int d, float eps, const float* dy,
-                                        const float* add, float* dx, float* dgamma, float* dbeta, void* stream,
-                                        int on_host) {
-  T4R_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && M > 0 && d > 0, "train_layer_norm_bwd: bad arguments");
-  T4R_TRY(zero(dgamma, sizeof(float) * d, stream, on_host));
-  T4R_TRY(zero(dbeta, sizeof(float) * d, stream, on_host));
-  T4R_ITEMS(M, "train_layer_norm_bwd", ln_bwd_row(x, gamma, d, eps, dy, add, dx, dgamma, dbeta, i));
+                                        const float* add, float* dx, float* dgamma, float* dbeta,
+                                        float* tmp /*[M, d] scratch*/, void* stream, int on_host) {
+  T4R_REQUIRE(x && gamma && dy && dx && dgamma && dbeta && tmp && M > 0 && d > 0, "train_layer_norm_bwd: bad arguments");
+  T4R_TRY(run_items(M, [=] __host__ __device__(int64_t i) { ln_bwd_row(x, gamma, d, eps, dy, add, dx, tmp, i); },
+                    "train_layer_norm_bwd", stream, on_host));
+  T4R_TRY(col_sum_impl(tmp, M, d, dgamma, stream, on_host));   // dgamma = sum_rows dy * xhat
+  return col_sum_impl(dy, M, d, dbeta, stream, on_host);         // dbeta  = sum_rows dy
 }
-// R / rw / rr / dR / drw / drr all NULL selects the causal (GPT-2) form
+// R / rw / rr / dR / drw / drr all NULL selects the causal (GPT-2) form.  part: scratch of B (2L + 2) d floats (relative
+// form): per-session partials of dR / drw / drr, reduced over the sessions here.
 extern "C" int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout,
-                                  int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, void* stream,
-                                  int on_host) {
+                                  int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
+                                  void* stream, int on_host) {
   T4R_REQUIRE(qkv && dout && dqkv && B > 0 && L > 0 && L <= kAttnMaxL && H > 0 && d % H == 0, "train_attn_bwd: bad arguments (L <= 64)");
   const bool rel = R != nullptr;
-  T4R_REQUIRE(!rel || (rw && rr && dR && drw && drr), "train_attn_bwd: the relative form needs R, both biases and their gradients");
-  const int64_t M = static_cast<int64_t>(B) * L;
-  T4R_TRY(zero(dqkv, sizeof(float) * M * 3 * d, stream, on_host));
-  if (rel) {
-    T4R_TRY(zero(dR, sizeof(float) * 2 * L * d, stream, on_host));
-    T4R_TRY(zero(drw, sizeof(float) * d, stream, on_host));
-    T4R_TRY(zero(drr, sizeof(float) * d, stream, on_host));
-  }
-  T4R_ITEMS(M * H, "train_attn_bwd", attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR, drw, drr, i));
+  T4R_REQUIRE(!rel || (rw && rr && dR && drw && drr && part), "train_attn_bwd: the relative form needs R, both biases, their gradients and the scratch");
+  float* dR_part = part;
+  float* drw_part = rel ? part + static_cast<int64_t>(B) * 2 * L * d : nullptr;
+  float* drr_part = rel ? drw_part + static_cast<int64_t>(B) * d : nullptr;
+  T4R_TRY(run_items(static_cast<int64_t>(B) * H, [=] __host__ __device__(int64_t i) {
+            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, i); },
+          "train_attn_bwd", stream, on_host));
+  if (!rel) return 0;
+  T4R_TRY(run_items(static_cast<int64_t>(2) * L * d, [=] __host__ __device__(int64_t i) { sum_sessions_item(dR_part, B, 2 * L, d, dR, i); },
+                    "train_attn_bwd_dR", stream, on_host));
+  T4R_TRY(col_sum_impl(drw_part, B, d, drw, stream, on_host));
+  return col_sum_impl(drr_part, B, d, drr, stream, on_host);
 }
 
 // ---------------------------------------------------------------------------------------------- forward pieces reused

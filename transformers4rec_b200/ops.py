@@ -682,9 +682,10 @@ def row_codes_bwd(dx, code, _on_host=False):
     code = code.reshape(-1).to(torch.uint8).contiguous()
     tail = _tr(_on_host, dx, code)
     dy = torch.empty_like(dx)
+    tmp = torch.empty_like(dx)
     dmask = torch.empty((dx.shape[1],), dtype=torch.float32, device=dx.device)
-    check(_lib.load().t4r_train_row_codes_bwd(ptr(dx), ptr(code), dx.shape[0], dx.shape[1], ptr(dy), ptr(dmask), *tail),
-          "t4r_train_row_codes_bwd")
+    check(_lib.load().t4r_train_row_codes_bwd(ptr(dx), ptr(code), dx.shape[0], dx.shape[1], ptr(dy), ptr(dmask), ptr(tmp),
+                                              *tail), "t4r_train_row_codes_bwd")
     return dmask, dy
 
 
@@ -751,10 +752,11 @@ def layer_norm_bwd(x_pre, gamma, eps, dy, add=None, _on_host=False):
     tail = _tr(_on_host, x_pre, gamma, dy, add)
     d = x_pre.shape[1]
     dx = torch.empty_like(x_pre)
+    tmp = torch.empty_like(x_pre)
     dg = torch.empty((d,), dtype=torch.float32, device=x_pre.device)
     db = torch.empty((d,), dtype=torch.float32, device=x_pre.device)
     check(_lib.load().t4r_train_layer_norm_bwd(ptr(x_pre), ptr(gamma), x_pre.shape[0], d, float(eps), ptr(dy), ptr(add),
-                                               ptr(dx), ptr(dg), ptr(db), *tail), "t4r_train_layer_norm_bwd")
+                                               ptr(dx), ptr(dg), ptr(db), ptr(tmp), *tail), "t4r_train_layer_norm_bwd")
     return dx, dg, db
 
 
@@ -767,8 +769,9 @@ def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, _on_host=False):
     dR = torch.empty((2 * L, d), dtype=torch.float32, device=dev)
     drw = torch.empty((d,), dtype=torch.float32, device=dev)
     drr = torch.empty((d,), dtype=torch.float32, device=dev)
+    part = torch.empty((B * (2 * L + 2) * d,), dtype=torch.float32, device=dev)
     check(_lib.load().t4r_train_attn_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv), ptr(dR),
-                                         ptr(drw), ptr(drr), *tail), "t4r_train_attn_bwd")
+                                         ptr(drw), ptr(drr), ptr(part), *tail), "t4r_train_attn_bwd")
     return dqkv, dR, drw, drr
 
 
@@ -777,7 +780,7 @@ def causal_attn_bwd(qkv, dout, B, L, H, _on_host=False):
     tail = _tr(_on_host, qkv, dout)
     dqkv = torch.empty_like(qkv)
     check(_lib.load().t4r_train_attn_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv), None,
-                                         None, None, *tail), "t4r_train_attn_bwd")
+                                         None, None, None, *tail), "t4r_train_attn_bwd")
     return dqkv
 
 
