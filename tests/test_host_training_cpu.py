@@ -115,3 +115,34 @@ def test_training_step_with_the_real_per_item_code(monkeypatch):
                 continue
             err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
             assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (arch, name, err)
+
+
+def test_sgd_trajectories_coincide(monkeypatch):
+    """Five optimizer steps through ``training_loss(...).backward()`` and through torch autograd of the oracle graph,
+    same data and draws: losses fall and the two parameter trajectories stay together (tied item table included)."""
+    from transformers4rec_b200.training import FusedTrainingStep, training_loss
+    D.install(monkeypatch)
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08)
+    oracle.train(False)
+    B, L = 6, 8
+    batch = synth_batch(B, L, CARDS, CONT, seed=9)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    step = FusedTrainingStep(model, head_chunk=512)
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.3)
+    opt_m = torch.optim.SGD(model.parameters(), lr=0.3)
+    losses = []
+    for _ in range(5):
+        opt_o.zero_grad()
+        lo = oracle(batch, training=True, draws=draws)["loss"]
+        lo.backward()
+        opt_o.step()
+        opt_m.zero_grad()
+        lm = training_loss(model, batch, step)
+        lm.backward()
+        opt_m.step()
+        losses.append((lo.item(), lm.item()))
+    assert all(abs(a - b) < 1e-3 for a, b in losses) and losses[-1][1] < losses[0][1]
+    for name, po, pm in _pairs(oracle, model):
+        assert (pm.detach() - po.detach().reshape(pm.shape)).abs().max().item() < 1e-3, name
