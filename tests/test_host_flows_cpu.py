@@ -205,3 +205,31 @@ def test_permutation_language_modeling_flow(monkeypatch):
     with pytest.raises(ValueError, match="requires the parameters"):
         tr.TransformerBlock(tr.GPT2Config.build(d_model=32, n_head=2, n_layer=1, total_seq_length=12),
                             masking=tr.PermutationLanguageModeling(hidden_size=32))
+
+
+@pytest.mark.parametrize("task", ["mlm", "masked", "clm", "causal", "plm", "permutation"])
+def test_body_built_with_the_shift_operator(monkeypatch, task):
+    """tests/unit/torch/block/test_transformer.py:39-89 (incl. test_xlnet_with_plm): ``features >> MLPBlock([64]) >>
+    TransformerBlock(config, masking=features.masking)`` on the reference's testing schema; output [B, L, 64]."""
+    import transformers4rec_b200.torch as tr
+    from test_abi_and_host import _testing_schema
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    tab = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, aggregation="concat", d_output=64,
+                                                 masking=task)
+    cfg = tr.XLNetConfig.build(d_model=64, n_head=4, n_layer=2, total_seq_length=20)
+    block = tab >> tr.MLPBlock([64]) >> tr.TransformerBlock(transformer=cfg, masking=tab.masking)
+    assert isinstance(block, tr.SequentialBlock) and len(block) == 3
+    g = torch.Generator().manual_seed(0)
+    batch = {}
+    for col in schema:
+        shape = (12, 20) if col.is_list else (12,)
+        batch[col.name] = (torch.randint(1, col.int_max + 1, shape, generator=g) if col.int_max
+                           else torch.rand(shape, generator=g))
+    with torch.no_grad():
+        out = block(batch, training=True)
+    assert out.ndim == 3 and out.shape == (12, 20, 64)
+    # test_transformer.py:92-120: PLM with an architecture that cannot take it
+    if task in ("plm", "permutation"):
+        with pytest.raises(ValueError, match="PermutationLanguageModeling requires the parameters: target_mapping, perm_mask"):
+            tr.TransformerBlock(tr.GPT2Config.build(d_model=64, n_head=4, n_layer=2, total_seq_length=20), masking=tab.masking)

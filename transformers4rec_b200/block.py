@@ -23,7 +23,21 @@ def _planes_of(x: torch.Tensor):
     return getattr(x, "_t4r_planes", None)
 
 
-class SequentialBlock(nn.Sequential):
+def right_shift_block(left, right):
+    """block/base.py:66-67, :265-311 (``a >> b``): chain two blocks, flattening sequential blocks, so that
+    ``features >> MLPBlock([64]) >> TransformerBlock(...)`` builds the body the way the reference's examples do."""
+    parts = []
+    for side in (left, right):
+        parts += list(side) if isinstance(side, SequentialBlock) and not isinstance(side, _BuiltMLP) else [side]
+    return SequentialBlock(*parts)
+
+
+class _RShift:
+    def __rshift__(self, other):
+        return right_shift_block(self, other)
+
+
+class SequentialBlock(nn.Sequential, _RShift):
     """block/base.py:160-262: passes ``training`` / ``testing`` (and friends) only to
     layers whose ``forward`` names them."""
 
@@ -126,7 +140,7 @@ class _BuiltMLP(SequentialBlock):
         return torch.Size(base[:-1] + [self[-1]._output_size])
 
 
-class MLPBlock:
+class MLPBlock(_RShift):
     """block/mlp.py:30-87 (a BuildableBlock: ``build(input_shape)`` returns the module)."""
 
     def __init__(self, dimensions, activation=torch.nn.ReLU, use_bias: bool = True, dropout: float = None,
@@ -353,7 +367,7 @@ def _encoder_from(transformer) -> nn.Module:
         f"{type(transformer).__name__}: only XLNet and GPT-2 are on the t4r_b200 hot path (SURVEY §2 row 9)")
 
 
-class TransformerBlock(nn.Module):
+class TransformerBlock(nn.Module, _RShift):
     """block/transformer.py:76-206."""
 
     def __init__(self, transformer, masking=None, prepare_module=None):

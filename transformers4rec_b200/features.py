@@ -369,6 +369,10 @@ class ContinuousFeatures(nn.Module):
 
 
 class TabularSequenceFeatures(nn.Module):
+    def __rshift__(self, other):   # block/base.py:66-67: ``features >> block``
+        from .block import right_shift_block
+        return right_shift_block(self, other)
+
     """features/sequence.py:97-296."""
 
     EMBEDDING_MODULE_CLASS = SequenceEmbeddingFeatures
