@@ -1,0 +1,92 @@
+"""The next-item model through the reference's public API -- the calls of the reference's own model tests
+(tests/unit/torch/model/test_model.py:296-407) on its testing schema -- for the maskings on this path.  CPU, kernels
+replaced by the test doubles: what is exercised is construction, the module protocol and the outputs' shapes / types."""
+import pytest
+import torch
+
+import _ops_double as D
+import transformers4rec_b200.torch as tr
+from test_abi_and_host import _testing_schema
+
+
+def _batch(schema, B=16, L=20, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(2, L + 1, (B,), generator=g)
+    valid = torch.arange(L)[None] < lens[:, None]
+    out = {}
+    for col in schema:
+        shape = (B, L) if col.is_list else (B,)
+        v = torch.randint(1, col.int_max + 1, shape, generator=g) if col.int_max else torch.rand(shape, generator=g)
+        out[col.name] = torch.where(valid, v, torch.zeros_like(v)) if col.is_list else v
+    return out
+
+
+@pytest.mark.parametrize("masking", ["causal", "mlm", "plm"])
+def test_eval_metrics_with_masking(monkeypatch, masking):
+    """test_model.py:342-359: default task (own output layer), continuous_projection, training forward, metrics from the
+    materialised predictions / labels."""
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_projection=64, d_output=64,
+                                                    masking=masking)
+    model = tr.XLNetConfig.build(64, 4, 2, 20).to_torch_model(inputs, tr.NextItemPredictionTask())
+    with torch.no_grad():
+        out = model(_batch(schema), training=True)
+        result = model.calculate_metrics(predictions=out["predictions"], targets=out["labels"])
+    assert result is not None and len(result) >= 1
+    assert out["predictions"].shape == (out["labels"].numel(), 51997)
+
+
+@pytest.mark.parametrize("d_model", [32, 64, 128])
+def test_with_d_model_different_from_item_dim(monkeypatch, d_model):
+    """test_model.py:362-374"""
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_projection=64,
+                                                    d_output=d_model, masking="mlm")
+    model = tr.XLNetConfig.build(d_model, 4, 2, 20).to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
+    with torch.no_grad():
+        out = model(_batch(schema), training=True)
+    assert torch.isfinite(out["loss"])
+
+
+def test_with_next_item_pred_sampled_softmax(monkeypatch):
+    """test_model.py:377-389"""
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_projection=64, d_output=32,
+                                                    masking="mlm")
+    task = tr.NextItemPredictionTask(weight_tying=True, sampled_softmax=True, max_n_samples=1000)
+    model = tr.XLNetConfig.build(32, 4, 2, 20).to_torch_model(inputs, task)
+    with torch.no_grad():
+        out = model(_batch(schema), training=True)
+    assert torch.isfinite(out["loss"]) and out["predictions"].shape[1] <= 1001
+
+
+@pytest.mark.parametrize("masking", ["causal", "mlm", "plm"])
+def test_output_shape_mode_eval(monkeypatch, masking):
+    """test_model.py:392-407: one prediction row per session in evaluation"""
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, d_output=64, masking=masking)
+    model = tr.XLNetConfig.build(d_model=64, n_head=8, n_layer=2, total_seq_length=20).to_torch_model(
+        inputs, tr.NextItemPredictionTask(weight_tying=True))
+    batch = _batch(schema)
+    with torch.no_grad():
+        out = model(batch, training=False, testing=True)
+    assert out["predictions"].shape[0] == batch["item_id/list"].size(0)
+
+
+@pytest.mark.parametrize("arch", ["xlnet", "gpt2"])
+def test_item_prediction_model_from_config_inference(monkeypatch, arch):
+    """test_model.py:296-316: ``model(batch)`` (inference) returns [B, target_dim] scores"""
+    D.install(monkeypatch)
+    schema = _testing_schema(tr)
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=20, continuous_projection=64, d_output=128,
+                                                    masking="causal")
+    task = tr.NextItemPredictionTask()
+    cfg = (tr.XLNetConfig if arch == "xlnet" else tr.GPT2Config).build(128, 4, 2, 20)
+    model = cfg.to_torch_model(inputs, task)
+    with torch.no_grad():
+        out = model(_batch(schema))
+    assert out.dim() == 2 and out.size(1) == task.target_dim == 51997
