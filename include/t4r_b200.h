@@ -438,6 +438,11 @@ int t4r_train_scatter_rows(const float* src, const int32_t* idx, int64_t n, int 
 /* in place: z[t, j] <- (exp(z[t, j] - lse[t]) - [labels[t] == v0 + j]) * scale */
 int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_t* labels, int64_t T, int64_t Vc, int64_t v0,
                              float scale, void* stream, int on_host);
+/* sampled softmax, in place: z[t, s] (= x_t . w_s / tau) <- exp(z + col_bias[s] / tau - lse[t]) * scale, 0 where
+ * col_ids[s] == labels[t] (accidental hits were constants in the forward) */
+int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, const float* col_bias,
+                             const int64_t* col_ids, int64_t T, int64_t S, float inv_tau, float scale, void* stream,
+                             int on_host);
 /* dst[idx[r], :] += src[r, col : col + width] (dst rows are `width` wide); rows with idx == skip_index are skipped */
 int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src, int col,
                              int width, int64_t skip_index, void* stream, int on_host);

@@ -454,6 +454,12 @@ def softmax_ce_bwd(z, row_lse, labels, v0, scale):
     return P
 
 
+def sampled_ce_bwd(z, row_lse, labels, col_bias, col_ids, inv_tau, scale):
+    P = torch.exp(z + col_bias.unsqueeze(0) * inv_tau - row_lse[: z.shape[0]].unsqueeze(1)) * scale
+    P[labels.long().unsqueeze(1) == col_ids.long().unsqueeze(0)] = 0.0
+    return P
+
+
 def index_add_rows(dst, idx, src, col, width, skip_index=None):
     idx = idx.long()
     keep = torch.ones_like(idx, dtype=torch.bool) if skip_index is None else idx != skip_index
@@ -466,7 +472,8 @@ TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_tab
                  causal_attn_bwd=causal_attn_bwd, layer_norm_fwd=layer_norm_fwd, layer_norm_bwd=layer_norm_bwd,
                  act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
                  apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,
-                 scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, index_add_rows=index_add_rows)
+                 scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, sampled_ce_bwd=sampled_ce_bwd,
+                 index_add_rows=index_add_rows)
 
 
 # ---------------------------------------------------------------------------------------------------- encoders

@@ -77,3 +77,32 @@ def test_training_step_gradients_on_gpu(arch, masking):
         l.backward()
         opt.step()
     assert l.item() < first
+
+
+def test_training_step_sampled_softmax_on_gpu():
+    import t4r_oracle as O
+    from transformers4rec_b200.training import FusedTrainingStep
+    cards, dims, S = {"item_id/list": 3001}, {"item_id/list": 64}, 300
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 1, 20, weight_scale=0.08, sampled=True, max_n_samples=S)
+    oracle.train(False)
+    B, L = 32, 20
+    batch = synth_batch(B, L, cards, seed=3)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    task = model.heads[0].prediction_task_dict["next-item"]
+    torch.manual_seed(4)
+    raw = torch.multinomial(oracle.dist, 2 * S, replacement=True)
+    task.set_negative_draws(raw.cuda())
+    for p in oracle.parameters():
+        p.grad = None
+    ref = oracle(batch, training=True, draws=draws, neg_samples=O.negatives_from_draws(raw, S))
+    ref["loss"].backward()
+    step = FusedTrainingStep(model)
+    loss = step.forward({k: v.cuda() for k, v in batch.items()})
+    step.backward()
+    assert abs(loss.item() - ref["loss"].item()) < 1e-3
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)

@@ -146,3 +146,42 @@ def test_sgd_trajectories_coincide(monkeypatch):
     assert all(abs(a - b) < 1e-3 for a, b in losses) and losses[-1][1] < losses[0][1]
     for name, po, pm in _pairs(oracle, model):
         assert (pm.detach() - po.detach().reshape(pm.shape)).abs().max().item() < 1e-3, name
+
+
+def test_training_step_sampled_softmax(monkeypatch):
+    """Sampled softmax (config 5's head): gradients against autograd of the oracle's sampled head with the same negatives,
+    with the real per-item code of the new kernel on its host twin."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    twin = ops.host_twin("sampled_ce_bwd")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "sampled_ce_bwd", twin)
+    S = 150
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08, sampled=True, max_n_samples=S)
+    oracle.train(False)
+    B, L = 6, 8
+    batch = synth_batch(B, L, CARDS, CONT, seed=5)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    torch.manual_seed(4)
+    raw = torch.multinomial(oracle.dist, 2 * S, replacement=True)
+    labels_all = batch["item_id/list"][batch["item_id/list"] != 0]
+    raw[:3] = labels_all[:3]     # make accidental hits likely
+    task.set_negative_draws(raw)
+    for p in oracle.parameters():
+        p.grad = None
+    ref = oracle(batch, training=True, draws=draws, neg_samples=O.negatives_from_draws(raw, S))
+    ref["loss"].backward()
+    step = FusedTrainingStep(model)
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref["loss"].item()) < 1e-4
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)

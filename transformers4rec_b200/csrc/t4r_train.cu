@@ -77,6 +77,15 @@ T4R_HD void softmax_ce_bwd_item(float* z, const float* lse, const int64_t* label
   if (labels[t] - v0 == j) p -= scale;
   z[i] = p;
 }
+// sampled softmax (model/prediction_task.py:673-696): z holds x.w_s / tau for the S sampled negatives; the logit the
+// forward used is z + bias_s / tau, except accidental hits (col_ids[s] == labels[t]) which were a constant -> no gradient.
+// In place: z[t, s] <- exp(logit - lse[t]) * scale, 0 at hits.
+T4R_HD void sampled_ce_bwd_item(float* z, const float* lse, const int64_t* labels, const float* col_bias,
+                                const int64_t* col_ids, int64_t S, float inv_tau, float scale, int64_t i) {
+  const int64_t t = i / S, s_ = i % S;
+  if (col_ids[s_] == labels[t]) { z[i] = 0.f; return; }
+  z[i] = expf(z[i] + col_bias[s_] * inv_tau - lse[t]) * scale;
+}
 // dst[idx[r], 0:width] += src[r, col:col+width]   (skip rows whose index is skip_index)
 T4R_HD void index_add_item(float* dst, const int64_t* idx, const float* src, int64_t ld_src, int col, int width,
                            int64_t skip_index, int64_t i) {
@@ -301,6 +310,12 @@ extern "C" int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_
                                         int64_t v0, float scale, void* stream, int on_host) {
   T4R_REQUIRE(z && lse && labels && T > 0 && Vc > 0, "train_softmax_ce_bwd: bad arguments");
   T4R_ITEMS(T * Vc, "train_softmax_ce_bwd", softmax_ce_bwd_item(z, lse, labels, Vc, v0, scale, i));
+}
+extern "C" int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, const float* col_bias,
+                                        const int64_t* col_ids, int64_t T, int64_t S, float inv_tau, float scale,
+                                        void* stream, int on_host) {
+  T4R_REQUIRE(z && lse && labels && col_bias && col_ids && T > 0 && S > 0, "train_sampled_ce_bwd: bad arguments");
+  T4R_ITEMS(T * S, "train_sampled_ce_bwd", sampled_ce_bwd_item(z, lse, labels, col_bias, col_ids, S, inv_tau, scale, i));
 }
 extern "C" int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src,
                                         int col, int width, int64_t skip_index, void* stream, int on_host) {

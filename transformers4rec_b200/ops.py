@@ -719,6 +719,18 @@ def softmax_ce_bwd(z, row_lse, labels, v0, scale, _on_host=False):
     return z
 
 
+def sampled_ce_bwd(z, row_lse, labels, col_bias, col_ids, inv_tau, scale, _on_host=False):
+    """In place on ``z`` [T, S] (= x . w_s / tau of the sampled negatives): exp(logit - lse) * scale, 0 at accidental hits."""
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    row_lse, col_bias = _f32c(row_lse), _f32c(col_bias)
+    labels, col_ids = labels.long().contiguous(), col_ids.long().contiguous()
+    tail = _tr(_on_host, z, row_lse, labels, col_bias, col_ids)
+    T, S = z.shape
+    check(_lib.load().t4r_train_sampled_ce_bwd(ptr(z), ptr(row_lse), ptr(labels), ptr(col_bias), ptr(col_ids), T, S,
+                                               float(inv_tau), float(scale), *tail), "t4r_train_sampled_ce_bwd")
+    return z
+
+
 def index_add_rows(dst, idx, src, col, width, skip_index=None, _on_host=False):
     assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.shape[1] == width
     src, idx = _f32c(src), idx.long().contiguous()

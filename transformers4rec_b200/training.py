@@ -23,8 +23,8 @@ Status: written without access to a GPU.  The COMPOSITION (every formula, every 
 masks / codes / tied weights) is verified on the CPU against torch autograd of the oracle graph with the kernels
 replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a one-thread-per-row/element call of
 a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
-nothing in the inference path uses this module.  Not covered: sampled softmax, row-sharded tables, soft embeddings /
-element-wise aggregations, label smoothing, PLM.
+nothing in the inference path uses this module.  Covered: full softmax (replicated or row-sharded table) and sampled
+softmax (replicated table).  Not covered: soft embeddings / element-wise aggregations, label smoothing, PLM.
 """
 from __future__ import annotations
 
@@ -221,8 +221,8 @@ class FusedTrainingStep:
             raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
         if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling)):
             raise NotImplementedError("FusedTrainingStep: MLM or CLM masking")
-        if not task.weight_tying or task.sampled_softmax or task.label_smoothing:
-            raise NotImplementedError("FusedTrainingStep: tied weights, full softmax, no label smoothing")
+        if not task.weight_tying or task.label_smoothing:
+            raise NotImplementedError("FusedTrainingStep: tied weights, no label smoothing")
         task.output_weight()             # refreshes task.item_embedding_table (the table may have been sharded after build)
         self.sharded = task._sharded()   # row-sharded item table (BASELINE configs 4-5): see _forward/_backward_sharded
         enc = self.tblock.transformer
@@ -295,6 +295,23 @@ class FusedTrainingStep:
         W = task.output_weight().detach().float()
         inv_tau = task._inv_tau()
         y_lab = self.labels[:T]
+        self.sampled = bool(task.sampled_softmax)
+        if self.sampled and self.sharded:
+            raise NotImplementedError("FusedTrainingStep: sampled softmax over a row-sharded table")
+        if self.sampled:
+            # model/prediction_task.py:673-696: the positive's logit + the S sampled negatives, logQ-corrected
+            neg, _, _ = task.sampler.sample(y_lab[:1], raw_draws=task._neg_draws)
+            self.neg = neg
+            nlq = task.sampler.neg_log_q
+            self.col_bias = nlq[neg].contiguous()
+            self.neg_rows = ops.gather_rows(W, neg)
+            self.pos = ops.label_logit(xt, W, y_lab, class_bias=nlq, inv_temperature=inv_tau)
+            res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(self.neg_rows), None,
+                                      inv_temperature=inv_tau, col_bias=self.col_bias, col_ids=neg,
+                                      hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=self.pos)
+            self.row_lse = res["row_lse"]
+            self.loss = res["loss"].reshape(())
+            return self.loss
         if self.sharded:
             # forward and backward of the sharded head in one go (its only upstream gradient is d loss = 1)
             from . import distributed as D
@@ -322,6 +339,8 @@ class FusedTrainingStep:
         if self.sharded:
             return self._backward_sharded(float(grad_loss))
         scale = float(grad_loss) / max(T, 1)
+        if self.sampled:
+            return self._backward_sampled(Wp, W, y_lab, inv_tau, scale)
         dxt = torch.zeros_like(self.xt)
         dW = torch.zeros_like(W)
         xt_t = ops.transpose(self.xt)                                   # [De, T]
@@ -334,6 +353,25 @@ class FusedTrainingStep:
             dxt = gemm_nt(P, ops.transpose(Wc), residual=dxt)              # dX_t += P W_c
             dW[v0:v1] = gemm_nt(ops.transpose(P), xt_t)                      # dW_c = P^T X_t
         _acc(Wp, dW)                                                        # tied: the item table's grad starts here
+        self._backward_body(dxt)
+        return self.loss
+
+    def _backward_sampled(self, Wp, W, y_lab, inv_tau, scale):
+        """Sampled softmax: the logits [T, 1 + S] are small enough to be recomputed whole.  P_neg = softmax over the
+        negatives (0 at accidental hits: constants in the forward), P_pos = softmax(positive) - 1; the logQ terms are
+        constants.  dX_t = (P_neg W_neg + P_pos W[y]) / tau; dW gets P_neg^T X_t at the negatives' rows and P_pos X_t at
+        the labels' rows (scatter-add: duplicates among the labels)."""
+        T, De = self.xt.shape
+        z = ops.head_logits(ops.split_planes(self.xt), ops.split_planes(self.neg_rows), De, inv_temperature=inv_tau)
+        P = ops.sampled_ce_bwd(z, self.row_lse, y_lab, self.col_bias, self.neg, inv_tau, scale * inv_tau)
+        p_pos = (torch.exp(self.pos[:T] - self.row_lse[:T]) - 1.0) * (scale * inv_tau)      # [T]: tiny, plain torch
+        w_pos = ops.gather_rows(W, y_lab)
+        dxt = gemm_nt(P, ops.transpose(self.neg_rows), residual=(w_pos * p_pos.unsqueeze(1)).contiguous())
+        dW = torch.zeros_like(W)
+        dneg = gemm_nt(ops.transpose(P), ops.transpose(self.xt))                              # [S, De]
+        ops.index_add_rows(dW, self.neg, dneg, 0, De)
+        ops.index_add_rows(dW, y_lab, (self.xt * p_pos.unsqueeze(1)).contiguous(), 0, De)
+        _acc(Wp, dW)
         self._backward_body(dxt)
         return self.loss
 
