@@ -221,6 +221,17 @@ def time_oracle_cpu(cfg, B_cpu, steps, warmup, budget_s=8.0):
             best_t, best_threads = t, threads
     torch.set_num_threads(best_threads)
     grow = int(max(1, min(8, budget_s // max(best_t, 1e-3))))
+    # memory bound: the reference materialises [T, V] fp32 logits (plus ~3 same-sized temporaries in CrossEntropyLoss);
+    # keep that under a quarter of the host memory that is free right now
+    try:
+        import psutil
+        free = psutil.virtual_memory().available
+    except Exception:
+        free = 16 << 30
+    labels_per_session = cfg["L"] if cfg["masking"] == "clm" else max(3.0, 0.15 * cfg["L"] + 1)
+    width = (cfg.get("sampled") or cfg["V"])
+    per_session = labels_per_session * width * 4 * 4
+    grow = int(max(1, min(grow, (0.25 * free) // max(per_session * B_cpu, 1))))
     B_run = B_cpu * grow
     med = _oracle_step_seconds(oracle, cfg, B_run, steps, warmup)
     return B_run / med, med, best_threads, B_run
