@@ -435,9 +435,10 @@ int t4r_train_row_codes_bwd(const float* dx, const uint8_t* code, int64_t M, int
 int t4r_train_gather_rows(const float* x, const int32_t* idx, int64_t n, int d, float* out, void* stream, int on_host);
 int t4r_train_scatter_rows(const float* src, const int32_t* idx, int64_t n, int d, int64_t out_rows, float* out,
                            void* stream, int on_host);
-/* in place: z[t, j] <- (exp(z[t, j] - lse[t]) - [labels[t] == v0 + j]) * scale */
+/* in place: z[t, j] <- (exp(z[t, j] - lse[t]) - (1 - e) [labels[t] == v0 + j] - e / V_total) * scale,
+ * e = label_smoothing (0 = plain cross-entropy) */
 int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_t* labels, int64_t T, int64_t Vc, int64_t v0,
-                             float scale, void* stream, int on_host);
+                             float scale, float label_smoothing, int64_t V_total, void* stream, int on_host);
 /* sampled softmax, in place: z[t, s] (= x_t . w_s / tau) <- exp(z + col_bias[s] / tau - lse[t]) * scale, 0 where
  * col_ids[s] == labels[t] (accidental hits were constants in the forward) */
 int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, const float* col_bias,

@@ -445,12 +445,13 @@ def scatter_rows(src, idx, n_rows):
     return out
 
 
-def softmax_ce_bwd(z, row_lse, labels, v0, scale):
-    P = torch.exp(z - row_lse[: z.shape[0]].unsqueeze(1)) * scale
+def softmax_ce_bwd(z, row_lse, labels, v0, scale, label_smoothing=0.0, V_total=None):
+    V_total = V_total if V_total is not None else z.shape[1]
+    P = (torch.exp(z - row_lse[: z.shape[0]].unsqueeze(1)) - label_smoothing / V_total) * scale
     loc = labels.long() - v0
     mine = (loc >= 0) & (loc < z.shape[1])
     rows = torch.arange(z.shape[0])[mine]
-    P[rows, loc[mine]] -= scale
+    P[rows, loc[mine]] -= (1.0 - label_smoothing) * scale
     return P
 
 

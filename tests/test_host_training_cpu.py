@@ -185,3 +185,37 @@ def test_training_step_sampled_softmax(monkeypatch):
             continue
         err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
+def test_training_step_label_smoothing(monkeypatch):
+    """nn.CrossEntropyLoss(label_smoothing=0.1) (transformers4rec/torch/losses.py:4-20): the smoothed target
+    distribution in the head's backward, with the kernel's real per-item code."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    twin = ops.host_twin("softmax_ce_bwd")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "softmax_ce_bwd", twin)
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08)
+    oracle.train(False)
+    B, L = 6, 8
+    batch = synth_batch(B, L, CARDS, CONT, seed=6)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    model.heads[0].prediction_task_dict["next-item"].label_smoothing = 0.1
+    for p in oracle.parameters():
+        p.grad = None
+    out = oracle(batch, training=True, draws=draws)
+    ref = torch.nn.functional.cross_entropy(out["predictions"], out["labels"], label_smoothing=0.1)
+    ref.backward()
+    step = FusedTrainingStep(model, head_chunk=500)
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref.item()) < 1e-4
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)

@@ -70,11 +70,12 @@ T4R_HD void scatter_rows_item(const float* src, const int32_t* idx, int d, float
   out[static_cast<int64_t>(idx[i / d]) * d + (i % d)] = src[i];  // label rows are unique
 }
 // P = exp(z - lse) * scale, minus scale at the label's column (if it falls in this column chunk)
+// label smoothing e (transformers4rec/torch/losses.py:4-20): the target distribution is (1 - e) onehot + e / V
 T4R_HD void softmax_ce_bwd_item(float* z, const float* lse, const int64_t* labels, int64_t Vc, int64_t v0, float scale,
-                                int64_t i) {
+                                float smooth, float inv_V, int64_t i) {
   const int64_t t = i / Vc, j = i % Vc;
-  float p = expf(z[i] - lse[t]) * scale;
-  if (labels[t] - v0 == j) p -= scale;
+  float p = (expf(z[i] - lse[t]) - smooth * inv_V) * scale;
+  if (labels[t] - v0 == j) p -= (1.0f - smooth) * scale;
   z[i] = p;
 }
 // sampled softmax (model/prediction_task.py:673-696): z holds x.w_s / tau for the S sampled negatives; the logit the
@@ -307,9 +308,11 @@ extern "C" int t4r_train_scatter_rows(const float* src, const int32_t* idx, int6
   T4R_ITEMS(n * d, "train_scatter_rows", scatter_rows_item(src, idx, d, out, i));
 }
 extern "C" int t4r_train_softmax_ce_bwd(float* z, const float* lse, const int64_t* labels, int64_t T, int64_t Vc,
-                                        int64_t v0, float scale, void* stream, int on_host) {
-  T4R_REQUIRE(z && lse && labels && T > 0 && Vc > 0, "train_softmax_ce_bwd: bad arguments");
-  T4R_ITEMS(T * Vc, "train_softmax_ce_bwd", softmax_ce_bwd_item(z, lse, labels, Vc, v0, scale, i));
+                                        int64_t v0, float scale, float label_smoothing, int64_t V_total, void* stream,
+                                        int on_host) {
+  T4R_REQUIRE(z && lse && labels && T > 0 && Vc > 0 && V_total > 0, "train_softmax_ce_bwd: bad arguments");
+  const float inv_V = 1.0f / static_cast<float>(V_total);
+  T4R_ITEMS(T * Vc, "train_softmax_ce_bwd", softmax_ce_bwd_item(z, lse, labels, Vc, v0, scale, label_smoothing, inv_V, i));
 }
 extern "C" int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, const float* col_bias,
                                         const int64_t* col_ids, int64_t T, int64_t S, float inv_tau, float scale,

@@ -708,13 +708,14 @@ def scatter_rows(src, idx, n_rows, _on_host=False):
     return out
 
 
-def softmax_ce_bwd(z, row_lse, labels, v0, scale, _on_host=False):
-    """In place on ``z`` [T, Vc]: (softmax - onehot) * scale; returns ``z``."""
+def softmax_ce_bwd(z, row_lse, labels, v0, scale, label_smoothing=0.0, V_total=None, _on_host=False):
+    """In place on ``z`` [T, Vc]: (softmax - target distribution) * scale; returns ``z``."""
     assert z.dtype == torch.float32 and z.is_contiguous()
     row_lse, labels = _f32c(row_lse), labels.long().contiguous()
     tail = _tr(_on_host, z, row_lse, labels)
     T, Vc = z.shape
-    check(_lib.load().t4r_train_softmax_ce_bwd(ptr(z), ptr(row_lse), ptr(labels), T, Vc, int(v0), float(scale), *tail),
+    check(_lib.load().t4r_train_softmax_ce_bwd(ptr(z), ptr(row_lse), ptr(labels), T, Vc, int(v0), float(scale),
+                                               float(label_smoothing), int(V_total if V_total is not None else Vc), *tail),
           "t4r_train_softmax_ce_bwd")
     return z
 

@@ -24,7 +24,8 @@ masks / codes / tied weights) is verified on the CPU against torch autograd of t
 replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a one-thread-per-row/element call of
 a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
 nothing in the inference path uses this module.  Covered: full softmax (replicated or row-sharded table) and sampled
-softmax (replicated table).  Not covered: soft embeddings / element-wise aggregations, label smoothing, PLM.
+softmax (replicated table), label smoothing (replicated full softmax).  Not covered: soft embeddings / element-wise
+aggregations, PLM.
 """
 from __future__ import annotations
 
@@ -221,8 +222,8 @@ class FusedTrainingStep:
             raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
         if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling)):
             raise NotImplementedError("FusedTrainingStep: MLM or CLM masking")
-        if not task.weight_tying or task.label_smoothing:
-            raise NotImplementedError("FusedTrainingStep: tied weights, no label smoothing")
+        if not task.weight_tying:
+            raise NotImplementedError("FusedTrainingStep: tied weights")
         task.output_weight()             # refreshes task.item_embedding_table (the table may have been sharded after build)
         self.sharded = task._sharded()   # row-sharded item table (BASELINE configs 4-5): see _forward/_backward_sharded
         enc = self.tblock.transformer
@@ -296,8 +297,11 @@ class FusedTrainingStep:
         inv_tau = task._inv_tau()
         y_lab = self.labels[:T]
         self.sampled = bool(task.sampled_softmax)
+        self.smooth = float(task.label_smoothing or 0.0)
         if self.sampled and self.sharded:
             raise NotImplementedError("FusedTrainingStep: sampled softmax over a row-sharded table")
+        if self.smooth and (self.sampled or self.sharded):
+            raise NotImplementedError("FusedTrainingStep: label smoothing with the replicated full softmax only")
         if self.sampled:
             # model/prediction_task.py:673-696: the positive's logit + the S sampled negatives, logQ-corrected
             neg, _, _ = task.sampler.sample(y_lab[:1], raw_draws=task._neg_draws)
@@ -321,7 +325,8 @@ class FusedTrainingStep:
                 head_chunk=self.head_chunk, head_rows=getattr(table, "train_head_rows", None),
                 train_head=getattr(table, "train_head", None))
             return self.loss
-        res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(W), W, inv_temperature=inv_tau)
+        res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(W), W, inv_temperature=inv_tau,
+                                  label_smoothing=self.smooth)
         self.row_lse = res["row_lse"]
         self.loss = res["loss"].reshape(())
         return self.loss
@@ -349,7 +354,8 @@ class FusedTrainingStep:
             v1 = min(V, v0 + self.head_chunk)
             Wc = W[v0:v1].contiguous()
             z = ops.head_logits(xt_planes, ops.split_planes(Wc), De, inv_temperature=inv_tau)          # [T, Vc]
-            P = ops.softmax_ce_bwd(z, self.row_lse, y_lab, v0, scale * inv_tau)   # (softmax - onehot) * dL/dz scale
+            P = ops.softmax_ce_bwd(z, self.row_lse, y_lab, v0, scale * inv_tau,   # (softmax - target) * dL/dz scale
+                                   label_smoothing=self.smooth, V_total=V)
             dxt = gemm_nt(P, ops.transpose(Wc), residual=dxt)              # dX_t += P W_c
             dW[v0:v1] = gemm_nt(ops.transpose(P), xt_t)                      # dW_c = P^T X_t
         _acc(Wp, dW)                                                        # tied: the item table's grad starts here
