@@ -219,3 +219,33 @@ def test_training_step_label_smoothing(monkeypatch):
             continue
         err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
+def test_model_forward_routes_to_the_training_step_when_enabled(monkeypatch):
+    """``model.enable_fused_training()``: the reference's training loop shape -- forward with training=True, loss.backward(),
+    optimizer.step() -- runs on the fused step; under no_grad (or with the switch off) nothing changes."""
+    D.install(monkeypatch)
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08)
+    batch = synth_batch(6, 8, CARDS, CONT, seed=7)
+    u, draws = mlm_draws(6, 8)
+    model.heads[0].body[0].masking.set_draws(u)
+    with torch.no_grad():
+        plain = model(batch, training=True)["loss"].item()
+    model.enable_fused_training(head_chunk=512)
+    with torch.no_grad():
+        assert model(batch, training=True)["loss"].item() == plain          # no autograd -> the forward-only path
+    opt = torch.optim.SGD(model.parameters(), lr=0.2)
+    first = None
+    for _ in range(4):
+        opt.zero_grad()
+        out = model(batch, training=True)
+        out["loss"].backward()
+        opt.step()
+        first = first if first is not None else out["loss"].item()
+    assert abs(first - plain) < 1e-4 and out["loss"].item() < first
+    assert out["labels"].numel() > 0 and all(p.grad is not None for n, p in model.named_parameters()
+                                              if "seg_embed" not in n and "r_s_bias" not in n and "word_embedding" not in n
+                                              and "mask_emb" not in n)
+    model.enable_fused_training(False)
+    assert getattr(model, "_fused_step") is None

@@ -102,7 +102,24 @@ class Model(nn.Module):
         self.top_k = kwargs.get("top_k", None)
         self.max_sequence_length = kwargs.get("max_sequence_length", None)
 
+    def enable_fused_training(self, on: bool = True, head_chunk: int = 32768):
+        """N3: route ``model(batch, training=True)`` through the fused training step whenever autograd is recording, so
+        that the usual ``loss = model(batch, training=True)["loss"]; loss.backward(); optimizer.step()`` (HF Trainer's
+        compute_loss / training_step, trainer.py:315-338 in the reference) trains on the t4r kernels.  Opt-in; with it
+        off (the default) or under ``torch.no_grad()`` the forward-only path runs as before."""
+        if on:
+            from .training import FusedTrainingStep
+            self._fused_step = FusedTrainingStep(self, head_chunk=head_chunk)
+        else:
+            self._fused_step = None
+        return self
+
     def forward(self, inputs: Dict[str, torch.Tensor], targets=None, training=False, testing=False, **kwargs):
+        if training and not testing and getattr(self, "_fused_step", None) is not None and torch.is_grad_enabled():
+            from .training import training_loss
+            step = self._fused_step
+            loss = training_loss(self, inputs, step)
+            return {"loss": loss, "labels": step.labels[:step.T]}
         # model/base.py:546-548: floating inputs are cast to fp32
         for name, val in inputs.items():
             if torch.is_floating_point(val) and val.dtype != torch.float32:
