@@ -460,7 +460,12 @@ int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int64_t M, int 
  * qkv / dqkv [M, 3d] (q | k | v), dout [M, d].  XLNet relative form: R [2L, d], rw / rr [d], their gradients and
  * part = scratch of B (2L + 2) d floats; all seven NULL selects GPT-2's causal form. */
 int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B, int L,
-                       int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part, void* stream, int on_host);
+                       int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
+                       const uint8_t* plm_mask /* NULL, or [B, L, L]: two-stream form over 2 B L rows */, void* stream,
+                       int on_host);
+/* two-stream (PLM) attention forward on split planes [2, 2 B L, 3d] (h rows then g rows), R planes [2, 2L, d] */
+int t4r_train_xlnet_attn_plm_fwd(const void* qkv_planes, const void* r_planes, const float* rw, const float* rr, int B,
+                                 int L, int d, int H, const uint8_t* plm_mask, void* out_planes, void* stream);
 /* forward pieces of the training graph that reuse inference kernels on fp32 q|k|v (device only) */
 int t4r_train_xlnet_attn_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d, int H,
                              void* out_planes /*[2, M, d]*/, void* stream);

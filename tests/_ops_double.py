@@ -365,12 +365,32 @@ def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H):
     return torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(B * L, -1)
 
 
-def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H):
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None):
     with torch.enable_grad():
         a, b, c, e = (t.detach().clone().requires_grad_(True) for t in (qkv, R, rw, rr))
-        out = xlnet_attn_fwd(a, b, c, e, B, L, H)
+        out = xlnet_attn_fwd(a, b, c, e, B, L, H) if plm_mask is None else xlnet_attn_plm_fwd(a, b, c, e, B, L, H, plm_mask)
         out.backward(dout)
     return a.grad, b.grad, c.grad, e.grad
+
+
+def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask):
+    """HF:xlnet two-stream rel_attn_core with target_mapping = identity: rows [0, M) = content stream h, [M, 2M) = query
+    stream g; K / V from h; score - 1e30 * mask (h: diagonal exempt)."""
+    M = B * L
+    d = qkv.shape[1] // 3
+    dh = d // H
+    kv = qkv[:M]
+    outs = []
+    for st in range(2):
+        q_rows = qkv[st * M:(st + 1) * M, :d]
+        fake = torch.cat([q_rows, kv[:, d:]], dim=1)
+        s, v = _xl_scores(fake, R, rw, rr, B, L, H)
+        m = plm_mask.float().view(B, 1, L, L)
+        if st == 0:
+            m = m * (1.0 - torch.eye(L)).view(1, 1, L, L)
+        s = s - 1e30 * m
+        outs.append(torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(M, d))
+    return torch.cat(outs, dim=0)
 
 
 def causal_attn_fwd(qkv, B, L, H):
@@ -469,7 +489,8 @@ def index_add_rows(dst, idx, src, col, width, skip_index=None):
 
 
 TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_table, rel_pos_proj=rel_pos_proj,
-                 xlnet_attn_fwd=xlnet_attn_fwd, xlnet_attn_bwd=xlnet_attn_bwd, causal_attn_fwd=causal_attn_fwd,
+                 xlnet_attn_fwd=xlnet_attn_fwd, xlnet_attn_plm_fwd=xlnet_attn_plm_fwd, xlnet_attn_bwd=xlnet_attn_bwd,
+                 causal_attn_fwd=causal_attn_fwd,
                  causal_attn_bwd=causal_attn_bwd, layer_norm_fwd=layer_norm_fwd, layer_norm_bwd=layer_norm_bwd,
                  act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
                  apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,

@@ -106,3 +106,35 @@ def test_training_step_sampled_softmax_on_gpu():
             continue
         err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
+def test_training_step_plm_on_gpu():
+    """PLM: two-stream forward (MASKED tensor-path attention) and backward on the GPU vs autograd of HF's two-stream model."""
+    from transformers4rec_b200.training import FusedTrainingStep
+    oracle, model = make_pair({"item_id/list": 3001}, {"item_id/list": 64}, "item_id/list", (), 64, 4, 2, 20,
+                              masking="plm", weight_scale=0.08)
+    oracle.train(False)
+    enc = model.heads[0].body[1].transformer
+    with torch.no_grad():
+        enc.mask_emb.normal_(0.0, 0.5)
+        oracle.transformer.mask_emb.copy_(enc.mask_emb.cpu())
+    B, L = 24, 20
+    batch = synth_batch(B, L, {"item_id/list": 3001}, seed=8)
+    g = torch.Generator().manual_seed(3)
+    draws = {"u_span": torch.rand((B, L), generator=g), "u_start": torch.rand((B, L), generator=g),
+             "u_force": torch.rand((B,), generator=g), "u_unmask": torch.rand((B,), generator=g),
+             "perm": torch.stack([torch.randperm(L, generator=g) for _ in range(B)])}
+    model.heads[0].body[0].masking.set_draws({k: v.cuda() for k, v in draws.items()})
+    for p in oracle.parameters():
+        p.grad = None
+    ref = oracle(batch, training=True, draws=draws)
+    ref["loss"].backward()
+    step = FusedTrainingStep(model, head_chunk=1024)
+    loss = step.forward({k: v.cuda() for k, v in batch.items()})
+    step.backward()
+    assert abs(loss.item() - ref["loss"].item()) < 1e-3
+    for name, po, pm in list(_pairs(oracle, model)) + [("mask_emb", oracle.transformer.mask_emb, enc.mask_emb)]:
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)

@@ -249,3 +249,44 @@ def test_model_forward_routes_to_the_training_step_when_enabled(monkeypatch):
                                               and "mask_emb" not in n)
     model.enable_fused_training(False)
     assert getattr(model, "_fused_step") is None
+
+
+def test_training_step_permutation_language_modeling(monkeypatch):
+    """PLM: XLNet's two-stream forward and its backward (incl. mask_emb) against autograd of HF's own two-stream model,
+    with the attention backward's real per-item code (mask / stream handling) on its host twin."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    twin = ops.host_twin("xlnet_attn_bwd")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "xlnet_attn_bwd", twin)
+    oracle, model = make_pair({"item_id/list": 801}, {"item_id/list": 32}, "item_id/list", (), 32, 2, 2, 10,
+                              masking="plm", device="cpu", weight_scale=0.08)
+    oracle.train(False)
+    enc = model.heads[0].body[1].transformer
+    with torch.no_grad():
+        enc.mask_emb.normal_(0.0, 0.5)
+        oracle.transformer.mask_emb.copy_(enc.mask_emb)
+    B, L = 7, 10
+    batch = synth_batch(B, L, {"item_id/list": 801}, seed=8)
+    g = torch.Generator().manual_seed(3)
+    draws = {"u_span": torch.rand((B, L), generator=g), "u_start": torch.rand((B, L), generator=g),
+             "u_force": torch.rand((B,), generator=g), "u_unmask": torch.rand((B,), generator=g),
+             "perm": torch.stack([torch.randperm(L, generator=g) for _ in range(B)])}
+    model.heads[0].body[0].masking.set_draws(draws)
+    for p in oracle.parameters():
+        p.grad = None
+    ref = oracle(batch, training=True, draws=draws)
+    ref["loss"].backward()
+    step = FusedTrainingStep(model, head_chunk=300)
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref["loss"].item()) < 1e-4
+    pairs = list(_pairs(oracle, model)) + [("mask_emb", oracle.transformer.mask_emb, enc.mask_emb)]
+    for name, po, pm in pairs:
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+    assert enc.mask_emb.grad is not None and enc.mask_emb.grad.abs().max().item() > 0

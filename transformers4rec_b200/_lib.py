@@ -182,7 +182,8 @@ SIGNATURES = {
     "t4r_train_col_sum": (c_int, [_P, c_int64, c_int64, _P, _P, c_int]),
     "t4r_train_layer_norm_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, c_int]),
     "t4r_train_layer_norm_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int]),
-    "t4r_train_attn_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int]),
+    "t4r_train_attn_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int]),
+    "t4r_train_xlnet_attn_plm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "t4r_train_xlnet_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "t4r_train_causal_attn_fwd": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),
     "t4r_train_rel_pos_proj": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, _P, _P]),

@@ -154,29 +154,40 @@ T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const f
 //   dq_i = sum_j ds_j (k_j + R_m)        dk_j += ds_j (q_i + rw)        dv_j += p_j do_i
 //   dR_m += ds_j (q_i + rr)              drw  += ds_j k_j               drr  += ds_j R_m          m = j + L - i
 constexpr int kAttnMaxL = 64;
+// plm_mask != nullptr: XLNet's two-stream form (permutation language modeling).  qkv / dout / dqkv then hold 2 B L rows
+// (content stream h, then query stream g); the item runs both streams: queries from the stream's rows, keys / values
+// from the h rows, score (i, j) forced to -1e30 where plm_mask[b, i, j] (h: except i == j) -- a constant, so such an
+// entry passes no gradient to q / k / R / the biases (its probability still weighs v_j, e.g. in a fully masked row).
 T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
                           int L, int d, int H, float* dqkv, float* dR_part, float* drw_part, float* drr_part,
-                          int64_t item) {
+                          const uint8_t* plm_mask, int64_t item) {
   const int dh = d / H;
   const int h = static_cast<int>(item % H);
   const int64_t b = item / H;
   const bool rel = R != nullptr;
+  const int n_streams = plm_mask ? 2 : 1;
+  const int64_t M = static_cast<int64_t>(B) * L;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  // zero what this item owns
-  for (int r = 0; r < L; ++r)
-    for (int part = 0; part < 3; ++part)
-      for (int c = 0; c < dh; ++c) dqkv[(b * L + r) * 3 * d + part * d + h * dh + c] = 0.f;
+  // zero what this item owns (for both streams' rows)
+  for (int st = 0; st < n_streams; ++st)
+    for (int r = 0; r < L; ++r)
+      for (int part = 0; part < 3; ++part)
+        for (int c = 0; c < dh; ++c) dqkv[(st * M + b * L + r) * 3 * d + part * d + h * dh + c] = 0.f;
   if (rel) {
     for (int m = 0; m < 2 * L; ++m)
       for (int c = 0; c < dh; ++c) dR_part[(b * 2 * L + m) * d + h * dh + c] = 0.f;
     for (int c = 0; c < dh; ++c) { drw_part[b * d + h * dh + c] = 0.f; drr_part[b * d + h * dh + c] = 0.f; }
   }
   float s[kAttnMaxL], dp[kAttnMaxL];
+  bool msk[kAttnMaxL];
+  for (int st = 0; st < n_streams; ++st)
   for (int i = 0; i < L; ++i) {
-    const float* q = qkv + (b * L + i) * 3 * d + h * dh;
-    const float* dor = dout + (b * L + i) * d + h * dh;
+    const float* q = qkv + (st * M + b * L + i) * 3 * d + h * dh;
+    const float* dor = dout + (st * M + b * L + i) * d + h * dh;
     float mx = -INFINITY;
     for (int j = 0; j < L; ++j) {
+      msk[j] = plm_mask && plm_mask[(b * L + i) * L + j] && !(st == 0 && i == j);
+      if (msk[j]) { s[j] = -1e30f; mx = fmaxf(mx, s[j]); continue; }
       if (!rel && j > i) { s[j] = -INFINITY; continue; }
       const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
       float acc = 0.f;
@@ -201,7 +212,7 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
       dp[j] = acc;
       dot += s[j] * acc;
     }
-    float* dq = dqkv + (b * L + i) * 3 * d + h * dh;
+    float* dq = dqkv + (st * M + b * L + i) * 3 * d + h * dh;
     for (int j = 0; j < L; ++j) {
       const float p = s[j];
       if (!rel && j > i) continue;
@@ -209,6 +220,10 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
       const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
       float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
       float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+      if (msk[j]) {   // constant score: only the value path carries a gradient
+        for (int c = 0; c < dh; ++c) dv[c] += p * dor[c];
+        continue;
+      }
       if (rel) {
         const int64_t m = j + L - i;
         const float* Rm = R + m * d + h * dh;
@@ -354,15 +369,16 @@ extern "C" int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int6
 // form): per-session partials of dR / drw / drr, reduced over the sessions here.
 extern "C" int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout,
                                   int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
-                                  void* stream, int on_host) {
+                                  const uint8_t* plm_mask, void* stream, int on_host) {
   T4R_REQUIRE(qkv && dout && dqkv && B > 0 && L > 0 && L <= kAttnMaxL && H > 0 && d % H == 0, "train_attn_bwd: bad arguments (L <= 64)");
   const bool rel = R != nullptr;
   T4R_REQUIRE(!rel || (rw && rr && dR && drw && drr && part), "train_attn_bwd: the relative form needs R, both biases, their gradients and the scratch");
+  T4R_REQUIRE(plm_mask == nullptr || rel, "train_attn_bwd: the two-stream (PLM) form is XLNet's relative attention");
   float* dR_part = part;
   float* drw_part = rel ? part + static_cast<int64_t>(B) * 2 * L * d : nullptr;
   float* drr_part = rel ? drw_part + static_cast<int64_t>(B) * d : nullptr;
   T4R_TRY(run_items(static_cast<int64_t>(B) * H, [=] __host__ __device__(int64_t i) {
-            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, i); },
+            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, i); },
           "train_attn_bwd", stream, on_host));
   if (!rel) return 0;
   T4R_TRY(run_items(static_cast<int64_t>(2) * L * d, [=] __host__ __device__(int64_t i) { sum_sessions_item(dR_part, B, 2 * L, d, dR, i); },
@@ -389,4 +405,15 @@ extern "C" int t4r_train_causal_attn_fwd(const float* qkv, int B, int L, int d, 
 extern "C" int t4r_train_rel_pos_proj(const float* const* wr, int n_layer, int L, int d, float* r_out, void* stream) {
   T4R_REQUIRE(wr && r_out && n_layer >= 1 && n_layer <= T4R_MAX_FEATURES && L > 0 && d > 0, "train_rel_pos_proj: bad arguments");
   return launch_rel_pos_proj(wr, n_layer, L, d, r_out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// two-stream (PLM) attention forward on split planes [2, 2 B L, 3d]: the MASKED tensor-path kernels of t4r_attn_mma.cu
+extern "C" int t4r_train_xlnet_attn_plm_fwd(const void* qkv_planes, const void* r_planes, const float* rw, const float* rr,
+                                            int B, int L, int d, int H, const uint8_t* plm_mask, void* out_planes,
+                                            void* stream) {
+  T4R_REQUIRE(qkv_planes && r_planes && rw && rr && plm_mask && out_planes && B > 0 && L > 0, "train_xlnet_attn_plm_fwd: bad arguments");
+  const int64_t M2 = static_cast<int64_t>(2) * B * L;
+  return launch_attn_mma_plm(static_cast<const __nv_bfloat16*>(qkv_planes), M2 * 3 * d,
+                             static_cast<const __nv_bfloat16*>(r_planes), static_cast<int64_t>(2) * L * d, rw, rr, B, L, d, H,
+                             static_cast<__nv_bfloat16*>(out_planes), M2 * d, plm_mask, static_cast<cudaStream_t>(stream));
 }

@@ -773,9 +773,11 @@ def layer_norm_bwd(x_pre, gamma, eps, dy, add=None, _on_host=False):
     return dx, dg, db
 
 
-def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, _on_host=False):
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None, _on_host=False):
+    """``plm_mask`` [B, L, L] uint8: the two-stream form (qkv / dout hold 2 B L rows: content stream, then query stream)."""
     qkv, R, rw, rr, dout = (_f32c(t) for t in (qkv, R, rw, rr, dout))
-    tail = _tr(_on_host, qkv, R, rw, rr, dout)
+    plm_mask = plm_mask.to(torch.uint8).contiguous() if plm_mask is not None else None
+    tail = _tr(_on_host, qkv, R, rw, rr, dout, plm_mask)
     d = dout.shape[1]
     dev = qkv.device
     dqkv = torch.empty_like(qkv)
@@ -784,7 +786,7 @@ def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, _on_host=False):
     drr = torch.empty((d,), dtype=torch.float32, device=dev)
     part = torch.empty((B * (2 * L + 2) * d,), dtype=torch.float32, device=dev)
     check(_lib.load().t4r_train_attn_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv), ptr(dR),
-                                         ptr(drw), ptr(drr), ptr(part), *tail), "t4r_train_attn_bwd")
+                                         ptr(drw), ptr(drr), ptr(part), ptr(plm_mask), *tail), "t4r_train_attn_bwd")
     return dqkv, dR, drw, drr
 
 
@@ -793,7 +795,7 @@ def causal_attn_bwd(qkv, dout, B, L, H, _on_host=False):
     tail = _tr(_on_host, qkv, dout)
     dqkv = torch.empty_like(qkv)
     check(_lib.load().t4r_train_attn_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv), None,
-                                         None, None, None, *tail), "t4r_train_attn_bwd")
+                                         None, None, None, None, *tail), "t4r_train_attn_bwd")
     return dqkv
 
 
@@ -808,6 +810,21 @@ def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H):
     out = torch.empty((2, B * L, d), dtype=torch.bfloat16, device=qkv.device)
     check(_lib.load().t4r_train_xlnet_attn_fwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), B, L, d, H, ptr(out), _stream()),
           "t4r_train_xlnet_attn_fwd")
+    return _planes_to_f32(out, d)
+
+
+def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask):
+    """Two-stream (PLM) attention forward: qkv fp32 [2 B L, 3d] (content stream rows, then query stream rows)."""
+    qkv, R, rw, rr = (_f32c(t) for t in (qkv, R, rw, rr))
+    pm = plm_mask.to(torch.uint8).contiguous()
+    _need_cuda(qkv, R, rw, rr, pm)
+    d = qkv.shape[1] // 3
+    if (3 * d) % 64 or d % 64:
+        raise _lib.T4RError("xlnet_attn_plm_fwd: d_model must be a multiple of 64 (plane rows are not padded)")
+    out = torch.empty((2, 2 * B * L, d), dtype=torch.bfloat16, device=qkv.device)
+    qkv_p, r_p = split_planes(qkv), split_planes(R)          # kept alive across the launch
+    check(_lib.load().t4r_train_xlnet_attn_plm_fwd(ptr(qkv_p), ptr(r_p), ptr(rw), ptr(rr), B, L, d, H, ptr(pm), ptr(out),
+                                                   _stream()), "t4r_train_xlnet_attn_plm_fwd")
     return _planes_to_f32(out, d)
 
 

@@ -24,8 +24,8 @@ masks / codes / tied weights) is verified on the CPU against torch autograd of t
 replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a one-thread-per-row/element call of
 a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
 nothing in the inference path uses this module.  Covered: full softmax (replicated or row-sharded table) and sampled
-softmax (replicated table), label smoothing (replicated full softmax).  Not covered: soft embeddings / element-wise
-aggregations, PLM.
+softmax (replicated table), label smoothing (replicated full softmax), MLM / CLM / PLM masking.  Not covered: soft
+embeddings / element-wise aggregations.
 """
 from __future__ import annotations
 
@@ -36,7 +36,7 @@ import torch
 
 from . import _lib, ops
 from .block import GPT2Encoder, XLNetEncoder
-from .masking import CausalLanguageModeling, MaskedLanguageModeling
+from .masking import CausalLanguageModeling, MaskedLanguageModeling, PermutationLanguageModeling
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -82,12 +82,16 @@ class _XLNetGraph:
         cfg = enc.config
         self.d, self.H, self.eps = cfg.d_model, cfg.n_head, float(cfg.layer_norm_eps)
 
-    def fwd(self, x: torch.Tensor, B: int, L: int) -> torch.Tensor:
+    def fwd(self, x: torch.Tensor, B: int, L: int, plm_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``plm_mask`` [B, L, L]: permutation language modeling -- the content stream (x) and the query stream (mask_emb
+        in every row) go through the layers stacked as [2 B L, d] rows; the query stream's rows are returned."""
         d, H = self.d, self.H
-        self.B, self.L = B, L
+        self.B, self.L, self.plm_mask = B, L, plm_mask
         self.tape = []
         R_all = ops.rel_pos_proj([lyr.rel_attn.r.detach().reshape(d, d).contiguous() for lyr in self.enc.layer], L, d)
         h = x
+        if plm_mask is not None:
+            h = torch.cat([x, self.enc.mask_emb.detach().reshape(1, d).float().expand(B * L, d)], dim=0).contiguous()
         for li, lyr in enumerate(self.enc.layer):
             ra, ff = lyr.rel_attn, lyr.ff
             t = {}
@@ -96,7 +100,8 @@ class _XLNetGraph:
             qkv = t["qkv_lin"].fwd(h)
             t["qkv"], t["R"] = qkv, R_all[li]
             t["rw"], t["rr"] = ra.r_w_bias.detach().reshape(-1).float(), ra.r_r_bias.detach().reshape(-1).float()
-            a = ops.xlnet_attn_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H)
+            a = (ops.xlnet_attn_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H) if plm_mask is None else
+                 ops.xlnet_attn_plm_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H, plm_mask))
             t["o_lin"] = _Linear(ra.o.detach().reshape(d, d))
             h1_pre = t["o_lin"].fwd(a, residual=h)
             t["h1_pre"] = h1_pre
@@ -110,10 +115,12 @@ class _XLNetGraph:
             t["y_pre"] = y_pre
             h = ops.layer_norm_fwd(y_pre, ff.layer_norm.weight.detach(), ff.layer_norm.bias.detach(), self.eps)
             self.tape.append(t)
-        return h
+        return h if plm_mask is None else h[B * L:]
 
     def bwd(self, dh: torch.Tensor) -> torch.Tensor:
         d, H, B, L = self.d, self.H, self.B, self.L
+        if self.plm_mask is not None:      # only the query stream's output was used
+            dh = torch.cat([torch.zeros_like(dh), dh], dim=0).contiguous()
         for li in reversed(range(len(self.enc.layer))):
             lyr, t = self.enc.layer[li], self.tape[li]
             ra, ff = lyr.rel_attn, lyr.ff
@@ -128,7 +135,7 @@ class _XLNetGraph:
             _acc(ra.layer_norm.weight, dg1); _acc(ra.layer_norm.bias, db1)
             da, dwo, _ = t["o_lin"].bwd(dh1_pre)
             _acc(ra.o, dwo)                                       # o: [d_model, H, dh] == Linear weight [d, HD]
-            dqkv, dR, drw, drr = ops.xlnet_attn_bwd(t["qkv"], t["R"], t["rw"], t["rr"], da, B, L, H)
+            dqkv, dR, drw, drr = ops.xlnet_attn_bwd(t["qkv"], t["R"], t["rw"], t["rr"], da, B, L, H, plm_mask=self.plm_mask)
             _acc(ra.r_w_bias, drw); _acc(ra.r_r_bias, drr)
             # R = pos @ Wr  (Wr = r.reshape(d, HD)):  dWr = pos^T dR
             pos = ops.rel_pos_table(L, d, dh.device)
@@ -136,6 +143,10 @@ class _XLNetGraph:
             dh, dwqkv, _ = t["qkv_lin"].bwd(dqkv, add_to_dx=dh1_pre)  # + the residual branch of the attention block
             for j, p in enumerate((ra.q, ra.k, ra.v)):            # rows [j d, (j+1) d) of the fused weight = W_j^T
                 _acc(p, dwqkv[j * d:(j + 1) * d].t().contiguous())
+        if self.plm_mask is not None:      # the query stream started from mask_emb in every row
+            M = B * L
+            _acc(self.enc.mask_emb, ops.col_sum(dh[M:].contiguous()))
+            dh = dh[:M].contiguous()
         return dh
 
 
@@ -220,8 +231,8 @@ class FusedTrainingStep:
             raise NotImplementedError("FusedTrainingStep: categorical / continuous features with concat aggregation")
         if inp._projection_linear() is None or inp.pre is not None:
             raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
-        if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling)):
-            raise NotImplementedError("FusedTrainingStep: MLM or CLM masking")
+        if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling, PermutationLanguageModeling)):
+            raise NotImplementedError("FusedTrainingStep: MLM, CLM or PLM masking")
         if not task.weight_tying:
             raise NotImplementedError("FusedTrainingStep: tied weights")
         task.output_weight()             # refreshes task.item_embedding_table (the table may have been sharded after build)
@@ -277,8 +288,11 @@ class FusedTrainingStep:
         self.proj_act = inp._projection_act()
         y = ops.act_fwd(self.proj_act, self.proj_pre) if self.proj_act != _lib.ACT_NONE else self.proj_pre
         x0 = ops.apply_row_codes(y, code, inp.masking.masked_item_embedding.detach().float())
-        # encoder
-        h = self.graph.fwd(x0, B, L)
+        # encoder (PLM: XLNet's two-stream forward under the permutation mask)
+        if isinstance(inp.masking, PermutationLanguageModeling):
+            h = self.graph.fwd(x0, B, L, plm_mask=inp.masking.perm_mask)
+        else:
+            h = self.graph.fwd(x0, B, L)
         # head: label rows, optional task_block, fused loss (keeps the per-row log-sum-exp)
         self.tgt_rows, self.labels, count = ops.compact_targets(inp.masking.masked_targets, task.padding_idx)
         T = int(count.item())                                  # the reference's masked_select synchronises too
