@@ -302,7 +302,9 @@ def main():
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     ap.add_argument("--train", action="store_true",
                     help="time a TRAINING step instead (forward + backward through transformers4rec_b200.training + one "
-                         "torch.optim.SGD step); not BASELINE.json's metric -- the line says so in `metric`")
+                         "optimizer step); not BASELINE.json's metric -- the line says so in `metric`")
+    ap.add_argument("--optimizer", choices=["sgd", "adamw"], default="sgd",
+                    help="with --train: torch.optim.SGD, or FusedAdamW (the t4r_train_adamw kernel)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -366,9 +368,10 @@ def main():
 
     train_step = opt = None
     if args.train:
-        from transformers4rec_b200.training import FusedTrainingStep, training_loss
+        from transformers4rec_b200.training import FusedAdamW, FusedTrainingStep, training_loss
         train_step = FusedTrainingStep(model)
-        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        opt = (FusedAdamW(model.parameters(), lr=1e-3) if args.optimizer == "adamw"
+               else torch.optim.SGD(model.parameters(), lr=1e-3))
 
     def step(batch):
         if train_step is not None:
@@ -481,7 +484,7 @@ def main():
                 "note": {3: "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction",
                          2: "fp16 + 2 x e4m3 cross terms: 2 bf16-equivalent tensor passes per MAC: frac <= 1/2",
                          1: "plain bf16 product"}[args.nprod]}
-    line = {"metric": METRIC if not args.train else "sessions/sec (fwd+bwd+SGD step; NOT the BASELINE metric)", "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
+    line = {"metric": METRIC if not args.train else "sessions/sec (fwd+bwd+%s step; NOT the BASELINE metric)" % args.optimizer, "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {3: "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)",
                                            2: "f32 (head: fp16 + e4m3 cross terms on tcgen05; rest bf16 hi/lo split)",

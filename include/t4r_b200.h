@@ -448,6 +448,9 @@ int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, 
 int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src, int col,
                              int width, int64_t skip_index, void* stream, int on_host);
 int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out /*[N]*/, void* stream, int on_host);
+/* one AdamW step (torch.optim.AdamW's rule, decoupled weight decay) on a flat fp32 tensor, in place on p / m / v */
+int t4r_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream, int on_host);
 int t4r_train_layer_norm_fwd(const float* x, const float* gamma, const float* beta, int64_t M, int d, float eps, float* y,
                              void* stream, int on_host);
 /* dx = LayerNorm backward of dy at x (+ add, optional); dgamma / dbeta [d] are overwritten (column sums of dy * xhat,

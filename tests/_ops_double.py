@@ -481,6 +481,15 @@ def sampled_ce_bwd(z, row_lse, labels, col_bias, col_ids, inv_tau, scale):
     return P
 
 
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    p.mul_(1.0 - lr * weight_decay)
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    p.addcdiv_(m, v.sqrt() / bc2 ** 0.5 + eps, value=-lr / bc1)
+    return p
+
+
 def index_add_rows(dst, idx, src, col, width, skip_index=None):
     idx = idx.long()
     keep = torch.ones_like(idx, dtype=torch.bool) if skip_index is None else idx != skip_index
@@ -494,7 +503,7 @@ TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_tab
                  causal_attn_bwd=causal_attn_bwd, layer_norm_fwd=layer_norm_fwd, layer_norm_bwd=layer_norm_bwd,
                  act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
                  apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,
-                 scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, sampled_ce_bwd=sampled_ce_bwd,
+                 scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, sampled_ce_bwd=sampled_ce_bwd, adamw_step=adamw_step,
                  index_add_rows=index_add_rows)
 
 

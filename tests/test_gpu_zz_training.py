@@ -138,3 +138,21 @@ def test_training_step_plm_on_gpu():
             continue
         err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
+def test_fused_adamw_on_gpu():
+    """The AdamW kernel on the device against torch.optim.AdamW (fp32, same hyper-parameters) over several steps."""
+    from transformers4rec_b200.training import FusedAdamW
+    g = torch.Generator().manual_seed(5)
+    shapes = [(1000, 64), (257,), (3, 5, 7)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.AdamW(pa, lr=1e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    ob = FusedAdamW(pb, lr=1e-2, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.05)
+    for _ in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).cuda()
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() < 1e-5

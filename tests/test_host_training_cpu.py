@@ -290,3 +290,43 @@ def test_training_step_permutation_language_modeling(monkeypatch):
         err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
     assert enc.mask_emb.grad is not None and enc.mask_emb.grad.abs().max().item() > 0
+
+
+def test_fused_adamw_follows_torch_adamw(monkeypatch):
+    """FusedAdamW (kernel's real per-element code on its host twin) against torch.optim.AdamW over several steps, with
+    weight decay, on parameters of different shapes; and through a short training run of the fused step."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedAdamW, FusedTrainingStep, training_loss
+    twin = ops.host_twin("adamw_step")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "adamw_step", twin)
+    g = torch.Generator().manual_seed(1)
+    shapes = [(7, 5), (13,), (3, 4, 2)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.AdamW(pa, lr=3e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    ob = FusedAdamW(pb, lr=3e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    for it in range(6):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() < 1e-6
+    assert ob.state[pb[0]]["step"] == 6 and set(ob.state[pb[0]]) == {"step", "exp_avg", "exp_avg_sq"}
+    # a short run of the whole step with it
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08)
+    batch = synth_batch(6, 8, CARDS, CONT, seed=9)
+    u, _ = mlm_draws(6, 8)
+    model.heads[0].body[0].masking.set_draws(u)
+    step = FusedTrainingStep(model, head_chunk=512)
+    opt = FusedAdamW(model.parameters(), lr=1e-2)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        l = training_loss(model, batch, step)
+        l.backward()
+        opt.step()
+        losses.append(l.item())
+    assert losses[-1] < losses[0]

@@ -96,6 +96,19 @@ T4R_HD void index_add_item(float* dst, const int64_t* idx, const float* src, int
   if (row == skip_index) return;
   T4R_ATOMIC_ADD(dst + row * width + c, src[r * ld_src + col + c]);
 }
+// AdamW (decoupled weight decay, torch.optim.AdamW's update rule), one element per item:
+//   p *= 1 - lr wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+T4R_HD void adamw_item(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
+                       float bc1, float bc2_sqrt, int64_t i) {
+  float pi = p[i] * (1.0f - lr * wd);
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
 // column sums over a slab of rows: one item = (column, slab)
 T4R_HD void col_sum_item(const float* x, int64_t M, int64_t N, int rows_per_slab, float* out, int64_t i) {
   const int64_t c = i % N, slab = i / N;
@@ -334,6 +347,14 @@ extern "C" int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_
                                         void* stream, int on_host) {
   T4R_REQUIRE(z && lse && labels && col_bias && col_ids && T > 0 && S > 0, "train_sampled_ce_bwd: bad arguments");
   T4R_ITEMS(T * S, "train_sampled_ce_bwd", sampled_ce_bwd_item(z, lse, labels, col_bias, col_ids, S, inv_tau, scale, i));
+}
+// One AdamW step on a flat fp32 tensor (step = 1, 2, ...: the bias corrections 1 - beta^step are formed here in double)
+extern "C" int t4r_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                               float eps, float weight_decay, int step, void* stream, int on_host) {
+  T4R_REQUIRE(p && g && m && v && n > 0 && step >= 1, "train_adamw: bad arguments");
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  T4R_ITEMS(n, "train_adamw", adamw_item(p, g, m, v, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, i));
 }
 extern "C" int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src,
                                         int col, int width, int64_t skip_index, void* stream, int on_host) {

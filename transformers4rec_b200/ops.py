@@ -742,6 +742,16 @@ def index_add_rows(dst, idx, src, col, width, skip_index=None, _on_host=False):
     return dst
 
 
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, _on_host=False):
+    """One AdamW update in place on ``p`` / ``m`` / ``v`` (flat fp32, contiguous)."""
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    tail = _tr(_on_host, p, g, m, v)
+    check(_lib.load().t4r_train_adamw(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                      float(eps), float(weight_decay), int(step), *tail), "t4r_train_adamw")
+    return p
+
+
 def col_sum(x, _on_host=False):
     x = _f32c(x)
     tail = _tr(_on_host, x)

@@ -16,4 +16,4 @@ from ..ranking_metric import (AvgPrecisionAt, DCGAt, MeanReciprocalRankAt, NDCGA
 from ..schema import ColumnSchema, Schema, Tags  # noqa: F401
 from ..padding import pad_batch, pad_inputs  # noqa: F401
 
-from ..training import FusedTrainingStep, training_loss  # noqa: F401,E402  (N3: backward of the fused path)
+from ..training import FusedAdamW, FusedTrainingStep, training_loss  # noqa: F401,E402  (N3: backward + optimizer step)

@@ -487,3 +487,37 @@ def training_loss(model, batch, step: Optional[FusedTrainingStep] = None) -> tor
     step = step or FusedTrainingStep(model)
     params = [p for p in model.parameters() if p.requires_grad]
     return _FusedLossFn.apply(step, batch, *params)
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW whose update runs in the t4r kernel (``t4r_train_adamw``: torch.optim.AdamW's rule, decoupled weight decay,
+    one element per thread, in place on the parameter and its two moment buffers).  Same constructor arguments and
+    state-dict layout (``step`` / ``exp_avg`` / ``exp_avg_sq``) as ``torch.optim.AdamW``."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                g = p.grad.float().contiguous()
+                data = p.data if p.data.is_contiguous() else p.data.contiguous()
+                ops.adamw_step(data.view(-1), g.view(-1), st["exp_avg"].view(-1), st["exp_avg_sq"].view(-1), group["lr"],
+                               b1, b2, group["eps"], group["weight_decay"], st["step"])
+                if data.data_ptr() != p.data.data_ptr():
+                    p.data.copy_(data)
+        return loss
