@@ -3,6 +3,7 @@ formula, transposition, residual branch, mask / code / tied-weight bookkeeping -
 graph, with the kernels replaced by the test doubles (tests/_ops_double.py: each primitive is a few lines of torch, the
 backward ones obtained from autograd of the forward one).  What runs on the GPU instead of the doubles is covered by the
 host twins (tests/test_abi_and_host.py) and the gated GPU tests."""
+import numpy as np
 import pytest
 import torch
 
@@ -330,3 +331,56 @@ def test_fused_adamw_follows_torch_adamw(monkeypatch):
         opt.step()
         losses.append(l.item())
     assert losses[-1] < losses[0]
+
+
+def test_model_fit_and_evaluate(monkeypatch, capsys):
+    """Model.fit / Model.evaluate (model/base.py:669-738; the reference's tests call them as
+    ``losses = model.fit(dataset, num_epochs=5); metrics = model.evaluate(dataset)``, test_model.py:228-229): fit's loss
+    curve equals a hand-written loop with torch.optim.Adam over the same fused step, evaluate returns the streaming
+    metrics of the evaluation forward."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep, training_loss
+    twin = ops.host_twin("adamw_step")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "adamw_step", twin)
+    dims = {"item_id/list": 32, "category/list": 32}
+
+    def fresh():
+        _, m = make_pair(CARDS, dims, "item_id/list", CONT, 32, 2, 1, 8, device="cpu", weight_scale=0.08)
+        u, _ = mlm_draws(6, 8)
+        m.heads[0].body[0].masking.set_draws(u)
+        return m
+    batches = [(synth_batch(6, 8, CARDS, CONT, seed=s), None) for s in (3, 4)]
+    model = fresh()
+    losses = model.fit(batches, num_epochs=5, verbose=False)
+    assert losses.shape == (5,) and np.isfinite(losses).all() and losses[-1] < losses[0]
+    # the same run by hand: Adam (the reference's default optimizer) on the fused step
+    other = fresh()
+    step = FusedTrainingStep(other, head_chunk=512)
+    opt = torch.optim.Adam(other.parameters())
+    want = []
+    for _ in range(5):
+        ep = []
+        for x, _y in batches:
+            loss = training_loss(other, x, step)
+            opt.zero_grad(); loss.backward(); opt.step()
+            ep.append(float(loss))
+        want.append(np.mean(ep))
+    assert np.allclose(losses, np.array(want), rtol=2e-5, atol=2e-6)
+    # an optimizer CLASS is instantiated on the model's parameters, as in the reference
+    third = fresh()
+    l3 = third.fit(batches, optimizer=torch.optim.Adam, num_epochs=5, verbose=False)
+    assert np.allclose(l3, losses, rtol=2e-5, atol=2e-6)
+    # evaluate: streaming metrics of the evaluation forward; verbose fit prints them per epoch
+    metrics = model.evaluate(batches, verbose=False)
+    assert metrics and all(torch.isfinite(torch.as_tensor(v)).all() for v in metrics.values())
+    assert any("recall_at" in k for k in metrics)
+    again = model.evaluate(batches, verbose=False)
+    assert metrics.keys() == again.keys() and all(torch.equal(torch.as_tensor(metrics[k]), torch.as_tensor(again[k]))
+                                                  for k in metrics)
+    model.fit(batches, eval_dataloader=batches, num_epochs=1, verbose=True)
+    assert "recall_at" in capsys.readouterr().out
+    # train=False: forward-only pass with train-mode metrics, no parameter moves
+    before = [p.detach().clone() for p in model.parameters()]
+    l0 = model.fit(batches, num_epochs=1, train=False, verbose=False)
+    assert np.isfinite(l0).all() and all(torch.equal(a, b) for a, b in zip(before, model.parameters()))

@@ -1,16 +1,32 @@
 """Head / Model: the call chain of model/base.py:371-407 (Head.forward) and
-:544-598 (Model.forward) for the next-item path.  fit/save/load, schemas and the
-HF Trainer integration are host orchestration outside the hot path (SURVEY §2
-row 12) and are not mirrored."""
+:544-598 (Model.forward) for the next-item path, plus the two callers SURVEY §8f N3 names on
+the model itself: ``Model.fit`` (model/base.py:669-717) and ``Model.evaluate``
+(:719-738).  save/load, schemas and the HF Trainer integration are host
+orchestration outside the hot path and are not mirrored."""
 from __future__ import annotations
 
+import inspect
+import logging
 from typing import Dict, List, Optional, Union
 
+import numpy as np
 import torch
 from torch import nn
 
 from .block import SequentialBlock
 from .prediction_task import PredictionTask
+
+LOG = logging.getLogger("transformers4rec_b200")
+
+
+def _batches(dataloader):
+    """The reference iterates ``dataloader.dataset`` when handed a torch DataLoader (model/base.py:680-683: Merlin's
+    loader is an IterableDataset that yields whole batches).  A DataLoader over a map-style dataset is iterated
+    itself, so that its collated batches arrive."""
+    if isinstance(dataloader, torch.utils.data.DataLoader) and isinstance(dataloader.dataset,
+                                                                         torch.utils.data.IterableDataset):
+        return dataloader.dataset
+    return dataloader
 
 
 class Head(nn.Module):
@@ -138,6 +154,77 @@ class Model(nn.Module):
             losses = torch.stack([o["loss"] * w for o, w in zip(outs, self.head_weights)])
             return {"loss": losses.mean() if self.head_reduction == "mean" else losses.sum(), "heads": outs}
         return outs
+
+    # ------------------------------------------------------------------ fit / evaluate (model/base.py:669-738)
+    def fit(self, dataloader, optimizer=None, eval_dataloader=None, num_epochs=1, amp=False, train=True, verbose=True,
+            compute_metric=True):
+        """model/base.py:669-717: ``num_epochs`` passes over ``dataloader`` (batches ``(x, y)``), one optimizer step
+        per batch; returns the mean loss of every epoch as a numpy array.
+
+        Training runs on the fused step (``enable_fused_training``: forward + backward on the t4r kernels); the
+        default optimizer is ``FusedAdamW`` with lr 1e-3 and no weight decay, i.e. the reference's ``torch.optim.Adam``
+        default computed by the t4r update kernel.  An optimizer class is instantiated on ``self.parameters()``
+        (as in the reference), an instance is used as is.  The fused head never materialises the [T, V] training
+        logits, so train-mode ranking metrics are accumulated only when the forward returns predictions
+        (``train=False``); use ``eval_dataloader`` / ``evaluate`` for metrics.  ``amp`` is accepted and ignored: the
+        path's GEMMs are fixed split-bf16 tensor-core products at fp32 accuracy, there is no autocast switch."""
+        if optimizer is None:
+            from .training import FusedAdamW
+            optimizer = FusedAdamW(self.parameters(), lr=1e-3, weight_decay=0.0)
+        elif inspect.isclass(optimizer):
+            optimizer = optimizer(self.parameters())
+        if amp:
+            LOG.warning("Model.fit: amp=True has no effect on the t4r path (fp32-grade tensor-core products)")
+        if train and getattr(self, "_fused_step", None) is None:
+            self.enable_fused_training()
+        self.train(mode=train)
+        epoch_losses = []
+        with torch.set_grad_enabled(mode=train):
+            for _ in range(num_epochs):
+                losses = []
+                it = iter(_batches(dataloader))
+                if verbose:
+                    from tqdm import tqdm
+                    it = tqdm(it)
+                for x, y in it:
+                    output = self(x, targets=y, training=True)
+                    losses.append(float(output["loss"].detach()))
+                    if compute_metric and not train:
+                        self._update_metrics(output)
+                    if train:
+                        optimizer.zero_grad()
+                        output["loss"].backward()
+                        optimizer.step()
+                if verbose:
+                    if compute_metric and not train:
+                        print(self.compute_metrics(mode="train"))
+                    if eval_dataloader:
+                        print(self.evaluate(eval_dataloader, verbose=False))
+                        self.train(mode=train)
+                epoch_losses.append(np.mean(losses))
+        return np.array(epoch_losses)
+
+    def evaluate(self, dataloader, targets=None, training=False, testing=True, verbose=True, mode="eval"):
+        """model/base.py:719-738: reset the metrics, run every batch ``(x, y)`` through the evaluation forward, update
+        the streaming metrics (from the label ranks the fused head produced -- no [T, V] logits are materialised) and
+        return ``compute_metrics``."""
+        it = iter(_batches(dataloader))
+        if verbose:
+            from tqdm import tqdm
+            it = tqdm(it)
+        self.reset_metrics()
+        with torch.no_grad():
+            for x, y in it:
+                output = self(x, targets=y, training=training, testing=testing)
+                self._update_metrics(output)
+        return self.compute_metrics(mode=mode)
+
+    def _update_metrics(self, output):
+        # the fused head hands back the label ranks with its outputs; without them (e.g. the reference's plain
+        # ``predictions`` / ``labels`` pair) the metrics take the materialised tensors, model/base.py:704-707
+        if getattr(output, "row_rank", None) is not None:
+            return self.calculate_metrics(output)
+        return self.calculate_metrics(output["predictions"], targets=output["labels"])
 
     def calculate_metrics(self, predictions, targets=None):
         out = {}
