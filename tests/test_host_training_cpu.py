@@ -364,7 +364,7 @@ def test_model_fit_and_evaluate(monkeypatch, capsys):
         for x, _y in batches:
             loss = training_loss(other, x, step)
             opt.zero_grad(); loss.backward(); opt.step()
-            ep.append(float(loss))
+            ep.append(float(loss.detach()))
         want.append(np.mean(ep))
     assert np.allclose(losses, np.array(want), rtol=2e-5, atol=2e-6)
     # an optimizer CLASS is instantiated on the model's parameters, as in the reference
