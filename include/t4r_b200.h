@@ -448,6 +448,14 @@ int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_t* labels, 
 int t4r_train_index_add_rows(float* dst, const int64_t* idx, const float* src, int64_t n, int64_t ld_src, int col,
                              int width, int64_t skip_index, void* stream, int on_host);
 int t4r_train_col_sum(const float* x, int64_t M, int64_t N, float* out /*[N]*/, void* stream, int on_host);
+/* soft embedding of one scalar per row (features/embedding.py:517-556): p[M, n] = softmax(x w + b), out[M, dim] = p table;
+ * backward per row: dlogit[M, n] and dlogit * x (d table = p^T dout, d w / d b = column sums: composed by the caller) */
+int t4r_train_soft_emb_fwd(const float* x, const float* w, const float* b, const float* table, int64_t M, int n, int dim,
+                           float* p, float* out, void* stream, int on_host);
+int t4r_train_soft_emb_bwd(const float* x, const float* table, const float* p, const float* dout, int64_t M, int n, int dim,
+                           float* dlogit, float* dlogit_x, void* stream, int on_host);
+/* out = a + b (op 0) or a * b (op 1), element-wise (aggregation.py:139-193 and its product rule) */
+int t4r_train_binary(int op, const float* a, const float* b, float* out, int64_t n, void* stream, int on_host);
 /* one AdamW step (torch.optim.AdamW's rule, decoupled weight decay) on a flat fp32 tensor, in place on p / m / v */
 int t4r_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream, int on_host);

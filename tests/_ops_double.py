@@ -481,6 +481,25 @@ def sampled_ce_bwd(z, row_lse, labels, col_bias, col_ids, inv_tau, scale):
     return P
 
 
+def soft_emb_fwd(x, w, b, table):
+    p = torch.softmax(x.reshape(-1, 1).float() * w.reshape(1, -1).float() + b.reshape(1, -1).float(), dim=-1)
+    return p @ table.float(), p
+
+
+def soft_emb_bwd(x, table, p, dout):
+    dp = dout @ table.float().t()
+    dl = p * (dp - (p * dp).sum(-1, keepdim=True))
+    return dl, dl * x.reshape(-1, 1)
+
+
+def ew_add(a, b):
+    return a + b
+
+
+def ew_mul(a, b):
+    return a * b
+
+
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
     p.mul_(1.0 - lr * weight_decay)
     m.mul_(beta1).add_(g, alpha=1.0 - beta1)
@@ -504,6 +523,7 @@ TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_tab
                  act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
                  apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,
                  scatter_rows=scatter_rows, softmax_ce_bwd=softmax_ce_bwd, sampled_ce_bwd=sampled_ce_bwd, adamw_step=adamw_step,
+                 soft_emb_fwd=soft_emb_fwd, soft_emb_bwd=soft_emb_bwd, ew_add=ew_add, ew_mul=ew_mul,
                  index_add_rows=index_add_rows)
 
 

@@ -174,3 +174,42 @@ def test_model_fit_and_evaluate_on_gpu():
     m2 = model.evaluate(batches, verbose=False)
     assert m1 and m1.keys() == m2.keys()
     assert all(torch.equal(torch.as_tensor(m1[k]), torch.as_tensor(m2[k])) for k in m1)
+
+
+def test_widened_input_block_training_on_gpu():
+    """Soft-embedding / element-wise kernels on the device vs their host twins, then the training step over the widened
+    input block (soft embeddings + per-feature LayerNorm, every aggregation) against autograd of the oracle graph."""
+    from test_host_training_cpu import _pairs_no_proj, _wide_batch, _wide_pair
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    g = torch.Generator().manual_seed(2)
+    M, n, dim = 500, 10, 64
+    x, w, b = torch.randn(M, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+    tab, dout = torch.randn(n, dim, generator=g), torch.randn(M, dim, generator=g)
+    H = ops.host_twin
+    out, p = ops.soft_emb_fwd(x.cuda(), w.cuda(), b.cuda(), tab.cuda())
+    out_h, p_h = H("soft_emb_fwd")(x, w, b, tab)
+    assert (out.cpu() - out_h).abs().max().item() < 1e-5 and (p.cpu() - p_h).abs().max().item() < 1e-6
+    dl, dlx = ops.soft_emb_bwd(x.cuda(), tab.cuda(), p, dout.cuda())
+    dl_h, dlx_h = H("soft_emb_bwd")(x, tab, p_h, dout)
+    assert (dl.cpu() - dl_h).abs().max().item() < 1e-4 and (dlx.cpu() - dlx_h).abs().max().item() < 1e-4
+    assert torch.equal(ops.ew_mul(out, dout.cuda()).cpu(), out.cpu() * dout)
+    for aggregation in ("concat", "element-wise-sum", "element-wise-sum-item-multi"):
+        oracle, model = _wide_pair(aggregation, True, None, 32)
+        model = model.cuda()
+        B, L = 6, 8
+        batch = _wide_batch(B, L)
+        u, draws = mlm_draws(B, L)
+        model.heads[0].body[0].masking.set_draws(u.cuda())
+        ref_loss = _oracle_grads(oracle, batch, draws)
+        step = FusedTrainingStep(model, head_chunk=128)
+        for prm in model.parameters():
+            prm.grad = None
+        loss = step.forward({k: v.cuda() for k, v in batch.items()})
+        step.backward()
+        assert abs(loss.item() - ref_loss) < 1e-3
+        for name, po, pm in list(oracle.pairs) + list(_pairs_no_proj(oracle, model)):
+            if po.grad is None and pm.grad is None:
+                continue
+            err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
+            assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (aggregation, name, err)

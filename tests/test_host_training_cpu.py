@@ -384,3 +384,212 @@ def test_model_fit_and_evaluate(monkeypatch, capsys):
     before = [p.detach().clone() for p in model.parameters()]
     l0 = model.fit(batches, num_epochs=1, train=False, verbose=False)
     assert np.isfinite(l0).all() and all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the widened input block in training (N3 x N4): soft embeddings, per-feature LayerNorm, continuous projection,
+# element-wise aggregations
+# ---------------------------------------------------------------------------------------------------------------
+class _WideOracle(O.OracleSessionModel):
+    """The oracle graph with the input block restated, with the oracle's functions, from clones of the product input
+    block's own parameters (embedding rows -> LayerNorm, soft embeddings -> LayerNorm, continuous projection MLP,
+    aggregation, projection, MLM mask)."""
+
+    def attach(self, inputs):
+        import torch.nn.functional as F  # noqa: F401
+        self.aggregation = inputs.aggregation or "concat"
+        self.extra = torch.nn.ParameterList()
+        self.pairs = []
+
+        def clone(p, label):
+            q = torch.nn.Parameter(p.detach().clone())
+            self.extra.append(q)
+            self.pairs.append((label, q, p))
+            return q
+        cm, cont = inputs.categorical_module, inputs.continuous_module
+        self.cat_ln = {}
+        if getattr(cm, "post", None) is not None:
+            for n, m in cm.post.feature_layer_norm.items():
+                self.cat_ln[n] = (clone(m.weight, f"cat_ln[{n}].weight"), clone(m.bias, f"cat_ln[{n}].bias"))
+        self.soft, self.mlp, self.plain_cont = {}, None, ()
+        if hasattr(cont, "embedding_tables"):
+            for n, m in cont.embedding_tables.items():
+                ln = cont.post.feature_layer_norm[n] if cont.post is not None and n in cont.post.feature_layer_norm else None
+                self.soft[n] = (clone(m.projection_layer.weight, f"soft[{n}].w"), clone(m.projection_layer.bias, f"soft[{n}].b"),
+                                clone(m.embedding_table.weight, f"soft[{n}].table"),
+                                (clone(ln.weight, f"soft_ln[{n}].weight"), clone(ln.bias, f"soft_ln[{n}].bias")) if ln else None)
+        elif hasattr(cont, "mlp"):
+            self.mlp = ([(clone(b[0].weight, f"mlp{i}.w"), clone(b[0].bias, f"mlp{i}.b")) for i, b in enumerate(cont.mlp)],
+                        list(cont.features))
+        elif cont is not None:
+            self.plain_cont = tuple(cont.features)
+        lin = inputs._projection_linear()
+        if lin is None:
+            self.proj = None
+        else:
+            self.proj = torch.nn.Linear(lin.in_features, lin.out_features)
+            with torch.no_grad():
+                self.proj.weight.copy_(lin.weight); self.proj.bias.copy_(lin.bias)
+            self.pairs += [("proj.weight", self.proj.weight, lin.weight), ("proj.bias", self.proj.bias, lin.bias)]
+        return self
+
+    def input_block(self, inputs, training, testing, draws=None):
+        import torch.nn.functional as F
+        feats = {}
+        for n in self.table_names:
+            x = F.embedding(inputs[n], self.tables[n.replace("/", "__")].weight, padding_idx=0)
+            feats[n] = O.tabular_layer_norm(x, *self.cat_ln[n]) if n in self.cat_ln else x
+        for n, (w, b, table, ln) in self.soft.items():
+            y = O.soft_embedding(inputs[n], w, b, table)
+            feats[n] = O.tabular_layer_norm(y, *ln) if ln is not None else y
+        if self.mlp is not None:
+            layers, names = self.mlp
+            c = torch.cat([inputs[n].unsqueeze(-1) for n in names], dim=-1)
+            for w, b in layers:
+                c = O.project_relu(c, w, b)
+            feats["continuous_projection"] = c
+        for n in self.plain_cont:
+            feats[n] = inputs[n].float().unsqueeze(-1)
+        x = O.aggregate(feats, self.aggregation, self.item_id)
+        if self.proj is not None:
+            x = O.project_relu(x, self.proj.weight, self.proj.bias)
+        d = draws or {}
+        mask, labels = O.mlm_compute_masked_targets(inputs[self.item_id], training, testing, u_bern=d.get("u_bern"),
+                                                    u_force=d.get("u_force"), u_unmask=d.get("u_unmask"))
+        return O.mlm_apply_mask_to_inputs(x, mask, self.masked_item_embedding, training, testing), mask, labels
+
+
+def _wide_pair(aggregation, soft, proj_cont, d_output, D=16, d_model=32, L=8):
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(31)
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 300, tags=[tr.Tags.ITEM_ID]),
+                        tr.ColumnSchema.create_categorical("category/list", 40),
+                        tr.ColumnSchema.create_categorical("user_country", 30, is_list=False),
+                        tr.ColumnSchema.create_continuous("price/list"),
+                        tr.ColumnSchema.create_continuous("rel_time/list")])
+    kw = dict(continuous_soft_embeddings=True, soft_embedding_dim_default=D) if soft else {}
+    if proj_cont:
+        kw["continuous_projection"] = proj_cont
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=L, aggregation=aggregation,
+                                                    embedding_dim_default=D, post="layer-norm", d_output=d_output,
+                                                    masking="mlm", **kw)
+    model = tr.XLNetConfig.build(d_model, 2, 1, L).to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
+    model = model.eval()
+    inputs, tblock = model.heads[0].body[0], model.heads[0].body[1]
+    with torch.no_grad():
+        for n, p in tblock.transformer.named_parameters():
+            if "layer_norm" not in n and (p.ndim >= 2 or "bias" in n):
+                p.normal_(0.0, 0.08)
+        inputs.masking.masked_item_embedding.normal_(0.0, 0.5)
+        posts = [m for m in (getattr(inputs.categorical_module, "post", None), getattr(inputs.continuous_module, "post", None)) if m]
+        for post in posts:           # non-trivial LayerNorm parameters
+            for mod in post.feature_layer_norm.values():
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0.0, 0.3)
+    cards = {"item_id/list": 301, "category/list": 41, "user_country": 31}
+    oracle = _WideOracle(cardinalities=cards, embedding_dims={k: D for k in cards}, item_id="item_id/list", continuous=(),
+                         d_model=d_model, n_head=2, n_layer=1, max_seq_len=L, arch="xlnet", masking="mlm",
+                         project=(d_model != D) or True).eval()
+    with torch.no_grad():
+        for name in oracle.table_names:
+            oracle.tables[name.replace("/", "__")].weight.copy_(inputs.categorical_module.embedding_tables[name].weight)
+        oracle.masked_item_embedding.copy_(inputs.masking.masked_item_embedding)
+        oracle.transformer.load_state_dict(tblock.transformer.state_dict(), strict=False)
+        task = model.heads[0].prediction_task_dict["next-item"]
+        if oracle.task_block is not None:
+            tl = task.task_block[0][0]
+            oracle.task_block.weight.copy_(tl.weight); oracle.task_block.bias.copy_(tl.bias)
+    oracle.attach(inputs)
+    return oracle, model
+
+
+def _wide_batch(B, L, seed=4):
+    batch = synth_batch(B, L, {"item_id/list": 301, "category/list": 41}, ("price/list", "rel_time/list"), seed=seed)
+    batch["user_country"] = torch.randint(1, 31, (B,), generator=torch.Generator().manual_seed(seed))
+    return batch
+
+
+@pytest.mark.parametrize("aggregation,soft,proj_cont,d_output", [
+    ("concat", True, None, 32),                           # the paper recipes: soft embeddings + layer-norm + MLP merge
+    ("element-wise-sum", True, None, 32),
+    ("element-wise-sum-item-multi", True, None, 32),
+    ("element-wise-sum", True, None, None),               # no projection: the aggregate enters the encoder directly
+    ("concat", False, [24, 16], 32),                      # continuous projection MLP as one feature
+    ("concat", False, None, 32),                          # plain scalars next to LayerNorm'd embeddings
+])
+def test_training_step_widened_input_block(monkeypatch, aggregation, soft, proj_cont, d_output):
+    """Gradients of every parameter of the widened input block (and everything above it) against torch autograd of the
+    oracle composition; the new element / row kernels run their real per-item code through the host twins."""
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    names = ("soft_emb_fwd", "soft_emb_bwd", "ew_add", "ew_mul", "gather_rows", "layer_norm_fwd", "layer_norm_bwd",
+             "index_add_rows", "col_sum", "act_fwd", "act_bwd", "transpose")
+    twins = {name: ops.host_twin(name) for name in names}
+    D.install(monkeypatch)
+    for name in names:
+        monkeypatch.setattr(ops, name, twins[name])
+    d_model = 32 if d_output else 16
+    oracle, model = _wide_pair(aggregation, soft, proj_cont, d_output, D=16, d_model=d_model)
+    B, L = 6, 8
+    batch = _wide_batch(B, L)
+    u, draws = mlm_draws(B, L)
+    inputs = model.heads[0].body[0]
+    inputs.masking.set_draws(u)
+    # forward agreement of the two product paths first: training composition vs the one-kernel inference input block
+    ref_loss = _oracle_grads(oracle, batch, draws)
+    step = FusedTrainingStep(model, head_chunk=128)
+    assert step.wide is not None
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref_loss) < 1e-4
+    with torch.no_grad():
+        assert abs(model(batch, training=True)["loss"].item() - loss.item()) < 1e-4
+    pairs = list(oracle.pairs) + [(n, a, b) for n, a, b in _pairs_no_proj(oracle, model)]
+    seen = 0
+    for name, po, pm in pairs:
+        if po.grad is None and pm.grad is None:
+            continue
+        assert po.grad is not None and pm.grad is not None, name
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+        seen += 1
+    assert seen >= 10 + 2 * (3 if soft else 0)
+
+
+def _pairs_no_proj(oracle, model):
+    head = model.heads[0]
+    inputs, tblock = head.body[0], head.body[1]
+    yield "masked_item_embedding", oracle.masked_item_embedding, inputs.masking.masked_item_embedding
+    for name in oracle.table_names:
+        yield f"table[{name}]", oracle.tables[name.replace("/", "__")].weight, inputs.categorical_module.embedding_tables[name].weight
+    od, md = dict(oracle.transformer.named_parameters()), dict(tblock.transformer.named_parameters())
+    for k, v in md.items():
+        if k in od and k not in ("word_embedding.weight", "mask_emb", "wte.weight"):
+            yield "transformer." + k, od[k], v
+    if oracle.task_block is not None:
+        tl = head.prediction_task_dict["next-item"].task_block[0][0]
+        yield "task_block.weight", oracle.task_block.weight, tl.weight
+        yield "task_block.bias", oracle.task_block.bias, tl.bias
+
+
+def test_soft_embedding_and_binary_twins_vs_torch():
+    """Real per-item code of the soft-embedding forward / backward and the element-wise kernels against torch autograd
+    of the oracle's soft_embedding (features/embedding.py:517-556)."""
+    from transformers4rec_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, n, dim = 37, 10, 16
+    x, w, b = torch.randn(M, generator=g), torch.randn(n, 1, generator=g), torch.randn(n, generator=g)
+    tab = torch.randn(n, dim, generator=g)
+    leaves = [t.clone().requires_grad_() for t in (w, b, tab)]
+    ref = O.soft_embedding(x, *leaves)
+    dout = torch.randn(M, dim, generator=g)
+    ref.backward(dout)
+    H = ops.host_twin
+    out, p = H("soft_emb_fwd")(x, w, b, tab)
+    assert (out - ref.detach()).abs().max().item() < 1e-5 and (p.sum(1) - 1).abs().max().item() < 1e-5
+    dl, dlx = H("soft_emb_bwd")(x, tab, p, dout)
+    assert (dlx.sum(0) - leaves[0].grad.reshape(-1)).abs().max().item() < 1e-4
+    assert (dl.sum(0) - leaves[1].grad).abs().max().item() < 1e-4
+    assert (p.t() @ dout - leaves[2].grad).abs().max().item() < 1e-4
+    assert torch.equal(H("ew_add")(out, dout), out + dout) and torch.equal(H("ew_mul")(out, dout), out * dout)

@@ -179,6 +179,9 @@ SIGNATURES = {
     "t4r_train_softmax_ce_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, c_int64, _P, c_int]),
     "t4r_train_sampled_ce_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float, _P, c_int]),
     "t4r_train_index_add_rows": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, c_int64, _P, c_int]),
+    "t4r_train_soft_emb_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_int]),
+    "t4r_train_soft_emb_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_int]),
+    "t4r_train_binary": (c_int, [c_int, _P, _P, _P, c_int64, _P, c_int]),
     "t4r_train_adamw": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, _P, c_int]),
     "t4r_train_col_sum": (c_int, [_P, c_int64, c_int64, _P, _P, c_int]),
     "t4r_train_layer_norm_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, c_int]),

@@ -96,6 +96,51 @@ T4R_HD void index_add_item(float* dst, const int64_t* idx, const float* src, int
   if (row == skip_index) return;
   T4R_ATOMIC_ADD(dst + row * width + c, src[r * ld_src + col + c]);
 }
+// soft embedding (features/embedding.py:517-556): p = softmax(x w + b) over the n rows of the table, out = p^T table;
+// p is kept for the backward.  One scalar per item.
+T4R_HD void soft_emb_fwd_row(const float* x, const float* w, const float* b, const float* table, int n, int dim, float* p,
+                             float* out, int64_t r) {
+  const float xv = x[r];
+  float* pr = p + r * n;
+  float mx = -INFINITY;
+  for (int j = 0; j < n; ++j) mx = fmaxf(mx, xv * w[j] + b[j]);
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float e = expf(xv * w[j] + b[j] - mx);
+    pr[j] = e;
+    s += e;
+  }
+  const float inv = 1.0f / s;
+  for (int j = 0; j < n; ++j) pr[j] *= inv;
+  for (int c = 0; c < dim; ++c) {
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc += pr[j] * table[static_cast<int64_t>(j) * dim + c];
+    out[r * dim + c] = acc;
+  }
+}
+// its backward per scalar: dp_j = <dout_r, table_j>, dlogit_j = p_j (dp_j - sum_k p_k dp_k); dlogit x for the slope's
+// gradient.  (d table = p^T dout, d w = column sums of dlogit x, d b = column sums of dlogit: composed by the caller.)
+T4R_HD void soft_emb_bwd_row(const float* x, const float* table, const float* p, const float* dout, int n, int dim,
+                             float* dlogit, float* dlogit_x, int64_t r) {
+  const float* pr = p + r * n;
+  const float* dr = dout + r * dim;
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) {
+    float dp = 0.f;
+    for (int c = 0; c < dim; ++c) dp += dr[c] * table[static_cast<int64_t>(j) * dim + c];
+    dlogit[r * n + j] = dp;
+    s += pr[j] * dp;
+  }
+  for (int j = 0; j < n; ++j) {
+    const float g = pr[j] * (dlogit[r * n + j] - s);
+    dlogit[r * n + j] = g;
+    dlogit_x[r * n + j] = g * x[r];
+  }
+}
+// element-wise a + b (op 0) or a * b (op 1): the element-wise aggregations and their product rule
+T4R_HD void binary_item(int op, const float* a, const float* b, float* out, int64_t i) {
+  out[i] = op == 0 ? a[i] + b[i] : a[i] * b[i];
+}
 // AdamW (decoupled weight decay, torch.optim.AdamW's update rule), one element per item:
 //   p *= 1 - lr wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
 T4R_HD void adamw_item(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd,
@@ -347,6 +392,20 @@ extern "C" int t4r_train_sampled_ce_bwd(float* z, const float* lse, const int64_
                                         void* stream, int on_host) {
   T4R_REQUIRE(z && lse && labels && col_bias && col_ids && T > 0 && S > 0, "train_sampled_ce_bwd: bad arguments");
   T4R_ITEMS(T * S, "train_sampled_ce_bwd", sampled_ce_bwd_item(z, lse, labels, col_bias, col_ids, S, inv_tau, scale, i));
+}
+extern "C" int t4r_train_soft_emb_fwd(const float* x, const float* w, const float* b, const float* table, int64_t M, int n,
+                                      int dim, float* p, float* out, void* stream, int on_host) {
+  T4R_REQUIRE(x && w && b && table && p && out && M > 0 && n > 0 && dim > 0, "train_soft_emb_fwd: bad arguments");
+  T4R_ITEMS(M, "train_soft_emb_fwd", soft_emb_fwd_row(x, w, b, table, n, dim, p, out, i));
+}
+extern "C" int t4r_train_soft_emb_bwd(const float* x, const float* table, const float* p, const float* dout, int64_t M, int n,
+                                      int dim, float* dlogit, float* dlogit_x, void* stream, int on_host) {
+  T4R_REQUIRE(x && table && p && dout && dlogit && dlogit_x && M > 0 && n > 0 && dim > 0, "train_soft_emb_bwd: bad arguments");
+  T4R_ITEMS(M, "train_soft_emb_bwd", soft_emb_bwd_row(x, table, p, dout, n, dim, dlogit, dlogit_x, i));
+}
+extern "C" int t4r_train_binary(int op, const float* a, const float* b, float* out, int64_t n, void* stream, int on_host) {
+  T4R_REQUIRE(a && b && out && n > 0 && (op == 0 || op == 1), "train_binary: bad arguments");
+  T4R_ITEMS(n, "train_binary", binary_item(op, a, b, out, i));
 }
 // One AdamW step on a flat fp32 tensor (step = 1, 2, ...: the bias corrections 1 - beta^step are formed here in double)
 extern "C" int t4r_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -742,6 +742,47 @@ def index_add_rows(dst, idx, src, col, width, skip_index=None, _on_host=False):
     return dst
 
 
+def soft_emb_fwd(x, w, b, table, _on_host=False):
+    """x [M] scalars, w / b [n] (``Linear(1, n)``), table [n, dim] -> (out [M, dim], p [M, n] softmax weights)."""
+    x, w, b, table = _f32c(x.reshape(-1)), _f32c(w.reshape(-1)), _f32c(b.reshape(-1)), _f32c(table)
+    tail = _tr(_on_host, x, w, b, table)
+    M, (n, dim) = x.numel(), table.shape
+    p = torch.empty((M, n), dtype=torch.float32, device=x.device)
+    out = torch.empty((M, dim), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_soft_emb_fwd(ptr(x), ptr(w), ptr(b), ptr(table), M, n, dim, ptr(p), ptr(out), *tail),
+          "t4r_train_soft_emb_fwd")
+    return out, p
+
+
+def soft_emb_bwd(x, table, p, dout, _on_host=False):
+    """-> (dlogit [M, n], dlogit * x [M, n])"""
+    x, table, p, dout = _f32c(x.reshape(-1)), _f32c(table), _f32c(p), _f32c(dout)
+    tail = _tr(_on_host, x, table, p, dout)
+    M, (n, dim) = x.numel(), table.shape
+    dl = torch.empty((M, n), dtype=torch.float32, device=x.device)
+    dlx = torch.empty((M, n), dtype=torch.float32, device=x.device)
+    check(_lib.load().t4r_train_soft_emb_bwd(ptr(x), ptr(table), ptr(p), ptr(dout), M, n, dim, ptr(dl), ptr(dlx), *tail),
+          "t4r_train_soft_emb_bwd")
+    return dl, dlx
+
+
+def _binary(op, a, b, _on_host):
+    a, b = _f32c(a), _f32c(b)
+    assert a.shape == b.shape
+    tail = _tr(_on_host, a, b)
+    out = torch.empty_like(a)
+    check(_lib.load().t4r_train_binary(op, ptr(a), ptr(b), ptr(out), a.numel(), *tail), "t4r_train_binary")
+    return out
+
+
+def ew_add(a, b, _on_host=False):
+    return _binary(0, a, b, _on_host)
+
+
+def ew_mul(a, b, _on_host=False):
+    return _binary(1, a, b, _on_host)
+
+
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, _on_host=False):
     """One AdamW update in place on ``p`` / ``m`` / ``v`` (flat fp32, contiguous)."""
     for t in (p, g, m, v):

@@ -24,8 +24,9 @@ masks / codes / tied weights) is verified on the CPU against torch autograd of t
 replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a one-thread-per-row/element call of
 a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
 nothing in the inference path uses this module.  Covered: full softmax (replicated or row-sharded table) and sampled
-softmax (replicated table), label smoothing (replicated full softmax), MLM / CLM / PLM masking.  Not covered: soft
-embeddings / element-wise aggregations.
+softmax (replicated table), label smoothing (replicated full softmax), MLM / CLM / PLM masking, the widened input block
+(per-feature LayerNorm, soft embeddings, continuous projection, element-wise aggregations; replicated tables).  Not
+covered: StochasticSwapNoise, dropout.
 """
 from __future__ import annotations
 
@@ -216,6 +217,150 @@ def _acc_rows(param, rows, n):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# the widened input block (SURVEY §8f N4 in training): per-feature LayerNorm, soft embeddings, continuous
+# projection, element-wise aggregations
+# --------------------------------------------------------------------------------------------------------------
+class _MLPGraph:
+    """A built MLPBlock (block/mlp.py:30-87): DenseBlocks of Linear (+ ReLU / GELU)."""
+
+    def __init__(self, built):
+        self.blocks = list(built)
+
+    def fwd(self, x):
+        self.tape = []
+        for blk in self.blocks:
+            lin = _Linear(blk[0].weight, blk[0].bias)
+            pre = lin.fwd(x)
+            act = blk.act_code()
+            x = ops.act_fwd(act, pre) if act != _lib.ACT_NONE else pre
+            self.tape.append((blk[0], lin, pre, act))
+        return x
+
+    def bwd(self, dy):
+        for mod, lin, pre, act in reversed(self.tape):
+            dpre = ops.act_bwd(act, pre, dy) if act != _lib.ACT_NONE else dy
+            dy, dw, db = lin.bwd(dpre)
+            _acc(mod.weight, dw)
+            if mod.bias is not None:
+                _acc(mod.bias, db)
+        return dy
+
+
+class _WideInput:
+    """Training forward / backward of the input block beyond ``embedding rows + scalars -> concat``: every feature is
+    produced as its own fp32 [M, width] matrix (embedding rows: features/embedding.py:226-249; soft embeddings:
+    :517-556; the continuous projection MLP: features/tabular.py:88-118), optionally LayerNorm'd
+    (tabular/transformations.py:95-141), then aggregated in sorted-name order (tabular/aggregation.py:35-47 concat,
+    :139-157 element-wise-sum, :160-193 element-wise-sum-item-multi = item * sum of the others).  The inference
+    path does all of this in one kernel (t4r_input_block_fwd); here each piece keeps what its backward needs."""
+
+    def __init__(self, inp, layout, C):
+        from .features import ContinuousProjection
+        self.inp, self.layout, self.C = inp, layout, C
+        self.agg = inp.AGGREGATIONS[inp.aggregation or "concat"]
+        cm, cont = inp.categorical_module, inp.continuous_module
+        if any(kind == "cat" and cm.is_sharded(n) for n, kind, *_ in layout):
+            raise NotImplementedError("FusedTrainingStep: a row-sharded table with the widened input block")
+        self.cat_ln = getattr(cm, "post", None) if cm is not None else None
+        self.cont_ln = getattr(cont, "post", None) if cont is not None else None
+        self.mlp = _MLPGraph(cont.mlp) if isinstance(cont, ContinuousProjection) else None
+        if self.agg == _lib.AGG_SUM_ITEM_MULTI and not any(n == cm.item_id for n, *_ in layout):
+            raise ValueError("element-wise-sum-item-multi needs the item-id feature")
+
+    def _ln(self, post, name):
+        if post is None or name not in post.feature_layer_norm:
+            return None
+        return post.feature_layer_norm[name]
+
+    def fwd(self, batch, B, L):
+        inp = self.inp
+        cm, cont = inp.categorical_module, inp.continuous_module
+        M = B * L
+
+        def seq(v):   # context features [B] / [B, 1] repeat over the positions (tabular/base.py:53-63)
+            if v.dim() == 1 or (v.dim() == 2 and v.shape[1] == 1 and L != 1):
+                v = v.reshape(B, 1).expand(B, L)
+            return v.reshape(-1)
+        self.nodes = []
+        for name, kind, col, width in self.layout:
+            node = {"name": name, "kind": kind, "col": col, "width": width, "ln": None}
+            if kind == "cat":
+                table = cm.embedding_tables[name].weight
+                node["ids"], node["table"] = seq(batch[name]).contiguous(), table
+                y = ops.gather_rows(table.detach().float(), node["ids"])
+                node["ln"] = self._ln(self.cat_ln, name)
+            elif kind == "cont":
+                y = seq(batch[name]).float().reshape(M, 1).contiguous()
+            elif kind == "soft":
+                mod = cont.embedding_tables[name]
+                node["x"], node["mod"] = seq(batch[name]).float().contiguous(), mod
+                y, node["p"] = ops.soft_emb_fwd(node["x"], mod.projection_layer.weight.detach(),
+                                                mod.projection_layer.bias.detach(), mod.embedding_table.weight.detach())
+                node["ln"] = self._ln(self.cont_ln, name)
+            else:             # "dense": the continuous projection
+                vals = [(seq(batch[n]), i) for i, n in enumerate(cont.features)]
+                x, _, _ = ops.embed_concat([], vals, M, len(vals), want_f32=True, want_planes=False)
+                y = self.mlp.fwd(x)
+            if node["ln"] is not None:
+                node["pre_ln"] = y
+                ln = node["ln"]
+                y = ops.layer_norm_fwd(y, ln.weight.detach(), ln.bias.detach(), float(ln.eps))
+            node["y"] = y
+            self.nodes.append(node)
+        if self.agg == _lib.AGG_CONCAT:
+            out = torch.empty((M, self.C), dtype=torch.float32, device=self.nodes[0]["y"].device)
+            for nd in self.nodes:      # column placement of whole feature matrices: plumbing
+                out[:, nd["col"]:nd["col"] + nd["width"]] = nd["y"]
+            return out
+        item = cm.item_id if self.agg == _lib.AGG_SUM_ITEM_MULTI else None
+        acc = None
+        for nd in self.nodes:
+            if nd["name"] == item:
+                continue
+            acc = nd["y"] if acc is None else ops.ew_add(acc, nd["y"])
+        if item is None:
+            return acc
+        self.item_y = next(nd["y"] for nd in self.nodes if nd["name"] == item)
+        self.others = acc
+        return ops.ew_mul(self.item_y, acc)
+
+    def bwd(self, dagg):
+        inp = self.inp
+        cm = inp.categorical_module
+        item = cm.item_id if self.agg == _lib.AGG_SUM_ITEM_MULTI else None
+        if item is not None:
+            d_item, d_others = ops.ew_mul(dagg, self.others), ops.ew_mul(dagg, self.item_y)
+        for nd in self.nodes:
+            kind = nd["kind"]
+            if kind == "cont":
+                continue
+            if self.agg == _lib.AGG_CONCAT:
+                dy = dagg[:, nd["col"]:nd["col"] + nd["width"]].contiguous()
+            elif item is None:
+                dy = dagg
+            else:
+                dy = d_item if nd["name"] == item else d_others
+            if nd["ln"] is not None:
+                ln = nd["ln"]
+                dy, dg, db = ops.layer_norm_bwd(nd["pre_ln"], ln.weight.detach(), float(ln.eps), dy)
+                _acc(ln.weight, dg); _acc(ln.bias, db)
+            if kind == "cat":
+                param = nd["table"]
+                g = torch.zeros_like(param.detach(), dtype=torch.float32) if param.grad is None else param.grad
+                ops.index_add_rows(g, nd["ids"], dy, 0, nd["width"], skip_index=inp.masking.padding_idx)
+                param.grad = g
+            elif kind == "soft":
+                mod = nd["mod"]
+                table = mod.embedding_table.weight
+                dl, dlx = ops.soft_emb_bwd(nd["x"], table.detach(), nd["p"], dy)
+                _acc(table, gemm_nt(ops.transpose(nd["p"]), ops.transpose(dy)))          # p^T dOut  [n, dim]
+                _acc(mod.projection_layer.weight, ops.col_sum(dlx))
+                _acc(mod.projection_layer.bias, ops.col_sum(dl))
+            else:
+                self.mlp.bwd(dy)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # the whole step
 # --------------------------------------------------------------------------------------------------------------
 class FusedTrainingStep:
@@ -227,9 +372,12 @@ class FusedTrainingStep:
         self.task = next(iter(head.prediction_task_dict.values()))
         inp, task = self.inputs, self.task
         layout, self.C = inp._layout()
-        if (inp.aggregation or "concat") != "concat" or any(kind not in ("cat", "cont") for _, kind, *_ in layout):
-            raise NotImplementedError("FusedTrainingStep: categorical / continuous features with concat aggregation")
-        if inp._projection_linear() is None or inp.pre is not None:
+        cat_post = getattr(inp.categorical_module, "post", None)
+        plain = ((inp.aggregation or "concat") == "concat" and all(kind in ("cat", "cont") for _, kind, *_ in layout)
+                 and not (cat_post is not None and len(cat_post.feature_layer_norm) > 0))
+        self.wide = None if plain else _WideInput(inp, layout, self.C)
+        if inp.pre is not None or (inp.projection_module is not None and inp._projection_linear() is None) or (
+                plain and inp._projection_linear() is None):
             raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
         if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling, PermutationLanguageModeling)):
             raise NotImplementedError("FusedTrainingStep: MLM, CLM or PLM masking")
@@ -256,7 +404,7 @@ class FusedTrainingStep:
         self.code = code
         # K1 gather + concat (fp32 rows; the gather is recomputed in the backward instead of being kept)
         cats, conts = [], []
-        for name, kind, col, width in self.layout:
+        for name, kind, col, width in (self.layout if self.wide is None else ()):
             v = batch[name].reshape(-1)
             if kind == "cat":
                 cats.append((cm.embedding_tables[name].weight.detach(), v, col))
@@ -264,7 +412,9 @@ class FusedTrainingStep:
                 conts.append((v, col))
         self.cats, self.conts = cats, conts
         self.item_plan = None
-        if self.sharded:
+        if self.wide is not None:
+            concat = self.wide.fwd(batch, B, L)
+        elif self.sharded:
             # the item rows come through the table's exchange (all-gather of ids + one all-to-all); the other features
             # are gathered locally into the same [M, C] buffer
             table = cm.embedding_tables[cm.item_id]
@@ -283,10 +433,13 @@ class FusedTrainingStep:
             concat, _, _ = ops.embed_concat(cats, conts, M, self.C, want_f32=True, want_planes=False)
         # K2 projection + activation, then the mask replace (apply_mask_to_inputs)
         lin = inp._projection_linear()
-        self.proj = _Linear(lin.weight, lin.bias)
-        self.proj_pre = self.proj.fwd(concat)
-        self.proj_act = inp._projection_act()
-        y = ops.act_fwd(self.proj_act, self.proj_pre) if self.proj_act != _lib.ACT_NONE else self.proj_pre
+        if lin is None:          # element-wise aggregation straight into the encoder (widened block only)
+            self.proj, y = None, concat
+        else:
+            self.proj = _Linear(lin.weight, lin.bias)
+            self.proj_pre = self.proj.fwd(concat)
+            self.proj_act = inp._projection_act()
+            y = ops.act_fwd(self.proj_act, self.proj_pre) if self.proj_act != _lib.ACT_NONE else self.proj_pre
         x0 = ops.apply_row_codes(y, code, inp.masking.masked_item_embedding.detach().float())
         # encoder (PLM: XLNet's two-stream forward under the permutation mask)
         if isinstance(inp.masking, PermutationLanguageModeling):
@@ -445,12 +598,18 @@ class FusedTrainingStep:
         # mask replace: rows with code 1 took masked_item_embedding, code 2 are constant zero
         dmask, dy = ops.row_codes_bwd(dx0, self.code)
         _acc(inp.masking.masked_item_embedding, dmask)
-        dpre = ops.act_bwd(self.proj_act, self.proj_pre, dy) if self.proj_act != _lib.ACT_NONE else dy
-        dconcat, dwp, dbp = self.proj.bwd(dpre)
-        lin = inp._projection_linear()
-        _acc(lin.weight, dwp)
-        if lin.bias is not None:
-            _acc(lin.bias, dbp)
+        if self.proj is None:
+            dconcat = dy
+        else:
+            dpre = ops.act_bwd(self.proj_act, self.proj_pre, dy) if self.proj_act != _lib.ACT_NONE else dy
+            dconcat, dwp, dbp = self.proj.bwd(dpre)
+            lin = inp._projection_linear()
+            _acc(lin.weight, dwp)
+            if lin.bias is not None:
+                _acc(lin.bias, dbp)
+        if self.wide is not None:
+            self.wide.bwd(dconcat)
+            return dconcat
         # embedding rows: scatter-add the column slice of every categorical feature (padding row gets no gradient)
         for table, ids, col in self.cats:
             param = next(p for p in cm.parameters() if p.data_ptr() == table.data_ptr())
