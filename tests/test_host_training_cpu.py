@@ -593,3 +593,44 @@ def test_soft_embedding_and_binary_twins_vs_torch():
     assert (dl.sum(0) - leaves[1].grad).abs().max().item() < 1e-4
     assert (p.t() @ dout - leaves[2].grad).abs().max().item() < 1e-4
     assert torch.equal(H("ew_add")(out, dout), out + dout) and torch.equal(H("ew_mul")(out, dout), out * dout)
+
+
+def test_training_step_with_stochastic_swap_noise(monkeypatch):
+    """StochasticSwapNoise as the input block's ``pre`` (tabular/transformations.py:29-92; the recipes'
+    --stochastic_shared_embeddings_replacement_prob): the step trains on the noised inputs -- loss and gradients equal
+    autograd of the oracle graph fed with the oracle's own noised batch (same draws)."""
+    import transformers4rec_b200.torch as tr
+    from transformers4rec_b200.training import FusedTrainingStep
+    D.install(monkeypatch)
+    oracle, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                              device="cpu", weight_scale=0.08)
+    oracle.train(False)
+    inputs = model.heads[0].body[0]
+    ssn = tr.StochasticSwapNoise(schema=inputs.schema, pad_token=0, replacement_prob=0.3)
+    inputs.pre = ssn
+    model.train()
+    B, L = 6, 8
+    batch = synth_batch(B, L, CARDS, CONT, seed=11)
+    mask = batch["item_id/list"] != 0
+    g = torch.Generator().manual_seed(1)
+    draws_ssn, noisy = {}, {}
+    for k, v in batch.items():
+        u, perm = torch.rand(v.shape, generator=g), torch.randperm(int(mask.sum()), generator=g)
+        draws_ssn[k] = (u, perm)
+        noisy[k] = O.stochastic_swap_noise(v, mask, u, perm, 0.3)
+    assert any(not torch.equal(noisy[k], batch[k]) for k in batch)
+    ssn.set_draws(draws_ssn)
+    u, draws = mlm_draws(B, L)
+    inputs.masking.set_draws(u)
+    ref_loss = _oracle_grads(oracle, noisy, draws)
+    step = FusedTrainingStep(model, head_chunk=512)
+    for p in model.parameters():
+        p.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref_loss) < 1e-4
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)

@@ -25,8 +25,8 @@ replaced by test doubles (tests/test_host_training_cpu.py); each new kernel is a
 a ``__host__ __device__`` function whose host twin is checked against torch on the CPU.  Not yet run on hardware;
 nothing in the inference path uses this module.  Covered: full softmax (replicated or row-sharded table) and sampled
 softmax (replicated table), label smoothing (replicated full softmax), MLM / CLM / PLM masking, the widened input block
-(per-feature LayerNorm, soft embeddings, continuous projection, element-wise aggregations; replicated tables).  Not
-covered: StochasticSwapNoise, dropout.
+(per-feature LayerNorm, soft embeddings, continuous projection, element-wise aggregations; replicated tables),
+StochasticSwapNoise as the input block's pre-transform.  Not covered: dropout.
 """
 from __future__ import annotations
 
@@ -376,9 +376,11 @@ class FusedTrainingStep:
         plain = ((inp.aggregation or "concat") == "concat" and all(kind in ("cat", "cont") for _, kind, *_ in layout)
                  and not (cat_post is not None and len(cat_post.feature_layer_norm) > 0))
         self.wide = None if plain else _WideInput(inp, layout, self.C)
-        if inp.pre is not None or (inp.projection_module is not None and inp._projection_linear() is None) or (
+        from .features import StochasticSwapNoise
+        if (inp.pre is not None and not isinstance(inp.pre, StochasticSwapNoise)) or (inp.projection_module is not None and inp._projection_linear() is None) or (
                 plain and inp._projection_linear() is None):
-            raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection, no pre-transform")
+            raise NotImplementedError("FusedTrainingStep: the default Linear (+ReLU) projection; StochasticSwapNoise as "
+                                      "the only pre-transform")
         if not isinstance(inp.masking, (MaskedLanguageModeling, CausalLanguageModeling, PermutationLanguageModeling)):
             raise NotImplementedError("FusedTrainingStep: MLM, CLM or PLM masking")
         if not task.weight_tying:
@@ -394,6 +396,8 @@ class FusedTrainingStep:
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         inp, task = self.inputs, self.task
         cm = inp.categorical_module
+        if inp.pre is not None:    # StochasticSwapNoise (tabular/transformations.py:29-92): a permutation of the RAW
+            batch = inp.pre(dict(batch))   # inputs, constant w.r.t. every parameter -- applied once, then forgotten
         ids = batch[cm.item_id]
         B, L = ids.shape
         M = B * L
