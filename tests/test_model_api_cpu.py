@@ -90,3 +90,61 @@ def test_item_prediction_model_from_config_inference(monkeypatch, arch):
     with torch.no_grad():
         out = model(_batch(schema))
     assert out.dim() == 2 and out.size(1) == task.target_dim == 51997
+
+
+def test_state_dict_keys_follow_the_reference_module_tree_and_save_load_round_trip(monkeypatch, tmp_path):
+    """Checkpoint surface ("state-dict key names ... are the compatibility surface"; model/base.py:839-922).
+    The key names below are what the reference's module tree produces for the same construction: ``to_merge`` /
+    ``embedding_tables`` (features/sequence.py, features/embedding.py), ``projection_module.0.0`` (MLPBlock ->
+    DenseBlock -> Linear), ``_masking.masked_item_embedding`` (masking.py:103-108), HF's XLNet names under
+    ``body.1.transformer``, and the task's aliases set in NextItemPredictionTask.build (prediction_task.py:380-417:
+    ``embeddings``, ``item_embedding_table``, ``masking``, ``task_block``)."""
+    D.install(monkeypatch)
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 300, tags=[tr.Tags.ITEM_ID]),
+                        tr.ColumnSchema.create_categorical("category/list", 40),
+                        tr.ColumnSchema.create_continuous("price/list")])
+
+    def build():
+        inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=8, d_output=32, masking="mlm")
+        return tr.XLNetConfig.build(32, 2, 1, 8).to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
+    model = build()
+    keys = set(model.state_dict().keys())
+    expected = {
+        "heads.0.body.0.to_merge.categorical_module.embedding_tables.item_id/list.weight",
+        "heads.0.body.0.to_merge.categorical_module.embedding_tables.category/list.weight",
+        "heads.0.body.0.projection_module.0.0.weight", "heads.0.body.0.projection_module.0.0.bias",
+        "heads.0.body.0._masking.masked_item_embedding",
+        "heads.0.body.1.masking.masked_item_embedding",
+        "heads.0.body.1.transformer.mask_emb", "heads.0.body.1.transformer.word_embedding.weight",
+        "heads.0.prediction_task_dict.next-item.embeddings.embedding_tables.item_id/list.weight",
+        "heads.0.prediction_task_dict.next-item.item_embedding_table.weight",
+        "heads.0.prediction_task_dict.next-item.masking.masked_item_embedding",
+        "heads.0.prediction_task_dict.next-item.task_block.0.0.weight",
+        "heads.0.prediction_task_dict.next-item.task_block.0.0.bias",
+    }
+    for leaf in ("q", "k", "v", "o", "r", "r_r_bias", "r_s_bias", "r_w_bias", "seg_embed", "layer_norm.weight",
+                 "layer_norm.bias"):
+        expected.add("heads.0.body.1.transformer.layer.0.rel_attn." + leaf)
+    for leaf in ("layer_norm.weight", "layer_norm.bias", "layer_1.weight", "layer_1.bias", "layer_2.weight", "layer_2.bias"):
+        expected.add("heads.0.body.1.transformer.layer.0.ff." + leaf)
+    assert expected <= keys, sorted(expected - keys)
+    # save -> torch.load -> Model.load over freshly built heads: same weights, same loss
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    model.save(tmp_path, model_name="m")
+    sd = torch.load(tmp_path / "m.pt")
+    other = tr.Model.load(sd, build().heads[0], max_sequence_length=8)
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), other.state_dict().values()))
+    batch = {"item_id/list": torch.randint(1, 301, (4, 8)), "category/list": torch.randint(1, 41, (4, 8)),
+             "price/list": torch.rand(4, 8)}
+    u = torch.rand(4, 10, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for m in (model, other):
+            m.heads[0].body[0].masking.set_draws(u)
+        a, b = model(dict(batch), training=True)["loss"], other(dict(batch), training=True)["loss"]
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        tr.Model.load([1, 2], build().heads[0])
+    with pytest.raises(RuntimeError):      # strict by default, as in the reference
+        tr.Model.load({k: v for k, v in sd.items() if "projection_module" not in k}, build().heads[0])

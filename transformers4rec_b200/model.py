@@ -1,12 +1,16 @@
 """Head / Model: the call chain of model/base.py:371-407 (Head.forward) and
 :544-598 (Model.forward) for the next-item path, plus the two callers SURVEY §8f N3 names on
 the model itself: ``Model.fit`` (model/base.py:669-717) and ``Model.evaluate``
-(:719-738).  save/load, schemas and the HF Trainer integration are host
-orchestration outside the hot path and are not mirrored."""
+(:719-738), and the checkpoint surface ``Model.save`` / ``Model.load`` (:839-922: the
+state dict, whose key names follow the reference's module tree).  Schemas and the HF
+Trainer integration are host orchestration outside the hot path
+and are not mirrored."""
 from __future__ import annotations
 
 import inspect
 import logging
+import os
+import pathlib
 from typing import Dict, List, Optional, Union
 
 import numpy as np
@@ -117,6 +121,7 @@ class Model(nn.Module):
         self.head_reduction = head_reduction
         self.top_k = kwargs.get("top_k", None)
         self.max_sequence_length = kwargs.get("max_sequence_length", None)
+        self.name = kwargs.get("name", None)
 
     def enable_fused_training(self, on: bool = True, head_chunk: int = 32768):
         """N3: route ``model(batch, training=True)`` through the fused training step whenever autograd is recording, so
@@ -225,6 +230,28 @@ class Model(nn.Module):
         if getattr(output, "row_rank", None) is not None:
             return self.calculate_metrics(output)
         return self.calculate_metrics(output["predictions"], targets=output["labels"])
+
+    # ------------------------------------------------------------------ checkpoint surface (model/base.py:839-922)
+    def save(self, path: Union[str, os.PathLike], model_name: str = "t4rec_model_class"):
+        """model/base.py:839-856: the state dict (weights only) goes to ``{path}/{model_name}.pt``; the architecture is
+        rebuilt by the caller before ``Model.load``.  A row-sharded item table is saved as THIS rank's rows."""
+        export_path = pathlib.Path(path)
+        export_path.mkdir(exist_ok=True)
+        torch.save(self.state_dict(), export_path / (model_name + ".pt"))
+
+    @classmethod
+    def load(cls, state_dict: Dict[str, torch.Tensor], heads, head_weights=None, head_reduction: str = "mean",
+             optimizer=None, name: Optional[str] = None, max_sequence_length: Optional[int] = None,
+             top_k: Optional[int] = None, strict: bool = True) -> "Model":
+        """model/base.py:858-922: a Model over already-built ``heads`` carrying ``state_dict`` (no file I/O here)."""
+        if not isinstance(heads, (list, nn.ModuleList)):
+            heads = [heads]
+        model = cls(*heads, head_weights=head_weights, head_reduction=head_reduction, name=name,
+                    max_sequence_length=max_sequence_length, top_k=top_k)
+        if not isinstance(state_dict, dict) or not all(isinstance(v, torch.Tensor) for v in state_dict.values()):
+            raise ValueError("`state_dict` must be a dictionary of parameter (torch) tensors.")
+        model.load_state_dict(state_dict, strict=strict)
+        return model
 
     def calculate_metrics(self, predictions, targets=None):
         out = {}
