@@ -634,3 +634,20 @@ def test_training_step_with_stochastic_swap_noise(monkeypatch):
             continue
         err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
         assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
+def test_training_step_says_that_dropout_is_not_applied(monkeypatch, caplog):
+    """The reference's configs default to dropout 0.3 (config/transformer.py:217-260,432-482); the fused step trains
+    without it and says so once at construction."""
+    import logging
+    from transformers4rec_b200.training import FusedTrainingStep
+    D.install(monkeypatch)
+    _, model = make_pair({"item_id/list": 101}, {"item_id/list": 32}, "item_id/list", (), 32, 2, 1, 8, device="cpu")
+    with caplog.at_level(logging.WARNING, logger="transformers4rec_b200"):
+        FusedTrainingStep(model)
+    assert any("no dropout" in r.getMessage() for r in caplog.records)
+    caplog.clear()
+    model.heads[0].body[1].transformer.config.dropout = 0.0
+    with caplog.at_level(logging.WARNING, logger="transformers4rec_b200"):
+        FusedTrainingStep(model)
+    assert not any("no dropout" in r.getMessage() for r in caplog.records)

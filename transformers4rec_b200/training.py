@@ -31,6 +31,7 @@ StochasticSwapNoise as the input block's pre-transform.  Not covered: dropout.
 from __future__ import annotations
 
 import math
+import logging
 from typing import Dict, List, Optional
 
 import torch
@@ -38,6 +39,8 @@ import torch
 from . import _lib, ops
 from .block import GPT2Encoder, XLNetEncoder
 from .masking import CausalLanguageModeling, MaskedLanguageModeling, PermutationLanguageModeling
+
+LOG = logging.getLogger("transformers4rec_b200")
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -391,6 +394,13 @@ class FusedTrainingStep:
         self.graph = _XLNetGraph(enc) if isinstance(enc, XLNetEncoder) else _GPT2Graph(enc)
         self.layout = layout
         self.head_chunk = int(head_chunk)
+        cfg = enc.config
+        rates = [float(getattr(cfg, k, 0.0) or 0.0) for k in ("dropout", "resid_pdrop", "embd_pdrop", "attn_pdrop")]
+        if max(rates) > 0.0:
+            # config/transformer.py:217-260,432-482 default to dropout = 0.3, which the reference applies in train() mode
+            LOG.warning("FusedTrainingStep: the encoder is configured with dropout %.2f; the fused training step applies "
+                        "no dropout (build the config with dropout=0 to train the same function as the reference)",
+                        max(rates))
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
