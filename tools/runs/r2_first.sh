@@ -23,5 +23,6 @@ echo "== timings (config-2 head shape): nprod 3 / 1, resident-A, nprod 2"; timeo
 echo "== bench A/B"; for a in "" "--nprod 2"; do timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline $a 2>&1 | tail -1 | cut -c1-700; done
 echo "== bench with the resident-A head"; T4R_HEAD_RESIDENT=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-700
 T4R_HEAD_RESIDENT=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --nprod 2 2>&1 | tail -1 | cut -c1-700
+echo "== training step timing (fwd + bwd + optimizer; not the BASELINE metric)"; for o in sgd adamw; do timeout 600 python bench.py --train --optimizer $o --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-500; done
 } > gpurun_out/r2_first.log 2>&1
 tail -60 gpurun_out/r2_first.log
