@@ -499,3 +499,27 @@ def test_descriptor_encodings_match_the_vendored_cutlass_headers(tmp_path):
     run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert run.returncode == 0 and "MISMATCH" not in run.stdout, run.stdout
     assert run.stdout.count(" ok") >= 17
+
+
+def test_every_c_abi_call_site_matches_its_ctypes_signature():
+    """Static check over the package's Python sources: every ``lib.t4r_*(...)`` call passes as many arguments as the
+    ctypes signature in _lib.SIGNATURES declares (``*tail`` = (stream, on_host)).  Most wrappers only run on a GPU, so
+    an arity slip would otherwise surface there first."""
+    import ast
+    import pathlib
+    from transformers4rec_b200 import _lib
+    root = pathlib.Path(_lib.__file__).parent
+    checked = 0
+    for path in sorted(root.glob("*.py")):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("t4r_")):
+                continue
+            name = node.func.attr
+            assert name in _lib.SIGNATURES, (path.name, node.lineno, name)
+            stars = sum(isinstance(a, ast.Starred) for a in node.args)
+            plain = len(node.args) - stars
+            assert stars <= 1, (path.name, node.lineno, name)
+            assert plain + 2 * stars == len(_lib.SIGNATURES[name][1]), (path.name, node.lineno, name)
+            checked += 1
+    assert checked >= 50
