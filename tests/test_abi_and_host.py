@@ -523,3 +523,20 @@ def test_every_c_abi_call_site_matches_its_ctypes_signature():
             assert plain + 2 * stars == len(_lib.SIGNATURES[name][1]), (path.name, node.lineno, name)
             checked += 1
     assert checked >= 50
+
+
+def test_header_prototypes_and_ctypes_signatures_agree_on_argument_counts():
+    """include/t4r_b200.h vs _lib.SIGNATURES: same set of entry points, same number of arguments each (the .cu files
+    include the header, so the compiler already holds the definitions to it)."""
+    import pathlib
+    import re
+    from transformers4rec_b200 import _lib
+    src = (pathlib.Path(__file__).parent.parent / "include" / "t4r_b200.h").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"\b(?:int|void|const char\s*\*|int64_t|size_t|long long)\s+(t4r_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert {n for n, _ in protos} == set(_lib.SIGNATURES)
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), name
