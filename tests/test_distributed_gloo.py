@@ -297,3 +297,70 @@ def test_training_step_over_sharded_item_table_world2():
         assert p.exitcode == 0
     for rank, r in res:
         assert r["loss"] < 1e-4 and r["table"] < 3e-4 and r["table_rows"] and r["worst"] < 3e-4 and r["n"] >= 15, (rank, r)
+
+
+def _ddp_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import _ops_double
+    from _util import make_pair, mlm_draws, synth_batch
+    from test_host_training_cpu import _pairs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _ops_double.install_plain()
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        cards, dims = {"item_id/list": 401, "category/list": 23}, {"item_id/list": 32, "category/list": 32}
+        Bm, Lm = 5, 8
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 32, 2, 1, Lm, weight_scale=0.08, device="cpu")
+        oracle.train(False)
+        batches = [synth_batch(Bm, Lm, cards, seed=100 + r) for r in range(world)]
+        us = [mlm_draws(Bm, Lm, seed=200 + r) for r in range(world)]
+        # what DDP computes: the mean over the ranks of every rank's own mean-loss gradient
+        want = {}
+        for r in range(world):
+            for p in oracle.parameters():
+                p.grad = None
+            oracle(batches[r], training=True, draws=us[r][1])["loss"].backward()
+            for n, p in oracle.named_parameters():
+                if p.grad is not None:
+                    want[n] = want.get(n, 0) + p.grad.detach().clone() / world
+        names = {id(p): n for n, p in oracle.named_parameters()}
+        model.heads[0].body[0].masking.set_draws(us[rank][0])
+        model.enable_fused_training(head_chunk=256)
+        ddp = DDP(model, find_unused_parameters=True)   # as the reference's multi-GPU recipe needs (docs/source/multi_gpu_train.md)
+        res = {"worst": 0.0, "n": 0, "steps": 0}
+        for it in range(2):                              # a second step proves the reducer finished the first one cleanly
+            for p in model.parameters():
+                p.grad = None
+            out = ddp(batches[rank], training=True)
+            out["loss"].backward()
+            res["steps"] += 1
+        for name, po, pm in _pairs(oracle, model):
+            key = names[id(po)]
+            if key not in want and pm.grad is None:
+                continue
+            err = (pm.grad - want[key].reshape(pm.grad.shape)).abs().max().item() / max(1.0, want[key].abs().max().item())
+            res["worst"] = max(res["worst"], err)
+            res["n"] += 1
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_training_under_distributed_data_parallel_world2():
+    """The reference's multi-GPU training mode is torch DDP around the model (docs/source/multi_gpu_train.md).
+    With ``enable_fused_training`` the same wrapper works: the fused step's autograd node feeds DDP's gradient hooks, and
+    every parameter ends with the mean over the ranks of the oracle's per-rank gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        assert r["steps"] == 2 and r["worst"] < 3e-4 and r["n"] >= 15, (rank, r)

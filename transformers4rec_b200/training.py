@@ -634,32 +634,41 @@ class FusedTrainingStep:
 
 
 class _FusedLossFn(torch.autograd.Function):
-    """loss = FusedTrainingStep(...) as ONE autograd node over all parameters: the forward runs the step's forward AND
-    backward eagerly (gradients parked aside), ``backward`` scales and returns them."""
+    """The loss of a step that has ALREADY run forward and backward, as one autograd node over exactly the parameters
+    that received a gradient: ``backward`` scales the parked gradients by the incoming one and hands them to autograd
+    (AccumulateGrad, hooks -- DistributedDataParallel's included).  Parameters the path does not touch (XLNet's
+    ``seg_embed`` / ``r_s_bias``, HF:xlnet:225-233, unused without token types) are not inputs of the node, so
+    ``find_unused_parameters`` sees them exactly as it does in the reference's autograd graph."""
 
     @staticmethod
-    def forward(ctx, step: FusedTrainingStep, batch, *params):
-        saved = [p.grad for p in params]
-        for p in params:
-            p.grad = None
-        with torch.no_grad():
-            loss = step.forward(batch)
-            step.backward(1.0)
-        ctx.grads = [p.grad for p in params]
-        for p, g in zip(params, saved):
-            p.grad = g
+    def forward(ctx, loss, grads, *params):
+        ctx.grads = grads
         return loss.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        return (None, None) + tuple(None if g is None else g * grad_out for g in ctx.grads)
+        return (None, None) + tuple(g * grad_out for g in ctx.grads)
 
 
 def training_loss(model, batch, step: Optional[FusedTrainingStep] = None) -> torch.Tensor:
-    """Differentiable training loss of the fused path: ``training_loss(model, batch).backward()`` fills ``.grad``."""
+    """Differentiable training loss of the fused path: ``training_loss(model, batch).backward()`` fills ``.grad``.
+    The step's forward and backward run here, eagerly (gradients parked aside, the parameters' own ``.grad`` untouched);
+    the returned scalar carries them as one autograd node."""
     step = step or FusedTrainingStep(model)
     params = [p for p in model.parameters() if p.requires_grad]
-    return _FusedLossFn.apply(step, batch, *params)
+    saved = [p.grad for p in params]
+    for p in params:
+        p.grad = None
+    try:
+        with torch.no_grad():
+            loss = step.forward(batch)
+            step.backward(1.0)
+        grads = [p.grad for p in params]
+    finally:
+        for p, g in zip(params, saved):
+            p.grad = g
+    used = [(p, g) for p, g in zip(params, grads) if g is not None]
+    return _FusedLossFn.apply(loss, [g for _, g in used], *[p for p, _ in used])
 
 
 class FusedAdamW(torch.optim.Optimizer):
