@@ -213,3 +213,64 @@ def test_widened_input_block_training_on_gpu():
                 continue
             err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
             assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (aggregation, name, err)
+
+
+def _ddp_nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cards, dims = {"item_id/list": 3001, "category/list": 37}, {"item_id/list": 64, "category/list": 64}
+        B, L = 16, 20
+        oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 2, L, weight_scale=0.08, device=f"cuda:{rank}")
+        oracle.train(False)
+        batches = [synth_batch(B, L, cards, seed=100 + r) for r in range(world)]
+        us = [mlm_draws(B, L, seed=200 + r) for r in range(world)]
+        want = {}
+        for r in range(world):
+            for p in oracle.parameters():
+                p.grad = None
+            oracle(batches[r], training=True, draws=us[r][1])["loss"].backward()
+            for n, p in oracle.named_parameters():
+                if p.grad is not None:
+                    want[n] = want.get(n, 0) + p.grad.detach().clone() / world
+        names = {id(p): n for n, p in oracle.named_parameters()}
+        model.heads[0].body[0].masking.set_draws(us[rank][0].cuda())
+        model.enable_fused_training(head_chunk=1024)
+        ddp = DDP(model, device_ids=[rank], find_unused_parameters=True)
+        dev = {k: v.cuda() for k, v in batches[rank].items()}
+        for _ in range(2):
+            for p in model.parameters():
+                p.grad = None
+            ddp(dev, training=True)["loss"].backward()
+        worst, n = 0.0, 0
+        for name, po, pm in _pairs(oracle, model):
+            key = names[id(po)]
+            if key not in want and pm.grad is None:
+                continue
+            err = (pm.grad.cpu() - want[key].reshape(pm.grad.shape)).abs().max().item() / max(1.0, want[key].abs().max().item())
+            worst, n = max(worst, err), n + 1
+        q.put((rank, worst, n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_training_under_ddp_nccl():
+    """DistributedDataParallel (NCCL, 2 GPUs) around a model with the fused training step: every parameter's gradient is
+    the mean over the ranks of the oracle's per-rank gradients."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_ddp_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, worst, n in res:
+        assert worst < 1e-3 and n >= 15, (rank, worst, n)
