@@ -380,6 +380,18 @@ def test_model_fit_and_evaluate(monkeypatch, capsys):
                                                   for k in metrics)
     model.fit(batches, eval_dataloader=batches, num_epochs=1, verbose=True)
     assert "recall_at" in capsys.readouterr().out
+    # train-mode metrics come from the label ranks among the training logits: one epoch at lr 0 leaves the weights
+    # alone, so they must equal the metrics of the forward-only training pass (materialised predictions)
+    model.reset_metrics()
+    model.fit(batches, optimizer=torch.optim.SGD(model.parameters(), lr=0.0), num_epochs=1, verbose=False)
+    from_ranks = model.compute_metrics(mode="train")
+    model.reset_metrics()
+    model.fit(batches, num_epochs=1, train=False, verbose=False)
+    from_logits = model.compute_metrics(mode="train")
+    assert from_ranks.keys() == from_logits.keys() and len(from_ranks) >= 2
+    assert any(float(torch.as_tensor(v).max()) > 0 for v in from_ranks.values())
+    for k in from_ranks:
+        assert torch.allclose(torch.as_tensor(from_ranks[k]), torch.as_tensor(from_logits[k]), atol=1e-6), k
     # train=False: forward-only pass with train-mode metrics, no parameter moves
     before = [p.detach().clone() for p in model.parameters()]
     l0 = model.fit(batches, num_epochs=1, train=False, verbose=False)

@@ -140,7 +140,10 @@ class Model(nn.Module):
             from .training import training_loss
             step = self._fused_step
             loss = training_loss(self, inputs, step)
-            return {"loss": loss, "labels": step.labels[:step.T]}
+            from .prediction_task import LazyOutputs
+            out = LazyOutputs({"loss": loss, "labels": step.labels[:step.T]}, {})
+            out.row_rank, out.count = step.row_rank, None    # label ranks among the training logits, when asked for
+            return out
         # model/base.py:546-548: floating inputs are cast to fp32
         for name, val in inputs.items():
             if torch.is_floating_point(val) and val.dtype != torch.float32:
@@ -170,8 +173,9 @@ class Model(nn.Module):
         default optimizer is ``FusedAdamW`` with lr 1e-3 and no weight decay, i.e. the reference's ``torch.optim.Adam``
         default computed by the t4r update kernel.  An optimizer class is instantiated on ``self.parameters()``
         (as in the reference), an instance is used as is.  The fused head never materialises the [T, V] training
-        logits, so train-mode ranking metrics are accumulated only when the forward returns predictions
-        (``train=False``); use ``eval_dataloader`` / ``evaluate`` for metrics.  ``amp`` is accepted and ignored: the
+        logits: with ``compute_metric`` the training head also emits every label's rank among them (replicated full
+        softmax) and the streaming metrics are updated from those ranks; with sampled softmax or a row-sharded table
+        train-mode metrics are not accumulated -- use ``eval_dataloader`` / ``evaluate``.  ``amp`` is accepted and ignored: the
         path's GEMMs are fixed split-bf16 tensor-core products at fp32 accuracy, there is no autocast switch."""
         if optimizer is None:
             from .training import FusedAdamW
@@ -182,6 +186,8 @@ class Model(nn.Module):
             LOG.warning("Model.fit: amp=True has no effect on the t4r path (fp32-grade tensor-core products)")
         if train and getattr(self, "_fused_step", None) is None:
             self.enable_fused_training()
+        if train:
+            self._fused_step.want_rank = bool(compute_metric)
         self.train(mode=train)
         epoch_losses = []
         with torch.set_grad_enabled(mode=train):
@@ -194,14 +200,14 @@ class Model(nn.Module):
                 for x, y in it:
                     output = self(x, targets=y, training=True)
                     losses.append(float(output["loss"].detach()))
-                    if compute_metric and not train:
+                    if compute_metric and (not train or getattr(output, "row_rank", None) is not None):
                         self._update_metrics(output)
                     if train:
                         optimizer.zero_grad()
                         output["loss"].backward()
                         optimizer.step()
                 if verbose:
-                    if compute_metric and not train:
+                    if compute_metric:
                         print(self.compute_metrics(mode="train"))
                     if eval_dataloader:
                         print(self.evaluate(eval_dataloader, verbose=False))

@@ -367,7 +367,11 @@ class _WideInput:
 # the whole step
 # --------------------------------------------------------------------------------------------------------------
 class FusedTrainingStep:
-    def __init__(self, model, head_chunk: int = 32768):
+    def __init__(self, model, head_chunk: int = 32768, want_rank: bool = False):
+        # want_rank: also produce the label ranks among the training logits (replicated full softmax), so that the
+        # streaming ranking metrics of ``Model.fit(compute_metric=True)`` (model/base.py:704-707) need no [T, V] logits
+        self.want_rank = bool(want_rank)
+        self.row_rank = None
         if len(model.heads) != 1 or len(model.heads[0].prediction_task_dict) != 1:
             raise NotImplementedError("FusedTrainingStep: one head with one NextItemPredictionTask")
         head = model.heads[0]
@@ -413,6 +417,7 @@ class FusedTrainingStep:
         M = B * L
         self.B, self.L, self.M = B, L, M
         cm.item_seq = ids
+        self.row_rank = None
         inp.masking.compute_masked_targets(ids, training=True, testing=False)
         code = inp.masking.row_code.reshape(-1)
         self.code = code
@@ -507,7 +512,8 @@ class FusedTrainingStep:
                 train_head=getattr(table, "train_head", None))
             return self.loss
         res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(W), W, inv_temperature=inv_tau,
-                                  label_smoothing=self.smooth)
+                                  label_smoothing=self.smooth, want_rank=self.want_rank)
+        self.row_rank = res["row_rank"][:T] if self.want_rank else None
         self.row_lse = res["row_lse"]
         self.loss = res["loss"].reshape(())
         return self.loss
