@@ -612,3 +612,32 @@ def test_gpu_only_wrappers_marshal_their_arguments(monkeypatch):
     ops.soft_emb_fwd(x[:, 0], rw[:10], rr[:10], W[:10]); ops.ew_add(x, dy); ops.ew_mul(x, dy)
     ops.adamw_step(x.view(-1), dy.view(-1), torch.zeros(M * d), torch.zeros(M * d), 1e-3, 0.9, 0.999, 1e-8, 0.01, 1)
     assert len(fake.calls) >= 25
+
+
+def test_mixed_mma_operand_offsets_pick_matching_k_ranges():
+    """The 2-unit product's MMA issue sequence (t4r_gemm.cu, ``nprod == 2`` branches), replayed on the byte layout the
+    REAL packing code produces: per 64-K block and 128-byte operand row, four K = 16 fp16 MMAs at byte offsets
+    ``k4 * 32`` of plane 0, then for j = 0, 1 one K = 32 e4m3 MMA of A bytes [64 + 32 j, +32) x B bytes [32 j, +32) of
+    plane 1 and one of A bytes [32 j, +32) x B bytes [64 + 32 j, +32).  Summed in fp64 this must be the emulated product
+    (main + lo8(A) hi8(B) + hi8(A) lo8(B)) -- i.e. the offsets pair the SAME K indices of the two operands."""
+    import _mixed_ref as R
+    from transformers4rec_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn(9, 200, generator=g), torch.randn(7, 200, generator=g) * 0.05
+    (pa, ia), (pb, ib) = ops.split_planes_mixed_host(a), ops.split_planes_mixed_host(b)
+    Kp = pa.shape[2]
+    rows = lambda p, plane: p[plane].contiguous().view(torch.uint8).reshape(p.shape[1], Kp // 64, 128)   # [row, kb, 128 B]
+    a0, a1, b0, b1 = rows(pa, 0), rows(pa, 1), rows(pb, 0), rows(pb, 1)
+    f16 = lambda t: t.contiguous().view(torch.float16).double()
+    f8 = lambda t: t.contiguous().view(torch.float8_e4m3fn).double()
+    acc = torch.zeros((9, 7), dtype=torch.float64)
+    for kb in range(Kp // 64):
+        for k4 in range(4):
+            acc += f16(a0[:, kb, k4 * 32:k4 * 32 + 32]) @ f16(b0[:, kb, k4 * 32:k4 * 32 + 32]).t()
+        for j in range(2):
+            acc += f8(a1[:, kb, 64 + j * 32:96 + j * 32]) @ f8(b1[:, kb, j * 32:32 + j * 32]).t()
+            acc += f8(a1[:, kb, j * 32:32 + j * 32]) @ f8(b1[:, kb, 64 + j * 32:96 + j * 32]).t()
+    got = acc * ia.double()[:, None] * ib.double()[None, :]
+    want = R.product(R.pack(a), R.pack(b))
+    assert torch.equal(got, want) or (got - want).abs().max().item() < 1e-12
+    assert (got - a.double() @ b.double().t()).abs().max().item() < 1e-4
