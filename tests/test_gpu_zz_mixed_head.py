@@ -165,3 +165,42 @@ def test_model_training_loss_with_mixed_head():
         preds = out["predictions"]  # lazily materialised through the 3-product planes
     assert math.isfinite(l2) and abs(l2 - ref) < 1e-3 and abs(l2 - l3) < 1e-4
     assert preds.shape[1] == 10001
+
+
+def test_head_variants_at_config2_full_size(ops, monkeypatch):
+    """BASELINE configs[1] head shape (T = 5120 label rows, V = 1 000 001, De = 256), size-independent properties:
+    every opt-in variant (resident-A kernel with the shipped 3-product arithmetic; 2-unit product on the CTA-pair and
+    on the resident-A kernel) reproduces the default kernel's per-row log-sum-exp and loss (same logits up to the
+    product's error budget), probabilities sum to one, and permuting the table rows -- columns of the GEMM, so a
+    different tile / chunk assignment for every class -- leaves every row's log-sum-exp where it was."""
+    torch.manual_seed(3)
+    T, V, De = 5120, 1_000_001, 256
+    xt = torch.nn.functional.layer_norm(torch.randn(T, De, device="cuda"), (De,))
+    W = torch.randn(V, De, device="cuda") * 0.05
+    y = torch.randint(1, V, (T,), device="cuda")
+    xp, wp = ops.split_planes(xt), ops.split_planes(W)
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "0")
+    base = ops.head_softmax_ce(xp, xt, y, wp, W)
+    perm = torch.randperm(V, device="cuda")
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(V, device="cuda")
+    Wq = W[perm].contiguous()
+    xm, xi = ops.split_planes_mixed(xt)
+    wm, wi = ops.split_planes_mixed(W)
+    wqm, wqi = ops.split_planes_mixed(Wq)
+    runs = {}
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "1")
+    runs["resident x3"] = (ops.head_softmax_ce(xp, xt, y, wp, W), 1e-5)
+    runs["resident x3, permuted table"] = (ops.head_softmax_ce(xp, xt, inv[y], ops.split_planes(Wq), Wq), 2e-5)
+    runs["resident 2-unit"] = (ops.head_softmax_ce(xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi, w_inv_scale=wi), 2e-4)
+    runs["resident 2-unit, permuted table"] = (ops.head_softmax_ce(xm, xt, inv[y], wqm, Wq, nprod=2, xt_inv_scale=xi,
+                                                                   w_inv_scale=wqi), 2e-4)
+    monkeypatch.setenv("T4R_HEAD_RESIDENT", "0")
+    runs["pair 2-unit"] = (ops.head_softmax_ce(xm, xt, y, wm, W, nprod=2, xt_inv_scale=xi, w_inv_scale=wi), 2e-4)
+    for name, (r, tol) in runs.items():
+        assert (r["row_lse"] - base["row_lse"]).abs().max().item() < tol, name
+        assert (r["row_loss"] - base["row_loss"]).abs().max().item() < 2 * tol, name
+        assert abs(r["loss"].item() - base["loss"].item()) < tol, name
+    # probabilities sum to one: materialised 2-unit logits of a slice of rows against the fused log-sum-exp
+    lg = ops.head_logits_mixed(xm[:, :128].contiguous(), xi[:128].contiguous(), wm, wi, De)
+    p_sum = torch.exp(lg - runs["resident 2-unit"][0]["row_lse"][:128].unsqueeze(1)).sum(1)
+    assert (p_sum - 1).abs().max().item() < 1e-3
