@@ -10,7 +10,7 @@ echo "== proven GPU suite"; timeout 900 python -m pytest tests -q -m gpu -x -p n
 echo "== device packing == host twin"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -x -k "packing" -p no:cacheprovider 2>&1 | tail -5
 echo "== 2-unit product, element-wise (dense epilogue), then each partial product alone"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "materialised or partial_product" -p no:cacheprovider 2>&1 | tail -12
 echo "== resident-A kernel vs default kernel (shipped arithmetic)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "resident_head_kernel" -p no:cacheprovider 2>&1 | tail -8
-echo "== fused head nprod=2 on single / pair / resident"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "full_softmax_nprod2 or requires or model_training" -p no:cacheprovider 2>&1 | tail -15
+echo "== fused head nprod=2 on single / pair / resident"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "full_softmax_nprod2 or requires or model_training or config2_full_size" -p no:cacheprovider 2>&1 | tail -15
 echo "== two-warp tensor-path attention for 32 < L <= 64"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_attn64.py -q -p no:cacheprovider 2>&1 | tail -8
 timeout 300 python tools/microbench.py attn50 2>&1 | tail -3
 echo "== permutation language modeling (mask kernel, two-stream attention, model)"; T4R_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_plm.py -q -p no:cacheprovider 2>&1 | tail -8
