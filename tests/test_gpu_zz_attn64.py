@@ -25,3 +25,11 @@ def test_xlnet_encoder_two_warp_attention(monkeypatch, d, H, NL, B, L):
 def test_gpt2_encoder_two_warp_attention(monkeypatch, d, H, NL, B, L):
     monkeypatch.setenv("T4R_ATTN_MMA64", "1")
     GP.test_gpt2_encoder_matches_hf(d, H, NL, B, L)
+
+
+def test_config5_shape_at_full_size_with_two_warp_attention(monkeypatch):
+    """BASELINE configs[4]'s shape (L = 50, sampled softmax) through the full-size property test of
+    test_gpu_fullsize.py, with the encoder's attention on the two-warp tensor-path kernel."""
+    import test_gpu_fullsize as FS
+    monkeypatch.setenv("T4R_ATTN_MMA64", "1")
+    FS.test_config5_shape_sampled_softmax_L50()
