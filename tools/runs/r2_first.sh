@@ -18,7 +18,8 @@ echo "== training step (N3): primitives vs host twins, gradients vs autograd, SG
 echo "== memcheck of the new small kernels (packing, PLM mask, training primitives)"
 T4R_TEST_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -q -p no:cacheprovider \
   tests/test_gpu_zz_mixed_head.py::test_device_packing_matches_host_twin_bit_exactly tests/test_gpu_zz_plm.py::test_mask_kernel_matches_host_twin \
-  tests/test_gpu_zz_training.py::test_training_primitives_device_vs_host_twin 2>&1 | tail -6
+  tests/test_gpu_zz_training.py::test_training_primitives_device_vs_host_twin tests/test_gpu_zz_training.py::test_fused_adamw_on_gpu \
+  tests/test_gpu_zz_training.py::test_widened_input_block_training_on_gpu 2>&1 | tail -6
 echo "== timings (config-2 head shape): nprod 3 / 1, resident-A, nprod 2"; timeout 600 python tools/microbench.py head headres head2 2>&1 | tail -12
 echo "== bench A/B"; for a in "" "--nprod 2"; do timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline $a 2>&1 | tail -1 | cut -c1-700; done
 echo "== bench with the resident-A head"; T4R_HEAD_RESIDENT=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-700
