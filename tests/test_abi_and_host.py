@@ -641,3 +641,41 @@ def test_mixed_mma_operand_offsets_pick_matching_k_ranges():
     want = R.product(R.pack(a), R.pack(b))
     assert torch.equal(got, want) or (got - want).abs().max().item() < 1e-12
     assert (got - a.double() @ b.double().t()).abs().max().item() < 1e-4
+
+
+def test_product_path_has_no_cpu_fallback(monkeypatch, tmp_path):
+    """The product fails loudly instead of computing on the CPU: module forward with CPU tensors, the training step with
+    CPU tensors, every public op wrapper with CPU tensors (the host twins are reachable only through ``ops.host_twin``,
+    which nothing in the package, bench.py or __graft_entry__ calls), and a missing shared library."""
+    import inspect
+    import pathlib
+    import transformers4rec_b200.torch as tr
+    from transformers4rec_b200 import T4RError, _lib, ops
+    schema = tr.Schema([tr.ColumnSchema.create_categorical("item_id/list", 300, tags=[tr.Tags.ITEM_ID])])
+    inputs = tr.TabularSequenceFeatures.from_schema(schema, max_sequence_length=8, d_output=64, masking="mlm")
+    model = tr.XLNetConfig.build(64, 2, 1, 8).to_torch_model(inputs, tr.NextItemPredictionTask(weight_tying=True))
+    batch = {"item_id/list": torch.randint(1, 301, (4, 8))}
+    with pytest.raises(T4RError, match="no CPU fallback"):
+        with torch.no_grad():
+            model(dict(batch), training=True)
+    with pytest.raises(T4RError, match="no CPU fallback"):
+        tr.training_loss(model, dict(batch))
+    x = torch.randn(8, 64)
+    for fn, args in ((ops.split_planes, (x,)), (ops.transpose, (x,)), (ops.col_sum, (x,)), (ops.ew_add, (x, x)),
+                     (ops.act_fwd, (_lib.ACT_GELU, x)), (ops.split_planes_mixed, (x,))):
+        with pytest.raises(T4RError, match="no CPU fallback"):
+            fn(*args)
+    # nothing shipped selects a host twin
+    root = pathlib.Path(_lib.__file__).parent
+    shipped = list(root.glob("*.py")) + list((root / "torch").glob("*.py")) + [root.parent / "bench.py",
+                                                                                   root.parent / "__graft_entry__.py"]
+    for path in shipped:
+        src = "\n".join(ln for ln in path.read_text().splitlines() if not ln.lstrip().startswith("#"))
+        assert "_on_host=True" not in src.replace("fn(*a, _on_host=True, **k)", ""), path
+        assert "host_twin(" not in src.replace("def host_twin(", ""), path
+    assert "_on_host=True" in inspect.getsource(ops.host_twin)
+    # missing library: a loud error, not a fallback
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(T4RError, match="no CPU/eager fallback"):
+        _lib.load()
