@@ -663,3 +663,29 @@ def test_training_step_says_that_dropout_is_not_applied(monkeypatch, caplog):
     with caplog.at_level(logging.WARNING, logger="transformers4rec_b200"):
         FusedTrainingStep(model)
     assert not any("no dropout" in r.getMessage() for r in caplog.records)
+
+
+def test_plm_attention_backward_on_fully_masked_rows():
+    """A session whose every item is a target (upstream allows it, masking.py:646) leaves the first target of the
+    permutation with nothing to attend to in the query stream: HF's ``score - 1e30 * mask`` softmaxes that row to the
+    uniform distribution and autograd passes gradient through the masked scores (d/d score = 1).  The kernel's real
+    per-item code follows that: gradients equal autograd of the formula, fully masked rows included (also L = 1)."""
+    import random
+    from transformers4rec_b200 import ops
+    twin = ops.host_twin("xlnet_attn_bwd")
+    g = torch.Generator().manual_seed(0)
+    random.seed(1)
+    for trial in range(12):
+        B, L, Hh, dh = random.choice([1, 2, 5]), random.choice([1, 2, 3, 7, 12]), random.choice([1, 2]), 8
+        d = Hh * dh
+        R = torch.randn(2 * L, d, generator=g)
+        rw, rr = torch.randn(d, generator=g), torch.randn(d, generator=g)
+        pm = torch.rand(B, L, L, generator=g) < 0.4
+        pm[0, 0, :] = True                               # row 0 of session 0 sees nobody (g stream; h keeps its diagonal)
+        qkv = torch.randn(2 * B * L, 3 * d, generator=g)
+        dout = torch.randn(2 * B * L, d, generator=g)
+        want = D.xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, Hh, plm_mask=pm)      # autograd of the formula
+        got = twin(qkv, R, rw, rr, dout, B, L, Hh, plm_mask=pm)
+        for a, b in zip(want, got):
+            assert torch.isfinite(b).all()
+            assert (a - b).abs().max().item() < 1e-5 * max(1.0, a.abs().max().item())

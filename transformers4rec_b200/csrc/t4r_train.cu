@@ -214,8 +214,10 @@ T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const f
 constexpr int kAttnMaxL = 64;
 // plm_mask != nullptr: XLNet's two-stream form (permutation language modeling).  qkv / dout / dqkv then hold 2 B L rows
 // (content stream h, then query stream g); the item runs both streams: queries from the stream's rows, keys / values
-// from the h rows, score (i, j) forced to -1e30 where plm_mask[b, i, j] (h: except i == j) -- a constant, so such an
-// entry passes no gradient to q / k / R / the biases (its probability still weighs v_j, e.g. in a fully masked row).
+// from the h rows, score (i, j) = -1e30 where plm_mask[b, i, j] (h: except i == j).  The backward uses the same
+// ds_j = p_j (dp_j - sum) for every j, as autograd of HF's `score - 1e30 * mask` does (d/d score = 1): a masked entry
+// next to a visible one has p_j = 0 exactly and passes nothing; in a FULLY masked row (the first target of the
+// permutation when every item of a session is a target) p is uniform and the gradient flows as in the reference.
 T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
                           int L, int d, int H, float* dqkv, float* dR_part, float* drw_part, float* drr_part,
                           const uint8_t* plm_mask, int64_t item) {
@@ -237,15 +239,14 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
     for (int c = 0; c < dh; ++c) { drw_part[b * d + h * dh + c] = 0.f; drr_part[b * d + h * dh + c] = 0.f; }
   }
   float s[kAttnMaxL], dp[kAttnMaxL];
-  bool msk[kAttnMaxL];
   for (int st = 0; st < n_streams; ++st)
   for (int i = 0; i < L; ++i) {
     const float* q = qkv + (st * M + b * L + i) * 3 * d + h * dh;
     const float* dor = dout + (st * M + b * L + i) * d + h * dh;
     float mx = -INFINITY;
     for (int j = 0; j < L; ++j) {
-      msk[j] = plm_mask && plm_mask[(b * L + i) * L + j] && !(st == 0 && i == j);
-      if (msk[j]) { s[j] = -1e30f; mx = fmaxf(mx, s[j]); continue; }
+      const bool masked = plm_mask && plm_mask[(b * L + i) * L + j] && !(st == 0 && i == j);
+      if (masked) { s[j] = -1e30f; mx = fmaxf(mx, s[j]); continue; }
       if (!rel && j > i) { s[j] = -INFINITY; continue; }
       const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
       float acc = 0.f;
@@ -278,10 +279,6 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
       const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
       float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
       float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
-      if (msk[j]) {   // constant score: only the value path carries a gradient
-        for (int c = 0; c < dh; ++c) dv[c] += p * dor[c];
-        continue;
-      }
       if (rel) {
         const int64_t m = j + L - i;
         const float* Rm = R + m * d + h * dh;
