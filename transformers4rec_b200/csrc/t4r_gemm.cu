@@ -83,6 +83,9 @@ constexpr int BM = 128;
 #ifndef T4R_FFN_2CTA_DEFAULT
 #define T4R_FFN_2CTA_DEFAULT 0
 #endif
+#ifndef T4R_HEAD_RESIDENT_DEFAULT
+#define T4R_HEAD_RESIDENT_DEFAULT 0  // resident-A head kernel: flip to 1 once validated on hardware (T4R_HEAD_RESIDENT overrides)
+#endif
 #ifndef T4R_GEMM_2CTA_DEFAULT
 #define T4R_GEMM_2CTA_DEFAULT 1
 #endif
@@ -1511,7 +1514,7 @@ namespace t4r {
 // block, CTA pairs and 128-byte rows enabled.  Returns the number of LSE partials per row the head call must size
 // for (2 per column CHUNK), or 0 when the regular kernels run (2 per column TILE).
 int head_resident_partials(int64_t M, int64_t V, int Kp) {
-  int resident = 0;
+  int resident = T4R_HEAD_RESIDENT_DEFAULT;
   if (const char* e = getenv("T4R_HEAD_RESIDENT")) resident = atoi(e);
   int two_cta = T4R_GEMM_2CTA_DEFAULT;
   if (const char* e = getenv("T4R_GEMM_2CTA")) two_cta = atoi(e);
