@@ -364,3 +364,25 @@ def test_fused_training_under_distributed_data_parallel_world2():
         assert p.exitcode == 0
     for rank, r in res:
         assert r["steps"] == 2 and r["worst"] < 3e-4 and r["n"] >= 15, (rank, r)
+
+
+def test_sharded_model_and_training_step_world3():
+    """The same workers at world size 3 (shards of uneven size: 1201 = 401 + 400 + 400 rows): model forward / eval /
+    top-k over the sharded table and the sharded training step."""
+    ctx = mp.get_context("spawn")
+    for worker, base in ((_model_worker, 37500), (_train_worker, 39500)):
+        q = ctx.Queue()
+        port = base + (os.getpid() % 2000)
+        procs = [ctx.Process(target=worker, args=(r, 3, port, q)) for r in range(3)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=300) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        for rank, r in res:
+            if worker is _model_worker:
+                assert r["train3"] < 1e-4 and r["train2"] < 1e-3 and r["eval"] < 1e-4 and r["recall"] < 1e-6, (rank, r)
+                assert r["topk_scores"] < 1e-4 and r["topk_ids"] == 1.0, (rank, r)
+            else:
+                assert r["loss"] < 1e-4 and r["table"] < 3e-4 and r["table_rows"] and r["worst"] < 3e-4, (rank, r)
