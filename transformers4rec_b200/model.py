@@ -127,7 +127,8 @@ class Model(nn.Module):
         """N3: route ``model(batch, training=True)`` through the fused training step whenever autograd is recording, so
         that the usual ``loss = model(batch, training=True)["loss"]; loss.backward(); optimizer.step()`` (HF Trainer's
         compute_loss / training_step, trainer.py:315-338 in the reference) trains on the t4r kernels.  Opt-in; with it
-        off (the default) or under ``torch.no_grad()`` the forward-only path runs as before."""
+        off (the default) or under ``torch.no_grad()`` the forward-only path runs as before.  The step reads the model's
+        structure once, here: call it after the model is final (device placement, ``shard_item_table``, ``pre`` ...)."""
         if on:
             from .training import FusedTrainingStep
             self._fused_step = FusedTrainingStep(self, head_chunk=head_chunk)
