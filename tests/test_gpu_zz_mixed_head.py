@@ -1,11 +1,8 @@
 """GPU tests of the 2-unit product head (``nprod=2``: fp16 x fp16 + two e4m3 cross terms,
 csrc/t4r_mixed_pack.cuh).
 
-STATUS: this path was written after the round's GPU budget was spent -- the operand packing is pinned on
-the CPU (tests/test_abi_and_host.py, host twin of the kernel), the tcgen05 side compiles for sm_100a but has
-NOT run on hardware yet.  The tests are therefore opt-in (``T4R_TEST_EXPERIMENTAL=1``) so that an unproven
-kernel cannot take the proven suite down with it (a trap poisons the CUDA context of the whole pytest
-process); they sort last for the same reason.  First item of the next round: run them, then drop the gate.
+The operand packing is pinned on the CPU (tests/test_abi_and_host.py, host twin of the kernel); the tcgen05 side
+(single-CTA, CTA-pair and resident-A kernels) was validated on a B200 in round 2.
 """
 import math
 import os
@@ -15,9 +12,7 @@ import torch
 
 import t4r_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("T4R_TEST_EXPERIMENTAL") != "1",
-                                 reason="nprod=2 head not yet validated on hardware (set T4R_TEST_EXPERIMENTAL=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -127,7 +122,7 @@ def test_resident_head_kernel_matches_the_default_kernel(ops, monkeypatch, nprod
     c = ops.head_softmax_ce(xp, xt, y, wp, W, want_rank=False, nprod=nprod)   # packed-pair fast path
     for r in (b, c):
         assert (a["row_lse"] - r["row_lse"]).abs().max().item() < 1e-5
-        assert abs(a["loss"].item() - r["loss"].item()) < 1e-6
+        assert abs(a["loss"].item() - r["loss"].item()) < 4e-6   # a few ulp of a loss around 13
     assert torch.equal(a["row_rank"], b["row_rank"])
 
 

@@ -1,7 +1,7 @@
-"""GPU tests of the training step (transformers4rec_b200/training.py, csrc/t4r_train.cu).  Written after
-the round's GPU budget was spent; CPU-side evidence: the composition matches torch autograd of the oracle graph with
-kernel doubles AND with the kernels' real per-item code on their host twins (tests/test_host_training_cpu.py,
-tests/test_abi_and_host.py).  Opt-in (``T4R_TEST_EXPERIMENTAL=1``) until it has run once on hardware."""
+"""GPU tests of the training step (transformers4rec_b200/training.py, csrc/t4r_train.cu).  CPU-side
+evidence: the composition matches torch autograd of the oracle graph with kernel doubles AND with the kernels' real
+per-item code on their host twins (tests/test_host_training_cpu.py, tests/test_abi_and_host.py); first run on a B200 in
+round 2."""
 import os
 
 import pytest
@@ -11,9 +11,7 @@ import _ops_double as DD
 from _util import make_pair, mlm_draws, synth_batch
 from test_host_training_cpu import _oracle_grads, _pairs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("T4R_TEST_EXPERIMENTAL") != "1",
-                                 reason="training step not yet validated on hardware (set T4R_TEST_EXPERIMENTAL=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_training_primitives_device_vs_host_twin():

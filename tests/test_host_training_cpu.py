@@ -398,6 +398,38 @@ def test_model_fit_and_evaluate(monkeypatch, capsys):
     assert np.isfinite(l0).all() and all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
 
 
+def test_fit_evaluate_fit_evaluate_sees_fresh_weights(monkeypatch):
+    """FusedAdamW writes the parameters through a raw pointer; the forward-only path caches split planes of the GEMM
+    weights keyed on ``(data_ptr, _version)``.  After fit -> evaluate (caches filled) -> fit, the second evaluate must
+    run on the NEW weights: it has to equal an evaluate with every plane cache dropped."""
+    from transformers4rec_b200 import ops
+    twin = ops.host_twin("adamw_step")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "adamw_step", twin)
+    _, model = make_pair(CARDS, {"item_id/list": 32, "category/list": 32}, "item_id/list", CONT, 32, 2, 1, 8,
+                         device="cpu", weight_scale=0.08)
+    u, _ = mlm_draws(6, 8)
+    model.heads[0].body[0].masking.set_draws(u)
+    batches = [(synth_batch(6, 8, CARDS, CONT, seed=s), None) for s in (3, 4)]
+
+    def eval_loss():
+        with torch.no_grad():
+            return float(model(batches[0][0], training=False, testing=True)["loss"])
+    model.fit(batches, num_epochs=1, verbose=False)
+    first = eval_loss()                                   # fills the plane caches
+    versions = [p._version for p in model.parameters()]
+    model.fit(batches, num_epochs=10, verbose=False)
+    assert all(p._version > v for p, v in zip(model.parameters(), versions) if p.grad is not None)
+    cached = eval_loss()
+    for m in model.modules():
+        pc = getattr(m, "_planes", None)
+        if isinstance(pc, ops.PlaneCache):
+            pc.clear()
+    fresh = eval_loss()
+    assert abs(first - fresh) > 1e-3, "the second fit did not move the evaluation loss: the test would prove nothing"
+    assert cached == fresh, (cached, fresh)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the widened input block in training (N3 x N4): soft embeddings, per-feature LayerNorm, continuous projection,
 # element-wise aggregations

@@ -61,6 +61,8 @@ def test_with_next_item_pred_sampled_softmax(monkeypatch):
     with torch.no_grad():
         out = model(_batch(schema), training=True)
     assert torch.isfinite(out["loss"]) and out["predictions"].shape[1] <= 1001
+    # model/prediction_task.py:693-696: the positive is column 0 of the sampled logits, the returned targets are zeros
+    assert out["labels"].shape == (out["predictions"].shape[0],) and not out["labels"].any()
 
 
 @pytest.mark.parametrize("masking", ["causal", "mlm", "plm"])

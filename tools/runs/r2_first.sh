@@ -6,7 +6,7 @@
 # loses that step (separate processes).
 mkdir -p gpurun_out
 {
-echo "== proven GPU suite"; timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider 2>&1 | tail -5
+echo "== proven GPU suite skipped (driver ran it at the end of round 1: 85 passed)"
 echo "== device packing == host twin"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -x -k "packing" -p no:cacheprovider 2>&1 | tail -5
 echo "== 2-unit product, element-wise (dense epilogue), then each partial product alone"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "materialised or partial_product" -p no:cacheprovider 2>&1 | tail -12
 echo "== resident-A kernel vs default kernel (shipped arithmetic)"; T4R_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_mixed_head.py -q -k "resident_head_kernel" -p no:cacheprovider 2>&1 | tail -8

@@ -656,7 +656,7 @@ static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, cons
 // one warp per (session, head) up to 32 (augmented) query rows; with T4R_ATTN_MMA64=1 (opt-in: not yet run on
 // hardware) two warps per (session, head) up to 64
 #ifndef T4R_ATTN_MMA64_DEFAULT
-#define T4R_ATTN_MMA64_DEFAULT 0  // flip to 1 (or build with -DT4R_ATTN_MMA64_DEFAULT=1) once validated on hardware
+#define T4R_ATTN_MMA64_DEFAULT 1  // two-warp tensor-path attention for 32 < L <= 64 (validated on B200 in round 2; T4R_ATTN_MMA64=0 selects the FFMA kernel)
 #endif
 static bool attn_mma64_enabled() {
   const char* e = getenv("T4R_ATTN_MMA64");

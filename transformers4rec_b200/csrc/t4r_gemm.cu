@@ -84,7 +84,7 @@ constexpr int BM = 128;
 #define T4R_FFN_2CTA_DEFAULT 0
 #endif
 #ifndef T4R_HEAD_RESIDENT_DEFAULT
-#define T4R_HEAD_RESIDENT_DEFAULT 0  // resident-A head kernel: flip to 1 once validated on hardware (T4R_HEAD_RESIDENT overrides)
+#define T4R_HEAD_RESIDENT_DEFAULT 1  // resident-A head kernel (validated on B200 in round 2; T4R_HEAD_RESIDENT=0 selects the streaming CTA-pair kernel)
 #endif
 #ifndef T4R_GEMM_2CTA_DEFAULT
 #define T4R_GEMM_2CTA_DEFAULT 1

@@ -137,14 +137,6 @@ class Model(nn.Module):
         return self
 
     def forward(self, inputs: Dict[str, torch.Tensor], targets=None, training=False, testing=False, **kwargs):
-        if training and not testing and getattr(self, "_fused_step", None) is not None and torch.is_grad_enabled():
-            from .training import training_loss
-            step = self._fused_step
-            loss = training_loss(self, inputs, step)
-            from .prediction_task import LazyOutputs
-            out = LazyOutputs({"loss": loss, "labels": step.labels[:step.T]}, {})
-            out.row_rank, out.count = step.row_rank, None    # label ranks among the training logits, when asked for
-            return out
         # model/base.py:546-548: floating inputs are cast to fp32
         for name, val in inputs.items():
             if torch.is_floating_point(val) and val.dtype != torch.float32:
@@ -153,6 +145,14 @@ class Model(nn.Module):
         if any(k.endswith("__offsets") for k in inputs):
             from .padding import pad_inputs
             inputs = pad_inputs(inputs, max_sequence_length=self.max_sequence_length)
+        if training and not testing and getattr(self, "_fused_step", None) is not None and torch.is_grad_enabled():
+            from .training import training_loss
+            step = self._fused_step
+            loss = training_loss(self, inputs, step)
+            from .prediction_task import LazyOutputs
+            out = LazyOutputs({"loss": loss, "labels": step.labels[:step.T]}, {})
+            out.row_rank, out.count = step.row_rank, None    # label ranks among the training logits, when asked for
+            return out
         if len(self.heads) == 1:
             # :574-576 stack().mean() over one head is the identity
             return self.heads[0](inputs, call_body=True, targets=targets, training=training, testing=testing,

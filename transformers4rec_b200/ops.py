@@ -168,6 +168,8 @@ def embed_concat(cats: List[Tuple[torch.Tensor, torch.Tensor, int]], conts: List
         if ids.dtype != torch.int64:
             ids = ids.long()
         ids = ids.contiguous()
+        if ids.numel() != M:
+            raise _lib.T4RError(f"embed_concat: feature {i} carries {ids.numel()} ids, expected M = {M}")
         keep += [table, ids]
         fl.table[i], fl.ids[i] = table.data_ptr(), ids.data_ptr()
         fl.table_rows[i], fl.dim[i], fl.cat_col[i] = table.shape[0], table.shape[1], col
@@ -175,6 +177,8 @@ def embed_concat(cats: List[Tuple[torch.Tensor, torch.Tensor, int]], conts: List
     for i, (vals, col) in enumerate(conts):
         _need_cuda(vals)
         vals = _f32c(vals.reshape(-1))
+        if vals.numel() != M:
+            raise _lib.T4RError(f"embed_concat: continuous feature {i} carries {vals.numel()} values, expected M = {M}")
         keep.append(vals)
         fl.cont[i], fl.cont_col[i] = vals.data_ptr(), col
         dev = dev or vals.device
@@ -735,6 +739,8 @@ def sampled_ce_bwd(z, row_lse, labels, col_bias, col_ids, inv_tau, scale, _on_ho
 def index_add_rows(dst, idx, src, col, width, skip_index=None, _on_host=False):
     assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.shape[1] == width
     src, idx = _f32c(src), idx.long().contiguous()
+    if idx.numel() != src.shape[0]:
+        raise _lib.T4RError(f"index_add_rows: {idx.numel()} indices for {src.shape[0]} source rows")
     tail = _tr(_on_host, dst, idx, src)
     check(_lib.load().t4r_train_index_add_rows(ptr(dst), ptr(idx), ptr(src), idx.numel(), src.shape[1], int(col), int(width),
                                                -1 if skip_index is None else int(skip_index), *tail),

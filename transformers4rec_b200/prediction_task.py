@@ -399,6 +399,10 @@ class NextItemPredictionTask(PredictionTask):
 
     def _lazy_labels(self):
         T = int(self._last["count"].item())
+        if self._last.get("sampled"):
+            # model/prediction_task.py:693-696: with sampled softmax the positive sits in column 0 of the
+            # [T, 1 + S] predictions and the returned targets are all zero
+            return torch.zeros_like(self._last["labels"][:T])
         return self._last["labels"][:T]
 
     def _lazy_predictions(self):

@@ -23,12 +23,18 @@ class RankingMetric:
             self.top_ks = [self.top_ks]
         self.labels_onehot = labels_onehot
         self.metric_mean: List[torch.Tensor] = []
+        self.metric_rows: List[torch.Tensor] = []
 
     def reset(self):
         self.metric_mean = []
+        self.metric_rows = []
 
     def update_from_ranks(self, row_rank: torch.Tensor, t_dev: Optional[torch.Tensor] = None):
-        self.metric_mean.append(self._from_ranks(row_rank, t_dev))
+        m = self._from_ranks(row_rank, t_dev)
+        self.metric_mean.append(m)
+        # rows behind this batch's mean (device-side count when the caller has one: no host sync here)
+        rows = t_dev.reshape(-1)[:1].to(m.dtype) if t_dev is not None else m.new_full((1,), float(row_rank.numel()))
+        self.metric_rows.append(rows.to(m.device))
 
     def update(self, preds: torch.Tensor, target: torch.Tensor, **kwargs):
         """Materialised scores [T, V] + class-id labels [T]."""
@@ -46,8 +52,11 @@ class RankingMetric:
         return self.metric_mean[-1]
 
     def compute(self):
-        # ranking_metric.py:61-63: mean over batches of the per-batch means
-        return torch.stack(self.metric_mean, dim=0).mean(0)
+        # ranking_metric.py:61-63 concatenates the per-ROW results of every update and takes their mean: a
+        # row-weighted mean of the per-batch means (equal to the plain mean only when every batch has the same T)
+        means = torch.stack(self.metric_mean, dim=0)
+        rows = torch.cat(self.metric_rows).reshape(-1, 1)
+        return (means * rows).sum(0) / rows.sum().clamp(min=1.0)
 
     def _from_ranks(self, row_rank, t_dev):
         raise NotImplementedError

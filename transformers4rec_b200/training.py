@@ -424,7 +424,14 @@ class FusedTrainingStep:
         # K1 gather + concat (fp32 rows; the gather is recomputed in the backward instead of being kept)
         cats, conts = [], []
         for name, kind, col, width in (self.layout if self.wide is None else ()):
-            v = batch[name].reshape(-1)
+            v = batch[name]
+            if v.dim() == 1 or (v.dim() == 2 and v.shape[1] == 1 and L != 1):
+                # a context feature ([B] / [B, 1]) is repeated for every position, as in the forward-only path
+                # (features.py seq(); tabular/base.py:53-63 in the reference)
+                v = v.reshape(B, 1).expand(B, L)
+            v = v.reshape(-1)
+            if v.numel() != M:
+                raise ValueError(f"feature {name!r} has {v.numel()} values, expected batch x length = {M}")
             if kind == "cat":
                 cats.append((cm.embedding_tables[name].weight.detach(), v, col))
             else:
@@ -708,4 +715,8 @@ class FusedAdamW(torch.optim.Optimizer):
                                b1, b2, group["eps"], group["weight_decay"], st["step"])
                 if data.data_ptr() != p.data.data_ptr():
                     p.data.copy_(data)
+                else:
+                    # the kernel wrote through a raw pointer: tell torch (and with it every cache keyed on
+                    # ``param._version``, e.g. ops.PlaneCache's split planes of this weight) that the values moved
+                    torch.autograd.graph.increment_version(p)
         return loss
