@@ -6,7 +6,9 @@ rank per GPU) prints ONE JSON line from rank 0.  A "step" is one pass of the hot
 path (gather -> projection -> masking -> encoder -> tied-weight softmax CE) over one
 batch of synthetic yoochoose-shaped sessions.  Workload at every N: BASELINE.json
 configs[1] (1M-item table, L=20, XLNet d=256 x4, MLM, B=2048 per GPU; weak scaling,
-independent replicas -- sessions are independent, no data-path collective).
+independent replicas -- sessions are independent, no data-path collective).  After the
+headline, every N also times the ROW-SHARDED table + tied head of configs[3] and configs[4]
+ and reports them in the line's ``sharded`` record.
 
 ``--impl reference`` times the reference's own CPU implementation of the path (the
 oracle graph: stock torch ops + the Hugging Face encoder, all host threads) on a
@@ -66,10 +68,11 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def head_traffic():
+def head_traffic(resident=True):
     """dram__bytes_read.sum + dram__bytes_write.sum of the head GEMM from the committed ncu capture
-    (profiles/r1c_head_traffic.json; config2 only) -- None when no capture is on record."""
-    p = os.path.join(ROOT, "profiles", "r1c_head_traffic.json")
+    (profiles/r2_head_traffic.json for the resident-A kernel, r1c_head_traffic.json for the streaming one; config2
+    only) -- None when no capture is on record."""
+    p = os.path.join(ROOT, "profiles", "r2_head_traffic.json" if resident else "r1c_head_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)["dram_bytes_per_launch"]
@@ -297,9 +300,15 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sessions", type=int, default=64, help="sessions per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nprod", type=int, default=3, help="3 = fp32-grade split-bf16 product (parity, default), 2 = fp16 + two e4m3 cross terms in the "
-                         "training head (2 tensor units per MAC, opt-in), 1 = plain bf16")
+    ap.add_argument("--nprod", type=int, default=2,
+                    help="arithmetic of the training full-softmax head: 2 (the library default) = fp16 x fp16 + two e4m3 "
+                         "cross terms (2 tensor units per MAC; device-side error table: profiles/r2_head_precision.json), "
+                         "3 = split-bf16 x3, 1 = plain bf16")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="skip the `sharded` record (row-sharded configs 4 and 5 timed at this N after the headline)")
+    ap.add_argument("--sharded-timeout", type=float, default=240.0,
+                    help="seconds the sharded legs may take before the headline line is printed without them")
     ap.add_argument("--train", action="store_true",
                     help="time a TRAINING step instead (forward + backward through transformers4rec_b200.training + one "
                          "optimizer step); not BASELINE.json's metric -- the line says so in `metric`")
@@ -346,11 +355,106 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1 or cfg.get("sharded"):
+    want_sharded_record = (args.workload == "config2" and not args.train and not args.no_sharded)
+    if world > 1 or cfg.get("sharded") or want_sharded_record:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
+    peaks, peak_kind = load_peaks()
+
+    def emit(line):
+        print(json.dumps(line), flush=True)
+
+    res = run_workload(args, cfg, dev, rank, world, local_rank, config_desc, peaks, peak_kind, headline=True)
+    line = res["line"] if rank == 0 else None
+    if want_sharded_record:
+        # SURVEY 8e / VERDICT r1 item 1: the row-sharded table + tied head, timed at this N next to the headline.
+        # The headline above is already measured; whatever happens below (an exception, a hang) it is still printed.
+        done = threading.Event()
+
+        def watchdog():
+            if done.wait(args.sharded_timeout):
+                return
+            if rank == 0:
+                line["sharded"] = {"error": f"the sharded legs did not finish within {args.sharded_timeout} s"}
+                emit(line)
+            os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        rec = {}
+        for name in ("config4", "config5"):
+            try:
+                rec[name] = run_sharded_leg(args, name, dev, rank, world, peaks)
+            except Exception as exc:  # noqa: BLE001 -- recorded in the line; the headline stands on its own
+                rec[name] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+                break  # a CUDA error is sticky: do not try the next leg on a broken context
+        done.set()
+        if rank == 0:
+            line["sharded"] = rec
+    if rank == 0:
+        emit(line)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        try:
+            torch.distributed.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+N_ROTATE = 8   # distinct batches cycled through the timed loops: no step re-reads the table rows of the one before
+
+
+def _stage_times(model, batches, K):
+    """CUDA-event times (ms, mean over K steps) of the three stages of the forward on the current stream."""
+    head = model.heads[0]
+    inputs, tblock = head.body[0], head.body[1]
+    task = head.prediction_task_dict["next-item"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    with torch.no_grad():
+        for i in range(K):
+            b = batches[i % len(batches)]
+            ev[i][0].record()
+            x = inputs(b, training=True)
+            ev[i][1].record()
+            h = tblock(x)
+            ev[i][2].record()
+            task(h, training=True)
+            ev[i][3].record()
+    torch.cuda.synchronize()
+    return [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / K for j in range(3)]
+
+
+def _gather_time(model, cfg, batches, K):
+    """The embedding gather (K1) alone, as the model calls it, over rotating id sets (rows not L2-resident)."""
+    from transformers4rec_b200 import ops
+    cm = model.heads[0].body[0].categorical_module
+    names = sorted(cardinalities(cfg))
+    C = sum(cm.embedding_tables[n].weight.shape[1] for n in names)
+    M = batches[0][names[0]].numel()
+
+    def call(b):
+        cats, col = [], 0
+        for n in names:
+            w = cm.embedding_tables[n].weight.detach()
+            cats.append((w, b[n].reshape(-1), col))
+            col += w.shape[1]
+        return ops.embed_concat(cats, [], M, C, want_f32=False, want_planes=True)
+    for i in range(3):
+        call(batches[i % len(batches)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        call(batches[i % len(batches)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    F = len(names)
+    # SURVEY 8d: gather_bytes = B*L*(8F + 4*sum(De)) read + the planes written (2 x bf16 x round_up64(C) = ~4C)
+    nbytes = M * (8 * F + 4 * C) + M * 4 * ((C + 63) // 64 * 64)
+    return ms, nbytes
+
+
+def run_workload(args, cfg, dev, rank, world, local_rank, config_desc, peaks, peak_kind, headline):
     import transformers4rec_b200 as t4r
     from transformers4rec_b200 import ops
 
@@ -359,12 +463,13 @@ def main():
     task = model.heads[0].prediction_task_dict["next-item"]
     task.nprod = args.nprod
     B, L, V = cfg["B"], cfg["L"], cfg["V"]
-    batch_host = {k: v.pin_memory() for k, v in synth_batch(B, L, cfg, seed=rank).items()}
-    batch_dev = {k: v.to(dev) for k, v in batch_host.items()}
+    hosts = [{k: v.pin_memory() for k, v in synth_batch(B, L, cfg, seed=1000 * rank + j).items()} for j in range(N_ROTATE)]
+    devs = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
+    batch_host, batch_dev = hosts[0], devs[0]
     h2d_bytes = int(sum(v.numel() * v.element_size() for v in batch_host.values()))
 
-    def to_device():
-        return {k: v.to(dev, non_blocking=True) for k, v in batch_host.items()}
+    def to_device(j):
+        return {k: v.to(dev, non_blocking=True) for k, v in hosts[j % N_ROTATE].items()}
 
     train_step = opt = None
     if args.train:
@@ -392,11 +497,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # started before warm-up so samples exist even for a short timed region
-    for _ in range(max(args.warmup, 3)):
-        step(batch_dev)
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(devs[i % N_ROTATE])
     barrier()
 
-    # --- timed region 1: inputs resident in HBM
+    # --- timed region 1: inputs resident in HBM, N_ROTATE distinct batches cycled
     K = args.steps
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for a, b in evs:  # torch creates the cudaEvent_t lazily: record once so .cuda_event is a live handle
@@ -409,7 +515,7 @@ def main():
     e0.record()
     for i in range(K):
         ops.HEAD_EVENTS = evs[i]
-        step(batch_dev)
+        step(devs[i % N_ROTATE])
     e1.record()
     barrier()
     ops.HEAD_EVENTS = None
@@ -426,7 +532,7 @@ def main():
         try:
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph):
-                loss_static = step(batch_dev)
+                step(batch_dev)
             for _ in range(3):
                 gph.replay()
             barrier()
@@ -442,14 +548,24 @@ def main():
 
     # --- timed region 2: end to end through the public API with HOST inputs
     loss_host = 0.0
-    for _ in range(2):
-        loss_host = step(to_device()).item()
+    for j in range(2):
+        loss_host = step(to_device(j)).item()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        loss_host = step(to_device()).item()  # H2D + D2H every step
+    for j in range(K):
+        loss_host = step(to_device(j)).item()  # H2D + D2H every step
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+
+    # --- stage breakdown and the gather alone (CUDA events, rank 0's own stream; not part of `value`)
+    stages = gather = None
+    if not args.train and not cfg.get("sharded"):
+        try:
+            stages = _stage_times(model, devs, K)
+            gather = _gather_time(model, cfg, devs, max(K, 20))
+        except Exception as exc:  # noqa: BLE001 -- explanatory numbers never cost the line
+            stages = gather = None
+            print(f"[bench] stage breakdown skipped: {type(exc).__name__}: {exc}", file=sys.stderr)
 
     tt = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
@@ -457,41 +573,60 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(tt[0]), float(tt[1])
     if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
-        return
+        del model
+        torch.cuda.empty_cache()
+        return {"line": None}
 
     ms_per_step = ms_total / K
     value = B * world / (ms_per_step / 1e3)
     e2e_value = B * world / (e2e_ms / K / 1e3)
-    peaks, peak_kind = load_peaks()
     head_flops = 2.0 * T * V * cfg["De"]  # algorithmic (head_flop = 2*T*V*De)
     if cfg.get("sharded"):  # per launch: the label rows of ALL ranks against this rank's V/world table rows
         head_flops = 2.0 * (T * world) * (V / world) * cfg["De"]
     if cfg.get("sampled"):  # 2*T*(S+1)*De with S = the negatives that survived unique()[:S]
         head_flops = 2.0 * T * (int(task._last["neg"].numel()) + 1) * cfg["De"]
     achieved_tf = head_flops / (head_ms_avg * 1e-3) / 1e12
-    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    head_kernel = ("head_resident_kernel (CTA-pair tcgen05 GEMM with the A tile resident in shared memory: tied logits + "
-                   "online LSE)" if os.environ.get("T4R_HEAD_RESIDENT") == "1" and cfg["De"] <= 256 else
+    peak_tf = float(peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained")))
+    resident = os.environ.get("T4R_HEAD_RESIDENT", "1") != "0" and cfg["De"] <= 256 and not cfg.get("sampled")
+    head_kernel = ("head_resident_kernel (CTA-pair tcgen05 GEMM, A tile resident in shared memory: tied logits + "
+                   "online LSE)" if resident else
                    "gemm2_bf16x3_kernel<256,false,true> (CTA-pair tcgen05 GEMM: tied logits + online LSE)")
     roofline = {"bound": "tensor", "kernel": head_kernel,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step)",
-                "traffic": head_traffic() if args.workload == "config2" else None, "launch_ms": head_ms_avg, "share_of_step": head_ms_avg / ms_per_step,
+                "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops (burst: the timed region is a fraction of a "
+                               f"second; sustained {peaks.get('bf16_tflops_sustained')} would give "
+                               f"{achieved_tf / float(peaks.get('bf16_tflops_sustained', peak_tf)):.3f})",
+                "traffic": head_traffic(resident) if args.workload == "config2" else None, "launch_ms": head_ms_avg,
+                "share_of_step": head_ms_avg / ms_per_step,
                 "algorithmic_flops_per_launch": head_flops, "label_rows_T": T,
                 "note": {3: "split-bf16 x3 issues 3 tensor-core MACs per algorithmic MAC: frac <= 1/3 by construction",
                          2: "fp16 + 2 x e4m3 cross terms: 2 bf16-equivalent tensor passes per MAC: frac <= 1/2",
                          1: "plain bf16 product"}[args.nprod]}
     line = {"metric": METRIC if not args.train else "sessions/sec (fwd+bwd+%s step; NOT the BASELINE metric)" % args.optimizer, "value": value, "unit": "sessions/s", "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {3: "f32 (bf16 hi/lo split operands on tcgen05, fp32 accumulate)",
                                            2: "f32 (head: fp16 + e4m3 cross terms on tcgen05; rest bf16 hi/lo split)",
                                            1: "bf16"}[args.nprod], "data": "synthetic", "config": config_desc, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "sessions/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "loss": loss_host},
             "gpu_launches": int(n1 - n0), "roofline": roofline}
+    if stages is not None:
+        enc_flops = cfg["NL"] * B * L * (24 * cfg["d"] ** 2 + 8 * L * cfg["d"])      # SURVEY §8d enc_flop
+        enc_tf = enc_flops / (stages[1] * 1e-3) / 1e12
+        line["stages_ms"] = {"input_block": stages[0], "encoder": stages[1], "head": stages[2],
+                             "how": "CUDA events between the three module calls, mean over the timed steps, separate pass"}
+        line["roofline_encoder"] = {"bound": "tensor", "achieved": enc_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": enc_tf / peak_tf, "ms": stages[1], "algorithmic_flops": enc_flops,
+                                    "note": "whole encoder (QKV, relative attention, O-proj + LN, fused FFN; 3 tensor "
+                                            "passes per MAC in the GEMMs); tensor-pipe % per kernel: profiles/ ncu summaries"}
+    if gather is not None:
+        g_ms, g_bytes = gather
+        hbm = float(peaks.get("hbm_gbs", 6482.4))
+        line["roofline_gather"] = {"bound": "hbm", "kernel": "embed_concat_kernel", "achieved": g_bytes / (g_ms * 1e-3) / 1e9,
+                                   "peak": hbm, "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm,
+                                   "launch_ms": g_ms, "algorithmic_bytes_per_launch": g_bytes,
+                                   "how": f"{N_ROTATE} distinct id sets cycled, launches back to back on one stream, "
+                                          f"CUDA events around the loop"}
     if graph_ms is not None:
         line["cuda_graph"] = {"ms_per_step": graph_ms, "value": (B * world / (graph_ms / 1e3)) if isinstance(graph_ms, float) else None}
     if not args.no_cpu_baseline and world == 1:
@@ -505,10 +640,147 @@ def main():
             line["recall_at_20"] = recall_agreement(cfg, model, batch_dev, batch_host)
         except Exception as exc:  # an accuracy side-note must never cost the throughput line
             line["recall_at_20"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    del model
+    torch.cuda.empty_cache()
+    return {"line": line}
+
+
+SHARDED_LEGS = {
+    # BASELINE.json configs[3]: 10M-row table, block-sharded over the N ranks (N = 1: the whole table on one GPU),
+    # tied full-softmax head, B = 2048 per GPU.  Per-rank head work T_global * V / N is constant in N: weak scaling.
+    "config4": dict(V=10_000_001, De=256, d=256, H=8, NL=4, L=20, B=2048, arch="xlnet", masking="mlm", sharded=True),
+    # BASELINE.json configs[4]: 50M-row table sharded over the N ranks, sampled softmax with 50K negatives, L = 50.
+    "config5": dict(V=50_000_001, De=256, d=256, H=8, NL=4, L=50, B=2048, arch="xlnet", masking="mlm", sharded=True,
+                    sampled=50_000),
+}
+
+
+def _time_loop(fn, K, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / K
+
+
+def run_sharded_leg(args, name, dev, rank, world, peaks):
+    """One row-sharded workload at this N: whole-step sessions/s (max over ranks) plus the pieces that move data
+    between GPUs, each timed alone with CUDA events: the peer-memory lookup, the label-row pull, the two 4-byte
+    ordering collectives -- and the head GEMM's own time from its event pair."""
+    import torch.distributed as dist
+
+    from transformers4rec_b200 import distributed as D
+    from transformers4rec_b200 import ops
+    cfg = dict(SHARDED_LEGS[name])
+    B, L, V, De = cfg["B"], cfg["L"], cfg["V"], cfg["De"]
+    model = build_product_model(cfg, dev)
+    task = model.heads[0].prediction_task_dict["next-item"]
+    task.nprod = args.nprod
+    inputs = model.heads[0].body[0]
+    table = inputs.categorical_module.embedding_tables["item_id/list"]
+    devs = [{k: v.to(dev) for k, v in synth_batch(B, L, cfg, seed=1000 * rank + j).items()} for j in range(N_ROTATE)]
+
+    def step(i):
+        with torch.no_grad():
+            return model(devs[i % N_ROTATE], training=True)["loss"]
+    K = max(3, min(args.steps, 10))
+    for i in range(3):
+        step(i)
+    dist.barrier(); torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in evs:
+        a.record(); b.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    loss = None
+    for i in range(K):
+        ops.HEAD_EVENTS = evs[i]
+        loss = step(i)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ops.HEAD_EVENTS = None
+    ms = e0.elapsed_time(e1) / K
+    head_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    T = int(task._last["count"].item())
+    peer = table.peer_view() is not None
+    rec = {"exchange": "nvlink peer memory (t4r_peer_* kernels)" if peer else "nccl all-gather + all-to-all"}
+    # pieces, each alone
+    n_ids = B * L
+    ids_flat = devs[0]["item_id/list"].reshape(-1)
+    lookup_ms = _time_loop(lambda: table.lookup(ids_flat), 10)
+    rec["lookup"] = {"ms": lookup_ms, "rows": n_ids, "bytes": n_ids * De * 4,
+                     "remote_bytes": int(n_ids * De * 4 * (world - 1) / world * 0.55),
+                     "note": "item rows of one batch from their owners' shards; ~45 % of the positions are the padding id, "
+                             "served from a per-CTA copy of that row (remote_bytes counts the other 55 % x (N-1)/N)"}
+    if cfg.get("sampled"):
+        S = int(task._last["S"])
+        neg = torch.randint(1, V, (S,), device=dev)
+        neg_ms = _time_loop(lambda: table.lookup(neg), 10)
+        rec["negatives_lookup"] = {"ms": neg_ms, "rows": S, "bytes": S * De * 4,
+                                   "remote_bytes": int(S * De * 4 * (world - 1) / world)}
+        head_flops = 2.0 * T * (S + 1) * De
+        colls = ["broadcast of the raw negative draws (2 x 50 000 int64)", "all-reduce of (sum of row losses, T)"]
+    else:
+        ph = getattr(task, "_peer_head_state", None)
+        if peer and ph is not None and ph.ok:
+            cnt = task._last["count"]
+            pull_ms = _time_loop(lambda: ops.peer_pull_rows(ph.views[0], ph.views[1], ph.counts, ph.cap, De), 10)
+            bar_ms = _time_loop(lambda: (dist.all_gather_into_tensor(ph.counts, cnt.reshape(1).to(torch.int32), group=ph.group),
+                                         dist.all_reduce(ph.token, group=ph.group)), 10)
+            t_tot = int(ph.counts.sum().item())
+            rec["label_row_pull"] = {"ms": pull_ms, "rows": t_tot, "bytes": t_tot * De * 4,
+                                     "remote_bytes": int((t_tot - T) * De * 4)}
+            rec["stats_exchange"] = {"bytes": t_tot * 12 * max(world - 1, 0),
+                                     "note": "peer_combine_lse reads 12 B per row from every other shard; its time is "
+                                             "inside ms_per_step"}
+            rec["ordering_collectives"] = {"ms": bar_ms, "bytes": 8,
+                                           "what": "4-byte all-gather of the label-row counts + 4-byte all-reduce"}
+            colls = ["all-gather of counts (4 B)", "all-reduce token (4 B)"]
+        else:
+            colls = ["all-gather of ids", "all-to-all of rows", "all-gather of counts", "all-gather of label rows",
+                     "all-gather of labels", "all-gather of (lse, label logit)"]
+        head_flops = 2.0 * (T * world) * (V / world) * De
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0])
+    value = B * world / (ms / 1e3)
+    peak_tf = float(peaks.get("bf16_tflops", 1719.6))
+    rec.update({"workload": f"BASELINE.json {name}: {V:,}-row item table row-sharded over {world} rank(s), "
+                            + ("sampled softmax 50 000 negatives, seq_len=50" if cfg.get("sampled") else "tied full softmax, seq_len=20")
+                            + f", XLNet-base d=256 x4, MLM, batch={B} per GPU",
+                "value": value, "unit": "sessions/s", "ms_per_step": ms, "steps": K, "n_gpus": world,
+                "rows_per_rank": table.weight.shape[0], "label_rows_T_this_rank": T, "loss": float(loss),
+                "head_gemm_ms": head_ms, "head_tflops_algorithmic": head_flops / (head_ms * 1e-3) / 1e12,
+                "head_frac_of_bf16_peak": head_flops / (head_ms * 1e-3) / 1e12 / peak_tf,
+                "nccl_collectives_per_step": colls, "scaling": "weak"})
+    # own efficiency v_N / (N * v_1): v_1 is read from the N = 1 run of the same session when it left its note
+    note = os.path.join(ROOT, ".bench_sharded_n1.json")
+    try:
+        if rank == 0 and world == 1:
+            prev = {}
+            if os.path.exists(note):
+                with open(note) as f:
+                    prev = json.load(f)
+            prev[name] = value
+            with open(note, "w") as f:
+                json.dump(prev, f)
+        if rank == 0 and world > 1 and os.path.exists(note):
+            with open(note) as f:
+                v1 = json.load(f).get(name)
+            if v1:
+                rec["efficiency_vs_n1"] = value / (world * v1)
+                rec["v1"] = v1
+    except Exception:  # noqa: BLE001
+        pass
+    del model, table, inputs, task
+    torch.cuda.empty_cache()
+    return rec
 
 
 if __name__ == "__main__":

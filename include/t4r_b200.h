@@ -509,6 +509,53 @@ int t4r_topk(const float* logits, int64_t rows, int64_t V, int64_t ld, int k, fl
 int t4r_combine_shard_lse(const float* parts, int world, int T_cap, const int32_t* t_dev, float* row_loss,
                           float* loss, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * K11 / K12 over NVLink PEER MEMORY (csrc/t4r_peer.cu): the row-sharded item table and tied head of
+ * BASELINE configs 4-5 with one process per GPU.  The reference replicates the table on every
+ * rank (DDP only, docs/source/multi_gpu_train.md:5-50; nn.Embedding features/embedding.py:226-249 and the
+ * tied logits model/prediction_task.py:648-671); here rank r holds rows [r * rows_per_shard, ...) and every
+ * rank maps its peers' shards and two small per-step windows through CUDA IPC, so that the kernels below read
+ * remote rows with plain loads over NVLink -- no bulk collective, no routing plan, exactly the needed bytes.
+ * ------------------------------------------------------------------------- */
+#define T4R_MAX_PEERS 16
+#define T4R_PEER_HANDLE_BYTES 64
+/* the same buffer on every rank of a group, as seen from THIS process: base[rank] is the local allocation,
+ * the others are mappings obtained with t4r_peer_open (in a single-process test they may all be local). */
+typedef struct {
+  const void* base[T4R_MAX_PEERS];
+  int world;
+  int rank;
+} t4r_peer_ptrs;
+/* Export the cudaMalloc'ed allocation that contains dev_ptr: handle_out (host, 64 bytes) is sent to the peers
+ * (any byte transport), offset_out (host) is dev_ptr's offset inside that allocation. */
+int t4r_peer_export(const void* dev_ptr, void* handle_out /*host*/, int64_t* offset_out /*host*/);
+/* Map a peer's exported allocation into this process (cudaIpcOpenMemHandle, lazy peer access);
+ * *mapped_out = the peer's dev_ptr as addressable here.  Not for handles of this same process. */
+int t4r_peer_open(const void* handle /*host*/, int64_t offset, void** mapped_out /*host*/);
+int t4r_peer_close(void* mapped, int64_t offset);
+/* out[i] = row ids[i] of the sharded table (owner = min(id / rows_per_shard, world - 1)) for i < *count_dev
+ * (all `cap` rows when NULL; with a count, rows from it up to the next multiple of 256 are zero and the rest of
+ * the outputs is left untouched).  K % 4 == 0, K <= 1024.  pad_id (-1: none): that row is read
+ * once per CTA and served from shared memory.  out_f32 [cap, K] and / or out_planes bf16 [2, cap, round_up64(K)].
+ * err_flag (optional) is set to 1 on ids outside [0, V) (their rows are zero). */
+int t4r_peer_gather_rows(const t4r_peer_ptrs* shards /*host*/, int64_t V, int64_t rows_per_shard, int K,
+                         const int64_t* ids, const int32_t* count_dev, int cap, int64_t pad_id, float* out_f32,
+                         void* out_planes, int32_t* err_flag, void* stream);
+/* Pull the label rows of every rank into one compact operand: mail_x->base[r] = fp32 [cap, K] rows of rank r,
+ * mail_y->base[r] = int64 [cap] labels, counts [world] (DEVICE, e.g. the output of a 4-byte all-gather) the
+ * number of valid rows per rank.  Rank-major concatenation -> out_f32 [world*cap, K] (optional), out_planes
+ * bf16 [2, world*cap, round_up64(K)] (optional), out_labels [world*cap]; *t_total = sum(counts),
+ * *my_start = first row of this rank (optional); rows up to round_up(t_total, 256) are zeroed. */
+int t4r_peer_pull_rows(const t4r_peer_ptrs* mail_x /*host*/, const t4r_peer_ptrs* mail_y /*host*/,
+                       const int32_t* counts, int cap, int K, float* out_f32, void* out_planes, int64_t* out_labels,
+                       int32_t* t_total, int32_t* my_start, void* stream);
+/* stats->base[s] = fp32 [3, cap_g] of shard s: row log-sum-exp over the shard's classes | label logit (0 when
+ * the label lives elsewhere) | int32 count of the shard's classes scoring above the label.  row_loss [cap_g] =
+ * logsumexp_s(lse_s) - sum_s(tgt_s) for rows < *t_total (0 beyond), row_rank [cap_g] = sum_s(count_s) when
+ * with_rank, loss (optional) = mean of row_loss over the *t_total rows. */
+int t4r_peer_combine_lse(const t4r_peer_ptrs* stats /*host*/, int64_t cap_g, const int32_t* t_total, int with_rank,
+                         float* row_loss, int32_t* row_rank, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
-"""2-GPU NCCL test of the row-sharded table + sharded head with the real
-CUDA kernels: lookup bit-exact against the replicated table, loss against the
-single-process oracle on the global batch.  Skipped with fewer than 2 GPUs."""
+"""Multi-process tests of the row-sharded table + sharded head with the real CUDA kernels: lookup bit-exact
+against the replicated table, loss / Recall@k against the single-process oracle on the GLOBAL batch.  Both formulations
+run: ``peer`` = NVLink peer memory (csrc/t4r_peer.cu, the default on GPUs) and ``nccl`` = all-gather + all-to-all
+(``T4R_PEER=0``).  World size 2 needs 2 GPUs (skipped otherwise); world size 1 runs the same code path -- process group,
+IPC export, windows, device-side counts -- on a single GPU, so the driver's one-GPU box covers it too."""
 import os
 
 import pytest
@@ -27,6 +29,25 @@ def _labels(rank):
     g = torch.Generator().manual_seed(20 + rank)
     T = 40 + 17 * rank
     return torch.randn((T, De), generator=g), torch.randint(1, V, (T,), generator=g)
+
+
+def _worlds():
+    return [pytest.param(1, id="world1"),
+            pytest.param(2, id="world2", marks=pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs"))]
+
+
+def _run(target, world, port, extra=(), timeout=600):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=target, args=(r, world, port, q) + tuple(extra)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=timeout) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
 
 
 def _worker(rank, world, port, q):
@@ -56,24 +77,22 @@ def _worker(rank, world, port, q):
         start = sum(x.shape[0] for x in xs[:rank])
         err_rows = (row_loss.cpu() - ref_rows[start:start + xt.shape[0]]).abs().max().item()
         err_loss = abs(loss.item() - ref_rows.mean().item())
+        # the same lookup over peer memory (the module's default on GPUs): bit-exact too, incl. a device-side count
+        emb = D.ShardedEmbedding.from_full(table.cuda())
+        assert emb.peer_view() is not None, "peer memory should be available between the GPUs of one box"
+        prow, pplanes = emb.lookup(ids.cuda())
+        ok_lookup = ok_lookup and torch.equal(prow.cpu(), ref) and torch.equal(pplanes.cpu(), planes.cpu())
+        cnt = torch.tensor([77], dtype=torch.int32, device="cuda")
+        crow, _ = emb.lookup(ids.cuda(), count=cnt)
+        ok_lookup = ok_lookup and torch.equal(crow[:77].cpu(), ref[:77]) and not crow[77:256].any()
         q.put((rank, ok_lookup, ok_planes, err_rows, err_loss, T_total == xg.shape[0]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_lookup_and_head_nccl():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+@pytest.mark.parametrize("world", _worlds())
+def test_sharded_lookup_and_head_nccl(world):
+    res = _run(_worker, world, 29600 + (os.getpid() % 1000) + 7 * world, timeout=300)
     for rank, ok_lookup, ok_planes, err_rows, err_loss, ok_T in res:
         assert ok_lookup and ok_planes and ok_T, f"rank {rank}: lookup/planes/T mismatch"
         assert err_rows < 1e-3 and err_loss < 1e-4, f"rank {rank}: loss rows {err_rows} mean {err_loss}"
@@ -85,9 +104,10 @@ def test_sharded_lookup_and_head_nccl():
 # CPU oracle on the GLOBAL batch ("multi-GPU parity is defined against the single-process
 # oracle on the global batch")
 # --------------------------------------------------------------------------- #
-def _model_worker(rank, world, port, q, sampled):
+def _model_worker(rank, world, port, q, sampled, peer):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
+    os.environ["T4R_PEER"] = "1" if peer else "0"
     import torch.distributed as dist
 
     import t4r_oracle as O
@@ -129,28 +149,22 @@ def _model_worker(rank, world, port, q, sampled):
                 ref_rec = O.recall_at_mean([1, 5, 20], ref_e["predictions"][mine], ref_e["labels"][mine])
                 import transformers4rec_b200.torch as tr
                 m = tr.RecallAt(top_ks=[1, 5, 20], labels_onehot=True)
-                m.update_from_ranks(out_e.row_rank, None)
+                m.update_from_ranks(out_e.row_rank, out_e.count)
                 res["recall"] = (m.metric_mean[-1].cpu() - ref_rec).abs().max().item()
+        res["peer"] = inputs.categorical_module.embedding_tables["item_id/list"].peer_view() is not None
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("sampled", [False, True])
-def test_model_over_sharded_item_table_nccl(sampled):
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + (50 if sampled else 0)
-    procs = [ctx.Process(target=_model_worker, args=(r, 2, port, q, sampled)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+@pytest.mark.parametrize("world", _worlds())
+@pytest.mark.parametrize("peer", [True, False], ids=["peer", "nccl"])
+@pytest.mark.parametrize("sampled", [False, True], ids=["full", "sampled"])
+def test_model_over_sharded_item_table_nccl(sampled, peer, world):
+    port = 29700 + (os.getpid() % 1000) + (50 if sampled else 0) + (11 if peer else 0) + 3 * world
+    res = _run(_model_worker, world, port, extra=(sampled, peer))
     for rank, r in res:
+        assert r["peer"] == peer, (rank, r)
         assert r["train"] < 1e-3, (rank, r)
         if not sampled:
             assert r["eval"] < 1e-3 and r["recall"] < 1e-6, (rank, r)
@@ -190,18 +204,8 @@ def _topk_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_topk_over_sharded_item_table_nccl():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29800 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_topk_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+@pytest.mark.parametrize("world", _worlds())
+def test_topk_over_sharded_item_table_nccl(world):
+    res = _run(_topk_worker, world, 29800 + (os.getpid() % 1000) + 5 * world)
     for rank, err, agree, sorted_desc in res:
         assert err < 1e-3 and agree > 0.98 and sorted_desc, (rank, err, agree, sorted_desc)

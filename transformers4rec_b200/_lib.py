@@ -126,6 +126,13 @@ class HeadArgs(C.Structure):
     ]
 
 
+T4R_MAX_PEERS, T4R_PEER_HANDLE_BYTES = 16, 64
+
+
+class PeerPtrs(C.Structure):
+    _fields_ = [("base", c_void_p * T4R_MAX_PEERS), ("world", c_int), ("rank", c_int)]
+
+
 # name -> (restype, argtypes); every symbol include/t4r_b200.h declares
 _P = c_void_p
 SIGNATURES = {
@@ -194,6 +201,12 @@ SIGNATURES = {
     "t4r_recall_from_ranks": (c_int, [_P, _P, c_int, C.POINTER(C.c_int32), c_int, _P, _P]),
     "t4r_topk": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "t4r_combine_shard_lse": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "t4r_peer_export": (c_int, [_P, _P, C.POINTER(c_int64)]),
+    "t4r_peer_open": (c_int, [_P, c_int64, C.POINTER(c_void_p)]),
+    "t4r_peer_close": (c_int, [_P, c_int64]),
+    "t4r_peer_gather_rows": (c_int, [C.POINTER(PeerPtrs), c_int64, c_int64, c_int, _P, _P, c_int, c_int64, _P, _P, _P, _P]),
+    "t4r_peer_pull_rows": (c_int, [C.POINTER(PeerPtrs), C.POINTER(PeerPtrs), _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "t4r_peer_combine_lse": (c_int, [C.POINTER(PeerPtrs), c_int64, _P, c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

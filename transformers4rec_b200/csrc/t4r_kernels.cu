@@ -1040,6 +1040,12 @@ combine_shard_lse_kernel(const float* __restrict__ parts, int world, int T_cap, 
   row_loss[row] = (m + logf(s)) - tgt;
 }
 
+int launch_mean_rows(const float* rows, int cap, const int32_t* t_dev, float* out, cudaStream_t s) {
+  mean_rows_kernel<<<1, 1024, 0, s>>>(rows, cap, t_dev, out);
+  T4R_LAUNCH_CHECK("mean_rows_kernel");
+  return 0;
+}
+
 }  // namespace t4r
 
 extern "C" int t4r_recall_from_ranks(const int32_t* row_rank, const int32_t* t_dev, int T_cap, const int32_t* ks,

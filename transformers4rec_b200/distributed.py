@@ -325,6 +325,159 @@ def sharded_softmax_ce_train(xt: torch.Tensor, labels: torch.Tensor, local_table
     return loss, dx[start:start + counts_l[rank]].contiguous(), dW
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# NVLink peer memory (csrc/t4r_peer.cu): the product path on GPUs.  One process per GPU; every rank maps its peers'
+# buffers through CUDA IPC once, after which the kernels read remote rows with plain loads -- no bulk collective.
+# ---------------------------------------------------------------------------------------------------------------
+_OPENED: dict = {}   # exported-allocation handle (bytes) -> base address of its mapping in this process
+
+
+def peer_memory_available(t: torch.Tensor, group=None) -> bool:
+    """CUDA tensor + NCCL backend + not switched off (``T4R_PEER=0`` keeps the NCCL all-to-all formulation)."""
+    import os
+    return bool(t.is_cuda and dist.is_initialized() and dist.get_backend(group) == "nccl"
+                and os.environ.get("T4R_PEER", "1") != "0")
+
+
+class PeerView:
+    """The same buffer on every rank of ``group`` as addressable from THIS process: ``local`` is this rank's tensor
+    (any cudaMalloc'ed torch tensor; it must stay alive and in place), the others are CUDA-IPC mappings of the peers'.
+    Construction is a collective (one all-gather of 72 bytes per rank) and synchronises with the host; it happens once
+    per buffer, not per step.  ``struct`` is the ``t4r_peer_ptrs`` the kernels take."""
+
+    def __init__(self, local: torch.Tensor, group=None):
+        import ctypes as C
+
+        from . import _lib
+        if not local.is_cuda or not local.is_contiguous():
+            raise _lib.T4RError("PeerView needs a contiguous CUDA tensor")
+        lib = _lib.load()
+        self.local, self.group = local, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.T4R_MAX_PEERS:
+            raise _lib.T4RError(f"peer windows support up to {_lib.T4R_MAX_PEERS} ranks per group")
+        hb = _lib.T4R_PEER_HANDLE_BYTES
+        handle = (C.c_ubyte * hb)()
+        off = C.c_int64(0)
+        _lib.check(lib.t4r_peer_export(local.data_ptr(), handle, C.byref(off)), "t4r_peer_export")
+        mine = torch.tensor(list(bytes(handle)) + list(int(off.value).to_bytes(8, "little")), dtype=torch.uint8,
+                            device=local.device)
+        allh = _all_gather(mine, self.world, group).cpu()
+        self.ptr_of_rank = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptr_of_rank.append(local.data_ptr())
+                continue
+            raw = bytes(allh[r].tolist())
+            h, o = raw[:hb], int.from_bytes(raw[hb:hb + 8], "little")
+            base = _OPENED.get(h)
+            if base is None:   # an allocation can be opened once per process: keep the mapping for later views
+                out = C.c_void_p()
+                _lib.check(lib.t4r_peer_open((C.c_ubyte * hb).from_buffer_copy(h), 0, C.byref(out)), "t4r_peer_open")
+                base = _OPENED[h] = int(out.value)
+            self.ptr_of_rank.append(base + o)
+        self.struct = _lib.PeerPtrs()
+        self.struct.world, self.struct.rank = self.world, self.rank
+        for r, p in enumerate(self.ptr_of_rank):
+            self.struct.base[r] = p
+        self.local_ptr = local.data_ptr()
+
+    def still_valid(self) -> bool:
+        return self.local.data_ptr() == self.local_ptr
+
+
+def _try_peer_view(local: torch.Tensor, group, what: str):
+    """PeerView or None -- the SAME answer on every rank (a failed mapping anywhere turns the feature off everywhere)."""
+    import logging
+    view, err = None, ""
+    try:
+        view = PeerView(local, group)
+    except Exception as exc:  # noqa: BLE001 -- the reason is logged; the NCCL formulation takes over
+        err = f"{type(exc).__name__}: {exc}"
+    ok = torch.tensor([1 if view is not None else 0], dtype=torch.int32, device=local.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        logging.getLogger("transformers4rec_b200").warning(
+            "peer memory is not available for %s (%s): using the NCCL all-to-all formulation", what, err or "a peer failed")
+        return None
+    return view
+
+
+class PeerHead:
+    """Per-step windows of the row-sharded full-softmax head over peer memory.
+
+    ``mail_x`` fp32 [cap, De] / ``mail_y`` int64 [cap]: this rank's label rows for the peers to pull;
+    ``stats`` fp32 [3, world*cap]: this shard's (lse, label logit, rank count) for ALL label rows, for the peers to
+    read.  One step on every rank, in stream order:
+
+        write mail            (gather_rows_split / compact_targets write straight into the window)
+        B1: all-gather of the 4-byte counts      -> every peer's mail is complete, counts on the device
+        pull                  (peer_pull_rows: exactly counts[r] rows from rank r, planes emitted in the same pass)
+        head                  (logits + online LSE over the local V/world rows; statistics into ``stats``)
+        B2: 4-byte all-reduce                    -> every peer's statistics are complete
+        combine               (peer_combine_lse reads all shards' statistics)
+
+    Write-after-read safety: a rank overwrites its mail for step i+1 only after its own B2(i), which cannot complete
+    before every peer has entered B2(i), i.e. after every peer's pull(i); it overwrites its statistics in head(i+1)
+    only after its own B1(i+1), which every peer enters after its combine(i).  No host synchronisation anywhere."""
+
+    def __init__(self, cap: int, De: int, device, group=None):
+        self.cap, self.De, self.group = int(cap), int(De), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap_g = self.world * self.cap
+        self.mail_x = torch.zeros((self.cap, De), dtype=torch.float32, device=device)
+        self.mail_y = torch.zeros((self.cap,), dtype=torch.int64, device=device)
+        self.stats = torch.zeros((3, self.cap_g), dtype=torch.float32, device=device)
+        self.views = None
+        caps = _all_gather(torch.tensor([self.cap, De], dtype=torch.int64, device=device), self.world, group).cpu()
+        if not bool((caps == caps[0]).all()):
+            raise RuntimeError(f"the row-sharded head needs the same batch x length capacity on every rank, got {caps.tolist()}")
+        vx = _try_peer_view(self.mail_x, group, "the head's label-row window")
+        vy = _try_peer_view(self.mail_y, group, "the head's label window") if vx is not None else None
+        vs = _try_peer_view(self.stats, group, "the head's statistics window") if vy is not None else None
+        if vs is not None:
+            self.views = (vx, vy, vs)
+        self.counts = torch.zeros(self.world, dtype=torch.int32, device=device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    @property
+    def ok(self) -> bool:
+        return self.views is not None
+
+
+def peer_softmax_ce(ph: PeerHead, count: torch.Tensor, local_table: torch.Tensor, V: int, w_planes=None,
+                    inv_tau: float = 1.0, want_rank: bool = False, rank_tgt_fn: Optional[Callable] = None,
+                    head_rows: Optional[Callable] = None):
+    """Full-softmax CE of the label rows of ALL ranks against the row-sharded output table, over peer memory.
+    The caller has written this rank's label rows / labels into ``ph.mail_x`` / ``ph.mail_y`` and holds their count
+    on the device (``count`` int32 [1]).  ``rank_tgt_fn(x_all, y_all, t_total)`` (evaluation) returns the labels'
+    logits over the WHOLE table.  Returns dict(loss [1], row_loss [cap_g], row_rank or None, t_total, my_start):
+    rows of all ranks, rank-major; this rank's rows start at ``my_start`` (device scalars -- nothing syncs)."""
+    from . import ops
+    vx, vy, vs = ph.views
+    rank, world = ph.rank, ph.world
+    dist.all_gather_into_tensor(ph.counts, count.reshape(1).to(torch.int32), group=ph.group)          # B1
+    pulled = ops.peer_pull_rows(vx, vy, ph.counts, ph.cap, ph.De, want_f32=True)
+    xg, yg, t_total = pulled["x"], pulled["labels"], pulled["t_total"]
+    lo, _ = shard_bounds(V, rank, world)
+    if w_planes is None:
+        w_planes = ops.split_planes(local_table)
+    rank_tgt = rank_tgt_fn(xg, yg, t_total) if want_rank else None
+    if head_rows is not None:
+        head_rows(pulled, w_planes, lo, inv_tau, rank_tgt, ph.stats)
+    elif isinstance(w_planes, tuple):   # the 2-unit product: (mixed planes, inverse row scales)
+        xm, xi = ops.split_planes_mixed(xg)
+        ops.head_softmax_ce(xm, xg, yg, w_planes[0], local_table, t_dev=t_total, inv_temperature=inv_tau, v_offset=lo,
+                            want_loss=False, want_rank=want_rank, rank_tgt=rank_tgt, nprod=2, xt_inv_scale=xi,
+                            w_inv_scale=w_planes[1], out_stats=ph.stats)
+    else:
+        ops.head_softmax_ce(pulled["planes"], xg, yg, w_planes, local_table, t_dev=t_total, inv_temperature=inv_tau,
+                            v_offset=lo, want_loss=False, want_rank=want_rank, rank_tgt=rank_tgt, out_stats=ph.stats)
+    dist.all_reduce(ph.token, group=ph.group)                                                           # B2
+    row_loss, loss, row_rank = ops.peer_combine_lse(vs, ph.cap_g, t_total, with_rank=want_rank)
+    return {"loss": loss, "row_loss": row_loss, "row_rank": row_rank, "t_total": t_total, "my_start": pulled["my_start"]}
+
+
 class ShardedEmbedding(torch.nn.Module):
     """Rows [lo, hi) of an item table of ``num_embeddings`` rows, block-partitioned over the process
     group: the drop-in for the item feature's ``nn.Embedding`` (and, under weight tying, for the output
@@ -344,6 +497,10 @@ class ShardedEmbedding(torch.nn.Module):
         # local compute steps of the exchange; None = the CUDA kernels (the gloo tests inject stand-ins)
         self.gather_rows: Optional[Callable] = None
         self.place: Optional[Callable] = None
+        # peer-memory view of all shards (set up lazily at the first lookup on GPUs; None = NCCL all-to-all)
+        self._peer: Optional[PeerView] = None
+        self._peer_tried = False
+        self._peer_version = -1
 
     @classmethod
     def from_full(cls, full_weight: torch.Tensor, group=None, padding_idx: int = 0) -> "ShardedEmbedding":
@@ -354,12 +511,46 @@ class ShardedEmbedding(torch.nn.Module):
             m.weight.copy_(full_weight[m.lo:m.hi])
         return m
 
-    def lookup(self, ids: torch.Tensor, ragged: bool = False, plan_out: Optional[list] = None):
-        """-> (rows fp32 [ids.numel(), dim], split planes) for arbitrary global ids (one all-gather of the
-        ids + one all-to-all of the rows).  ``ragged``: the ranks pass different numbers of ids (label
-        rows); they are padded to the longest with the padding id for the exchange."""
+    @property
+    def rows_per_shard(self) -> int:
+        return (self.num_embeddings + self.world - 1) // self.world
+
+    def peer_view(self) -> Optional[PeerView]:
+        """The shards of all ranks as peer memory, or None when that is not available (CPU / gloo tests, T4R_PEER=0,
+        a failed mapping).  The first call on a CUDA weight is a collective."""
+        w = self.weight
+        if self._peer is not None and not self._peer.still_valid():
+            self._peer, self._peer_tried = None, False          # the parameter was re-allocated (.to(), load): map again
+        if self._peer is None and not self._peer_tried:
+            self._peer_tried = True
+            if peer_memory_available(w, self.group) and self.embedding_dim % 4 == 0 and self.embedding_dim <= 1024 \
+                    and self.gather_rows is None and self.place is None:
+                self._peer = _try_peer_view(w.detach(), self.group, "the row-sharded item table")
+                self._peer_version = w._version
+        return self._peer
+
+    def lookup(self, ids: torch.Tensor, ragged: bool = False, plan_out: Optional[list] = None,
+               count: Optional[torch.Tensor] = None):
+        """-> (rows fp32 [ids.numel(), dim], split planes) for arbitrary global ids.
+
+        On GPUs the rows are read straight from their owners' shards over NVLink peer memory (``t4r_peer_gather_rows``:
+        no collective, no host synchronisation; ``count`` = optional device-side number of valid ids, the rest give
+        zero rows).  Otherwise -- and whenever the caller needs the routing plan for the backward (``plan_out``) --
+        one all-gather of the ids + one all-to-all of the rows.  ``ragged``: the ranks pass different numbers of ids
+        (label rows); for the all-to-all they are padded to the longest with the padding id."""
         flat = ids.reshape(-1)
         n = flat.numel()
+        peer = self.peer_view() if plan_out is None else None
+        if peer is not None:
+            from . import ops
+            if self.weight._version != self._peer_version:
+                # the shards moved (an optimizer step): every rank must be done writing before anyone reads remotely
+                dist.barrier(group=self.group)
+                self._peer_version = self.weight._version
+            return ops.peer_gather_rows(peer, self.num_embeddings, self.rows_per_shard, self.embedding_dim, flat, count,
+                                        pad_id=self.padding_idx if self.padding_idx is not None else -1)
+        if count is not None:
+            raise NotImplementedError("a device-side id count needs the peer-memory lookup")
         if ragged:
             counts = _all_gather(torch.tensor([n], dtype=torch.int64, device=flat.device), self.world, self.group)
             n_max = int(counts.max())

@@ -377,12 +377,17 @@ def compact_targets(masked_targets: torch.Tensor, padding_idx: int = 0):
 
 
 def gather_rows_split(x2d: torch.Tensor, idx: torch.Tensor, count: Optional[torch.Tensor], cap: int,
-                      want_f32: bool = True):
+                      want_f32: bool = True, out_f32: Optional[torch.Tensor] = None):
+    """``out_f32``: caller-owned fp32 [cap, K] destination (e.g. a peer window, distributed.PeerHead)."""
     _need_cuda(x2d, idx, count)
     x2d = _f32c(x2d)
     K = x2d.shape[1]
     planes = torch.empty((2, cap, round_up64(K)), dtype=torch.bfloat16, device=x2d.device)
-    of = torch.empty((cap, K), dtype=torch.float32, device=x2d.device) if want_f32 else None
+    if out_f32 is not None:
+        assert out_f32.shape == (cap, K) and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+        of = out_f32
+    else:
+        of = torch.empty((cap, K), dtype=torch.float32, device=x2d.device) if want_f32 else None
     lib = _lib.load()
     if idx.dtype == torch.int32:
         check(lib.t4r_gather_rows_split(ptr(x2d), K, K, ptr(idx), ptr(count), cap, ptr(of), ptr(planes), _stream()),
@@ -516,8 +521,11 @@ def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: in
 # --------------------------------------------------------------------------- #
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
-                    nprod=3, events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None):
-    """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank)."""
+                    nprod=3, events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None,
+                    out_stats: Optional[torch.Tensor] = None):
+    """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank).
+    ``out_stats``: caller-owned fp32 [3, T_cap] buffer that receives row_lse | row_tgt | row_rank (int32 bits) --
+    the layout ``peer_combine_lse`` reads from every shard's window."""
     _need_cuda(xt_planes, w_planes)
     lib = _lib.load()
     T_cap = xt_planes.shape[1]
@@ -531,11 +539,16 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     a.inv_temperature = inv_temperature
     a.col_bias, a.col_ids, a.hit_value, a.pos_logit = ptr(col_bias), ptr(col_ids), hit_value, ptr(pos_logit)
     a.v_offset = v_offset
-    row_lse = torch.empty(T_cap, dtype=torch.float32, device=dev)
-    row_tgt = torch.empty(T_cap, dtype=torch.float32, device=dev)
+    if out_stats is not None:
+        assert out_stats.shape == (3, T_cap) and out_stats.dtype == torch.float32 and out_stats.is_contiguous()
+        row_lse, row_tgt = out_stats[0], out_stats[1]
+        row_rank = out_stats[2].view(torch.int32) if want_rank else None
+    else:
+        row_lse = torch.empty(T_cap, dtype=torch.float32, device=dev)
+        row_tgt = torch.empty(T_cap, dtype=torch.float32, device=dev)
+        row_rank = torch.empty(T_cap, dtype=torch.int32, device=dev) if want_rank else None
     row_loss = torch.empty(T_cap, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev) if want_loss else None
-    row_rank = torch.empty(T_cap, dtype=torch.int32, device=dev) if want_rank else None
     a.row_lse, a.row_tgt, a.row_loss, a.loss, a.row_rank = ptr(row_lse), ptr(row_tgt), ptr(row_loss), ptr(loss), ptr(row_rank)
     nbytes = lib.t4r_head_workspace_bytes(T_cap, V, De)
     ws = WS.get("head", nbytes, dev)
@@ -613,6 +626,74 @@ def combine_shard_lse(parts: torch.Tensor, t_dev=None):
     check(_lib.load().t4r_combine_shard_lse(ptr(parts), world, T_cap, ptr(t_dev), ptr(row_loss), ptr(loss), _stream()),
           "t4r_combine_shard_lse")
     return row_loss, loss
+
+
+# --------------------------------------------------------------------------- #
+# K11 / K12 over NVLink peer memory (csrc/t4r_peer.cu).  ``peers`` arguments are objects with a ``.struct``
+# (_lib.PeerPtrs: the same buffer on every rank as addressable from this process) -- distributed.PeerView, or
+# ``local_peer_view`` below for single-process use.
+# --------------------------------------------------------------------------- #
+class LocalPeerView:
+    """A "group" whose ranks' buffers all live in THIS process (single-GPU tests / world size 1)."""
+
+    def __init__(self, tensors: Sequence[torch.Tensor], rank: int = 0):
+        if not 1 <= len(tensors) <= _lib.T4R_MAX_PEERS:
+            raise _lib.T4RError(f"1..{_lib.T4R_MAX_PEERS} ranks")
+        _need_cuda(*tensors)
+        self.tensors = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+        self.world, self.rank = len(tensors), rank
+        self.local = self.tensors[rank]
+        self.struct = _lib.PeerPtrs()
+        self.struct.world, self.struct.rank = self.world, rank
+        for r, t in enumerate(self.tensors):
+            self.struct.base[r] = t.data_ptr()
+
+
+def peer_gather_rows(shards, V: int, rows_per_shard: int, K: int, ids: torch.Tensor, count: Optional[torch.Tensor] = None,
+                     pad_id: int = -1, want_f32: bool = True, want_planes: bool = True, err_flag=None):
+    """Rows ``ids`` of a table row-sharded over the ranks of ``shards`` -> (fp32 [n, K] or None, planes or None)."""
+    _need_cuda(ids, count)
+    ids = ids.reshape(-1)
+    if ids.dtype != torch.int64:
+        ids = ids.long()
+    ids = ids.contiguous()
+    n, dev = ids.numel(), ids.device
+    of = torch.empty((n, K), dtype=torch.float32, device=dev) if want_f32 else None
+    planes = torch.empty((2, n, round_up64(K)), dtype=torch.bfloat16, device=dev) if want_planes else None
+    if n == 0:
+        return of, planes
+    check(_lib.load().t4r_peer_gather_rows(C.byref(shards.struct), int(V), int(rows_per_shard), int(K), ptr(ids), ptr(count),
+                                           n, int(pad_id), ptr(of), ptr(planes), ptr(err_flag), _stream()),
+          "t4r_peer_gather_rows")
+    return of, planes
+
+
+def peer_pull_rows(mail_x, mail_y, counts: torch.Tensor, cap: int, K: int, want_f32: bool = True):
+    """Label rows of every rank, rank-major and compact -> dict(x fp32 [world*cap, K] or None, planes, labels,
+    t_total int32[1], my_start int32[1])."""
+    _need_cuda(counts)
+    assert counts.dtype == torch.int32 and counts.numel() == mail_x.world
+    dev, cap_g = counts.device, mail_x.world * cap
+    of = torch.empty((cap_g, K), dtype=torch.float32, device=dev) if want_f32 else None
+    planes = torch.empty((2, cap_g, round_up64(K)), dtype=torch.bfloat16, device=dev)
+    labels = torch.empty(cap_g, dtype=torch.int64, device=dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)
+    check(_lib.load().t4r_peer_pull_rows(C.byref(mail_x.struct), C.byref(mail_y.struct), ptr(counts), int(cap), int(K),
+                                         ptr(of), ptr(planes), ptr(labels), ptr(meta[0:1]), ptr(meta[1:2]), _stream()),
+          "t4r_peer_pull_rows")
+    return {"x": of, "planes": planes, "labels": labels, "t_total": meta[0:1], "my_start": meta[1:2]}
+
+
+def peer_combine_lse(stats, cap_g: int, t_total: torch.Tensor, with_rank: bool = False):
+    """Every shard's [3, cap_g] statistics -> (row_loss [cap_g], loss [1], row_rank int32 [cap_g] or None)."""
+    _need_cuda(t_total)
+    dev = t_total.device
+    row_loss = torch.empty(cap_g, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    row_rank = torch.empty(cap_g, dtype=torch.int32, device=dev) if with_rank else None
+    check(_lib.load().t4r_peer_combine_lse(C.byref(stats.struct), int(cap_g), ptr(t_total), int(bool(with_rank)),
+                                           ptr(row_loss), ptr(row_rank), ptr(loss), _stream()), "t4r_peer_combine_lse")
+    return row_loss, loss, row_rank
 
 
 # --------------------------------------------------------------------------- #

@@ -181,12 +181,15 @@ class NextItemPredictionTask(PredictionTask):
         self.masking = None
         self.output_layer = None
         self.sampler = None
-        # tensor-core arithmetic of the GEMMs on this task: 3 = split-bf16, three products (fp32-grade, default);
-        # 1 = plain bf16; 2 = the 2-unit product of the TRAINING full-softmax head only, replicated or row-sharded
-        # (fp16 x fp16 + two e4m3 cross terms, ~2.3x the error of 3 at 2/3 of its tensor time,
-        # csrc/t4r_mixed_pack.cuh) -- every other GEMM of the task (task_block, sampled head, evaluation ranks,
-        # predictions, serving) then runs with 3.
-        self.nprod = 3
+        # tensor-core arithmetic of the GEMMs on this task: 3 = split-bf16, three products per MAC; 1 = plain bf16;
+        # 2 (default) = the 2-unit product in the TRAINING full-softmax head, replicated or row-sharded (fp16 x fp16 +
+        # two e4m3 cross terms, csrc/t4r_mixed_pack.cuh) -- every other GEMM of the task (task_block, sampled head,
+        # evaluation ranks, predictions, serving) runs with 3.  Measured on a B200 against fp64 (tools/precision_gpu.py,
+        # profiles/r2_head_precision.json; 2048 rows x 200 k classes x 256): max row-loss error 7.3e-6 (2) vs 5.9e-6
+        # (3) vs 3.1e-6 for torch's own fp32 sgemm at the reference's initialisation scale, 3.6e-4 vs 1.4e-4 at
+        # |logit| <= 52, identical mean-loss error in every regime -- two orders inside the 1e-3 parity bar where
+        # the bar is meaningful, at 2/3 of the tensor time (config-2 head 4.63 -> 3.76 ms).
+        self.nprod = 2
         self._planes = ops.PlaneCache()
         self._last = None
         self._neg_draws = None
@@ -279,11 +282,20 @@ class NextItemPredictionTask(PredictionTask):
             labels_2d = self.masking.masked_targets
             tgt_rows, tgt_labels, count = ops.compact_targets(labels_2d, self.padding_idx)
             cap = B * L
-            xt_planes, xt_f32 = ops.gather_rows_split(x.reshape(B * L, d), tgt_rows, count, cap, want_f32=True)
+            want_rank = bool(testing and not training)
+            peer_head = None
+            if self._sharded() and not (self.sampled_softmax and training):
+                # over NVLink peer memory the label rows go straight into the window the other ranks pull from
+                peer_head = self._peer_head(cap, Wd.shape[1], x.device)
+            direct = peer_head is not None and self.task_block is None and d == Wd.shape[1]
+            xt_planes, xt_f32 = ops.gather_rows_split(x.reshape(B * L, d), tgt_rows, count, cap, want_f32=True,
+                                                      **(dict(out_f32=peer_head.mail_x) if direct else {}))
             if self.task_block is not None:
                 xt_f32, xt_planes = self._task_block_rows(xt_planes, count)
-            want_rank = bool(testing and not training)
             if self._sharded():
+                if peer_head is not None or (self.sampled_softmax and training and self.item_embedding_table.peer_view() is not None):
+                    return self._forward_sharded_peer(peer_head, xt_planes, xt_f32, tgt_labels, count, training, want_rank,
+                                                      w_planes, inv_tau)
                 return self._forward_sharded(xt_planes, xt_f32, tgt_labels, count, training, want_rank, w_planes, inv_tau)
             if self.sampled_softmax and training:
                 neg, _, _ = self.sampler.sample(tgt_labels[:1], raw_draws=self._neg_draws)
@@ -392,6 +404,77 @@ class NextItemPredictionTask(PredictionTask):
         out = LazyOutputs({"loss": loss}, {"labels": self._lazy_labels, "predictions": self._no_sharded_predictions})
         out.row_rank = res[3] if want_rank else None
         out.count = None if want_rank else count  # ranks are already trimmed to this rank's T rows
+        return out
+
+    def _peer_head(self, cap: int, De: int, device):
+        """The head's peer-memory windows for this capacity (created once: a collective), or None when peer memory
+        is not available (CPU / gloo, T4R_PEER=0, failed mapping) -- then the NCCL formulation below runs."""
+        from . import distributed as D
+        table = self.item_embedding_table
+        if self.label_smoothing or table.peer_view() is None:
+            return None
+        ph = getattr(self, "_peer_head_state", None)
+        if ph is None or ph.cap != cap or ph.De != De or ph.mail_x.device != device:
+            ph = D.PeerHead(cap, De, device, table.group)
+            self._peer_head_state = ph
+        return ph if ph.ok else None
+
+    def _forward_sharded_peer(self, ph, xt_planes, xt_f32, tgt_labels, count, training, want_rank, w_planes, inv_tau):
+        """SURVEY 8e over NVLink peer memory (csrc/t4r_peer.cu): no bulk collective and no host synchronisation.
+        Full softmax: the ranks pull each other's label rows, score them against their V/world rows and read each
+        other's (lse, label logit, rank count) statistics -- two 4-byte NCCL collectives order the steps.  Sampled
+        softmax: the negatives' and the positives' rows are read from their owners' shards, after which the head is
+        data parallel; only (sum of row losses, T) is all-reduced."""
+        import torch.distributed as dist
+
+        from . import distributed as D
+        table = self.item_embedding_table
+        Wd = table.weight.detach()
+        cap = tgt_labels.numel()
+        if self.sampled_softmax and training:
+            if self._neg_draws is not None:
+                raw = self._neg_draws
+            else:
+                raw = self.sampler.draw()
+                dist.broadcast(raw, src=dist.get_global_rank(table.group, 0) if table.group is not None else 0,
+                               group=table.group)
+            neg, _, _ = self.sampler.sample(tgt_labels[:1], raw_draws=raw)
+            S = neg.numel()
+            _, neg_planes = table.lookup(neg)
+            wy, _ = table.lookup(tgt_labels, count=count)
+            col_bias = self.sampler.neg_log_q[neg].contiguous()
+            pos = ops.label_logit(xt_f32, wy, torch.arange(cap, device=xt_f32.device), t_dev=count,
+                                  class_bias=self.sampler.neg_log_q[tgt_labels].contiguous(), inv_temperature=inv_tau)
+            res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, neg_planes, None, t_dev=count, inv_temperature=inv_tau,
+                                      col_bias=col_bias, col_ids=neg, hit_value=float(torch.finfo(torch.float16).min / 100.0),
+                                      pos_logit=pos, nprod=self._dense_nprod())
+            n = count.to(torch.float32)
+            tot = torch.cat([res["loss"].reshape(1) * n, n])
+            dist.all_reduce(tot, group=table.group)
+            loss = (tot[0] / tot[1].clamp(min=1.0)).reshape(())
+            self._last = dict(count=count, labels=tgt_labels, sampled=True, sharded=True, S=S)
+            out = LazyOutputs({"loss": loss}, {"labels": self._lazy_labels, "predictions": self._no_sharded_predictions})
+            out.row_rank, out.count = None, count
+            return out
+        if xt_f32.data_ptr() != ph.mail_x.data_ptr():
+            ph.mail_x.copy_(xt_f32)
+        ph.mail_y.copy_(tgt_labels)
+
+        def label_logits_over_all_shards(xg, yg, t_total):
+            wy, _ = table.lookup(yg, count=t_total)            # W[y] from the label's owner
+            return ops.label_logit(xg, wy, torch.arange(yg.numel(), device=xg.device), t_dev=t_total,
+                                   inv_temperature=inv_tau)
+        res = D.peer_softmax_ce(ph, count, Wd, table.num_embeddings, w_planes=w_planes, inv_tau=inv_tau,
+                                want_rank=want_rank, rank_tgt_fn=label_logits_over_all_shards)
+        loss = res["loss"].reshape(())
+        self._last = dict(count=count, labels=tgt_labels, sampled=False, sharded=True, t_total=res["t_total"])
+        out = LazyOutputs({"loss": loss}, {"labels": self._lazy_labels, "predictions": self._no_sharded_predictions})
+        if want_rank:   # this rank's rows sit at [my_start, my_start + count) of the rank-major order
+            idx = (torch.arange(cap, device=xt_f32.device) + res["my_start"].long()).clamp_(max=ph.cap_g - 1)
+            out.row_rank = res["row_rank"][idx].contiguous()
+        else:
+            out.row_rank = None
+        out.count = count
         return out
 
     def _no_sharded_predictions(self):

@@ -48,8 +48,10 @@ LOG = logging.getLogger("transformers4rec_b200")
 # --------------------------------------------------------------------------------------------------------------
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias=None, residual=None) -> torch.Tensor:
     K = a.shape[1]
-    y, _, _ = ops.linear(ops.split_planes(a), ops.split_planes(b), K, bias=bias, residual=residual, want_planes=False)
-    return y
+    fused = residual is None or b.shape[0] % 32 == 0   # the GEMM epilogue adds a residual only for N % 32 == 0
+    y, _, _ = ops.linear(ops.split_planes(a), ops.split_planes(b), K, bias=bias, residual=residual if fused else None,
+                         want_planes=False)
+    return y if fused else ops.ew_add(y, residual)
 
 
 def _acc(param: torch.nn.Parameter, grad: torch.Tensor):
