@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
+#include <unordered_map>
 
 #include "t4r_common.cuh"
 #include "t4r_tmem_ld.cuh"
@@ -45,8 +46,43 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, Kp] row-major, box = [box_rows, rb/2 elements] with rb-byte swizzle.
+// Descriptors are pure functions of (base, rows, Kp, box_rows, rb): encoded once and kept (the same weights, the same
+// workspace slices and the same grow-only activation buffers come back every step; cuTensorMapEncodeTiled costs a
+// microsecond or two of host time per call and a GEMM launch needs four to six of them -- the launch-bound small
+// configurations spent a third of their host time here).  Bounded: the table is dropped when it reaches 8192 entries.
+struct TmapKey {
+  const void* base; int64_t rows; int Kp, box_rows, rb;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && Kp == o.Kp && box_rows == o.box_rows && rb == o.rb;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= static_cast<uint64_t>(k.rows) * 0xC2B2AE3D27D4EB4Full + (static_cast<uint64_t>(k.Kp) << 20) +
+         (static_cast<uint64_t>(k.box_rows) << 8) + static_cast<uint64_t>(k.rb);
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+static int make_tmap_uncached(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows, int rb);
 static int make_tmap(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows, int rb) {
+  const TmapKey key{base, rows, Kp, box_rows, rb};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *map = it->second; return 0; }
+  }
+  T4R_TRY(make_tmap_uncached(map, base, rows, Kp, box_rows, rb));
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *map);
+  return 0;
+}
+
+static int make_tmap_uncached(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int Kp, int box_rows, int rb) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");

@@ -359,9 +359,12 @@ class PeerView:
         hb = _lib.T4R_PEER_HANDLE_BYTES
         handle = (C.c_ubyte * hb)()
         off = C.c_int64(0)
-        _lib.check(lib.t4r_peer_export(local.data_ptr(), handle, C.byref(off)), "t4r_peer_export")
-        mine = torch.tensor(list(bytes(handle)) + list(int(off.value).to_bytes(8, "little")), dtype=torch.uint8,
-                            device=local.device)
+        # every rank runs the SAME two collectives whatever fails locally (a rank that skipped one would desynchronise
+        # the communicator): byte hb + 8 of the exchanged record says whether this rank's export worked
+        rc = lib.t4r_peer_export(local.data_ptr(), handle, C.byref(off))
+        err = "" if rc == 0 else (lib.t4r_last_error() or b"t4r_peer_export failed").decode()
+        mine = torch.tensor(list(bytes(handle)) + list(int(off.value if rc == 0 else 0).to_bytes(8, "little")) +
+                            [1 if rc == 0 else 0], dtype=torch.uint8, device=local.device)
         allh = _all_gather(mine, self.world, group).cpu()
         self.ptr_of_rank = []
         for r in range(self.world):
@@ -369,13 +372,24 @@ class PeerView:
                 self.ptr_of_rank.append(local.data_ptr())
                 continue
             raw = bytes(allh[r].tolist())
-            h, o = raw[:hb], int.from_bytes(raw[hb:hb + 8], "little")
+            h, o, ok = raw[:hb], int.from_bytes(raw[hb:hb + 8], "little"), raw[hb + 8]
+            if not ok:
+                err = err or f"rank {r} could not export its buffer"
+                continue
+            if err:
+                continue
             base = _OPENED.get(h)
             if base is None:   # an allocation can be opened once per process: keep the mapping for later views
                 out = C.c_void_p()
-                _lib.check(lib.t4r_peer_open((C.c_ubyte * hb).from_buffer_copy(h), 0, C.byref(out)), "t4r_peer_open")
+                if lib.t4r_peer_open((C.c_ubyte * hb).from_buffer_copy(h), 0, C.byref(out)) != 0:
+                    err = (lib.t4r_last_error() or b"t4r_peer_open failed").decode()
+                    continue
                 base = _OPENED[h] = int(out.value)
             self.ptr_of_rank.append(base + o)
+        ok_t = torch.tensor([0 if err else 1], dtype=torch.int32, device=local.device)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN, group=group)
+        if int(ok_t.item()) == 0:
+            raise _lib.T4RError("peer memory is not available: " + (err or "a peer rank failed to map the buffers"))
         self.struct = _lib.PeerPtrs()
         self.struct.world, self.struct.rank = self.world, self.rank
         for r, p in enumerate(self.ptr_of_rank):
@@ -389,18 +403,13 @@ class PeerView:
 def _try_peer_view(local: torch.Tensor, group, what: str):
     """PeerView or None -- the SAME answer on every rank (a failed mapping anywhere turns the feature off everywhere)."""
     import logging
-    view, err = None, ""
+
+    from . import _lib
     try:
-        view = PeerView(local, group)
-    except Exception as exc:  # noqa: BLE001 -- the reason is logged; the NCCL formulation takes over
-        err = f"{type(exc).__name__}: {exc}"
-    ok = torch.tensor([1 if view is not None else 0], dtype=torch.int32, device=local.device)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if int(ok.item()) == 0:
-        logging.getLogger("transformers4rec_b200").warning(
-            "peer memory is not available for %s (%s): using the NCCL all-to-all formulation", what, err or "a peer failed")
+        return PeerView(local, group)   # raises on EVERY rank or on none (its last step is an all-reduce of the outcome)
+    except _lib.T4RError as exc:
+        logging.getLogger("transformers4rec_b200").warning("%s for %s: using the NCCL all-to-all formulation", exc, what)
         return None
-    return view
 
 
 class PeerHead:
