@@ -46,19 +46,27 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+EXTRA = ("pipe_tensor", "xbar2l1tex", "lts__t_bytes", "lts__t_sectors_srcunit_tex", "dram__throughput",
+         "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warp_issue_stalled")
+
+
 def full(src, dst):
+    """Summary of the judged metrics + the raw per-kernel CSV next to it (dst with .csv), so the summary can be re-cut."""
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    with open(re.sub(r"\.txt$", "", dst) + ".raw.csv", "w") as f:
+        f.write(raw)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
+    keys = list(KEYS) + sorted(h for h in hdr if h not in KEYS and any(e in h for e in EXTRA))
     with open(dst, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on : {src}\n")
         for r in rows[2:]:
             f.write("\n" + r[idx["Kernel Name"]][:150] + "\n")
-            for k in KEYS:
+            for k in keys:
                 if k in idx:
                     f.write(f"  {k:95s} {r[idx[k]]:>16} {units[idx[k]]}\n")
-    print(open(dst).read())
+    print(open(dst).read()[:6000])
 
 
 if __name__ == "__main__":
