@@ -12,6 +12,9 @@ python tools/summarize_ncu.py launches gpurun_out/r2_launches.csv gpurun_out/r2_
 cap() {  # name, kernel regex, skip, extra bench args
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c 1 -o gpurun_out/r2_$1 -f $B --steps 3 --warmup 3 $4 > gpurun_out/r2_$1_ncu.log 2>&1
   python tools/summarize_ncu.py full gpurun_out/r2_$1.ncu-rep gpurun_out/r2_$1_full.txt > /dev/null 2>&1 && head -45 gpurun_out/r2_$1_full.txt
+  python tools/ncu_lines.py gpurun_out/r2_$1.ncu-rep . 40 > gpurun_out/r2_$1_lines.txt 2>&1
+  python tools/ncu_stalls.py gpurun_out/r2_$1.ncu-rep . 0 40 > gpurun_out/r2_$1_stalls.txt 2>&1
+  ls -la gpurun_out/r2_$1.ncu-rep; [ "$1" = head ] || rm -f gpurun_out/r2_$1.ncu-rep   # the summaries / raw CSV / per-line stalls travel; one report is kept
 }
 echo "== ncu full: head"; cap head "head_resident_kernel" 4 ""
 echo "== ncu full: gather"; cap gather "embed_concat_kernel" 5 ""
