@@ -329,6 +329,30 @@ def test_bench_recall_leg_helpers_on_cpu():
         assert ranks.shape == (6,) and int(ranks.min()) >= 0 and int(ranks.max()) < cfg["V"]
 
 
+def test_bench_trained_recall_leg_on_cpu(monkeypatch):
+    """bench.py's non-vacuous Recall@20 leg (train the config-1-size model with the fused step, evaluate it with the
+    product's head and with the oracle carrying the trained weights), end to end on the CPU with kernel doubles: the
+    two sides must agree on every label rank, and training must move the loss."""
+    import importlib.util
+    import os
+    import _ops_double as D
+    from transformers4rec_b200 import ops
+    twin = ops.host_twin("adamw_step")
+    D.install(monkeypatch)
+    monkeypatch.setattr(ops, "adamw_step", twin)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod5", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    b = bench.skewed_stream(16, 20, 10001, 3)["item_id/list"]
+    lens = (b != 0).sum(1)
+    assert int(lens.min()) >= 2 and all(torch.equal(r[:n], r[0] + torch.arange(n)) for r, n in zip(b, lens.tolist()))
+    rec = bench.trained_recall(torch.device("cpu"), steps=4, batch=16, n_eval=12)
+    assert rec["eval_sessions"] == 12 and 0.0 <= rec["ours"] <= 1.0
+    assert rec["label_rank_max_abs_diff"] <= 2 and rec["abs_diff"] <= 1.0 / 12 + 1e-9
+    assert abs(rec["eval_loss_ours"] - rec["eval_loss_oracle"]) < 1e-3
+
+
 def test_attention_kernels_index_algebra_emulated():
     """tools/emu_attn_mma.py: lane-level emulation (ldmatrix / mma.sync fragment layouts) of the index algebra of the
     tensor-path attention kernels, transcribed from the CUDA source.  The one-warp kernel (proven on hardware)
