@@ -474,6 +474,20 @@ int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const 
                        int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
                        const uint8_t* plm_mask /* NULL, or [B, L, L]: two-stream form over 2 B L rows */, void* stream,
                        int on_host);
+/* Dropout of the training step (HF:xlnet dropout sites :129, :147, :300-303, :1085-1180; HF:gpt2 :66, :225, :241, :584):
+ * y[i] = x[i] * keep(i) / (1 - p) with keep(i) a pure function of (seed, site, i) -- Philox4x32-10, so the backward
+ * regenerates the forward's mask by calling the same entry on the gradient.  Works in place (y == x). */
+int t4r_train_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, void* stream, int on_host);
+/* Attention forward of the training graph with dropout of the probabilities (mask index = HF's [stream, B, H, L, L]
+ * "bnij" order), one work item per (session, head) like the backward: out [M, d] fp32 (2 M rows in the two-stream
+ * form).  R / rw / rr NULL selects GPT-2's causal form.  t4r_train_attn_drop_bwd = t4r_train_attn_bwd under the
+ * same (p_drop, seed, site). */
+int t4r_train_attn_drop_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d, int H,
+                            const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, float* out, void* stream,
+                            int on_host);
+int t4r_train_attn_drop_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
+                            int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
+                            const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, void* stream, int on_host);
 /* two-stream (PLM) attention forward on split planes [2, 2 B L, 3d] (h rows then g rows), R planes [2, 2L, d] */
 int t4r_train_xlnet_attn_plm_fwd(const void* qkv_planes, const void* r_planes, const float* rw, const float* rr, int B,
                                  int L, int d, int H, const uint8_t* plm_mask, void* out_planes, void* stream);

@@ -453,18 +453,27 @@ def xlnet_relative_positions(L: int, d: int) -> torch.Tensor:
 
 
 def xlnet_forward_restated(x: torch.Tensor, sd: Dict[str, torch.Tensor], n_layer: int, n_head: int,
-                           eps: float = 0.03) -> torch.Tensor:
+                           eps: float = 0.03, drop=None) -> torch.Tensor:
     """Literal restatement of HF XLNetModel.forward for the arguments the reference
     passes (inputs_embeds only; HF:xlnet:979-1205, rel_attn_core :95-140,
     rel_shift_bnij :81-93, post_attention :142-152, XLNetFeedForward :285-305).
-    x: [B, L, d] -> [B, L, d].  ``sd`` uses HF state_dict names."""
+    x: [B, L, d] -> [B, L, d].  ``sd`` uses HF state_dict names.
+
+    ``drop(site, tensor)`` (train mode; None = eval) is called at every place HF applies ``self.dropout``: site 0 the
+    input rows (:1085), 5 the returned rows (:1180); per layer l, base 16 (l + 1): +1 the attention probabilities
+    [B, H, L, L] (:129), +2 the output projection (:147), +3 after the activation (:300), +4 after layer_2 (:302).
+    Site base + 0 is the projected relative-position table [2L, d]: HF drops pos_emb [2L, B, d] per batch element
+    before projecting it (:1159); the product drops the shared projection instead (DESIGN: dropout) -- with ``drop``
+    returning its argument at that site the function is HF's."""
     B, L, d = x.shape
     H = n_head
     dh = d // H
     pos = xlnet_relative_positions(L, d)  # [2L, d]
     scale = 1.0 / math.sqrt(dh)
-    h = x
+    D = drop if drop is not None else (lambda site, t: t)
+    h = D(0, x)
     for i in range(n_layer):
+        s0 = 16 * (i + 1)
         p = f"layer.{i}."
         Wq = sd[p + "rel_attn.q"].reshape(d, H * dh)
         Wk = sd[p + "rel_attn.k"].reshape(d, H * dh)
@@ -476,34 +485,39 @@ def xlnet_forward_restated(x: torch.Tensor, sd: Dict[str, torch.Tensor], n_layer
         q = (h @ Wq).view(B, L, H, dh)
         k = (h @ Wk).view(B, L, H, dh)
         v = (h @ Wv).view(B, L, H, dh)
-        r = (pos @ Wr).view(2 * L, H, dh)
+        r = D(s0, pos @ Wr).view(2 * L, H, dh)
         ac = torch.einsum("bihd,bjhd->bhij", q + rw, k)
         bd_full = torch.einsum("bihd,mhd->bhim", q + rr, r)  # [B,H,L,2L]
         # rel_shift_bnij identity: shift(x)[i, j] == x[i, j + L - i]
         idx = (torch.arange(L).view(1, L) + L - torch.arange(L).view(L, 1))  # [L(i), L(j)]
         bd = torch.gather(bd_full, 3, idx.view(1, 1, L, L).expand(B, H, L, L))
-        prob = torch.softmax((ac + bd) * scale, dim=-1)
+        prob = D(s0 + 1, torch.softmax((ac + bd) * scale, dim=-1))
         a = torch.einsum("bhij,bjhd->bihd", prob, v).reshape(B, L, H * dh)
-        attn_out = a @ Wo.t()
+        attn_out = D(s0 + 2, a @ Wo.t())
         h = F.layer_norm(h + attn_out, (d,), sd[p + "rel_attn.layer_norm.weight"], sd[p + "rel_attn.layer_norm.bias"], eps)
         ff = F.linear(h, sd[p + "ff.layer_1.weight"], sd[p + "ff.layer_1.bias"])
-        ff = F.gelu(ff)
-        ff = F.linear(ff, sd[p + "ff.layer_2.weight"], sd[p + "ff.layer_2.bias"])
+        ff = D(s0 + 3, F.gelu(ff))
+        ff = D(s0 + 4, F.linear(ff, sd[p + "ff.layer_2.weight"], sd[p + "ff.layer_2.bias"]))
         h = F.layer_norm(h + ff, (d,), sd[p + "ff.layer_norm.weight"], sd[p + "ff.layer_norm.bias"], eps)
-    return h
+    return D(5, h)
 
 
 def gpt2_forward_restated(x: torch.Tensor, sd: Dict[str, torch.Tensor], n_layer: int, n_head: int,
-                          eps: float = 1e-5) -> torch.Tensor:
+                          eps: float = 1e-5, drop=None) -> torch.Tensor:
     """Literal restatement of HF GPT2Model.forward with inputs_embeds only
     (HF:models/gpt2/modeling_gpt2.py:522-636, GPT2Block :246-309, GPT2Attention
-    :144-226, GPT2MLP :229-243).  Conv1D weights are [in, out] (y = x @ W + b)."""
+    :144-226, GPT2MLP :229-243).  Conv1D weights are [in, out] (y = x @ W + b).
+    ``drop(site, tensor)`` marks HF's dropout calls (train mode): 0 after the position embeddings (:584), per layer l,
+    base 16 (l + 1): +1 the attention probabilities [B, H, L, L] (:66), +2 the attention output projection (:225),
+    +4 the MLP output projection (:241)."""
     B, L, d = x.shape
     H = n_head
     dh = d // H
-    h = x + sd["wpe.weight"][:L].unsqueeze(0)
+    D = drop if drop is not None else (lambda site, t: t)
+    h = D(0, x + sd["wpe.weight"][:L].unsqueeze(0))
     causal = torch.tril(torch.ones(L, L, dtype=torch.bool))
     for i in range(n_layer):
+        s0 = 16 * (i + 1)
         p = f"h.{i}."
         a = F.layer_norm(h, (d,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], eps)
         qkv = a @ sd[p + "attn.c_attn.weight"] + sd[p + "attn.c_attn.bias"]
@@ -513,11 +527,11 @@ def gpt2_forward_restated(x: torch.Tensor, sd: Dict[str, torch.Tensor], n_layer:
         v = v.view(B, L, H, dh).transpose(1, 2)
         s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
         s = s.masked_fill(~causal, float("-inf"))
-        o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, L, d)
-        h = h + (o @ sd[p + "attn.c_proj.weight"] + sd[p + "attn.c_proj.bias"])
+        o = (D(s0 + 1, torch.softmax(s, dim=-1)) @ v).transpose(1, 2).reshape(B, L, d)
+        h = h + D(s0 + 2, o @ sd[p + "attn.c_proj.weight"] + sd[p + "attn.c_proj.bias"])
         m = F.layer_norm(h, (d,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], eps)
         m = F.gelu(m @ sd[p + "mlp.c_fc.weight"] + sd[p + "mlp.c_fc.bias"])
-        h = h + (m @ sd[p + "mlp.c_proj.weight"] + sd[p + "mlp.c_proj.bias"])
+        h = h + D(s0 + 4, m @ sd[p + "mlp.c_proj.weight"] + sd[p + "mlp.c_proj.bias"])
     return F.layer_norm(h, (d,), sd["ln_f.weight"], sd["ln_f.bias"], eps)
 
 

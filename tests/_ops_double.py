@@ -14,6 +14,7 @@ import torch.nn.functional as F
 import _mixed_ref as R
 import t4r_oracle as O
 from transformers4rec_b200 import _lib
+from transformers4rec_b200.ops import dropout as _REAL_DROPOUT   # bound before install() swaps ops.dropout
 
 
 def _r64(k):
@@ -360,20 +361,43 @@ def _xl_scores(qkv, R, rw, rr, B, L, H):
     return (ac + bd) / dh ** 0.5, v
 
 
-def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H):
+def dropout(x, p, seed, site):
+    """The mask IS the kernel's definition (Philox keyed on (seed, site, flat index)): its host twin, on any shape."""
+    if p <= 0.0:
+        return x
+    mask = _REAL_DROPOUT(torch.ones(x.numel()), p, seed, site, _on_host=True).reshape(x.shape)
+    return x * mask
+
+
+def _prob_mask(shape, drop):
+    return None if drop is None or drop[0] <= 0.0 else dropout(torch.ones(shape), *drop)
+
+
+def xlnet_attn_fwd(qkv, R, rw, rr, B, L, H, drop=None):
     s, v = _xl_scores(qkv, R, rw, rr, B, L, H)
-    return torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(B * L, -1)
+    p = torch.softmax(s, -1)
+    mk = _prob_mask((B, H, L, L), drop)
+    return torch.einsum("bhij,bjhd->bihd", p if mk is None else p * mk, v).reshape(B * L, -1)
 
 
-def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None):
+def attn_drop_fwd(qkv, R, rw, rr, B, L, H, drop, plm_mask=None):
+    if R is None:
+        return causal_attn_fwd(qkv, B, L, H, drop=drop)
+    if plm_mask is not None:
+        return xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask, drop=drop)
+    return xlnet_attn_fwd(qkv, R, rw, rr, B, L, H, drop=drop)
+
+
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None, drop=None):
     with torch.enable_grad():
         a, b, c, e = (t.detach().clone().requires_grad_(True) for t in (qkv, R, rw, rr))
-        out = xlnet_attn_fwd(a, b, c, e, B, L, H) if plm_mask is None else xlnet_attn_plm_fwd(a, b, c, e, B, L, H, plm_mask)
+        out = (xlnet_attn_fwd(a, b, c, e, B, L, H, drop=drop) if plm_mask is None else
+               xlnet_attn_plm_fwd(a, b, c, e, B, L, H, plm_mask, drop=drop))
         out.backward(dout)
     return a.grad, b.grad, c.grad, e.grad
 
 
-def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask):
+def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask, drop=None):
     """HF:xlnet two-stream rel_attn_core with target_mapping = identity: rows [0, M) = content stream h, [M, 2M) = query
     stream g; K / V from h; score - 1e30 * mask (h: diagonal exempt)."""
     M = B * L
@@ -381,6 +405,7 @@ def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask):
     dh = d // H
     kv = qkv[:M]
     outs = []
+    mk_all = _prob_mask((2, B, H, L, L), drop)
     for st in range(2):
         q_rows = qkv[st * M:(st + 1) * M, :d]
         fake = torch.cat([q_rows, kv[:, d:]], dim=1)
@@ -389,23 +414,28 @@ def xlnet_attn_plm_fwd(qkv, R, rw, rr, B, L, H, plm_mask):
         if st == 0:
             m = m * (1.0 - torch.eye(L)).view(1, 1, L, L)
         s = s - 1e30 * m
-        outs.append(torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), v).reshape(M, d))
+        pr = torch.softmax(s, -1)
+        if mk_all is not None:
+            pr = pr * mk_all[st]
+        outs.append(torch.einsum("bhij,bjhd->bihd", pr, v).reshape(M, d))
     return torch.cat(outs, dim=0)
 
 
-def causal_attn_fwd(qkv, B, L, H):
+def causal_attn_fwd(qkv, B, L, H, drop=None):
     d = qkv.shape[1] // 3
     dh = d // H
     q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1))
     s = (q @ k.transpose(-1, -2)) / dh ** 0.5
     s = s.masked_fill(~torch.tril(torch.ones(L, L, dtype=torch.bool)), float("-inf"))
-    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, d)
+    pr = torch.softmax(s, -1)
+    mk = _prob_mask((B, H, L, L), drop)
+    return ((pr if mk is None else pr * mk) @ v).transpose(1, 2).reshape(B * L, d)
 
 
-def causal_attn_bwd(qkv, dout, B, L, H):
+def causal_attn_bwd(qkv, dout, B, L, H, drop=None):
     with torch.enable_grad():
         a = qkv.detach().clone().requires_grad_(True)
-        causal_attn_fwd(a, B, L, H).backward(dout)
+        causal_attn_fwd(a, B, L, H, drop=drop).backward(dout)
     return a.grad
 
 
@@ -518,7 +548,7 @@ def index_add_rows(dst, idx, src, col, width, skip_index=None):
 
 TRAIN_OPS = dict(transpose=transpose, col_sum=col_sum, rel_pos_table=rel_pos_table, rel_pos_proj=rel_pos_proj,
                  xlnet_attn_fwd=xlnet_attn_fwd, xlnet_attn_plm_fwd=xlnet_attn_plm_fwd, xlnet_attn_bwd=xlnet_attn_bwd,
-                 causal_attn_fwd=causal_attn_fwd,
+                 causal_attn_fwd=causal_attn_fwd, dropout=dropout, attn_drop_fwd=attn_drop_fwd,
                  causal_attn_bwd=causal_attn_bwd, layer_norm_fwd=layer_norm_fwd, layer_norm_bwd=layer_norm_bwd,
                  act_fwd=act_fwd, act_bwd=act_bwd, add_positions=add_positions, sum_over_sessions=sum_over_sessions,
                  apply_row_codes=apply_row_codes, row_codes_bwd=row_codes_bwd, gather_rows=gather_rows,

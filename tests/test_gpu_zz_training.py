@@ -44,6 +44,78 @@ def test_training_primitives_device_vs_host_twin():
     assert close(ops.causal_attn_fwd(qkv.cuda(), B, L, Hh), DD.causal_attn_fwd(qkv, B, L, Hh), 1e-4)
 
 
+def test_dropout_kernels_device_vs_host_twin():
+    """Dropout of the training step on the device: the element-wise mask is bit-identical to its host twin (same Philox
+    stream), the attention forward / backward with dropped probabilities agree with theirs."""
+    from transformers4rec_b200 import ops
+    g = torch.Generator().manual_seed(43)
+    H = ops.host_twin
+    close = lambda a, b, tol=1e-5: (a.cpu() - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    x = torch.randn(100_003, generator=g)
+    assert torch.equal(ops.dropout(x.cuda(), 0.3, 2**40 + 17, 35).cpu(), H("dropout")(x, 0.3, 2**40 + 17, 35))
+    B, L, Hh, dh = 5, 20, 4, 16
+    d = Hh * dh
+    drop = (0.3, 977, 18)
+    qkv, dout = torch.randn(B * L, 3 * d, generator=g), torch.randn(B * L, d, generator=g)
+    R, rw, rr = torch.randn(2 * L, d, generator=g), torch.randn(d, generator=g), torch.randn(d, generator=g)
+    c = lambda *ts: [t.cuda() for t in ts]
+    assert close(ops.attn_drop_fwd(*c(qkv, R, rw, rr), B, L, Hh, drop), H("attn_drop_fwd")(qkv, R, rw, rr, B, L, Hh, drop), 1e-4)
+    assert close(ops.attn_drop_fwd(qkv.cuda(), None, None, None, B, L, Hh, drop), H("attn_drop_fwd")(qkv, None, None, None, B, L, Hh, drop), 1e-4)
+    got = ops.xlnet_attn_bwd(*c(qkv, R, rw, rr, dout), B, L, Hh, drop=drop)
+    ref = H("xlnet_attn_bwd")(qkv, R, rw, rr, dout, B, L, Hh, drop=drop)
+    assert all(close(a, b, 1e-4) for a, b in zip(got, ref))
+    assert close(ops.causal_attn_bwd(qkv.cuda(), dout.cuda(), B, L, Hh, drop=drop), H("causal_attn_bwd")(qkv, dout, B, L, Hh, drop=drop), 1e-4)
+    pm = torch.rand(B, L, L, generator=g) < 0.4
+    qkv2, dout2 = torch.cat([qkv, qkv.flip(0)]), torch.cat([dout, dout.flip(0)])
+    assert close(ops.attn_drop_fwd(*c(qkv2, R, rw, rr), B, L, Hh, drop, plm_mask=pm.cuda()),
+                 H("attn_drop_fwd")(qkv2, R, rw, rr, B, L, Hh, drop, plm_mask=pm), 1e-4)
+    got = ops.xlnet_attn_bwd(*c(qkv2, R, rw, rr, dout2), B, L, Hh, plm_mask=pm.cuda(), drop=drop)
+    ref = H("xlnet_attn_bwd")(qkv2, R, rw, rr, dout2, B, L, Hh, plm_mask=pm, drop=drop)
+    assert all(close(a, b, 1e-4) for a, b in zip(got, ref))
+
+
+@pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("gpt2", "clm")])
+def test_training_step_with_dropout_on_gpu(monkeypatch, arch, masking):
+    """Train mode on the device: dropout at HF's sites with masks regenerated in the backward -- loss and gradients
+    against autograd of the oracle graph whose encoder is the restated forward carrying the SAME masks (host twin of
+    the mask kernel)."""
+    import t4r_oracle as O
+    from transformers4rec_b200 import ops
+    from transformers4rec_b200.training import FusedTrainingStep
+    cards, dims = {"item_id/list": 3001, "category/list": 37}, {"item_id/list": 64, "category/list": 64}
+    NL, Hh, p, seed = 2, 4, 0.3, 31337
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, Hh, NL, 20, arch=arch, masking=masking, weight_scale=0.08)
+    oracle.train(False)
+    B, L = 16, 20
+    batch = synth_batch(B, L, cards, seed=5)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    twin = ops.host_twin("dropout")
+
+    def drop(site, t):
+        return t * twin(torch.ones(t.numel()), p, seed, site).reshape(t.shape)
+
+    def encoder_with_masks(hf, x):
+        sd = dict(hf.named_parameters())
+        if arch == "xlnet":
+            return O.xlnet_forward_restated(x, sd, NL, Hh, drop=drop)
+        return O.gpt2_forward_restated(x, sd, NL, Hh, eps=hf.config.layer_norm_epsilon, drop=drop)
+    monkeypatch.setattr(O, "hf_encoder_forward", encoder_with_masks)
+    ref_loss = _oracle_grads(oracle, batch, draws)
+    step = FusedTrainingStep(model, head_chunk=1024).set_dropout_seed(seed)
+    model.heads[0].body[1].transformer.train()
+    for prm in model.parameters():
+        prm.grad = None
+    loss = step.forward({k: v.cuda() for k, v in batch.items()})
+    step.backward()
+    assert abs(loss.item() - ref_loss) < 1e-3
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad.cpu() - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 1e-3 * max(1.0, po.grad.abs().max().item()), (name, err)
+
+
 @pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("gpt2", "clm")])
 def test_training_step_gradients_on_gpu(arch, masking):
     from transformers4rec_b200.training import FusedTrainingStep, training_loss

@@ -349,6 +349,7 @@ def test_model_fit_and_evaluate(monkeypatch, capsys):
         _, m = make_pair(CARDS, dims, "item_id/list", CONT, 32, 2, 1, 8, device="cpu", weight_scale=0.08)
         u, _ = mlm_draws(6, 8)
         m.heads[0].body[0].masking.set_draws(u)
+        m.heads[0].body[1].transformer.config.dropout = 0.0   # fit() trains in train() mode: keep the curves comparable
         return m
     batches = [(synth_batch(6, 8, CARDS, CONT, seed=s), None) for s in (3, 4)]
     model = fresh()
@@ -653,6 +654,7 @@ def test_training_step_with_stochastic_swap_noise(monkeypatch):
     ssn = tr.StochasticSwapNoise(schema=inputs.schema, pad_token=0, replacement_prob=0.3)
     inputs.pre = ssn
     model.train()
+    model.heads[0].body[1].transformer.eval()   # the noise is what is under test here; dropout has its own tests below
     B, L = 6, 8
     batch = synth_batch(B, L, CARDS, CONT, seed=11)
     mask = batch["item_id/list"] != 0
@@ -680,21 +682,153 @@ def test_training_step_with_stochastic_swap_noise(monkeypatch):
         assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
 
 
-def test_training_step_says_that_dropout_is_not_applied(monkeypatch, caplog):
-    """The reference's configs default to dropout 0.3 (config/transformer.py:217-260,432-482); the fused step trains
-    without it and says so once at construction."""
-    import logging
+def _kernel_mask(shape, p, seed, site):
+    """The dropout mask the kernels use, as a tensor of ``shape`` in the kernels' flat index order."""
+    return D._REAL_DROPOUT(torch.ones(int(torch.Size(shape).numel())), p, seed, site, _on_host=True).reshape(shape)
+
+
+def test_dropout_mask_is_counter_based():
+    """t4r_train_dropout: keep probability 1 - p, scale 1 / (1 - p), a pure function of (seed, site, index)."""
+    from transformers4rec_b200 import ops
+    tw = ops.host_twin("dropout")
+    x = torch.randn(50_000)
+    y = tw(x, 0.3, 99, 17)
+    kept = y != 0
+    assert abs(kept.float().mean().item() - 0.7) < 0.01
+    assert torch.allclose(y[kept], x[kept] / 0.7)
+    assert torch.equal(y, tw(x, 0.3, 99, 17)) and not torch.equal(y, tw(x, 0.3, 99, 18)) and not torch.equal(y, tw(x, 0.3, 100, 17))
+    assert tw(x, 0.0, 1, 1) is x
+    # a longer tensor under the same key extends the same stream (the backward of a slice sees the forward's mask)
+    assert torch.equal(tw(torch.ones(100), 0.5, 5, 3), tw(torch.ones(1000), 0.5, 5, 3)[:100])
+
+
+@pytest.mark.parametrize("arch", ["xlnet", "gpt2"])
+def test_restated_dropout_sites_are_huggingfaces(arch):
+    """The oracle's restated encoders mark every place HF calls dropout (``drop(site, tensor)``); held to HF's own
+    forward in train() mode with ``torch.nn.functional.dropout`` replaced by the same masks, identified by call order."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    B, L, d, H, NL, p = 3, 6, 16, 2, 2, 0.3      # the rate the reference builds HF with (config/transformer.py:217-260, :432-482)
+    hf = (O.build_hf_xlnet(d, H, NL) if arch == "xlnet" else O.build_hf_gpt2(d, H, NL, L)).train()
+    if arch == "gpt2":
+        hf.config._attn_implementation = "eager"     # the eager path applies F.dropout to the probabilities (HF:gpt2:66)
+    with torch.no_grad():
+        for prm in hf.parameters():
+            prm.add_(torch.randn_like(prm) * 0.1)
+    x = torch.randn(B, L, d)
+    if arch == "xlnet":   # call order of XLNetModel.forward / XLNetLayer: input, pos_emb, then per layer prob, o-proj, act, ff
+        order = [0, None] + [s for l in range(NL) for s in (16 * (l + 1) + 1, 16 * (l + 1) + 2, 16 * (l + 1) + 3, 16 * (l + 1) + 4)] + [5]
+    else:
+        order = [0] + [s for l in range(NL) for s in (16 * (l + 1) + 1, 16 * (l + 1) + 2, 16 * (l + 1) + 4)]
+    calls = []
+
+    def to_kernel_layout(t, site):   # HF's XLNet works on [L, B, d]; the probabilities are [B, H, L, L] in both
+        return t.transpose(0, 1) if (arch == "xlnet" and t.dim() == 3) else t
+
+    def fake_dropout(inp, p=0.5, training=True, inplace=False):
+        site = order[len(calls)]
+        calls.append(tuple(inp.shape))
+        if site is None or not training:
+            return inp
+        k = to_kernel_layout(inp, site)
+        out = k * _kernel_mask(k.shape, p, 7, site)
+        return to_kernel_layout(out, site)
+    orig = F.dropout
+    F.dropout = fake_dropout
+    try:
+        with torch.no_grad():
+            got = hf(inputs_embeds=x)[0]
+    finally:
+        F.dropout = orig
+    assert len(calls) == len(order), (len(calls), len(order))
+
+    def drop(site, t):
+        return t if site % 16 == 0 and site > 0 else t * _kernel_mask(t.shape, p, 7, site)   # R site: identity (HF drops pos_emb)
+    sd = dict(hf.named_parameters())
+    with torch.no_grad():
+        want = (O.xlnet_forward_restated(x, sd, NL, H, drop=drop) if arch == "xlnet" else
+                O.gpt2_forward_restated(x, sd, NL, H, eps=hf.config.layer_norm_epsilon, drop=drop))
+    assert (got - want).abs().max().item() < 2e-5
+
+
+def test_attention_kernels_with_dropped_probabilities():
+    """The per-(session, head) attention forward / backward with dropout of the probabilities (host twins = the
+    kernels' per-item code) against autograd of the plain formula with the same mask: XLNet relative, XLNet two-stream
+    (PLM) and GPT-2 causal forms."""
+    from transformers4rec_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, L, Hh, d = 3, 7, 2, 16
+    drop = (0.3, 4242, 33)
+    qkv, dout = torch.randn(B * L, 3 * d, generator=g), torch.randn(B * L, d, generator=g)
+    R, rw, rr = torch.randn(2 * L, d, generator=g), torch.randn(d, generator=g), torch.randn(d, generator=g)
+    fwd, bwd, cbwd = ops.host_twin("attn_drop_fwd"), ops.host_twin("xlnet_attn_bwd"), ops.host_twin("causal_attn_bwd")
+    assert (fwd(qkv, R, rw, rr, B, L, Hh, drop) - D.xlnet_attn_fwd(qkv, R, rw, rr, B, L, Hh, drop=drop)).abs().max() < 1e-5
+    assert (fwd(qkv, R, rw, rr, B, L, Hh, drop) - D.xlnet_attn_fwd(qkv, R, rw, rr, B, L, Hh)).abs().max() > 1e-2
+    for got, want in zip(bwd(qkv, R, rw, rr, dout, B, L, Hh, drop=drop), D.xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, Hh, drop=drop)):
+        assert (got - want).abs().max().item() < 1e-4
+    assert (fwd(qkv, None, None, None, B, L, Hh, drop) - D.causal_attn_fwd(qkv, B, L, Hh, drop=drop)).abs().max() < 1e-5
+    assert (cbwd(qkv, dout, B, L, Hh, drop=drop) - D.causal_attn_bwd(qkv, dout, B, L, Hh, drop=drop)).abs().max() < 1e-4
+    qkv2, dout2 = torch.randn(2 * B * L, 3 * d, generator=g), torch.randn(2 * B * L, d, generator=g)
+    pm = (torch.rand(B, L, L, generator=g) < 0.4)
+    assert (fwd(qkv2, R, rw, rr, B, L, Hh, drop, plm_mask=pm) -
+            D.xlnet_attn_plm_fwd(qkv2, R, rw, rr, B, L, Hh, pm, drop=drop)).abs().max() < 1e-5
+    for got, want in zip(bwd(qkv2, R, rw, rr, dout2, B, L, Hh, plm_mask=pm, drop=drop),
+                         D.xlnet_attn_bwd(qkv2, R, rw, rr, dout2, B, L, Hh, plm_mask=pm, drop=drop)):
+        assert (got - want).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("arch,masking", [("xlnet", "mlm"), ("gpt2", "clm")])
+def test_training_step_applies_dropout_in_train_mode(monkeypatch, arch, masking):
+    """With the encoder in train() mode the fused step applies dropout at HF's sites (masks regenerated in the
+    backward): loss and every gradient equal autograd of the oracle graph whose encoder is the restated forward with
+    the SAME masks; in eval() mode (and at rate 0) nothing is dropped."""
     from transformers4rec_b200.training import FusedTrainingStep
     D.install(monkeypatch)
-    _, model = make_pair({"item_id/list": 101}, {"item_id/list": 32}, "item_id/list", (), 32, 2, 1, 8, device="cpu")
-    with caplog.at_level(logging.WARNING, logger="transformers4rec_b200"):
-        FusedTrainingStep(model)
-    assert any("no dropout" in r.getMessage() for r in caplog.records)
-    caplog.clear()
-    model.heads[0].body[1].transformer.config.dropout = 0.0
-    with caplog.at_level(logging.WARNING, logger="transformers4rec_b200"):
-        FusedTrainingStep(model)
-    assert not any("no dropout" in r.getMessage() for r in caplog.records)
+    dims = {"item_id/list": 32, "category/list": 32}
+    oracle, model = make_pair(CARDS, dims, "item_id/list", CONT, 32, 2, 2, 8, arch=arch, masking=masking, device="cpu",
+                              weight_scale=0.08)
+    B, L, NL, Hh, p, seed = 6, 8, 2, 2, 0.3, 1234
+    batch = synth_batch(B, L, CARDS, CONT, seed=9)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u)
+    enc = model.heads[0].body[1].transformer
+    assert float(enc.config.dropout if arch == "xlnet" else enc.config.resid_pdrop) == 0.3   # the reference's default
+
+    def drop(site, t):
+        return t * _kernel_mask(t.shape, p, seed, site)
+
+    def encoder_with_masks(hf, x):
+        sd = dict(hf.named_parameters())
+        if arch == "xlnet":
+            return O.xlnet_forward_restated(x, sd, NL, Hh, drop=drop)
+        return O.gpt2_forward_restated(x, sd, NL, Hh, eps=hf.config.layer_norm_epsilon, drop=drop)
+    monkeypatch.setattr(O, "hf_encoder_forward", encoder_with_masks)
+    ref_loss = _oracle_grads(oracle, batch, draws)
+    step = FusedTrainingStep(model, head_chunk=512).set_dropout_seed(seed)
+    enc.train()
+    for prm in model.parameters():
+        prm.grad = None
+    loss = step.forward(batch)
+    step.backward()
+    assert abs(loss.item() - ref_loss) < 1e-4
+    n = 0
+    for name, po, pm in _pairs(oracle, model):
+        if po.grad is None and pm.grad is None:
+            continue
+        err = (pm.grad - po.grad.reshape(pm.grad.shape)).abs().max().item()
+        assert err < 3e-4 * max(1.0, po.grad.abs().max().item()), (name, err)
+        n += 1
+    assert n > 10
+    # the next step draws new masks; eval() mode drops nothing
+    loss2 = step.forward(batch)
+    assert abs(loss2.item() - loss.item()) > 1e-6
+    enc.eval()
+    monkeypatch.setattr(O, "hf_encoder_forward", lambda hf, x: (
+        O.xlnet_forward_restated(x, dict(hf.named_parameters()), NL, Hh) if arch == "xlnet" else
+        O.gpt2_forward_restated(x, dict(hf.named_parameters()), NL, Hh, eps=hf.config.layer_norm_epsilon)))
+    with torch.no_grad():
+        plain = float(oracle(batch, training=True, draws=draws)["loss"])
+    assert abs(step.forward(batch).item() - plain) < 1e-4
 
 
 def test_plm_attention_backward_on_fully_masked_rows():

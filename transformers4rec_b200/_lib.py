@@ -194,6 +194,11 @@ SIGNATURES = {
     "t4r_train_layer_norm_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, _P, _P, c_int]),
     "t4r_train_layer_norm_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P, _P, _P, _P, _P, _P, _P, c_int]),
     "t4r_train_attn_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int]),
+    "t4r_train_dropout": (c_int, [_P, _P, c_int64, c_float, C.c_uint64, C.c_uint32, _P, c_int]),
+    "t4r_train_attn_drop_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_float, C.c_uint64, C.c_uint32, _P, _P,
+                                        c_int]),
+    "t4r_train_attn_drop_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float,
+                                        C.c_uint64, C.c_uint32, _P, c_int]),
     "t4r_train_xlnet_attn_plm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "t4r_train_xlnet_attn_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "t4r_train_causal_attn_fwd": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P]),

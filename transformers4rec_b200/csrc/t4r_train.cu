@@ -29,6 +29,37 @@ T4R_HD float gelu_grad(float x) {
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// ---------------------------------------------------------------------------------------------- dropout
+// Counter-based, so the backward regenerates the forward's mask instead of storing it: element `idx` of dropout site
+// `site` under `seed` keeps its value (scaled by 1 / (1 - p)) iff word (idx & 3) of Philox4x32-10(key = seed,
+// counter = (idx >> 2, site)) >= p * 2^32.  Same bits on the host and on the device.
+T4R_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = static_cast<uint32_t>(p0);
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+T4R_HD float keep_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  uint32_t w[4];
+  const uint64_t ctr = idx >> 2;
+  philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(ctr),
+                static_cast<uint32_t>(ctr >> 32), site, 0x7434720u, w);
+  const uint32_t bits = w[idx & 3];
+  const float u = static_cast<float>(bits >> 8) * (1.0f / 16777216.0f);   // 24 uniform bits in [0, 1)
+  return u >= p ? 1.0f / (1.0f - p) : 0.f;
+}
+T4R_HD void dropout_item(const float* x, float* y, float p, uint64_t seed, uint32_t site, int64_t i) {
+  y[i] = x[i] * keep_scale(seed, site, static_cast<uint64_t>(i), p);
+}
+
 T4R_HD void transpose_item(const float* x, int64_t R, int64_t C, float* out, int64_t i) {
   const int64_t r = i / C, c = i % C;
   out[c * R + r] = x[i];
@@ -212,6 +243,11 @@ T4R_HD void ln_bwd_row(const float* x, const float* g, int d, float eps, const f
 //   dq_i = sum_j ds_j (k_j + R_m)        dk_j += ds_j (q_i + rw)        dv_j += p_j do_i
 //   dR_m += ds_j (q_i + rr)              drw  += ds_j k_j               drr  += ds_j R_m          m = j + L - i
 constexpr int kAttnMaxL = 64;
+// flat index of probability (stream st, session b, head h, query i, key j): the [n_streams, B, H, L, L] order of HF's
+// attn_prob ("bnij") -- what the dropout mask of the probabilities is keyed on
+T4R_HD uint64_t attn_prob_index(int st, int B, int64_t b, int H, int h, int L, int i, int j) {
+  return (((static_cast<uint64_t>(st) * B + b) * H + h) * L + i) * L + j;
+}
 // plm_mask != nullptr: XLNet's two-stream form (permutation language modeling).  qkv / dout / dqkv then hold 2 B L rows
 // (content stream h, then query stream g); the item runs both streams: queries from the stream's rows, keys / values
 // from the h rows, score (i, j) = -1e30 where plm_mask[b, i, j] (h: except i == j).  The backward uses the same
@@ -220,7 +256,8 @@ constexpr int kAttnMaxL = 64;
 // permutation when every item of a session is a target) p is uniform and the gradient flows as in the reference.
 T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
                           int L, int d, int H, float* dqkv, float* dR_part, float* drw_part, float* drr_part,
-                          const uint8_t* plm_mask, int64_t item) {
+                          const uint8_t* plm_mask, int64_t item, float p_drop = 0.f, uint64_t seed = 0,
+                          uint32_t site = 0) {
   const int dh = d / H;
   const int h = static_cast<int>(item % H);
   const int64_t b = item / H;
@@ -263,19 +300,21 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
     for (int j = 0; j < L; ++j) { s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx); sum += s[j]; }
     const float inv = 1.0f / sum;
     float dot = 0.f;
+    float mk[kAttnMaxL];   // dropout of the probabilities (HF:xlnet:129 / HF:gpt2:66): a_i = sum_j (p_j mk_j) v_j
     for (int j = 0; j < L; ++j) {
       s[j] *= inv;                                            // p_j
+      mk[j] = keep_scale(seed, site, attn_prob_index(st, B, b, H, h, L, i, j), p_drop);
       const float* v = qkv + (b * L + j) * 3 * d + 2 * d + h * dh;
       float acc = 0.f;
       for (int c = 0; c < dh; ++c) acc += dor[c] * v[c];
-      dp[j] = acc;
-      dot += s[j] * acc;
+      dp[j] = acc * mk[j];                                    // d loss / d p_j
+      dot += s[j] * dp[j];
     }
     float* dq = dqkv + (st * M + b * L + i) * 3 * d + h * dh;
     for (int j = 0; j < L; ++j) {
-      const float p = s[j];
       if (!rel && j > i) continue;
-      const float ds = p * (dp[j] - dot) * scale;
+      const float ds = s[j] * (dp[j] - dot) * scale;
+      const float p = s[j] * mk[j];                            // the (dropped) weight v_j entered the output with
       const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
       float* dk = dqkv + (b * L + j) * 3 * d + d + h * dh;
       float* dv = dqkv + (b * L + j) * 3 * d + 2 * d + h * dh;
@@ -298,6 +337,52 @@ T4R_HD void attn_bwd_item(const float* qkv, const float* R, const float* rw, con
           dv[c] += p * dor[c];
         }
       }
+    }
+  }
+}
+
+// Attention FORWARD of the training graph in the same one-item-per-(session, head) form, with dropout of the
+// probabilities (training mode with a dropout rate; without one the training forward runs the inference kernels).
+// out [n_streams * M, d] fp32.
+T4R_HD void attn_fwd_item(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d, int H,
+                          float* out, const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, int64_t item) {
+  const int dh = d / H;
+  const int h = static_cast<int>(item % H);
+  const int64_t b = item / H;
+  const bool rel = R != nullptr;
+  const int n_streams = plm_mask ? 2 : 1;
+  const int64_t M = static_cast<int64_t>(B) * L;
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  float s[kAttnMaxL];
+  for (int st = 0; st < n_streams; ++st)
+  for (int i = 0; i < L; ++i) {
+    const float* q = qkv + (st * M + b * L + i) * 3 * d + h * dh;
+    float mx = -INFINITY;
+    for (int j = 0; j < L; ++j) {
+      const bool masked = plm_mask && plm_mask[(b * L + i) * L + j] && !(st == 0 && i == j);
+      if (masked) { s[j] = -1e30f; mx = fmaxf(mx, s[j]); continue; }
+      if (!rel && j > i) { s[j] = -INFINITY; continue; }
+      const float* k = qkv + (b * L + j) * 3 * d + d + h * dh;
+      float acc = 0.f;
+      if (rel) {
+        const float* Rm = R + static_cast<int64_t>(j + L - i) * d + h * dh;
+        for (int c = 0; c < dh; ++c) acc += (q[c] + rw[h * dh + c]) * k[c] + (q[c] + rr[h * dh + c]) * Rm[c];
+      } else {
+        for (int c = 0; c < dh; ++c) acc += q[c] * k[c];
+      }
+      s[j] = acc * scale;
+      mx = fmaxf(mx, s[j]);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < L; ++j) { s[j] = (s[j] == -INFINITY) ? 0.f : expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float* o = out + (st * M + b * L + i) * d + h * dh;
+    for (int c = 0; c < dh; ++c) o[c] = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float p = s[j] * inv * keep_scale(seed, site, attn_prob_index(st, B, b, H, h, L, i, j), p_drop);
+      if (p == 0.f) continue;
+      const float* v = qkv + (b * L + j) * 3 * d + 2 * d + h * dh;
+      for (int c = 0; c < dh; ++c) o[c] += p * v[c];
     }
   }
 }
@@ -444,9 +529,41 @@ extern "C" int t4r_train_layer_norm_bwd(const float* x, const float* gamma, int6
 }
 // R / rw / rr / dR / drw / drr all NULL selects the causal (GPT-2) form.  part: scratch of B (2L + 2) d floats (relative
 // form): per-session partials of dR / drw / drr, reduced over the sessions here.
+extern "C" int t4r_train_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t site, void* stream,
+                                 int on_host) {
+  T4R_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "train_dropout: bad arguments (0 <= p < 1)");
+  T4R_ITEMS(n, "train_dropout", dropout_item(x, y, p, seed, site, i));
+}
+
+extern "C" int t4r_train_attn_drop_fwd(const float* qkv, const float* R, const float* rw, const float* rr, int B, int L, int d,
+                                       int H, const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, float* out,
+                                       void* stream, int on_host) {
+  T4R_REQUIRE(qkv && out && B > 0 && L > 0 && L <= kAttnMaxL && H > 0 && d % H == 0, "train_attn_drop_fwd: bad arguments (L <= 64)");
+  T4R_REQUIRE((R == nullptr) == (rw == nullptr) && (R == nullptr) == (rr == nullptr), "train_attn_drop_fwd: R, rw, rr go together");
+  T4R_REQUIRE(plm_mask == nullptr || R != nullptr, "train_attn_drop_fwd: the two-stream (PLM) form is XLNet's relative attention");
+  T4R_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "train_attn_drop_fwd: 0 <= p < 1");
+  T4R_ITEMS(static_cast<int64_t>(B) * H, "train_attn_drop_fwd",
+            attn_fwd_item(qkv, R, rw, rr, B, L, d, H, out, plm_mask, p_drop, seed, site, i));
+}
+
+static int attn_bwd_impl(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B, int L,
+                         int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part, const uint8_t* plm_mask,
+                         float p_drop, uint64_t seed, uint32_t site, void* stream, int on_host);
+extern "C" int t4r_train_attn_drop_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout,
+                                       int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
+                                       const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, void* stream,
+                                       int on_host) {
+  T4R_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "train_attn_drop_bwd: 0 <= p < 1");
+  return attn_bwd_impl(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR, drw, drr, part, plm_mask, p_drop, seed, site, stream, on_host);
+}
 extern "C" int t4r_train_attn_bwd(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout,
                                   int B, int L, int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part,
                                   const uint8_t* plm_mask, void* stream, int on_host) {
+  return attn_bwd_impl(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR, drw, drr, part, plm_mask, 0.f, 0, 0, stream, on_host);
+}
+static int attn_bwd_impl(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B, int L,
+                         int d, int H, float* dqkv, float* dR, float* drw, float* drr, float* part, const uint8_t* plm_mask,
+                         float p_drop, uint64_t seed, uint32_t site, void* stream, int on_host) {
   T4R_REQUIRE(qkv && dout && dqkv && B > 0 && L > 0 && L <= kAttnMaxL && H > 0 && d % H == 0, "train_attn_bwd: bad arguments (L <= 64)");
   const bool rel = R != nullptr;
   T4R_REQUIRE(!rel || (rw && rr && dR && drw && drr && part), "train_attn_bwd: the relative form needs R, both biases, their gradients and the scratch");
@@ -455,7 +572,7 @@ extern "C" int t4r_train_attn_bwd(const float* qkv, const float* R, const float*
   float* drw_part = rel ? part + static_cast<int64_t>(B) * 2 * L * d : nullptr;
   float* drr_part = rel ? drw_part + static_cast<int64_t>(B) * d : nullptr;
   T4R_TRY(run_items(static_cast<int64_t>(B) * H, [=] __host__ __device__(int64_t i) {
-            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, i); },
+            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, i, p_drop, seed, site); },
           "train_attn_bwd", stream, on_host));
   if (!rel) return 0;
   T4R_TRY(run_items(static_cast<int64_t>(2) * L * d, [=] __host__ __device__(int64_t i) { sum_sessions_item(dR_part, B, 2 * L, d, dR, i); },

@@ -911,8 +911,36 @@ def layer_norm_bwd(x_pre, gamma, eps, dy, add=None, _on_host=False):
     return dx, dg, db
 
 
-def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None, _on_host=False):
-    """``plm_mask`` [B, L, L] uint8: the two-stream form (qkv / dout hold 2 B L rows: content stream, then query stream)."""
+def dropout(x, p: float, seed: int, site: int, _on_host=False):
+    """x * keep / (1 - p) with the counter-based mask of (seed, site) (t4r_train_dropout); applying it to a gradient
+    with the same (p, seed, site) is the backward.  p == 0 returns x itself."""
+    if p <= 0.0:
+        return x
+    x = _f32c(x)
+    tail = _tr(_on_host, x)
+    y = torch.empty_like(x)
+    check(_lib.load().t4r_train_dropout(ptr(x), ptr(y), x.numel(), float(p), int(seed), int(site), *tail), "t4r_train_dropout")
+    return y
+
+
+def attn_drop_fwd(qkv, R, rw, rr, B, L, H, drop, plm_mask=None, _on_host=False):
+    """Attention forward of the training graph with dropout of the probabilities: ``drop`` = (p, seed, site).
+    R / rw / rr None selects GPT-2's causal form; ``plm_mask`` the two-stream form.  -> fp32 [rows of qkv, d]."""
+    qkv = _f32c(qkv)
+    R, rw, rr = ((_f32c(t) if t is not None else None) for t in (R, rw, rr))
+    plm_mask = plm_mask.to(torch.uint8).contiguous() if plm_mask is not None else None
+    tail = _tr(_on_host, qkv, R, rw, rr, plm_mask)
+    d = qkv.shape[1] // 3
+    out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
+    p, seed, site = drop
+    check(_lib.load().t4r_train_attn_drop_fwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), B, L, d, H, ptr(plm_mask), float(p),
+                                              int(seed), int(site), ptr(out), *tail), "t4r_train_attn_drop_fwd")
+    return out
+
+
+def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None, drop=None, _on_host=False):
+    """``plm_mask`` [B, L, L] uint8: the two-stream form (qkv / dout hold 2 B L rows: content stream, then query stream).
+    ``drop`` = (p, seed, site): the forward dropped its probabilities with that mask."""
     qkv, R, rw, rr, dout = (_f32c(t) for t in (qkv, R, rw, rr, dout))
     plm_mask = plm_mask.to(torch.uint8).contiguous() if plm_mask is not None else None
     tail = _tr(_on_host, qkv, R, rw, rr, dout, plm_mask)
@@ -923,17 +951,27 @@ def xlnet_attn_bwd(qkv, R, rw, rr, dout, B, L, H, plm_mask=None, _on_host=False)
     drw = torch.empty((d,), dtype=torch.float32, device=dev)
     drr = torch.empty((d,), dtype=torch.float32, device=dev)
     part = torch.empty((B * (2 * L + 2) * d,), dtype=torch.float32, device=dev)
-    check(_lib.load().t4r_train_attn_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv), ptr(dR),
-                                         ptr(drw), ptr(drr), ptr(part), ptr(plm_mask), *tail), "t4r_train_attn_bwd")
+    if drop is not None and drop[0] > 0.0:
+        check(_lib.load().t4r_train_attn_drop_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv),
+                                                  ptr(dR), ptr(drw), ptr(drr), ptr(part), ptr(plm_mask), float(drop[0]),
+                                                  int(drop[1]), int(drop[2]), *tail), "t4r_train_attn_drop_bwd")
+    else:
+        check(_lib.load().t4r_train_attn_bwd(ptr(qkv), ptr(R), ptr(rw), ptr(rr), ptr(dout), B, L, d, H, ptr(dqkv), ptr(dR),
+                                             ptr(drw), ptr(drr), ptr(part), ptr(plm_mask), *tail), "t4r_train_attn_bwd")
     return dqkv, dR, drw, drr
 
 
-def causal_attn_bwd(qkv, dout, B, L, H, _on_host=False):
+def causal_attn_bwd(qkv, dout, B, L, H, drop=None, _on_host=False):
     qkv, dout = _f32c(qkv), _f32c(dout)
     tail = _tr(_on_host, qkv, dout)
     dqkv = torch.empty_like(qkv)
-    check(_lib.load().t4r_train_attn_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv), None,
-                                         None, None, None, None, *tail), "t4r_train_attn_bwd")
+    if drop is not None and drop[0] > 0.0:
+        check(_lib.load().t4r_train_attn_drop_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv),
+                                                  None, None, None, None, None, float(drop[0]), int(drop[1]), int(drop[2]),
+                                                  *tail), "t4r_train_attn_drop_bwd")
+    else:
+        check(_lib.load().t4r_train_attn_bwd(ptr(qkv), None, None, None, ptr(dout), B, L, dout.shape[1], H, ptr(dqkv), None,
+                                             None, None, None, None, *tail), "t4r_train_attn_bwd")
     return dqkv
 
 

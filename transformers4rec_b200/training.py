@@ -83,10 +83,20 @@ class _Linear:
 class _XLNetGraph:
     """HF:xlnet:979-1205 as exercised by the reference (oracle: xlnet_forward_restated)."""
 
+    # dropout sites (HF:xlnet): 0 = the input rows (:1085 word_emb_k, :1090 word_emb_q), 5 = the returned rows (:1180);
+    # per layer l, base 16 (l + 1): +0 the relative-position rows R_l (HF drops pos_emb per batch element BEFORE its
+    # projection, :1159 -- here the projected table shared by the whole batch is dropped instead, which keeps the
+    # one-R-per-layer precomputation; a different draw of the same regulariser), +1 the attention probabilities
+    # (:129), +2 the output projection before the residual (:147), +3 after the activation (:300), +4 after layer_2
+    # (:302).  Active when the encoder module is in train() mode and its config carries a rate.
     def __init__(self, enc: XLNetEncoder):
         self.enc = enc
         cfg = enc.config
         self.d, self.H, self.eps = cfg.d_model, cfg.n_head, float(cfg.layer_norm_eps)
+        self.seed = 0
+
+    def _rate(self) -> float:
+        return float(getattr(self.enc.config, "dropout", 0.0) or 0.0) if self.enc.training else 0.0
 
     def fwd(self, x: torch.Tensor, B: int, L: int, plm_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``plm_mask`` [B, L, L]: permutation language modeling -- the content stream (x) and the query stream (mask_emb
@@ -94,61 +104,82 @@ class _XLNetGraph:
         d, H = self.d, self.H
         self.B, self.L, self.plm_mask = B, L, plm_mask
         self.tape = []
+        p = self.p = self._rate()
+        D = (lambda t, site: ops.dropout(t, p, self.seed, site))
         R_all = ops.rel_pos_proj([lyr.rel_attn.r.detach().reshape(d, d).contiguous() for lyr in self.enc.layer], L, d)
         h = x
         if plm_mask is not None:
             h = torch.cat([x, self.enc.mask_emb.detach().reshape(1, d).float().expand(B * L, d)], dim=0).contiguous()
+        if p:
+            h = D(h, 0)
         for li, lyr in enumerate(self.enc.layer):
             ra, ff = lyr.rel_attn, lyr.ff
+            s0 = 16 * (li + 1)
             t = {}
-            wqkv = torch.cat([p.detach().reshape(d, d).t() for p in (ra.q, ra.k, ra.v)], dim=0)   # [3d, d]
+            wqkv = torch.cat([q.detach().reshape(d, d).t() for q in (ra.q, ra.k, ra.v)], dim=0)   # [3d, d]
             t["qkv_lin"] = _Linear(wqkv)
             qkv = t["qkv_lin"].fwd(h)
-            t["qkv"], t["R"] = qkv, R_all[li]
+            t["qkv"], t["R"] = qkv, (D(R_all[li], s0) if p else R_all[li])
             t["rw"], t["rr"] = ra.r_w_bias.detach().reshape(-1).float(), ra.r_r_bias.detach().reshape(-1).float()
-            a = (ops.xlnet_attn_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H) if plm_mask is None else
-                 ops.xlnet_attn_plm_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H, plm_mask))
+            if p:
+                a = ops.attn_drop_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H, (p, self.seed, s0 + 1), plm_mask=plm_mask)
+            else:
+                a = (ops.xlnet_attn_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H) if plm_mask is None else
+                     ops.xlnet_attn_plm_fwd(qkv, t["R"], t["rw"], t["rr"], B, L, H, plm_mask))
             t["o_lin"] = _Linear(ra.o.detach().reshape(d, d))
-            h1_pre = t["o_lin"].fwd(a, residual=h)
+            h1_pre = ops.ew_add(D(t["o_lin"].fwd(a), s0 + 2), h) if p else t["o_lin"].fwd(a, residual=h)
             t["h1_pre"] = h1_pre
             h1 = ops.layer_norm_fwd(h1_pre, ra.layer_norm.weight.detach(), ra.layer_norm.bias.detach(), self.eps)
             t["w1"] = _Linear(ff.layer_1.weight, ff.layer_1.bias)
             ffp = t["w1"].fwd(h1)
             t["ffp"] = ffp
             g = ops.act_fwd(_lib.ACT_GELU, ffp)
+            if p:
+                g = D(g, s0 + 3)
             t["w2"] = _Linear(ff.layer_2.weight, ff.layer_2.bias)
-            y_pre = t["w2"].fwd(g, residual=h1)
+            y_pre = ops.ew_add(D(t["w2"].fwd(g), s0 + 4), h1) if p else t["w2"].fwd(g, residual=h1)
             t["y_pre"] = y_pre
             h = ops.layer_norm_fwd(y_pre, ff.layer_norm.weight.detach(), ff.layer_norm.bias.detach(), self.eps)
             self.tape.append(t)
-        return h if plm_mask is None else h[B * L:]
+        out = h if plm_mask is None else h[B * L:].contiguous()
+        return D(out, 5) if p else out
 
     def bwd(self, dh: torch.Tensor) -> torch.Tensor:
         d, H, B, L = self.d, self.H, self.B, self.L
+        p = self.p
+        D = (lambda t, site: ops.dropout(t, p, self.seed, site))   # the same mask on the gradient = the backward
+        if p:
+            dh = D(dh, 5)
         if self.plm_mask is not None:      # only the query stream's output was used
             dh = torch.cat([torch.zeros_like(dh), dh], dim=0).contiguous()
         for li in reversed(range(len(self.enc.layer))):
             lyr, t = self.enc.layer[li], self.tape[li]
             ra, ff = lyr.rel_attn, lyr.ff
+            s0 = 16 * (li + 1)
             dy_pre, dg2, db2 = ops.layer_norm_bwd(t["y_pre"], ff.layer_norm.weight.detach(), self.eps, dh)
             _acc(ff.layer_norm.weight, dg2); _acc(ff.layer_norm.bias, db2)
-            dgel, dw2, dbias2 = t["w2"].bwd(dy_pre)
+            dgel, dw2, dbias2 = t["w2"].bwd(D(dy_pre, s0 + 4) if p else dy_pre)
             _acc(ff.layer_2.weight, dw2); _acc(ff.layer_2.bias, dbias2)
-            dffp = ops.act_bwd(_lib.ACT_GELU, t["ffp"], dgel)
+            dffp = ops.act_bwd(_lib.ACT_GELU, t["ffp"], D(dgel, s0 + 3) if p else dgel)
             dh1, dw1, dbias1 = t["w1"].bwd(dffp, add_to_dx=dy_pre)   # + the residual branch of the feed-forward block
             _acc(ff.layer_1.weight, dw1); _acc(ff.layer_1.bias, dbias1)
             dh1_pre, dg1, db1 = ops.layer_norm_bwd(t["h1_pre"], ra.layer_norm.weight.detach(), self.eps, dh1)
             _acc(ra.layer_norm.weight, dg1); _acc(ra.layer_norm.bias, db1)
-            da, dwo, _ = t["o_lin"].bwd(dh1_pre)
+            da, dwo, _ = t["o_lin"].bwd(D(dh1_pre, s0 + 2) if p else dh1_pre)
             _acc(ra.o, dwo)                                       # o: [d_model, H, dh] == Linear weight [d, HD]
-            dqkv, dR, drw, drr = ops.xlnet_attn_bwd(t["qkv"], t["R"], t["rw"], t["rr"], da, B, L, H, plm_mask=self.plm_mask)
+            dqkv, dR, drw, drr = ops.xlnet_attn_bwd(t["qkv"], t["R"], t["rw"], t["rr"], da, B, L, H, plm_mask=self.plm_mask,
+                                                    drop=(p, self.seed, s0 + 1) if p else None)
             _acc(ra.r_w_bias, drw); _acc(ra.r_r_bias, drr)
+            if p:
+                dR = D(dR, s0)
             # R = pos @ Wr  (Wr = r.reshape(d, HD)):  dWr = pos^T dR
             pos = ops.rel_pos_table(L, d, dh.device)
             _acc(ra.r, gemm_nt(ops.transpose(pos), ops.transpose(dR)))
             dh, dwqkv, _ = t["qkv_lin"].bwd(dqkv, add_to_dx=dh1_pre)  # + the residual branch of the attention block
-            for j, p in enumerate((ra.q, ra.k, ra.v)):            # rows [j d, (j+1) d) of the fused weight = W_j^T
-                _acc(p, dwqkv[j * d:(j + 1) * d].t().contiguous())
+            for j, prm in enumerate((ra.q, ra.k, ra.v)):          # rows [j d, (j+1) d) of the fused weight = W_j^T
+                _acc(prm, dwqkv[j * d:(j + 1) * d].t().contiguous())
+        if p:
+            dh = D(dh, 0)
         if self.plm_mask is not None:      # the query stream started from mask_emb in every row
             M = B * L
             _acc(self.enc.mask_emb, ops.col_sum(dh[M:].contiguous()))
@@ -159,25 +190,40 @@ class _XLNetGraph:
 class _GPT2Graph:
     """HF:gpt2:522-636 as exercised by the reference (oracle: gpt2_forward_restated); Conv1D weights are [in, out]."""
 
+    # dropout sites (HF:gpt2; GPT2Config.build sets embd / attn / resid_pdrop to one rate): 0 = after the position
+    # embeddings are added (:584 self.drop), per layer l, base 16 (l + 1): +1 the attention probabilities (:66),
+    # +2 the attention output projection (:225 resid_dropout), +4 the MLP output projection (:241).
     def __init__(self, enc: GPT2Encoder):
         self.enc = enc
         cfg = enc.config
         self.d, self.H, self.eps = cfg.n_embd, cfg.n_head, float(cfg.layer_norm_epsilon)
+        self.seed = 0
+
+    def _rates(self):
+        cfg = self.enc.config
+        if not self.enc.training:
+            return 0.0, 0.0, 0.0
+        return tuple(float(getattr(cfg, k, 0.0) or 0.0) for k in ("embd_pdrop", "attn_pdrop", "resid_pdrop"))
 
     def fwd(self, x: torch.Tensor, B: int, L: int) -> torch.Tensor:
         d, H, enc = self.d, self.H, self.enc
         self.B, self.L = B, L
         self.tape = []
+        pe, pa, pr = self.rates = self._rates()
+        D = (lambda t, rate, site: ops.dropout(t, rate, self.seed, site))
         h = ops.add_positions(x, enc.wpe.weight.detach(), B, L)
-        for blk in enc.h:
+        h = D(h, pe, 0)
+        for li, blk in enumerate(enc.h):
+            s0 = 16 * (li + 1)
             t = {"h_in": h}
             a = ops.layer_norm_fwd(h, blk.ln_1.weight.detach(), blk.ln_1.bias.detach(), self.eps)
             t["qkv_lin"] = _Linear(blk.attn.c_attn.weight.detach().t(), blk.attn.c_attn.bias)
             qkv = t["qkv_lin"].fwd(a)
             t["qkv"] = qkv
-            o = ops.causal_attn_fwd(qkv, B, L, H)
+            o = (ops.attn_drop_fwd(qkv, None, None, None, B, L, H, (pa, self.seed, s0 + 1)) if pa else
+                 ops.causal_attn_fwd(qkv, B, L, H))
             t["o_lin"] = _Linear(blk.attn.c_proj.weight.detach().t(), blk.attn.c_proj.bias)
-            h = t["o_lin"].fwd(o, residual=h)
+            h = ops.ew_add(D(t["o_lin"].fwd(o), pr, s0 + 2), h) if pr else t["o_lin"].fwd(o, residual=h)
             t["h_mid"] = h
             m = ops.layer_norm_fwd(h, blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), self.eps)
             t["fc"] = _Linear(blk.mlp.c_fc.weight.detach().t(), blk.mlp.c_fc.bias)
@@ -185,32 +231,36 @@ class _GPT2Graph:
             t["fp"] = fp
             g = ops.act_fwd(_lib.ACT_GELU, fp)
             t["pr"] = _Linear(blk.mlp.c_proj.weight.detach().t(), blk.mlp.c_proj.bias)
-            h = t["pr"].fwd(g, residual=h)
+            h = ops.ew_add(D(t["pr"].fwd(g), pr, s0 + 4), h) if pr else t["pr"].fwd(g, residual=h)
             self.tape.append(t)
         self.h_last = h
         return ops.layer_norm_fwd(h, enc.ln_f.weight.detach(), enc.ln_f.bias.detach(), self.eps)
 
     def bwd(self, dout: torch.Tensor) -> torch.Tensor:
         enc, H, B, L = self.enc, self.H, self.B, self.L
+        pe, pa, pr = self.rates
+        D = (lambda t, rate, site: ops.dropout(t, rate, self.seed, site))
         dh, dg, db = ops.layer_norm_bwd(self.h_last, enc.ln_f.weight.detach(), self.eps, dout)
         _acc(enc.ln_f.weight, dg); _acc(enc.ln_f.bias, db)
         for li in reversed(range(len(enc.h))):
             blk, t = enc.h[li], self.tape[li]
-            dgel, dwp, dbp = t["pr"].bwd(dh)
+            s0 = 16 * (li + 1)
+            dgel, dwp, dbp = t["pr"].bwd(D(dh, pr, s0 + 4))
             _acc(blk.mlp.c_proj.weight, dwp.t()); _acc(blk.mlp.c_proj.bias, dbp)
             dfp = ops.act_bwd(_lib.ACT_GELU, t["fp"], dgel)
             dm, dwf, dbf = t["fc"].bwd(dfp)
             _acc(blk.mlp.c_fc.weight, dwf.t()); _acc(blk.mlp.c_fc.bias, dbf)
             dh, dg2, db2 = ops.layer_norm_bwd(t["h_mid"], blk.ln_2.weight.detach(), self.eps, dm, add=dh)
             _acc(blk.ln_2.weight, dg2); _acc(blk.ln_2.bias, db2)
-            do, dwo, dbo = t["o_lin"].bwd(dh)
+            do, dwo, dbo = t["o_lin"].bwd(D(dh, pr, s0 + 2))
             _acc(blk.attn.c_proj.weight, dwo.t()); _acc(blk.attn.c_proj.bias, dbo)
-            dqkv = ops.causal_attn_bwd(t["qkv"], do, B, L, H)
+            dqkv = ops.causal_attn_bwd(t["qkv"], do, B, L, H, drop=(pa, self.seed, s0 + 1) if pa else None)
             da, dwq, dbq = t["qkv_lin"].bwd(dqkv)
             _acc(blk.attn.c_attn.weight, dwq.t()); _acc(blk.attn.c_attn.bias, dbq)
             dh, dg1, db1 = ops.layer_norm_bwd(t["h_in"], blk.ln_1.weight.detach(), self.eps, da, add=dh)
             _acc(blk.ln_1.weight, dg1); _acc(blk.ln_1.bias, db1)
-        # h0 = x + wpe[:L]
+        # h0 = dropout(x + wpe[:L])
+        dh = D(dh, pe, 0)
         _acc_rows(enc.wpe.weight, ops.sum_over_sessions(dh, B, L), L)
         return dh
 
@@ -400,17 +450,21 @@ class FusedTrainingStep:
         self.graph = _XLNetGraph(enc) if isinstance(enc, XLNetEncoder) else _GPT2Graph(enc)
         self.layout = layout
         self.head_chunk = int(head_chunk)
-        cfg = enc.config
-        rates = [float(getattr(cfg, k, 0.0) or 0.0) for k in ("dropout", "resid_pdrop", "embd_pdrop", "attn_pdrop")]
-        if max(rates) > 0.0:
-            # config/transformer.py:217-260,432-482 default to dropout = 0.3, which the reference applies in train() mode
-            LOG.warning("FusedTrainingStep: the encoder is configured with dropout %.2f; the fused training step applies "
-                        "no dropout (build the config with dropout=0 to train the same function as the reference)",
-                        max(rates))
+        # Dropout (config/transformer.py:217-260, :432-482 default to 0.3): applied at HF's sites whenever the encoder
+        # module is in train() mode, as in the reference (Model.fit calls self.train(), model/base.py:692); the masks
+        # are counter-based (seed, step, site), regenerated in the backward.  ``set_dropout_seed`` pins the stream.
+        self.dropout_seed = int(torch.initial_seed()) & ((1 << 62) - 1)
+        self.dropout_step = 0
+
+    def set_dropout_seed(self, seed: int, step: int = 0):
+        self.dropout_seed, self.dropout_step = int(seed) & ((1 << 62) - 1), int(step)
+        return self
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         inp, task = self.inputs, self.task
+        self.graph.seed = (self.dropout_seed + 0x9E3779B97F4A7C15 * self.dropout_step) & ((1 << 64) - 1)
+        self.dropout_step += 1
         cm = inp.categorical_module
         if inp.pre is not None:    # StochasticSwapNoise (tabular/transformations.py:29-92): a permutation of the RAW
             batch = inp.pre(dict(batch))   # inputs, constant w.r.t. every parameter -- applied once, then forgotten
