@@ -230,7 +230,10 @@ def label_logit(xt_f32, w_f32, labels, *, t_dev=None, class_bias=None, inv_tempe
 
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True, nprod=3,
-                    events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None):
+                    events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None, out_stats=None,
+                    col_ids_sorted_unique=False):
+    if col_ids is not None and col_ids_sorted_unique:
+        assert bool((col_ids[1:] > col_ids[:-1]).all()), "col_ids_sorted_unique promised, but the ids are not ascending"
     if nprod == 2 and (xt_inv_scale is None or w_inv_scale is None):
         raise _lib.T4RError("head_softmax_ce: nprod=2 needs the mixed planes' inverse row scales")
     T_cap, V = xt_planes.shape[1], w_planes.shape[1]

@@ -272,7 +272,7 @@ def test_ctypes_structs_mirror_the_compiled_layouts():
     for which, cls in enumerate(mirrors):
         assert lib.t4r_sizeof_struct(which) == C.sizeof(cls), (cls.__name__, lib.t4r_sizeof_struct(which), C.sizeof(cls))
     assert lib.t4r_sizeof_struct(99) == 0
-    assert lib.t4r_head_args_last_offset() == _lib.HeadArgs.w_inv_scale.offset
+    assert lib.t4r_head_args_last_offset() == _lib.HeadArgs.col_ids_sorted_unique.offset
 
 
 def test_bench_reference_arm_prints_the_contract_line():

@@ -80,6 +80,8 @@ def test_task_block_and_mixed_head_arithmetic(monkeypatch):
     monkeypatch.setattr(ops, "head_softmax_ce", lambda *a, **k: (calls.append((k.get("nprod"), k.get("want_rank"))), real(*a, **k))[1])
     with torch.no_grad():
         ref = oracle(batch, training=True, draws=draws)["loss"].item()
+        assert task.nprod == 2       # the library default since round 2 (device-side error table: profiles/)
+        task.nprod = 3
         l3 = model(batch, training=True)["loss"].item()
         lse3 = task._last["row_lse"].clone()
         task.nprod = 2

@@ -123,6 +123,7 @@ class HeadArgs(C.Structure):
         ("rank_tgt", c_void_p),
         ("xt_inv_scale", c_void_p),
         ("w_inv_scale", c_void_p),
+        ("col_ids_sorted_unique", c_int),
     ]
 
 

@@ -447,7 +447,7 @@ extern "C" size_t t4r_head_workspace_bytes(int T_cap, int64_t V, int De) {
   (void)De;
   const size_t part_ld = static_cast<size_t>((T_cap + 127) / 128) * 128;
   const size_t n_tiles = 2 * static_cast<size_t>((V + kHeadBN - 1) / kHeadBN);  // two column halves per tile
-  return 3 * pad256(n_tiles * part_ld * 4) + pad256(3 * 64 * part_ld * 4) + 1024;
+  return 3 * pad256(n_tiles * part_ld * 4) + pad256(3 * 64 * part_ld * 4) + pad256(part_ld * 4) + 1024;
 }
 
 extern "C" size_t t4r_sizeof_struct(int which) {
@@ -461,7 +461,7 @@ extern "C" size_t t4r_sizeof_struct(int which) {
     default: return 0;
   }
 }
-extern "C" size_t t4r_head_args_last_offset(void) { return offsetof(t4r_head_args, w_inv_scale); }
+extern "C" size_t t4r_head_args_last_offset(void) { return offsetof(t4r_head_args, col_ids_sorted_unique); }
 
 extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   T4R_REQUIRE(a != nullptr, "head: null args");
@@ -481,6 +481,7 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   float* part_m = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
   float* part_s = ar.take<float>(static_cast<size_t>(n_tiles) * part_ld);
   float* scratch = ar.take<float>(static_cast<size_t>(3) * 64 * part_ld);
+  int32_t* hit_col = reinterpret_cast<int32_t*>(ar.take<float>(part_ld));
   float* part_z = nullptr;
   if (a->label_smoothing != 0.f) {
     T4R_REQUIRE(a->pos_logit == nullptr && a->v_offset == 0, "head: label smoothing needs the unsharded full softmax");
@@ -516,6 +517,12 @@ extern "C" int t4r_head_softmax_ce_fwd(const t4r_head_args* a, void* stream) {
   ep.inv_tau = inv_tau;
   ep.col_bias = a->col_bias;
   ep.col_ids = a->col_ids;
+  if (a->col_ids && a->col_ids_sorted_unique && a->labels && a->V < (1ll << 31)) {
+    // one binary search per row instead of one 8-byte id comparison per logit
+    T4R_TRY(launch_hit_cols(a->col_ids, a->V, a->labels, a->T_cap, a->t_dev, hit_col, s));
+    ep.hit_col = hit_col;
+    ep.col_ids = nullptr;
+  }
   ep.row_label = a->labels;
   ep.hit_value = a->hit_value;
   ep.row_tgt = a->rank_tgt ? a->rank_tgt : a->row_tgt;

@@ -573,6 +573,7 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
   const bool want_rank = (ep.row_rank != nullptr);
   if (row_ok && ep.row_label) label = ep.row_label[row];
   if (row_ok && want_rank) tgt = ep.row_tgt[row];
+  const int hit_c = (row_ok && ep.hit_col) ? ep.hit_col[row] : -1;
   const float row_scale = (row_ok && ep.row_scale) ? ep.row_scale[row] : 1.f;
   const bool full_tile = (n0 + COLS <= p.N);
 #pragma unroll 1
@@ -599,11 +600,27 @@ __device__ __forceinline__ void epilogue_head(const GemmDev& p, uint32_t taddr, 
       }
     }
     if (ep.col_bias) {
+      if (full_tile && (ncol0 & 3) == 0) {
+        const float4* b4 = reinterpret_cast<const float4*>(ep.col_bias + ncol0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (full_tile || ncol0 + j < p.N) v[j] += __ldg(ep.col_bias + ncol0 + j);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full_tile || ncol0 + j < p.N) v[j] += __ldg(ep.col_bias + ncol0 + j);
+      }
     }
-    if (ep.col_ids) {
+    if (ep.hit_col) {           // the row's accidental hit, found once per row (launch_hit_cols)
+      const int64_t rel = static_cast<int64_t>(hit_c) - ncol0;
+      if (rel >= 0 && rel < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j == rel) v[j] = ep.hit_value;
+      }
+    } else if (ep.col_ids) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if ((full_tile || ncol0 + j < p.N) && __ldg(ep.col_ids + ncol0 + j) == label) v[j] = ep.hit_value;
@@ -1066,6 +1083,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 struct HeadRowState {
   float m_run, s_run, z_run, tgt, row_scale;
   int cnt;
+  int hit_col;
   int64_t label;
 };
 __device__ __forceinline__ void head_state_init(HeadRowState& st, const GemmEpilogue& ep, int64_t row, bool row_ok) {
@@ -1073,6 +1091,7 @@ __device__ __forceinline__ void head_state_init(HeadRowState& st, const GemmEpil
   if (row_ok && ep.row_label) st.label = ep.row_label[row];
   if (row_ok && ep.row_rank) st.tgt = ep.row_tgt[row];
   st.row_scale = (row_ok && ep.row_scale) ? ep.row_scale[row] : 1.f;
+  st.hit_col = (row_ok && ep.hit_col) ? ep.hit_col[row] : -1;
 }
 template <int BN>
 __device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev& p, uint32_t taddr, bool row_ok, int64_t n0) {
@@ -1087,7 +1106,7 @@ __device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev&
   // inside V): packed fp32 pairs (fmul2 / ffma2 / fadd2) halve the FMA-pipe instructions per logit and the row scale
   // of the 2-unit product rides in the exponent's scale factor instead of costing a multiply per logit.  With K = 64
   // (config 3) or nprod = 2 the main loop is short enough for this epilogue to be on the critical path.
-  if (full_tile && !ep.col_bias && !ep.col_ids && !want_rank && !want_z) {
+  if (full_tile && !ep.col_bias && !ep.col_ids && !ep.hit_col && !want_rank && !want_z) {
     const float scale2r = scale2 * st.row_scale;  // > 0: power-of-two row scale
 #pragma unroll 1
     for (int c = 0; c < COLS / 32; ++c) {
@@ -1150,11 +1169,27 @@ __device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev&
       }
     }
     if (ep.col_bias) {
+      if (full_tile && (ncol0 & 3) == 0) {
+        const float4* b4 = reinterpret_cast<const float4*>(ep.col_bias + ncol0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (full_tile || ncol0 + j < p.N) v[j] += __ldg(ep.col_bias + ncol0 + j);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full_tile || ncol0 + j < p.N) v[j] += __ldg(ep.col_bias + ncol0 + j);
+      }
     }
-    if (ep.col_ids) {
+    if (ep.hit_col) {           // the row's accidental hit, found once per row (launch_hit_cols)
+      const int64_t rel = static_cast<int64_t>(st.hit_col) - ncol0;
+      if (rel >= 0 && rel < 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j == rel) v[j] = ep.hit_value;
+      }
+    } else if (ep.col_ids) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if ((full_tile || ncol0 + j < p.N) && __ldg(ep.col_ids + ncol0 + j) == st.label) v[j] = ep.hit_value;

@@ -76,6 +76,7 @@ struct GemmEpilogue {
   float inv_tau = 1.f;
   const float* col_bias = nullptr;     // [N]
   const int64_t* col_ids = nullptr;    // [N]
+  const int32_t* hit_col = nullptr;    // [M] column holding the row's own label (accidental hit) or -1; replaces col_ids
   const int64_t* row_label = nullptr;  // [M]
   float hit_value = 0.f;
   const float* row_tgt = nullptr;      // [M] label logit (already scaled), for ranks
@@ -134,6 +135,8 @@ int launch_head_reduce(const float* part_m, const float* part_s, const float* pa
                        int T_cap, const int32_t* t_dev, const float* pos_logit, const float* row_tgt_in,
                        float label_smoothing, int64_t n_classes, float* row_lse, float* row_loss, float* loss,
                        float* scratch, cudaStream_t s);
+int launch_hit_cols(const int64_t* col_ids, int64_t S, const int64_t* labels, int T_cap, const int32_t* t_dev,
+                    int32_t* hit_col, cudaStream_t s);
 int launch_target_logit(const float* xt, const float* w, const int64_t* labels, int T_cap, const int32_t* t_dev,
                         int De, int64_t v_offset, int64_t V, const float* class_bias, float inv_tau, float* out,
                         cudaStream_t s);

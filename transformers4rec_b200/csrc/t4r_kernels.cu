@@ -1040,6 +1040,33 @@ combine_shard_lse_kernel(const float* __restrict__ parts, int world, int T_cap, 
   row_loss[row] = (m + logf(s)) - tgt;
 }
 
+// accidental hits of the sampled softmax: hit_col[t] = the column c with col_ids[c] == labels[t], -1 if none.
+// col_ids strictly ascending (unique negatives, sorted): one binary search per row.
+__global__ void __launch_bounds__(256)
+hit_cols_kernel(const int64_t* __restrict__ col_ids, int S, const int64_t* __restrict__ labels, int T_cap,
+                const int32_t* __restrict__ t_dev, int32_t* __restrict__ hit_col) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_cap) return;
+  const int T = t_dev ? min(*t_dev, T_cap) : T_cap;
+  int32_t hit = -1;
+  if (t < T) {
+    const int64_t y = labels[t];
+    int lo = 0, hi = S;   // first column with col_ids >= y
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(col_ids + mid) < y) lo = mid + 1; else hi = mid;
+    }
+    if (lo < S && __ldg(col_ids + lo) == y) hit = lo;
+  }
+  hit_col[t] = hit;
+}
+int launch_hit_cols(const int64_t* col_ids, int64_t S, const int64_t* labels, int T_cap, const int32_t* t_dev,
+                    int32_t* hit_col, cudaStream_t s) {
+  hit_cols_kernel<<<(T_cap + 255) / 256, 256, 0, s>>>(col_ids, static_cast<int>(S), labels, T_cap, t_dev, hit_col);
+  T4R_LAUNCH_CHECK("hit_cols_kernel");
+  return 0;
+}
+
 int launch_mean_rows(const float* rows, int cap, const int32_t* t_dev, float* out, cudaStream_t s) {
   mean_rows_kernel<<<1, 1024, 0, s>>>(rows, cap, t_dev, out);
   T4R_LAUNCH_CHECK("mean_rows_kernel");

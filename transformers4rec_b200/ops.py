@@ -522,7 +522,7 @@ def gpt2_encoder(layers_struct, n_layer: int, B: int, L: int, d: int, n_head: in
 def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, inv_temperature=1.0, col_bias=None,
                     col_ids=None, hit_value=0.0, pos_logit=None, v_offset=0, want_rank=False, want_loss=True,
                     nprod=3, events=None, label_smoothing=0.0, rank_tgt=None, xt_inv_scale=None, w_inv_scale=None,
-                    out_stats: Optional[torch.Tensor] = None):
+                    out_stats: Optional[torch.Tensor] = None, col_ids_sorted_unique: bool = False):
     """Fused logits + log-sum-exp + CE.  Returns dict(row_lse,row_tgt,row_loss,loss,row_rank).
     ``out_stats``: caller-owned fp32 [3, T_cap] buffer that receives row_lse | row_tgt | row_rank (int32 bits) --
     the layout ``peer_combine_lse`` reads from every shard's window."""
@@ -556,6 +556,7 @@ def head_softmax_ce(xt_planes, xt_f32, labels, w_planes, w_f32, *, t_dev=None, i
     a.nprod = nprod
     a.label_smoothing = float(label_smoothing)
     a.rank_tgt = ptr(rank_tgt)
+    a.col_ids_sorted_unique = 1 if (col_ids is not None and col_ids_sorted_unique) else 0
     if nprod == 2:
         if xt_inv_scale is None or w_inv_scale is None:
             raise _lib.T4RError("head_softmax_ce: nprod=2 needs the mixed planes' inverse row scales")

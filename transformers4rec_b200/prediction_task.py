@@ -305,7 +305,7 @@ class NextItemPredictionTask(PredictionTask):
                 pos = ops.label_logit(xt_f32, Wd, tgt_labels, t_dev=count, class_bias=self.sampler.neg_log_q,
                                       inv_temperature=inv_tau)
                 res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, neg_planes, None, t_dev=count,
-                                          inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg,
+                                          inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg, col_ids_sorted_unique=True,
                                           hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos,
                                           nprod=self._dense_nprod())
                 self._last = dict(xt_planes=xt_planes, w_planes=neg_planes, count=count, neg=neg, pos=pos,
@@ -387,7 +387,7 @@ class NextItemPredictionTask(PredictionTask):
             pos = ops.label_logit(xt, wy, torch.arange(T, device=xt.device), class_bias=self.sampler.neg_log_q[y].contiguous(),
                                   inv_temperature=inv_tau)
             xp = xt_planes[:, :T].contiguous()
-            res = ops.head_softmax_ce(xp, xt, y, neg_planes, None, inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg,
+            res = ops.head_softmax_ce(xp, xt, y, neg_planes, None, inv_temperature=inv_tau, col_bias=col_bias, col_ids=neg, col_ids_sorted_unique=True,
                                       hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=pos,
                                       nprod=self._dense_nprod())
             tot = torch.stack([res["row_loss"][:T].sum(), torch.tensor(float(T), device=xt.device)])
@@ -446,7 +446,7 @@ class NextItemPredictionTask(PredictionTask):
             pos = ops.label_logit(xt_f32, wy, torch.arange(cap, device=xt_f32.device), t_dev=count,
                                   class_bias=self.sampler.neg_log_q[tgt_labels].contiguous(), inv_temperature=inv_tau)
             res = ops.head_softmax_ce(xt_planes, xt_f32, tgt_labels, neg_planes, None, t_dev=count, inv_temperature=inv_tau,
-                                      col_bias=col_bias, col_ids=neg, hit_value=float(torch.finfo(torch.float16).min / 100.0),
+                                      col_bias=col_bias, col_ids=neg, col_ids_sorted_unique=True, hit_value=float(torch.finfo(torch.float16).min / 100.0),
                                       pos_logit=pos, nprod=self._dense_nprod())
             n = count.to(torch.float32)
             tot = torch.cat([res["loss"].reshape(1) * n, n])

@@ -560,7 +560,7 @@ class FusedTrainingStep:
             self.neg_rows = ops.gather_rows(W, neg)
             self.pos = ops.label_logit(xt, W, y_lab, class_bias=nlq, inv_temperature=inv_tau)
             res = ops.head_softmax_ce(ops.split_planes(xt), xt, y_lab, ops.split_planes(self.neg_rows), None,
-                                      inv_temperature=inv_tau, col_bias=self.col_bias, col_ids=neg,
+                                      inv_temperature=inv_tau, col_bias=self.col_bias, col_ids=neg, col_ids_sorted_unique=True,
                                       hit_value=float(torch.finfo(torch.float16).min / 100.0), pos_logit=self.pos)
             self.row_lse = res["row_lse"]
             self.loss = res["loss"].reshape(())
