@@ -128,11 +128,12 @@ class LogUniformSampler(nn.Module):
         return (-(-dist.double().log1p_() * n_sample).expm1_()).float()
 
     def draw(self) -> torch.Tensor:
-        if self.dist.numel() <= (1 << 24):
+        if self.dist.numel() <= (1 << 20):
             return torch.multinomial(self.dist, self.n_sample, replacement=True)
         # torch.multinomial stops at 2^24 categories (the reference's sampler cannot run BASELINE config 5's
-        # 50 M items at all).  Same distribution by inverting its CDF, log(k + 2) / log(R + 1) for the k-th id
-        # of the range (:766-787): k = floor(exp(u * log(R + 1))) - 1, in fp64.
+        # 50 M items at all) and costs milliseconds per draw long before that (measured: 4 ms of a 10.8 ms config-5
+        # step at 6.25 M categories).  Same distribution by inverting its CDF, log(k + 2) / log(R + 1) for the k-th
+        # id of the range (:766-787): k = floor(exp(u * log(R + 1))) - 1, in fp64.
         R = self.max_id - self.min_id
         u = torch.rand(self.n_sample, dtype=torch.float64, device=self.dist.device)
         k = torch.exp(u * math.log(R + 1.0)).floor().long().sub_(1).clamp_(0, R - 1)
