@@ -235,6 +235,31 @@ def test_xlnet_encoder_matches_hf(d, H, NL, B, L):
     assert err < TOL, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("d,H,NL,B,L,parts", [(256, 8, 2, 128, 20, 2), (64, 4, 3, 256, 20, 4), (128, 8, 1, 64, 50, 2),
+                                              (256, 8, 1, 60, 20, 4), (64, 4, 1, 7, 20, 2)])
+def test_xlnet_encoder_row_parts_on_concurrent_streams(monkeypatch, d, H, NL, B, L, parts):
+    """T4R_ENC_PARTS: the session ranges of the batch run their layer chains on separate streams.  Every row's
+    arithmetic is unchanged, so the result must be BIT-identical to the single-stream run (and within the bar of HF);
+    shapes that do not divide (B = 60 into 4 parts of >= 512 rows, B = 7) fall back to fewer parts."""
+    import transformers4rec_b200.torch as tr
+    torch.manual_seed(12)
+    hf = O.build_hf_xlnet(d, H, NL).eval()
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            p.normal_(0.0, 0.08) if "layer_norm" not in n else p.add_(torch.randn_like(p) * 0.1)
+    blk = tr.TransformerBlock(hf).cuda()
+    x = torch.randn(B, L, d)
+    with torch.no_grad():
+        monkeypatch.setenv("T4R_ENC_PARTS", "1")
+        one = blk(x.cuda())
+        monkeypatch.setenv("T4R_ENC_PARTS", str(parts))
+        many = [blk(x.cuda()) for _ in range(3)]       # repeated: the fork / join events are reused across calls
+        torch.cuda.synchronize()
+        ref = O.hf_encoder_forward(hf, x)
+    assert all(torch.equal(one, m) for m in many)
+    assert (one.cpu() - ref).abs().max().item() < TOL
+
+
 @pytest.mark.parametrize("d,H,NL,B,L", [(64, 4, 2, 33, 20), (256, 8, 2, 16, 20), (128, 2, 1, 7, 40), (64, 4, 1, 1, 2),
                                         (64, 1, 1, 2, 64), (128, 4, 1, 5, 32), (128, 4, 1, 5, 33)])
 def test_gpt2_encoder_matches_hf(d, H, NL, B, L):

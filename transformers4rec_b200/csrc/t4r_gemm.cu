@@ -2271,13 +2271,15 @@ bool ffn_fused_supported(int d, int hidden) { return (d == 64 || d == 128 || d =
 // x_planes [2, M, d], w1_planes [2, hidden, d], w2_planes [2, d, hidden]; `ep` = final epilogue (bias = b2,
 // residual / residual_planes, ln_gamma/beta/eps, out_f32 / out_pre / out_planes, all with row length d).
 int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden, const __nv_bfloat16* w1_planes,
-                     const float* b1, const __nv_bfloat16* w2_planes, const GemmEpilogue& ep, cudaStream_t stream) {
+                     const float* b1, const __nv_bfloat16* w2_planes, const GemmEpilogue& ep, cudaStream_t stream,
+                     int64_t x_plane_stride) {
   T4R_REQUIRE(ffn_fused_supported(d, hidden), "ffn_fused: unsupported d=%d hidden=%d", d, hidden);
   T4R_REQUIRE(ep.ln_gamma && ep.ln_beta && b1, "ffn_fused: needs b1 and a LayerNorm epilogue");
   T4R_REQUIRE(M > 0 && M < (1ll << 31), "ffn_fused: bad M");
+  if (x_plane_stride <= 0) x_plane_stride = M * d;   // elements between the hi and the lo plane of X
   CUtensorMap tm[6];
   T4R_TRY(make_tmap(&tm[0], x_planes, M, d, BM, 128));
-  T4R_TRY(make_tmap(&tm[1], x_planes + M * d, M, d, BM, 128));
+  T4R_TRY(make_tmap(&tm[1], x_planes + x_plane_stride, M, d, BM, 128));
   T4R_TRY(make_tmap(&tm[2], w1_planes, hidden, d, FFN_HC, 128));
   T4R_TRY(make_tmap(&tm[3], w1_planes + static_cast<int64_t>(hidden) * d, hidden, d, FFN_HC, 128));
   T4R_TRY(make_tmap(&tm[4], w2_planes, d, hidden, d, 128));
