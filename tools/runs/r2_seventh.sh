@@ -13,7 +13,7 @@ echo "== bench config 5, T4R_ENC_PARTS=$P"; T4R_ENC_PARTS=$P timeout 600 $B --wo
 done
 echo "== bench config 2 from a CUDA graph, parts 1 / 2"; for P in 1 2; do T4R_ENC_PARTS=$P timeout 600 $B --graph 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d.get('cuda_graph'))"; done
 echo "== launch list of a training step"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 4000 --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --train --optimizer adamw --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_train_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --train --optimizer adamw --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_train_bench.log 2>&1
 python tools/summarize_ncu.py launches gpurun_out/r2_train_launches.csv gpurun_out/r2_train_launches.txt | head -45
 } > gpurun_out/r2_seventh.log 2>&1
 tail -80 gpurun_out/r2_seventh.log
