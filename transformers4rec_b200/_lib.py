@@ -12,7 +12,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt4r_b200.so")
+# T4R_LIB_PATH: developer switch for A/B runs of an alternative build of the same sources (never set in production)
+LIB_PATH = os.environ.get("T4R_LIB_PATH") or os.path.join(_HERE, "libt4r_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 T4R_MAX_FEATURES = 32

@@ -125,14 +125,16 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
       }
       if (REL) {
         // query rows L and L+1 carry r_w_bias / r_r_bias (split on the fly)
-        for (int c = lane; c < DH; c += 32) {
-          __nv_bfloat16 hi, lo;
-          split_bf16(__ldg(rw + h * DH + c), hi, lo);
-          Qs[(0 * QR + L) * LDS + c] = hi;
-          Qs[(1 * QR + L) * LDS + c] = lo;
-          split_bf16(__ldg(rr + h * DH + c), hi, lo);
-          Qs[(0 * QR + L + 1) * LDS + c] = hi;
-          Qs[(1 * QR + L + 1) * LDS + c] = lo;
+        for (int c = 2 * lane; c < DH; c += 64) {   // pairs: cvt.rn.bf16x2 (the scalar conversion runs on the XU pipe)
+          uint32_t hi, lo;
+          const float2 w2 = __ldg(reinterpret_cast<const float2*>(rw + h * DH + c));
+          split_bf16x2(w2.x, w2.y, hi, lo);
+          *reinterpret_cast<uint32_t*>(Qs + (0 * QR + L) * LDS + c) = hi;
+          *reinterpret_cast<uint32_t*>(Qs + (1 * QR + L) * LDS + c) = lo;
+          const float2 r2 = __ldg(reinterpret_cast<const float2*>(rr + h * DH + c));
+          split_bf16x2(r2.x, r2.y, hi, lo);
+          *reinterpret_cast<uint32_t*>(Qs + (0 * QR + L + 1) * LDS + c) = hi;
+          *reinterpret_cast<uint32_t*>(Qs + (1 * QR + L + 1) * LDS + c) = lo;
         }
       }
       cp_async_wait_all();
@@ -258,7 +260,8 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_stride,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float v = s1[mt][nt][e];
-          const float p = (v == -INFINITY) ? 0.f : expf(v - rmax[mt][e >> 1]);
+          // 2^((v - max) log2 e) on the SFU (ex2.approx, 2 ulp): expf's range reduction was 20 % of this kernel's samples
+          const float p = (v == -INFINITY) ? 0.f : fast_exp2((v - rmax[mt][e >> 1]) * 1.4426950408889634f);
           s1[mt][nt][e] = p;
           rsum[mt][e >> 1] += p;
         }
@@ -561,7 +564,7 @@ attn_mma64_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_plane_strid
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float v = s1[ml][nt][e];
-          const float p = (v == -INFINITY) ? 0.f : expf(v - rmax[ml][e >> 1]);
+          const float p = (v == -INFINITY) ? 0.f : fast_exp2((v - rmax[ml][e >> 1]) * 1.4426950408889634f);
           s1[ml][nt][e] = p;
           rsum[ml][e >> 1] += p;
         }

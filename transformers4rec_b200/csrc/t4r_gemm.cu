@@ -1733,7 +1733,10 @@ struct FfnDev {
 
 constexpr int FFN_HC = 128;                 // hidden units per chunk
 constexpr int FFN_STAGE_BYTES = 64 * 1024;  // one ring stage (see below)
-constexpr int FFN_STAGES = 3;
+#ifndef T4R_FFN_STAGES
+#define T4R_FFN_STAGES 3
+#endif
+constexpr int FFN_STAGES = T4R_FFN_STAGES;
 constexpr int FFN_SMEM_BYTES = FFN_STAGES * FFN_STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
 
 template <int D>
