@@ -106,8 +106,10 @@ def kernel_variant(request, monkeypatch):
 
 
 @pytest.mark.parametrize("kernel_variant", [{"T4R_GEMM_2CTA": "0"}, {"T4R_GEMM_2CTA": "1"}, {"T4R_FFN_2CTA": "1"},
-                                            {"T4R_GEMM_2CTA": "0", "T4R_FFN_FUSED": "0"}], indirect=True,
-                         ids=["gemm-1cta", "gemm-cta-pair", "ffn-cta-pair", "unfused-ffn-1cta"])
+                                            {"T4R_GEMM_2CTA": "0", "T4R_FFN_FUSED": "0"}, {"T4R_FFN_EPW": "8"},
+                                            {"T4R_FFN_EPW": "16"}], indirect=True,
+                         ids=["gemm-1cta", "gemm-cta-pair", "ffn-cta-pair", "unfused-ffn-1cta", "ffn-8-epilogue-warps",
+                              "ffn-16-epilogue-warps"])
 def test_kernel_variants_hold_parity(ops, kernel_variant):
     """Every GEMM flavour that can be selected (single-CTA, CTA pair = tcgen05 cta_group::2; fused feed-forward as a
     CTA pair) against the same references as the defaults: plain GEMM with an odd shape, LayerNorm epilogue, fused

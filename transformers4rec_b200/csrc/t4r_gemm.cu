@@ -116,6 +116,9 @@ int make_tmap_public(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
 // kernel
 // ----------------------------------------------------------------------------
 constexpr int BM = 128;
+#ifndef T4R_FFN_EPW_DEFAULT
+#define T4R_FFN_EPW_DEFAULT 8
+#endif
 #ifndef T4R_FFN_2CTA_DEFAULT
 #define T4R_FFN_2CTA_DEFAULT 0
 #endif
@@ -414,10 +417,16 @@ __device__ __forceinline__ void residual_add(const GemmEpilogue& ep, float* stg_
   }
 }
 
-template <int BN>
+// NG = column groups a tile's row is split into (one epilogue warp per TMEM lane quadrant and group: 4 NG epilogue warps
+// per CTA).  NG = 2 is the original eight-warp form (bit-identical); NG = 4 halves every warp's share of the latency-
+// bound work (staging transposes, residual loads, stores) with twice the warps in flight.  With NG > 2 the residual
+// prefetch of the next chunk is dropped (registers: 576 threads leave 112 per thread) -- thread-level parallelism hides
+// that latency instead.  xch_grp0 = this row's slot in group 0 of the exchange area [NG][128]; grp = own group.
+template <int BN, int NG>
 __device__ __forceinline__ void epilogue_ln_chunked(const GemmDev& p, uint32_t taddr, int64_t row0, int rows_valid, int lane,
-                                                    int64_t n0, float* stg, float2* xch_mine, const float2* xch_other) {
-  constexpr int COLS = BN / 2, NCH = COLS / 32;
+                                                    int64_t n0, float* stg, float2* xch_grp0, int grp) {
+  constexpr int COLS = BN / NG, NCH = COLS / 32;
+  constexpr bool PREFETCH = (NG == 2);
   const GemmEpilogue& ep = p.ep;
   if (ep.debug & 1) rows_valid = 0;
   const bool row_ok = lane < rows_valid;
@@ -428,15 +437,19 @@ __device__ __forceinline__ void epilogue_ln_chunked(const GemmDev& p, uint32_t t
   const bool lprof = (ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
   const long long l0 = lprof ? clock64() : 0;
   // ---- pass 1: bias (+act, mask) + residual, statistics, park the pre-LN values in TMEM
-  uint4 nxt[8];
-  if (has_res) residual_issue(ep, row0, n0, rows_valid, lane, nxt);
+  uint4 nxt[PREFETCH ? 8 : 1];
+  if (PREFETCH && has_res) residual_issue(ep, row0, n0, rows_valid, lane, *reinterpret_cast<uint4(*)[8]>(nxt));
   float mean_h = 0.f, m2_h = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     uint4 cur[8];
+    if constexpr (PREFETCH) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-    if (has_res && c + 1 < NCH) residual_issue(ep, row0, n0 + (c + 1) * 32, rows_valid, lane, nxt);
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      if (has_res && c + 1 < NCH) residual_issue(ep, row0, n0 + (c + 1) * 32, rows_valid, lane, *reinterpret_cast<uint4(*)[8]>(nxt));
+    } else {
+      if (has_res) residual_issue(ep, row0, n0 + c * 32, rows_valid, lane, cur);
+    }
     float v[32];
     tmem_ld<32>(taddr + c * 32, v);
     dense_chunk(v, ep, n0 + c * 32, code);
@@ -459,13 +472,25 @@ __device__ __forceinline__ void epilogue_ln_chunked(const GemmDev& p, uint32_t t
   }
   tmem_st_wait();
   const long long l1 = lprof ? clock64() : 0;
-  // ---- combine the two halves of the row (equal counts)
-  *xch_mine = make_float2(mean_h, m2_h);
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const float2 o = *xch_other;
-  const float delta = o.x - mean_h;
-  const float mean = 0.5f * (mean_h + o.x);
-  const float m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
+  // ---- combine the NG groups of the row (equal counts)
+  xch_grp0[grp * 128] = make_float2(mean_h, m2_h);
+  asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
+  float mean, m2;
+  if constexpr (NG == 2) {
+    const float2 o = xch_grp0[(grp ^ 1) * 128];
+    const float delta = o.x - mean_h;
+    mean = 0.5f * (mean_h + o.x);
+    m2 = m2_h + o.y + delta * delta * (0.5f * COLS);
+  } else {
+    float2 part[NG];
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { part[g] = xch_grp0[g * 128]; sum += part[g].x; }
+    mean = sum * (1.f / NG);
+    m2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { const float dl = part[g].x - mean; m2 += part[g].y + dl * dl * static_cast<float>(COLS); }
+  }
   const float rstd = rsqrtf(m2 * (1.f / BN) + ep.ln_eps);
   const long long l2 = lprof ? clock64() : 0;
   // ---- pass 2: normalise and store
@@ -497,10 +522,10 @@ __device__ __forceinline__ void epilogue_ln_chunked(const GemmDev& p, uint32_t t
 // Each epilogue thread owns one output row (its TMEM lane) and COLS = BN/2 columns
 // (warps 2-5 take the first half of the tile's columns, warps 6-9 the second half).
 // row0 = first row of the warp's 32-row block; n0 = first column of the warp's half.
-template <int BN, bool LN>
+template <int BN, bool LN, int NG = 2>
 __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr, int64_t row0, int rows_valid, int lane,
-                                               int64_t n0, float* stg, float2* xch_mine, const float2* xch_other) {
-  constexpr int COLS = BN / 2;
+                                               int64_t n0, float* stg, float2* xch_grp0, int grp) {
+  constexpr int COLS = BN / NG;
   const GemmEpilogue& ep = p.ep;
   if (ep.debug & 1) rows_valid = 0;  // timing experiment: no global traffic from the epilogue
   const bool row_ok = lane < rows_valid;
@@ -508,7 +533,7 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
   int code = 0;
   if (row_ok && ep.row_code) code = ep.row_code[row];
   if constexpr (LN) {
-    epilogue_ln_chunked<BN>(p, taddr, row0, rows_valid, lane, n0, stg, xch_mine, xch_other);
+    epilogue_ln_chunked<BN, NG>(p, taddr, row0, rows_valid, lane, n0, stg, xch_grp0, grp);
   } else {
     const bool prof = (ep.debug & 2) && blockIdx.x == 0 && threadIdx.x == 64;
 #pragma unroll 1
@@ -849,11 +874,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       if (HEAD) {
         epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
       } else {
-        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
-        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        float2* xg0 = xch + (tile_parity * 2) * 128 + quad * 32 + lane;   // [parity][group][row]
         const int64_t left = static_cast<int64_t>(M_eff) - row0;
         const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
-        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xm, xo);
+        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xg0, half);
       }
       if (prof) { g_dbg_cycles[0] += tw1 - tw0; g_dbg_cycles[1] += clock64() - tw1; g_dbg_cycles[6] += 1; }
       tile_parity ^= 1;
@@ -1053,11 +1077,10 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       if (HEAD) {
         epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
       } else {
-        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
-        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        float2* xg0 = xch + (tile_parity * 2) * 128 + quad * 32 + lane;   // [parity][group][row]
         const int64_t left = static_cast<int64_t>(M_eff) - row0;
         const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
-        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xm, xo);
+        epilogue_dense<BN, LN>(p, taddr, row0, rows_valid, lane, n0, stg_all + (warp - 2) * STG_WORDS, xg0, half);
       }
       tile_parity ^= 1;
       tc_fence_before_sync();
@@ -1737,13 +1760,26 @@ constexpr int FFN_STAGE_BYTES = 64 * 1024;  // one ring stage (see below)
 #define T4R_FFN_STAGES 3
 #endif
 constexpr int FFN_STAGES = T4R_FFN_STAGES;
-constexpr int FFN_SMEM_BYTES = FFN_STAGES * FFN_STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
+constexpr int FFN_SMEM_BYTES = FFN_STAGES * FFN_STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;   // CTA-pair variant
 
-template <int D>
-__global__ void __launch_bounds__(320, 1)
+// NG = column groups of the epilogue (4 NG epilogue warps): 2 = the original eight warps, 4 = sixteen (each warp then
+// GELUs 32 instead of 64 hidden units of a chunk and owns D / 4 instead of D / 2 columns of the final LayerNorm
+// epilogue).  Sixteen warps need 40 KB of staging tiles: the operand ring drops to two 64 KB stages (FfnCfg).
+template <int NG>
+struct FfnCfg {
+  static constexpr int STAGES = (NG == 2) ? FFN_STAGES : 2;
+  static constexpr int THREADS = (2 + 4 * NG) * 32;
+  static constexpr int XCH_BYTES = 2 * NG * 128 * 8;
+  static constexpr int SMEM_BYTES = STAGES * FFN_STAGE_BYTES + 1024 + 256 + XCH_BYTES + 4 * NG * 32 * 20 * 4;
+};
+
+template <int D, int NG>
+__global__ void __launch_bounds__(FfnCfg<NG>::THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                  const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
                  const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnDev p) {
+  constexpr int STAGES = FfnCfg<NG>::STAGES;
+  constexpr int HCW = FFN_HC / NG;                  // hidden units of a chunk per epilogue warp
   constexpr int KB1 = D / 64;                       // k blocks of GEMM1 (K = d)
   constexpr int KB2 = FFN_HC / 64;                  // k blocks of GEMM2 per chunk (K = 128)
   constexpr int XP = BM * 128;                      // X plane bytes per k block
@@ -1752,17 +1788,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   constexpr uint32_t Y_COL = 0, S_COL = 256, GH_COL = 384, GL_COL = 448;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FFN_STAGES * FFN_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + FFN_STAGES;
-  uint64_t* s_full = empty_bar + FFN_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * FFN_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* s_full = empty_bar + STAGES;
   uint64_t* s_empty = s_full + 1;
   uint64_t* g_full = s_empty + 1;
   uint64_t* g_empty = g_full + 1;
   uint64_t* y_full = g_empty + 1;
   uint64_t* y_empty = y_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
-  float2* xch = reinterpret_cast<float2*>(smem + FFN_STAGES * FFN_STAGE_BYTES + 256);
-  float* stg_all = reinterpret_cast<float*>(smem + FFN_STAGES * FFN_STAGE_BYTES + 256 + 4096);
+  float2* xch = reinterpret_cast<float2*>(smem + STAGES * FFN_STAGE_BYTES + 256);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * FFN_STAGE_BYTES + 256 + FfnCfg<NG>::XCH_BYTES);
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -1775,10 +1811,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < FFN_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 8);
-    mbar_init(g_full, 8); mbar_init(g_empty, 1);
-    mbar_init(y_full, 1); mbar_init(y_empty, 8);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4 * NG);
+    mbar_init(g_full, 4 * NG); mbar_init(g_empty, 1);
+    mbar_init(y_full, 1); mbar_init(y_empty, 4 * NG);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -1803,7 +1839,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         tma_load_2d(st + XP, &tmXl, &full_bar[stage], kb * 64, m0);
         tma_load_2d(st + 2 * XP, &tmW1h, &full_bar[stage], kb * 64, c * FFN_HC);
         tma_load_2d(st + 2 * XP + W1P, &tmW1l, &full_bar[stage], kb * 64, c * FFN_HC);
-        if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
       auto load_g2 = [&](int c, int kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -1811,7 +1847,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         mbar_arrive_expect_tx(&full_bar[stage], 2 * W2P);
         tma_load_2d(st, &tmW2h, &full_bar[stage], c * FFN_HC + kb * 64, 0);
         tma_load_2d(st + W2P, &tmW2l, &full_bar[stage], c * FFN_HC + kb * 64, 0);
-        if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < tiles_m; tile += gridDim.x) {
         const int m0 = tile * BM;
@@ -1852,7 +1888,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             umma_bf16(tmem_base + S_COL, umma_desc_sw128(a_hi + k4 * 32), umma_desc_sw128(b_hi + k4 * 32), idesc1, 1u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(s_full);
         if (mprof) { g_dbg_ffn[8] += q1 - q0; g_dbg_ffn[9] += clock64() - q1; }
@@ -1885,7 +1921,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
               umma_bf16_ts(tmem_base + Y_COL, tmem_base + GH_COL + acol, umma_desc_sw128(b_hi + k4 * 32), idesc2, 1u);
             }
             umma_commit(&empty_bar[stage]);
-            if (++stage == FFN_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(g_empty);
           if (c == NC - 1) umma_commit(y_full);
@@ -1895,9 +1931,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps (2..9) =====================
+    // ===================== epilogue warps (2 .. 1 + 4 NG) =====================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;   // column group 0 .. NG-1
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t ph_s_full = 0, ph_g_empty = 0, ph_y_full = 0, tile_parity = 0;
     GemmDev gp;  // view of the final epilogue for epilogue_dense
@@ -1912,16 +1948,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         const long long e1 = eprof ? clock64() : 0;
         ph_s_full ^= 1;
         tc_fence_after_sync();
-        float v[64];
-        tmem_ld<64>(tmem_base + lane_base + S_COL + half * 64, v);
+        float v[HCW];
+        tmem_ld<HCW>(tmem_base + lane_base + S_COL + half * HCW, v);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by GEMM1(c+1)
         const long long e2 = eprof ? clock64() : 0;
-        const float* b1 = p.b1 + c * FFN_HC + half * 64;
-        uint32_t gh[32], gl[32];
+        const float* b1 = p.b1 + c * FFN_HC + half * HCW;
+        uint32_t gh[HCW / 2], gl[HCW / 2];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {  // bias + GELU + hi/lo split on packed fp32 pairs (fma.rn.f32x2)
+        for (int j = 0; j < HCW / 4; ++j) {  // bias + GELU + hi/lo split on packed fp32 pairs (fma.rn.f32x2)
           const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + j);
           const float2 g0 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 0], v[4 * j + 1]), make_float2(b.x, b.y)));
           const float2 g1 = gelu_erf2(__fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w)));
@@ -1934,14 +1970,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         ph_g_empty ^= 1;
         tc_fence_after_sync();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < HCW / 16; ++q) {
           uint32_t r[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = gh[q * 8 + j];
-          tmem_st8(tmem_base + lane_base + GH_COL + half * 32 + q * 8, r);
+          tmem_st8(tmem_base + lane_base + GH_COL + half * (HCW / 2) + q * 8, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] = gl[q * 8 + j];
-          tmem_st8(tmem_base + lane_base + GL_COL + half * 32 + q * 8, r);
+          tmem_st8(tmem_base + lane_base + GL_COL + half * (HCW / 2) + q * 8, r);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -1961,10 +1997,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       {
         const int64_t left = static_cast<int64_t>(p.M) - row0;
         const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
-        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
-        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
-        epilogue_dense<D, true>(gp, tmem_base + lane_base + Y_COL + half * (D / 2), row0, rows_valid, lane,
-                                static_cast<int64_t>(half) * (D / 2), stg_all + (warp - 2) * STG_WORDS, xm, xo);
+        float2* xg0 = xch + (tile_parity * NG) * 128 + quad * 32 + lane;   // [parity][group][row]
+        epilogue_dense<D, true, NG>(gp, tmem_base + lane_base + Y_COL + half * (D / NG), row0, rows_valid, lane,
+                                    static_cast<int64_t>(half) * (D / NG), stg_all + (warp - 2) * STG_WORDS, xg0, half);
         tile_parity ^= 1;
       }
       tc_fence_before_sync();
@@ -1980,17 +2015,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D>
+template <int D, int NG>
 static int launch_ffn_inst(const CUtensorMap (&tm)[6], const FfnDev& dp, cudaStream_t stream) {
-  auto kern = ffn_fused_kernel<D>;
+  auto kern = ffn_fused_kernel<D, NG>;
   static bool attr_set = false;
   if (!attr_set) {
-    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM_BYTES));
+    T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<NG>::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = (dp.M + BM - 1) / BM;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 320, FFN_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dp);
+  kern<<<grid, FfnCfg<NG>::THREADS, FfnCfg<NG>::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], dp);
   T4R_LAUNCH_CHECK("ffn_fused_kernel");
   return 0;
 }
@@ -2222,10 +2257,9 @@ ffn_fused2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
       {
         const int64_t left = static_cast<int64_t>(p.M) - row0;
         const int rows_valid = left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
-        float2* xm = xch + (tile_parity * 2 + half) * 128 + quad * 32 + lane;
-        const float2* xo = xch + (tile_parity * 2 + (half ^ 1)) * 128 + quad * 32 + lane;
+        float2* xg0 = xch + (tile_parity * 2) * 128 + quad * 32 + lane;   // [parity][group][row]
         epilogue_dense<D, true>(gp, tmem_base + lane_base + Y_COL + half * (D / 2), row0, rows_valid, lane,
-                                static_cast<int64_t>(half) * (D / 2), stg_all + (warp - 2) * STG_WORDS, xm, xo);
+                                static_cast<int64_t>(half) * (D / 2), stg_all + (warp - 2) * STG_WORDS, xg0, half);
         tile_parity ^= 1;
       }
       tc_fence_before_sync();
@@ -2309,9 +2343,15 @@ int launch_ffn_fused(const __nv_bfloat16* x_planes, int64_t M, int d, int hidden
     if (d == 128) return launch_ffn2_inst<128>(t2, dp, stream);
     return launch_ffn2_inst<64>(t2, dp, stream);
   }
-  if (d == 256) return launch_ffn_inst<256>(tm, dp, stream);
-  if (d == 128) return launch_ffn_inst<128>(tm, dp, stream);
-  return launch_ffn_inst<64>(tm, dp, stream);
+  // T4R_FFN_EPW: epilogue warps of the fused kernel, 8 or 16 (16: each warp's share of the GELU chunk and of the
+  // final LayerNorm epilogue halves; d >= 128 only: a LayerNorm chunk is 32 columns wide)
+  int epw = T4R_FFN_EPW_DEFAULT;
+  if (const char* e = getenv("T4R_FFN_EPW")) epw = atoi(e);
+  if (epw == 16 && d == 256) return launch_ffn_inst<256, 4>(tm, dp, stream);
+  if (epw == 16 && d == 128) return launch_ffn_inst<128, 4>(tm, dp, stream);
+  if (d == 256) return launch_ffn_inst<256, 2>(tm, dp, stream);
+  if (d == 128) return launch_ffn_inst<128, 2>(tm, dp, stream);
+  return launch_ffn_inst<64, 2>(tm, dp, stream);
 }
 
 }  // namespace t4r

@@ -387,6 +387,199 @@ T4R_HD void attn_fwd_item(const float* qkv, const float* R, const float* rw, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------- attention backward, device
+// The same arithmetic as attn_bwd_item (which stays the host twin and the reference the device is tested against), but
+// one WARP per (session, head) instead of one thread: the per-thread form was 49 % of a training step (24 ms per call
+// at config-2 shapes: 16 384 threads each walking L^2 dh serially).  Here q / k / v / dout of the head and its R slice
+// sit in shared memory; lanes run over the keys j for the scores, the softmax and dp (warp reductions for max / sum /
+// dot), then over the head dimension c for the accumulations, where lane c owns column c of dq_i, dk, dv, dR and of
+// drw / drr -- no atomics, same ownership as the item form.  dh <= 64, L <= 64.
+template <int DH>
+__global__ void __launch_bounds__(32)
+attn_bwd_warp_kernel(const float* __restrict__ qkv, const float* __restrict__ R, const float* __restrict__ rw,
+                     const float* __restrict__ rr, const float* __restrict__ dout, int B, int L, int d, int H,
+                     float* __restrict__ dqkv, float* __restrict__ dR_part, float* __restrict__ drw_part,
+                     float* __restrict__ drr_part, const uint8_t* __restrict__ plm_mask, float p_drop, uint64_t seed,
+                     uint32_t site) {
+  constexpr int LD = DH + 1;                     // padded rows: lanes over j read column c without bank conflicts
+  constexpr int CPL = (DH + 31) / 32;            // columns per lane in the accumulation phase
+  extern __shared__ float sm[];
+  const int item = blockIdx.x;
+  const int h = item % H;
+  const int64_t b = item / H;
+  const int lane = threadIdx.x;
+  const bool rel = R != nullptr;
+  const int n_streams = plm_mask ? 2 : 1;
+  const int64_t M = static_cast<int64_t>(B) * L;
+  const float scale = 1.0f / sqrtf(static_cast<float>(DH));
+  float* ks = sm;                      // [L][LD]   keys of the content stream
+  float* vs = ks + L * LD;             // [L][LD]
+  float* qs = vs + L * LD;             // [L][LD]   queries of the current stream
+  float* dos = qs + L * LD;            // [L][LD]   dout of the current stream
+  float* Rs = dos + L * LD;            // [2L][LD]  (relative form)
+  float* dks = Rs + (rel ? 2 * L * LD : 0);   // [L][DH] accumulators
+  float* dvs = dks + L * DH;
+  float* dRs = dvs + L * DH;           // [2L][DH]  (relative form)
+  float* ps = dRs + (rel ? 2 * L * DH : 0);   // [L] probabilities of the current query row
+  float* dss = ps + L;                 // [L] ds_j
+  float* mks = dss + L;                // [L] dropout keep scales
+  for (int idx = lane; idx < L * DH; idx += 32) {
+    const int r = idx / DH, c = idx % DH;
+    const float* row = qkv + (b * L + r) * 3 * d + h * DH + c;
+    ks[r * LD + c] = row[d];
+    vs[r * LD + c] = row[2 * d];
+    dks[idx] = 0.f;
+    dvs[idx] = 0.f;
+  }
+  if (rel)
+    for (int idx = lane; idx < 2 * L * DH; idx += 32) {
+      const int r = idx / DH, c = idx % DH;
+      Rs[r * LD + c] = R[static_cast<int64_t>(r) * d + h * DH + c];
+      dRs[idx] = 0.f;
+    }
+  float rwv[CPL], rrv[CPL], drw_acc[CPL], drr_acc[CPL];
+#pragma unroll
+  for (int u = 0; u < CPL; ++u) {
+    const int c = lane + 32 * u;
+    rwv[u] = (rel && c < DH) ? rw[h * DH + c] : 0.f;
+    rrv[u] = (rel && c < DH) ? rr[h * DH + c] : 0.f;
+    drw_acc[u] = 0.f; drr_acc[u] = 0.f;
+  }
+  for (int st = 0; st < n_streams; ++st) {
+    __syncwarp();
+    for (int idx = lane; idx < L * DH; idx += 32) {
+      const int r = idx / DH, c = idx % DH;
+      qs[r * LD + c] = qkv[(st * M + b * L + r) * 3 * d + h * DH + c];
+      dos[r * LD + c] = dout[(st * M + b * L + r) * d + h * DH + c];
+    }
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {
+      // ---- scores, softmax, dp: lanes over the keys
+      float sj[2], dpj[2], mkj[2];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        float s = -INFINITY, dp = 0.f, mk = 1.f;
+        if (j < L) {
+          const bool masked = plm_mask && plm_mask[(b * L + i) * L + j] && !(st == 0 && i == j);
+          if (masked) s = -1e30f;
+          else if (rel || j <= i) {
+            float acc = 0.f;
+            if (rel) {
+              const float* Rm = Rs + (j + L - i) * LD;
+              for (int c = 0; c < DH; ++c) {
+                const float q = qs[i * LD + c];
+                acc += (q + rw[h * DH + c]) * ks[j * LD + c] + (q + rr[h * DH + c]) * Rm[c];
+              }
+            } else {
+              for (int c = 0; c < DH; ++c) acc += qs[i * LD + c] * ks[j * LD + c];
+            }
+            s = acc * scale;
+          }
+          mk = keep_scale(seed, site, attn_prob_index(st, B, b, H, h, L, i, j), p_drop);
+          for (int c = 0; c < DH; ++c) dp += dos[i * LD + c] * vs[j * LD + c];
+          dp *= mk;
+        }
+        sj[u] = s; dpj[u] = dp; mkj[u] = mk;
+        mx = fmaxf(mx, s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { sj[u] = (sj[u] == -INFINITY) ? 0.f : expf(sj[u] - mx); sum += sj[u]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      float dot = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { sj[u] *= inv; dot += sj[u] * dpj[u]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        if (j < L) {
+          const bool live = rel || j <= i;
+          ps[j] = live ? sj[u] * mkj[u] : 0.f;                            // the (dropped) weight of v_j
+          dss[j] = live ? sj[u] * (dpj[u] - dot) * scale : 0.f;
+        }
+      }
+      __syncwarp();
+      // ---- accumulations: lane c owns column c
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) {
+        const int c = lane + 32 * u;
+        if (c < DH) {
+          const float q = qs[i * LD + c], dor = dos[i * LD + c];
+          float dq = 0.f;
+          const int jend = rel ? L : i + 1;
+          for (int j = 0; j < jend; ++j) {
+            const float ds = dss[j], p = ps[j];
+            const float k = ks[j * LD + c];
+            if (rel) {
+              const int m = j + L - i;
+              const float Rm = Rs[m * LD + c];
+              dq += ds * (k + Rm);
+              dks[j * DH + c] += ds * (q + rwv[u]);
+              dRs[m * DH + c] += ds * (q + rrv[u]);
+              drw_acc[u] += ds * k;
+              drr_acc[u] += ds * Rm;
+            } else {
+              dq += ds * k;
+              dks[j * DH + c] += ds * q;
+            }
+            dvs[j * DH + c] += p * dor;
+          }
+          dqkv[(st * M + b * L + i) * 3 * d + h * DH + c] = dq;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- what the item owns: dk / dv of the content stream's rows (the query stream's stay zero), dR / drw / drr partials
+  for (int idx = lane; idx < L * DH; idx += 32) {
+    const int r = idx / DH, c = idx % DH;
+    float* row = dqkv + (b * L + r) * 3 * d + h * DH + c;
+    row[d] = dks[idx];
+    row[2 * d] = dvs[idx];
+    if (n_streams == 2) {
+      float* row2 = dqkv + (M + b * L + r) * 3 * d + h * DH + c;
+      row2[d] = 0.f;
+      row2[2 * d] = 0.f;
+    }
+  }
+  if (rel) {
+    for (int idx = lane; idx < 2 * L * DH; idx += 32) {
+      const int r = idx / DH, c = idx % DH;
+      dR_part[(b * 2 * L + r) * d + h * DH + c] = dRs[idx];
+    }
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      const int c = lane + 32 * u;
+      if (c < DH) { drw_part[b * d + h * DH + c] = drw_acc[u]; drr_part[b * d + h * DH + c] = drr_acc[u]; }
+    }
+  }
+}
+static size_t attn_bwd_warp_smem(int L, int DH, bool rel) {
+  const size_t LD = DH + 1;
+  return sizeof(float) * (4 * L * LD + (rel ? 2 * L * LD : 0) + 2 * static_cast<size_t>(L) * DH +
+                          (rel ? 2 * static_cast<size_t>(L) * DH : 0) + 3 * L);
+}
+template <int DH>
+static int launch_attn_bwd_warp(const float* qkv, const float* R, const float* rw, const float* rr, const float* dout, int B,
+                                int L, int d, int H, float* dqkv, float* dR_part, float* drw_part, float* drr_part,
+                                const uint8_t* plm_mask, float p_drop, uint64_t seed, uint32_t site, cudaStream_t s) {
+  const size_t smem = attn_bwd_warp_smem(L, DH, R != nullptr);
+  auto kern = attn_bwd_warp_kernel<DH>;
+  T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<static_cast<unsigned>(B) * H, 32, smem, s>>>(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part,
+                                                     plm_mask, p_drop, seed, site);
+  T4R_LAUNCH_CHECK("attn_bwd_warp_kernel");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- launch plumbing
 template <typename F>
 __global__ void __launch_bounds__(256) items_kernel(int64_t n, F f) {
@@ -571,9 +764,19 @@ static int attn_bwd_impl(const float* qkv, const float* R, const float* rw, cons
   float* dR_part = part;
   float* drw_part = rel ? part + static_cast<int64_t>(B) * 2 * L * d : nullptr;
   float* drr_part = rel ? drw_part + static_cast<int64_t>(B) * d : nullptr;
-  T4R_TRY(run_items(static_cast<int64_t>(B) * H, [=] __host__ __device__(int64_t i) {
-            attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, i, p_drop, seed, site); },
-          "train_attn_bwd", stream, on_host));
+  const int dh = d / H;
+  const bool warp_form = !on_host && (dh == 16 || dh == 32 || dh == 64) &&
+                         attn_bwd_warp_smem(L, dh, rel) <= 200 * 1024 && getenv("T4R_TRAIN_ATTN_ITEMS") == nullptr;
+  if (warp_form) {   // one warp per (session, head); same arithmetic, tested against the item form (the host twin)
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (dh == 16) T4R_TRY(launch_attn_bwd_warp<16>(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, p_drop, seed, site, cs));
+    else if (dh == 32) T4R_TRY(launch_attn_bwd_warp<32>(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, p_drop, seed, site, cs));
+    else T4R_TRY(launch_attn_bwd_warp<64>(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, p_drop, seed, site, cs));
+  } else {
+    T4R_TRY(run_items(static_cast<int64_t>(B) * H, [=] __host__ __device__(int64_t i) {
+              attn_bwd_item(qkv, R, rw, rr, dout, B, L, d, H, dqkv, dR_part, drw_part, drr_part, plm_mask, i, p_drop, seed, site); },
+            "train_attn_bwd", stream, on_host));
+  }
   if (!rel) return 0;
   T4R_TRY(run_items(static_cast<int64_t>(2) * L * d, [=] __host__ __device__(int64_t i) { sum_sessions_item(dR_part, B, 2 * L, d, dR, i); },
                     "train_attn_bwd_dR", stream, on_host));
