@@ -80,6 +80,15 @@ def head_traffic(resident=True):
         return None
 
 
+def ncu_tensor_pipe():
+    """Per-kernel tensor-pipe utilisation from the committed ncu captures (profiles/r2_tensor_pipe.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_tensor_pipe.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def cardinalities(cfg):
     cards = {"item_id/list": cfg["V"]}
     for name, card in cfg.get("side", {}).items():
@@ -684,7 +693,8 @@ def run_workload(args, cfg, dev, rank, world, local_rank, config_desc, peaks, pe
         line["roofline_encoder"] = {"bound": "tensor", "achieved": enc_tf, "peak": peak_tf, "unit": "TFLOP/s",
                                     "frac": enc_tf / peak_tf, "ms": stages[1], "algorithmic_flops": enc_flops,
                                     "note": "whole encoder (QKV, relative attention, O-proj + LN, fused FFN; 3 tensor "
-                                            "passes per MAC in the GEMMs); tensor-pipe % per kernel: profiles/ ncu summaries"}
+                                            "passes per MAC in the GEMMs)",
+                                    "ncu_tensor_pipe": ncu_tensor_pipe()}
     if gather is not None:
         g_ms, g_bytes = gather
         hbm = float(peaks.get("hbm_gbs", 6482.4))

@@ -13,6 +13,10 @@ import sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        # the tensor-pipe figure /opt/skills/guides/B200_PROFILING.md greps; the TPC.TriageCompute "realtime" variant
+        # below it reads about 0.4-0.8x of it on the same launch (it was the one round 1's summaries quoted)
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -52,9 +56,12 @@ EXTRA = ("pipe_tensor", "xbar2l1tex", "lts__t_bytes", "lts__t_sectors_srcunit_te
 
 def full(src, dst):
     """Summary of the judged metrics + the raw per-kernel CSV next to it (dst with .csv), so the summary can be re-cut."""
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    with open(re.sub(r"\.txt$", "", dst) + ".raw.csv", "w") as f:
-        f.write(raw)
+    if src.endswith(".csv"):      # re-cut a summary from a raw CSV kept under profiles/
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        with open(re.sub(r"\.txt$", "", dst) + ".raw.csv", "w") as f:
+            f.write(raw)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
