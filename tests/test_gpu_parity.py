@@ -124,6 +124,32 @@ def test_kernel_variants_hold_parity(ops, kernel_variant):
     test_head_full_softmax(ops, 517, 30011, 256, 1.0)
 
 
+def test_forward_replayed_from_a_cuda_graph():
+    """Model.graphed: the forward-only pass captured once and replayed -- same loss and label ranks as the eager call on
+    the same draws, new inputs take effect through the captured buffers, a shape change is refused."""
+    cards, dims = {"item_id/list": 3001, "category/list": 37}, {"item_id/list": 64, "category/list": 64}
+    B, L = 48, 20
+    oracle, model = make_pair(cards, dims, "item_id/list", (), 64, 4, 2, L, weight_scale=0.08)
+    u, draws = mlm_draws(B, L)
+    model.heads[0].body[0].masking.set_draws(u.cuda())
+    b1 = {k: v.cuda() for k, v in synth_batch(B, L, cards, seed=1).items()}
+    b2 = {k: v.cuda() for k, v in synth_batch(B, L, cards, seed=2).items()}
+    with torch.no_grad():
+        e1 = model(b1, training=True)["loss"].item()
+        e2 = model(b2, training=True)["loss"].item()
+        ev = model(b2, training=False, testing=True)
+        ev_loss, ev_rank = ev["loss"].item(), ev.row_rank.clone()
+    g = model.graphed(b1, training=True)
+    assert abs(g(b1).item() - e1) < 1e-6 and abs(g(b2).item() - e2) < 1e-6 and abs(g(b1).item() - e1) < 1e-6
+    assert abs(e1 - e2) > 1e-4
+    ref = oracle(synth_batch(B, L, cards, seed=2), training=True, draws=draws)["loss"].item()
+    assert abs(g(b2).item() - ref) < 1e-3
+    ge = model.graphed(b1, training=False, testing=True)
+    assert abs(ge(b2).item() - ev_loss) < 1e-6 and torch.equal(ge.row_rank, ev_rank)
+    with pytest.raises(ValueError):
+        g({k: v[:8] for k, v in b1.items()})
+
+
 def test_unsupported_shapes_fail_loudly():
     """no silent fallback: shapes outside the kernels' envelope raise T4RError with the limit in the message"""
     import transformers4rec_b200.torch as tr

@@ -111,6 +111,52 @@ class Head(nn.Module):
             task.reset_metrics()
 
 
+class GraphedForward:
+    """The forward-only pass of a model (``model(batch, training=..., testing=...)``: loss, label ranks) captured once
+    into a CUDA graph and replayed: no host work per step besides copying the inputs into the captured buffers.  For the
+    small configurations the eager step is launch-bound (BASELINE config 1: 27 launches, 0.44 ms eager vs 0.185 ms
+    replayed); at config-2 size the two are equal.  The forward has no host synchronisation (the label count stays on
+    the device), which is what makes it capturable.
+
+    Fixed at capture time: input shapes / dtypes, the mode flags, and the WEIGHTS' split planes -- call ``recapture()``
+    after the parameters change (an optimizer step, ``load_state_dict``).  The random draws of MLM masking are made
+    inside the graph by torch's graph-safe generator, so every replay masks differently, as eager calls do."""
+
+    def __init__(self, model: "Model", example_batch: Dict[str, torch.Tensor], training: bool = True, testing: bool = False,
+                 warmup: int = 2):
+        if not all(v.is_cuda for v in example_batch.values()):
+            raise ValueError("GraphedForward needs CUDA input tensors")
+        self.model, self.training, self.testing, self.warmup = model, training, testing, int(warmup)
+        self.static = {k: v.clone() for k, v in example_batch.items()}
+        self.graph = None
+        self.recapture()
+
+    def recapture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.no_grad(), torch.cuda.stream(side):      # warm-up off the capture: workspaces, plane caches, lazy inits
+            for _ in range(max(1, self.warmup)):
+                self.model(self.static, training=self.training, testing=self.testing)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            out = self.model(self.static, training=self.training, testing=self.testing)
+            self.loss = out["loss"]
+            self.row_rank, self.count = getattr(out, "row_rank", None), getattr(out, "count", None)
+        return self
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """-> the loss tensor (a captured buffer: read it, or copy it, before the next call)."""
+        for k, buf in self.static.items():
+            v = batch[k]
+            if v.shape != buf.shape or v.dtype != buf.dtype:
+                raise ValueError(f"GraphedForward was captured for {k!r} of shape {tuple(buf.shape)} / {buf.dtype}, "
+                                 f"got {tuple(v.shape)} / {v.dtype}")
+            buf.copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 class Model(nn.Module):
     """model/base.py:448-598."""
 
@@ -122,6 +168,10 @@ class Model(nn.Module):
         self.top_k = kwargs.get("top_k", None)
         self.max_sequence_length = kwargs.get("max_sequence_length", None)
         self.name = kwargs.get("name", None)
+
+    def graphed(self, example_batch: Dict[str, torch.Tensor], training: bool = True, testing: bool = False) -> GraphedForward:
+        """CUDA-graph replay of the forward-only pass for batches shaped like ``example_batch`` (see GraphedForward)."""
+        return GraphedForward(self, example_batch, training=training, testing=testing)
 
     def enable_fused_training(self, on: bool = True, head_chunk: int = 32768):
         """N3: route ``model(batch, training=True)`` through the fused training step whenever autograd is recording, so

@@ -9,7 +9,7 @@ from ..features import (ContinuousFeatures, ContinuousProjection, FeatureConfig,
                         TabularSequenceFeatures)
 from ..masking import (CausalLanguageModeling, MaskedLanguageModeling, MaskSequence,  # noqa: F401
                        PermutationLanguageModeling, masking_registry)
-from ..model import Head, Model  # noqa: F401
+from ..model import GraphedForward, Head, Model  # noqa: F401
 from ..prediction_task import (LogUniformSampler, NextItemPredictionTask, PredictionTask)  # noqa: F401
 from ..ranking_metric import (AvgPrecisionAt, DCGAt, MeanReciprocalRankAt, NDCGAt, PrecisionAt, RecallAt,  # noqa: F401
                               ranking_metrics_registry)
