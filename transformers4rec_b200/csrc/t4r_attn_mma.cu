@@ -360,8 +360,9 @@ static int launch_attn_mma_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, const 
 // pair through shared memory.  What crossed lanes by shuffle in the one-warp kernel crosses warps through shared
 // memory here: the (r_w_bias . k_j) row of S1 goes to WB[64], the (r_r_bias . R) row of S2 is read from the pair's S2
 // scratch like every other row; named barriers (one id per pair, 64 threads) order the stages.  A block holds one or
-// two pairs (shared-memory footprint decides) which share the head's R planes.  Opt-in (T4R_ATTN_MMA64=1) until it
-// has run on hardware; without it 32 < L <= 64 keeps the FFMA kernel (attn_kernel in t4r_kernels.cu).
+// two pairs (shared-memory footprint decides) which share the head's R planes.  Validated on a B200 in round 2
+// (12 / 12 parity cases; XLNet layer at L = 50: 1.60 -> 1.05 ms) and the default since; T4R_ATTN_MMA64=0 keeps
+// 32 < L <= 64 on the FFMA kernel (attn_kernel in t4r_kernels.cu).
 // ============================================================================
 __device__ __forceinline__ void pair_bar(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
 
@@ -656,8 +657,8 @@ static int launch_attn_mma64_inst(const __nv_bfloat16* qkv, int64_t qkv_ps, cons
   return 0;
 }
 
-// one warp per (session, head) up to 32 (augmented) query rows; with T4R_ATTN_MMA64=1 (opt-in: not yet run on
-// hardware) two warps per (session, head) up to 64
+// one warp per (session, head) up to 32 (augmented) query rows; two warps per (session, head) up to 64 (the default
+// since its first B200 run in round 2; T4R_ATTN_MMA64=0 keeps those lengths on the FFMA kernel)
 #ifndef T4R_ATTN_MMA64_DEFAULT
 #define T4R_ATTN_MMA64_DEFAULT 1  // two-warp tensor-path attention for 32 < L <= 64 (validated on B200 in round 2; T4R_ATTN_MMA64=0 selects the FFMA kernel)
 #endif

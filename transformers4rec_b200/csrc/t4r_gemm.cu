@@ -1269,7 +1269,7 @@ __device__ __forceinline__ void head_state_flush(const HeadRowState& st, const G
 }
 
 // ============================================================================
-// Head GEMM with a RESIDENT A tile (CTA pairs, K <= 256; opt-in: T4R_HEAD_RESIDENT=1).
+// Head GEMM with a RESIDENT A tile (CTA pairs, K <= 256; the default head kernel since round 2, T4R_HEAD_RESIDENT=0 = streaming).
 // The tied-logits GEMM multiplies a small A (T label rows) by a huge B (the item table).  In gemm2_bf16x3_kernel
 // every 256 x 256 output tile re-streams both operands from L2: 64 KB per CTA and K block, half of it A -- the same
 // A rows over and over.  Here a CTA pair works on UNITS of (one 256-row block of A) x (HEAD_CHUNK consecutive column
@@ -1604,7 +1604,7 @@ extern "C" int t4r_debug_gemm_cycles(unsigned long long* out8, int reset) {
   return 0;
 }
 namespace t4r {
-// T4R_HEAD_RESIDENT=1 (opt-in) and a shape the resident-A head kernel covers: K <= 256, more than one 128-row
+// T4R_HEAD_RESIDENT != 0 (the default) and a shape the resident-A head kernel covers: K <= 256, more than one 128-row
 // block, CTA pairs and 128-byte rows enabled.  Returns the number of LSE partials per row the head call must size
 // for (2 per column CHUNK), or 0 when the regular kernels run (2 per column TILE).
 int head_resident_partials(int64_t M, int64_t V, int Kp) {
