@@ -1131,21 +1131,36 @@ __device__ __forceinline__ void head_state_tile(HeadRowState& st, const GemmDev&
   // (config 3) or nprod = 2 the main loop is short enough for this epilogue to be on the critical path.
   if (full_tile && !ep.col_bias && !ep.col_ids && !ep.hit_col && !want_rank && !want_z) {
     const float scale2r = scale2 * st.row_scale;  // > 0: power-of-two row scale
+    // The column scales of the 2-unit product (one per table row) are the only global loads of this epilogue, and their
+    // latency sat right in front of the multiply: 54 % of the kernel's stall samples (profiles/r2_head_lines.txt), with
+    // the tensor pipe at 74 % -- the epilogue paces the kernel.  They are now fetched one chunk AHEAD, before the
+    // TMEM load of the chunk they follow.
+    const bool scaled = ep.col_scale != nullptr;
+    float4 cs_cur[8], cs_nxt[8];
+    if (scaled) {
+      const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs_cur[j] = __ldg(c4 + j);
+    }
 #pragma unroll 1
     for (int c = 0; c < COLS / 32; ++c) {
+      if (scaled && c + 1 < COLS / 32) {
+        const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + n0 + (c + 1) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs_nxt[j] = __ldg(c4 + j);
+      }
       float v[32];
       tmem_ld<32>(taddr + c * 32, v);
-      if (!row_ok) continue;
       float2* v2 = reinterpret_cast<float2*>(v);
-      if (ep.col_scale) {
-        const float4* c4 = reinterpret_cast<const float4*>(ep.col_scale + n0 + c * 32);
+      if (scaled) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 cs = __ldg(c4 + j);
-          v2[2 * j] = __fmul2_rn(v2[2 * j], make_float2(cs.x, cs.y));
-          v2[2 * j + 1] = __fmul2_rn(v2[2 * j + 1], make_float2(cs.z, cs.w));
+          v2[2 * j] = __fmul2_rn(v2[2 * j], make_float2(cs_cur[j].x, cs_cur[j].y));
+          v2[2 * j + 1] = __fmul2_rn(v2[2 * j + 1], make_float2(cs_cur[j].z, cs_cur[j].w));
+          cs_cur[j] = cs_nxt[j];
         }
       }
+      if (!row_ok) continue;
       float mx[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
       for (int j = 4; j < 32; j += 4) {
