@@ -528,7 +528,7 @@ class ShardedEmbedding(torch.nn.Module):
         """The shards of all ranks as peer memory, or None when that is not available (CPU / gloo tests, T4R_PEER=0,
         a failed mapping).  The first call on a CUDA weight is a collective."""
         w = self.weight
-        if self._peer is not None and not self._peer.still_valid():
+        if self._peer is not None and w.data_ptr() != self._peer.local_ptr:
             self._peer, self._peer_tried = None, False          # the parameter was re-allocated (.to(), load): map again
         if self._peer is None and not self._peer_tried:
             self._peer_tried = True
