@@ -206,10 +206,15 @@ int t4r_split_planes(const float* x, int64_t rows, int K, int ld, const uint8_t*
  * (HOST pointers, no CUDA call) -- test infrastructure. */
 int t4r_split_planes_mixed(const float* x, int64_t rows, int K, int ld, void* out_planes, float* out_inv_scale,
                            void* stream);
+/* the same with a device-side row count (the head's label rows: capacity B*L, ~13 % of it valid): rows from
+ * round_up(*count_dev, 256) on are not touched */
+int t4r_split_planes_mixed_n(const float* x, int64_t rows, int K, int ld, const int32_t* count_dev, void* out_planes,
+                             float* out_inv_scale, void* stream);
 int t4r_debug_split_planes_mixed_host(const float* x, int64_t rows, int K, int ld, void* out_planes,
                                       float* out_inv_scale);
 /* gather rows then split: out[i] = x[idx[i]] for i < *count_dev (all `cap` rows when
- * count_dev is NULL); rows >= count are zero.  out_f32 optional. */
+ * count_dev is NULL); with a count, rows from it up to the next multiple of 256 are zero and the
+ * rest of the outputs is left untouched.  out_f32 optional. */
 int t4r_gather_rows_split(const float* x, int K, int ld, const int32_t* idx, const int32_t* count_dev, int cap,
                           float* out_f32, void* out_planes, void* stream);
 /* idx variant for int64 indices (embedding rows for sampled softmax) */

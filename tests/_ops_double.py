@@ -54,7 +54,7 @@ def split_planes(x, row_code=None, mask_vec=None, want_f32=False, out=None):
     return (planes, v) if want_f32 else planes
 
 
-def split_planes_mixed(x):
+def split_planes_mixed(x, count=None):
     from transformers4rec_b200 import ops
     return ops.split_planes_mixed_host(x)  # the kernel's own packing code, compiled for the host
 

@@ -225,10 +225,14 @@ def test_mask_clm_bit_exact(ops, mode):
     assert torch.equal(got, ref)
 
 
-def test_compact_targets(ops):
-    torch.manual_seed(8)
-    labels = torch.randint(0, 50, (300, 20))
-    labels[labels < 40] = 0
+@pytest.mark.parametrize("B,L,keep", [(300, 20, 0.2), (2048, 20, 0.13), (1, 1, 1.0), (1, 3, 0.0), (7, 5, 1.0),
+                                      (33, 31, 0.5), (2048, 50, 0.1), (52, 20, 0.9)])
+def test_compact_targets(ops, B, L, keep):
+    """row-major order of the non-padding labels, device-side count, zero tail -- from one label to config 5's 102 400,
+    none / all of them labels, sizes around the kernel's 32-label steps and 1024-label rounds"""
+    torch.manual_seed(8 + B)
+    labels = torch.randint(1, 10**9, (B, L))
+    labels[torch.rand(B, L) >= keep] = 0
     rows, labs, count = ops.compact_targets(labels.cuda(), 0)
     T = int(count.item())
     flat = labels.flatten()

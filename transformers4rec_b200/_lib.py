@@ -155,6 +155,7 @@ SIGNATURES = {
     "t4r_compact_targets": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
     "t4r_split_planes": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "t4r_split_planes_mixed": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
+    "t4r_split_planes_mixed_n": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "t4r_debug_split_planes_mixed_host": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "t4r_gather_rows_split": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     "t4r_gather_rows_split_i64": (c_int, [_P, c_int, c_int, _P, c_int, _P, _P, _P]),

@@ -320,46 +320,65 @@ __global__ void mask_clm_kernel(const int64_t* __restrict__ ids, int B, int L, i
   for (int l = 0; l < L; ++l) cd[l] = mk[l] ? ((l == L - 1) ? 2 : 0) : 1;
 }
 
-// label compaction: single block, contiguous chunks per thread, block-wide scan
+// label compaction: single block; every WARP owns a contiguous segment and walks it 32 labels at a time (coalesced
+// 256-byte reads, four steps in flight), counting with ballots; one scan over the 32 warp totals; a second walk writes
+// the compacted rows in order (position = warp base + popc of the lower lanes' ballots).  The first form gave each
+// THREAD a contiguous chunk -- 32 lanes reading 32 different 320-byte-strided lines per instruction -- and cost 43 us
+// of the 5.5 ms step for 40 960 labels.
 __global__ void __launch_bounds__(1024)
 compact_targets_kernel(const int64_t* __restrict__ labels, int64_t n, int64_t pad, int32_t* __restrict__ rows,
                        int64_t* __restrict__ out_labels, int32_t* __restrict__ count) {
   __shared__ int warp_tot[32];
   __shared__ int total_s;
-  const int tid = threadIdx.x;
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t beg = tid * per;
-  const int64_t end = (beg + per < n) ? beg + per : n;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int64_t steps = (n + 32 * 32 - 1) / (32 * 32);        // 32-label steps per warp
+  const int64_t seg = steps * 32;
+  const int64_t beg = warp * seg;
+  const int64_t end = (beg + seg < n) ? beg + seg : n;
   int cnt = 0;
-  for (int64_t i = beg; i < end; ++i) cnt += (labels[i] != pad);
-  // inclusive scan within warp
-  int incl = cnt;
+  for (int64_t i0 = beg; i0 < end; i0 += 4 * 32) {
+    int64_t v[4];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane_id() >= o) incl += t;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      v[u] = (i < end) ? labels[i] : pad;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt += __popc(__ballot_sync(0xffffffffu, v[u] != pad));
   }
-  if (lane_id() == 31) warp_tot[warp_id()] = incl;
+  if (lane == 0) warp_tot[warp] = cnt;      // every lane holds the warp's total
   __syncthreads();
-  if (warp_id() == 0) {
-    int w = warp_tot[lane_id()];
+  if (warp == 0) {
+    const int w = warp_tot[lane];
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane_id() >= o) wi += t;
+      if (lane >= o) wi += t;
     }
-    warp_tot[lane_id()] = wi - w;  // exclusive
-    if (lane_id() == 31) total_s = wi;
+    warp_tot[lane] = wi - w;  // exclusive
+    if (lane == 31) total_s = wi;
   }
   __syncthreads();
-  int pos = warp_tot[warp_id()] + incl - cnt;
-  for (int64_t i = beg; i < end; ++i) {
-    const int64_t v = labels[i];
-    if (v != pad) {
-      rows[pos] = static_cast<int32_t>(i);
-      out_labels[pos] = v;
-      ++pos;
+  int pos = warp_tot[warp];
+  const unsigned lower = (1u << lane) - 1u;
+  for (int64_t i0 = beg; i0 < end; i0 += 4 * 32) {
+    int64_t v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      v[u] = (i < end) ? labels[i] : pad;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool keep = v[u] != pad;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int at = pos + __popc(m & lower);
+        rows[at] = static_cast<int32_t>(i0 + u * 32 + lane);
+        out_labels[at] = v[u];
+      }
+      pos += __popc(m);
     }
   }
   const int total = total_s;
@@ -447,6 +466,9 @@ gather_rows_split_kernel(const float* __restrict__ x, int K, int64_t ld, int Kp,
   if (row >= cap) return;
   const int lane = lane_id();
   const int count = count_dev ? *count_dev : cap;
+  // with a device-side count the zero rows stop at the next multiple of 256 (the last row tile a GEMM consumer reads):
+  // at the head's capacity of B*L rows with ~13 % of them labels, zero-filling the rest was most of this kernel
+  if (count_dev && row >= (static_cast<int64_t>(count) + 255) / 256 * 256) return;
   const bool valid = row < count;
   const float* src = valid ? x + static_cast<int64_t>(idx[row]) * ld : nullptr;
   __nv_bfloat16* hi = planes ? planes + row * Kp : nullptr;

@@ -12,9 +12,12 @@ namespace t4r {
 // Per 64-wide K block a lane owns elements (2 lane, 2 lane + 1): 128 B of fp16 and 2 x 64 B of e4m3 per warp store.
 __global__ void __launch_bounds__(256)
 split_planes_mixed_kernel(const float* __restrict__ x, int64_t rows, int K, int64_t ld, int Kp,
-                          uint16_t* __restrict__ planes, float* __restrict__ inv_scale) {
+                          uint16_t* __restrict__ planes, float* __restrict__ inv_scale,
+                          const int32_t* __restrict__ count_dev) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_id();
   if (row >= rows) return;
+  // with a device-side row count only the rows a consumer's last 256-row tile can touch are packed
+  if (count_dev && row >= (static_cast<int64_t>(*count_dev) + 255) / 256 * 256) return;
   const int lane = lane_id();
   const float* src = x + row * ld;
   float m = 0.f;
@@ -38,16 +41,20 @@ split_planes_mixed_kernel(const float* __restrict__ x, int64_t rows, int K, int6
 
 }  // namespace t4r
 
-extern "C" int t4r_split_planes_mixed(const float* x, int64_t rows, int K, int ld, void* out_planes, float* out_inv_scale,
-                                      void* stream) {
+extern "C" int t4r_split_planes_mixed_n(const float* x, int64_t rows, int K, int ld, const int32_t* count_dev,
+                                        void* out_planes, float* out_inv_scale, void* stream) {
   using namespace t4r;
   T4R_REQUIRE(x && out_planes && out_inv_scale && rows > 0 && K > 0 && ld >= K, "split_planes_mixed: bad arguments");
   const int Kp = t4r_round_up64(K);
   const int64_t blocks = (rows + 7) / 8;
   split_planes_mixed_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, K, ld, Kp, static_cast<uint16_t*>(out_planes), out_inv_scale);
+      x, rows, K, ld, Kp, static_cast<uint16_t*>(out_planes), out_inv_scale, count_dev);
   T4R_LAUNCH_CHECK("split_planes_mixed_kernel");
   return 0;
+}
+extern "C" int t4r_split_planes_mixed(const float* x, int64_t rows, int K, int ld, void* out_planes, float* out_inv_scale,
+                                      void* stream) {
+  return t4r_split_planes_mixed_n(x, rows, K, ld, nullptr, out_planes, out_inv_scale, stream);
 }
 
 // Host twin of the kernel above (HOST pointers; no CUDA call): the same mixed_row_scale / mixed_pack_pair code

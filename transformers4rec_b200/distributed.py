@@ -475,7 +475,7 @@ def peer_softmax_ce(ph: PeerHead, count: torch.Tensor, local_table: torch.Tensor
     if head_rows is not None:
         head_rows(pulled, w_planes, lo, inv_tau, rank_tgt, ph.stats)
     elif isinstance(w_planes, tuple):   # the 2-unit product: (mixed planes, inverse row scales)
-        xm, xi = ops.split_planes_mixed(xg)
+        xm, xi = ops.split_planes_mixed(xg, count=t_total)
         ops.head_softmax_ce(xm, xg, yg, w_planes[0], local_table, t_dev=t_total, inv_temperature=inv_tau, v_offset=lo,
                             want_loss=False, want_rank=want_rank, rank_tgt=rank_tgt, nprod=2, xt_inv_scale=xi,
                             w_inv_scale=w_planes[1], out_stats=ph.stats)

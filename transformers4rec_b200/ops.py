@@ -81,17 +81,18 @@ def split_planes(x: torch.Tensor, row_code: Optional[torch.Tensor] = None, mask_
     return (planes, of) if want_f32 else planes
 
 
-def split_planes_mixed(x: torch.Tensor):
+def split_planes_mixed(x: torch.Tensor, count: Optional[torch.Tensor] = None):
     """fp32 [rows, K] -> (int16 words [2, rows, Kp], fp32 [rows] inverse row scales): the operands of the 2-unit
-    product (``nprod=2``: fp16 x fp16 + two e4m3 cross terms, csrc/t4r_mixed_pack.cuh)."""
-    _need_cuda(x)
+    product (``nprod=2``: fp16 x fp16 + two e4m3 cross terms, csrc/t4r_mixed_pack.cuh).  ``count`` (device int32):
+    only the first round_up(count, 256) rows are packed (the rest of the outputs is left untouched)."""
+    _need_cuda(x, count)
     x = _f32c(x)
     rows, K = x.shape
     Kp = round_up64(K)
     planes = torch.empty((2, rows, Kp), dtype=torch.int16, device=x.device)
     inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
-    check(_lib.load().t4r_split_planes_mixed(ptr(x), rows, K, K, ptr(planes), ptr(inv), _stream()),
-          "t4r_split_planes_mixed")
+    check(_lib.load().t4r_split_planes_mixed_n(ptr(x), rows, K, K, ptr(count), ptr(planes), ptr(inv), _stream()),
+          "t4r_split_planes_mixed_n")
     return planes, inv
 
 

@@ -313,7 +313,7 @@ class NextItemPredictionTask(PredictionTask):
                                   col_bias=col_bias, labels=tgt_labels, De=Wd.shape[1], sampled=True)
             elif mixed_head:
                 w_mixed, w_inv = self._planes.get_mixed("W", W)
-                xt_mixed, xt_inv = ops.split_planes_mixed(xt_f32)
+                xt_mixed, xt_inv = ops.split_planes_mixed(xt_f32, count=count)
                 res = ops.head_softmax_ce(xt_mixed, xt_f32, tgt_labels, w_mixed, Wd, t_dev=count,
                                           inv_temperature=inv_tau, want_rank=want_rank, nprod=2,
                                           label_smoothing=self.label_smoothing, xt_inv_scale=xt_inv, w_inv_scale=w_inv)
