@@ -124,6 +124,32 @@ def test_kernel_variants_hold_parity(ops, kernel_variant):
     test_head_full_softmax(ops, 517, 30011, 256, 1.0)
 
 
+@pytest.mark.parametrize("M,N,K", [(40960, 768, 256), (1000, 512, 256), (333, 256, 64), (257, 768, 128), (4096, 1024, 256)])
+def test_tma_store_epilogue_is_bit_identical(ops, monkeypatch, M, N, K):
+    """T4R_GEMM_TMA_STORE=1: the planes-only dense epilogue of the CTA-pair GEMM (the Q|K|V projection) hands its output
+    to the TMA unit from 64B-swizzled shared-memory boxes instead of storing per lane.  Same values, so the planes must
+    be BIT-identical to the staged-store epilogue's, incl. partial row blocks (M % 32 != 0: clipped by the TMA unit),
+    with bias + GELU in front, and nothing may be written outside the output."""
+    from transformers4rec_b200 import _lib
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.1
+    b = torch.randn(N, device="cuda")
+    xp, wp = ops.split_planes(x), ops.split_planes(w)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("T4R_GEMM_TMA_STORE", flag)
+        _, p1, _ = ops.linear(xp, wp, K, want_f32=False, want_planes=True)
+        _, p2, _ = ops.linear(xp, wp, K, bias=b, act=_lib.ACT_GELU, want_f32=False, want_planes=True)
+        torch.cuda.synchronize()
+        outs[flag] = (p1.clone(), p2.clone())
+    for a, c in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, c)
+    ref = x.double() @ w.double().t()
+    got = outs["1"][0][0].double() + outs["1"][0][1].double()
+    assert (got[:, :N] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_forward_replayed_from_a_cuda_graph():
     """Model.graphed: the forward-only pass captured once and replayed -- same loss and label ranks as the eager call on
     the same draws, new inputs take effect through the captured buffers, a shape change is refused."""

@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "t4r_common.cuh"
@@ -116,6 +117,9 @@ int make_tmap_public(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, 
 // kernel
 // ----------------------------------------------------------------------------
 constexpr int BM = 128;
+#ifndef T4R_GEMM_TMA_STORE_DEFAULT
+#define T4R_GEMM_TMA_STORE_DEFAULT 0
+#endif
 #ifndef T4R_FFN_EPW_DEFAULT
 #define T4R_FFN_EPW_DEFAULT 8
 #endif
@@ -581,6 +585,53 @@ __device__ __forceinline__ void epilogue_dense(const GemmDev& p, uint32_t taddr,
   }
 }
 
+// Dense epilogue with TMA STORES (planes-only outputs, no residual / LayerNorm / mask: the Q|K|V projection, whose
+// 126 MB of plane stores per call bound it).  Each thread splits its row's 32-column chunk to bf16 hi / lo and writes
+// the two 64-byte row pieces into a 64B-swizzled [32 rows x 64 B] shared-memory box per plane (16-byte chunk j of row
+// r sits at chunk j ^ ((r >> 1) & 3): the layout CU_TENSOR_MAP_SWIZZLE_64B expects, and conflict-free for one row per
+// lane); one lane then issues two cp.async.bulk.tensor stores.  No row <-> column transposition through a staging
+// tile, no per-lane global store instructions, and the stores drain asynchronously while the next chunk is computed
+// (two boxes per warp, `cp.async.bulk.wait_group.read 1` before a box is rewritten).  Rows / columns outside the
+// tensor are clipped by the TMA unit.
+template <int BN>
+__device__ __forceinline__ void epilogue_dense_tma(const GemmDev& p, uint32_t taddr, int64_t row0, int lane, int64_t n0,
+                                                   uint8_t* boxes, uint32_t& nstores, const CUtensorMap* tm_hi,
+                                                   const CUtensorMap* tm_lo) {
+  constexpr int COLS = BN / 2;
+  const GemmEpilogue& ep = p.ep;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll 1
+  for (int c = 0; c < COLS / 32; ++c) {
+    float v[32];
+    tmem_ld<32>(taddr + c * 32, v);
+    const int64_t ncol0 = n0 + c * 32;
+    if (ncol0 >= p.N) continue;   // warp-uniform
+    dense_chunk(v, ep, ncol0, 0);
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+    uint8_t* box = boxes + (nstores & 1u) * 4096u;
+    if (nstores >= 2) {
+      if (lane == 0) tma_store_wait_read<1>();   // the stores issued from this box two chunks ago have read it
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int off = lane * 64 + ((j ^ sw) << 4);
+      *reinterpret_cast<uint4*>(box + off) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      *reinterpret_cast<uint4*>(box + 2048 + off) = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm_hi, box, static_cast<int>(ncol0), static_cast<int>(row0));
+      tma_store_2d(tm_lo, box + 2048, static_cast<int>(ncol0), static_cast<int>(row0));
+      tma_store_commit();
+    }
+    ++nstores;
+  }
+}
+
 // head epilogue: per row, online log-sum-exp (base 2) over this thread's COLS classes
 // of the tile, optional logQ bias / accidental-hit removal (sampled softmax), rank count.
 template <int BN>
@@ -916,12 +967,26 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4096 + 8 * 32 * 20 * 4;
 };
 
-template <int BN, bool LN, bool HEAD>
+// TMA-store variant of the configuration: two ring stages (these GEMMs are epilogue-bound) and, instead of the
+// per-warp staging tiles, two 4 KB store boxes per epilogue warp (1024-byte aligned).
+template <int BN>
+struct Gemm2CfgTma {
+  static constexpr int A_PLANE_BYTES = Gemm2Cfg<BN>::A_PLANE_BYTES;
+  static constexpr int B_PLANE_BYTES = Gemm2Cfg<BN>::B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = Gemm2Cfg<BN>::STAGE_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BOX_BYTES = 8 * 2 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers, keeps the boxes aligned*/ + BOX_BYTES;
+};
+
+template <int BN, bool LN, bool HEAD, bool TMAOUT = false>
 __global__ void __launch_bounds__(320, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                    const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
                     const GemmDev p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = typename std::conditional<TMAOUT, Gemm2CfgTma<BN>, Gemm2Cfg<BN>>::type;
   constexpr int A_PLANE_BYTES = Cfg::A_PLANE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -932,6 +997,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* xch = reinterpret_cast<float2*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
   float* stg_all = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + 4096);
+  uint8_t* box_all = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 1024;   // TMAOUT: [8 warps][2 boxes][hi 2 KB | lo 2 KB]
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -1063,6 +1129,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     int as = 0;
     uint32_t aph = 0;
     uint32_t tile_parity = 0;
+    uint32_t nstores = 0;   // TMAOUT: chunks this warp has handed to the TMA unit (selects the box, paces its reuse)
     for (int64_t tile = pair; tile < num_tiles; tile += npairs) {
       const int tile_n = static_cast<int>(tile / tiles_m);
       const int64_t m0 = static_cast<int64_t>(tile % tiles_m) * (2 * BM) + rank * BM;
@@ -1076,6 +1143,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       const bool row_ok = row < M_eff;
       if (HEAD) {
         epilogue_head<BN>(p, taddr, row, row_ok, n0, tile_n * 2 + half);
+      } else if constexpr (TMAOUT) {
+        if (row0 < M_eff)   // warp-uniform; a block of rows wholly beyond M is not stored (partial blocks: TMA clips)
+          epilogue_dense_tma<BN>(p, taddr, row0, lane, n0, box_all + (warp - 2) * 8192, nstores, &tmOh, &tmOl);
       } else {
         float2* xg0 = xch + (tile_parity * 2) * 128 + quad * 32 + lane;   // [parity][group][row]
         const int64_t left = static_cast<int64_t>(M_eff) - row0;
@@ -1091,6 +1161,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     }
   }
 
+  if constexpr (TMAOUT) {
+    if (warp >= 2 && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the stores that read it
+  }
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // no CTA tears down its barriers / TMEM while the peer may still signal or read them
@@ -1549,11 +1622,14 @@ static int launch_inst(const CUtensorMap& ah, const CUtensorMap& al, const CUten
 }
 
 
-template <int BN, bool LN, bool HEAD>
+template <int BN, bool LN, bool HEAD, bool TMAOUT = false>
 static int launch_inst2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                        const GemmDev& dp, int64_t max_pair_tiles, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm2_bf16x3_kernel<BN, LN, HEAD>;
+                        const GemmDev& dp, int64_t max_pair_tiles, cudaStream_t stream,
+                        const CUtensorMap* oh = nullptr, const CUtensorMap* ol = nullptr) {
+  using Cfg = typename std::conditional<TMAOUT, Gemm2CfgTma<BN>, Gemm2Cfg<BN>>::type;
+  auto kern = gemm2_bf16x3_kernel<BN, LN, HEAD, TMAOUT>;
+  const CUtensorMap& toh = oh ? *oh : ah;   // unused unless TMAOUT
+  const CUtensorMap& tol = ol ? *ol : al;
   static bool attr_set = false;
   if (!attr_set) {
     T4R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1574,7 +1650,7 @@ static int launch_inst2(const CUtensorMap& ah, const CUtensorMap& al, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  T4R_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dp));
+  T4R_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, toh, tol, dp));
   T4R_LAUNCH_CHECK("gemm2_bf16x3_kernel");
   return 0;
 }
@@ -1711,6 +1787,17 @@ int launch_gemm(const GemmProblem& pb, const GemmEpilogue& ep, cudaStream_t stre
       if (bn == 256) return launch_inst2<256, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
       if (bn == 128) return launch_inst2<128, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
       return launch_inst2<64, true, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
+    }
+    // planes-only dense output (the Q|K|V projection): TMA stores instead of per-lane global stores (T4R_GEMM_TMA_STORE)
+    int tma_store = T4R_GEMM_TMA_STORE_DEFAULT;
+    if (const char* e = getenv("T4R_GEMM_TMA_STORE")) tma_store = atoi(e);
+    if (tma_store && bn == 256 && ep.out_planes && !ep.out_f32 && !ep.out_pre && !ep.residual && !ep.residual_planes &&
+        !ep.row_code && !ep.col_scale && pb.m_dev == nullptr && pb.N % 32 == 0 && ep.ldpl % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(ep.out_planes) & 15) == 0 && (ep.plane_stride * 2) % 16 == 0 && dp.ep.debug == 0) {
+      CUtensorMap oh, ol;
+      T4R_TRY(make_tmap(&oh, ep.out_planes, pb.M, ep.ldpl, 32, 64));
+      T4R_TRY(make_tmap(&ol, ep.out_planes + ep.plane_stride, pb.M, ep.ldpl, 32, 64));
+      return launch_inst2<256, false, false, true>(ah, al, bh2, bl2, dp, pair_tiles, stream, &oh, &ol);
     }
     if (bn == 256) return launch_inst2<256, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
     if (bn == 128) return launch_inst2<128, false, false>(ah, al, bh2, bl2, dp, pair_tiles, stream);
